@@ -1,0 +1,201 @@
+"""Smoothed-aggregation AMG (oracle; test infrastructure only).
+
+The reference's inner solves of the Schur-complement sweeps are hypre BoomerAMG, two
+V-cycles from a zero guess, set up from scratch at every time step of every
+preconditioner application (control/control.py:2056-2067, 2098-2109, 2139-2150,
+2172-2183 CN; 2242-2252 ... 2421-2431 BE).  hypre is a third-party dependency that is
+not in /root/reference and cannot be installed here, and a classical C/F AMG cannot be
+reproduced by an aggregation AMG, so this module does NOT restate BoomerAMG: it defines
+the deterministic smoothed-aggregation hierarchy and V-cycle that ``control_b200``
+implements in C++ (setup, host) and CUDA (cycle), and is the oracle for THAT algorithm.
+Parity of the AMG with hypre is unpinned (DESIGN.md section "AMG").
+
+Algorithm (identical, step for step, in control_b200/csrc/amg_setup.cpp):
+  strength   |a_ij|^2 >= theta^2 |a_ii a_jj|, j != i
+  aggregate  three greedy passes in natural order (root + strong neighbours; join the
+             aggregate of the strongest already-aggregated strong neighbour; leftovers);
+             rows without strong neighbours (e.g. Dirichlet identity rows) stay out
+  prolong    P = (I - omega D^-1 A) T,  T_iJ = |agg_J|^-1/2,
+             omega = 4 / (3 rho),  rho = max_i sum_j |a_ij| / |a_ii|  (Gershgorin)
+  coarse     A_c = P^T A P; stop at n <= coarse_max (dense inverse) or max_levels
+  smoother   Chebyshev (oracle/cheb.py) of degree nu on D^-1 A over [lo*rho, hi*rho]
+  cycle      V(nu, nu); ``solve`` = ``cycles`` V-cycles from a zero guess
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from .cheb import chebyshev
+
+try:                                       # the loops below are plain Python; numba only
+    import numba                           # makes large oracle runs (CPU baseline) bearable
+    _jit = numba.njit(cache=True)
+except Exception:                          # pragma: no cover
+    def _jit(f):
+        return f
+
+
+DEFAULTS = dict(theta=0.08, max_levels=10, coarse_max=200, nu=2, lo=0.25, hi=1.0, cycles=2)
+
+
+@_jit
+def _aggregate(n, indptr, indices, data, theta):
+    diag = np.zeros(n)
+    for i in range(n):
+        for k in range(indptr[i], indptr[i + 1]):
+            if indices[k] == i:
+                diag[i] = data[k]
+    strong = np.zeros(indices.shape[0], dtype=np.bool_)
+    th2 = theta * theta
+    for i in range(n):
+        for k in range(indptr[i], indptr[i + 1]):
+            j = indices[k]
+            if j != i:
+                a = data[k]
+                if a != 0.0 and a * a >= th2 * abs(diag[i] * diag[j]):
+                    strong[k] = True
+    agg = np.full(n, -1, dtype=np.int64)
+    n_agg = 0
+    # pass 1: a node whose strong neighbourhood is entirely free roots an aggregate
+    for i in range(n):
+        if agg[i] != -1:
+            continue
+        has_nbr = False
+        free = True
+        for k in range(indptr[i], indptr[i + 1]):
+            if strong[k]:
+                has_nbr = True
+                if agg[indices[k]] != -1:
+                    free = False
+                    break
+        if has_nbr and free:
+            agg[i] = n_agg
+            for k in range(indptr[i], indptr[i + 1]):
+                if strong[k]:
+                    agg[indices[k]] = n_agg
+            n_agg += 1
+    # pass 2: join the aggregate of the strongest strong neighbour aggregated in pass 1
+    agg1 = agg.copy()
+    for i in range(n):
+        if agg1[i] != -1:
+            continue
+        best = -1
+        best_val = -1.0
+        for k in range(indptr[i], indptr[i + 1]):
+            if strong[k] and agg1[indices[k]] != -1:
+                a = abs(data[k])
+                if a > best_val:
+                    best_val = a
+                    best = agg1[indices[k]]
+        if best != -1:
+            agg[i] = best
+    # pass 3: leftovers with strong neighbours form new aggregates among themselves
+    for i in range(n):
+        if agg[i] != -1:
+            continue
+        has_nbr = False
+        for k in range(indptr[i], indptr[i + 1]):
+            if strong[k]:
+                has_nbr = True
+                break
+        if not has_nbr:
+            continue
+        agg[i] = n_agg
+        for k in range(indptr[i], indptr[i + 1]):
+            if strong[k] and agg[indices[k]] == -1:
+                agg[indices[k]] = n_agg
+        n_agg += 1
+    return agg, n_agg
+
+
+def aggregate(A, theta):
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    agg, n_agg = _aggregate(A.shape[0], A.indptr.astype(np.int64), A.indices.astype(np.int64),
+                            A.data.astype(np.float64), float(theta))
+    return np.asarray(agg), int(n_agg)
+
+
+def gershgorin_rho(A):
+    A = sp.csr_matrix(A)
+    d = np.abs(A.diagonal())
+    rowsum = np.asarray(abs(A).sum(axis=1)).ravel()
+    return float(np.max(rowsum / d))
+
+
+class Level:
+    __slots__ = ("A", "dinv", "rho", "P", "R", "agg", "Ainv")
+
+
+class Hierarchy:
+    def __init__(self, levels, params):
+        self.levels = levels
+        self.params = params
+
+    def sizes(self):
+        return [(L.A.shape[0], L.A.nnz) for L in self.levels]
+
+
+def setup(A, **kw):
+    params = dict(DEFAULTS)
+    params.update(kw)
+    levels = []
+    A = sp.csr_matrix(A).astype(np.float64)
+    A.sort_indices()
+    while True:
+        L = Level()
+        L.A = A
+        d = A.diagonal()
+        L.dinv = 1.0 / d
+        L.rho = gershgorin_rho(A)
+        L.P = L.R = L.agg = L.Ainv = None
+        levels.append(L)
+        n = A.shape[0]
+        if n <= params["coarse_max"] or len(levels) >= params["max_levels"]:
+            break
+        agg, n_agg = aggregate(A, params["theta"])
+        if n_agg == 0 or n_agg >= 0.9 * n:
+            break
+        L.agg = agg
+        sizes = np.bincount(agg[agg >= 0], minlength=n_agg).astype(np.float64)
+        rows = np.flatnonzero(agg >= 0)
+        T = sp.csr_matrix((1.0 / np.sqrt(sizes[agg[rows]]), (rows, agg[rows])), shape=(n, n_agg))
+        omega = 4.0 / (3.0 * L.rho)
+        Az = A.copy()
+        Az.eliminate_zeros()
+        P = (T - sp.diags(omega * L.dinv) @ (Az @ T)).tocsr()
+        P.sort_indices()
+        L.P = P
+        L.R = P.T.tocsr()
+        L.R.sort_indices()
+        A = (L.R @ (A @ P)).tocsr()
+        A.sort_indices()
+    last = levels[-1]
+    if last.A.shape[0] <= 4096:
+        last.Ainv = np.linalg.inv(last.A.toarray())
+    return Hierarchy(levels, params)
+
+
+def vcycle(H, lvl, b, x=None):
+    """One V(nu, nu) cycle on level ``lvl``; ``x`` None means zero initial guess."""
+    L = H.levels[lvl]
+    p = H.params
+    if lvl == len(H.levels) - 1:
+        if L.Ainv is not None:
+            return L.Ainv @ b
+        return chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
+    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
+    r = b - L.A @ x
+    xc = vcycle(H, lvl + 1, L.R @ r, None)
+    x = x + L.P @ xc
+    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
+    return x
+
+
+def solve(H, b, cycles=None):
+    """``cycles`` V-cycles from a zero guess (the stand-in for
+    ``pc_hypre_boomeramg_max_iter``: 2, control/control.py:2065)."""
+    cycles = H.params["cycles"] if cycles is None else cycles
+    x = None
+    for _ in range(cycles):
+        x = vcycle(H, 0, b, x)
+    return x

@@ -1,0 +1,153 @@
+"""``MultiBlockSystem.solve`` and ``Control.Instationary.linear_solve`` (oracle; test
+infrastructure only), restated on spatial matrices instead of UFL forms.
+
+  * ``system_solve``  preconditioner/preconditioner.py:337-786
+  * ``linear_solve``  control/control.py:2820-3375 (numerics only; no output / plots)
+  * ``objective``     the discrete objective defined in SURVEY.md section 8c
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import kkt, krylov
+from .pc import construct_pc, construct_pc_diagonal
+
+DEFAULT_SOLVER_PARAMETERS = {"linear_solver": "gmres",        # control/control.py:3260-3266
+                             "gmres_restart": 10,
+                             "maximum_iterations": 50,
+                             "relative_tolerance": 1.0e-6,
+                             "absolute_tolerance": 0.0}
+
+
+def system_solve(apply_A, nullspace, u_0, u_1, b_0, b_1, *, solver_parameters, pc_fn=None):
+    """``MultiBlockSystem.solve``.  ``apply_A(x0, x1) -> (y0, y1)`` is the operator
+    (already including the nullspace handling of ``mult``); ``pc_fn(b_0, b_1) ->
+    (u_0, u_1)``.  Returns (u_0, u_1, KSPResult)."""
+    N, n = b_0.shape
+    if pc_fn is None:
+        def pc_fn(b_0, b_1):
+            return b_0.copy(), b_1.copy()
+
+    def pack(a0, a1):
+        return np.concatenate([a0.ravel(), a1.ravel()])
+
+    def unpack(x):
+        return x[:N * n].reshape(N, n).copy(), x[N * n:].reshape(N, n).copy()
+
+    def A(x):
+        y0, y1 = apply_A(*unpack(x))
+        return pack(y0, y1)
+
+    def P(x):
+        # Preconditioner.apply: preconditioner/preconditioner.py:562-656
+        b0, b1 = unpack(x)
+        b0c = nullspace.pc_pre_mult_corrected(b0)
+        b1c = nullspace.pc_pre_mult_corrected(b1)
+        v0, v1 = pc_fn(b0c, b1c)
+        v0 = v0.copy()
+        v1 = v1.copy()
+        nullspace.pc_post_mult_correct(v0, b0)
+        nullspace.pc_post_mult_correct(v1, b1)
+        return pack(v0, v1)
+
+    u0 = u_0.copy()
+    u1 = u_1.copy()
+    nullspace.project(u0)              # correct_soln, 658-678
+    nullspace.project(u1)
+    c0 = b_0.copy()
+    c1 = b_1.copy()
+    nullspace.project(c0)              # correct_rhs, 680-704
+    nullspace.project(c1)
+
+    sp_ = solver_parameters
+    ksp_type = sp_.get("linear_solver", "fgmres")
+    kw = dict(rtol=sp_["relative_tolerance"], atol=sp_["absolute_tolerance"],
+              max_it=sp_.get("maximum_iterations", 1000))
+    if sp_.get("divergence limit") is not None:
+        kw["divtol"] = sp_["divergence limit"]
+    monitor = sp_.get("monitor")
+    if ksp_type in ("gmres", "fgmres"):
+        x, res = krylov.gmres(A, pack(c0, c1), pack(u0, u1), pc=P,
+                              flexible=(ksp_type == "fgmres"),
+                              restart=sp_.get("gmres_restart", 30), monitor=monitor, **kw)
+    elif ksp_type == "minres":
+        x, res = krylov.minres(A, pack(c0, c1), pack(u0, u1), pc=P, monitor=monitor, **kw)
+    else:
+        raise ValueError(f"unsupported linear_solver {ksp_type!r}")
+    u0, u1 = unpack(x)
+    nullspace.project(u0)              # 761-766
+    nullspace.project(u1)
+    if not sp_.get("preconditioner", False) and res.reason <= 0:
+        raise RuntimeError("Solver failed to converge")         # 768-770
+    return u0, u1, res
+
+
+def linear_solve(M, K_levels, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs,
+                 v_d=None, f=None, v_0=None, check_v_d=True, check_f=True,
+                 P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
+                 inner="amg", amg_params=None, pc_mode="triangular", literal=False):
+    """``Instationary.linear_solve`` on assembled matrices.  Returns a dict with the
+    unpacked n_t-level ``v``/``zeta``, the raw block solution and the KSP result."""
+    t_0, T_f = time_interval
+    tau = (T_f - t_0) / (n_t - 1.0)
+    n = M.shape[0]
+    if v_0 is None:
+        v_0 = np.zeros(n)
+    if sp.issparse(K_levels):
+        K_list = [K_levels] * n_t
+    else:
+        K_list = list(K_levels)
+    nullspace = kkt.DirichletBCNullspace(bdofs)
+    b_0, b_1 = kkt.build_rhs(M, K_list, tau, n_t, CN, bdofs, v_d, f, v_0,
+                             check_v_d=check_v_d, check_f=check_f)
+    if literal:
+        blocks = kkt.build_blocks(M, K_list, tau, beta, n_t, CN)
+
+        def apply_A(x0, x1):
+            return kkt.kkt_apply_literal(blocks, nullspace, CN, x0, x1)
+    else:
+        def apply_A(x0, x1):
+            return kkt.kkt_apply_fused(M, K_list, tau, beta, n_t, CN, bdofs, x0, x1)
+    if P is None:
+        if pc_mode == "triangular":
+            pc_fn = construct_pc(M, K_list, tau, beta, n_t, CN, bdofs,
+                                 lambda_v_bounds=lambda_v_bounds, Multigrid=Multigrid,
+                                 inner=inner, amg_params=amg_params)
+        elif pc_mode == "diagonal":
+            assert CN
+            pc_fn = construct_pc_diagonal(M, K_list[0], tau, beta, n_t, bdofs,
+                                          lambda_v_bounds=lambda_v_bounds, inner=inner,
+                                          amg_params=amg_params)
+        else:
+            raise ValueError(pc_mode)
+    else:
+        pc_fn = P
+    if solver_parameters is None:
+        solver_parameters = dict(DEFAULT_SOLVER_PARAMETERS)
+    N = kkt.n_blocks(n_t, CN)
+    v, zeta, res = system_solve(apply_A, nullspace, np.zeros((N, n)), np.zeros((N, n)),
+                                b_0, b_1, solver_parameters=solver_parameters, pc_fn=pc_fn)
+    y0, y1 = apply_A(v, zeta)
+    c0, c1 = b_0.copy(), b_1.copy()
+    nullspace.project(c0)
+    nullspace.project(c1)
+    kkt_res = np.sqrt(np.linalg.norm(c0 - y0) ** 2 + np.linalg.norm(c1 - y1) ** 2)
+    v_full, zeta_full = kkt.unpack_solution(v, zeta, n_t, CN,
+                                            v_0 if (check_f and check_v_d) else None)
+    return dict(v=v_full, zeta=zeta_full, v_blocks=v, zeta_blocks=zeta, ksp=res,
+                kkt_residual=kkt_res, b_0=b_0, b_1=b_1, tau=tau, pc_fn=pc_fn)
+
+
+def objective(M, v, zeta, v_hat, tau, beta, CN):
+    """J_h = 1/2 sum_i w_i (v_i - vhat_i)^T M (v_i - vhat_i) + 1/(2 beta) sum_i w_i
+    zeta_i^T M zeta_i over the n_t levels, trapezoid weights for CN, tau for BE (SURVEY.md
+    section 8c; the reference never evaluates J, control/control.py:1876-1885)."""
+    n_t = v.shape[0]
+    w = np.full(n_t, tau)
+    if CN:
+        w[0] = w[-1] = 0.5 * tau
+    d = v - v_hat
+    J = 0.0
+    for i in range(n_t):
+        J += 0.5 * w[i] * float(d[i] @ (M @ d[i]))
+        J += 0.5 / beta * w[i] * float(zeta[i] @ (M @ zeta[i]))
+    return J

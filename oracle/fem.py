@@ -1,0 +1,177 @@
+"""Structured-mesh finite-element assemblers (oracle; test infrastructure only).
+
+Stand-ins for ``assemble(inner(trial, test) * dx)`` (mass ``M``, control/control.py:1562)
+and ``assemble(forward_form)`` for the Laplacian ``inner(grad(trial), grad(test)) * dx``
+(stiffness ``K``, e.g. test/test_control.py:1251-1253) on the meshes BASELINE.md names.
+Dof numbering is lexicographic (x fastest).  ``M`` and ``K`` always share one sparsity
+pattern (structural zeros of ``K`` are kept) and have sorted column indices.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+
+def _csr_same_pattern(n, rows, cols, vals_list):
+    """Assemble several COO value sets over the same (rows, cols) into CSR matrices that
+    share indptr/indices exactly (explicit zeros kept)."""
+    order = np.lexsort((cols, rows))
+    rows = rows[order]
+    cols = cols[order]
+    key_change = np.empty(rows.size, dtype=bool)
+    key_change[0] = True
+    key_change[1:] = (rows[1:] != rows[:-1]) | (cols[1:] != cols[:-1])
+    starts = np.flatnonzero(key_change)
+    u_rows = rows[starts]
+    u_cols = cols[starts].astype(np.int32)
+    indptr = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(indptr, u_rows + 1, 1)
+    indptr = np.cumsum(indptr).astype(np.int32)
+    out = []
+    for vals in vals_list:
+        data = np.add.reduceat(vals[order], starts)
+        out.append(sp.csr_matrix((data, u_cols.copy(), indptr.copy()), shape=(n, n)))
+    return out
+
+
+def p1_triangle_mesh(nx, ny, lx=1.0, ly=1.0):
+    """Vertices and triangles of an nx-by-ny rectangle mesh, each cell split by the
+    diagonal joining its lower-right and upper-left corners."""
+    xs = np.linspace(0.0, lx, nx + 1)
+    ys = np.linspace(0.0, ly, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords = np.stack([X.ravel(), Y.ravel()], axis=1)
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    v00 = (j * (nx + 1) + i).ravel()
+    v10 = v00 + 1
+    v01 = v00 + (nx + 1)
+    v11 = v01 + 1
+    tris = np.concatenate([np.stack([v00, v10, v01], axis=1),
+                           np.stack([v10, v11, v01], axis=1)], axis=0)
+    return coords, tris
+
+
+def assemble_p1_2d(nx, ny, lx=1.0, ly=1.0):
+    """P1 mass and Laplacian stiffness on triangles.  Returns (M, K, coords, bdofs)."""
+    coords, tris = p1_triangle_mesh(nx, ny, lx, ly)
+    n = coords.shape[0]
+    p = coords[tris]                      # (nt, 3, 2)
+    e1 = p[:, 1] - p[:, 0]
+    e2 = p[:, 2] - p[:, 0]
+    det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.abs(det)
+    # gradients of the barycentric basis functions
+    g = np.empty((tris.shape[0], 3, 2))
+    g[:, 1, 0] = e2[:, 1] / det
+    g[:, 1, 1] = -e2[:, 0] / det
+    g[:, 2, 0] = -e1[:, 1] / det
+    g[:, 2, 1] = e1[:, 0] / det
+    g[:, 0] = -g[:, 1] - g[:, 2]
+    Ke = area[:, None, None] * np.einsum("tad,tbd->tab", g, g)
+    Me = area[:, None, None] / 12.0 * (np.ones((3, 3)) + np.eye(3))[None]
+    rows = np.repeat(tris, 3, axis=1).ravel()
+    cols = np.tile(tris, (1, 3)).ravel()
+    M, K = _csr_same_pattern(n, rows, cols, [Me.ravel(), Ke.ravel()])
+    x, y = coords[:, 0], coords[:, 1]
+    tol = 1e-12 * max(lx, ly)
+    bd = np.flatnonzero((x < tol) | (x > lx - tol) | (y < tol) | (y > ly - tol))
+    return M, K, coords, bd.astype(np.int32)
+
+
+def _p2_1d(nel, length):
+    """1-D P2 mass/stiffness on a uniform mesh, nodes ordered left to right."""
+    h = length / nel
+    Me = h / 30.0 * np.array([[4.0, 2.0, -1.0], [2.0, 16.0, 2.0], [-1.0, 2.0, 4.0]])
+    Ke = 1.0 / (3.0 * h) * np.array([[7.0, -8.0, 1.0], [-8.0, 16.0, -8.0], [1.0, -8.0, 7.0]])
+    n = 2 * nel + 1
+    M = sp.lil_matrix((n, n))
+    K = sp.lil_matrix((n, n))
+    for e in range(nel):
+        idx = np.arange(2 * e, 2 * e + 3)
+        M[np.ix_(idx, idx)] += Me
+        K[np.ix_(idx, idx)] += Ke
+    return M.tocsr(), K.tocsr()
+
+
+def assemble_q2_2d(nx, ny, lx=1.0, ly=1.0):
+    """Q2 (tensor-product biquadratic) mass and Laplacian stiffness on a uniform
+    quadrilateral mesh: the element of the reference's instationary known-answer tests
+    (test/test_control.py:1245-1247).  Returns (M, K, coords, bdofs)."""
+    Mx, Kx = _p2_1d(nx, lx)
+    My, Ky = _p2_1d(ny, ly)
+    # the 1-D factors share one pattern, so every Kronecker product below has the same
+    # (row, col) list; sum the value sets over it (scipy's "+" would prune exact zeros)
+    MM = sp.kron(My, Mx, format="coo")
+    KM = sp.kron(My, Kx, format="coo")
+    MK = sp.kron(Ky, Mx, format="coo")
+    n = MM.shape[0]
+    rows = np.concatenate([MM.row, KM.row, MK.row]).astype(np.int64)
+    cols = np.concatenate([MM.col, KM.col, MK.col]).astype(np.int64)
+    zM = np.zeros(KM.nnz + MK.nnz)
+    M, K = _csr_same_pattern(
+        n, rows, cols,
+        [np.concatenate([MM.data, zM]),
+         np.concatenate([np.zeros(MM.nnz), KM.data, MK.data])])
+    xs = np.linspace(0.0, lx, 2 * nx + 1)
+    ys = np.linspace(0.0, ly, 2 * ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords = np.stack([X.ravel(), Y.ravel()], axis=1)
+    x, y = coords[:, 0], coords[:, 1]
+    tol = 1e-12 * max(lx, ly)
+    bd = np.flatnonzero((x < tol) | (x > lx - tol) | (y < tol) | (y > ly - tol))
+    return M, K, coords, bd.astype(np.int32)
+
+
+def assemble_p1_3d(nx, ny, nz, lx=1.0, ly=1.0, lz=1.0):
+    """P1 mass and Laplacian stiffness on tetrahedra (each cube split into six Kuhn
+    tetrahedra sharing the main diagonal).  Returns (M, K, coords, bdofs)."""
+    xs = np.linspace(0.0, lx, nx + 1)
+    ys = np.linspace(0.0, ly, ny + 1)
+    zs = np.linspace(0.0, lz, nz + 1)
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    coords = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    n = coords.shape[0]
+    sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    base = (k * sz + j * sy + i).ravel()
+    import itertools
+    tets = []
+    for perm in itertools.permutations((sx, sy, sz)):
+        a = base
+        b = a + perm[0]
+        c = b + perm[1]
+        d = c + perm[2]
+        tets.append(np.stack([a, b, c, d], axis=1))
+    tets = np.concatenate(tets, axis=0)
+    p = coords[tets]                     # (nt, 4, 3)
+    J = np.stack([p[:, 1] - p[:, 0], p[:, 2] - p[:, 0], p[:, 3] - p[:, 0]], axis=1)  # rows = edges
+    det = np.linalg.det(J)
+    vol = np.abs(det) / 6.0
+    Jinv = np.linalg.inv(J)              # columns of Jinv = gradients of lambda_1..3
+    g = np.empty((tets.shape[0], 4, 3))
+    g[:, 1:] = np.transpose(Jinv, (0, 2, 1))
+    g[:, 0] = -g[:, 1] - g[:, 2] - g[:, 3]
+    Ke = vol[:, None, None] * np.einsum("tad,tbd->tab", g, g)
+    Me = vol[:, None, None] / 20.0 * (np.ones((4, 4)) + np.eye(4))[None]
+    rows = np.repeat(tets, 4, axis=1).ravel()
+    cols = np.tile(tets, (1, 4)).ravel()
+    M, K = _csr_same_pattern(n, rows, cols, [Me.ravel(), Ke.ravel()])
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    tol = 1e-12 * max(lx, ly, lz)
+    bd = np.flatnonzero((x < tol) | (x > lx - tol) | (y < tol) | (y > ly - tol)
+                        | (z < tol) | (z > lz - tol))
+    return M, K, coords, bd.astype(np.int32)
+
+
+def assemble_bc(A, bdofs):
+    """``assemble(a, bcs=...)``: zero constrained rows and columns, unit diagonal
+    (Firedrake convention relied on at control/control.py:1971-1972, 2057-2059).
+    The sparsity pattern of ``A`` is kept (zeros stay as explicit entries)."""
+    A = A.tocsr().copy()
+    n = A.shape[0]
+    mask = np.zeros(n, dtype=bool)
+    mask[bdofs] = True
+    row_of = np.repeat(np.arange(n), np.diff(A.indptr))
+    kill = mask[row_of] | mask[A.indices]
+    A.data[kill] = 0.0
+    diag = (row_of == A.indices) & mask[row_of]
+    A.data[diag] = 1.0
+    return A

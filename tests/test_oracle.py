@@ -1,0 +1,284 @@
+"""CPU tests that pin the oracle (oracle/) before anything is checked against it.
+
+The two instationary known-answer tests of the reference (test/test_control.py:1243-1444,
+1447-1655) are re-created in tests/kat.py; the oracle must reproduce their analytic
+solutions through the literal block-by-block operator AND through the fused form the CUDA
+kernel implements.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import kat
+from oracle import amg, cheb, control, fem, kkt, krylov
+
+
+# ---------------------------------------------------------------- assemblers
+def test_p1_2d_counts_match_baseline_config_c1():
+    M, K, coords, bd = fem.assemble_p1_2d(10, 10, 2.0, 2.0)
+    assert M.shape == (121, 121) and M.nnz == 761 and K.nnz == 761
+    assert np.array_equal(M.indptr, K.indptr) and np.array_equal(M.indices, K.indices)
+    assert M.indices.dtype == np.int32 and M.indptr.dtype == np.int32
+    assert len(bd) == 40
+    assert abs(M.sum() - 4.0) < 1e-13                      # area of (0,2)^2
+    assert np.abs(K @ np.ones(121)).max() < 1e-13          # constants in the kernel
+    assert np.abs((M - M.T)).max() < 1e-18 and np.abs((K - K.T)).max() < 1e-15
+    x = coords[:, 0]
+    assert abs(x @ (K @ x) - 4.0) < 1e-12                  # |grad x|^2 integrated
+
+
+def test_p1_2d_mass_spectrum_bounds():
+    # D^-1 M of P1 triangles has spectrum in [0.5, 2] (bounds used at test_control.py:1185)
+    M, _, _, _ = fem.assemble_p1_2d(6, 6)
+    d = M.diagonal()
+    ev = np.linalg.eigvalsh((M.toarray() / np.sqrt(d)[:, None]) / np.sqrt(d)[None, :])
+    assert ev.min() >= 0.5 - 1e-12 and ev.max() <= 2.0 + 1e-12
+
+
+def test_q2_and_p1_3d_basic_identities():
+    M, K, coords, bd = fem.assemble_q2_2d(4, 4)
+    assert M.shape[0] == 81 and np.array_equal(M.indices, K.indices)
+    assert abs(M.sum() - 1.0) < 1e-13 and np.abs(K @ np.ones(81)).max() < 1e-12
+    d = M.diagonal()
+    ev = np.linalg.eigvalsh((M.toarray() / np.sqrt(d)[:, None]) / np.sqrt(d)[None, :])
+    assert ev.min() >= 0.25 - 1e-12 and ev.max() <= 1.5625 + 1e-12   # test_control.py:1416
+    M3, K3, c3, bd3 = fem.assemble_p1_3d(3, 3, 3)
+    assert M3.shape[0] == 64 and abs(M3.sum() - 1.0) < 1e-13
+    assert np.abs(K3 @ np.ones(64)).max() < 1e-12
+    z = c3[:, 2]
+    assert abs(z @ (K3 @ z) - 1.0) < 1e-12
+    assert len(bd3) == 64 - 8
+    M4, K4, _, _ = fem.assemble_p1_3d(6, 6, 6)
+    interior = np.diff(M4.indptr).max()
+    assert interior == 15                                   # 15-point Kuhn stencil
+
+
+def test_assemble_bc_identity_rows_and_cols():
+    M, K, _, bd = fem.assemble_p1_2d(5, 5)
+    A = fem.assemble_bc(K, bd).toarray()
+    assert np.array_equal(A[bd][:, bd], np.eye(len(bd)))
+    mask = np.ones(A.shape[0], bool)
+    mask[bd] = False
+    assert np.abs(A[bd][:, mask]).max() == 0 and np.abs(A[mask][:, bd]).max() == 0
+    assert np.allclose(A[mask][:, mask], K.toarray()[mask][:, mask])
+
+
+# ---------------------------------------------------------------- T transforms
+def test_T_transforms_and_inverses():
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((7, 5))
+    S = np.diag(np.ones(6), 1)
+    assert np.allclose(kkt.apply_T_1(x), (np.eye(7) + S) @ x)
+    assert np.allclose(kkt.apply_T_2(x), (np.eye(7) + S.T) @ x)
+    assert np.allclose(kkt.apply_T_1_inv(kkt.apply_T_1(x)), x)
+    assert np.allclose(kkt.apply_T_2_inv(kkt.apply_T_2(x)), x)
+    one = rng.standard_normal((1, 5))
+    assert np.array_equal(kkt.apply_T_1(one), one) and np.array_equal(kkt.apply_T_2_inv(one), one)
+
+
+# ---------------------------------------------------------------- operator
+@pytest.mark.parametrize("CN", [True, False])
+def test_block_counts(CN):
+    M, K, _, _ = fem.assemble_p1_2d(3, 3)
+    for n_t in (2, 3, 6):
+        blocks = kkt.build_blocks(M, K, 0.1, 1e-2, n_t, CN)
+        N = kkt.n_blocks(n_t, CN)
+        assert kkt.count_blocks(blocks) == (8 * N - 4 if CN else 6 * N - 4)
+
+
+@pytest.mark.parametrize("CN", [True, False])
+@pytest.mark.parametrize("time_dependent", [False, True])
+def test_fused_operator_equals_literal(CN, time_dependent):
+    M, K, _, bd = fem.assemble_p1_2d(6, 5, 2.0, 1.0)
+    n_t, tau, beta = 6, 0.2, 1e-3
+    rng = np.random.default_rng(3)
+    if time_dependent:            # non-symmetric, different per level, same pattern
+        K_levels = []
+        for i in range(n_t):
+            Ki = K.copy()
+            Ki.data = Ki.data * (1.0 + 0.3 * rng.standard_normal(Ki.nnz))
+            K_levels.append(Ki)
+    else:
+        K_levels = [K] * n_t
+    N = kkt.n_blocks(n_t, CN)
+    x0 = rng.standard_normal((N, M.shape[0]))
+    x1 = rng.standard_normal((N, M.shape[0]))
+    blocks = kkt.build_blocks(M, K_levels, tau, beta, n_t, CN)
+    ns = kkt.DirichletBCNullspace(bd)
+    yl = kkt.kkt_apply_literal(blocks, ns, CN, x0, x1)
+    yf = kkt.kkt_apply_fused(M, K_levels, tau, beta, n_t, CN, bd, x0, x1)
+    scale = max(np.abs(yl[0]).max(), np.abs(yl[1]).max())
+    assert np.abs(yl[0] - yf[0]).max() <= 1e-14 * scale
+    assert np.abs(yl[1] - yf[1]).max() <= 1e-14 * scale
+    assert np.array_equal(yf[0][:, bd], x0[:, bd]) and np.array_equal(yl[1][:, bd], x1[:, bd])
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_operator_symmetric_for_symmetric_K(CN):
+    M, K, _, bd = fem.assemble_p1_2d(4, 4)
+    n_t, tau, beta = 5, 0.25, 1e-2
+    N = kkt.n_blocks(n_t, CN)
+    n = M.shape[0]
+    dim = 2 * N * n
+    A = np.zeros((dim, dim))
+    for k in range(dim):
+        e = np.zeros(dim)
+        e[k] = 1.0
+        y0, y1 = kkt.kkt_apply_fused(M, K, tau, beta, n_t, CN, bd, e[:N * n].reshape(N, n),
+                                     e[N * n:].reshape(N, n))
+        A[:, k] = np.concatenate([y0.ravel(), y1.ravel()])
+    assert np.abs(A - A.T).max() < 1e-13 * np.abs(A).max()
+
+
+# ---------------------------------------------------------------- known-answer tests
+@pytest.mark.parametrize("CN", [False, True])
+@pytest.mark.parametrize("literal", [True, False])
+def test_reference_known_answer(CN, literal):
+    """test/test_control.py:1243-1444 (BE) and 1447-1655 (CN): the solve must return the
+    analytic v_ref / zeta_ref.  The reference asserts 1e-13 on each L2 error after FGMRES
+    to rtol = atol = 1e-14; the attainable error is a few ulps times the conditioning of
+    the system (beta = 1e-3), so 5e-13 is asserted here."""
+    p = kat.instationary_kat(CN)
+    out = control.linear_solve(p["M"], p["K"], beta=p["beta"], n_t=p["n_t"], CN=CN,
+                               bdofs=p["bdofs"], v_d=p["b_0"], f=p["b_1"], check_v_d=False,
+                               check_f=False, solver_parameters=p["solver_parameters"],
+                               lambda_v_bounds=p["lambda_v_bounds"], inner="exact",
+                               literal=literal)
+    assert out["ksp"].reason > 0
+    assert kat.l2_error(p["M"], out["v"], p["v_ref"]) < 5e-13
+    assert kat.l2_error(p["M"], out["zeta"], p["zeta_ref"]) < 5e-13
+
+
+@pytest.mark.parametrize("CN", [False, True])
+def test_known_answer_with_amg_inner_solves(CN):
+    p = kat.instationary_kat(CN)
+    out = control.linear_solve(p["M"], p["K"], beta=p["beta"], n_t=p["n_t"], CN=CN,
+                               bdofs=p["bdofs"], v_d=p["b_0"], f=p["b_1"], check_v_d=False,
+                               check_f=False, solver_parameters=p["solver_parameters"],
+                               lambda_v_bounds=p["lambda_v_bounds"], inner="amg")
+    assert kat.l2_error(p["M"], out["v"], p["v_ref"]) < 5e-13
+    assert kat.l2_error(p["M"], out["zeta"], p["zeta_ref"]) < 5e-13
+
+
+# ---------------------------------------------------------------- Chebyshev / AMG / Krylov
+def test_chebyshev_is_an_accurate_mass_inverse():
+    # 20 steps with the exact bounds reach ~4e-10 in the M-norm
+    M, _, _, bd = fem.assemble_p1_2d(20, 20)
+    Mb = fem.assemble_bc(M, bd)
+    rng = np.random.default_rng(0)
+    xs = rng.standard_normal(M.shape[0])
+    xs[bd] = 0.0
+    b = Mb @ xs
+    x = cheb.chebyshev(Mb, 1.0 / Mb.diagonal(), b, 0.5, 2.0, 20)
+    e = x - xs
+    assert np.sqrt(e @ (Mb @ e)) / np.sqrt(xs @ (Mb @ xs)) < 1e-9
+    assert np.all(x[bd] == 0.0)
+    # batched call == column by column
+    B = rng.standard_normal((M.shape[0], 3))
+    Xb = cheb.chebyshev(Mb, 1.0 / Mb.diagonal(), B, 0.5, 2.0, 20)
+    for k in range(3):
+        assert np.allclose(Xb[:, k], cheb.chebyshev(Mb, 1.0 / Mb.diagonal(), B[:, k], 0.5, 2.0, 20),
+                           rtol=1e-13, atol=1e-15)
+
+
+def test_amg_vcycle_contracts_and_is_symmetric():
+    M, K, _, bd = fem.assemble_p1_2d(48, 48, 2.0, 2.0)
+    tau, beta = 2.0 / 63, 1e-4
+    c = 0.5 * tau / beta ** 0.5
+    A = fem.assemble_bc((0.5 * tau * K + (1 + c) * M).tocsr(), bd)
+    H = amg.setup(A)
+    assert len(H.levels) >= 3 and H.levels[-1].Ainv is not None
+    rng = np.random.default_rng(0)
+    xs = rng.standard_normal(A.shape[0])
+    xs[bd] = 0.0
+    b = A @ xs
+    x = amg.solve(H, b)                                    # two V-cycles
+    assert np.linalg.norm(x - xs) / np.linalg.norm(xs) < 3e-2
+    # the two-cycle operator is symmetric (needed by the MINRES variant)
+    u, w = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    assert abs(u @ amg.solve(H, w) - w @ amg.solve(H, u)) < 1e-10 * abs(u @ amg.solve(H, w))
+    # aggregates: every interior row aggregated, Dirichlet identity rows left out
+    agg = H.levels[0].agg
+    assert np.all(agg[bd] == -1) and np.all(np.delete(agg, bd) >= 0)
+
+
+def test_krylov_methods_solve_small_systems():
+    rng = np.random.default_rng(0)
+    n = 40
+    Q = rng.standard_normal((n, n))
+    A = Q @ Q.T + n * np.eye(n)
+    A[:, :5] *= -1
+    A = 0.5 * (A + A.T) - 0.0
+    b = rng.standard_normal(n)
+    xs = np.linalg.solve(A, b)
+    d = np.abs(np.diag(A))
+    for flexible in (False, True):
+        x, res = krylov.gmres(lambda v: A @ v, b, np.zeros(n), pc=lambda v: v / d,
+                              flexible=flexible, restart=10, rtol=1e-12, atol=0.0, max_it=500)
+        assert res.reason == krylov.CONVERGED_RTOL and np.allclose(x, xs, atol=1e-8)
+        assert len(res.history) == res.its + 1
+    x, res = krylov.minres(lambda v: A @ v, b, np.zeros(n), pc=lambda v: v / d, rtol=1e-12,
+                           atol=0.0, max_it=500)
+    assert res.reason == krylov.CONVERGED_RTOL and np.allclose(x, xs, atol=1e-8)
+    x, res = krylov.gmres(lambda v: A @ v, b, np.zeros(n), restart=5, rtol=1e-30, atol=0.0, max_it=7)
+    assert res.reason == krylov.DIVERGED_ITS and res.its == 7
+
+
+# ---------------------------------------------------------------- preconditioner properties
+def test_ideal_cn_preconditioner_spectrum():
+    """with exact inner solves eig(P^-1 A) is real in [0.5, 1] for CN."""
+    q = kat.heat_problem(6, 5, True, beta=1e-2)
+    M, K, bd = q["M"], q["K"], q["bdofs"]
+    from oracle.pc import construct_pc
+    n_t, tau = q["n_t"], q["tau"]
+    N, n = n_t - 1, M.shape[0]
+    # exact M^-1 instead of Chebyshev/Jacobi for the (1,1) block
+    import scipy.sparse.linalg as spla
+    lu = spla.splu(sp.csc_matrix(fem.assemble_bc(M, bd)))
+    import oracle.pc as opc
+    free = np.setdiff1d(np.arange(n), bd)
+    dim = 2 * N * n
+    PA = np.zeros((dim, dim))
+    orig = opc.make_solver_0
+    opc.make_solver_0 = lambda *a, **k: (lambda B: np.stack([lu.solve(b) for b in B]))
+    try:
+        pc = construct_pc(M, K, tau, q["beta"], n_t, True, bd, inner="exact")
+    finally:
+        opc.make_solver_0 = orig
+    for k in range(dim):
+        e = np.zeros(dim)
+        e[k] = 1.0
+        y0, y1 = kkt.kkt_apply_fused(M, K, tau, q["beta"], n_t, True, bd,
+                                     e[:N * n].reshape(N, n), e[N * n:].reshape(N, n))
+        y0[:, bd] = 0
+        y1[:, bd] = 0
+        u0, u1 = pc(y0, y1)
+        PA[:, k] = np.concatenate([u0.ravel(), u1.ravel()])
+    idx = np.concatenate([(i * n + free) for i in range(2 * N)])
+    ev = np.linalg.eigvals(PA[np.ix_(idx, idx)])
+    assert np.abs(ev.imag).max() < 1e-6
+    assert ev.real.min() > 0.5 - 1e-6 and ev.real.max() < 1.0 + 1e-6
+
+
+def test_config_c1_readme_problem_all_krylov_variants_agree():
+    """BASELINE config C1 (README heat control, 10x10 P1, beta 1e-4, n_t 10, CN)."""
+    q = kat.heat_problem(10, 10, True)
+    sols = {}
+    for name, sp_, mode in (
+            ("gmres", {"linear_solver": "gmres", "gmres_restart": 10}, "triangular"),
+            ("fgmres", {"linear_solver": "fgmres"}, "triangular"),
+            ("minres", {"linear_solver": "minres"}, "diagonal")):
+        sp_.update({"maximum_iterations": 200, "relative_tolerance": 1e-12,
+                    "absolute_tolerance": 0.0})
+        out = control.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=True,
+                                   time_interval=q["time_interval"], bdofs=q["bdofs"],
+                                   v_d=q["v_d"], f=q["f"], lambda_v_bounds=q["lambda_v_bounds"],
+                                   solver_parameters=sp_, pc_mode=mode)
+        assert out["ksp"].reason > 0
+        sols[name] = out
+    J = {k: control.objective(q["M"], o["v"], o["zeta"], q["v_hat"], q["tau"], q["beta"], True)
+         for k, o in sols.items()}
+    assert abs(J["gmres"] - J["fgmres"]) < 1e-8 * abs(J["fgmres"])
+    assert abs(J["minres"] - J["fgmres"]) < 1e-8 * abs(J["fgmres"])
+    assert np.abs(sols["minres"]["v"] - sols["fgmres"]["v"]).max() < 1e-8 * np.abs(sols["fgmres"]["v"]).max()
+    assert sols["fgmres"]["ksp"].its <= 14
