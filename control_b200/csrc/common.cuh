@@ -1,0 +1,159 @@
+// Internal declarations shared by the translation units of libctl_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/ctl_b200.h"
+
+struct ctl_handle_s;
+
+// ---------------------------------------------------------------- error plumbing
+#define CTL_CUDA(call)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            ctl_set_error(h, std::string(#call) + ": " + cudaGetErrorString(e__));         \
+            return CTL_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+#define CTL_CHECK(cond, code, msg)                                                         \
+    do {                                                                                   \
+        if (!(cond)) {                                                                     \
+            ctl_set_error(h, msg);                                                         \
+            return (code);                                                                 \
+        }                                                                                  \
+    } while (0)
+
+#define CTL_TRY(expr)                                                                      \
+    do {                                                                                   \
+        int rc__ = (expr);                                                                 \
+        if (rc__ != CTL_OK) return rc__;                                                   \
+    } while (0)
+
+void ctl_set_error(ctl_handle_s *h, const std::string &msg);
+
+// ---------------------------------------------------------------- device containers
+// SELL-32 (sliced ELLPACK, slice height 32): the format of every single-column SpMV
+// (time sweeps, AMG levels).  Entry k of row r sits at slice_ptr[r/32] + k*32 + r%32.
+struct SellMatrix {
+    int n_rows = 0, n_cols = 0, n_slices = 0;
+    int64_t n_stored = 0;          // padded entries
+    int64_t nnz = 0;               // true entries (byte model)
+    int *slice_ptr = nullptr;      // n_slices + 1 (offsets in entries; fits int for our sizes)
+    int *slice_len = nullptr;      // row width of each slice
+    int *cols = nullptr;           // n_stored
+    double *vals = nullptr;        // n_stored (first value set)
+    // host-side map from CSR entry index to SELL position, kept so further value sets on the
+    // same pattern can be laid out without recomputing the structure
+    std::vector<int64_t> csr_to_sell;
+};
+
+struct HostCSR {
+    int n_rows = 0, n_cols = 0;
+    std::vector<int> indptr, indices;
+    std::vector<double> values;
+    int64_t nnz() const { return (int64_t)indices.size(); }
+};
+
+// ---------------------------------------------------------------- AMG hierarchy
+struct AmgLevel {
+    int n = 0;
+    HostCSR A, P;                       // host copies (introspection, tests)
+    std::vector<int> agg;
+    double rho = 0.0;
+    SellMatrix dA, dP, dR;              // device
+    double *dinv = nullptr;             // 1/diag(A)
+    double *x = nullptr, *b = nullptr, *r = nullptr, *t0 = nullptr, *t1 = nullptr;  // work vectors (levels >= 1 own x, b)
+    double *Ainv = nullptr;             // dense inverse (coarsest level only), row-major n x n
+};
+
+struct AmgHierarchy {
+    std::vector<AmgLevel> levels;
+    // Chebyshev smoother coefficients are derived per level from rho and the options
+};
+
+// ---------------------------------------------------------------- the handle
+struct ctl_handle_s {
+    ctl_config cfg{};
+    int N = 0;                 // time blocks
+    int ld = 0;                // padded columns of the time-fastest layout
+    int n = 0;                 // global spatial dofs
+    int n_loc = 0;             // rows owned by this rank
+    int row_begin = 0;
+    int n_halo = 0;            // ghost rows appended behind the owned rows
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+    bool assembled = false;
+
+    // host copies of what the caller handed over (global numbering)
+    std::vector<int> h_indptr, h_indices;
+    std::vector<double> h_M;
+    std::vector<std::vector<double>> h_K;     // 1 (all levels) or n_t value arrays
+    std::vector<std::vector<double>> h_KT;    // optional, same shape as h_K
+    std::vector<int> h_bc;
+    std::vector<uint8_t> h_bcmask;            // global rows
+
+    // local (this rank's rows) CSR in local column numbering: owned columns first, ghosts after
+    HostCSR loc;                              // values unused; pattern only
+    std::vector<int64_t> loc_entry;           // local entry -> global CSR entry index
+    std::vector<int> loc_tperm;               // local entry (r,c) -> global entry index of (c,r)
+    std::vector<int> halo_global;             // global row id of each ghost row
+
+    // device: shared pattern + value sets of the batched (time-fastest) kernels
+    int *d_indptr = nullptr, *d_indices = nullptr;
+    double *d_M = nullptr;      // BC columns zeroed
+    double *d_K = nullptr;      // scalar per entry (time independent) or panel [nnz x ld]
+    double *d_KT = nullptr;     // may alias d_K (symmetric, time independent)
+    bool per_level = false;
+    bool k_symmetric = false;
+    uint8_t *d_bcmask = nullptr;   // local rows (owned + ghost)
+    double *d_halo = nullptr;      // ghost rows of the current SpMM input, [2][n_halo x ld]
+
+    // reduction workspace (vec_ops.cu)
+    double *d_red = nullptr, *h_red = nullptr;
+
+    // scratch vectors (time-fastest, 2 * n_loc * ld doubles each)
+    std::vector<double *> pool;
+
+    // preconditioner, Krylov workspace, communicator: defined in their own units
+    std::shared_ptr<struct PcState> pc;
+    std::shared_ptr<struct KrylovState> ks;
+    std::shared_ptr<struct CommState> comm;
+    ctl_pc_callback pc_cb = nullptr;
+    void *pc_cb_user = nullptr;
+
+    int64_t vec_len() const { return 2ll * n_loc * ld; }
+};
+
+// ---------------------------------------------------------------- kernels / helpers (defined in .cu files)
+// layout.cu
+int ctl_to_tf(ctl_handle_s *h, const double *src_bm, double *dst_tf);
+int ctl_to_bm(ctl_handle_s *h, const double *src_tf, double *dst_bm);
+// kkt_apply.cu
+int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf);
+
+// unit-private state teardown / invalidation
+void ctl_pc_free(ctl_handle_s *h);        // pc.cu
+void ctl_krylov_free(ctl_handle_s *h);    // krylov.cu
+void ctl_comm_free(ctl_handle_s *h);      // comm.cu
+int ctl_pc_invalidate(ctl_handle_s *h);   // pc.cu: matrices changed, rebuild on next setup
+// comm.cu
+int ctl_halo_exchange(ctl_handle_s *h, const double *x_tf);
+int ctl_allreduce_sum(ctl_handle_s *h, double *dev, int count);
+
+// scratch management
+int ctl_scratch_get(ctl_handle_s *h, double **out);            // one full vector
+void ctl_scratch_put(ctl_handle_s *h, double *p);
+
+template <typename T>
+int ctl_upload(ctl_handle_s *h, T **dst, const T *src, size_t count);
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

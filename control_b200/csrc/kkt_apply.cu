@@ -1,0 +1,222 @@
+// Fused all-at-once KKT operator apply (SURVEY.md rows K1 + K2 + K3).
+//
+// Replaces MultiBlockSystemMatrix.mult (preconditioner/preconditioner.py:375-543): the
+// 8N-4 (CN) / 6N-4 (BE) MatMultAdd calls over separately assembled blocks
+// (control/control.py:2889-2978), the T_1 / T_2 time-coupling transforms (437-470) and the
+// DirichletBCNullspace pre/post corrections (384-393, 527-537) become ONE kernel:
+//
+//   * vectors live in the time-fastest layout X[row][ld]: the N time columns of a spatial
+//     dof are contiguous, so a (sub-)warp reads the whole N-column row segment of a
+//     gathered dof with coalesced 16-byte loads (lane l owns columns 2l, 2l+1);
+//   * every time step shares the pattern and the values of M and K, so the matrix is read
+//     once per row, not once per block (per-level values: [nnz][ld] panels, same access);
+//   * the four products MV, KV, MZ, KZ of a row stay in registers; the block stencil and
+//     T_1 / T_2 are neighbour exchanges along the time axis = warp shuffles;
+//   * Dirichlet columns are eliminated from the value arrays at setup (x_c = P x) and
+//     Dirichlet rows return x (y = P A P x + (I - P) x).
+//
+// HBM-bound: algorithmic bytes per apply = 32 n N + 20 nnz + 4 (n+1).
+#include "common.cuh"
+
+namespace {
+
+constexpr int CHUNK = 8;          // matrix entries staged per pass (covers a P1 2-D row)
+
+struct KktArgs {
+    int n_rows;                   // owned rows
+    int n_own_cols;               // columns < n_own_cols come from x, the rest from halo
+    int N, ld;
+    const int *indptr, *indices;
+    const double *Mv, *Kv, *KTv;  // value sets (BC columns zeroed)
+    const uint8_t *bcmask;
+    const double *xv, *xz;        // input panels  [n_rows x ld]
+    const double *hv, *hz;        // ghost rows    [n_halo x ld]
+    double *y0, *y1;              // output panels
+    double tau, beta;
+};
+
+__device__ __forceinline__ double2 ldg2(const double *p)
+{
+    return __ldg(reinterpret_cast<const double2 *>(p));
+}
+
+// G = lanes per row (ld = 2 G columns); 32 / G rows per warp.
+template <bool CN, bool PER_LEVEL, int G>
+__global__ void __launch_bounds__(256) kkt_apply_kernel(const KktArgs a)
+{
+    constexpr int ROWS_PER_WARP = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G;
+    const int l = lane % G;
+    const int warp = (blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5);
+    const int row = warp * ROWS_PER_WARP + sub;
+    const bool live = row < a.n_rows;
+    const int r = live ? row : a.n_rows - 1;        // keep the whole warp in the shuffles
+    const int c0 = 2 * l;
+    const int ld = a.ld;
+
+    double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
+
+    const int kbeg = a.indptr[r], kend = a.indptr[r + 1];
+    for (int k0 = kbeg; k0 < kend; k0 += CHUNK) {
+        int col[CHUNK];
+        double m[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+            const int k = k0 + j;
+            const bool ok = k < kend;
+            col[j] = ok ? __ldg(a.indices + k) : r;
+            m[j] = ok ? __ldg(a.Mv + k) : 0.0;
+        }
+        double2 xv[CHUNK], xz[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+            const int c = col[j];
+            const bool own = c < a.n_own_cols;
+            const double *pv = own ? a.xv + (size_t)c * ld : a.hv + (size_t)(c - a.n_own_cols) * ld;
+            const double *pz = own ? a.xz + (size_t)c * ld : a.hz + (size_t)(c - a.n_own_cols) * ld;
+            xv[j] = ldg2(pv + c0);
+            xz[j] = ldg2(pz + c0);
+        }
+        if (!PER_LEVEL) {
+            double kk[CHUNK], kt[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                const int k = k0 + j;
+                const bool ok = k < kend;
+                kk[j] = ok ? __ldg(a.Kv + k) : 0.0;
+                kt[j] = ok ? __ldg(a.KTv + k) : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                mv0 = fma(m[j], xv[j].x, mv0);
+                mv1 = fma(m[j], xv[j].y, mv1);
+                mz0 = fma(m[j], xz[j].x, mz0);
+                mz1 = fma(m[j], xz[j].y, mz1);
+                kv0 = fma(kk[j], xv[j].x, kv0);
+                kv1 = fma(kk[j], xv[j].y, kv1);
+                kz0 = fma(kt[j], xz[j].x, kz0);
+                kz1 = fma(kt[j], xz[j].y, kz1);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                const int k = k0 + j;
+                if (k < kend) {
+                    const double2 kk = ldg2(a.Kv + (size_t)k * ld + c0);
+                    const double2 kt = ldg2(a.KTv + (size_t)k * ld + c0);
+                    mv0 = fma(m[j], xv[j].x, mv0);
+                    mv1 = fma(m[j], xv[j].y, mv1);
+                    mz0 = fma(m[j], xz[j].x, mz0);
+                    mz1 = fma(m[j], xz[j].y, mz1);
+                    kv0 = fma(kk.x, xv[j].x, kv0);
+                    kv1 = fma(kk.y, xv[j].y, kv1);
+                    kz0 = fma(kt.x, xz[j].x, kz0);
+                    kz1 = fma(kt.y, xz[j].y, kz1);
+                }
+            }
+        }
+    }
+
+    // ---- block stencil + T_1 / T_2 along the time axis (columns c0, c0+1 of this lane)
+    const unsigned full = 0xffffffffu;
+    const bool first = (l == 0), last = (l == G - 1);
+    const int N = a.N;
+    const bool in0 = c0 < N, in1 = c0 + 1 < N;
+    double y00, y01, y10, y11;
+    if (CN) {
+        const double h = 0.5 * a.tau, hb = h / a.beta;
+        double t;
+        t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+        t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
+        t = __shfl_down_sync(full, kz0, 1, G); const double kzn1 = last ? 0.0 : t;
+        t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+        // rows of the untransformed block system (control/control.py:2938-2958)
+        double r00 = h * (mvp0 + mv0) + h * (kz0 + kz1) + mz0 - mz1;
+        double r01 = h * (mv0 + mv1) + h * (kz1 + kzn1) + mz1 - mzn1;
+        double r10 = h * (kvp0 + kv0) - mvp0 + mv0 - hb * (mz0 + mz1);
+        double r11 = h * (kv0 + kv1) - mv0 + mv1 - hb * (mz1 + mzn1);
+        if (!in0) { r00 = 0.0; r10 = 0.0; }
+        if (!in1) { r01 = 0.0; r11 = 0.0; }
+        // T_1: add the next block row; T_2: add the previous one (preconditioner.py:33-60)
+        t = __shfl_down_sync(full, r00, 1, G); const double r0n = last ? 0.0 : t;
+        t = __shfl_up_sync(full, r11, 1, G);   const double r1p = first ? 0.0 : t;
+        y00 = r00 + r01;
+        y01 = r01 + r0n;
+        y10 = r10 + r1p;
+        y11 = r11 + r10;
+    } else {
+        const double tau = a.tau, tb = tau / a.beta;
+        double t;
+        t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+        t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+        // control/control.py:2907-2928, 2960-2978: block_00 last row None, block_11 row 0 None
+        y00 = tau * kz0 + mz0 + ((c0 < N - 1) ? (tau * mv0 - mz1) : 0.0);
+        y01 = tau * kz1 + mz1 + ((c0 + 1 < N - 1) ? (tau * mv1 - mzn1) : 0.0);
+        y10 = tau * kv0 + mv0 + ((c0 >= 1) ? (-mvp0 - tb * mz0) : 0.0);
+        y11 = tau * kv1 + mv1 + (-mv0 - tb * mz1);
+    }
+    if (!in0) { y00 = 0.0; y10 = 0.0; }
+    if (!in1) { y01 = 0.0; y11 = 0.0; }
+    if (!live) return;
+    if (a.bcmask[r]) {           // y = (I - P) x on constrained rows
+        const double2 xv = ldg2(a.xv + (size_t)r * ld + c0);
+        const double2 xz = ldg2(a.xz + (size_t)r * ld + c0);
+        y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
+    }
+    *reinterpret_cast<double2 *>(a.y0 + (size_t)r * ld + c0) = make_double2(y00, y01);
+    *reinterpret_cast<double2 *>(a.y1 + (size_t)r * ld + c0) = make_double2(y10, y11);
+}
+
+template <bool CN, bool PER_LEVEL>
+void launch_g(const KktArgs &a, int G, cudaStream_t s)
+{
+    const int threads = 256;
+    const int rows_per_block = (threads / 32) * (32 / G);
+    const int blocks = ceil_div(a.n_rows, rows_per_block);
+    switch (G) {
+    case 4: kkt_apply_kernel<CN, PER_LEVEL, 4><<<blocks, threads, 0, s>>>(a); break;
+    case 8: kkt_apply_kernel<CN, PER_LEVEL, 8><<<blocks, threads, 0, s>>>(a); break;
+    case 16: kkt_apply_kernel<CN, PER_LEVEL, 16><<<blocks, threads, 0, s>>>(a); break;
+    default: kkt_apply_kernel<CN, PER_LEVEL, 32><<<blocks, threads, 0, s>>>(a); break;
+    }
+}
+
+}  // namespace
+
+int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
+{
+    CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_kkt_apply: ctl_assemble has not been called");
+    if (h->n_halo > 0) CTL_TRY(ctl_halo_exchange(h, x_tf));
+    KktArgs a;
+    a.n_rows = h->n_loc;
+    a.n_own_cols = h->n_loc;
+    a.N = h->N;
+    a.ld = h->ld;
+    a.indptr = h->d_indptr;
+    a.indices = h->d_indices;
+    a.Mv = h->d_M;
+    a.Kv = h->d_K;
+    a.KTv = h->d_KT;
+    a.bcmask = h->d_bcmask;
+    const size_t panel = (size_t)h->n_loc * h->ld;
+    a.xv = x_tf;
+    a.xz = x_tf + panel;
+    a.hv = h->d_halo;
+    a.hz = h->d_halo ? h->d_halo + (size_t)h->n_halo * h->ld : nullptr;
+    a.y0 = y_tf;
+    a.y1 = y_tf + panel;
+    a.tau = h->cfg.tau;
+    a.beta = h->cfg.beta;
+    const int G = h->ld / 2;
+    if (h->cfg.CN) {
+        if (h->per_level) launch_g<true, true>(a, G, h->stream);
+        else launch_g<true, false>(a, G, h->stream);
+    } else {
+        if (h->per_level) launch_g<false, true>(a, G, h->stream);
+        else launch_g<false, false>(a, G, h->stream);
+    }
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}

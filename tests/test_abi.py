@@ -1,0 +1,71 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+that include/ctl_b200.h declares (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ctl_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(ctl_[a-z0-9_]+)\s*\(", src)
+    typedefs = set(re.findall(r"\(\*(ctl_[a-z0-9_]+)\)", src))
+    return sorted(set(names) - typedefs)
+
+
+def test_header_declares_the_path():
+    names = declared_functions()
+    for required in ("ctl_create", "ctl_destroy", "ctl_set_pattern", "ctl_set_values", "ctl_set_bc",
+                     "ctl_kkt_apply", "ctl_pc_setup", "ctl_pc_apply", "ctl_solve", "ctl_solve_host",
+                     "ctl_last_error", "ctl_comm_init"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    from control_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build the library first (__graft_entry__.build())"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in declared_functions() if not hasattr(lib, n)]
+    assert not missing, f"declared in ctl_b200.h but not exported: {missing}"
+
+
+def test_python_binding_covers_the_header():
+    from control_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+    lib = _lib.load()
+    assert lib.ctl_version().startswith(b"ctl_b200")
+
+
+def test_struct_layouts_match_the_header():
+    """sizeof checks against a tiny C program compiled from the header itself."""
+    import subprocess
+    import tempfile
+    from control_b200 import _lib
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write(
+            '#include <stdio.h>\n#include "ctl_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n",'
+            'sizeof(ctl_config),sizeof(ctl_pc_options),sizeof(ctl_krylov_options),'
+            'sizeof(ctl_solve_result));return 0;}\n')
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [ctypes.sizeof(_lib.ctl_config), ctypes.sizeof(_lib.ctl_pc_options),
+                     ctypes.sizeof(_lib.ctl_krylov_options), ctypes.sizeof(_lib.ctl_solve_result)]
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    import scipy.sparse as sp
+    from control_b200 import CtlError, MultiBlockSystem
+    M = sp.identity(4, format="csr")
+    with pytest.raises(CtlError):
+        MultiBlockSystem(M, M, n_t=3, beta=1e-2, CN=True, bc_dofs=np.array([0]))
