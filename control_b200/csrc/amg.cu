@@ -1,0 +1,134 @@
+// Aggregation-AMG V-cycle on the device: the inner solver of the
+// Schur-complement time sweeps, standing in for "preonly + hypre boomeramg, max_iter 2"
+// (control/control.py:2056-2067 and the nine other sites).  The hierarchy is set up on
+// the host once per distinct matrix (amg_setup.cpp); a cycle is a fixed sequence of SELL
+// SpMV-family kernels (sell.cu), so the time sweeps can be captured in a CUDA graph.
+#include "amg.cuh"
+
+#include <stdexcept>
+
+#include "cheb_coefficients.h"
+
+static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
+{
+    CTL_CUDA(cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(double)));
+    CTL_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(double), h->stream));
+    return CTL_OK;
+}
+
+int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
+              const std::shared_ptr<SellPattern> &fine_pattern, AmgHierarchyDev &H)
+{
+    H.params = p;
+    try {
+        amg_setup_host(A0, p, H.host);
+    } catch (const std::exception &e) {
+        ctl_set_error(h, e.what());
+        return CTL_ERR_STATE;
+    }
+    const int nl = (int)H.host.size();
+    H.dev.assign(nl, AmgLevelDev());
+    H.bytes_per_cycle = 0;
+    for (int l = 0; l < nl; ++l) {
+        AmgLevelHost &Lh = H.host[l];
+        AmgLevelDev &Ld = H.dev[l];
+        Ld.n = Lh.A.n_rows;
+        Ld.rho = Lh.rho;
+        std::shared_ptr<SellPattern> pat;
+        if (l == 0 && fine_pattern) pat = fine_pattern;
+        else CTL_TRY(sell_build_pattern(h, Lh.A, pat));
+        CTL_TRY(sell_set_values(h, pat, Lh.A.values.data(), Ld.A));
+        CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data(), Lh.dinv.size()));
+        CTL_TRY(dev_alloc(h, &Ld.r, Ld.n));
+        CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n));
+        if (l > 0) {
+            CTL_TRY(dev_alloc(h, &Ld.x, Ld.n));
+            CTL_TRY(dev_alloc(h, &Ld.b, Ld.n));
+        }
+        const int64_t spmv = 12 * Lh.A.nnz() + 4ll * (Ld.n + 1) + 16ll * Ld.n;
+        if (l + 1 < nl) {
+            std::shared_ptr<SellPattern> pp, pr;
+            CTL_TRY(sell_build_pattern(h, Lh.P, pp));
+            CTL_TRY(sell_set_values(h, pp, Lh.P.values.data(), Ld.P));
+            CTL_TRY(sell_build_pattern(h, Lh.R, pr));
+            CTL_TRY(sell_set_values(h, pr, Lh.R.values.data(), Ld.R));
+            // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
+            H.bytes_per_cycle += spmv * (2 * p.nu) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
+        } else if (!Lh.Ainv.empty()) {
+            CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
+            H.bytes_per_cycle += 8ll * Ld.n * Ld.n;
+        } else {
+            H.bytes_per_cycle += spmv * p.nu;
+        }
+    }
+    return CTL_OK;
+}
+
+void amg_free(AmgHierarchyDev &H)
+{
+    for (AmgLevelDev &L : H.dev) {
+        sell_free(L.A);
+        sell_free(L.P);
+        sell_free(L.R);
+        cudaFree(L.dinv);
+        cudaFree(L.x);
+        cudaFree(L.b);
+        cudaFree(L.r);
+        cudaFree(L.t0);
+        cudaFree(L.Ainv);
+    }
+    H.dev.clear();
+    H.host.clear();
+}
+
+// nu Chebyshev steps on D^-1 A over [lo rho, hi rho] (oracle/cheb.py::chebyshev), result in x.
+// Iterates alternate between x and t0; for a non-zero guess and odd nu one copy moves the
+// result back into x.
+static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, const double *b, double *x, bool zero_guess)
+{
+    double scale;
+    std::vector<double> om;
+    cheb_coefficients(p.lo * L.rho, p.hi * L.rho, p.nu, &scale, om);
+    double *buf[2] = {x, L.t0};
+    // p_k lives in buf[slot(k)]; p_nu must be x when possible
+    auto slot = [&](int k) { return zero_guess ? ((p.nu - k) & 1) : (k & 1); };
+    if (zero_guess) {
+        CTL_TRY(vec_dinv_scale(h, L.dinv, b, buf[slot(1)], scale, L.n));
+    } else {
+        // p_1 = x + scale D^-1 (b - A x)
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, buf[slot(1)], 0.0, 1.0, scale));
+    }
+    for (int k = 2; k <= p.nu; ++k) {
+        const double w = om[k - 2];
+        const double *prev = (k == 2 && zero_guess) ? nullptr : buf[slot(k - 2)];
+        const double a = (k == 2 && zero_guess) ? 0.0 : (1.0 - w);
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, prev, buf[slot(k - 1)], buf[slot(k)], a, w, w * scale));
+    }
+    if (buf[slot(p.nu)] != x)
+        CTL_CUDA(cudaMemcpyAsync(x, buf[slot(p.nu)], (size_t)L.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return CTL_OK;
+}
+
+static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, double *x, bool zero_guess)
+{
+    AmgLevelDev &L = H.dev[l];
+    const int last = (int)H.dev.size() - 1;
+    if (l == last) {
+        if (L.Ainv) return dense_gemv(h, L.Ainv, b, x, L.n);
+        return smooth(h, H.params, L, b, x, zero_guess);
+    }
+    AmgLevelDev &C = H.dev[l + 1];
+    CTL_TRY(smooth(h, H.params, L, b, x, zero_guess));
+    CTL_TRY(sell_spmv(h, L.A, x, L.r, b, SELL_RESIDUAL));
+    CTL_TRY(sell_spmv(h, L.R, L.r, C.b, nullptr, SELL_ASSIGN));
+    CTL_TRY(vcycle(h, H, l + 1, C.b, C.x, true));
+    CTL_TRY(sell_spmv(h, L.P, C.x, x, nullptr, SELL_ADD));
+    CTL_TRY(smooth(h, H.params, L, b, x, false));
+    return CTL_OK;
+}
+
+int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x)
+{
+    for (int c = 0; c < H.params.cycles; ++c) CTL_TRY(vcycle(h, H, 0, b, x, c == 0));
+    return CTL_OK;
+}

@@ -1,0 +1,248 @@
+// Smoothed-aggregation AMG setup on the host, once per distinct matrix (the reference
+// re-runs BoomerAMG setup 2N times per preconditioner application:
+// control/control.py:2056-2067, 2098-2109, 2139-2150, 2172-2183).
+#include "amg_setup.h"
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+
+void csr_transpose(const HostCSR &A, HostCSR &At)
+{
+    At.n_rows = A.n_cols;
+    At.n_cols = A.n_rows;
+    At.indptr.assign(A.n_cols + 1, 0);
+    At.indices.resize(A.indices.size());
+    At.values.resize(A.values.size());
+    for (int c : A.indices) At.indptr[c + 1]++;
+    for (int i = 0; i < A.n_cols; ++i) At.indptr[i + 1] += At.indptr[i];
+    std::vector<int> pos(At.indptr.begin(), At.indptr.end() - 1);
+    for (int r = 0; r < A.n_rows; ++r)
+        for (int k = A.indptr[r]; k < A.indptr[r + 1]; ++k) {
+            const int q = pos[A.indices[k]]++;
+            At.indices[q] = r;
+            At.values[q] = A.values[k];
+        }
+}
+
+// Gustavson SpGEMM; accumulation order = ascending k of A's row, then B's row order
+// (the order scipy's csr_matmat uses), columns of C sorted.
+void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C)
+{
+    C.n_rows = A.n_rows;
+    C.n_cols = B.n_cols;
+    C.indptr.assign(A.n_rows + 1, 0);
+    C.indices.clear();
+    C.values.clear();
+    std::vector<double> acc(B.n_cols, 0.0);
+    std::vector<int> mark(B.n_cols, -1), cols;
+    for (int i = 0; i < A.n_rows; ++i) {
+        cols.clear();
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+            const int j = A.indices[k];
+            const double a = A.values[k];
+            for (int q = B.indptr[j]; q < B.indptr[j + 1]; ++q) {
+                const int c = B.indices[q];
+                if (mark[c] != i) {
+                    mark[c] = i;
+                    acc[c] = 0.0;
+                    cols.push_back(c);
+                }
+                acc[c] += a * B.values[q];
+            }
+        }
+        std::sort(cols.begin(), cols.end());
+        for (int c : cols) {
+            C.indices.push_back(c);
+            C.values.push_back(acc[c]);
+        }
+        C.indptr[i + 1] = (int)C.indices.size();
+    }
+}
+
+// oracle/amg.py:_aggregate
+static int aggregate(const HostCSR &A, double theta, std::vector<int> &agg)
+{
+    const int n = A.n_rows;
+    std::vector<double> diag(n, 0.0);
+    for (int i = 0; i < n; ++i)
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+            if (A.indices[k] == i) diag[i] = A.values[k];
+    std::vector<char> strong(A.indices.size(), 0);
+    const double th2 = theta * theta;
+    for (int i = 0; i < n; ++i)
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+            const int j = A.indices[k];
+            if (j != i) {
+                const double a = A.values[k];
+                if (a != 0.0 && a * a >= th2 * std::fabs(diag[i] * diag[j])) strong[k] = 1;
+            }
+        }
+    agg.assign(n, -1);
+    int n_agg = 0;
+    for (int i = 0; i < n; ++i) {                       // pass 1
+        if (agg[i] != -1) continue;
+        bool has_nbr = false, free_ = true;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+            if (strong[k]) {
+                has_nbr = true;
+                if (agg[A.indices[k]] != -1) {
+                    free_ = false;
+                    break;
+                }
+            }
+        if (has_nbr && free_) {
+            agg[i] = n_agg;
+            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+                if (strong[k]) agg[A.indices[k]] = n_agg;
+            ++n_agg;
+        }
+    }
+    const std::vector<int> agg1 = agg;                  // pass 2
+    for (int i = 0; i < n; ++i) {
+        if (agg1[i] != -1) continue;
+        int best = -1;
+        double best_val = -1.0;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+            if (strong[k] && agg1[A.indices[k]] != -1) {
+                const double a = std::fabs(A.values[k]);
+                if (a > best_val) {
+                    best_val = a;
+                    best = agg1[A.indices[k]];
+                }
+            }
+        if (best != -1) agg[i] = best;
+    }
+    for (int i = 0; i < n; ++i) {                       // pass 3
+        if (agg[i] != -1) continue;
+        bool has_nbr = false;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+            if (strong[k]) {
+                has_nbr = true;
+                break;
+            }
+        if (!has_nbr) continue;
+        agg[i] = n_agg;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k)
+            if (strong[k] && agg[A.indices[k]] == -1) agg[A.indices[k]] = n_agg;
+        ++n_agg;
+    }
+    return n_agg;
+}
+
+static double gershgorin_rho(const HostCSR &A, std::vector<double> &dinv)
+{
+    const int n = A.n_rows;
+    dinv.assign(n, 0.0);
+    double rho = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double d = 0.0, s = 0.0;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+            s += std::fabs(A.values[k]);
+            if (A.indices[k] == i) d = A.values[k];
+        }
+        if (d == 0.0) throw std::runtime_error("AMG setup: zero diagonal entry");
+        dinv[i] = 1.0 / d;
+        rho = std::max(rho, s / std::fabs(d));
+    }
+    return rho;
+}
+
+// Gauss-Jordan with partial pivoting on [A | I]; A is small (coarsest level)
+static void dense_inverse(const HostCSR &A, std::vector<double> &inv)
+{
+    const int n = A.n_rows;
+    std::vector<double> a((size_t)n * n, 0.0);
+    inv.assign((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        inv[(size_t)i * n + i] = 1.0;
+        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) a[(size_t)i * n + A.indices[k]] += A.values[k];
+    }
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < n; ++r)
+            if (std::fabs(a[(size_t)r * n + c]) > std::fabs(a[(size_t)piv * n + c])) piv = r;
+        if (a[(size_t)piv * n + c] == 0.0) throw std::runtime_error("AMG setup: singular coarse matrix");
+        if (piv != c)
+            for (int j = 0; j < n; ++j) {
+                std::swap(a[(size_t)piv * n + j], a[(size_t)c * n + j]);
+                std::swap(inv[(size_t)piv * n + j], inv[(size_t)c * n + j]);
+            }
+        const double d = 1.0 / a[(size_t)c * n + c];
+        for (int j = 0; j < n; ++j) {
+            a[(size_t)c * n + j] *= d;
+            inv[(size_t)c * n + j] *= d;
+        }
+        for (int r = 0; r < n; ++r) {
+            if (r == c) continue;
+            const double f = a[(size_t)r * n + c];
+            if (f == 0.0) continue;
+            for (int j = 0; j < n; ++j) {
+                a[(size_t)r * n + j] -= f * a[(size_t)c * n + j];
+                inv[(size_t)r * n + j] -= f * inv[(size_t)c * n + j];
+            }
+        }
+    }
+}
+
+void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelHost> &levels)
+{
+    levels.clear();
+    HostCSR A = A0;
+    while (true) {
+        levels.emplace_back();
+        AmgLevelHost &L = levels.back();
+        L.A = A;
+        L.rho = gershgorin_rho(L.A, L.dinv);
+        const int n = A.n_rows;
+        if (n <= p.coarse_max || (int)levels.size() >= p.max_levels) break;
+        std::vector<int> agg;
+        const int n_agg = aggregate(A, p.theta, agg);
+        if (n_agg == 0 || n_agg >= 0.9 * n) break;
+        L.agg = agg;
+        std::vector<double> t(n_agg, 0.0);
+        for (int i = 0; i < n; ++i)
+            if (agg[i] >= 0) t[agg[i]] += 1.0;
+        for (int J = 0; J < n_agg; ++J) t[J] = 1.0 / std::sqrt(t[J]);
+        // P = T - diag(omega * dinv) (A T), explicit zeros of A skipped
+        const double omega = 4.0 / (3.0 * L.rho);
+        HostCSR &P = L.P;
+        P.n_rows = n;
+        P.n_cols = n_agg;
+        P.indptr.assign(n + 1, 0);
+        std::vector<std::pair<int, double>> row;
+        for (int i = 0; i < n; ++i) {
+            row.clear();
+            // (A T)_iJ accumulated in CSR order of j
+            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+                const double a = A.values[k];
+                const int J = agg[A.indices[k]];
+                if (a == 0.0 || J < 0) continue;
+                auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
+                if (it == row.end()) row.emplace_back(J, a * t[J]);
+                else it->second += a * t[J];
+            }
+            const double d = omega * L.dinv[i];
+            for (auto &e : row) e.second = -(d * e.second);
+            if (agg[i] >= 0) {
+                const int J = agg[i];
+                auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
+                if (it == row.end()) row.emplace_back(J, t[J]);
+                else it->second = t[J] + it->second;
+            }
+            std::sort(row.begin(), row.end());
+            for (auto &e : row) {
+                P.indices.push_back(e.first);
+                P.values.push_back(e.second);
+            }
+            P.indptr[i + 1] = (int)P.indices.size();
+        }
+        csr_transpose(P, L.R);
+        HostCSR AP, Ac;
+        csr_matmat(A, P, AP);
+        csr_matmat(L.R, AP, Ac);
+        A = std::move(Ac);
+    }
+    AmgLevelHost &last = levels.back();
+    if (last.A.n_rows <= 4096) dense_inverse(last.A, last.Ainv);
+}

@@ -1,0 +1,32 @@
+// Host-side smoothed-aggregation setup (amg_setup.cpp).  Step-for-step the algorithm of
+// oracle/amg.py; see that file's header for the definition and DESIGN.md for why this
+// replaces hypre BoomerAMG (control/control.py:2056-2067).
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+struct AmgParams {
+    double theta = 0.08;
+    int max_levels = 10;
+    int coarse_max = 200;
+    int nu = 2;
+    double lo = 0.25, hi = 1.0;
+    int cycles = 2;
+};
+
+struct AmgLevelHost {
+    HostCSR A;                 // level operator
+    std::vector<double> dinv;  // 1 / diag(A)
+    double rho = 0.0;          // Gershgorin bound of D^-1 A
+    std::vector<int> agg;      // aggregate id per row (-1 = not aggregated); empty on the last level
+    HostCSR P, R;              // prolongation (n x n_coarse) and R = P^T; empty on the last level
+    std::vector<double> Ainv;  // dense inverse, row-major (last level, n <= 4096)
+};
+
+// A must have sorted column indices.  Returns the levels, finest first.
+void amg_setup_host(const HostCSR &A, const AmgParams &p, std::vector<AmgLevelHost> &levels);
+
+// helpers shared with tests / other units
+void csr_transpose(const HostCSR &A, HostCSR &At);
+void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C);

@@ -1,6 +1,7 @@
 // C ABI: handle lifetime, matrix hand-over, row partition, operator apply entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -119,6 +120,7 @@ int ctl_destroy(ctl_handle h)
     if (h->d_KT != h->d_K) cudaFree(h->d_KT);
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
+    cudaFree(h->d_bc_rows_all);
     cudaFree(h->d_halo);
     cudaFree(h->d_red);
     if (h->h_red) cudaFreeHost(h->h_red);
@@ -230,7 +232,9 @@ static int build_local_pattern(ctl_handle_s *h)
             h->loc_tperm[p] = (f != e && *f == g) ? (int)(f - ix.data()) : -1;
         }
         L.indptr[r + 1] = (int)p;
+        h->max_row_len = std::max(h->max_row_len, ip[g + 1] - ip[g]);
     }
+    if (const char *e = getenv("CTL_KKT_UNSTAGED")) h->force_unstaged = (e[0] == '1');
     // note: local column order within a row is no longer sorted when ghosts precede owned
     // columns globally; the kernels do not rely on sorted columns.
     return CTL_OK;
@@ -262,6 +266,13 @@ int ctl_assemble(ctl_handle h)
     for (int r = 0; r < nl; ++r) mask[r] = h->h_bcmask[rb + r];
     for (int g = 0; g < h->n_halo; ++g) mask[nl + g] = h->h_bcmask[h->halo_global[g]];
     CTL_TRY(ctl_upload(h, &h->d_bcmask, mask.data(), mask.size()));
+    {
+        std::vector<int> rows;
+        for (int r = 0; r < nl; ++r)
+            if (mask[r]) rows.push_back(r);
+        h->n_bc_all = (int)rows.size();
+        CTL_TRY(ctl_upload(h, &h->d_bc_rows_all, rows.data(), rows.size()));
+    }
     auto colmask = [&](int64_t p) { return mask[h->loc.indices[p]] != 0; };
 
     std::vector<double> buf(nnz);

@@ -38,44 +38,12 @@ struct ctl_handle_s;
 
 void ctl_set_error(ctl_handle_s *h, const std::string &msg);
 
-// ---------------------------------------------------------------- device containers
-// SELL-32 (sliced ELLPACK, slice height 32): the format of every single-column SpMV
-// (time sweeps, AMG levels).  Entry k of row r sits at slice_ptr[r/32] + k*32 + r%32.
-struct SellMatrix {
-    int n_rows = 0, n_cols = 0, n_slices = 0;
-    int64_t n_stored = 0;          // padded entries
-    int64_t nnz = 0;               // true entries (byte model)
-    int *slice_ptr = nullptr;      // n_slices + 1 (offsets in entries; fits int for our sizes)
-    int *slice_len = nullptr;      // row width of each slice
-    int *cols = nullptr;           // n_stored
-    double *vals = nullptr;        // n_stored (first value set)
-    // host-side map from CSR entry index to SELL position, kept so further value sets on the
-    // same pattern can be laid out without recomputing the structure
-    std::vector<int64_t> csr_to_sell;
-};
-
+// ---------------------------------------------------------------- host containers
 struct HostCSR {
     int n_rows = 0, n_cols = 0;
     std::vector<int> indptr, indices;
     std::vector<double> values;
     int64_t nnz() const { return (int64_t)indices.size(); }
-};
-
-// ---------------------------------------------------------------- AMG hierarchy
-struct AmgLevel {
-    int n = 0;
-    HostCSR A, P;                       // host copies (introspection, tests)
-    std::vector<int> agg;
-    double rho = 0.0;
-    SellMatrix dA, dP, dR;              // device
-    double *dinv = nullptr;             // 1/diag(A)
-    double *x = nullptr, *b = nullptr, *r = nullptr, *t0 = nullptr, *t1 = nullptr;  // work vectors (levels >= 1 own x, b)
-    double *Ainv = nullptr;             // dense inverse (coarsest level only), row-major n x n
-};
-
-struct AmgHierarchy {
-    std::vector<AmgLevel> levels;
-    // Chebyshev smoother coefficients are derived per level from rho and the options
 };
 
 // ---------------------------------------------------------------- the handle
@@ -113,8 +81,12 @@ struct ctl_handle_s {
     double *d_K = nullptr;      // scalar per entry (time independent) or panel [nnz x ld]
     double *d_KT = nullptr;     // may alias d_K (symmetric, time independent)
     bool per_level = false;
+    int max_row_len = 0;        // longest local row (sizes the shared-memory staging)
+    bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
     bool k_symmetric = false;
     uint8_t *d_bcmask = nullptr;   // local rows (owned + ghost)
+    int *d_bc_rows_all = nullptr;  // list of constrained owned rows
+    int n_bc_all = 0;
     double *d_halo = nullptr;      // ghost rows of the current SpMM input, [2][n_halo x ld]
 
     // reduction workspace (vec_ops.cu)
@@ -139,6 +111,8 @@ int ctl_to_tf(ctl_handle_s *h, const double *src_bm, double *dst_tf);
 int ctl_to_bm(ctl_handle_s *h, const double *src_tf, double *dst_bm);
 // kkt_apply.cu
 int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf);
+// pc.cu: Preconditioner.apply on time-fastest vectors
+int ctl_pc_apply_tf(ctl_handle_s *h, const double *b_tf, double *u_tf);
 
 // unit-private state teardown / invalidation
 void ctl_pc_free(ctl_handle_s *h);        // pc.cu

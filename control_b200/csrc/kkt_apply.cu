@@ -16,11 +16,20 @@
 //     Dirichlet rows return x (y = P A P x + (I - P) x).
 //
 // HBM-bound: algorithmic bytes per apply = 32 n N + 20 nnz + 4 (n+1).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int CHUNK = 8;          // matrix entries staged per pass (covers a P1 2-D row)
+constexpr int STAGE_CAP = 1024;   // CSR entries a CTA stages in shared memory
+constexpr int CHUNK = 8;
+#ifndef SCHUNK
+#define SCHUNK 4
+#endif
+#ifndef SMINB
+#define SMINB 4
+#endif          // matrix entries staged per pass (covers a P1 2-D row)
 
 struct KktArgs {
     int n_rows;                   // owned rows
@@ -168,6 +177,156 @@ __global__ void __launch_bounds__(256) kkt_apply_kernel(const KktArgs a)
     *reinterpret_cast<double2 *>(a.y1 + (size_t)r * ld + c0) = make_double2(y10, y11);
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Staged variant (the one normally launched): a CTA owns `rows_per_cta` consecutive rows.
+// Their CSR entries are contiguous, so the CTA first copies column indices and matrix
+// values into shared memory with fully coalesced loads; afterwards the only global
+// latency a warp sees per row is the gather of the X row segments themselves (the
+// unstaged kernel above serialises indptr -> indices -> X per row and is latency bound:
+// profiles/r01_kkt_apply_v1.txt).
+// ---------------------------------------------------------------------------------------
+template <bool CN, bool PER_LEVEL, bool SYM, int G>
+__global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktArgs a, const int rows_per_cta,
+                                                                 const int cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_m = reinterpret_cast<double *>(smem_raw);
+    double *s_k = s_m + cap;
+    double *s_kt = SYM ? s_k : s_k + cap;
+    int *s_col = reinterpret_cast<int *>((PER_LEVEL ? s_m + cap : (SYM ? s_k + cap : s_kt + cap)));
+    int *s_ptr = s_col + cap;
+
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane / G, l = lane % G;
+    const int c0 = 2 * l;
+    const int ld = a.ld;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int nrows = min(rows_per_cta, a.n_rows - r0);
+
+    for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
+    __syncthreads();
+    const int kb = s_ptr[0];
+    const int cnt = s_ptr[nrows] - kb;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        s_col[k] = __ldg(a.indices + kb + k);
+        s_m[k] = __ldg(a.Mv + kb + k);
+        if (!PER_LEVEL) {
+            s_k[k] = __ldg(a.Kv + kb + k);
+            if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+        }
+    }
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const bool first = (l == 0), last = (l == G - 1);
+    const int N = a.N;
+    const bool in0 = c0 < N, in1 = c0 + 1 < N;
+
+    for (int base = wid * RPW; base < nrows; base += (blockDim.x >> 5) * RPW) {
+        const int lr_raw = base + sub;
+        const bool live = lr_raw < nrows;
+        const int lr = live ? lr_raw : nrows - 1;
+        const int r = r0 + lr;
+        const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
+        double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
+        for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
+            double2 xv[SCHUNK], xz[SCHUNK];
+#pragma unroll
+            for (int j = 0; j < SCHUNK; ++j) {
+                const int k = k0 + j;
+                const int c = (k < kend) ? s_col[k] : r;
+                const bool own = c < a.n_own_cols;
+                const double *pv = own ? a.xv + (size_t)c * ld : a.hv + (size_t)(c - a.n_own_cols) * ld;
+                const double *pz = own ? a.xz + (size_t)c * ld : a.hz + (size_t)(c - a.n_own_cols) * ld;
+                xv[j] = ldg2(pv + c0);
+                xz[j] = ldg2(pz + c0);
+            }
+#pragma unroll
+            for (int j = 0; j < SCHUNK; ++j) {
+                const int k = k0 + j;
+                if (k < kend) {
+                    const double m = s_m[k];
+                    mv0 = fma(m, xv[j].x, mv0);
+                    mv1 = fma(m, xv[j].y, mv1);
+                    mz0 = fma(m, xz[j].x, mz0);
+                    mz1 = fma(m, xz[j].y, mz1);
+                    if (!PER_LEVEL) {
+                        const double kk = s_k[k], kt = s_kt[k];
+                        kv0 = fma(kk, xv[j].x, kv0);
+                        kv1 = fma(kk, xv[j].y, kv1);
+                        kz0 = fma(kt, xz[j].x, kz0);
+                        kz1 = fma(kt, xz[j].y, kz1);
+                    } else {
+                        const double2 kk = ldg2(a.Kv + (size_t)(kb + k) * ld + c0);
+                        const double2 kt = ldg2(a.KTv + (size_t)(kb + k) * ld + c0);
+                        kv0 = fma(kk.x, xv[j].x, kv0);
+                        kv1 = fma(kk.y, xv[j].y, kv1);
+                        kz0 = fma(kt.x, xz[j].x, kz0);
+                        kz1 = fma(kt.y, xz[j].y, kz1);
+                    }
+                }
+            }
+        }
+        double y00, y01, y10, y11;
+        if (CN) {
+            const double h = 0.5 * a.tau, hb = h / a.beta;
+            double t;
+            t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+            t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
+            t = __shfl_down_sync(full, kz0, 1, G); const double kzn1 = last ? 0.0 : t;
+            t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+            double r00 = h * (mvp0 + mv0) + h * (kz0 + kz1) + mz0 - mz1;
+            double r01 = h * (mv0 + mv1) + h * (kz1 + kzn1) + mz1 - mzn1;
+            double r10 = h * (kvp0 + kv0) - mvp0 + mv0 - hb * (mz0 + mz1);
+            double r11 = h * (kv0 + kv1) - mv0 + mv1 - hb * (mz1 + mzn1);
+            if (!in0) { r00 = 0.0; r10 = 0.0; }
+            if (!in1) { r01 = 0.0; r11 = 0.0; }
+            t = __shfl_down_sync(full, r00, 1, G); const double r0n = last ? 0.0 : t;
+            t = __shfl_up_sync(full, r11, 1, G);   const double r1p = first ? 0.0 : t;
+            y00 = r00 + r01;
+            y01 = r01 + r0n;
+            y10 = r10 + r1p;
+            y11 = r11 + r10;
+        } else {
+            const double tau = a.tau, tb = tau / a.beta;
+            double t;
+            t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+            t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+            y00 = tau * kz0 + mz0 + ((c0 < N - 1) ? (tau * mv0 - mz1) : 0.0);
+            y01 = tau * kz1 + mz1 + ((c0 + 1 < N - 1) ? (tau * mv1 - mzn1) : 0.0);
+            y10 = tau * kv0 + mv0 + ((c0 >= 1) ? (-mvp0 - tb * mz0) : 0.0);
+            y11 = tau * kv1 + mv1 + (-mv0 - tb * mz1);
+        }
+        if (!in0) { y00 = 0.0; y10 = 0.0; }
+        if (!in1) { y01 = 0.0; y11 = 0.0; }
+        if (live) {
+            if (a.bcmask[r]) {
+                const double2 xv = ldg2(a.xv + (size_t)r * ld + c0);
+                const double2 xz = ldg2(a.xz + (size_t)r * ld + c0);
+                y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
+            }
+            *reinterpret_cast<double2 *>(a.y0 + (size_t)r * ld + c0) = make_double2(y00, y01);
+            *reinterpret_cast<double2 *>(a.y1 + (size_t)r * ld + c0) = make_double2(y10, y11);
+        }
+    }
+}
+
+template <bool CN, bool PER_LEVEL, bool SYM>
+void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, cudaStream_t s)
+{
+    const int blocks = ceil_div(a.n_rows, rows_per_cta);
+    const int nval = PER_LEVEL ? 1 : (SYM ? 2 : 3);
+    const size_t smem = (size_t)cap * (8 * nval + 4) + (size_t)(rows_per_cta + 1) * 4;
+    switch (G) {
+    case 4: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 4><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    case 8: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 8><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    case 16: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 16><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    default: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 32><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    }
+}
+
 template <bool CN, bool PER_LEVEL>
 void launch_g(const KktArgs &a, int G, cudaStream_t s)
 {
@@ -209,7 +368,23 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     a.tau = h->cfg.tau;
     a.beta = h->cfg.beta;
     const int G = h->ld / 2;
-    if (h->cfg.CN) {
+    // rows per CTA: as many consecutive rows as fit the shared-memory entry budget
+    const int max_len = std::max(1, h->max_row_len);
+    int rows_per_cta = std::min(64, (STAGE_CAP / max_len) / 8 * 8);
+    const bool staged = rows_per_cta >= 8 && !h->force_unstaged;
+    if (staged) {
+        const int cap = rows_per_cta * max_len;
+        const bool sym = h->d_KT == h->d_K;
+        if (h->cfg.CN) {
+            if (h->per_level) launch_staged<true, true, false>(a, G, rows_per_cta, cap, h->stream);
+            else if (sym) launch_staged<true, false, true>(a, G, rows_per_cta, cap, h->stream);
+            else launch_staged<true, false, false>(a, G, rows_per_cta, cap, h->stream);
+        } else {
+            if (h->per_level) launch_staged<false, true, false>(a, G, rows_per_cta, cap, h->stream);
+            else if (sym) launch_staged<false, false, true>(a, G, rows_per_cta, cap, h->stream);
+            else launch_staged<false, false, false>(a, G, rows_per_cta, cap, h->stream);
+        }
+    } else if (h->cfg.CN) {
         if (h->per_level) launch_g<true, true>(a, G, h->stream);
         else launch_g<true, false>(a, G, h->stream);
     } else {

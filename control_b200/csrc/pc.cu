@@ -1,0 +1,476 @@
+// In-built block preconditioner of Control.Instationary on the device
+// (Instationary.construct_pc -> pc_linear, control/control.py:1943-2440), wrapped as
+// Preconditioner.apply (preconditioner/preconditioner.py:562-656).
+//
+//   setup   once per matrix set: Jacobi diagonal of assemble(M, bcs); SELL copies of M and
+//           of the sub/super-diagonal blocks of L_hat; one AMG hierarchy per DISTINCT
+//           diagonal block (block_ii + shift M, assembled with bcs).  The reference
+//           re-assembles and re-sets-up each of them at every time step of every
+//           application (control/control.py:2056-2067 ...).
+//   apply   (1,1) block: batched Chebyshev/Jacobi in the time-fastest layout
+//           (pc_batched.cu); Schur block: right-hand side batched, then the forward and
+//           backward time sweeps on time-slowest columns, one AMG solve per step.  The
+//           sweeps are sequential in time as in the reference (control.py:2077, 2158) and
+//           are replayed from ONE CUDA graph (about 70 small kernels per time step).
+#include "pc.cuh"
+
+#include <cmath>
+#include <cstdlib>
+
+#include "cheb_coefficients.h"
+#include "vec_ops.cuh"
+
+namespace {
+
+// values of (w K_level(^T) + m_coef M) on the GLOBAL pattern, assembled with bcs when
+// `identity`: constrained rows and columns zeroed, unit diagonal (Firedrake's
+// assemble(a, bcs=...), control/control.py:2057-2059); otherwise rows and columns zeroed.
+void combine_global(ctl_handle_s *h, int level, bool transposed, double w, double m_coef, bool identity,
+                    std::vector<double> &out)
+{
+    const std::vector<int> &ip = h->h_indptr, &ix = h->h_indices;
+    const int lv = h->h_K.size() > 1 ? level : 0;
+    const std::vector<double> &Kv = h->h_K[lv];
+    const std::vector<double> *KTv = h->h_KT.empty() ? nullptr : &h->h_KT[lv];
+    out.assign(ix.size(), 0.0);
+    for (int r = 0; r < h->n; ++r) {
+        for (int k = ip[r]; k < ip[r + 1]; ++k) {
+            const int c = ix[k];
+            if (h->h_bcmask[r] || h->h_bcmask[c]) {
+                out[k] = (identity && r == c) ? 1.0 : 0.0;
+                continue;
+            }
+            double kv = 0.0;
+            if (w != 0.0) {
+                if (!transposed) kv = Kv[k];
+                else if (KTv) kv = (*KTv)[k];
+                else {
+                    // entry (c, r) of the structurally symmetric pattern
+                    const int *b = ix.data() + ip[c], *e = ix.data() + ip[c + 1];
+                    const int *f = std::lower_bound(b, e, r);
+                    kv = Kv[f - ix.data()];
+                }
+            }
+            out[k] = w * kv + m_coef * h->h_M[k];
+        }
+    }
+}
+
+HostCSR global_csr(ctl_handle_s *h, const std::vector<double> &vals)
+{
+    HostCSR A;
+    A.n_rows = A.n_cols = h->n;
+    A.indptr = h->h_indptr;
+    A.indices = h->h_indices;
+    A.values = vals;
+    return A;
+}
+
+// restrict global-pattern values to this rank's rows (local entry order)
+std::vector<double> local_values(ctl_handle_s *h, const std::vector<double> &global_vals)
+{
+    std::vector<double> v(h->loc_entry.size());
+    for (size_t p = 0; p < v.size(); ++p) v[p] = global_vals[h->loc_entry[p]];
+    return v;
+}
+
+}  // namespace
+
+void ctl_pc_free(ctl_handle_s *h)
+{
+    if (!h->pc) return;
+    PcState &st = *h->pc;
+    if (st.sweep_graph) cudaGraphExecDestroy(st.sweep_graph);
+    for (auto &H : st.hier) amg_free(H);
+    for (auto &m : st.off) sell_free(m);
+    sell_free(st.Msell);
+    cudaFree(st.d_mass_dinv);
+    cudaFree(st.B);
+    cudaFree(st.Uf);
+    cudaFree(st.Ub);
+    h->pc.reset();
+}
+
+int ctl_pc_invalidate(ctl_handle_s *h)
+{
+    ctl_pc_free(h);
+    return CTL_OK;
+}
+
+static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
+{
+    const int N = h->N;
+    const size_t S = st.ts_stride;
+    const bool cn = h->cfg.CN != 0;
+    const double tau = h->cfg.tau, eps = h->cfg.epsilon;
+    // forward sweep (control/control.py:2053-2116 CN, 2241-2328 BE)
+    for (int i = 0; i < N; ++i) {
+        double *bi = st.B + i * S;
+        if (i > 0) {
+            const double *up = st.Uf + (i - 1) * S;
+            if (cn) CTL_TRY(sell_spmv(h, st.off[st.fwd_off[i]], up, bi, nullptr, SELL_SUB));
+            else CTL_TRY(sell_spmv(h, st.Msell, up, bi, nullptr, SELL_ADD));     // b_i -= (-M) u_{i-1}
+        }
+        CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], bi, st.Uf + i * S));
+    }
+    // middle scaling fused with the backward right-hand sides
+    // (control/control.py:2118-2133 + 2158-2168 CN; 2330-2350 + 2375-2385 BE)
+    for (int i = N - 1; i >= 0; --i) {
+        double *bi = st.B + i * S;
+        const double *ui = st.Uf + i * S;
+        const double *un = i + 1 < N ? st.Ub + (i + 1) * S : nullptr;
+        if (cn) {
+            // b_i = tau/2 M (T_2 u)_i - (L_hat^T)_{i,i+1} u_{i+1}; the block-diagonal variant has
+            // no T_2 / T_2^-1 pair (oracle/pc.py::construct_pc_diagonal)
+            const bool t2 = st.opts.mode == CTL_PCMODE_TRIANGULAR;
+            const double *up = (t2 && i > 0) ? st.Uf + (i - 1) * S : nullptr;
+            const SellMat &offm = un ? st.off[st.bwd_off[i]] : st.Msell;
+            CTL_TRY(sell_spmv2(h, st.Msell, offm, ui, up, un, bi, 0.5 * tau, -1.0));
+        } else {
+            // b_i = tau M u_i (eps tau for the last block) - (-M) u_{i+1}
+            const double a = (i == N - 1) ? eps * tau : tau;
+            CTL_TRY(sell_spmv2(h, st.Msell, st.Msell, ui, nullptr, un, bi, a, 1.0));
+        }
+        CTL_TRY(amg_solve(h, st.hier[st.bwd_h[i]], bi, st.Ub + i * S));
+    }
+    return CTL_OK;
+}
+
+static int run_sweeps(ctl_handle_s *h, PcState &st)
+{
+    if (!st.use_graph) return enqueue_sweeps(h, st);
+    if (!st.sweep_graph) {
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        CTL_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+        const int rc = enqueue_sweeps(h, st);
+        const cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (rc != CTL_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (e != cudaSuccess) {
+            ctl_set_error(h, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+            return CTL_ERR_CUDA;
+        }
+        CTL_CUDA(cudaGraphInstantiate(&st.sweep_graph, graph, 0));
+        cudaGraphDestroy(graph);
+        st.sweep_launches = h->launches - before;
+        h->launches = before;
+    }
+    CTL_CUDA(cudaGraphLaunch(st.sweep_graph, h->stream));
+    h->launches += st.sweep_launches;
+    return CTL_OK;
+}
+
+// pc_fn(u_0, u_1, b_0, b_1) on time-fastest vectors.  wrap != 0 adds the nullspace handling
+// of Preconditioner.apply: constrained entries of u take the values of b.
+static int pc_fn_tf(ctl_handle_s *h, const double *b, double *u, bool wrap)
+{
+    CTL_CHECK(h->pc && h->pc->ready, CTL_ERR_STATE, "preconditioner: call ctl_pc_setup first");
+    PcState &st = *h->pc;
+    const size_t panel = (size_t)h->n_loc * h->ld;
+    const double *b0 = b, *b1 = b + panel;
+    double *u0 = u, *u1 = u + panel;
+    const bool cn = h->cfg.CN != 0;
+    const double tau = h->cfg.tau;
+    double *s1 = nullptr, *s2 = nullptr;
+    CTL_TRY(ctl_scratch_get(h, &s1));
+    CTL_TRY(ctl_scratch_get(h, &s2));
+    double *btil = s1, *pa = s1 + panel, *pb = s2, *rhs = s2 + panel;
+    int rc = CTL_OK;
+    do {
+        // ---- (1,1) block: control/control.py:1997-2014 (CN), 2193-2206 (BE)
+        const double *p_fin = nullptr;
+        if (st.opts.solver_0 == CTL_S0_CHEBYSHEV) {
+            double scale;
+            std::vector<double> om;
+            cheb_coefficients(st.opts.cheb_emin, st.opts.cheb_emax, st.opts.cheb_steps, &scale, om);
+            double *buf[2] = {pa, pb};
+            if ((rc = pcb_u0_first(h, b0, st.d_mass_dinv, btil, buf[1], scale)) != CTL_OK) break;
+            for (int k = 2; k <= st.opts.cheb_steps && rc == CTL_OK; ++k) {
+                const double w = om[k - 2];
+                if (h->n_halo > 0) rc = ctl_halo_exchange(h, buf[(k - 1) & 1]);
+                if (rc != CTL_OK) break;
+                rc = pcb_cheb_step(h, st.d_mass_dinv, btil, k == 2 ? nullptr : buf[k & 1], buf[(k - 1) & 1],
+                                   buf[k & 1], k == 2 ? 0.0 : 1.0 - w, w, w * scale);
+            }
+            if (rc != CTL_OK) break;
+            p_fin = buf[st.opts.cheb_steps & 1];
+        } else if (st.opts.solver_0 == CTL_S0_JACOBI) {
+            if ((rc = pcb_u0_first(h, b0, st.d_mass_dinv, btil, pa, 1.0)) != CTL_OK) break;
+            p_fin = pa;
+        } else {
+            // Multigrid=True: AMG on assemble(M, bcs), column by column
+            if ((rc = pcb_u0_first(h, b0, st.d_mass_dinv, btil, pa, 1.0)) != CTL_OK) break;
+            if ((rc = pcb_panel_to_ts(h, btil, st.B, st.ts_stride)) != CTL_OK) break;
+            for (int i = 0; i < h->N && rc == CTL_OK; ++i)
+                rc = amg_solve(h, st.hier[st.h_mass], st.B + i * st.ts_stride, st.Uf + i * st.ts_stride);
+            if (rc != CTL_OK) break;
+            if ((rc = pcb_ts_to_panel(h, st.Uf, pa, st.ts_stride)) != CTL_OK) break;
+            p_fin = pa;
+        }
+        const double sc = cn ? 2.0 / tau : 1.0 / tau;
+        const double sc_last = cn ? sc : 1.0 / (tau * h->cfg.epsilon);
+        if ((rc = pcb_u0_final(h, p_fin, wrap ? b0 : nullptr, u0, sc, sc_last)) != CTL_OK) break;
+        // ---- Schur block right-hand side: control/control.py:2016-2053 (CN), 2208-2237 (BE)
+        if (st.opts.mode == CTL_PCMODE_TRIANGULAR) {
+            // u0 has b's values on constrained rows when wrapping; the products must see
+            // zeros there: the value arrays have constrained COLUMNS eliminated, so they do
+            if (h->n_halo > 0 && (rc = ctl_halo_exchange(h, u0)) != CTL_OK) break;
+            rc = pcb_schur_rhs(h, u0, b1, rhs);
+        } else {
+            rc = pcb_schur_rhs(h, nullptr, b1, rhs);
+        }
+        if (rc != CTL_OK) break;
+        if ((rc = pcb_panel_to_ts(h, rhs, st.B, st.ts_stride)) != CTL_OK) break;
+        // ---- forward / backward time sweeps
+        if ((rc = run_sweeps(h, st)) != CTL_OK) break;
+        if ((rc = pcb_ts_to_panel(h, st.Ub, u1, st.ts_stride)) != CTL_OK) break;
+        rc = pcb_bc_fixup(h, h->d_bc_rows_all, h->n_bc_all, wrap ? b1 : nullptr, u1);
+    } while (0);
+    ctl_scratch_put(h, s1);
+    ctl_scratch_put(h, s2);
+    return rc;
+}
+
+int ctl_pc_apply_tf(ctl_handle_s *h, const double *b_tf, double *u_tf) { return pc_fn_tf(h, b_tf, u_tf, true); }
+
+static int pc_entry(ctl_handle_s *h, const double *b, double *u, int layout, bool wrap)
+{
+    CTL_CHECK(h && b && u, CTL_ERR_ARG, "ctl_pc_apply: null argument");
+    CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_pc_apply: ctl_assemble has not been called");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    if (layout == CTL_LAYOUT_TIME_FASTEST) return pc_fn_tf(h, b, u, wrap);
+    double *bt = nullptr, *ut = nullptr;
+    CTL_TRY(ctl_scratch_get(h, &bt));
+    CTL_TRY(ctl_scratch_get(h, &ut));
+    int rc = ctl_to_tf(h, b, bt);
+    if (rc == CTL_OK) rc = pc_fn_tf(h, bt, ut, wrap);
+    if (rc == CTL_OK) rc = ctl_to_bm(h, ut, u);
+    ctl_scratch_put(h, bt);
+    ctl_scratch_put(h, ut);
+    return rc;
+}
+
+extern "C" {
+
+int ctl_pc_default_options(ctl_pc_options *o)
+{
+    if (!o) return CTL_ERR_ARG;
+    AmgParams d;
+    o->mode = CTL_PCMODE_TRIANGULAR;
+    o->solver_0 = CTL_S0_JACOBI;
+    o->cheb_emin = 0.0;
+    o->cheb_emax = 0.0;
+    o->cheb_steps = 20;                  // "ksp_max_it": 20, control/control.py:1980
+    o->amg_cycles = d.cycles;            // "pc_hypre_boomeramg_max_iter": 2, control/control.py:2065
+    o->amg_nu = d.nu;
+    o->amg_max_levels = d.max_levels;
+    o->amg_coarse_max = d.coarse_max;
+    o->amg_theta = d.theta;
+    o->amg_lo = d.lo;
+    o->amg_hi = d.hi;
+    return CTL_OK;
+}
+
+int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
+{
+    CTL_CHECK(h && opts, CTL_ERR_ARG, "ctl_pc_setup: null argument");
+    CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_pc_setup: ctl_assemble has not been called");
+    CTL_CHECK(opts->mode == CTL_PCMODE_TRIANGULAR || opts->mode == CTL_PCMODE_DIAGONAL, CTL_ERR_ARG,
+              "ctl_pc_setup: unknown mode");
+    CTL_CHECK(opts->solver_0 >= CTL_S0_JACOBI && opts->solver_0 <= CTL_S0_AMG, CTL_ERR_ARG,
+              "ctl_pc_setup: unknown solver_0");
+    if (opts->solver_0 == CTL_S0_CHEBYSHEV)
+        CTL_CHECK(opts->cheb_emax > opts->cheb_emin && opts->cheb_emin > 0 && opts->cheb_steps >= 1, CTL_ERR_ARG,
+                  "ctl_pc_setup: Chebyshev needs 0 < e_min < e_max and at least one step");
+    CTL_CHECK(opts->amg_cycles >= 1 && opts->amg_nu >= 1 && opts->amg_max_levels >= 1, CTL_ERR_ARG,
+              "ctl_pc_setup: bad AMG options");
+    if (opts->mode == CTL_PCMODE_DIAGONAL)
+        CTL_CHECK(h->cfg.CN && !h->per_level && h->k_symmetric, CTL_ERR_ARG,
+                  "ctl_pc_setup: the block-diagonal (MINRES) variant needs CN and a time-independent symmetric K");
+    CTL_CHECK(h->cfg.world == 1, CTL_ERR_STATE, "ctl_pc_setup: multi-rank preconditioner not available in this build");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    ctl_pc_free(h);
+    h->pc = std::make_shared<PcState>();
+    PcState &st = *h->pc;
+    st.opts = *opts;
+    st.amg.theta = opts->amg_theta;
+    st.amg.max_levels = opts->amg_max_levels;
+    st.amg.coarse_max = opts->amg_coarse_max;
+    st.amg.nu = opts->amg_nu;
+    st.amg.lo = opts->amg_lo;
+    st.amg.hi = opts->amg_hi;
+    st.amg.cycles = opts->amg_cycles;
+    if (const char *e = getenv("CTL_NO_GRAPH")) st.use_graph = !(e[0] == '1');
+
+    const int N = h->N, nl = h->n_loc, rb = h->row_begin;
+    const bool cn = h->cfg.CN != 0;
+    const double tau = h->cfg.tau, beta = h->cfg.beta, eps = h->cfg.epsilon;
+
+    // Jacobi diagonal of assemble(M, bcs) and the list of constrained rows
+    {
+        std::vector<double> dinv(nl);
+        for (int r = 0; r < nl; ++r) {
+            const int g = rb + r;
+            if (h->h_bcmask[g]) {
+                dinv[r] = 1.0;
+                continue;
+            }
+            double d = 0.0;
+            for (int k = h->h_indptr[g]; k < h->h_indptr[g + 1]; ++k)
+                if (h->h_indices[k] == g) d = h->h_M[k];
+            CTL_CHECK(d != 0.0, CTL_ERR_ARG, "ctl_pc_setup: mass matrix has a zero diagonal entry");
+            dinv[r] = 1.0 / d;
+        }
+        CTL_TRY(ctl_upload(h, &st.d_mass_dinv, dinv.data(), dinv.size()));
+    }
+
+    CTL_TRY(sell_build_pattern(h, h->loc, st.fine));
+    std::vector<double> vals;
+    combine_global(h, 0, false, 0.0, 1.0, false, vals);
+    {
+        const std::vector<double> lv = local_values(h, vals);
+        CTL_TRY(sell_set_values(h, st.fine, lv.data(), st.Msell));
+    }
+
+    // distinct diagonal blocks -> AMG hierarchies; distinct off-diagonal blocks -> SELL
+    const bool per_level = h->h_K.size() > 1;
+    const bool sym = h->k_symmetric;
+    std::map<std::tuple<int, int, double>, int> hier_index, off_index;
+    auto get_hier = [&](int level, bool transposed, double shift, double w, int *out) -> int {
+        const auto key = std::make_tuple(per_level ? level : -1, (transposed && !sym) ? 1 : 0, shift);
+        auto it = hier_index.find(key);
+        if (it != hier_index.end()) {
+            *out = it->second;
+            return CTL_OK;
+        }
+        std::vector<double> v;
+        combine_global(h, level, transposed && !sym, w, 1.0 + shift, true, v);
+        st.hier.emplace_back();
+        CTL_TRY(amg_build(h, global_csr(h, v), st.amg, st.fine, st.hier.back()));
+        *out = hier_index[key] = (int)st.hier.size() - 1;
+        return CTL_OK;
+    };
+    auto get_off = [&](int level, bool transposed, double w, double m_coef, int *out) -> int {
+        const auto key = std::make_tuple(per_level ? level : -1, (transposed && !sym) ? 1 : 0, m_coef);
+        auto it = off_index.find(key);
+        if (it != off_index.end()) {
+            *out = it->second;
+            return CTL_OK;
+        }
+        std::vector<double> v;
+        combine_global(h, level, transposed && !sym, w, m_coef, false, v);
+        const std::vector<double> lv = local_values(h, v);
+        st.off.emplace_back();
+        CTL_TRY(sell_set_values(h, st.fine, lv.data(), st.off.back()));
+        *out = off_index[key] = (int)st.off.size() - 1;
+        return CTL_OK;
+    };
+
+    st.fwd_h.assign(N, -1);
+    st.bwd_h.assign(N, -1);
+    st.fwd_off.assign(N, -1);
+    st.bwd_off.assign(N, -1);
+    if (cn) {
+        const double w = 0.5 * tau, c = 0.5 * tau / std::sqrt(beta);     // my_const, control.py:2051
+        for (int i = 0; i < N; ++i) {
+            // forward: block_10[(i,i)] + c M = w K_{i+1} + (1+c) M; block_10[(i,i-1)] + c M = w K_i + (c-1) M
+            CTL_TRY(get_hier(i + 1, false, c, w, &st.fwd_h[i]));
+            if (i > 0) CTL_TRY(get_off(i, false, w, c - 1.0, &st.fwd_off[i]));
+            // backward: block_01[(i,i)] + c M = w K_i^T + (1+c) M; block_01[(i,i+1)] + c M = w K_{i+1}^T + (c-1) M
+            CTL_TRY(get_hier(i, true, c, w, &st.bwd_h[i]));
+            if (i + 1 < N) CTL_TRY(get_off(i + 1, true, w, c - 1.0, &st.bwd_off[i]));
+        }
+    } else {
+        const double s = tau / std::sqrt(beta), se = std::sqrt(eps) * s;
+        for (int i = 0; i < N; ++i) {
+            const double sf = (i == 0) ? 0.0 : (i < N - 1 ? s : se);     // control.py:2243, 2279, 2312
+            const double sb = (i == N - 1) ? se : (i > 0 ? s : 0.0);     // control.py:2358, 2391, 2422
+            CTL_TRY(get_hier(i, false, sf, tau, &st.fwd_h[i]));
+            CTL_TRY(get_hier(i, true, sb, tau, &st.bwd_h[i]));
+        }
+    }
+    if (opts->solver_0 == CTL_S0_AMG) {
+        std::vector<double> v;
+        combine_global(h, 0, false, 0.0, 1.0, true, v);
+        st.hier.emplace_back();
+        CTL_TRY(amg_build(h, global_csr(h, v), st.amg, st.fine, st.hier.back()));
+        st.h_mass = (int)st.hier.size() - 1;
+    }
+
+    st.ts_stride = (size_t)nl + h->n_halo;
+    const size_t ts_bytes = (size_t)N * st.ts_stride * sizeof(double);
+    CTL_CUDA(cudaMalloc((void **)&st.B, ts_bytes));
+    CTL_CUDA(cudaMalloc((void **)&st.Uf, ts_bytes));
+    CTL_CUDA(cudaMalloc((void **)&st.Ub, ts_bytes));
+    CTL_CUDA(cudaMemsetAsync(st.B, 0, ts_bytes, h->stream));
+    CTL_CUDA(cudaMemsetAsync(st.Uf, 0, ts_bytes, h->stream));
+    CTL_CUDA(cudaMemsetAsync(st.Ub, 0, ts_bytes, h->stream));
+    CTL_CUDA(cudaStreamSynchronize(h->stream));
+    st.ready = true;
+    return CTL_OK;
+}
+
+int ctl_pc_apply(ctl_handle h, const double *b, double *u, int layout) { return pc_entry(h, b, u, layout, true); }
+
+int ctl_pc_fn(ctl_handle h, const double *b, double *u, int layout) { return pc_entry(h, b, u, layout, false); }
+
+int ctl_set_pc_callback(ctl_handle h, ctl_pc_callback fn, void *user)
+{
+    CTL_CHECK(h, CTL_ERR_ARG, "ctl_set_pc_callback: null handle");
+    h->pc_cb = fn;
+    h->pc_cb_user = user;
+    return CTL_OK;
+}
+
+// ---- AMG introspection
+int32_t ctl_amg_num_hierarchies(ctl_handle h) { return (h && h->pc) ? (int32_t)h->pc->hier.size() : 0; }
+
+int32_t ctl_amg_num_levels(ctl_handle h, int32_t hi)
+{
+    if (!h || !h->pc || hi < 0 || hi >= (int)h->pc->hier.size()) return 0;
+    return (int32_t)h->pc->hier[hi].host.size();
+}
+
+#define AMG_LEVEL(h, hi, lvl)                                                                         \
+    CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && lvl >= 0 &&                     \
+                  lvl < (int)h->pc->hier[hi].host.size(),                                              \
+              CTL_ERR_ARG, "AMG introspection: bad hierarchy / level");                                \
+    const AmgLevelHost &L = h->pc->hier[hi].host[lvl]
+
+int ctl_amg_level_size(ctl_handle h, int32_t hi, int32_t lvl, int32_t *n, int64_t *nnz_A, int64_t *nnz_P)
+{
+    AMG_LEVEL(h, hi, lvl);
+    if (n) *n = L.A.n_rows;
+    if (nnz_A) *nnz_A = L.A.nnz();
+    if (nnz_P) *nnz_P = L.P.nnz();
+    return CTL_OK;
+}
+
+int ctl_amg_get_csr(ctl_handle h, int32_t hi, int32_t lvl, int which, int32_t *indptr, int32_t *indices, double *values)
+{
+    AMG_LEVEL(h, hi, lvl);
+    const HostCSR &A = which == 0 ? L.A : L.P;
+    std::copy(A.indptr.begin(), A.indptr.end(), indptr);
+    std::copy(A.indices.begin(), A.indices.end(), indices);
+    std::copy(A.values.begin(), A.values.end(), values);
+    return CTL_OK;
+}
+
+int ctl_amg_get_aggregates(ctl_handle h, int32_t hi, int32_t lvl, int32_t *agg)
+{
+    AMG_LEVEL(h, hi, lvl);
+    std::copy(L.agg.begin(), L.agg.end(), agg);
+    return CTL_OK;
+}
+
+int ctl_amg_solve(ctl_handle h, int32_t hi, const double *b, double *x)
+{
+    CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && b && x, CTL_ERR_ARG, "ctl_amg_solve: bad argument");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    return amg_solve(h, h->pc->hier[hi], b, x);
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// SELL-32 construction and the single-column SpMV kernel family (see sell.cuh).
+// All kernels: one thread per row, 128 threads per CTA, HBM/L2-bound streaming of
+// (4 + 8) bytes per stored entry plus the gathered x.
+#include <algorithm>
+
+#include "sell.cuh"
+
+SellPattern::~SellPattern()
+{
+    cudaFree(slice_ptr);
+    cudaFree(cols);
+}
+
+void sell_free(SellMat &m)
+{
+    cudaFree(m.vals);
+    m.vals = nullptr;
+    m.pat.reset();
+}
+
+int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPattern> &out)
+{
+    auto p = std::make_shared<SellPattern>();
+    p->n_rows = A.n_rows;
+    p->n_cols = A.n_cols;
+    p->n_slices = ceil_div(A.n_rows, 32);
+    p->nnz = A.nnz();
+    std::vector<int> sptr(p->n_slices + 1, 0);
+    for (int s = 0; s < p->n_slices; ++s) {
+        int w = 0;
+        for (int r = 32 * s; r < std::min(A.n_rows, 32 * s + 32); ++r) w = std::max(w, A.indptr[r + 1] - A.indptr[r]);
+        sptr[s + 1] = sptr[s] + 32 * w;
+    }
+    p->n_stored = sptr[p->n_slices];
+    std::vector<int> cols((size_t)p->n_stored);
+    p->csr_to_sell.resize(A.nnz());
+    for (int s = 0; s < p->n_slices; ++s) {
+        const int w = (sptr[s + 1] - sptr[s]) / 32;
+        for (int lane = 0; lane < 32; ++lane) {
+            const int r = 32 * s + lane;
+            const int len = r < A.n_rows ? A.indptr[r + 1] - A.indptr[r] : 0;
+            for (int k = 0; k < w; ++k) {
+                const int64_t pos = (int64_t)sptr[s] + 32 * k + lane;
+                if (k < len) {
+                    cols[pos] = A.indices[A.indptr[r] + k];
+                    p->csr_to_sell[A.indptr[r] + k] = pos;
+                } else {
+                    cols[pos] = r < A.n_rows ? std::min(r, A.n_cols - 1) : 0;
+                }
+            }
+        }
+    }
+    CTL_TRY(ctl_upload(h, &p->slice_ptr, sptr.data(), sptr.size()));
+    CTL_TRY(ctl_upload(h, &p->cols, cols.data(), cols.size()));
+    out = p;
+    return CTL_OK;
+}
+
+int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values,
+                    SellMat &out)
+{
+    std::vector<double> v((size_t)pat->n_stored, 0.0);
+    for (size_t k = 0; k < pat->csr_to_sell.size(); ++k) v[pat->csr_to_sell[k]] = csr_values[k];
+    out.pat = pat;
+    CTL_TRY(ctl_upload(h, &out.vals, v.data(), v.size()));
+    return CTL_OK;
+}
+
+namespace {
+
+constexpr int ST = 128;
+
+__device__ __forceinline__ double sell_row_dot(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
+                                               const double *__restrict__ vals, const double *__restrict__ x,
+                                               int row)
+{
+    const int s = row >> 5, lane = row & 31;
+    const int beg = __ldg(slice_ptr + s), end = __ldg(slice_ptr + s + 1);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int p = beg + lane; p < end; p += 32) acc = fma(__ldg(vals + p), __ldg(x + __ldg(cols + p)), acc);
+    return acc;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ST) sell_spmv_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      const double *b, double *y, int n_rows)
+{
+    const int row = blockIdx.x * ST + threadIdx.x;
+    if (row >= n_rows) return;
+    const double ax = sell_row_dot(slice_ptr, cols, vals, x, row);
+    if (MODE == SELL_ASSIGN) y[row] = ax;
+    else if (MODE == SELL_RESIDUAL) y[row] = b[row] - ax;
+    else if (MODE == SELL_ADD) y[row] += ax;
+    else y[row] -= ax;
+}
+
+__global__ void __launch_bounds__(ST) sell_cheb_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
+                                                      const double *__restrict__ vals, const double *__restrict__ dinv,
+                                                      const double *__restrict__ b, const double *p_prev,
+                                                      const double *__restrict__ p_cur, double *out, double a,
+                                                      double bq, double c, int n_rows)
+{
+    const int row = blockIdx.x * ST + threadIdx.x;
+    if (row >= n_rows) return;
+    const double ax = sell_row_dot(slice_ptr, cols, vals, p_cur, row);
+    double r = bq * p_cur[row] + c * dinv[row] * (b[row] - ax);
+    if (a != 0.0) r = fma(a, p_prev[row], r);
+    out[row] = r;
+}
+
+__global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
+                                                       double *__restrict__ out, double c, int n)
+{
+    const int i = blockIdx.x * ST + threadIdx.x;
+    if (i < n) out[i] = c * dinv[i] * b[i];
+}
+
+// one warp per row of a small dense matrix
+__global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
+                                                       double *__restrict__ y, int n)
+{
+    const int row = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    double acc = 0.0;
+    for (int j = lane; j < n; j += 32) acc = fma(A[(size_t)row * n + j], b[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = acc;
+}
+
+__global__ void __launch_bounds__(ST) sell_spmv2_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
+                                                       const double *__restrict__ v1, const double *__restrict__ v2,
+                                                       const double *__restrict__ x1, const double *__restrict__ x2,
+                                                       const double *__restrict__ x3, double *__restrict__ y,
+                                                       double alpha, double beta, int n_rows)
+{
+    const int row = blockIdx.x * ST + threadIdx.x;
+    if (row >= n_rows) return;
+    const int s = row >> 5, lane = row & 31;
+    const int beg = __ldg(slice_ptr + s), end = __ldg(slice_ptr + s + 1);
+    double acc1 = 0.0, acc2 = 0.0;
+    for (int p = beg + lane; p < end; p += 32) {
+        const int c = __ldg(cols + p);
+        double xa = __ldg(x1 + c);
+        if (x2) xa += __ldg(x2 + c);
+        acc1 = fma(__ldg(v1 + p), xa, acc1);
+        if (x3) acc2 = fma(__ldg(v2 + p), __ldg(x3 + c), acc2);
+    }
+    y[row] = alpha * acc1 + beta * acc2;
+}
+
+}  // namespace
+
+int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
+{
+    const SellPattern &p = *A.pat;
+    const int blocks = ceil_div(p.n_rows, ST);
+    if (blocks == 0) return CTL_OK;
+    switch (mode) {
+    case SELL_ASSIGN: sell_spmv_kernel<SELL_ASSIGN><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    case SELL_RESIDUAL: sell_spmv_kernel<SELL_RESIDUAL><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    case SELL_ADD: sell_spmv_kernel<SELL_ADD><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    default: sell_spmv_kernel<SELL_SUB><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    }
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const double *b,
+                   const double *p_prev, const double *p_cur, double *out, double a, double bq, double c)
+{
+    const SellPattern &p = *A.pat;
+    const int blocks = ceil_div(p.n_rows, ST);
+    if (blocks == 0) return CTL_OK;
+    sell_cheb_kernel<<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, dinv, b, p_prev, p_cur, out, a,
+                                                   bq, c, p.n_rows);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n)
+{
+    if (n == 0) return CTL_OK;
+    dinv_scale_kernel<<<ceil_div(n, ST), ST, 0, h->stream>>>(dinv, b, out, c, n);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
+{
+    if (n == 0) return CTL_OK;
+    dense_gemv_kernel<<<ceil_div(n, ST / 32), ST, 0, h->stream>>>(Ainv, b, y, n);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const double *x1, const double *x2,
+               const double *x3, double *y, double alpha, double beta)
+{
+    const SellPattern &p = *A1.pat;
+    const int blocks = ceil_div(p.n_rows, ST);
+    if (blocks == 0) return CTL_OK;
+    sell_spmv2_kernel<<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A1.vals, A2.vals, x1, x2, x3, y, alpha,
+                                                    beta, p.n_rows);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}

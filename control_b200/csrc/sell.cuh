@@ -1,0 +1,54 @@
+// SELL-32 matrices and the single-column SpMV kernel family (sell.cu).
+//
+// Every product inside the time sweeps and the AMG V-cycles acts on ONE spatial vector
+// (SURVEY.md rows K8, K9), so rows cannot be spread over a warp the way the time-batched
+// kernels do.  Sliced ELLPACK with slice height 32 gives one row per thread with fully
+// coalesced index/value loads: entry k of row r is stored at slice_ptr[r / 32] + 32 k +
+// r % 32.  Padding entries have value 0 and the row's own index as column.
+#pragma once
+#include <memory>
+
+#include "common.cuh"
+
+struct SellPattern {
+    int n_rows = 0, n_cols = 0, n_slices = 0;
+    int64_t n_stored = 0, nnz = 0;
+    int *slice_ptr = nullptr;          // device, n_slices + 1
+    int *cols = nullptr;               // device, n_stored
+    std::vector<int64_t> csr_to_sell;  // host: CSR entry -> stored position
+    ~SellPattern();
+};
+
+struct SellMat {
+    std::shared_ptr<SellPattern> pat;
+    double *vals = nullptr;            // device, n_stored (owned)
+    bool valid() const { return pat && vals; }
+};
+
+// build the pattern from a host CSR (column indices need not be sorted)
+int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPattern> &out);
+// lay one value set (CSR order, host) out on a pattern
+int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values,
+                    SellMat &out);
+void sell_free(SellMat &m);
+
+enum SellMode {
+    SELL_ASSIGN = 0,      // y  = A x
+    SELL_RESIDUAL = 1,    // y  = b - A x
+    SELL_ADD = 2,         // y += A x
+    SELL_SUB = 3          // y -= A x
+};
+int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode);
+
+// Chebyshev / Jacobi step: out = a * p_prev + bq * p_cur + c * dinv .* (b - A p_cur)
+// (p_prev may be null when a == 0; out may alias p_prev)
+int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const double *b,
+                   const double *p_prev, const double *p_cur, double *out, double a, double bq, double c);
+// out = c * dinv .* b   (first step from a zero guess)
+int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n);
+// y = Ainv b, dense row-major n x n
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n);
+// two-matrix product on one shared pattern (backward-sweep right-hand side, pc.cu):
+//   y = alpha * A1 (x1 + x2) + beta * A2 x3      (x2, x3 may be null)
+int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const double *x1, const double *x2,
+               const double *x3, double *y, double alpha, double beta);

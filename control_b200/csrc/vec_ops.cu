@@ -17,6 +17,7 @@ namespace {
 
 constexpr int RB = 1024;            // reduction grid (blocks), >= 148 * resident CTAs
 constexpr int RT = 256;             // threads per block
+constexpr int MAXK = 256;           // most vectors in one multi-dot / maxpy (GMRES restart + 2)
 
 __device__ __forceinline__ double warp_sum(double v)
 {
@@ -160,14 +161,14 @@ int grid_for(int64_t len2)
 
 int vec_workspace(ctl_handle_s *h, double **partials, double **scalars)
 {
-    // lives with the handle: 64 * RB partials + 64 result slots (+64 sqrt slots)
+    // lives with the handle: MAXK * RB partials + 2 * MAXK scalar slots
     static_assert(RB >= 1, "");
     if (!h->d_red) {
-        CTL_CUDA(cudaMalloc((void **)&h->d_red, (size_t)(64 * RB + 128) * sizeof(double)));
-        CTL_CUDA(cudaMallocHost((void **)&h->h_red, 128 * sizeof(double)));
+        CTL_CUDA(cudaMalloc((void **)&h->d_red, (size_t)(MAXK * RB + 2 * MAXK) * sizeof(double)));
+        CTL_CUDA(cudaMallocHost((void **)&h->h_red, 2 * MAXK * sizeof(double)));
     }
     *partials = h->d_red;
-    *scalars = h->d_red + 64 * RB;
+    *scalars = h->d_red + MAXK * RB;
     return CTL_OK;
 }
 
@@ -200,7 +201,7 @@ int vec_multi_dot_dev(ctl_handle_s *h, const double *const *V, int k, const doub
 {
     double *partials, *scalars;
     CTL_TRY(vec_workspace(h, &partials, &scalars));
-    CTL_CHECK(k <= 64, CTL_ERR_ARG, "vec_multi_dot: too many vectors");
+    CTL_CHECK(k <= MAXK, CTL_ERR_ARG, "vec_multi_dot: too many vectors");
     const int64_t len2 = len / 2;
     const int nb = grid_for(len2);
     for (int j0 = 0; j0 < k; j0 += 8) {
@@ -269,13 +270,13 @@ int vec_maxpy_host(ctl_handle_s *h, double *w, const double *const *V, int k, co
 {
     double *partials, *scalars;
     CTL_TRY(vec_workspace(h, &partials, &scalars));
-    CTL_CHECK(k <= 64, CTL_ERR_ARG, "vec_maxpy: too many vectors");
+    CTL_CHECK(k <= MAXK, CTL_ERR_ARG, "vec_maxpy: too many vectors");
     // stage the coefficients in the second half of the scalar area
     CTL_CUDA(cudaStreamSynchronize(h->stream));
-    memcpy(h->h_red + 64, coef_host, k * sizeof(double));
-    CTL_CUDA(cudaMemcpyAsync(scalars + 64, h->h_red + 64, k * sizeof(double), cudaMemcpyHostToDevice,
+    memcpy(h->h_red + MAXK, coef_host, k * sizeof(double));
+    CTL_CUDA(cudaMemcpyAsync(scalars + MAXK, h->h_red + MAXK, k * sizeof(double), cudaMemcpyHostToDevice,
                              h->stream));
-    return vec_maxpy_dev(h, w, V, k, scalars + 64, sign, len, nullptr, nullptr);
+    return vec_maxpy_dev(h, w, V, k, scalars + MAXK, sign, len, nullptr, nullptr);
 }
 
 int vec_read_scalars(ctl_handle_s *h, const double *dev, int k, double *host_out)

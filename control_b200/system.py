@@ -95,7 +95,9 @@ class MultiBlockSystem:
         self.beta = float(beta)
         t_0, T_f = time_interval
         self.tau = (T_f - t_0) / (n_t - 1.0)                 # control/control.py:2831
-        self._stream = torch.cuda.current_stream(self.device) if stream is None else stream
+        # the library runs on its own stream (the legacy default stream cannot be captured
+        # into the sweep CUDA graph); every call is fenced against torch's current stream
+        self._stream = torch.cuda.Stream(self.device) if stream is None else stream
         cfg = L.ctl_config(n=self.n, n_t=self.n_t, CN=int(self.CN), device=self.device.index,
                            tau=self.tau, beta=self.beta, epsilon=float(epsilon),
                            stream=C.c_void_p(self._stream.cuda_stream), rank=rank, world=world)
@@ -120,6 +122,20 @@ class MultiBlockSystem:
     # ------------------------------------------------------------------ plumbing
     def _check(self, rc):
         L.check(self._h, rc)
+
+    @property
+    def stream(self):
+        """The CUDA stream the library launches on (time it with events recorded here)."""
+        return self._stream
+
+    def _call(self, fn, *args):
+        """Library call ordered after the work already queued on torch's current stream,
+        and torch's later work ordered after the call."""
+        cur = torch.cuda.current_stream(self.device)
+        self._stream.wait_stream(cur)
+        rc = fn(self._h, *args)
+        cur.wait_stream(self._stream)
+        self._check(rc)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -187,8 +203,7 @@ class MultiBlockSystem:
 
     def convert(self, x_dev, src_layout, dst_layout):
         out = self.new_vector(dst_layout)
-        self._check(self._lib.ctl_convert_layout(self._h, x_dev.data_ptr(), src_layout,
-                                                 out.data_ptr(), dst_layout))
+        self._call(self._lib.ctl_convert_layout, x_dev.data_ptr(), src_layout, out.data_ptr(), dst_layout)
         return out
 
     # ------------------------------------------------------------------ operator
@@ -196,13 +211,12 @@ class MultiBlockSystem:
         """y = A x on device vectors."""
         if y_dev is None:
             y_dev = torch.empty_like(x_dev)
-        self._check(self._lib.ctl_kkt_apply(self._h, x_dev.data_ptr(), y_dev.data_ptr(), layout))
+        self._call(self._lib.ctl_kkt_apply, x_dev.data_ptr(), y_dev.data_ptr(), layout)
         return y_dev
 
     def time_apply(self, x_tf, y_tf, reps):
         ms = C.c_float()
-        self._check(self._lib.ctl_time_kkt_apply(self._h, x_tf.data_ptr(), y_tf.data_ptr(), reps,
-                                                 C.byref(ms)))
+        self._call(self._lib.ctl_time_kkt_apply, x_tf.data_ptr(), y_tf.data_ptr(), reps, C.byref(ms))
         return float(ms.value)
 
     def matshell(self):
@@ -246,7 +260,7 @@ class MultiBlockSystem:
         if u_dev is None:
             u_dev = torch.zeros_like(b_dev)
         fn = self._lib.ctl_pc_fn if raw else self._lib.ctl_pc_apply
-        self._check(fn(self._h, b_dev.data_ptr(), u_dev.data_ptr(), layout))
+        self._call(fn, b_dev.data_ptr(), u_dev.data_ptr(), layout)
         return u_dev
 
     def pc_fn(self):
@@ -286,8 +300,7 @@ class MultiBlockSystem:
             raise L.CtlError("call setup_preconditioner() first")
         o = self._krylov_options(solver_parameters, kind)
         res = L.ctl_solve_result()
-        self._check(self._lib.ctl_solve(self._h, b_dev.data_ptr(), u_dev.data_ptr(), layout,
-                                        C.byref(o), C.byref(res)))
+        self._call(self._lib.ctl_solve, b_dev.data_ptr(), u_dev.data_ptr(), layout, C.byref(o), C.byref(res))
         return KSPInfo(res)
 
     def _install_callback(self, pc_fn):
@@ -297,13 +310,13 @@ class MultiBlockSystem:
             try:
                 b = _wrap_device_ptr(b_ptr, sys_.vec_len(), sys_.device)
                 u = _wrap_device_ptr(u_ptr, sys_.vec_len(), sys_.device)
-                with torch.cuda.stream(sys_._stream):
-                    b0, b1 = sys_.to_host_blocks(b)
-                    u0 = np.zeros_like(b0)
-                    u1 = np.zeros_like(b1)
-                    pc_fn(u0, u1, b0, b1)
-                    u.copy_(sys_.to_device(u0, u1))
-                sys_._stream.synchronize()
+                # the library synchronised its stream before calling back
+                b0, b1 = sys_.to_host_blocks(b)
+                u0 = np.zeros_like(b0)
+                u1 = np.zeros_like(b1)
+                pc_fn(u0, u1, b0, b1)
+                u.copy_(sys_.to_device(u0, u1))
+                torch.cuda.current_stream(sys_.device).synchronize()
                 return 0
             except Exception:                                     # flag_errors, preconditioner.py:64-72
                 _error_flag[0] = True
@@ -350,8 +363,7 @@ class MultiBlockSystem:
 
     def residual_norm(self, b_dev, x_dev, layout=L.CTL_LAYOUT_BLOCK_MAJOR):
         out = C.c_double()
-        self._check(self._lib.ctl_kkt_residual_norm(self._h, b_dev.data_ptr(), x_dev.data_ptr(),
-                                                    layout, C.byref(out)))
+        self._call(self._lib.ctl_kkt_residual_norm, b_dev.data_ptr(), x_dev.data_ptr(), layout, C.byref(out))
         return float(out.value)
 
     def objective(self, v, zeta, v_hat):
@@ -406,7 +418,7 @@ class MultiBlockSystem:
 
     def amg_solve(self, b_dev, hierarchy=0):
         x = torch.zeros_like(b_dev)
-        self._check(self._lib.ctl_amg_solve(self._h, hierarchy, b_dev.data_ptr(), x.data_ptr()))
+        self._call(self._lib.ctl_amg_solve, hierarchy, b_dev.data_ptr(), x.data_ptr())
         return x
 
 
