@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the all-at-once KKT solve (BASELINE.json: "KKT solve s & SpMM HBM GB/s, heat
+control 1024^2 P1 n_t=64").
+
+A step = one complete KKT solve of BASELINE config C2 (2-D heat control, P1 on a
+1024 x 1024 mesh of (0,2)^2, n_t = 64, trapezoidal rule, beta = 1e-4, rtol 1e-6) with the
+right-hand side resident in HBM.  `value` = seconds per solve (device time, CUDA events, max
+over ranks).  `e2e` = the same solve through the public API with HOST buffers (pinned
+host -> device copy of b and of the initial guess, device -> host copy of the solution inside
+the timed region).  `roofline` = the dominant kernel of the step (fine-level AMG smoother
+SpMV of the time sweeps); `roofline_spmm` = the fused time-batched KKT-apply SpMM the metric
+names.  `cpu_baseline` = the CPU oracle on a bounded sample of the same workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--ksp minres|fgmres|gmres]
+    python bench.py --impl reference ...      # CPU oracle arm (the reference's algorithm)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "kkt_solve_time"
+UNIT = "s"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, val in zip(names, f[2:]):
+                    if val.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def solver_parameters(ksp, rtol):
+    return {"linear_solver": ksp, "gmres_restart": 30, "maximum_iterations": 200,
+            "relative_tolerance": rtol, "absolute_tolerance": 0.0, "preconditioner": True}
+
+
+# --------------------------------------------------------------------------------------
+# CPU oracle sample: one Krylov iteration (KKT apply + preconditioner apply) at the full
+# spatial size on n_s of the N time blocks, scaled to a whole solve.
+# --------------------------------------------------------------------------------------
+def cpu_sample(q_full, n_blocks_sample, its, mode):
+    from oracle import kkt
+    from oracle import pc as opc
+    M, K, bd, beta = q_full["M"], q_full["K"], q_full["bdofs"], q_full["beta"]
+    tau = q_full["tau"]
+    n_t_s = n_blocks_sample + 1
+    n = M.shape[0]
+    N_full = q_full["n_t"] - 1
+    if mode == "diagonal":
+        pc = opc.construct_pc_diagonal(M, K, tau, beta, n_t_s, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
+    else:
+        pc = opc.construct_pc(M, K, tau, beta, n_t_s, True, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
+    rng = np.random.default_rng(0)
+    x0 = rng.standard_normal((n_blocks_sample, n))
+    x1 = rng.standard_normal((n_blocks_sample, n))
+    x0[:, bd] = 0.0
+    x1[:, bd] = 0.0
+    pc(x0, x1)                      # untimed: AMG setup + numba compilation happen on first use
+    t0 = time.perf_counter()
+    y0, y1 = kkt.kkt_apply_fused(M, K, tau, beta, n_t_s, True, bd, x0, x1)
+    t_apply = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    pc(y0, y1)
+    t_pc = time.perf_counter() - t0
+    scale = N_full / n_blocks_sample
+    per_iter = (t_apply + t_pc) * scale
+    return {"seconds_sample": t_apply + t_pc, "seconds_per_iteration_full": per_iter,
+            "value": per_iter * (its + 1), "kkt_apply_s_full": t_apply * scale, "pc_apply_s_full": t_pc * scale}
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port: the real
+    Firedrake/PETSc/hypre stack cannot be installed here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import kat
+    q = kat.heat_problem(args.nx, args.n_t, True)
+    mode = "diagonal" if args.ksp == "minres" else "triangular"
+    its = args.ref_its
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_sample(q, args.sample_blocks, its, mode)
+        if i >= args.warmup:
+            times.append(info["value"])
+    val = float(np.mean(times))
+    cores = 1
+    sample = (f"1 {args.ksp} iteration (KKT apply + preconditioner apply, AMG set up once, untimed) at "
+              f"the full {args.nx}^2 spatial size on {args.sample_blocks} of {args.n_t - 1} time blocks, "
+              f"scaled x{(args.n_t - 1) / args.sample_blocks:.3g} to all blocks and x{its + 1} "
+              f"to a solve of {its} iterations; numpy/scipy oracle, 1 thread")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args):
+    return {"workload": f"C2: 2-D heat control, P1 on {args.nx}x{args.nx} mesh of (0,2)^2, n_t={args.n_t}, "
+                        f"trapezoidal (CN), beta=1e-4, {args.ksp} + in-built block preconditioner "
+                        f"({'block-diagonal SPD variant' if args.ksp == 'minres' else 'block lower-triangular'}), "
+                        f"rtol {args.rtol:g}",
+            "n": (args.nx + 1) ** 2, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol,
+            "l2": "Krylov vectors (1.08 GB each) exceed L2; per-kernel micro-timings flush L2 between launches"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=1024)
+    ap.add_argument("--n_t", type=int, default=64)
+    ap.add_argument("--ksp", default="minres", choices=["minres", "fgmres", "gmres"])
+    ap.add_argument("--rtol", type=float, default=1e-6)
+    ap.add_argument("--sample_blocks", type=int, default=4)
+    ap.add_argument("--ref_its", type=int, default=12, help="iterations assumed by the reference arm")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import kat
+    from control_b200 import MultiBlockSystem, _lib as L
+    from oracle import kkt
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    q = kat.heat_problem(args.nx, args.n_t, True)
+    mode = "diagonal" if args.ksp == "minres" else "triangular"
+    s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=True,
+                         time_interval=q["time_interval"], bc_dofs=q["bdofs"], device=local_rank,
+                         rank=rank, world=world)
+    if world > 1:
+        s.init_comm(dist)
+    t0 = time.perf_counter()
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
+    setup_s = time.perf_counter() - t0
+    b0, b1 = kkt.build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"],
+                           np.zeros(s.n))
+    rows = slice(s.row_begin, s.row_begin + s.n_local)
+    b0, b1 = np.ascontiguousarray(b0[:, rows]), np.ascontiguousarray(b1[:, rows])
+    sp_ = solver_parameters(args.ksp, args.rtol)
+    b_dev = s.to_device(b0, b1)
+    b_host = torch.from_numpy(np.concatenate([b0.ravel(), b1.ravel()])).pin_memory()
+    u_host = torch.zeros_like(b_host).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def solve_resident():
+        u = s.new_vector()
+        return s.solve_device(b_dev, u, solver_parameters=sp_, pc="builtin"), u
+
+    def solve_e2e():
+        u_host.zero_()
+        bd = b_host.to(s.device, non_blocking=True)
+        ud = u_host.to(s.device, non_blocking=True)
+        info = s.solve_device(bd, ud, solver_parameters=sp_, pc="builtin")
+        u_host.copy_(ud, non_blocking=True)
+        torch.cuda.synchronize()
+        return info
+
+    for _ in range(args.warmup):
+        solve_resident()
+    # ---- timed region: exactly `steps` solves, device time, max over ranks
+    barrier()
+    l0 = s.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    infos = []
+    with ClockSampler(local_rank) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            info, u_last = solve_resident()
+            infos.append(info)
+        ev1.record()
+        barrier()
+    launches = s.kernel_launches() - l0
+    total_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    value = total_s / args.steps
+    res_norm = s.residual_norm(b_dev, u_last)
+
+    # ---- end to end through the public API with host buffers
+    solve_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solve_e2e()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    nbytes = b_host.numel() * 8
+
+    info = infos[-1]
+    # ---- roofline: KKT-apply SpMM, live over the timed region (events around every apply)
+    peak, peak_src = measured_peak()
+    n, N, nnz = s.n_local, s.N, int(q["M"].nnz * s.n_local / s.n)
+    spmm_bytes = 32.0 * n * N + 20.0 * nnz + 4.0 * (n + 1)
+    spmm_ms = sum(i.seconds_mult for i in infos) / sum(i.n_mult for i in infos) * 1e3
+    roof_spmm = {"kernel": "kkt_apply_staged_kernel (fused time-batched KKT SpMM)", "bound": "hbm",
+                 "achieved": spmm_bytes / spmm_ms / 1e6, "peak": peak, "unit": "GB/s",
+                 "frac": spmm_bytes / spmm_ms / 1e6 / peak, "traffic": None,
+                 "alg_bytes_per_launch": spmm_bytes, "ms_per_launch": spmm_ms,
+                 "how": "CUDA events around every apply inside the timed solves"}
+    # ---- roofline: dominant kernel of the step = fine-level smoother SpMV of the AMG sweeps
+    micro = s.micro_benchmarks(flush_l2=True) if hasattr(s, "micro_benchmarks") else None
+    roof = roof_spmm
+    if micro:
+        roof = {"kernel": "sell_cheb_kernel, AMG level 0 (smoother step of the time sweeps)", "bound": "hbm",
+                "achieved": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6, "peak": peak, "unit": "GB/s",
+                "frac": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6 / peak, "traffic": None,
+                "alg_bytes_per_launch": micro["cheb_bytes"], "ms_per_launch": micro["cheb_ms"],
+                "how": "CUDA events per launch, L2 flushed between launches"}
+    pc_s = sum(i.seconds_pc for i in infos) / max(1, sum(i.n_pc for i in infos))
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": value * 1e3, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args),
+            "iterations": info.its, "converged_reason": info.reason, "kkt_residual": res_norm,
+            "rel_residual": info.rnorm / info.ref_norm if info.ref_norm else None,
+            "setup_s": setup_s, "pc_apply_ms": pc_s * 1e3, "kkt_apply_ms": spmm_ms,
+            "peak_source": peak_src,
+            "roofline": roof, "roofline_spmm": roof_spmm,
+            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes},
+            "gpu_launches": int(launches), "clocks": clocks.summary()}
+    if micro:
+        line["kernels"] = micro
+    if rank == 0 and not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        cb = cpu_sample(q, args.sample_blocks, info.its, mode)
+        line["cpu_baseline"] = {
+            "value": cb["value"], "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": (f"1 {args.ksp} iteration (KKT apply + preconditioner apply; AMG setup untimed) at the full "
+                       f"{args.nx}^2 size on {args.sample_blocks} of {N} time blocks = {cb['seconds_sample']:.1f} s, "
+                       f"scaled x{N / args.sample_blocks:.3g} x{info.its + 1} applications; numpy/scipy oracle, "
+                       f"1 thread, {os.cpu_count()} cores on the box"),
+            "kkt_apply_s": cb["kkt_apply_s_full"], "pc_apply_s": cb["pc_apply_s_full"],
+            "wall_s": time.perf_counter() - t0}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,7 +30,8 @@ class ctl_pc_options(C.Structure):
                 ("cheb_emin", C.c_double), ("cheb_emax", C.c_double),
                 ("cheb_steps", C.c_int32), ("amg_cycles", C.c_int32), ("amg_nu", C.c_int32),
                 ("amg_max_levels", C.c_int32), ("amg_coarse_max", C.c_int32),
-                ("amg_theta", C.c_double), ("amg_lo", C.c_double), ("amg_hi", C.c_double)]
+                ("amg_theta", C.c_double), ("amg_lo", C.c_double), ("amg_hi", C.c_double),
+                ("amg_acc_lo", C.c_double), ("amg_acc_hi", C.c_double)]
 
 
 class ctl_krylov_options(C.Structure):
@@ -94,6 +95,7 @@ SIGNATURES = {
     "ctl_comm_init": (C.c_int, [_H, C.c_void_p]),
     "ctl_kernel_launches": (C.c_int64, [_H]),
     "ctl_time_kkt_apply": (C.c_int, [_H, _F64P, _F64P, C.c_int, C.POINTER(C.c_float)]),
+    "ctl_time_amg": (C.c_int, [_H, C.c_int32, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

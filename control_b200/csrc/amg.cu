@@ -61,11 +61,20 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             H.bytes_per_cycle += spmv * p.nu;
         }
     }
+    if (p.acc_lo > 0.0) {
+        CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n));
+        CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n));
+        CTL_TRY(dev_alloc(h, &H.acc_p, H.dev[0].n));
+    }
     return CTL_OK;
 }
 
 void amg_free(AmgHierarchyDev &H)
 {
+    cudaFree(H.acc_r);
+    cudaFree(H.acc_z);
+    cudaFree(H.acc_p);
+    H.acc_r = H.acc_z = H.acc_p = nullptr;
     for (AmgLevelDev &L : H.dev) {
         sell_free(L.A);
         sell_free(L.P);
@@ -127,8 +136,46 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, d
     return CTL_OK;
 }
 
+namespace {
+// out = a x + b y + c z on n-vectors (x may be null when a == 0; out may alias x)
+__global__ void lincomb3_kernel(double *out, double a, const double *x, double b, const double *__restrict__ y,
+                                double c, const double *__restrict__ z, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r = c * z[i];
+    if (y) r = fma(b, y[i], r);
+    if (x) r = fma(a, x[i], r);
+    out[i] = r;
+}
+}  // namespace
+
 int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x)
 {
-    for (int c = 0; c < H.params.cycles; ++c) CTL_TRY(vcycle(h, H, 0, b, x, c == 0));
+    const AmgParams &p = H.params;
+    if (p.acc_lo <= 0.0) {
+        for (int c = 0; c < p.cycles; ++c) CTL_TRY(vcycle(h, H, 0, b, x, c == 0));
+        return CTL_OK;
+    }
+    // Chebyshev semi-iteration on (V-cycle * A) over [acc_lo, acc_hi]: oracle/amg.py::solve
+    const int n = H.dev[0].n;
+    double scale;
+    std::vector<double> om;
+    cheb_coefficients(p.acc_lo, p.acc_hi, p.cycles, &scale, om);
+    double *buf[2] = {x, H.acc_p};
+    auto slot = [&](int k) { return (p.cycles - k) & 1; };      // p_cycles lands in x
+    const int blocks = ceil_div(n, 256);
+    CTL_TRY(vcycle(h, H, 0, b, H.acc_z, true));
+    lincomb3_kernel<<<blocks, 256, 0, h->stream>>>(buf[slot(1)], 0.0, nullptr, 0.0, nullptr, scale, H.acc_z, n);
+    h->launches++;
+    for (int k = 2; k <= p.cycles; ++k) {
+        const double w = om[k - 2];
+        CTL_TRY(sell_spmv(h, H.dev[0].A, buf[slot(k - 1)], H.acc_r, b, SELL_RESIDUAL));
+        CTL_TRY(vcycle(h, H, 0, H.acc_r, H.acc_z, true));
+        lincomb3_kernel<<<blocks, 256, 0, h->stream>>>(buf[slot(k)], 1.0 - w, k == 2 ? nullptr : buf[slot(k - 2)], w,
+                                                      buf[slot(k - 1)], w * scale, H.acc_z, n);
+        h->launches++;
+    }
+    CTL_CUDA(cudaGetLastError());
     return CTL_OK;
 }

@@ -18,6 +18,7 @@ struct AmgHierarchyDev {
     std::vector<AmgLevelHost> host;      // kept for introspection (ctl_amg_get_csr)
     std::vector<AmgLevelDev> dev;
     int64_t bytes_per_cycle = 0;         // algorithmic bytes of one V-cycle (byte model)
+    double *acc_r = nullptr, *acc_z = nullptr, *acc_p = nullptr;   // level-0 work vectors of the accelerated solve
 };
 
 // A0 on level 0 may share an existing SELL pattern (fine-level matrices all have the

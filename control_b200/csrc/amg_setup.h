@@ -10,9 +10,10 @@ struct AmgParams {
     double theta = 0.08;
     int max_levels = 10;
     int coarse_max = 200;
-    int nu = 2;
+    int nu = 3;
     double lo = 0.25, hi = 1.0;
-    int cycles = 2;
+    int cycles = 4;      // see oracle/amg.py::solve for why not the reference's 2
+    double acc_lo = 0.0, acc_hi = 1.0;   // > 0: Chebyshev-accelerated cycles (oracle/amg.py::solve)
 };
 
 struct AmgLevelHost {

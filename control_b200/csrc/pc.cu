@@ -264,13 +264,15 @@ int ctl_pc_default_options(ctl_pc_options *o)
     o->cheb_emin = 0.0;
     o->cheb_emax = 0.0;
     o->cheb_steps = 20;                  // "ksp_max_it": 20, control/control.py:1980
-    o->amg_cycles = d.cycles;            // "pc_hypre_boomeramg_max_iter": 2, control/control.py:2065
+    o->amg_cycles = d.cycles;            // stands in for "pc_hypre_boomeramg_max_iter": 2, control.py:2065
     o->amg_nu = d.nu;
     o->amg_max_levels = d.max_levels;
     o->amg_coarse_max = d.coarse_max;
     o->amg_theta = d.theta;
     o->amg_lo = d.lo;
     o->amg_hi = d.hi;
+    o->amg_acc_lo = d.acc_lo;
+    o->amg_acc_hi = d.acc_hi;
     return CTL_OK;
 }
 
@@ -287,6 +289,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
                   "ctl_pc_setup: Chebyshev needs 0 < e_min < e_max and at least one step");
     CTL_CHECK(opts->amg_cycles >= 1 && opts->amg_nu >= 1 && opts->amg_max_levels >= 1, CTL_ERR_ARG,
               "ctl_pc_setup: bad AMG options");
+    CTL_CHECK(opts->amg_acc_lo <= 0.0 || opts->amg_acc_hi > opts->amg_acc_lo, CTL_ERR_ARG,
+              "ctl_pc_setup: AMG acceleration needs acc_lo < acc_hi");
     if (opts->mode == CTL_PCMODE_DIAGONAL)
         CTL_CHECK(h->cfg.CN && !h->per_level && h->k_symmetric, CTL_ERR_ARG,
                   "ctl_pc_setup: the block-diagonal (MINRES) variant needs CN and a time-independent symmetric K");
@@ -303,6 +307,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     st.amg.lo = opts->amg_lo;
     st.amg.hi = opts->amg_hi;
     st.amg.cycles = opts->amg_cycles;
+    st.amg.acc_lo = opts->amg_acc_lo;
+    st.amg.acc_hi = opts->amg_acc_hi;
     if (const char *e = getenv("CTL_NO_GRAPH")) st.use_graph = !(e[0] == '1');
 
     const int N = h->N, nl = h->n_loc, rb = h->row_begin;
@@ -471,6 +477,63 @@ int ctl_amg_solve(ctl_handle h, int32_t hi, const double *b, double *x)
     CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && b && x, CTL_ERR_ARG, "ctl_amg_solve: bad argument");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
     return amg_solve(h, h->pc->hier[hi], b, x);
+}
+
+int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
+{
+    CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && out && reps > 0, CTL_ERR_ARG,
+              "ctl_time_amg: bad argument");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    AmgHierarchyDev &H = h->pc->hier[hi];
+    AmgLevelDev &L0 = H.dev[0];
+    const int n = L0.n;
+    double *x = nullptr, *b = nullptr, *flush = nullptr;
+    const size_t flush_bytes = 256u << 20;
+    CTL_CUDA(cudaMalloc((void **)&x, (size_t)n * sizeof(double)));
+    CTL_CUDA(cudaMalloc((void **)&b, (size_t)n * sizeof(double)));
+    if (flush_l2) CTL_CUDA(cudaMalloc((void **)&flush, flush_bytes));
+    {
+        std::vector<double> hb(n);
+        for (int i = 0; i < n; ++i) hb[i] = std::sin(0.37 * i) + 0.1;
+        CTL_CUDA(cudaMemcpy(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        CTL_CUDA(cudaMemset(x, 0, (size_t)n * sizeof(double)));
+    }
+    cudaEvent_t e0, e1;
+    CTL_CUDA(cudaEventCreate(&e0));
+    CTL_CUDA(cudaEventCreate(&e1));
+    double acc[3] = {0, 0, 0};
+    int64_t launches_solve = 0;
+    int rc = CTL_OK;
+    for (int which = 0; which < 3 && rc == CTL_OK; ++which) {
+        for (int r = -2; r < reps && rc == CTL_OK; ++r) {       // two warm-up launches
+            if (flush) cudaMemsetAsync(flush, r & 0xff, flush_bytes, h->stream);
+            cudaEventRecord(e0, h->stream);
+            const int64_t l0 = h->launches;
+            if (which == 0) rc = sell_cheb_step(h, L0.A, L0.dinv, b, x, b, L0.t0, 0.3, 0.7, 0.1);
+            else if (which == 1) rc = sell_spmv(h, L0.A, b, L0.r, x, SELL_RESIDUAL);
+            else rc = amg_solve(h, H, b, x);
+            launches_solve = h->launches - l0;
+            cudaEventRecord(e1, h->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r >= 0) acc[which] += ms;
+        }
+    }
+    const double nnz = (double)L0.A.pat->nnz;
+    out[0] = acc[0] / reps;
+    out[1] = 12.0 * nnz + 40.0 * n;          // values + indices + dinv, b, p_prev, p_cur, out
+    out[2] = acc[1] / reps;
+    out[3] = 12.0 * nnz + 24.0 * n;          // values + indices + b, x, r
+    out[4] = acc[2] / reps;
+    out[5] = (double)H.bytes_per_cycle * H.params.cycles;
+    out[6] = (double)launches_solve;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(x);
+    cudaFree(b);
+    cudaFree(flush);
+    return rc;
 }
 
 }  // extern "C"

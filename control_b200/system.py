@@ -246,7 +246,8 @@ class MultiBlockSystem:
         o.cheb_steps = int(cheb_steps)
         for key, field in (("cycles", "amg_cycles"), ("nu", "amg_nu"), ("max_levels", "amg_max_levels"),
                            ("coarse_max", "amg_coarse_max"), ("theta", "amg_theta"),
-                           ("lo", "amg_lo"), ("hi", "amg_hi")):
+                           ("lo", "amg_lo"), ("hi", "amg_hi"), ("acc_lo", "amg_acc_lo"),
+                           ("acc_hi", "amg_acc_hi")):
             if key in amg:
                 setattr(o, field, amg.pop(key))
         if amg:
@@ -374,6 +375,14 @@ class MultiBlockSystem:
         self._check(self._lib.ctl_objective_host(self._h, v.ctypes.data, zeta.ctypes.data,
                                                  v_hat.ctypes.data, C.byref(out)))
         return float(out.value)
+
+    def micro_benchmarks(self, hierarchy=0, reps=10, flush_l2=True):
+        """Isolated timings of the sweep kernels (CUDA events per launch)."""
+        out = (C.c_double * 7)()
+        self._call(self._lib.ctl_time_amg, hierarchy, reps, int(flush_l2), out)
+        return {"cheb_ms": out[0], "cheb_bytes": out[1], "residual_ms": out[2], "residual_bytes": out[3],
+                "inner_solve_ms": out[4], "inner_solve_bytes": out[5], "inner_solve_kernels": int(out[6]),
+                "l2_flushed": bool(flush_l2)}
 
     def kernel_launches(self):
         return int(self._lib.ctl_kernel_launches(self._h))

@@ -88,12 +88,14 @@ typedef struct {
     int32_t solver_0;        /* CTL_S0_*                                                   */
     double cheb_emin, cheb_emax;   /* lambda_v_bounds                                      */
     int32_t cheb_steps;      /* ksp_max_it of solver_0: 20 (control/control.py:1980)       */
-    int32_t amg_cycles;      /* V-cycles per inner solve: 2                                */
+    int32_t amg_cycles;      /* V-cycles per inner solve (default 4; the reference: 2 of hypre) */
     int32_t amg_nu;          /* Chebyshev smoother degree (pre = post)                     */
     int32_t amg_max_levels;
     int32_t amg_coarse_max;  /* coarsest level solved with a dense inverse below this size */
     double amg_theta;        /* strength-of-connection threshold                           */
     double amg_lo, amg_hi;   /* smoother interval [lo*rho, hi*rho] of D^-1 A                */
+    double amg_acc_lo, amg_acc_hi; /* > 0: Chebyshev-accelerate the V-cycles over this
+                                      interval of spec(V-cycle * A); 0 = plain cycles      */
 } ctl_pc_options;
 
 /* solver_parameters (preconditioner/preconditioner.py:732-756) */
@@ -209,6 +211,13 @@ int64_t ctl_kernel_launches(ctl_handle h);     /* kernels launched by this handl
 /* time `reps` back-to-back launches of the fused KKT-apply kernel alone (time-fastest
  * layout, CUDA events on the handle's stream); average milliseconds per launch */
 int ctl_time_kkt_apply(ctl_handle h, const double *x_tf, double *y_tf, int reps, float *ms);
+
+/* time the kernels of the time sweeps in isolation on AMG hierarchy `hierarchy` (CUDA
+ * events around each launch on the handle's stream; flush_l2 != 0 overwrites a 256 MB
+ * buffer between launches).  out[0] = level-0 smoother step, ms; out[1] = its algorithmic
+ * bytes; out[2] = level-0 residual SpMV, ms; out[3] = its bytes; out[4] = one inner solve
+ * (all cycles, all levels), ms; out[5] = its algorithmic bytes; out[6] = kernels per solve */
+int ctl_time_amg(ctl_handle h, int32_t hierarchy, int reps, int flush_l2, double *out7);
 
 #ifdef __cplusplus
 }
