@@ -34,10 +34,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
         AmgLevelDev &Ld = H.dev[l];
         Ld.n = Lh.A.n_rows;
         Ld.rho = Lh.rho;
-        std::shared_ptr<SellPattern> pat;
-        if (l == 0 && fine_pattern) pat = fine_pattern;
-        else CTL_TRY(sell_build_pattern(h, Lh.A, pat));
-        CTL_TRY(sell_set_values(h, pat, Lh.A.values.data(), Ld.A));
+        if (l == 0 && fine_pattern) CTL_TRY(sell_set_values(h, fine_pattern, Lh.A.values.data(), Ld.A));
+        else CTL_TRY(sell_from_csr(h, Lh.A, Ld.A));
         CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data(), Lh.dinv.size()));
         CTL_TRY(dev_alloc(h, &Ld.r, Ld.n));
         CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n));
@@ -47,11 +45,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
         }
         const int64_t spmv = 12 * Lh.A.nnz() + 4ll * (Ld.n + 1) + 16ll * Ld.n;
         if (l + 1 < nl) {
-            std::shared_ptr<SellPattern> pp, pr;
-            CTL_TRY(sell_build_pattern(h, Lh.P, pp));
-            CTL_TRY(sell_set_values(h, pp, Lh.P.values.data(), Ld.P));
-            CTL_TRY(sell_build_pattern(h, Lh.R, pr));
-            CTL_TRY(sell_set_values(h, pr, Lh.R.values.data(), Ld.R));
+            CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
+            CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
             // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
             H.bytes_per_cycle += spmv * (2 * p.nu) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
         } else if (!Lh.Ainv.empty()) {

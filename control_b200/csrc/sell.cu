@@ -14,8 +14,33 @@ SellPattern::~SellPattern()
 void sell_free(SellMat &m)
 {
     cudaFree(m.vals);
-    m.vals = nullptr;
+    cudaFree(m.csr_ptr);
+    cudaFree(m.csr_cols);
+    cudaFree(m.csr_vals);
+    m.vals = m.csr_vals = nullptr;
+    m.csr_ptr = m.csr_cols = nullptr;
+    m.lanes = 0;
     m.pat.reset();
+}
+
+int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out)
+{
+    const double mean = A.n_rows ? (double)A.nnz() / A.n_rows : 0.0;
+    if (mean <= 10.0) {
+        std::shared_ptr<SellPattern> pat;
+        CTL_TRY(sell_build_pattern(h, A, pat));
+        return sell_set_values(h, pat, A.values.data(), out);
+    }
+    auto pat = std::make_shared<SellPattern>();     // sizes only; no SELL arrays
+    pat->n_rows = A.n_rows;
+    pat->n_cols = A.n_cols;
+    pat->nnz = A.nnz();
+    out.pat = pat;
+    out.lanes = mean <= 16.0 ? 8 : (mean <= 48.0 ? 16 : 32);
+    CTL_TRY(ctl_upload(h, &out.csr_ptr, A.indptr.data(), A.indptr.size()));
+    CTL_TRY(ctl_upload(h, &out.csr_cols, A.indices.data(), A.indices.size()));
+    CTL_TRY(ctl_upload(h, &out.csr_vals, A.values.data(), A.values.size()));
+    return CTL_OK;
 }
 
 int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPattern> &out)
@@ -152,6 +177,65 @@ __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const int *__restrict__ 
     y[row] = alpha * acc1 + beta * acc2;
 }
 
+// ---- CSR-vector variants: T lanes per row, shuffle reduction
+template <int T>
+__device__ __forceinline__ double csr_row_dot(const int *__restrict__ ptr, const int *__restrict__ cols,
+                                              const double *__restrict__ vals, const double *__restrict__ x,
+                                              int row, int lane)
+{
+    const int beg = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+    double acc = 0.0;
+    for (int p = beg + lane; p < end; p += T) acc = fma(__ldg(vals + p), __ldg(x + __ldg(cols + p)), acc);
+#pragma unroll
+    for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
+    return acc;
+}
+
+template <int MODE, int T>
+__global__ void __launch_bounds__(ST) csrv_spmv_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      const double *b, double *y, int n_rows)
+{
+    const int t = blockIdx.x * ST + threadIdx.x;
+    const int row = t / T, lane = t % T;
+    const int r = row < n_rows ? row : n_rows - 1;       // whole warp takes part in the shuffles
+    const double ax = csr_row_dot<T>(ptr, cols, vals, x, r, lane);
+    if (row >= n_rows || lane != 0) return;
+    if (MODE == SELL_ASSIGN) y[row] = ax;
+    else if (MODE == SELL_RESIDUAL) y[row] = b[row] - ax;
+    else if (MODE == SELL_ADD) y[row] += ax;
+    else y[row] -= ax;
+}
+
+template <int T>
+__global__ void __launch_bounds__(ST) csrv_cheb_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
+                                                      const double *__restrict__ vals, const double *__restrict__ dinv,
+                                                      const double *__restrict__ b, const double *p_prev,
+                                                      const double *__restrict__ p_cur, double *out, double a,
+                                                      double bq, double c, int n_rows)
+{
+    const int t = blockIdx.x * ST + threadIdx.x;
+    const int row = t / T, lane = t % T;
+    const int r = row < n_rows ? row : n_rows - 1;
+    const double ax = csr_row_dot<T>(ptr, cols, vals, p_cur, r, lane);
+    if (row >= n_rows || lane != 0) return;
+    double v = bq * p_cur[row] + c * dinv[row] * (b[row] - ax);
+    if (a != 0.0) v = fma(a, p_prev[row], v);
+    out[row] = v;
+}
+
+template <int T>
+void launch_csrv_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
+{
+    const int n = A.pat->n_rows, blocks = ceil_div((int64_t)n * T, ST);
+    switch (mode) {
+    case SELL_ASSIGN: csrv_spmv_kernel<SELL_ASSIGN, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_RESIDUAL: csrv_spmv_kernel<SELL_RESIDUAL, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_ADD: csrv_spmv_kernel<SELL_ADD, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    default: csrv_spmv_kernel<SELL_SUB, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    }
+}
+
 }  // namespace
 
 int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
@@ -159,6 +243,14 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, con
     const SellPattern &p = *A.pat;
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
+    if (A.lanes) {
+        if (A.lanes == 8) launch_csrv_spmv<8>(h, A, x, y, b, mode);
+        else if (A.lanes == 16) launch_csrv_spmv<16>(h, A, x, y, b, mode);
+        else launch_csrv_spmv<32>(h, A, x, y, b, mode);
+        h->launches++;
+        CTL_CUDA(cudaGetLastError());
+        return CTL_OK;
+    }
     switch (mode) {
     case SELL_ASSIGN: sell_spmv_kernel<SELL_ASSIGN><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
     case SELL_RESIDUAL: sell_spmv_kernel<SELL_RESIDUAL><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
@@ -176,6 +268,18 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
     const SellPattern &p = *A.pat;
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
+    if (A.lanes) {
+        const int n = p.n_rows;
+        if (A.lanes == 8)
+            csrv_cheb_kernel<8><<<ceil_div((int64_t)n * 8, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+        else if (A.lanes == 16)
+            csrv_cheb_kernel<16><<<ceil_div((int64_t)n * 16, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+        else
+            csrv_cheb_kernel<32><<<ceil_div((int64_t)n * 32, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+        h->launches++;
+        CTL_CUDA(cudaGetLastError());
+        return CTL_OK;
+    }
     sell_cheb_kernel<<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, dinv, b, p_prev, p_cur, out, a,
                                                    bq, c, p.n_rows);
     h->launches++;

@@ -22,7 +22,14 @@ struct SellPattern {
 struct SellMat {
     std::shared_ptr<SellPattern> pat;
     double *vals = nullptr;            // device, n_stored (owned)
-    bool valid() const { return pat && vals; }
+    // Rows much longer than a fine-mesh stencil (coarse AMG operators, restrictions) are
+    // latency-bound with one thread per row: they are stored as plain CSR instead and
+    // processed by `lanes` threads per row (lanes = 0: SELL, one thread per row).
+    int lanes = 0;
+    int *csr_ptr = nullptr, *csr_cols = nullptr;
+    double *csr_vals = nullptr;
+    int n_rows() const { return pat->n_rows; }
+    bool valid() const { return pat && (vals || csr_vals); }
 };
 
 // build the pattern from a host CSR (column indices need not be sorted)
@@ -30,6 +37,8 @@ int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPa
 // lay one value set (CSR order, host) out on a pattern
 int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values,
                     SellMat &out);
+// one call for matrices that own their pattern: picks SELL or CSR-vector by mean row length
+int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out);
 void sell_free(SellMat &m);
 
 enum SellMode {
