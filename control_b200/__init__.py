@@ -4,6 +4,7 @@ in-built block preconditioner -- behind the reference's own ``P=`` / ``solver_pa
 / shell-matrix hooks.  All numerics run in libctl_b200.so (include/ctl_b200.h)."""
 from . import _lib
 from ._lib import CtlError
+from . import partition
 from .system import KSPInfo, MultiBlockSystem, csr_arrays
 
-__all__ = ["MultiBlockSystem", "KSPInfo", "CtlError", "csr_arrays", "_lib"]
+__all__ = ["MultiBlockSystem", "KSPInfo", "CtlError", "csr_arrays", "partition", "_lib"]

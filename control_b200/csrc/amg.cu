@@ -32,21 +32,46 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
     for (int l = 0; l < nl; ++l) {
         AmgLevelHost &Lh = H.host[l];
         AmgLevelDev &Ld = H.dev[l];
-        Ld.n = Lh.A.n_rows;
+        // level 0 is distributed by rows (this rank's block, ghost columns appended); the
+        // coarse levels are replicated on every rank
+        const bool dist0 = (l == 0);
+        const int rb = dist0 ? h->row_begin : 0;
+        Ld.n = dist0 ? h->n_loc : Lh.A.n_rows;
+        const int ghosts = dist0 ? h->n_halo : 0;
         Ld.rho = Lh.rho;
-        if (l == 0 && fine_pattern) CTL_TRY(sell_set_values(h, fine_pattern, Lh.A.values.data(), Ld.A));
-        else CTL_TRY(sell_from_csr(h, Lh.A, Ld.A));
-        CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data(), Lh.dinv.size()));
-        CTL_TRY(dev_alloc(h, &Ld.r, Ld.n));
-        CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n));
+        if (dist0) {
+            CTL_CHECK(fine_pattern != nullptr, CTL_ERR_ARG, "amg_build: level 0 needs the mesh pattern");
+            std::vector<double> lv(h->loc_entry.size());
+            for (size_t q = 0; q < lv.size(); ++q) lv[q] = Lh.A.values[h->loc_entry[q]];
+            CTL_TRY(sell_set_values(h, fine_pattern, lv.data(), Ld.A));
+        } else {
+            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A));
+        }
+        CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data() + rb, (size_t)Ld.n));
+        CTL_TRY(dev_alloc(h, &Ld.r, Ld.n + ghosts));
+        CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n + ghosts));
         if (l > 0) {
             CTL_TRY(dev_alloc(h, &Ld.x, Ld.n));
             CTL_TRY(dev_alloc(h, &Ld.b, Ld.n));
         }
         const int64_t spmv = 12 * Lh.A.nnz() + 4ll * (Ld.n + 1) + 16ll * Ld.n;
         if (l + 1 < nl) {
-            CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
-            CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
+            if (dist0 && h->cfg.world > 1) {
+                HostCSR Pl, Rl;               // rows of P owned by this rank, and their transpose
+                Pl.n_rows = Ld.n;
+                Pl.n_cols = Lh.P.n_cols;
+                Pl.indptr.assign(Ld.n + 1, 0);
+                const int k0 = Lh.P.indptr[rb];
+                for (int r = 0; r <= Ld.n; ++r) Pl.indptr[r] = Lh.P.indptr[rb + r] - k0;
+                Pl.indices.assign(Lh.P.indices.begin() + k0, Lh.P.indices.begin() + Lh.P.indptr[rb + Ld.n]);
+                Pl.values.assign(Lh.P.values.begin() + k0, Lh.P.values.begin() + Lh.P.indptr[rb + Ld.n]);
+                csr_transpose(Pl, Rl);
+                CTL_TRY(sell_from_csr(h, Pl, Ld.P));
+                CTL_TRY(sell_from_csr(h, Rl, Ld.R));
+            } else {
+                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
+                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
+            }
             // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
             H.bytes_per_cycle += spmv * (2 * p.nu) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
         } else if (!Lh.Ainv.empty()) {
@@ -56,10 +81,12 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             H.bytes_per_cycle += spmv * p.nu;
         }
     }
+    if (h->cfg.world > 1)
+        CTL_CHECK(nl > 1, CTL_ERR_ARG, "amg_build: the problem is too small for a multi-rank hierarchy (single level)");
     if (p.acc_lo > 0.0) {
-        CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n));
-        CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n));
-        CTL_TRY(dev_alloc(h, &H.acc_p, H.dev[0].n));
+        CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n + h->n_halo));
+        CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n + h->n_halo));
+        CTL_TRY(dev_alloc(h, &H.acc_p, H.dev[0].n + h->n_halo));
     }
     return CTL_OK;
 }
@@ -88,7 +115,10 @@ void amg_free(AmgHierarchyDev &H)
 // nu Chebyshev steps on D^-1 A over [lo rho, hi rho] (oracle/cheb.py::chebyshev), result in x.
 // Iterates alternate between x and t0; for a non-zero guess and odd nu one copy moves the
 // result back into x.
-static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, const double *b, double *x, bool zero_guess)
+// ghost entries of a level-0 vector must be current before a product with the distributed A
+static inline int halo0(ctl_handle_s *h, int l, double *v) { return l == 0 ? ctl_halo_exchange_vec(h, v) : CTL_OK; }
+
+static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, const double *b, double *x, bool zero_guess)
 {
     double scale;
     std::vector<double> om;
@@ -100,12 +130,14 @@ static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, const dou
         CTL_TRY(vec_dinv_scale(h, L.dinv, b, buf[slot(1)], scale, L.n));
     } else {
         // p_1 = x + scale D^-1 (b - A x)
+        CTL_TRY(halo0(h, l, x));
         CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, buf[slot(1)], 0.0, 1.0, scale));
     }
     for (int k = 2; k <= p.nu; ++k) {
         const double w = om[k - 2];
         const double *prev = (k == 2 && zero_guess) ? nullptr : buf[slot(k - 2)];
         const double a = (k == 2 && zero_guess) ? 0.0 : (1.0 - w);
+        CTL_TRY(halo0(h, l, buf[slot(k - 1)]));
         CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, prev, buf[slot(k - 1)], buf[slot(k)], a, w, w * scale));
     }
     if (buf[slot(p.nu)] != x)
@@ -119,15 +151,17 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, d
     const int last = (int)H.dev.size() - 1;
     if (l == last) {
         if (L.Ainv) return dense_gemv(h, L.Ainv, b, x, L.n);
-        return smooth(h, H.params, L, b, x, zero_guess);
+        return smooth(h, H.params, L, l, b, x, zero_guess);
     }
     AmgLevelDev &C = H.dev[l + 1];
-    CTL_TRY(smooth(h, H.params, L, b, x, zero_guess));
+    CTL_TRY(smooth(h, H.params, L, l, b, x, zero_guess));
+    CTL_TRY(halo0(h, l, x));
     CTL_TRY(sell_spmv(h, L.A, x, L.r, b, SELL_RESIDUAL));
     CTL_TRY(sell_spmv(h, L.R, L.r, C.b, nullptr, SELL_ASSIGN));
+    if (l == 0) CTL_TRY(ctl_allreduce_sum(h, C.b, C.n));      // partial restrictions of the row blocks
     CTL_TRY(vcycle(h, H, l + 1, C.b, C.x, true));
     CTL_TRY(sell_spmv(h, L.P, C.x, x, nullptr, SELL_ADD));
-    CTL_TRY(smooth(h, H.params, L, b, x, false));
+    CTL_TRY(smooth(h, H.params, L, l, b, x, false));
     return CTL_OK;
 }
 
@@ -165,6 +199,7 @@ int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x)
     h->launches++;
     for (int k = 2; k <= p.cycles; ++k) {
         const double w = om[k - 2];
+        CTL_TRY(halo0(h, 0, buf[slot(k - 1)]));
         CTL_TRY(sell_spmv(h, H.dev[0].A, buf[slot(k - 1)], H.acc_r, b, SELL_RESIDUAL));
         CTL_TRY(vcycle(h, H, 0, H.acc_r, H.acc_z, true));
         lincomb3_kernel<<<blocks, 256, 0, h->stream>>>(buf[slot(k)], 1.0 - w, k == 2 ? nullptr : buf[slot(k - 2)], w,

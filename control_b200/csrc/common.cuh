@@ -120,7 +120,9 @@ void ctl_krylov_free(ctl_handle_s *h);    // krylov.cu
 void ctl_comm_free(ctl_handle_s *h);      // comm.cu
 int ctl_pc_invalidate(ctl_handle_s *h);   // pc.cu: matrices changed, rebuild on next setup
 // comm.cu
-int ctl_halo_exchange(ctl_handle_s *h, const double *x_tf);
+int ctl_halo_exchange(ctl_handle_s *h, const double *x_tf);            // both panels -> d_halo
+int ctl_halo_exchange_panel(ctl_handle_s *h, const double *panel_tf);  // one panel -> d_halo[0]
+int ctl_halo_exchange_vec(ctl_handle_s *h, double *x);                 // n_loc owned + n_halo ghost entries, in place
 int ctl_allreduce_sum(ctl_handle_s *h, double *dev, int count);
 
 // scratch management

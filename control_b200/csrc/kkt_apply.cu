@@ -346,6 +346,7 @@ void launch_g(const KktArgs &a, int G, cudaStream_t s)
 int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
 {
     CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_kkt_apply: ctl_assemble has not been called");
+    CTL_CHECK(h->cfg.world == 1 || h->comm, CTL_ERR_STATE, "ctl_kkt_apply: call ctl_comm_init first (world > 1)");
     if (h->n_halo > 0) CTL_TRY(ctl_halo_exchange(h, x_tf));
     KktArgs a;
     a.n_rows = h->n_loc;

@@ -112,6 +112,7 @@ static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
             else CTL_TRY(sell_spmv(h, st.Msell, up, bi, nullptr, SELL_ADD));     // b_i -= (-M) u_{i-1}
         }
         CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], bi, st.Uf + i * S));
+        CTL_TRY(ctl_halo_exchange_vec(h, st.Uf + i * S));      // later products read its ghost entries
     }
     // middle scaling fused with the backward right-hand sides
     // (control/control.py:2118-2133 + 2158-2168 CN; 2330-2350 + 2375-2385 BE)
@@ -132,6 +133,7 @@ static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
             CTL_TRY(sell_spmv2(h, st.Msell, st.Msell, ui, nullptr, un, bi, a, 1.0));
         }
         CTL_TRY(amg_solve(h, st.hier[st.bwd_h[i]], bi, st.Ub + i * S));
+        if (i > 0) CTL_TRY(ctl_halo_exchange_vec(h, st.Ub + i * S));
     }
     return CTL_OK;
 }
@@ -190,7 +192,7 @@ static int pc_fn_tf(ctl_handle_s *h, const double *b, double *u, bool wrap)
             if ((rc = pcb_u0_first(h, b0, st.d_mass_dinv, btil, buf[1], scale)) != CTL_OK) break;
             for (int k = 2; k <= st.opts.cheb_steps && rc == CTL_OK; ++k) {
                 const double w = om[k - 2];
-                if (h->n_halo > 0) rc = ctl_halo_exchange(h, buf[(k - 1) & 1]);
+                if (h->n_halo > 0) rc = ctl_halo_exchange_panel(h, buf[(k - 1) & 1]);
                 if (rc != CTL_OK) break;
                 rc = pcb_cheb_step(h, st.d_mass_dinv, btil, k == 2 ? nullptr : buf[k & 1], buf[(k - 1) & 1],
                                    buf[k & 1], k == 2 ? 0.0 : 1.0 - w, w, w * scale);
@@ -217,7 +219,7 @@ static int pc_fn_tf(ctl_handle_s *h, const double *b, double *u, bool wrap)
         if (st.opts.mode == CTL_PCMODE_TRIANGULAR) {
             // u0 has b's values on constrained rows when wrapping; the products must see
             // zeros there: the value arrays have constrained COLUMNS eliminated, so they do
-            if (h->n_halo > 0 && (rc = ctl_halo_exchange(h, u0)) != CTL_OK) break;
+            if (h->n_halo > 0 && (rc = ctl_halo_exchange_panel(h, u0)) != CTL_OK) break;
             rc = pcb_schur_rhs(h, u0, b1, rhs);
         } else {
             rc = pcb_schur_rhs(h, nullptr, b1, rhs);
@@ -294,7 +296,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     if (opts->mode == CTL_PCMODE_DIAGONAL)
         CTL_CHECK(h->cfg.CN && !h->per_level && h->k_symmetric, CTL_ERR_ARG,
                   "ctl_pc_setup: the block-diagonal (MINRES) variant needs CN and a time-independent symmetric K");
-    CTL_CHECK(h->cfg.world == 1, CTL_ERR_STATE, "ctl_pc_setup: multi-rank preconditioner not available in this build");
+    CTL_CHECK(h->cfg.world == 1 || h->comm, CTL_ERR_STATE, "ctl_pc_setup: call ctl_comm_init first (world > 1)");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
     ctl_pc_free(h);
     h->pc = std::make_shared<PcState>();
@@ -476,7 +478,14 @@ int ctl_amg_solve(ctl_handle h, int32_t hi, const double *b, double *x)
 {
     CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && b && x, CTL_ERR_ARG, "ctl_amg_solve: bad argument");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
-    return amg_solve(h, h->pc->hier[hi], b, x);
+    if (h->n_halo == 0) return amg_solve(h, h->pc->hier[hi], b, x);
+    // distributed level 0: the cycle needs ghost space behind the owned entries
+    PcState &st = *h->pc;
+    const size_t nb = (size_t)h->n_loc * sizeof(double);
+    CTL_CUDA(cudaMemcpyAsync(st.B, b, nb, cudaMemcpyDeviceToDevice, h->stream));
+    CTL_TRY(amg_solve(h, st.hier[hi], st.B, st.Uf));
+    CTL_CUDA(cudaMemcpyAsync(x, st.Uf, nb, cudaMemcpyDeviceToDevice, h->stream));
+    return CTL_OK;
 }
 
 int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)

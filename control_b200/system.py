@@ -178,6 +178,24 @@ class MultiBlockSystem:
         self._check(self._lib.ctl_assemble(self._h))
         self._pc_ready = False
 
+    def init_comm(self, dist=None):
+        """Create the library's NCCL communicator: rank 0 draws the unique id, torch.distributed
+        carries it to the other ranks (the one piece of plumbing done outside the library)."""
+        if self.world == 1:
+            return
+        if dist is None:
+            import torch.distributed as dist
+        idbuf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            rc = self._lib.ctl_comm_unique_id(idbuf)
+            if rc != 0:
+                raise L.CtlError(f"ctl_comm_unique_id failed ({rc})")
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device=self.device if on_gpu else "cpu")
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        self._call(self._lib.ctl_comm_init, raw)
+
     # ------------------------------------------------------------------ device vectors
     def vec_len(self, layout=L.CTL_LAYOUT_BLOCK_MAJOR):
         return int(self._lib.ctl_vec_len(self._h, layout))

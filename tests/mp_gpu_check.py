@@ -1,0 +1,77 @@
+"""Multi-rank GPU check, launched by torchrun (one rank per GPU): the row-partitioned KKT
+apply, preconditioner and solve must reproduce the single-rank oracle results."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import kat  # noqa: E402
+from control_b200 import MultiBlockSystem, partition  # noqa: E402
+from oracle import control as ocontrol  # noqa: E402
+from oracle import kkt  # noqa: E402
+from oracle import pc as opc  # noqa: E402
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    for CN in (True, False):
+        q = kat.heat_problem(40, 9, CN, beta=1e-3)
+        n = q["M"].shape[0]
+        s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=CN,
+                             time_interval=q["time_interval"], bc_dofs=q["bdofs"], rank=rank, world=world)
+        s.init_comm(dist)
+        assert (s.row_begin, s.n_local) == partition.ownership_range(n, world, rank)
+        rng = np.random.default_rng(0)
+        x0 = rng.standard_normal((s.N, n))
+        x1 = rng.standard_normal((s.N, n))
+        y0, y1 = kkt.kkt_apply_fused(q["M"], q["K"], s.tau, q["beta"], q["n_t"], CN, q["bdofs"], x0, x1)
+        loc = lambda a: partition.local_blocks(a, n, world, rank)
+        g0, g1 = s.to_host_blocks(s.apply(s.to_device(loc(x0), loc(x1))))
+        e_apply = max(rel(g0, loc(y0)), rel(g1, loc(y1)))
+        assert e_apply < 1e-13, e_apply
+        # preconditioner
+        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"])
+        pc = opc.construct_pc(q["M"], q["K"], q["tau"], q["beta"], q["n_t"], CN, q["bdofs"],
+                              lambda_v_bounds=q["lambda_v_bounds"])
+        b0, b1 = x0.copy(), x1.copy()
+        b0[:, q["bdofs"]] = 0.0
+        b1[:, q["bdofs"]] = 0.0
+        r0, r1 = pc(b0, b1)
+        p0, p1 = s.to_host_blocks(s.pc_apply(s.to_device(loc(b0), loc(b1)), raw=True))
+        e_pc = max(rel(p0, loc(r0)), rel(p1, loc(r1)))
+        assert e_pc < 1e-10, e_pc
+        # solve
+        sp_ = {"linear_solver": "fgmres", "maximum_iterations": 100, "relative_tolerance": 1e-8,
+               "absolute_tolerance": 0.0}
+        ref = ocontrol.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+                                    time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"],
+                                    f=q["f"], lambda_v_bounds=q["lambda_v_bounds"], solver_parameters=sp_)
+        u0 = np.zeros((s.N, s.n_local))
+        u1 = np.zeros((s.N, s.n_local))
+        info = s.solve(u0, u1, loc(ref["b_0"]), loc(ref["b_1"]), solver_parameters=sp_, pc_fn="builtin")
+        e_sol = max(rel(u0, loc(ref["v_blocks"])), rel(u1, loc(ref["zeta_blocks"])))
+        assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1, (info.its, ref["ksp"].its)
+        assert e_sol < 1e-6, e_sol
+        if rank == 0:
+            print(f"CN={CN} world={world}: apply {e_apply:.1e} pc {e_pc:.1e} solve its {info.its}/{ref['ksp'].its} "
+                  f"diff {e_sol:.1e}", flush=True)
+        s.close()
+    dist.barrier()
+    if rank == 0:
+        print("MP_GPU_CHECK_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
