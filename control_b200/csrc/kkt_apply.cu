@@ -180,22 +180,25 @@ __global__ void __launch_bounds__(256) kkt_apply_kernel(const KktArgs a)
 
 // ---------------------------------------------------------------------------------------
 // Staged variant (the one normally launched): a CTA owns `rows_per_cta` consecutive rows.
-// Their CSR entries are contiguous, so the CTA first copies column indices and matrix
-// values into shared memory with fully coalesced loads; afterwards the only global
-// latency a warp sees per row is the gather of the X row segments themselves (the
-// unstaged kernel above serialises indptr -> indices -> X per row and is latency bound:
-// profiles/r01_kkt_apply_v1.txt).
+// Their CSR entries are contiguous, so the CTA first copies them into shared memory with
+// fully coalesced loads, already converted to what the inner loop needs: the BYTE offset of
+// the gathered X row (32 bit) and the (M, K) value pair as one 16-byte word.  Afterwards the
+// only global latency a warp sees per row is the gather of the X row segments themselves.
+// History (profiles/): v1 unstaged = latency bound (1.51 ms); v2 staged = 0.74 ms but issue
+// bound (67% issue slots, 574 M warp instructions of which 11% DFMA: address IMADs, constant
+// reloads, predication selects); v3 below cuts the per-entry overhead to two LDS, one
+// integer add, two LDG.128 and eight DFMA.
 // ---------------------------------------------------------------------------------------
-template <bool CN, bool PER_LEVEL, bool SYM, int G>
+template <bool CN, bool PER_LEVEL, bool SYM, bool HALO, int G>
 __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktArgs a, const int rows_per_cta,
-                                                                 const int cap)
+                                                                     const int cap)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *s_m = reinterpret_cast<double *>(smem_raw);
-    double *s_k = s_m + cap;
-    double *s_kt = SYM ? s_k : s_k + cap;
-    int *s_col = reinterpret_cast<int *>((PER_LEVEL ? s_m + cap : (SYM ? s_k + cap : s_kt + cap)));
-    int *s_ptr = s_col + cap;
+    // layout: [cap+1] double2 (m, k) | [cap+1] double kt (only !SYM) | [cap+1] unsigned off | [rows+1] int ptr
+    double2 *s_mk = reinterpret_cast<double2 *>(smem_raw);
+    double *s_kt = reinterpret_cast<double *>(s_mk + (cap + 1));
+    unsigned *s_off = reinterpret_cast<unsigned *>(SYM || PER_LEVEL ? s_kt : s_kt + (cap + 1));
+    int *s_ptr = reinterpret_cast<int *>(s_off + (cap + 1));
 
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -204,18 +207,29 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
     const int ld = a.ld;
     const int r0 = blockIdx.x * rows_per_cta;
     const int nrows = min(rows_per_cta, a.n_rows - r0);
+    const int n_own = a.n_own_cols;
+    const char *__restrict__ xv_b = reinterpret_cast<const char *>(a.xv);
+    const char *__restrict__ xz_b = reinterpret_cast<const char *>(a.xz);
+    const char *__restrict__ hv_b = reinterpret_cast<const char *>(a.hv);
+    const char *__restrict__ hz_b = reinterpret_cast<const char *>(a.hz);
+    const unsigned lane_b = (unsigned)c0 * 8u;
+    const unsigned row_b = (unsigned)ld * 8u;
 
     for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
     __syncthreads();
     const int kb = s_ptr[0];
     const int cnt = s_ptr[nrows] - kb;
     for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-        s_col[k] = __ldg(a.indices + kb + k);
-        s_m[k] = __ldg(a.Mv + kb + k);
-        if (!PER_LEVEL) {
-            s_k[k] = __ldg(a.Kv + kb + k);
-            if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
-        }
+        const int c = __ldg(a.indices + kb + k);
+        // ghost rows (HALO) are addressed relative to the halo buffers: flag them in bit 31
+        s_off[k] = (HALO && c >= n_own) ? (0x80000000u | ((unsigned)(c - n_own) * row_b)) : (unsigned)c * row_b;
+        s_mk[k] = make_double2(__ldg(a.Mv + kb + k), PER_LEVEL ? 0.0 : __ldg(a.Kv + kb + k));
+        if (!PER_LEVEL && !SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+    }
+    if (threadIdx.x == 0) {          // sentinel entry: zero values, a valid row to gather
+        s_off[cap] = 0u;
+        s_mk[cap] = make_double2(0.0, 0.0);
+        if (!PER_LEVEL && !SYM) s_kt[cap] = 0.0;
     }
     __syncthreads();
 
@@ -223,8 +237,10 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
     const bool first = (l == 0), last = (l == G - 1);
     const int N = a.N;
     const bool in0 = c0 < N, in1 = c0 + 1 < N;
+    const double tau = a.tau, beta = a.beta;
+    const int nwarps = blockDim.x >> 5;
 
-    for (int base = wid * RPW; base < nrows; base += (blockDim.x >> 5) * RPW) {
+    for (int base = wid * RPW; base < nrows; base += nwarps * RPW) {
         const int lr_raw = base + sub;
         const bool live = lr_raw < nrows;
         const int lr = live ? lr_raw : nrows - 1;
@@ -232,46 +248,52 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
         const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
         double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
         for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
+            unsigned off[SCHUNK];
+            int kk[SCHUNK];
+#pragma unroll
+            for (int j = 0; j < SCHUNK; ++j) {
+                kk[j] = (k0 + j < kend) ? k0 + j : cap;       // padding slots read the sentinel
+                off[j] = s_off[kk[j]];
+            }
             double2 xv[SCHUNK], xz[SCHUNK];
 #pragma unroll
             for (int j = 0; j < SCHUNK; ++j) {
-                const int k = k0 + j;
-                const int c = (k < kend) ? s_col[k] : r;
-                const bool own = c < a.n_own_cols;
-                const double *pv = own ? a.xv + (size_t)c * ld : a.hv + (size_t)(c - a.n_own_cols) * ld;
-                const double *pz = own ? a.xz + (size_t)c * ld : a.hz + (size_t)(c - a.n_own_cols) * ld;
-                xv[j] = ldg2(pv + c0);
-                xz[j] = ldg2(pz + c0);
+                if (HALO && (off[j] & 0x80000000u)) {
+                    const unsigned o = (off[j] & 0x7fffffffu) + lane_b;
+                    xv[j] = __ldg(reinterpret_cast<const double2 *>(hv_b + o));
+                    xz[j] = __ldg(reinterpret_cast<const double2 *>(hz_b + o));
+                } else {
+                    const unsigned o = off[j] + lane_b;
+                    xv[j] = __ldg(reinterpret_cast<const double2 *>(xv_b + o));
+                    xz[j] = __ldg(reinterpret_cast<const double2 *>(xz_b + o));
+                }
             }
 #pragma unroll
             for (int j = 0; j < SCHUNK; ++j) {
-                const int k = k0 + j;
-                if (k < kend) {
-                    const double m = s_m[k];
-                    mv0 = fma(m, xv[j].x, mv0);
-                    mv1 = fma(m, xv[j].y, mv1);
-                    mz0 = fma(m, xz[j].x, mz0);
-                    mz1 = fma(m, xz[j].y, mz1);
-                    if (!PER_LEVEL) {
-                        const double kk = s_k[k], kt = s_kt[k];
-                        kv0 = fma(kk, xv[j].x, kv0);
-                        kv1 = fma(kk, xv[j].y, kv1);
-                        kz0 = fma(kt, xz[j].x, kz0);
-                        kz1 = fma(kt, xz[j].y, kz1);
-                    } else {
-                        const double2 kk = ldg2(a.Kv + (size_t)(kb + k) * ld + c0);
-                        const double2 kt = ldg2(a.KTv + (size_t)(kb + k) * ld + c0);
-                        kv0 = fma(kk.x, xv[j].x, kv0);
-                        kv1 = fma(kk.y, xv[j].y, kv1);
-                        kz0 = fma(kt.x, xz[j].x, kz0);
-                        kz1 = fma(kt.y, xz[j].y, kz1);
-                    }
+                const double2 mk = s_mk[kk[j]];
+                mv0 = fma(mk.x, xv[j].x, mv0);
+                mv1 = fma(mk.x, xv[j].y, mv1);
+                mz0 = fma(mk.x, xz[j].x, mz0);
+                mz1 = fma(mk.x, xz[j].y, mz1);
+                if (!PER_LEVEL) {
+                    const double kt = SYM ? mk.y : s_kt[kk[j]];
+                    kv0 = fma(mk.y, xv[j].x, kv0);
+                    kv1 = fma(mk.y, xv[j].y, kv1);
+                    kz0 = fma(kt, xz[j].x, kz0);
+                    kz1 = fma(kt, xz[j].y, kz1);
+                } else if (kk[j] != cap) {
+                    const double2 kp = ldg2(a.Kv + (size_t)(kb + kk[j]) * ld + c0);
+                    const double2 kt = ldg2(a.KTv + (size_t)(kb + kk[j]) * ld + c0);
+                    kv0 = fma(kp.x, xv[j].x, kv0);
+                    kv1 = fma(kp.y, xv[j].y, kv1);
+                    kz0 = fma(kt.x, xz[j].x, kz0);
+                    kz1 = fma(kt.y, xz[j].y, kz1);
                 }
             }
         }
         double y00, y01, y10, y11;
         if (CN) {
-            const double h = 0.5 * a.tau, hb = h / a.beta;
+            const double h = 0.5 * tau, hb = h / beta;
             double t;
             t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
             t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
@@ -290,7 +312,7 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
             y10 = r10 + r1p;
             y11 = r11 + r10;
         } else {
-            const double tau = a.tau, tb = tau / a.beta;
+            const double tb = tau / beta;
             double t;
             t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
             t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
@@ -302,29 +324,36 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
         if (!in0) { y00 = 0.0; y10 = 0.0; }
         if (!in1) { y01 = 0.0; y11 = 0.0; }
         if (live) {
+            const size_t ro = (size_t)r * ld + c0;
             if (a.bcmask[r]) {
-                const double2 xv = ldg2(a.xv + (size_t)r * ld + c0);
-                const double2 xz = ldg2(a.xz + (size_t)r * ld + c0);
+                const double2 xv = ldg2(a.xv + ro);
+                const double2 xz = ldg2(a.xz + ro);
                 y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
             }
-            *reinterpret_cast<double2 *>(a.y0 + (size_t)r * ld + c0) = make_double2(y00, y01);
-            *reinterpret_cast<double2 *>(a.y1 + (size_t)r * ld + c0) = make_double2(y10, y11);
+            *reinterpret_cast<double2 *>(a.y0 + ro) = make_double2(y00, y01);
+            *reinterpret_cast<double2 *>(a.y1 + ro) = make_double2(y10, y11);
         }
     }
 }
 
-template <bool CN, bool PER_LEVEL, bool SYM>
-void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, cudaStream_t s)
+template <bool CN, bool PER_LEVEL, bool SYM, bool HALO>
+void launch_staged_h(const KktArgs &a, int G, int rows_per_cta, int cap, cudaStream_t s)
 {
     const int blocks = ceil_div(a.n_rows, rows_per_cta);
-    const int nval = PER_LEVEL ? 1 : (SYM ? 2 : 3);
-    const size_t smem = (size_t)cap * (8 * nval + 4) + (size_t)(rows_per_cta + 1) * 4;
+    const size_t smem = (size_t)(cap + 1) * (16 + ((SYM || PER_LEVEL) ? 0 : 8) + 4) + (size_t)(rows_per_cta + 1) * 4;
     switch (G) {
-    case 4: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 4><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    case 8: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 8><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    case 16: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 16><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    default: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, 32><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    case 4: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 4><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    case 8: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 8><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    case 16: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 16><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+    default: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 32><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
     }
+}
+
+template <bool CN, bool PER_LEVEL, bool SYM>
+void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, bool halo, cudaStream_t s)
+{
+    if (halo) launch_staged_h<CN, PER_LEVEL, SYM, true>(a, G, rows_per_cta, cap, s);
+    else launch_staged_h<CN, PER_LEVEL, SYM, false>(a, G, rows_per_cta, cap, s);
 }
 
 template <bool CN, bool PER_LEVEL>
@@ -372,18 +401,21 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     // rows per CTA: as many consecutive rows as fit the shared-memory entry budget
     const int max_len = std::max(1, h->max_row_len);
     int rows_per_cta = std::min(64, (STAGE_CAP / max_len) / 8 * 8);
-    const bool staged = rows_per_cta >= 8 && !h->force_unstaged;
+    // the staged kernel addresses gathered rows with 31-bit byte offsets
+    const bool fits = (size_t)std::max(h->n_loc, h->n_halo) * h->ld * 8 < 0x7fffffffull;
+    const bool staged = rows_per_cta >= 8 && !h->force_unstaged && fits;
+    const bool halo = h->n_halo > 0;
     if (staged) {
         const int cap = rows_per_cta * max_len;
         const bool sym = h->d_KT == h->d_K;
         if (h->cfg.CN) {
-            if (h->per_level) launch_staged<true, true, false>(a, G, rows_per_cta, cap, h->stream);
-            else if (sym) launch_staged<true, false, true>(a, G, rows_per_cta, cap, h->stream);
-            else launch_staged<true, false, false>(a, G, rows_per_cta, cap, h->stream);
+            if (h->per_level) launch_staged<true, true, false>(a, G, rows_per_cta, cap, halo, h->stream);
+            else if (sym) launch_staged<true, false, true>(a, G, rows_per_cta, cap, halo, h->stream);
+            else launch_staged<true, false, false>(a, G, rows_per_cta, cap, halo, h->stream);
         } else {
-            if (h->per_level) launch_staged<false, true, false>(a, G, rows_per_cta, cap, h->stream);
-            else if (sym) launch_staged<false, false, true>(a, G, rows_per_cta, cap, h->stream);
-            else launch_staged<false, false, false>(a, G, rows_per_cta, cap, h->stream);
+            if (h->per_level) launch_staged<false, true, false>(a, G, rows_per_cta, cap, halo, h->stream);
+            else if (sym) launch_staged<false, false, true>(a, G, rows_per_cta, cap, halo, h->stream);
+            else launch_staged<false, false, false>(a, G, rows_per_cta, cap, halo, h->stream);
         }
     } else if (h->cfg.CN) {
         if (h->per_level) launch_g<true, true>(a, G, h->stream);

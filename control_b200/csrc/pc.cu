@@ -510,24 +510,35 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
     cudaEvent_t e0, e1;
     CTL_CUDA(cudaEventCreate(&e0));
     CTL_CUDA(cudaEventCreate(&e1));
+    // Each kernel is timed as (reps x [flush, kernel]) minus (reps x [flush]) between ONE pair of
+    // events: an event pair around a single 25 us launch would add several microseconds of
+    // record / launch latency to it.
     double acc[3] = {0, 0, 0};
     int64_t launches_solve = 0;
     int rc = CTL_OK;
-    for (int which = 0; which < 3 && rc == CTL_OK; ++which) {
-        for (int r = -2; r < reps && rc == CTL_OK; ++r) {       // two warm-up launches
+    auto timed = [&](int which, bool with_kernel, float *ms) -> int {
+        int r2 = CTL_OK;
+        cudaEventRecord(e0, h->stream);
+        for (int r = 0; r < reps && r2 == CTL_OK; ++r) {
             if (flush) cudaMemsetAsync(flush, r & 0xff, flush_bytes, h->stream);
-            cudaEventRecord(e0, h->stream);
+            if (!with_kernel) continue;
             const int64_t l0 = h->launches;
-            if (which == 0) rc = sell_cheb_step(h, L0.A, L0.dinv, b, x, b, L0.t0, 0.3, 0.7, 0.1);
-            else if (which == 1) rc = sell_spmv(h, L0.A, b, L0.r, x, SELL_RESIDUAL);
-            else rc = amg_solve(h, H, b, x);
+            if (which == 0) r2 = sell_cheb_step(h, L0.A, L0.dinv, b, x, b, L0.t0, 0.3, 0.7, 0.1);
+            else if (which == 1) r2 = sell_spmv(h, L0.A, b, L0.r, x, SELL_RESIDUAL);
+            else r2 = amg_solve(h, H, b, x);
             launches_solve = h->launches - l0;
-            cudaEventRecord(e1, h->stream);
-            cudaEventSynchronize(e1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, e0, e1);
-            if (r >= 0) acc[which] += ms;
         }
+        cudaEventRecord(e1, h->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(ms, e0, e1);
+        return r2;
+    };
+    for (int which = 0; which < 3 && rc == CTL_OK; ++which) {
+        float warm = 0.f, with_k = 0.f, without_k = 0.f;
+        rc = timed(which, true, &warm);
+        if (rc == CTL_OK) rc = timed(which, true, &with_k);
+        if (rc == CTL_OK) rc = timed(which, false, &without_k);
+        acc[which] = with_k - (flush ? without_k : 0.f);
     }
     const double nnz = (double)L0.A.pat->nnz;
     out[0] = acc[0] / reps;

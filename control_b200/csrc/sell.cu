@@ -95,15 +95,34 @@ namespace {
 
 constexpr int ST = 128;
 
+// One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is
+// divergence free; entries are fetched in chunks of SC with all index/value loads issued
+// before the dependent gathers of x (memory-level parallelism instead of a serial
+// load -> gather -> fma chain per entry).
+constexpr int SC = 8;
 __device__ __forceinline__ double sell_row_dot(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
                                                const double *__restrict__ vals, const double *__restrict__ x,
                                                int row)
 {
     const int s = row >> 5, lane = row & 31;
-    const int beg = __ldg(slice_ptr + s), end = __ldg(slice_ptr + s + 1);
+    const int beg = __ldg(slice_ptr + s) + lane, end = __ldg(slice_ptr + s + 1);
     double acc = 0.0;
-#pragma unroll 4
-    for (int p = beg + lane; p < end; p += 32) acc = fma(__ldg(vals + p), __ldg(x + __ldg(cols + p)), acc);
+    for (int p0 = beg; p0 < end; p0 += 32 * SC) {
+        int c[SC];
+        double v[SC];
+#pragma unroll
+        for (int j = 0; j < SC; ++j) {
+            const int p = p0 + 32 * j;
+            const bool ok = p < end;
+            c[j] = ok ? __ldg(cols + p) : 0;
+            v[j] = ok ? __ldg(vals + p) : 0.0;
+        }
+        double xv[SC];
+#pragma unroll
+        for (int j = 0; j < SC; ++j) xv[j] = __ldg(x + c[j]);
+#pragma unroll
+        for (int j = 0; j < SC; ++j) acc = fma(v[j], xv[j], acc);
+    }
     return acc;
 }
 
