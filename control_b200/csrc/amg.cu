@@ -170,6 +170,7 @@ namespace {
 __global__ void lincomb3_kernel(double *out, double a, const double *x, double b, const double *__restrict__ y,
                                 double c, const double *__restrict__ z, int n)
 {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double r = c * z[i];
@@ -195,14 +196,14 @@ int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x)
     auto slot = [&](int k) { return (p.cycles - k) & 1; };      // p_cycles lands in x
     const int blocks = ceil_div(n, 256);
     CTL_TRY(vcycle(h, H, 0, b, H.acc_z, true));
-    lincomb3_kernel<<<blocks, 256, 0, h->stream>>>(buf[slot(1)], 0.0, nullptr, 0.0, nullptr, scale, H.acc_z, n);
+    pdl_launch(h, blocks, 256, lincomb3_kernel, buf[slot(1)], 0.0, nullptr, 0.0, nullptr, scale, H.acc_z, n);
     h->launches++;
     for (int k = 2; k <= p.cycles; ++k) {
         const double w = om[k - 2];
         CTL_TRY(halo0(h, 0, buf[slot(k - 1)]));
         CTL_TRY(sell_spmv(h, H.dev[0].A, buf[slot(k - 1)], H.acc_r, b, SELL_RESIDUAL));
         CTL_TRY(vcycle(h, H, 0, H.acc_r, H.acc_z, true));
-        lincomb3_kernel<<<blocks, 256, 0, h->stream>>>(buf[slot(k)], 1.0 - w, k == 2 ? nullptr : buf[slot(k - 2)], w,
+        pdl_launch(h, blocks, 256, lincomb3_kernel, buf[slot(k)], 1.0 - w, k == 2 ? nullptr : buf[slot(k - 2)], w,
                                                       buf[slot(k - 1)], w * scale, H.acc_z, n);
         h->launches++;
     }

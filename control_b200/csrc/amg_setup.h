@@ -9,7 +9,7 @@
 struct AmgParams {
     double theta = 0.08;
     int max_levels = 10;
-    int coarse_max = 200;
+    int coarse_max = 600;   // dense inverse below this size (one GEMV instead of two more levels of launches)
     int nu = 3;
     double lo = 0.25, hi = 1.0;
     int cycles = 4;      // see oracle/amg.py::solve for why not the reference's 2

@@ -101,6 +101,7 @@ int ctl_create(const ctl_config *cfg, ctl_handle *out)
         h->own_stream = true;
     }
     h->h_bcmask.assign(cfg->n, 0);
+    if (const char *e = getenv("CTL_NO_PDL")) h->use_pdl = !(e[0] == '1');
     *out = h;
     return CTL_OK;
 }

@@ -60,6 +60,7 @@ struct ctl_handle_s {
     std::string err;
     int64_t launches = 0;
     bool assembled = false;
+    bool use_pdl = true;       // programmatic dependent launch for the chains of small sweep kernels (CTL_NO_PDL=1 disables)
 
     // host copies of what the caller handed over (global numbering)
     std::vector<int> h_indptr, h_indices;
@@ -133,3 +134,34 @@ template <typename T>
 int ctl_upload(ctl_handle_s *h, T **dst, const T *src, size_t count);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// Programmatic dependent launch (sm_90+): the time sweeps are chains of ~10^4 small dependent
+// kernels per preconditioner application, so the gap between two launches matters as much as
+// the kernels.  A kernel launched through pdl_launch may be scheduled while its predecessor
+// drains; it calls pdl_sync() before its first global memory access, which (a) lets ITS
+// successor be scheduled early and (b) waits until the predecessor grid has completed and its
+// writes are visible.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync()
+{
+#if __CUDA_ARCH__ >= 900
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline void pdl_launch(ctl_handle_s *h, int grid, int block, void (*kernel)(KArgs...), Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = h->use_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(ST) sell_spmv_kernel(const int *__restrict__ s
                                                       const double *__restrict__ vals, const double *__restrict__ x,
                                                       const double *b, double *y, int n_rows)
 {
+    pdl_sync();
     const int row = blockIdx.x * ST + threadIdx.x;
     if (row >= n_rows) return;
     const double ax = sell_row_dot(slice_ptr, cols, vals, x, row);
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(ST) sell_cheb_kernel(const int *__restrict__ s
                                                       const double *__restrict__ p_cur, double *out, double a,
                                                       double bq, double c, int n_rows)
 {
+    pdl_sync();
     const int row = blockIdx.x * ST + threadIdx.x;
     if (row >= n_rows) return;
     const double ax = sell_row_dot(slice_ptr, cols, vals, p_cur, row);
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(ST) sell_cheb_kernel(const int *__restrict__ s
 __global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
                                                        double *__restrict__ out, double c, int n)
 {
+    pdl_sync();
     const int i = blockIdx.x * ST + threadIdx.x;
     if (i < n) out[i] = c * dinv[i] * b[i];
 }
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict
 __global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
                                                        double *__restrict__ y, int n)
 {
+    pdl_sync();
     const int row = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const int *__restrict__ 
                                                        const double *__restrict__ x3, double *__restrict__ y,
                                                        double alpha, double beta, int n_rows)
 {
+    pdl_sync();
     const int row = blockIdx.x * ST + threadIdx.x;
     if (row >= n_rows) return;
     const int s = row >> 5, lane = row & 31;
@@ -215,6 +220,7 @@ __global__ void __launch_bounds__(ST) csrv_spmv_kernel(const int *__restrict__ p
                                                       const double *__restrict__ vals, const double *__restrict__ x,
                                                       const double *b, double *y, int n_rows)
 {
+    pdl_sync();
     const int t = blockIdx.x * ST + threadIdx.x;
     const int row = t / T, lane = t % T;
     const int r = row < n_rows ? row : n_rows - 1;       // whole warp takes part in the shuffles
@@ -233,6 +239,7 @@ __global__ void __launch_bounds__(ST) csrv_cheb_kernel(const int *__restrict__ p
                                                       const double *__restrict__ p_cur, double *out, double a,
                                                       double bq, double c, int n_rows)
 {
+    pdl_sync();
     const int t = blockIdx.x * ST + threadIdx.x;
     const int row = t / T, lane = t % T;
     const int r = row < n_rows ? row : n_rows - 1;
@@ -248,10 +255,10 @@ void launch_csrv_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double
 {
     const int n = A.pat->n_rows, blocks = ceil_div((int64_t)n * T, ST);
     switch (mode) {
-    case SELL_ASSIGN: csrv_spmv_kernel<SELL_ASSIGN, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_RESIDUAL: csrv_spmv_kernel<SELL_RESIDUAL, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_ADD: csrv_spmv_kernel<SELL_ADD, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    default: csrv_spmv_kernel<SELL_SUB, T><<<blocks, ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_ASSIGN: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ASSIGN, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_RESIDUAL, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_ADD: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ADD, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    default: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_SUB, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
     }
 }
 
@@ -271,10 +278,10 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, con
         return CTL_OK;
     }
     switch (mode) {
-    case SELL_ASSIGN: sell_spmv_kernel<SELL_ASSIGN><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    case SELL_RESIDUAL: sell_spmv_kernel<SELL_RESIDUAL><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    case SELL_ADD: sell_spmv_kernel<SELL_ADD><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    default: sell_spmv_kernel<SELL_SUB><<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    case SELL_ASSIGN: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_ASSIGN>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_RESIDUAL>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    case SELL_ADD: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_ADD>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
+    default: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_SUB>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
     }
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -290,16 +297,16 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
     if (A.lanes) {
         const int n = p.n_rows;
         if (A.lanes == 8)
-            csrv_cheb_kernel<8><<<ceil_div((int64_t)n * 8, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+            pdl_launch(h, ceil_div((int64_t)n * 8, ST), ST, csrv_cheb_kernel<8>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
         else if (A.lanes == 16)
-            csrv_cheb_kernel<16><<<ceil_div((int64_t)n * 16, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+            pdl_launch(h, ceil_div((int64_t)n * 16, ST), ST, csrv_cheb_kernel<16>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
         else
-            csrv_cheb_kernel<32><<<ceil_div((int64_t)n * 32, ST), ST, 0, h->stream>>>(A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+            pdl_launch(h, ceil_div((int64_t)n * 32, ST), ST, csrv_cheb_kernel<32>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
         h->launches++;
         CTL_CUDA(cudaGetLastError());
         return CTL_OK;
     }
-    sell_cheb_kernel<<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A.vals, dinv, b, p_prev, p_cur, out, a,
+    pdl_launch(h, blocks, ST, sell_cheb_kernel, p.slice_ptr, p.cols, A.vals, dinv, b, p_prev, p_cur, out, a,
                                                    bq, c, p.n_rows);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -309,7 +316,7 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
 int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n)
 {
     if (n == 0) return CTL_OK;
-    dinv_scale_kernel<<<ceil_div(n, ST), ST, 0, h->stream>>>(dinv, b, out, c, n);
+    pdl_launch(h, ceil_div(n, ST), ST, dinv_scale_kernel, dinv, b, out, c, n);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -318,7 +325,7 @@ int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double 
 int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
 {
     if (n == 0) return CTL_OK;
-    dense_gemv_kernel<<<ceil_div(n, ST / 32), ST, 0, h->stream>>>(Ainv, b, y, n);
+    pdl_launch(h, ceil_div(n, ST / 32), ST, dense_gemv_kernel, Ainv, b, y, n);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -330,7 +337,7 @@ int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const doub
     const SellPattern &p = *A1.pat;
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
-    sell_spmv2_kernel<<<blocks, ST, 0, h->stream>>>(p.slice_ptr, p.cols, A1.vals, A2.vals, x1, x2, x3, y, alpha,
+    pdl_launch(h, blocks, ST, sell_spmv2_kernel, p.slice_ptr, p.cols, A1.vals, A2.vals, x1, x2, x3, y, alpha,
                                                     beta, p.n_rows);
     h->launches++;
     CTL_CUDA(cudaGetLastError());

@@ -35,7 +35,7 @@ except Exception:                          # pragma: no cover
         return f
 
 
-DEFAULTS = dict(theta=0.08, max_levels=10, coarse_max=200, nu=3, lo=0.25, hi=1.0, cycles=4,
+DEFAULTS = dict(theta=0.08, max_levels=10, coarse_max=600, nu=3, lo=0.25, hi=1.0, cycles=4,
                 acc_lo=0.0, acc_hi=1.0)
 
 

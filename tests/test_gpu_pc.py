@@ -28,12 +28,13 @@ def _rel(a, b):
 def test_amg_hierarchy_matches_oracle_setup():
     q = kat.heat_problem(40, 8, True)
     s = _system(q, True)
-    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"])
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], coarse_max=50)
     tau, beta = s.tau, q["beta"]
     c = 0.5 * tau / beta ** 0.5
     A = fem.assemble_bc((0.5 * tau * q["K"] + (1 + c) * q["M"]).tocsr(), q["bdofs"])
-    H = oamg.setup(A)
+    H = oamg.setup(A, coarse_max=50)
     G = s.amg_hierarchy(0)
+    assert len(G) >= 3
     assert [e["n"] for e in G] == [L.A.shape[0] for L in H.levels]
     for e, L in zip(G, H.levels):
         assert abs(e["A"] - L.A).max() <= 1e-13 * abs(L.A).max()
@@ -279,7 +280,7 @@ def test_accelerated_amg_solve_matches_oracle():
     """Chebyshev-accelerated V-cycles (oracle/amg.py::solve with acc_lo > 0)."""
     q = kat.heat_problem(40, 6, True)
     s = _system(q, True)
-    params = dict(cycles=4, nu=3, acc_lo=0.5, acc_hi=1.0)
+    params = dict(cycles=4, nu=3, acc_lo=0.5, acc_hi=1.0, coarse_max=50)
     s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], **params)
     c = 0.5 * s.tau / q["beta"] ** 0.5
     A = fem.assemble_bc((0.5 * s.tau * q["K"] + (1 + c) * q["M"]).tocsr(), q["bdofs"])

@@ -186,7 +186,7 @@ def test_amg_vcycle_contracts_and_is_symmetric():
     tau, beta = 2.0 / 63, 1e-4
     c = 0.5 * tau / beta ** 0.5
     A = fem.assemble_bc((0.5 * tau * K + (1 + c) * M).tocsr(), bd)
-    H = amg.setup(A)
+    H = amg.setup(A, coarse_max=60)
     assert len(H.levels) >= 3 and H.levels[-1].Ainv is not None
     rng = np.random.default_rng(0)
     xs = rng.standard_normal(A.shape[0])
