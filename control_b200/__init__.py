@@ -5,6 +5,7 @@ in-built block preconditioner -- behind the reference's own ``P=`` / ``solver_pa
 from . import _lib
 from ._lib import CtlError
 from . import partition
+from .control import Control
 from .system import KSPInfo, MultiBlockSystem, csr_arrays
 
-__all__ = ["MultiBlockSystem", "KSPInfo", "CtlError", "csr_arrays", "partition", "_lib"]
+__all__ = ["Control", "MultiBlockSystem", "KSPInfo", "CtlError", "csr_arrays", "partition", "_lib"]

@@ -1,0 +1,277 @@
+"""Host-side mirror of ``Control.Instationary`` for the heat-control path (the caller of the
+hot path: SURVEY.md section 8 rows a8, a11).
+
+In the reference this layer is UFL/Firedrake: it builds the block dicts, assembles the
+right-hand sides and drives ``MultiBlockSystem.solve`` (control/control.py:2820-3375) and the
+Picard / Gauss-Newton loop (control/control.py:3377-3590, residual 2442-2818).  Here the same
+driver works on ASSEMBLED objects -- the mass matrix, a callable returning the matrix of
+``forward_form`` (or of its derivative) at a given state and time, nodal data tested against
+the basis -- because only those ever reach the CUDA library.  Host work in this file is the
+small vector algebra Firedrake does on the CPU in the reference (right-hand sides, residuals,
+unpacking); every solve runs on the GPU through ``MultiBlockSystem``.
+
+Keeps the reference's names, keyword arguments and defaults, including both spellings of the
+force keyword (``force_function`` in the constructor, control/control.py:1490, ``force_f`` in
+README.md:57 and every test).
+"""
+import numpy as np
+
+from .system import MultiBlockSystem
+
+__all__ = ["Control"]
+
+
+def _apply_T_1(x):      # control/control.py:26-41
+    y = x.copy()
+    y[:-1] += x[1:]
+    return y
+
+
+def _apply_T_2(x):      # control/control.py:44-59
+    y = x.copy()
+    y[1:] += x[:-1]
+    return y
+
+
+class Control:
+    class Instationary:
+        def __init__(self, M, forward_matrix, *, desired_state=None, force_f=None, force_function=None,
+                     beta=1.0e-3, Gauss_Newton=False, CN=True, n_t=20, initial_condition=None,
+                     time_interval=(0.0, 1.0), bc_dofs=(), device=None, rank=0, world=1):
+            """``M``: mass matrix (scipy CSR).  ``forward_matrix(v_i, t, gauss_newton)`` -> CSR
+            on M's pattern: the matrix ``D_v`` of ``construct_D_v`` (control.py:1887-1896) at
+            state ``v_i`` and time ``t``; a plain CSR matrix means a linear, time-independent
+            operator.  ``desired_state(t)`` -> (M @ v_hat(t), v_hat(t)), the two returns of
+            the reference's callable (control.py:1929-1931); ``force_f(t)`` -> M @ f(t)."""
+            if force_f is not None and force_function is not None:
+                raise TypeError("give either force_f or force_function")
+            self._M = M.tocsr()
+            self._forward_matrix = forward_matrix
+            self._desired_state = desired_state
+            self._force = force_f if force_f is not None else force_function
+            self._beta = float(beta)
+            self._Gauss_Newton = bool(Gauss_Newton)
+            self._CN = bool(CN)
+            self._n_t = int(n_t)
+            self._time_interval = tuple(time_interval)
+            self._bc_dofs = np.ascontiguousarray(bc_dofs, dtype=np.int32)
+            self._initial_condition = initial_condition
+            self._n = self._M.shape[0]
+            self._v = np.zeros((self._n_t, self._n))          # control.py:1569-1597
+            self._zeta = np.zeros((self._n_t, self._n))
+            self._system = None
+            self._dev = dict(device=device, rank=rank, world=world)
+            self.last_ksp = None
+            self.non_linear_history = []
+
+        # ------------------------------------------------------------------ helpers
+        @property
+        def tau(self):
+            t_0, T_f = self._time_interval
+            return (T_f - t_0) / (self._n_t - 1.0)
+
+        def _times(self):
+            return self._time_interval[0] + self.tau * np.arange(self._n_t)
+
+        def _is_linear(self):
+            return not callable(self._forward_matrix)
+
+        def construct_D_v(self, v_i, t):
+            if self._is_linear():
+                return self._forward_matrix
+            return self._forward_matrix(v_i, t, self._Gauss_Newton)
+
+        def _K_levels(self, v):
+            if self._is_linear():
+                return self._forward_matrix
+            return [self.construct_D_v(v[i], t) for i, t in enumerate(self._times())]
+
+        def construct_f(self):          # control.py:1898-1916
+            if self._force is None:
+                return np.zeros((self._n_t, self._n))
+            return np.stack([self._force(t) for t in self._times()])
+
+        def construct_v_d(self):        # control.py:1918-1941
+            if self._desired_state is None:
+                self._true_v = np.zeros((self._n_t, self._n))
+                return np.zeros((self._n_t, self._n))
+            pairs = [self._desired_state(t) for t in self._times()]
+            self._true_v = np.stack([p[1] for p in pairs])
+            return np.stack([p[0] for p in pairs])
+
+        def _bc(self, b):
+            b[..., self._bc_dofs] = 0.0
+
+        def _ensure_system(self, K):
+            if self._system is None:
+                self._system = MultiBlockSystem(self._M, K, n_t=self._n_t, beta=self._beta, CN=self._CN,
+                                                time_interval=self._time_interval, bc_dofs=self._bc_dofs,
+                                                **self._dev)
+                if self._dev["world"] > 1:
+                    self._system.init_comm()
+            else:
+                self._system.set_K(K)
+            return self._system
+
+        def close(self):
+            if self._system is not None:
+                self._system.close()
+                self._system = None
+
+        # ------------------------------------------------------------------ linear_solve
+        def linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
+                         v_d=None, f=None, print_error=True, create_output=False, plots=False,
+                         pc_mode="triangular", **amg):
+            """control/control.py:2820-3375 (homogeneous Dirichlet data)."""
+            n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
+            M = self._M
+            N = n_t - 1 if CN else n_t
+            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
+            check_f, check_v_d = f is None, v_d is None
+            if check_f:
+                f = self.construct_f()
+            if check_v_d:
+                v_d = self.construct_v_d()
+            K = self._K_levels(self._v)                         # D_v at self._v, control.py:2884-2904
+            K0 = K if self._is_linear() else self.construct_D_v(v_0, self._time_interval[0])
+            b_0 = np.zeros((N, n))
+            b_1 = np.zeros((N, n))
+            if not CN:                                          # control.py:2990-3130
+                if check_v_d:
+                    b_0[:n_t - 1] = tau * v_d[:n_t - 1]
+                    self._bc(b_0)
+                else:
+                    b_0[:] = v_d
+                if check_f:
+                    b_1[0] = tau * (K0 @ v_0) + M @ v_0
+                    b_1[1:] = tau * f[1:]
+                    self._bc(b_1)
+                else:
+                    b_1[:] = f
+            else:                                               # control.py:3131-3243
+                if check_v_d:
+                    b_0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+                    self._bc(b_0)
+                    b_0[0] -= 0.5 * tau * (M @ v_0)
+                    self._bc(b_0[0])
+                else:
+                    b_0[:] = v_d
+                if check_f:
+                    b_1[:] = 0.5 * tau * (f[:-1] + f[1:])
+                    self._bc(b_1)
+                    b_1[0] -= 0.5 * tau * (K0 @ v_0) - M @ v_0
+                    self._bc(b_1[0])
+                else:
+                    b_1[:] = f
+                b_0 = _apply_T_1(b_0)
+                b_1 = _apply_T_2(b_1)
+            if solver_parameters is None:                       # control.py:3260-3266
+                solver_parameters = {"linear_solver": "gmres", "gmres_restart": 10, "maximum_iterations": 50,
+                                     "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0,
+                                     "monitor_convergence": print_error}
+            system = self._ensure_system(K)
+            if P is None:                                       # control.py:3245-3258
+                system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, Multigrid=Multigrid,
+                                            mode=pc_mode, **amg)
+                pc_fn = "builtin"
+            else:
+                pc_fn = P
+            rows = slice(system.row_begin, system.row_begin + system.n_local)
+            v = np.zeros((N, system.n_local))
+            zeta = np.zeros((N, system.n_local))
+            self.last_ksp = system.solve(v, zeta, np.ascontiguousarray(b_0[:, rows]),
+                                         np.ascontiguousarray(b_1[:, rows]),
+                                         solver_parameters=solver_parameters, pc_fn=pc_fn)
+            if system.world > 1:
+                v, zeta = system.allgather_blocks(v), system.allgather_blocks(zeta)
+            if CN:                                              # control.py:3299-3312
+                v_new = np.zeros((n_t, n))
+                zeta_new = np.zeros((n_t, n))
+                if check_f and check_v_d:
+                    v_new[0] = v_0
+                v_new[1:] = v
+                zeta_new[:-1] = zeta
+                self._v, self._zeta = v_new, zeta_new
+            else:
+                self._v, self._zeta = v, zeta
+            self._bc(self._zeta)                                # set_zeta re-applies bcs, control.py:1847-1856
+            return self.last_ksp
+
+        # ------------------------------------------------------------------ non_linear_solve
+        def non_linear_res_eval(self, v_old, zeta_old, v_0, v_d, f):
+            """control/control.py:2442-2818: right-hand side minus the KKT operator applied to
+            the current iterate, row by row, with D_v evaluated at the iterate."""
+            n_t, n, tau, beta, CN, M = self._n_t, self._n, self.tau, self._beta, self._CN, self._M
+            times = self._times()
+            D = [self.construct_D_v(v_old[i], times[i]) for i in range(n_t)]
+            if CN:
+                h = 0.5 * tau
+                rhs_0 = np.zeros((n_t - 1, n))
+                rhs_1 = np.zeros((n_t - 1, n))
+                for i in range(n_t - 1):                        # control.py:2621-2814
+                    rhs_0[i] = h * (v_d[i] + v_d[i + 1]) - h * (M @ v_old[i]) - h * (M @ v_old[i + 1]) \
+                        - (h * (D[i].T @ zeta_old[i]) + M @ zeta_old[i]) \
+                        - (h * (D[i + 1].T @ zeta_old[i + 1]) - M @ zeta_old[i + 1])
+                    rhs_1[i] = h * (f[i] + f[i + 1]) - (h * (D[i] @ v_old[i]) - M @ v_old[i]) \
+                        - (h * (D[i + 1] @ v_old[i + 1]) + M @ v_old[i + 1]) \
+                        + (h / beta) * (M @ zeta_old[i]) + (h / beta) * (M @ zeta_old[i + 1])
+            else:
+                rhs_0 = np.zeros((n_t, n))
+                rhs_1 = np.zeros((n_t, n))
+                D_v_0 = self.construct_D_v(v_0, times[0])
+                for i in range(n_t):                            # control.py:2457-2620
+                    if i < n_t - 1:
+                        rhs_0[i] = tau * v_d[i] - tau * (M @ v_old[i]) \
+                            - (tau * (D[i].T @ zeta_old[i]) + M @ zeta_old[i]) + M @ zeta_old[i + 1]
+                    else:
+                        rhs_0[i] = -(tau * (D[i].T @ zeta_old[i]) + M @ zeta_old[i])
+                    if i == 0:
+                        rhs_1[0] = (tau * (D_v_0 @ v_0) + M @ v_0) - (tau * (D[0] @ v_old[0]) + M @ v_old[0])
+                    else:
+                        rhs_1[i] = tau * f[i] - (tau * (D[i] @ v_old[i]) + M @ v_old[i]) + M @ v_old[i - 1] \
+                            + (tau / beta) * (M @ zeta_old[i])
+            self._bc(rhs_0)
+            self._bc(rhs_1)
+            return rhs_0, rhs_1
+
+        def non_linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
+                             max_non_linear_iter=10, relative_non_linear_tol=10.0**-5,
+                             absolute_non_linear_tol=10.0**-8, print_error_linear=False,
+                             print_error_non_linear=True, create_output=False, plots=False, **amg):
+            """control/control.py:3377-3590: Picard / Gauss-Newton loop.  Every outer iteration
+            hands new ``K_i`` values to the GPU (``MultiBlockSystem.set_K``) and solves for
+            the increment."""
+            n_t, n = self._n_t, self._n
+            v_old = self._v.copy()
+            zeta_old = self._zeta.copy()
+            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
+            if self._CN:
+                v_old[0] = v_0
+            zeta_old[n_t - 1] = 0.0
+            f = self.construct_f()
+            v_d = self.construct_v_d()
+            self._v, self._zeta = v_old.copy(), zeta_old.copy()
+            rhs_0, rhs_1 = self.non_linear_res_eval(v_old, zeta_old, v_0, v_d, f)
+            norm_0 = float(np.sqrt((rhs_0 ** 2).sum() + (rhs_1 ** 2).sum()))
+            norm_k = norm_0
+            k = 0
+            self.non_linear_history = [norm_0]
+            if print_error_non_linear:
+                print(f"Initial non-linear residual: {norm_0:.16e}")
+            while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+                self.linear_solve(P=P, solver_parameters=solver_parameters, Multigrid=Multigrid,
+                                  lambda_v_bounds=lambda_v_bounds, v_d=rhs_0, f=rhs_1,
+                                  print_error=print_error_linear, **amg)
+                v_old = v_old + self._v
+                zeta_old = zeta_old + self._zeta
+                self._bc(zeta_old)
+                self._v, self._zeta = v_old.copy(), zeta_old.copy()
+                rhs_0, rhs_1 = self.non_linear_res_eval(v_old, zeta_old, v_0, v_d, f)
+                norm_k = float(np.sqrt((rhs_0 ** 2).sum() + (rhs_1 ** 2).sum()))
+                k += 1
+                self.non_linear_history.append(norm_k)
+                if print_error_non_linear:
+                    print(f"Non-linear solver: iteration {k:d}, non-linear residual norm {norm_k:.16e}")
+                if k + 1 > max_non_linear_iter:
+                    break
+            return k

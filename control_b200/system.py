@@ -219,6 +219,15 @@ class MultiBlockSystem:
         half = self.N * self.n_local
         return a[:half].reshape(self.N, self.n_local), a[half:].reshape(self.N, self.n_local)
 
+    def allgather_blocks(self, x_loc):
+        """(N, n_local) blocks of every rank -> global (N, n) on every rank."""
+        if self.world == 1:
+            return x_loc
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, np.ascontiguousarray(x_loc))
+        return np.concatenate(parts, axis=1)
+
     def convert(self, x_dev, src_layout, dst_layout):
         out = self.new_vector(dst_layout)
         self._call(self._lib.ctl_convert_layout, x_dev.data_ptr(), src_layout, out.data_ptr(), dst_layout)

@@ -151,3 +151,80 @@ def objective(M, v, zeta, v_hat, tau, beta, CN):
         J += 0.5 * w[i] * float(d[i] @ (M @ d[i]))
         J += 0.5 / beta * w[i] * float(zeta[i] @ (M @ zeta[i]))
     return J
+
+
+def non_linear_res_eval(M, D_v, times, tau, beta, n_t, CN, bdofs, v_old, zeta_old, v_0, v_d, f):
+    """``Instationary.non_linear_res_eval`` (control/control.py:2442-2818): the right-hand side
+    minus the KKT operator applied to the iterate, block row by block row (untransformed rows:
+    ``linear_solve`` applies T_1 / T_2 itself), with ``D_v`` evaluated at the iterate.
+    ``D_v(v_i, t)`` returns the matrix of ``construct_D_v`` (control/control.py:1887-1896)."""
+    n = M.shape[0]
+    D = [D_v(v_old[i], times[i]) for i in range(n_t)]
+    if CN:
+        h = 0.5 * tau
+        rhs_0 = np.zeros((n_t - 1, n))
+        rhs_1 = np.zeros((n_t - 1, n))
+        for i in range(n_t - 1):                                # 2621-2814
+            rhs_0[i] = h * (v_d[i] + v_d[i + 1]) - h * (M @ v_old[i]) - h * (M @ v_old[i + 1]) \
+                - (h * (D[i].T @ zeta_old[i]) + M @ zeta_old[i]) \
+                - (h * (D[i + 1].T @ zeta_old[i + 1]) - M @ zeta_old[i + 1])
+            rhs_1[i] = h * (f[i] + f[i + 1]) - (h * (D[i] @ v_old[i]) - M @ v_old[i]) \
+                - (h * (D[i + 1] @ v_old[i + 1]) + M @ v_old[i + 1]) \
+                + (h / beta) * (M @ zeta_old[i]) + (h / beta) * (M @ zeta_old[i + 1])
+    else:
+        rhs_0 = np.zeros((n_t, n))
+        rhs_1 = np.zeros((n_t, n))
+        D_v_0 = D_v(v_0, times[0])
+        for i in range(n_t):                                    # 2457-2620
+            if i < n_t - 1:
+                rhs_0[i] = tau * v_d[i] - tau * (M @ v_old[i]) \
+                    - (tau * (D[i].T @ zeta_old[i]) + M @ zeta_old[i]) + M @ zeta_old[i + 1]
+            else:
+                rhs_0[i] = -(tau * (D[i].T @ zeta_old[i]) + M @ zeta_old[i])
+            if i == 0:
+                rhs_1[0] = (tau * (D_v_0 @ v_0) + M @ v_0) - (tau * (D[0] @ v_old[0]) + M @ v_old[0])
+            else:
+                rhs_1[i] = tau * f[i] - (tau * (D[i] @ v_old[i]) + M @ v_old[i]) + M @ v_old[i - 1] \
+                    + (tau / beta) * (M @ zeta_old[i])
+    rhs_0[:, bdofs] = 0.0
+    rhs_1[:, bdofs] = 0.0
+    return rhs_0, rhs_1
+
+
+def non_linear_solve(M, D_v, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs, v_d, f, v_0=None,
+                     solver_parameters=None, lambda_v_bounds=None, inner="amg", amg_params=None,
+                     max_non_linear_iter=10, relative_non_linear_tol=1e-5, absolute_non_linear_tol=1e-8):
+    """``Instationary.non_linear_solve`` (control/control.py:3377-3590).  Returns a dict with
+    the final iterate, the residual-norm history and the inner iteration counts."""
+    t_0, T_f = time_interval
+    tau = (T_f - t_0) / (n_t - 1.0)
+    times = t_0 + tau * np.arange(n_t)
+    n = M.shape[0]
+    v_0 = np.zeros(n) if v_0 is None else v_0
+    v_old = np.zeros((n_t, n))
+    zeta_old = np.zeros((n_t, n))
+    if CN:
+        v_old[0] = v_0
+    rhs_0, rhs_1 = non_linear_res_eval(M, D_v, times, tau, beta, n_t, CN, bdofs, v_old, zeta_old, v_0, v_d, f)
+    norm_0 = float(np.sqrt((rhs_0 ** 2).sum() + (rhs_1 ** 2).sum()))
+    norm_k = norm_0
+    history = [norm_0]
+    inner_its = []
+    k = 0
+    while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+        K_levels = [D_v(v_old[i], times[i]) for i in range(n_t)]
+        out = linear_solve(M, K_levels, beta=beta, n_t=n_t, CN=CN, time_interval=time_interval, bdofs=bdofs,
+                           v_d=rhs_0, f=rhs_1, check_v_d=False, check_f=False,
+                           solver_parameters=solver_parameters, lambda_v_bounds=lambda_v_bounds,
+                           inner=inner, amg_params=amg_params)
+        inner_its.append(out["ksp"].its)
+        v_old = v_old + out["v"]
+        zeta_old = zeta_old + out["zeta"]
+        zeta_old[:, bdofs] = 0.0
+        rhs_0, rhs_1 = non_linear_res_eval(M, D_v, times, tau, beta, n_t, CN, bdofs, v_old, zeta_old, v_0, v_d, f)
+        norm_k = float(np.sqrt((rhs_0 ** 2).sum() + (rhs_1 ** 2).sum()))
+        k += 1
+        history.append(norm_k)
+        if k + 1 > max_non_linear_iter:
+            break
+    return dict(v=v_old, zeta=zeta_old, history=history, iterations=k, inner_its=inner_its)

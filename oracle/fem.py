@@ -175,3 +175,40 @@ def assemble_bc(A, bdofs):
     diag = (row_of == A.indices) & mask[row_of]
     A.data[diag] = 1.0
     return A
+
+
+def nonlinear_diffusion_p1_2d(nx, ny, lx=1.0, ly=1.0):
+    """Assembler for the non-linear diffusion operator of BASELINE config C5,
+    forward_form(trial, test, v) = (1 + v^2) grad(trial) . grad(test) dx, on the P1 mesh of
+    ``assemble_p1_2d`` (one-point quadrature at the centroid).  Returns ``D_v(v, gauss_newton)``:
+    the matrix of the form at state v (Picard, symmetric) or of its derivative
+    ufl.derivative(form(v, test, v), v, trial) (Gauss-Newton, non-symmetric), the two choices of
+    ``construct_D_v`` (control/control.py:1887-1896).  Both on the pattern of M."""
+    coords, tris = p1_triangle_mesh(nx, ny, lx, ly)
+    n = coords.shape[0]
+    p = coords[tris]
+    e1 = p[:, 1] - p[:, 0]
+    e2 = p[:, 2] - p[:, 0]
+    det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.abs(det)
+    g = np.empty((tris.shape[0], 3, 2))
+    g[:, 1, 0] = e2[:, 1] / det
+    g[:, 1, 1] = -e2[:, 0] / det
+    g[:, 2, 0] = -e1[:, 1] / det
+    g[:, 2, 1] = e1[:, 0] / det
+    g[:, 0] = -g[:, 1] - g[:, 2]
+    GG = np.einsum("tad,tbd->tab", g, g)
+    rows = np.repeat(tris, 3, axis=1).ravel()
+    cols = np.tile(tris, (1, 3)).ravel()
+
+    def D_v(v, gauss_newton=False):
+        vt = v[tris]                                   # (nt, 3)
+        vc = vt.mean(axis=1)
+        Ke = (area * (1.0 + vc ** 2))[:, None, None] * GG
+        if gauss_newton:
+            gradv = np.einsum("ta,tad->td", vt, g)     # grad v_h per triangle
+            gv = np.einsum("td,tid->ti", gradv, g)     # grad v . grad phi_i
+            Ke = Ke + (area * 2.0 * vc / 3.0)[:, None, None] * gv[:, :, None] * np.ones((1, 1, 3))
+        return _csr_same_pattern(n, rows, cols, [Ke.ravel()])[0]
+
+    return D_v

@@ -282,3 +282,29 @@ def test_config_c1_readme_problem_all_krylov_variants_agree():
     assert abs(J["minres"] - J["fgmres"]) < 1e-8 * abs(J["fgmres"])
     assert np.abs(sols["minres"]["v"] - sols["fgmres"]["v"]).max() < 1e-8 * np.abs(sols["fgmres"]["v"]).max()
     assert sols["fgmres"]["ksp"].its <= 14
+
+
+def test_non_linear_loop_picard_contracts_and_residual_is_consistent():
+    """control/control.py:3377-3590 restated: Picard on (1 + v^2) diffusion (config C5 in small).
+    At the converged iterate the residual of non_linear_res_eval vanishes; for a linear operator
+    the first outer iteration already solves the problem."""
+    nx, n_t = 8, 5
+    q = kat.heat_problem(nx, n_t, True, beta=1e-2)
+    Dv = fem.nonlinear_diffusion_p1_2d(nx, nx, 2.0, 2.0)
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 100, "relative_tolerance": 1e-10,
+           "absolute_tolerance": 0.0}
+    out = control.non_linear_solve(q["M"], lambda v, t: Dv(v, False), beta=q["beta"], n_t=n_t, CN=True,
+                                   time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"],
+                                   solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"], inner="exact",
+                                   relative_non_linear_tol=1e-8)
+    h = out["history"]
+    assert h[-1] < 1e-6 * h[0] and all(b < 0.5 * a for a, b in zip(h[2:], h[3:]))
+    lin = control.non_linear_solve(q["M"], lambda v, t: q["K"], beta=q["beta"], n_t=n_t, CN=True,
+                                   time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"],
+                                   solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"], inner="exact",
+                                   relative_non_linear_tol=1e-6)
+    assert lin["iterations"] == 1
+    ref = control.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=n_t, CN=True, time_interval=q["time_interval"],
+                               bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], solver_parameters=sp_,
+                               lambda_v_bounds=q["lambda_v_bounds"], inner="exact")
+    assert np.abs(lin["v"] - ref["v"]).max() < 1e-8 * np.abs(ref["v"]).max()
