@@ -16,6 +16,7 @@
 
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "cheb_coefficients.h"
 #include "vec_ops.cuh"
@@ -406,6 +407,30 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         st.hier.emplace_back();
         CTL_TRY(amg_build(h, global_csr(h, v), st.amg, st.fine, st.hier.back()));
         st.h_mass = (int)st.hier.size() - 1;
+    }
+
+    // Experiment (CTL_L2_PERSIST=<MB>): pin the fine-level matrix of hierarchy 0 in the persisting L2 carve-out
+    if (const char *e = getenv("CTL_L2_PERSIST")) {
+        const size_t want = (size_t)atoi(e) << 20;
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->cfg.device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->cfg.device);
+        const size_t carve = std::min<size_t>(want, (size_t)max_persist);
+        fprintf(stderr, "[ctl] L2 persist: max carve-out %d MB, max window %d MB, using %zu MB\n", max_persist >> 20,
+                max_window >> 20, carve >> 20);
+        if (want > 0 && !st.hier.empty()) {
+            CTL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
+            const SellMat &A0 = st.hier[0].dev[0].A;
+            const size_t bytes = (size_t)A0.pat->n_stored * sizeof(double);
+            cudaStreamAttrValue attr;
+            memset(&attr, 0, sizeof(attr));
+            attr.accessPolicyWindow.base_ptr = A0.vals;
+            attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
+            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CTL_CUDA(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        }
     }
 
     st.ts_stride = (size_t)nl + h->n_halo;

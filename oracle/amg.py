@@ -26,6 +26,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .cheb import chebyshev
+from .fastmv import mv
 
 try:                                       # the loops below are plain Python; numba only
     import numba                           # makes large oracle runs (CPU baseline) bearable
@@ -186,9 +187,9 @@ def vcycle(H, lvl, b, x=None):
             return L.Ainv @ b
         return chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
     x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
-    r = b - L.A @ x
-    xc = vcycle(H, lvl + 1, L.R @ r, None)
-    x = x + L.P @ xc
+    r = b - mv(L.A, x)
+    xc = vcycle(H, lvl + 1, mv(L.R, r), None)
+    x = x + mv(L.P, xc)
     x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
     return x
 
@@ -219,7 +220,7 @@ def solve(H, b, cycles=None):
     p_prev = np.zeros_like(b)
     p_cur = scale * vcycle(H, 0, b, None)
     for omega in omegas:
-        r = b - A @ p_cur
+        r = b - mv(A, p_cur)
         p_next = (1.0 - omega) * p_prev + omega * p_cur + (omega * scale) * vcycle(H, 0, r, None)
         p_prev, p_cur = p_cur, p_next
     return p_cur

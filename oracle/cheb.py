@@ -9,6 +9,8 @@ is the smoother of the aggregation AMG (``oracle/amg.py``).
 """
 import numpy as np
 
+from .fastmv import mv
+
 
 def chebyshev_coefficients(e_min, e_max, steps):
     """Scalars of the three-term recurrence: (scale, [omega_2 .. omega_steps])."""
@@ -38,10 +40,10 @@ def chebyshev(A, dinv, b, e_min, e_max, steps, x0=None):
         r = b
     else:
         p_prev = x0
-        r = b - A @ x0
+        r = b - mv(A, x0)
     p_cur = p_prev + scale * (d * r)
     for omega in omegas:
-        r = b - A @ p_cur
+        r = b - mv(A, p_cur)
         p_next = (1.0 - omega) * p_prev + omega * p_cur + (omega * scale) * (d * r)
         p_prev, p_cur = p_cur, p_next
     return p_cur

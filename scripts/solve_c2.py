@@ -23,13 +23,14 @@ def main():
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--be", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--amg", default="", help="comma list key=value of AMG options (cycles, nu, lo, hi, acc_lo, ...)")
     args = ap.parse_args()
     import kat
     from control_b200 import MultiBlockSystem
     from oracle import kkt
     t = time.time()
-    q = kat.heat_problem(args.nx, args.n_t, not args.be)
+    q = kat.heat_problem(args.nx, args.n_t, not args.be) if args.dim == 2 else kat.heat_problem_3d(args.nx, args.n_t, not args.be)
     print(f"assembled n={q['M'].shape[0]} in {time.time() - t:.1f}s", flush=True)
     t = time.time()
     s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=not args.be,

@@ -99,3 +99,19 @@ def heat_problem(nx, n_t, CN=True, beta=1e-4, length=2.0, T=2.0):
     return dict(M=M, K=K, coords=coords, bdofs=bdofs, beta=beta, n_t=n_t, CN=CN,
                 time_interval=(0.0, T), tau=tau, v_hat=v_hat, v_d=v_d, f=f,
                 lambda_v_bounds=(0.5, 2.0))
+
+
+def heat_problem_3d(nx, n_t, CN=False, beta=1e-4, length=1.0, T=1.0):
+    """BASELINE config C3 family: 3-D heat control, P1 tetrahedra on the unit cube, zero Dirichlet
+    data (nx=128, n_t=32, backward Euler in BASELINE.json).  Chebyshev bounds (0.5, 2.5): Wathen's
+    bound for D^-1 M of P1 tetrahedra (not from the reference, which has no 3-D test)."""
+    M, K, coords, bdofs = fem.assemble_p1_3d(nx, nx, nx, length, length, length)
+    x, y, z = coords[:, 0], coords[:, 1], coords[:, 2]
+    shape = np.sin(np.pi * x / length) * np.sin(np.pi * y / length) * np.sin(np.pi * z / length)
+    tau = T / (n_t - 1.0)
+    t = tau * np.arange(n_t)
+    v_hat = t[:, None] * shape[None, :]
+    f_nodal = np.tile(shape, (n_t, 1))
+    return dict(M=M, K=K, coords=coords, bdofs=bdofs, beta=beta, n_t=n_t, CN=CN,
+                time_interval=(0.0, T), tau=tau, v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T,
+                lambda_v_bounds=(0.5, 2.5))
