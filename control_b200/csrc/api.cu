@@ -122,6 +122,9 @@ int ctl_destroy(ctl_handle h)
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
     cudaFree(h->d_bc_rows_all);
+    cudaFree(h->d_tile_uptr);
+    cudaFree(h->d_tile_ucols);
+    cudaFree(h->d_tile_slot);
     cudaFree(h->d_halo);
     cudaFree(h->d_red);
     if (h->h_red) cudaFreeHost(h->h_red);
@@ -236,6 +239,58 @@ static int build_local_pattern(ctl_handle_s *h)
         h->max_row_len = std::max(h->max_row_len, ip[g + 1] - ip[g]);
     }
     if (const char *e = getenv("CTL_KKT_UNSTAGED")) h->force_unstaged = (e[0] == '1');
+    h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
+    if (const char *e = getenv("CTL_KKT_TMA")) h->no_tma = !(e[0] == '1');
+    // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows
+    {
+        int TR = 32;
+        if (const char *e = getenv("CTL_TILE_ROWS")) TR = atoi(e) == 16 ? 16 : 32;
+        const int nblk = (nl + TR - 1) / TR;
+        // per block: the sorted unique columns, stored as maximal runs of consecutive columns
+        // (col_start, length, slot_start) so that one bulk copy moves a whole run
+        std::vector<int> uptr(nblk + 1, 0), ucols, tmp;
+        std::vector<int> utot(nblk, 0);
+        std::vector<uint8_t> slot(L.indices.size(), 0);
+        int umax = 0;
+        bool ok = true;
+        for (int b = 0; b < nblk && ok; ++b) {
+            const int r0 = b * TR, r1 = std::min(nl, r0 + TR);
+            tmp.assign(L.indices.begin() + L.indptr[r0], L.indices.begin() + L.indptr[r1]);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if (tmp.size() > 255) ok = false;
+            umax = std::max(umax, (int)tmp.size());
+            for (int k = L.indptr[r0]; k < L.indptr[r1] && ok; ++k)
+                slot[k] = (uint8_t)(std::lower_bound(tmp.begin(), tmp.end(), L.indices[k]) - tmp.begin());
+            for (size_t i = 0; i < tmp.size();) {
+                size_t j = i + 1;
+                while (j < tmp.size() && tmp[j] == tmp[j - 1] + 1 && (tmp[j] < nl) == (tmp[i] < nl)) ++j;
+                ucols.push_back(tmp[i]);
+                ucols.push_back((int)(j - i));
+                ucols.push_back((int)i);
+                i = j;
+            }
+            utot[b] = (int)tmp.size();
+            uptr[b + 1] = (int)ucols.size() / 3;
+        }
+        // the per-block unique counts ride behind the run table
+        const size_t n_runs = ucols.size() / 3;
+        ucols.insert(ucols.end(), utot.begin(), utot.end());
+        h->tile_count_off = (int)(3 * n_runs);
+        cudaFree(h->d_tile_uptr);
+        cudaFree(h->d_tile_ucols);
+        cudaFree(h->d_tile_slot);
+        h->d_tile_uptr = h->d_tile_ucols = nullptr;
+        h->d_tile_slot = nullptr;
+        h->tile_rows = 0;
+        if (ok && nblk > 0) {
+            CTL_TRY(ctl_upload(h, &h->d_tile_uptr, uptr.data(), uptr.size()));
+            CTL_TRY(ctl_upload(h, &h->d_tile_ucols, ucols.data(), ucols.size()));
+            CTL_TRY(ctl_upload(h, &h->d_tile_slot, slot.data(), slot.size()));
+            h->tile_rows = TR;
+            h->tile_umax = umax;
+        }
+    }
     // note: local column order within a row is no longer sorted when ghosts precede owned
     // columns globally; the kernels do not rely on sorted columns.
     return CTL_OK;

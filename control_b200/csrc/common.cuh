@@ -84,6 +84,14 @@ struct ctl_handle_s {
     bool per_level = false;
     int max_row_len = 0;        // longest local row (sizes the shared-memory staging)
     bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
+    bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
+    // TMA tile plan of the fused KKT apply (kkt_apply.cu): row blocks of TILE_ROWS rows, the
+    // unique columns each block gathers, and for every CSR entry its slot in that list
+    int tile_rows = 0, tile_umax = 0;      // 0 = no plan (fallback to the LDG-gather kernel)
+    int tile_count_off = 0;                // offset of the per-block unique-row counts inside d_tile_ucols
+    int *d_tile_uptr = nullptr;            // n_blocks + 1: run ranges of each block
+    int *d_tile_ucols = nullptr;           // runs (first column, length, first slot) x 3, then per-block unique counts
+    uint8_t *d_tile_slot = nullptr;        // per local CSR entry
     bool k_symmetric = false;
     uint8_t *d_bcmask = nullptr;   // local rows (owned + ghost)
     int *d_bc_rows_all = nullptr;  // list of constrained owned rows

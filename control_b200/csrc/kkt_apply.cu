@@ -42,6 +42,9 @@ struct KktArgs {
     const double *hv, *hz;        // ghost rows    [n_halo x ld]
     double *y0, *y1;              // output panels
     double tau, beta;
+    const int *tile_uptr, *tile_ucols;   // TMA tile plan (see common.cuh)
+    int tile_count_off;
+    const uint8_t *tile_slot;
 };
 
 __device__ __forceinline__ double2 ldg2(const double *p)
@@ -356,6 +359,220 @@ void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, bool halo
     else launch_staged_h<CN, PER_LEVEL, SYM, false>(a, G, rows_per_cta, cap, s);
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA-staged variant (opt-in, CTL_KKT_TMA=1; round-1 result: correct, but 0.73 ms against 0.66 ms for
+// the LDG-gather kernel above): v3 is bound by the L1 LDG data pipe (7 gathered 1 KB row segments per
+// row, profiles/r01_kkt_apply_v3.txt).  Here a CTA owns 32 consecutive rows; the UNIQUE X
+// rows they reference (host-built tile plan, about 3x34 for a 7-point mesh stencil) are
+// copied once into shared memory by the TMA engine -- one cp.async.bulk of ld*8 bytes per
+// row and panel, completion on an mbarrier -- while the other warps stage the CSR entries.
+// All gathers of the inner loop are then LDS.128 from the tile (shared memory delivers
+// 128 B/clk/SM against about 64 B/clk for LDG hits), and HBM -> SM traffic no longer passes
+// through registers.  Two CTAs per SM (about 108 KB each) overlap one CTA's copy with the
+// other's arithmetic.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+template <bool CN, bool SYM, bool HALO, int G, int TR>
+__global__ void __launch_bounds__(TR * 8, 512 / (TR * 8) * 2) kkt_apply_tma_kernel(const KktArgs a, const int cap, const int umax)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ld = a.ld;
+    const unsigned row_b = (unsigned)ld * 8u;
+    // layout: tile_v [umax*row_b] | tile_z [umax*row_b] | mk [cap+1] double2 | kt [cap+1] double (!SYM)
+    //         | off [cap+1] unsigned | ptr [TR+1] int | mbarrier (8 B)
+    unsigned char *tile_v = smem_raw;
+    unsigned char *tile_z = tile_v + (size_t)umax * row_b;
+    double2 *s_mk = reinterpret_cast<double2 *>(tile_z + (size_t)umax * row_b);
+    double *s_kt = reinterpret_cast<double *>(s_mk + (cap + 1));
+    unsigned *s_off = reinterpret_cast<unsigned *>(SYM ? s_kt : s_kt + (cap + 1));
+    int *s_ptr = reinterpret_cast<int *>(s_off + (cap + 1));
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(s_ptr + (TR + 1)) + 7) & ~(uintptr_t)7);
+
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane / G, l = lane % G;
+    const int c0 = 2 * l;
+    const int r0 = blockIdx.x * TR;
+    const int nrows = min(TR, a.n_rows - r0);
+    const int ub = __ldg(a.tile_uptr + blockIdx.x);
+    const int n_runs = __ldg(a.tile_uptr + blockIdx.x + 1) - ub;
+    const int U = __ldg(a.tile_ucols + a.tile_count_off + blockIdx.x);
+    const unsigned mbar_s = smem_u32(mbar);
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (wid == 0) {
+        // producer warp: arm the barrier with the byte count, then one bulk copy per row and panel
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_s), "r"(2u * (unsigned)U * row_b)
+                         : "memory");
+        __syncwarp();
+        for (int u = lane; u < n_runs; u += 32) {
+            const int c = __ldg(a.tile_ucols + 3 * (ub + u));
+            const unsigned bytes = (unsigned)__ldg(a.tile_ucols + 3 * (ub + u) + 1) * row_b;
+            const size_t dst = (size_t)__ldg(a.tile_ucols + 3 * (ub + u) + 2) * row_b;
+            const double *sv, *sz;
+            if (HALO && c >= a.n_own_cols) {
+                sv = a.hv + (size_t)(c - a.n_own_cols) * ld;
+                sz = a.hz + (size_t)(c - a.n_own_cols) * ld;
+            } else {
+                sv = a.xv + (size_t)c * ld;
+                sz = a.xz + (size_t)c * ld;
+            }
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tile_v + dst)),
+                         "l"(sv), "r"(bytes), "r"(mbar_s)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tile_z + dst)),
+                         "l"(sz), "r"(bytes), "r"(mbar_s)
+                         : "memory");
+        }
+    }
+    // everybody: stage the CSR entries of the block (slot -> byte offset inside the tile)
+    for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
+    __syncthreads();
+    const int kb = s_ptr[0];
+    const int cnt = s_ptr[nrows] - kb;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        s_off[k] = (unsigned)__ldg(a.tile_slot + kb + k) * row_b;
+        s_mk[k] = make_double2(__ldg(a.Mv + kb + k), __ldg(a.Kv + kb + k));
+        if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+    }
+    if (threadIdx.x == 0) {
+        s_off[cap] = 0u;
+        s_mk[cap] = make_double2(0.0, 0.0);
+        if (!SYM) s_kt[cap] = 0.0;
+    }
+    __syncthreads();
+    // wait for the tile (phase 0 of the barrier)
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(mbar_s), "r"(0u)
+                         : "memory");
+        }
+    }
+
+    const unsigned full = 0xffffffffu;
+    const bool first = (l == 0), last = (l == G - 1);
+    const int N = a.N;
+    const bool in0 = c0 < N, in1 = c0 + 1 < N;
+    const double tau = a.tau, beta = a.beta;
+    const unsigned lane_b = (unsigned)c0 * 8u;
+    const int nwarps = blockDim.x >> 5;
+
+    for (int base = wid * RPW; base < nrows; base += nwarps * RPW) {
+        const int lr_raw = base + sub;
+        const bool live = lr_raw < nrows;
+        const int lr = live ? lr_raw : nrows - 1;
+        const int r = r0 + lr;
+        const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
+        double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
+        for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
+#pragma unroll
+            for (int j = 0; j < SCHUNK; ++j) {
+                const int kk = (k0 + j < kend) ? k0 + j : cap;
+                const unsigned o = s_off[kk] + lane_b;
+                const double2 xv = *reinterpret_cast<const double2 *>(tile_v + o);
+                const double2 xz = *reinterpret_cast<const double2 *>(tile_z + o);
+                const double2 mk = s_mk[kk];
+                const double kt = SYM ? mk.y : s_kt[kk];
+                mv0 = fma(mk.x, xv.x, mv0);
+                mv1 = fma(mk.x, xv.y, mv1);
+                mz0 = fma(mk.x, xz.x, mz0);
+                mz1 = fma(mk.x, xz.y, mz1);
+                kv0 = fma(mk.y, xv.x, kv0);
+                kv1 = fma(mk.y, xv.y, kv1);
+                kz0 = fma(kt, xz.x, kz0);
+                kz1 = fma(kt, xz.y, kz1);
+            }
+        }
+        double y00, y01, y10, y11;
+        if (CN) {
+            const double h = 0.5 * tau, hb = h / beta;
+            double t;
+            t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+            t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
+            t = __shfl_down_sync(full, kz0, 1, G); const double kzn1 = last ? 0.0 : t;
+            t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+            double r00 = h * (mvp0 + mv0) + h * (kz0 + kz1) + mz0 - mz1;
+            double r01 = h * (mv0 + mv1) + h * (kz1 + kzn1) + mz1 - mzn1;
+            double r10 = h * (kvp0 + kv0) - mvp0 + mv0 - hb * (mz0 + mz1);
+            double r11 = h * (kv0 + kv1) - mv0 + mv1 - hb * (mz1 + mzn1);
+            if (!in0) { r00 = 0.0; r10 = 0.0; }
+            if (!in1) { r01 = 0.0; r11 = 0.0; }
+            t = __shfl_down_sync(full, r00, 1, G); const double r0n = last ? 0.0 : t;
+            t = __shfl_up_sync(full, r11, 1, G);   const double r1p = first ? 0.0 : t;
+            y00 = r00 + r01;
+            y01 = r01 + r0n;
+            y10 = r10 + r1p;
+            y11 = r11 + r10;
+        } else {
+            const double tb = tau / beta;
+            double t;
+            t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+            t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+            y00 = tau * kz0 + mz0 + ((c0 < N - 1) ? (tau * mv0 - mz1) : 0.0);
+            y01 = tau * kz1 + mz1 + ((c0 + 1 < N - 1) ? (tau * mv1 - mzn1) : 0.0);
+            y10 = tau * kv0 + mv0 + ((c0 >= 1) ? (-mvp0 - tb * mz0) : 0.0);
+            y11 = tau * kv1 + mv1 + (-mv0 - tb * mz1);
+        }
+        if (!in0) { y00 = 0.0; y10 = 0.0; }
+        if (!in1) { y01 = 0.0; y11 = 0.0; }
+        if (live) {
+            const size_t ro = (size_t)r * ld + c0;
+            if (a.bcmask[r]) {
+                const double2 xv = ldg2(a.xv + ro);
+                const double2 xz = ldg2(a.xz + ro);
+                y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
+            }
+            *reinterpret_cast<double2 *>(a.y0 + ro) = make_double2(y00, y01);
+            *reinterpret_cast<double2 *>(a.y1 + ro) = make_double2(y10, y11);
+        }
+    }
+}
+
+template <bool CN, bool SYM, bool HALO, int G, int TR>
+cudaError_t launch_tma_gt(const KktArgs &a, int cap, int umax, cudaStream_t s)
+{
+    const int blocks = ceil_div(a.n_rows, TR);
+    const size_t smem = (size_t)2 * umax * a.ld * 8 + (size_t)(cap + 1) * (16 + (SYM ? 0 : 8) + 4) + (TR + 1) * 4 + 16;
+    auto kern = kkt_apply_tma_kernel<CN, SYM, HALO, G, TR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<blocks, TR * 8, smem, s>>>(a, cap, umax);
+    return cudaSuccess;
+}
+
+template <bool CN, bool SYM, bool HALO, int G>
+cudaError_t launch_tma_g(const KktArgs &a, int cap, int umax, int tile_rows, cudaStream_t s)
+{
+    if (tile_rows == 16) return launch_tma_gt<CN, SYM, HALO, G, 16>(a, cap, umax, s);
+    return launch_tma_gt<CN, SYM, HALO, G, 32>(a, cap, umax, s);
+}
+
+template <bool CN, bool SYM, bool HALO>
+cudaError_t launch_tma(const KktArgs &a, int G, int cap, int umax, int tile_rows, cudaStream_t s)
+{
+    switch (G) {
+    case 4: return launch_tma_g<CN, SYM, HALO, 4>(a, cap, umax, tile_rows, s);
+    case 8: return launch_tma_g<CN, SYM, HALO, 8>(a, cap, umax, tile_rows, s);
+    case 16: return launch_tma_g<CN, SYM, HALO, 16>(a, cap, umax, tile_rows, s);
+    default: return launch_tma_g<CN, SYM, HALO, 32>(a, cap, umax, tile_rows, s);
+    }
+}
+
 template <bool CN, bool PER_LEVEL>
 void launch_g(const KktArgs &a, int G, cudaStream_t s)
 {
@@ -405,7 +622,26 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     const bool fits = (size_t)std::max(h->n_loc, h->n_halo) * h->ld * 8 < 0x7fffffffull;
     const bool staged = rows_per_cta >= 8 && !h->force_unstaged && fits;
     const bool halo = h->n_halo > 0;
-    if (staged) {
+    a.tile_uptr = h->d_tile_uptr;
+    a.tile_ucols = h->d_tile_ucols;
+    a.tile_slot = h->d_tile_slot;
+    a.tile_count_off = h->tile_count_off;
+    // TMA-staged kernel: time-independent K, tile plan available, tile + entries fit in shared memory
+    const int tcap = h->tile_rows * max_len;
+    const size_t tma_smem = (size_t)2 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 16;
+    const bool use_tma = h->tile_rows > 0 && !h->per_level && !h->force_unstaged && !h->no_tma && tma_smem <= 113 * 1024;
+    if (use_tma) {
+        const bool sym = h->d_KT == h->d_K;
+        cudaError_t e;
+        if (h->cfg.CN) {
+            if (sym) e = halo ? launch_tma<true, true, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma<true, true, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma<true, false, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma<true, false, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+        } else {
+            if (sym) e = halo ? launch_tma<false, true, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma<false, true, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma<false, false, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma<false, false, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+        }
+        CTL_CUDA(e);
+    } else if (staged) {
         const int cap = rows_per_cta * max_len;
         const bool sym = h->d_KT == h->d_K;
         if (h->cfg.CN) {
