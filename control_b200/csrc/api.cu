@@ -239,6 +239,22 @@ static int build_local_pattern(ctl_handle_s *h)
         h->max_row_len = std::max(h->max_row_len, ip[g + 1] - ip[g]);
     }
     if (const char *e = getenv("CTL_KKT_UNSTAGED")) h->force_unstaged = (e[0] == '1');
+    {   // gather chunk with the fewest padding slots over all rows (ties: the larger chunk)
+        const int cand[4] = {4, 5, 7, 8};
+        long best = -1;
+        for (int c : cand) {
+            long slots = 0;
+            for (int r = 0; r < nl; ++r) {
+                const int len = L.indptr[r + 1] - L.indptr[r];
+                slots += (long)((len + c - 1) / c) * c;
+            }
+            if (best < 0 || slots <= best) {
+                best = slots;
+                h->gather_chunk = c;
+            }
+        }
+        if (const char *e = getenv("CTL_KKT_CHUNK")) h->gather_chunk = atoi(e);
+    }
     h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
     if (const char *e = getenv("CTL_KKT_TMA")) h->no_tma = !(e[0] == '1');
     // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows

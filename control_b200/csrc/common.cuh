@@ -83,6 +83,7 @@ struct ctl_handle_s {
     double *d_KT = nullptr;     // may alias d_K (symmetric, time independent)
     bool per_level = false;
     int max_row_len = 0;        // longest local row (sizes the shared-memory staging)
+    int gather_chunk = 4;       // entries per gather pass of the staged KKT apply (4, 5, 7 or 8: least padding)
     bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
     bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
     // TMA tile plan of the fused KKT apply (kkt_apply.cu): row blocks of TILE_ROWS rows, the

@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) kkt_apply_kernel(const KktArgs a)
 // reloads, predication selects); v3 below cuts the per-entry overhead to two LDS, one
 // integer add, two LDG.128 and eight DFMA.
 // ---------------------------------------------------------------------------------------
-template <bool CN, bool PER_LEVEL, bool SYM, bool HALO, int G>
+template <bool CN, bool PER_LEVEL, bool SYM, bool HALO, int G, int SC>
 __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktArgs a, const int rows_per_cta,
                                                                      const int cap)
 {
@@ -250,17 +250,17 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
         const int r = r0 + lr;
         const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
         double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
-        for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
-            unsigned off[SCHUNK];
-            int kk[SCHUNK];
+        for (int k0 = kbeg; k0 < kend; k0 += SC) {
+            unsigned off[SC];
+            int kk[SC];
 #pragma unroll
-            for (int j = 0; j < SCHUNK; ++j) {
+            for (int j = 0; j < SC; ++j) {
                 kk[j] = (k0 + j < kend) ? k0 + j : cap;       // padding slots read the sentinel
                 off[j] = s_off[kk[j]];
             }
-            double2 xv[SCHUNK], xz[SCHUNK];
+            double2 xv[SC], xz[SC];
 #pragma unroll
-            for (int j = 0; j < SCHUNK; ++j) {
+            for (int j = 0; j < SC; ++j) {
                 if (HALO && (off[j] & 0x80000000u)) {
                     const unsigned o = (off[j] & 0x7fffffffu) + lane_b;
                     xv[j] = __ldg(reinterpret_cast<const double2 *>(hv_b + o));
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
                 }
             }
 #pragma unroll
-            for (int j = 0; j < SCHUNK; ++j) {
+            for (int j = 0; j < SC; ++j) {
                 const double2 mk = s_mk[kk[j]];
                 mv0 = fma(mk.x, xv[j].x, mv0);
                 mv1 = fma(mk.x, xv[j].y, mv1);
@@ -340,23 +340,36 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
 }
 
 template <bool CN, bool PER_LEVEL, bool SYM, bool HALO>
-void launch_staged_h(const KktArgs &a, int G, int rows_per_cta, int cap, cudaStream_t s)
+void launch_staged_h(const KktArgs &a, int G, int rows_per_cta, int cap, int chunk, cudaStream_t s)
 {
     const int blocks = ceil_div(a.n_rows, rows_per_cta);
     const size_t smem = (size_t)(cap + 1) * (16 + ((SYM || PER_LEVEL) ? 0 : 8) + 4) + (size_t)(rows_per_cta + 1) * 4;
-    switch (G) {
-    case 4: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 4><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    case 8: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 8><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    case 16: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 16><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
-    default: kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, 32><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap); break;
+#define LS(GG, CC) kkt_apply_staged_kernel<CN, PER_LEVEL, SYM, HALO, GG, CC><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap)
+    if (G == 32 && !PER_LEVEL) {
+        // chunk = entries gathered per pass; matched to the row length so that no padding
+        // slots are processed (7 for a P1 triangle mesh, 5 for the 15-point P1 tetrahedra stencil)
+        switch (chunk) {
+        case 5: LS(32, 5); break;
+        case 7: LS(32, 7); break;
+        case 8: LS(32, 8); break;
+        default: LS(32, 4); break;
+        }
+        return;
     }
+    switch (G) {
+    case 4: LS(4, 4); break;
+    case 8: LS(8, 4); break;
+    case 16: LS(16, 4); break;
+    default: LS(32, 4); break;
+    }
+#undef LS
 }
 
 template <bool CN, bool PER_LEVEL, bool SYM>
-void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, bool halo, cudaStream_t s)
+void launch_staged(const KktArgs &a, int G, int rows_per_cta, int cap, int chunk, bool halo, cudaStream_t s)
 {
-    if (halo) launch_staged_h<CN, PER_LEVEL, SYM, true>(a, G, rows_per_cta, cap, s);
-    else launch_staged_h<CN, PER_LEVEL, SYM, false>(a, G, rows_per_cta, cap, s);
+    if (halo) launch_staged_h<CN, PER_LEVEL, SYM, true>(a, G, rows_per_cta, cap, chunk, s);
+    else launch_staged_h<CN, PER_LEVEL, SYM, false>(a, G, rows_per_cta, cap, chunk, s);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -645,13 +658,13 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
         const int cap = rows_per_cta * max_len;
         const bool sym = h->d_KT == h->d_K;
         if (h->cfg.CN) {
-            if (h->per_level) launch_staged<true, true, false>(a, G, rows_per_cta, cap, halo, h->stream);
-            else if (sym) launch_staged<true, false, true>(a, G, rows_per_cta, cap, halo, h->stream);
-            else launch_staged<true, false, false>(a, G, rows_per_cta, cap, halo, h->stream);
+            if (h->per_level) launch_staged<true, true, false>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
+            else if (sym) launch_staged<true, false, true>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
+            else launch_staged<true, false, false>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
         } else {
-            if (h->per_level) launch_staged<false, true, false>(a, G, rows_per_cta, cap, halo, h->stream);
-            else if (sym) launch_staged<false, false, true>(a, G, rows_per_cta, cap, halo, h->stream);
-            else launch_staged<false, false, false>(a, G, rows_per_cta, cap, halo, h->stream);
+            if (h->per_level) launch_staged<false, true, false>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
+            else if (sym) launch_staged<false, false, true>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
+            else launch_staged<false, false, false>(a, G, rows_per_cta, cap, h->gather_chunk, halo, h->stream);
         }
     } else if (h->cfg.CN) {
         if (h->per_level) launch_g<true, true>(a, G, h->stream);
