@@ -5,9 +5,13 @@
 // SpMV-family kernels (sell.cu), so the time sweeps can be captured in a CUDA graph.
 #include "amg.cuh"
 
+#include <cstdlib>
 #include <stdexcept>
 
 #include "cheb_coefficients.h"
+
+// levels >= FUSED_FROM of a V-cycle run as one cooperative kernel (sell.cu: fused coarse tail)
+static constexpr int FUSED_FROM = 2;
 
 static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
 {
@@ -15,6 +19,8 @@ static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
     CTL_CUDA(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(double), h->stream));
     return CTL_OK;
 }
+
+static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, double *x, bool zero_guess);
 
 int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
               const std::shared_ptr<SellPattern> &fine_pattern, AmgHierarchyDev &H)
@@ -45,11 +51,12 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             for (size_t q = 0; q < lv.size(); ++q) lv[q] = Lh.A.values[h->loc_entry[q]];
             CTL_TRY(sell_set_values(h, fine_pattern, lv.data(), Ld.A));
         } else {
-            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A));
+            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A, l >= FUSED_FROM));
         }
         CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data() + rb, (size_t)Ld.n));
         CTL_TRY(dev_alloc(h, &Ld.r, Ld.n + ghosts));
         CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n + ghosts));
+        CTL_TRY(dev_alloc(h, &Ld.t1, Ld.n + ghosts));
         if (l > 0) {
             CTL_TRY(dev_alloc(h, &Ld.x, Ld.n));
             CTL_TRY(dev_alloc(h, &Ld.b, Ld.n));
@@ -69,8 +76,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
                 CTL_TRY(sell_from_csr(h, Pl, Ld.P));
                 CTL_TRY(sell_from_csr(h, Rl, Ld.R));
             } else {
-                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
-                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
+                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P, l >= FUSED_FROM));
+                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R, l >= FUSED_FROM));
             }
             // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
             H.bytes_per_cycle += spmv * (2 * p.nu) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
@@ -81,8 +88,22 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             H.bytes_per_cycle += spmv * p.nu;
         }
     }
+    H.fused_from = 0;
     if (h->cfg.world > 1)
         CTL_CHECK(nl > 1, CTL_ERR_ARG, "amg_build: the problem is too small for a multi-rank hierarchy (single level)");
+    // record the sub-cycle below level FUSED_FROM - 1 once (zero guess at entry, exactly what vcycle() issues)
+    // (opt-in, CTL_FUSED=1: round-1 measurement showed the cooperative kernel slower than the separate
+    // launches, 1.56 ms against 1.27 ms per inner solve: the operations are bound by dependent memory
+    // round trips, not by launch gaps)
+    const char *fe = getenv("CTL_FUSED");
+    if (nl > FUSED_FROM && fe && fe[0] == '1') {
+        h->recorder = &H.fused;
+        const int rc = vcycle(h, H, FUSED_FROM, H.dev[FUSED_FROM].b, H.dev[FUSED_FROM].x, true);
+        h->recorder = nullptr;
+        CTL_TRY(rc);
+        CTL_TRY(fused_upload(h, H.fused));
+        H.fused_from = FUSED_FROM;
+    }
     if (p.acc_lo > 0.0) {
         CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n + h->n_halo));
         CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n + h->n_halo));
@@ -93,6 +114,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
 
 void amg_free(AmgHierarchyDev &H)
 {
+    fused_free(H.fused);
+    H.fused_from = 0;
     cudaFree(H.acc_r);
     cudaFree(H.acc_z);
     cudaFree(H.acc_p);
@@ -106,6 +129,7 @@ void amg_free(AmgHierarchyDev &H)
         cudaFree(L.b);
         cudaFree(L.r);
         cudaFree(L.t0);
+        cudaFree(L.t1);
         cudaFree(L.Ainv);
     }
     H.dev.clear();
@@ -123,25 +147,34 @@ static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, co
     double scale;
     std::vector<double> om;
     cheb_coefficients(p.lo * L.rho, p.hi * L.rho, p.nu, &scale, om);
-    double *buf[2] = {x, L.t0};
-    // p_k lives in buf[slot(k)]; p_nu must be x when possible
-    auto slot = [&](int k) { return zero_guess ? ((p.nu - k) & 1) : (k & 1); };
+    // Where iterate p_k lives.  A step reads p_{k-1} through the gather (must not be the buffer
+    // being written) and p_{k-2} element-wise (may be).  Zero guess: alternate x / t0 so that
+    // p_nu lands in x.  Non-zero guess (p_0 = x): rotate x / t0 / t1 backwards from p_nu = x;
+    // this never overwrites a buffer that is still gathered unless nu % 3 == 1, in which case
+    // the iterates alternate t0 / x and one copy moves an odd-nu result back into x.
+    double *buf3[3] = {x, L.t0, L.t1};
+    const bool rotate3 = !zero_guess && (p.nu % 3 != 1);
+    auto where = [&](int k) -> double * {
+        if (k == 0) return x;
+        if (zero_guess) return ((p.nu - k) & 1) ? L.t0 : x;
+        if (rotate3) return buf3[(p.nu - k) % 3];
+        return (k & 1) ? L.t0 : x;
+    };
     if (zero_guess) {
-        CTL_TRY(vec_dinv_scale(h, L.dinv, b, buf[slot(1)], scale, L.n));
+        CTL_TRY(vec_dinv_scale(h, L.dinv, b, where(1), scale, L.n));
     } else {
         // p_1 = x + scale D^-1 (b - A x)
         CTL_TRY(halo0(h, l, x));
-        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, buf[slot(1)], 0.0, 1.0, scale));
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, where(1), 0.0, 1.0, scale));
     }
     for (int k = 2; k <= p.nu; ++k) {
         const double w = om[k - 2];
-        const double *prev = (k == 2 && zero_guess) ? nullptr : buf[slot(k - 2)];
-        const double a = (k == 2 && zero_guess) ? 0.0 : (1.0 - w);
-        CTL_TRY(halo0(h, l, buf[slot(k - 1)]));
-        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, prev, buf[slot(k - 1)], buf[slot(k)], a, w, w * scale));
+        const bool no_prev = (k == 2 && zero_guess);
+        CTL_TRY(halo0(h, l, where(k - 1)));
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, no_prev ? nullptr : where(k - 2), where(k - 1), where(k),
+                               no_prev ? 0.0 : (1.0 - w), w, w * scale));
     }
-    if (buf[slot(p.nu)] != x)
-        CTL_CUDA(cudaMemcpyAsync(x, buf[slot(p.nu)], (size_t)L.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (where(p.nu) != x) CTL_TRY(vec_copy_n(h, x, where(p.nu), L.n));
     return CTL_OK;
 }
 
@@ -159,7 +192,8 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, d
     CTL_TRY(sell_spmv(h, L.A, x, L.r, b, SELL_RESIDUAL));
     CTL_TRY(sell_spmv(h, L.R, L.r, C.b, nullptr, SELL_ASSIGN));
     if (l == 0) CTL_TRY(ctl_allreduce_sum(h, C.b, C.n));      // partial restrictions of the row blocks
-    CTL_TRY(vcycle(h, H, l + 1, C.b, C.x, true));
+    if (H.fused_from == l + 1 && !h->recorder) CTL_TRY(fused_run(h, H.fused));
+    else CTL_TRY(vcycle(h, H, l + 1, C.b, C.x, true));
     CTL_TRY(sell_spmv(h, L.P, C.x, x, nullptr, SELL_ADD));
     CTL_TRY(smooth(h, H.params, L, l, b, x, false));
     return CTL_OK;

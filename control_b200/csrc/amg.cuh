@@ -9,7 +9,7 @@ struct AmgLevelDev {
     SellMat A, P, R;
     double *dinv = nullptr;
     double *x = nullptr, *b = nullptr;   // owned on levels >= 1 (level 0 uses the caller's)
-    double *r = nullptr, *t0 = nullptr;  // residual / Chebyshev work vectors
+    double *r = nullptr, *t0 = nullptr, *t1 = nullptr;  // residual / Chebyshev work vectors
     double *Ainv = nullptr;              // dense inverse on the last level
 };
 
@@ -17,6 +17,8 @@ struct AmgHierarchyDev {
     AmgParams params;
     std::vector<AmgLevelHost> host;      // kept for introspection (ctl_amg_get_csr)
     std::vector<AmgLevelDev> dev;
+    FusedProgram fused;                  // recorded sub-cycle of levels >= fused_from (0 = none)
+    int fused_from = 0;
     int64_t bytes_per_cycle = 0;         // algorithmic bytes of one V-cycle (byte model)
     double *acc_r = nullptr, *acc_z = nullptr, *acc_p = nullptr;   // level-0 work vectors of the accelerated solve
 };

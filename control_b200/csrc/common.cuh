@@ -109,6 +109,7 @@ struct ctl_handle_s {
     std::shared_ptr<struct PcState> pc;
     std::shared_ptr<struct KrylovState> ks;
     std::shared_ptr<struct CommState> comm;
+    struct FusedProgram *recorder = nullptr;   // sell.cu: record operations instead of launching them
     ctl_pc_callback pc_cb = nullptr;
     void *pc_cb_user = nullptr;
 

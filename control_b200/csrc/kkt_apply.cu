@@ -333,8 +333,9 @@ __global__ void __launch_bounds__(256, SMINB) kkt_apply_staged_kernel(const KktA
                 const double2 xz = ldg2(a.xz + ro);
                 y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
             }
-            *reinterpret_cast<double2 *>(a.y0 + ro) = make_double2(y00, y01);
-            *reinterpret_cast<double2 *>(a.y1 + ro) = make_double2(y10, y11);
+            // streaming stores: the 1 GB result must not push the X rows still to be gathered out of L2
+            __stcs(reinterpret_cast<double2 *>(a.y0 + ro), make_double2(y00, y01));
+            __stcs(reinterpret_cast<double2 *>(a.y1 + ro), make_double2(y10, y11));
         }
     }
 }

@@ -2,6 +2,7 @@
 // All kernels: one thread per row, 128 threads per CTA, HBM/L2-bound streaming of
 // (4 + 8) bytes per stored entry plus the gathered x.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sell.cuh"
 
@@ -23,10 +24,10 @@ void sell_free(SellMat &m)
     m.pat.reset();
 }
 
-int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out)
+int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_csr)
 {
     const double mean = A.n_rows ? (double)A.nnz() / A.n_rows : 0.0;
-    if (mean <= 10.0) {
+    if (mean <= 10.0 && !force_csr) {
         std::shared_ptr<SellPattern> pat;
         CTL_TRY(sell_build_pattern(h, A, pat));
         return sell_set_values(h, pat, A.values.data(), out);
@@ -36,7 +37,7 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out)
     pat->n_cols = A.n_cols;
     pat->nnz = A.nnz();
     out.pat = pat;
-    out.lanes = mean <= 16.0 ? 8 : (mean <= 48.0 ? 16 : 32);
+    out.lanes = mean <= 6.0 ? 4 : (mean <= 16.0 ? 8 : (mean <= 48.0 ? 16 : 32));
     CTL_TRY(ctl_upload(h, &out.csr_ptr, A.indptr.data(), A.indptr.size()));
     CTL_TRY(ctl_upload(h, &out.csr_cols, A.indices.data(), A.indices.size()));
     CTL_TRY(ctl_upload(h, &out.csr_vals, A.values.data(), A.values.size()));
@@ -114,8 +115,10 @@ __device__ __forceinline__ double sell_row_dot(const int *__restrict__ slice_ptr
         for (int j = 0; j < SC; ++j) {
             const int p = p0 + 32 * j;
             const bool ok = p < end;
-            c[j] = ok ? __ldg(cols + p) : 0;
-            v[j] = ok ? __ldg(vals + p) : 0.0;
+            // streamed once per pass: evict-first, so that the 88 MB fine matrix does not flush the
+            // coarse levels and the vectors out of L2 between two uses
+            c[j] = ok ? __ldcs(cols + p) : 0;
+            v[j] = ok ? __ldcs(vals + p) : 0.0;
         }
         double xv[SC];
 #pragma unroll
@@ -192,30 +195,35 @@ __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const int *__restrict__ 
     const int beg = __ldg(slice_ptr + s), end = __ldg(slice_ptr + s + 1);
     double acc1 = 0.0, acc2 = 0.0;
     for (int p = beg + lane; p < end; p += 32) {
-        const int c = __ldg(cols + p);
+        const int c = __ldcs(cols + p);
         double xa = __ldg(x1 + c);
         if (x2) xa += __ldg(x2 + c);
-        acc1 = fma(__ldg(v1 + p), xa, acc1);
-        if (x3) acc2 = fma(__ldg(v2 + p), __ldg(x3 + c), acc2);
+        acc1 = fma(__ldcs(v1 + p), xa, acc1);
+        if (x3) acc2 = fma(__ldcs(v2 + p), __ldg(x3 + c), acc2);
     }
     y[row] = alpha * acc1 + beta * acc2;
 }
 
 // ---- CSR-vector variants: T lanes per row, shuffle reduction
-template <int T>
+// STREAM: the matrix is large and read once per pass (fine-level restriction): evict-first loads
+template <int T, bool STREAM>
 __device__ __forceinline__ double csr_row_dot(const int *__restrict__ ptr, const int *__restrict__ cols,
                                               const double *__restrict__ vals, const double *__restrict__ x,
                                               int row, int lane)
 {
     const int beg = __ldg(ptr + row), end = __ldg(ptr + row + 1);
     double acc = 0.0;
-    for (int p = beg + lane; p < end; p += T) acc = fma(__ldg(vals + p), __ldg(x + __ldg(cols + p)), acc);
+    for (int p = beg + lane; p < end; p += T) {
+        const int c = STREAM ? __ldcs(cols + p) : __ldg(cols + p);
+        const double v = STREAM ? __ldcs(vals + p) : __ldg(vals + p);
+        acc = fma(v, __ldg(x + c), acc);
+    }
 #pragma unroll
     for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
     return acc;
 }
 
-template <int MODE, int T>
+template <int MODE, int T, bool STREAM>
 __global__ void __launch_bounds__(ST) csrv_spmv_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
                                                       const double *__restrict__ vals, const double *__restrict__ x,
                                                       const double *b, double *y, int n_rows)
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(ST) csrv_spmv_kernel(const int *__restrict__ p
     const int t = blockIdx.x * ST + threadIdx.x;
     const int row = t / T, lane = t % T;
     const int r = row < n_rows ? row : n_rows - 1;       // whole warp takes part in the shuffles
-    const double ax = csr_row_dot<T>(ptr, cols, vals, x, r, lane);
+    const double ax = csr_row_dot<T, STREAM>(ptr, cols, vals, x, r, lane);
     if (row >= n_rows || lane != 0) return;
     if (MODE == SELL_ASSIGN) y[row] = ax;
     else if (MODE == SELL_RESIDUAL) y[row] = b[row] - ax;
@@ -243,34 +251,52 @@ __global__ void __launch_bounds__(ST) csrv_cheb_kernel(const int *__restrict__ p
     const int t = blockIdx.x * ST + threadIdx.x;
     const int row = t / T, lane = t % T;
     const int r = row < n_rows ? row : n_rows - 1;
-    const double ax = csr_row_dot<T>(ptr, cols, vals, p_cur, r, lane);
+    const double ax = csr_row_dot<T, false>(ptr, cols, vals, p_cur, r, lane);
     if (row >= n_rows || lane != 0) return;
     double v = bq * p_cur[row] + c * dinv[row] * (b[row] - ax);
     if (a != 0.0) v = fma(a, p_prev[row], v);
     out[row] = v;
 }
 
-template <int T>
-void launch_csrv_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
+template <int T, bool STREAM>
+void launch_csrv_spmv_s(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
 {
     const int n = A.pat->n_rows, blocks = ceil_div((int64_t)n * T, ST);
     switch (mode) {
-    case SELL_ASSIGN: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ASSIGN, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_RESIDUAL, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_ADD: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ADD, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    default: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_SUB, T>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_ASSIGN: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ASSIGN, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_RESIDUAL, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    case SELL_ADD: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ADD, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
+    default: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_SUB, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
     }
+}
+
+template <int T>
+void launch_csrv_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
+{
+    // matrices above 32 MB (fine-level restriction) stream through L2 with evict-first
+    if (A.pat->nnz * 12 > (32ll << 20)) launch_csrv_spmv_s<T, true>(h, A, x, y, b, mode);
+    else launch_csrv_spmv_s<T, false>(h, A, x, y, b, mode);
 }
 
 }  // namespace
 
 int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
 {
+    if (h->recorder) {
+        CTL_CHECK(A.lanes > 0, CTL_ERR_STATE, "fused tail: matrix is not in CSR form");
+        FusedOp op{};
+        op.type = FOP_SPMV; op.n = A.pat->n_rows; op.lanes = A.lanes; op.mode = mode;
+        op.ptr = A.csr_ptr; op.cols = A.csr_cols; op.vals = A.csr_vals;
+        op.cur = x; op.b = b; op.out = y;
+        h->recorder->host.push_back(op);
+        return CTL_OK;
+    }
     const SellPattern &p = *A.pat;
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
     if (A.lanes) {
-        if (A.lanes == 8) launch_csrv_spmv<8>(h, A, x, y, b, mode);
+        if (A.lanes == 4) launch_csrv_spmv<4>(h, A, x, y, b, mode);
+        else if (A.lanes == 8) launch_csrv_spmv<8>(h, A, x, y, b, mode);
         else if (A.lanes == 16) launch_csrv_spmv<16>(h, A, x, y, b, mode);
         else launch_csrv_spmv<32>(h, A, x, y, b, mode);
         h->launches++;
@@ -291,12 +317,24 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, con
 int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const double *b,
                    const double *p_prev, const double *p_cur, double *out, double a, double bq, double c)
 {
+    if (h->recorder) {
+        CTL_CHECK(A.lanes > 0, CTL_ERR_STATE, "fused tail: matrix is not in CSR form");
+        FusedOp op{};
+        op.type = FOP_CHEB; op.n = A.pat->n_rows; op.lanes = A.lanes;
+        op.ptr = A.csr_ptr; op.cols = A.csr_cols; op.vals = A.csr_vals;
+        op.dinv = dinv; op.b = b; op.prev = p_prev; op.cur = p_cur; op.out = out;
+        op.a = a; op.bq = bq; op.c = c;
+        h->recorder->host.push_back(op);
+        return CTL_OK;
+    }
     const SellPattern &p = *A.pat;
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
     if (A.lanes) {
         const int n = p.n_rows;
-        if (A.lanes == 8)
+        if (A.lanes == 4)
+            pdl_launch(h, ceil_div((int64_t)n * 4, ST), ST, csrv_cheb_kernel<4>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+        else if (A.lanes == 8)
             pdl_launch(h, ceil_div((int64_t)n * 8, ST), ST, csrv_cheb_kernel<8>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
         else if (A.lanes == 16)
             pdl_launch(h, ceil_div((int64_t)n * 16, ST), ST, csrv_cheb_kernel<16>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
@@ -315,6 +353,12 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
 
 int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n)
 {
+    if (h->recorder) {
+        FusedOp op{};
+        op.type = FOP_DINV_SCALE; op.n = n; op.dinv = dinv; op.b = b; op.out = out; op.c = c;
+        h->recorder->host.push_back(op);
+        return CTL_OK;
+    }
     if (n == 0) return CTL_OK;
     pdl_launch(h, ceil_div(n, ST), ST, dinv_scale_kernel, dinv, b, out, c, n);
     h->launches++;
@@ -324,6 +368,12 @@ int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double 
 
 int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
 {
+    if (h->recorder) {
+        FusedOp op{};
+        op.type = FOP_GEMV; op.n = n; op.vals = Ainv; op.b = b; op.out = y;
+        h->recorder->host.push_back(op);
+        return CTL_OK;
+    }
     if (n == 0) return CTL_OK;
     pdl_launch(h, ceil_div(n, ST / 32), ST, dense_gemv_kernel, Ainv, b, y, n);
     h->launches++;
@@ -341,5 +391,135 @@ int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const doub
                                                     beta, p.n_rows);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused coarse tail.  Below the second AMG level every operation is a few microseconds of
+// dependent L2 round trips on a few thousand rows, and a V-cycle issues about ten of them
+// per level: as separate kernels (even inside a CUDA graph) each costs about 5 us.  The
+// recorded program of the sub-cycle (same primitives, same order, same arithmetic) runs as
+// ONE cooperative kernel with a grid barrier between operations.
+// ---------------------------------------------------------------------------------------
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int FT = 1024;    // threads per CTA of the fused kernel
+
+template <int T>
+__device__ __forceinline__ void fused_rows(const FusedOp &op, int gtid, int gthreads)
+{
+    const int lane = gtid % T;
+    const int groups = gthreads / T;
+    const int n_pad = (op.n + groups - 1) / groups * groups;      // every thread joins the shuffles
+    for (int row = gtid / T; row < n_pad; row += groups) {
+        const bool live = row < op.n;
+        const int r = live ? row : op.n - 1;
+        const int beg = __ldg(op.ptr + r), end = __ldg(op.ptr + r + 1);
+        double acc = 0.0;
+        for (int p = beg + lane; p < end; p += T) acc = fma(__ldg(op.vals + p), op.cur[__ldg(op.cols + p)], acc);
+#pragma unroll
+        for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
+        if (!live || lane != 0) continue;
+        if (op.type == FOP_CHEB) {
+            double v = op.bq * op.cur[r] + op.c * op.dinv[r] * (op.b[r] - acc);
+            if (op.a != 0.0) v = fma(op.a, op.prev[r], v);
+            op.out[r] = v;
+        } else if (op.mode == SELL_ASSIGN) op.out[r] = acc;
+        else if (op.mode == SELL_RESIDUAL) op.out[r] = op.b[r] - acc;
+        else if (op.mode == SELL_ADD) op.out[r] += acc;
+        else op.out[r] -= acc;
+    }
+}
+
+__global__ void __launch_bounds__(FT) fused_tail_kernel(const FusedOp *__restrict__ ops, int n_ops)
+{
+    cg::grid_group grid = cg::this_grid();
+    const int gtid = blockIdx.x * FT + threadIdx.x;
+    const int gthreads = gridDim.x * FT;
+    for (int i = 0; i < n_ops; ++i) {
+        const FusedOp op = ops[i];
+        if (op.type == FOP_DINV_SCALE) {
+            for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.c * op.dinv[r] * op.b[r];
+        } else if (op.type == FOP_COPY) {
+            for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.cur[r];
+        } else if (op.type == FOP_GEMV) {
+            const int lane = gtid & 31, warps = gthreads >> 5;
+            for (int row = gtid >> 5; row < op.n; row += warps) {
+                double acc = 0.0;
+                for (int j = lane; j < op.n; j += 32) acc = fma(__ldg(op.vals + (size_t)row * op.n + j), op.b[j], acc);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) op.out[row] = acc;
+            }
+        } else {
+            switch (op.lanes) {
+            case 4: fused_rows<4>(op, gtid, gthreads); break;
+            case 8: fused_rows<8>(op, gtid, gthreads); break;
+            case 16: fused_rows<16>(op, gtid, gthreads); break;
+            default: fused_rows<32>(op, gtid, gthreads); break;
+            }
+        }
+        grid.sync();
+    }
+}
+
+}  // namespace
+
+int vec_copy_n(ctl_handle_s *h, double *dst, const double *src, int n)
+{
+    if (h->recorder) {
+        FusedOp op{};
+        op.type = FOP_COPY; op.n = n; op.cur = src; op.out = dst;
+        h->recorder->host.push_back(op);
+        return CTL_OK;
+    }
+    CTL_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return CTL_OK;
+}
+
+int fused_upload(ctl_handle_s *h, FusedProgram &p)
+{
+    p.n_ops = (int)p.host.size();
+    if (p.n_ops == 0) return CTL_OK;
+    CTL_CUDA(cudaMalloc((void **)&p.dev, p.host.size() * sizeof(FusedOp)));
+    CTL_CUDA(cudaMemcpyAsync(p.dev, p.host.data(), p.host.size() * sizeof(FusedOp), cudaMemcpyHostToDevice, h->stream));
+    CTL_CUDA(cudaStreamSynchronize(h->stream));
+    return CTL_OK;
+}
+
+void fused_free(FusedProgram &p)
+{
+    cudaFree(p.dev);
+    p.dev = nullptr;
+    p.n_ops = 0;
+    p.host.clear();
+}
+
+int fused_run(ctl_handle_s *h, const FusedProgram &p)
+{
+    if (p.n_ops == 0) return CTL_OK;
+    static int n_sm = 0;
+    if (!n_sm) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    cudaLaunchConfig_t cfg{};
+    static int n_cta = 0;
+    if (!n_cta) {
+        n_cta = 32;
+        if (const char *e = getenv("CTL_FUSED_CTAS")) n_cta = std::max(1, std::min(n_sm, atoi(e)));
+    }
+    cfg.gridDim = dim3(n_cta);
+    cfg.blockDim = dim3(FT);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeCooperative;
+    at.val.cooperative = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    const FusedOp *ops = p.dev;
+    int n_ops = p.n_ops;
+    CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_tail_kernel, ops, n_ops));
+    h->launches++;
     return CTL_OK;
 }

@@ -38,7 +38,30 @@ int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPa
 int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values,
                     SellMat &out);
 // one call for matrices that own their pattern: picks SELL or CSR-vector by mean row length
-int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out);
+// (force_csr: always CSR, the only format the fused coarse-tail kernel reads)
+int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_csr = false);
+
+// ---- fused coarse tail: while a recorder is installed on the handle, the primitives below
+// append their operation to it instead of launching a kernel; the recorded program is later
+// executed by ONE cooperative kernel with grid-wide barriers between operations (sell.cu).
+enum FusedType { FOP_DINV_SCALE = 0, FOP_CHEB = 1, FOP_SPMV = 2, FOP_GEMV = 3, FOP_COPY = 4 };
+struct FusedOp {
+    int type, n, lanes, mode;
+    const int *ptr, *cols;
+    const double *vals;
+    const double *dinv, *b, *prev, *cur;
+    double *out;
+    double a, bq, c;
+};
+struct FusedProgram {
+    std::vector<FusedOp> host;
+    FusedOp *dev = nullptr;
+    int n_ops = 0;
+};
+int fused_upload(ctl_handle_s *h, FusedProgram &p);
+int fused_run(ctl_handle_s *h, const FusedProgram &p);
+void fused_free(FusedProgram &p);
+int vec_copy_n(ctl_handle_s *h, double *dst, const double *src, int n);   // recordable device copy
 void sell_free(SellMat &m);
 
 enum SellMode {
