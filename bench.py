@@ -33,6 +33,16 @@ METRIC = "kkt_solve_time"
 UNIT = "s"
 
 
+def ncu_traffic(key, args):
+    """DRAM bytes per launch from the committed ncu capture (only valid for the C2 sizes)."""
+    if args.nx != 1024 or args.n_t != 64 or args.gpus != 1:
+        return None
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]["bytes"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -282,7 +292,7 @@ def main():
     spmm_ms = sum(i.seconds_mult for i in infos) / sum(i.n_mult for i in infos) * 1e3
     roof_spmm = {"kernel": "kkt_apply_staged_kernel (fused time-batched KKT SpMM)", "bound": "hbm",
                  "achieved": spmm_bytes / spmm_ms / 1e6, "peak": peak, "unit": "GB/s",
-                 "frac": spmm_bytes / spmm_ms / 1e6 / peak, "traffic": None,
+                 "frac": spmm_bytes / spmm_ms / 1e6 / peak, "traffic": ncu_traffic("kkt_apply_C2", args),
                  "alg_bytes_per_launch": spmm_bytes, "ms_per_launch": spmm_ms,
                  "how": "CUDA events around every apply inside the timed solves"}
     # ---- roofline: dominant kernel of the step = fine-level smoother SpMV of the AMG sweeps
@@ -291,7 +301,8 @@ def main():
     if micro:
         roof = {"kernel": "sell_cheb_kernel, AMG level 0 (smoother step of the time sweeps)", "bound": "hbm",
                 "achieved": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6, "peak": peak, "unit": "GB/s",
-                "frac": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6 / peak, "traffic": None,
+                "frac": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6 / peak,
+                "traffic": ncu_traffic("sell_cheb_kernel_level0_C2", args),
                 "alg_bytes_per_launch": micro["cheb_bytes"], "ms_per_launch": micro["cheb_ms"],
                 "how": "CUDA events per launch, L2 flushed between launches"}
     pc_s = sum(i.seconds_pc for i in infos) / max(1, sum(i.n_pc for i in infos))
