@@ -369,6 +369,7 @@ static int solve_tf(ctl_handle_s *h, const double *b_tf, double *u_tf, const ctl
         if (rc == CTL_OK) rc = S.project(u_tf, nullptr);
         if (rc == CTL_OK) rc = (opts->ksp_type == CTL_KSP_MINRES) ? S.minres(b, u_tf) : S.gmres(b, u_tf);
         if (rc == CTL_OK) rc = S.project(u_tf, nullptr);                   // 761-766
+        if (rc == CTL_OK) rc = ctl_comm_check(h);
     }
     cudaEventRecord(e1, h->stream);
     cudaEventSynchronize(e1);

@@ -52,8 +52,9 @@ def main():
         e_pc = max(rel(p0, loc(r0)), rel(p1, loc(r1)))
         assert e_pc < 1e-10, e_pc
         # solve
-        sp_ = {"linear_solver": "fgmres", "maximum_iterations": 100, "relative_tolerance": 1e-8,
-               "absolute_tolerance": 0.0}
+        # BE stalls near 1e-8 (rounding floor, see test_gpu_pc.py): compare counts above it
+        sp_ = {"linear_solver": "fgmres", "maximum_iterations": 100, "relative_tolerance": 1e-8 if CN else 1e-6,
+               "absolute_tolerance": 0.0, "gmres_restart": 100}
         ref = ocontrol.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=CN,
                                     time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"],
                                     f=q["f"], lambda_v_bounds=q["lambda_v_bounds"], solver_parameters=sp_)
@@ -62,7 +63,7 @@ def main():
         info = s.solve(u0, u1, loc(ref["b_0"]), loc(ref["b_1"]), solver_parameters=sp_, pc_fn="builtin")
         e_sol = max(rel(u0, loc(ref["v_blocks"])), rel(u1, loc(ref["zeta_blocks"])))
         assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1, (info.its, ref["ksp"].its)
-        assert e_sol < 1e-6, e_sol
+        assert e_sol < (1e-6 if CN else 1e-4), e_sol
         if rank == 0:
             print(f"CN={CN} world={world}: apply {e_apply:.1e} pc {e_pc:.1e} solve its {info.its}/{ref['ksp'].its} "
                   f"diff {e_sol:.1e}", flush=True)
