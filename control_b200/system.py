@@ -389,6 +389,21 @@ class MultiBlockSystem:
             raise RuntimeError("Error encountered in PETSc solve")
         return info
 
+    def solve_host(self, u_host, b_host, *, solver_parameters, pc="builtin"):
+        """``ctl_solve_host``: the end-to-end C entry point.  ``b_host`` / ``u_host`` are flat
+        block-major float64 numpy arrays (``u_host``: initial guess in, solution out); the
+        library copies them to the device and back itself."""
+        kind = {"none": L.CTL_PC_NONE, "builtin": L.CTL_PC_BUILTIN, "callback": L.CTL_PC_CALLBACK}[pc]
+        if kind == L.CTL_PC_BUILTIN and not self._pc_ready:
+            raise L.CtlError("call setup_preconditioner() first")
+        if b_host.dtype != np.float64 or u_host.dtype != np.float64 or not b_host.flags.c_contiguous \
+                or not u_host.flags.c_contiguous or b_host.size != self.vec_len() or u_host.size != self.vec_len():
+            raise ValueError("solve_host needs contiguous float64 arrays of vec_len() entries")
+        o = self._krylov_options(solver_parameters, kind)
+        res = L.ctl_solve_result()
+        self._call(self._lib.ctl_solve_host, b_host.ctypes.data, u_host.ctypes.data, C.byref(o), C.byref(res))
+        return KSPInfo(res)
+
     def residual_norm(self, b_dev, x_dev, layout=L.CTL_LAYOUT_BLOCK_MAJOR):
         out = C.c_double()
         self._call(self._lib.ctl_kkt_residual_norm, b_dev.data_ptr(), x_dev.data_ptr(), layout, C.byref(out))

@@ -88,3 +88,19 @@ def test_state_errors_are_loud():
         s2 = MultiBlockSystem(q["M"], K2, n_t=q["n_t"], beta=q["beta"], CN=True, bc_dofs=q["bdofs"])
         s2.setup_preconditioner(mode="diagonal")
     s.close()
+
+
+def test_solve_host_entry_point_matches_device_solve():
+    """ctl_solve_host (host buffers in, host buffers out) == ctl_solve on device vectors."""
+    from control_b200 import MultiBlockSystem
+    q = kat.heat_problem(12, 7, True, beta=1e-3)
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 100, "relative_tolerance": 1e-9, "absolute_tolerance": 0.0}
+    s, info, u0, u1, ref = _solve_both(q, True, sp_)
+    b = np.concatenate([ref["b_0"].ravel(), ref["b_1"].ravel()])
+    u = np.zeros_like(b)
+    info_h = s.solve_host(u, b, solver_parameters=sp_)
+    assert info_h.its == info.its and info_h.reason == info.reason
+    assert np.array_equal(u, np.concatenate([u0.ravel(), u1.ravel()]))      # same kernels, same order: bit-identical
+    with pytest.raises(ValueError):
+        s.solve_host(u[:-1], b, solver_parameters=sp_)
+    s.close()
