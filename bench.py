@@ -106,35 +106,46 @@ def solver_parameters(ksp, rtol):
 # CPU oracle sample: one Krylov iteration (KKT apply + preconditioner apply) at the full
 # spatial size on n_s of the N time blocks, scaled to a whole solve.
 # --------------------------------------------------------------------------------------
+class CpuSample:
+    """Oracle preconditioner + operator on `n_blocks_sample` time blocks; AMG set up once."""
+
+    def __init__(self, q_full, n_blocks_sample, mode):
+        from oracle import pc as opc
+        self.q = q_full
+        self.ns = n_blocks_sample
+        M, K, bd, beta = q_full["M"], q_full["K"], q_full["bdofs"], q_full["beta"]
+        tau = q_full["tau"]
+        n_t_s = n_blocks_sample + 1
+        n = M.shape[0]
+        if mode == "diagonal":
+            self.pc = opc.construct_pc_diagonal(M, K, tau, beta, n_t_s, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
+        else:
+            self.pc = opc.construct_pc(M, K, tau, beta, n_t_s, True, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
+        rng = np.random.default_rng(0)
+        self.x0 = rng.standard_normal((n_blocks_sample, n))
+        self.x1 = rng.standard_normal((n_blocks_sample, n))
+        self.x0[:, bd] = 0.0
+        self.x1[:, bd] = 0.0
+        self.pc(self.x0, self.x1)          # untimed: AMG setup + numba compilation happen on first use
+
+    def run(self, its):
+        from oracle import fastmv, kkt
+        q = self.q
+        M, K, bd, beta, tau = q["M"], q["K"], q["bdofs"], q["beta"], q["tau"]
+        t0 = time.perf_counter()
+        y0, y1 = kkt.kkt_apply_fused(M, K, tau, beta, self.ns + 1, True, bd, self.x0, self.x1)
+        t_apply = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        self.pc(y0, y1)
+        t_pc = time.perf_counter() - t0
+        scale = (q["n_t"] - 1) / self.ns
+        per_iter = (t_apply + t_pc) * scale
+        return {"threads": fastmv.threads(), "seconds_sample": t_apply + t_pc, "seconds_per_iteration_full": per_iter,
+                "value": per_iter * (its + 1), "kkt_apply_s_full": t_apply * scale, "pc_apply_s_full": t_pc * scale}
+
+
 def cpu_sample(q_full, n_blocks_sample, its, mode):
-    from oracle import kkt
-    from oracle import pc as opc
-    M, K, bd, beta = q_full["M"], q_full["K"], q_full["bdofs"], q_full["beta"]
-    tau = q_full["tau"]
-    n_t_s = n_blocks_sample + 1
-    n = M.shape[0]
-    N_full = q_full["n_t"] - 1
-    if mode == "diagonal":
-        pc = opc.construct_pc_diagonal(M, K, tau, beta, n_t_s, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
-    else:
-        pc = opc.construct_pc(M, K, tau, beta, n_t_s, True, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
-    rng = np.random.default_rng(0)
-    x0 = rng.standard_normal((n_blocks_sample, n))
-    x1 = rng.standard_normal((n_blocks_sample, n))
-    x0[:, bd] = 0.0
-    x1[:, bd] = 0.0
-    pc(x0, x1)                      # untimed: AMG setup + numba compilation happen on first use
-    t0 = time.perf_counter()
-    y0, y1 = kkt.kkt_apply_fused(M, K, tau, beta, n_t_s, True, bd, x0, x1)
-    t_apply = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    pc(y0, y1)
-    t_pc = time.perf_counter() - t0
-    scale = N_full / n_blocks_sample
-    per_iter = (t_apply + t_pc) * scale
-    from oracle import fastmv
-    return {"threads": fastmv.threads(), "seconds_sample": t_apply + t_pc, "seconds_per_iteration_full": per_iter,
-            "value": per_iter * (its + 1), "kkt_apply_s_full": t_apply * scale, "pc_apply_s_full": t_pc * scale}
+    return CpuSample(q_full, n_blocks_sample, mode).run(its)
 
 
 def run_reference(args):
@@ -149,8 +160,9 @@ def run_reference(args):
     its = args.ref_its
     times = []
     info = None
+    sampler = CpuSample(q, args.sample_blocks, mode)
     for i in range(args.warmup + args.steps):
-        info = cpu_sample(q, args.sample_blocks, its, mode)
+        info = sampler.run(its)
         if i >= args.warmup:
             times.append(info["value"])
     val = float(np.mean(times))

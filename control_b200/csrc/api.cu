@@ -71,8 +71,7 @@ int ctl_create(const ctl_config *cfg, ctl_handle *out)
     CTL_CHECK(cfg->world >= 1 && cfg->rank >= 0 && cfg->rank < cfg->world, CTL_ERR_ARG,
               "ctl_create: bad rank/world");
     const int N = cfg->CN ? cfg->n_t - 1 : cfg->n_t;
-    CTL_CHECK(N <= 64, CTL_ERR_ARG,
-              "ctl_create: more than 64 time blocks are not supported by the fused kernels yet");
+    CTL_CHECK(N <= 256, CTL_ERR_ARG, "ctl_create: more than 256 time blocks are not supported");
     {
         cudaError_t e = cudaSetDevice(cfg->device);
         if (e != cudaSuccess) {

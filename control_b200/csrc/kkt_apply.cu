@@ -587,6 +587,162 @@ cudaError_t launch_tma(const KktArgs &a, int G, int cap, int umax, int tile_rows
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Wide variant for more than 64 time blocks (ld = 128 or 256): one warp per row, every lane
+// owns CPL = ld / 32 CONSECUTIVE time columns, so the block stencil and T_1 / T_2 only cross
+// lanes at the ends of a lane's column group.  Same staging as the kernel above.
+// ---------------------------------------------------------------------------------------
+template <int CPL>
+__device__ __forceinline__ void time_prev(const double (&a)[CPL], double (&out)[CPL], int lane)
+{
+    const double t = __shfl_up_sync(0xffffffffu, a[CPL - 1], 1);
+    out[0] = lane == 0 ? 0.0 : t;
+#pragma unroll
+    for (int c = 1; c < CPL; ++c) out[c] = a[c - 1];
+}
+
+template <int CPL>
+__device__ __forceinline__ void time_next(const double (&a)[CPL], double (&out)[CPL], int lane)
+{
+    const double t = __shfl_down_sync(0xffffffffu, a[0], 1);
+#pragma unroll
+    for (int c = 0; c < CPL - 1; ++c) out[c] = a[c + 1];
+    out[CPL - 1] = lane == 31 ? 0.0 : t;
+}
+
+template <bool CN, bool PER_LEVEL, bool SYM, bool HALO, int CPL>
+__global__ void __launch_bounds__(256) kkt_apply_wide_kernel(const KktArgs a, const int rows_per_cta, const int cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2 *s_mk = reinterpret_cast<double2 *>(smem_raw);
+    double *s_kt = reinterpret_cast<double *>(s_mk + (cap + 1));
+    int *s_col = reinterpret_cast<int *>(SYM || PER_LEVEL ? s_kt : s_kt + (cap + 1));
+    int *s_ptr = s_col + (cap + 1);
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int c0 = CPL * lane;
+    const int ld = a.ld;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int nrows = min(rows_per_cta, a.n_rows - r0);
+
+    for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
+    __syncthreads();
+    const int kb = s_ptr[0];
+    const int cnt = s_ptr[nrows] - kb;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        s_col[k] = __ldg(a.indices + kb + k);
+        s_mk[k] = make_double2(__ldg(a.Mv + kb + k), PER_LEVEL ? 0.0 : __ldg(a.Kv + kb + k));
+        if (!PER_LEVEL && !SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+    }
+    __syncthreads();
+
+    const int N = a.N;
+    const double tau = a.tau, beta = a.beta;
+    for (int lr = wid; lr < nrows; lr += (blockDim.x >> 5)) {
+        const int r = r0 + lr;
+        const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
+        double mv[CPL], kv[CPL], mz[CPL], kz[CPL];
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) mv[c] = kv[c] = mz[c] = kz[c] = 0.0;
+        for (int k = kbeg; k < kend; ++k) {
+            const int col = s_col[k];
+            const bool own = !HALO || col < a.n_own_cols;
+            const double *pv = own ? a.xv + (size_t)col * ld : a.hv + (size_t)(col - a.n_own_cols) * ld;
+            const double *pz = own ? a.xz + (size_t)col * ld : a.hz + (size_t)(col - a.n_own_cols) * ld;
+            const double2 mk = s_mk[k];
+            const double kt = (SYM || PER_LEVEL) ? mk.y : s_kt[k];
+#pragma unroll
+            for (int q = 0; q < CPL / 2; ++q) {
+                const double2 xv = ldg2(pv + c0 + 2 * q);
+                const double2 xz = ldg2(pz + c0 + 2 * q);
+                double2 kk = make_double2(mk.y, mk.y), kkt = make_double2(kt, kt);
+                if (PER_LEVEL) {
+                    kk = ldg2(a.Kv + (size_t)(kb + k) * ld + c0 + 2 * q);
+                    kkt = ldg2(a.KTv + (size_t)(kb + k) * ld + c0 + 2 * q);
+                }
+                mv[2 * q] = fma(mk.x, xv.x, mv[2 * q]);
+                mv[2 * q + 1] = fma(mk.x, xv.y, mv[2 * q + 1]);
+                mz[2 * q] = fma(mk.x, xz.x, mz[2 * q]);
+                mz[2 * q + 1] = fma(mk.x, xz.y, mz[2 * q + 1]);
+                kv[2 * q] = fma(kk.x, xv.x, kv[2 * q]);
+                kv[2 * q + 1] = fma(kk.y, xv.y, kv[2 * q + 1]);
+                kz[2 * q] = fma(kkt.x, xz.x, kz[2 * q]);
+                kz[2 * q + 1] = fma(kkt.y, xz.y, kz[2 * q + 1]);
+            }
+        }
+        double y0[CPL], y1[CPL];
+        if (CN) {
+            const double h = 0.5 * tau, hb = h / beta;
+            double mvp[CPL], kvp[CPL], kzn[CPL], mzn[CPL], r0v[CPL], r1v[CPL], r0n[CPL], r1p[CPL];
+            time_prev<CPL>(mv, mvp, lane);
+            time_prev<CPL>(kv, kvp, lane);
+            time_next<CPL>(kz, kzn, lane);
+            time_next<CPL>(mz, mzn, lane);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const bool in = c0 + c < N;
+                r0v[c] = in ? h * (mvp[c] + mv[c]) + h * (kz[c] + kzn[c]) + mz[c] - mzn[c] : 0.0;
+                r1v[c] = in ? h * (kvp[c] + kv[c]) - mvp[c] + mv[c] - hb * (mz[c] + mzn[c]) : 0.0;
+            }
+            time_next<CPL>(r0v, r0n, lane);
+            time_prev<CPL>(r1v, r1p, lane);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                y0[c] = r0v[c] + r0n[c];
+                y1[c] = r1v[c] + r1p[c];
+            }
+        } else {
+            const double tb = tau / beta;
+            double mvp[CPL], mzn[CPL];
+            time_prev<CPL>(mv, mvp, lane);
+            time_next<CPL>(mz, mzn, lane);
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int col = c0 + c;
+                y0[c] = tau * kz[c] + mz[c] + ((col < N - 1) ? (tau * mv[c] - mzn[c]) : 0.0);
+                y1[c] = tau * kv[c] + mv[c] + ((col >= 1) ? (-mvp[c] - tb * mz[c]) : 0.0);
+            }
+        }
+        const size_t ro = (size_t)r * ld + c0;
+        const bool bc = a.bcmask[r] != 0;
+#pragma unroll
+        for (int q = 0; q < CPL / 2; ++q) {
+            double2 o0 = make_double2(c0 + 2 * q < N ? y0[2 * q] : 0.0, c0 + 2 * q + 1 < N ? y0[2 * q + 1] : 0.0);
+            double2 o1 = make_double2(c0 + 2 * q < N ? y1[2 * q] : 0.0, c0 + 2 * q + 1 < N ? y1[2 * q + 1] : 0.0);
+            if (bc) {
+                o0 = ldg2(a.xv + ro + 2 * q);
+                o1 = ldg2(a.xz + ro + 2 * q);
+            }
+            __stcs(reinterpret_cast<double2 *>(a.y0 + ro + 2 * q), o0);
+            __stcs(reinterpret_cast<double2 *>(a.y1 + ro + 2 * q), o1);
+        }
+    }
+}
+
+template <bool CN, bool PER_LEVEL, bool SYM, bool HALO>
+void launch_wide_h(const KktArgs &a, int rows_per_cta, int cap, cudaStream_t s)
+{
+    const int blocks = ceil_div(a.n_rows, rows_per_cta);
+    const size_t smem = (size_t)(cap + 1) * (16 + ((SYM || PER_LEVEL) ? 0 : 8) + 4) + (size_t)(rows_per_cta + 1) * 4;
+    if (a.ld == 128) kkt_apply_wide_kernel<CN, PER_LEVEL, SYM, HALO, 4><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap);
+    else kkt_apply_wide_kernel<CN, PER_LEVEL, SYM, HALO, 8><<<blocks, 256, smem, s>>>(a, rows_per_cta, cap);
+}
+
+template <bool CN>
+void launch_wide(const KktArgs &a, bool per_level, bool sym, bool halo, int rows_per_cta, int cap, cudaStream_t s)
+{
+    if (per_level) {
+        if (halo) launch_wide_h<CN, true, false, true>(a, rows_per_cta, cap, s);
+        else launch_wide_h<CN, true, false, false>(a, rows_per_cta, cap, s);
+    } else if (sym) {
+        if (halo) launch_wide_h<CN, false, true, true>(a, rows_per_cta, cap, s);
+        else launch_wide_h<CN, false, true, false>(a, rows_per_cta, cap, s);
+    } else {
+        if (halo) launch_wide_h<CN, false, false, true>(a, rows_per_cta, cap, s);
+        else launch_wide_h<CN, false, false, false>(a, rows_per_cta, cap, s);
+    }
+}
+
 template <bool CN, bool PER_LEVEL>
 void launch_g(const KktArgs &a, int G, cudaStream_t s)
 {
@@ -636,6 +792,15 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     const bool fits = (size_t)std::max(h->n_loc, h->n_halo) * h->ld * 8 < 0x7fffffffull;
     const bool staged = rows_per_cta >= 8 && !h->force_unstaged && fits;
     const bool halo = h->n_halo > 0;
+    if (h->ld > 64) {
+        CTL_CHECK(rows_per_cta >= 8, CTL_ERR_ARG, "ctl_kkt_apply: rows too long for the wide (N > 64) kernel");
+        const bool sym = h->d_KT == h->d_K;
+        if (h->cfg.CN) launch_wide<true>(a, h->per_level, sym, halo, rows_per_cta, rows_per_cta * max_len, h->stream);
+        else launch_wide<false>(a, h->per_level, sym, halo, rows_per_cta, rows_per_cta * max_len, h->stream);
+        h->launches++;
+        CTL_CUDA(cudaGetLastError());
+        return CTL_OK;
+    }
     a.tile_uptr = h->d_tile_uptr;
     a.tile_ucols = h->d_tile_ucols;
     a.tile_slot = h->d_tile_slot;

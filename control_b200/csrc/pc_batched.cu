@@ -9,7 +9,8 @@
 //   u0_final   scaling 2/tau | 1/tau | 1/(tau eps) and T_2^-1         (2008-2014, 2202-2206)
 //   schur_rhs  b = T_2 (L u_0) - b_1, masked, then T_2^-1             (2017-2053, 2209-2237)
 //
-// Thread mapping as in kkt_apply.cu: G = ld/2 lanes per row, lane l owns columns 2l, 2l+1.
+// Thread mapping as in kkt_apply.cu: G lanes per row, every lane owns CPL consecutive time columns
+// (ld = G * CPL: CPL = 2 up to 64 columns, 4 or 8 for 128 / 256 columns).
 #include <algorithm>
 
 #include "common.cuh"
@@ -45,24 +46,51 @@ __device__ __forceinline__ double group_suffix(double v, int l)
     return v;
 }
 
+// A lane owns CPL consecutive time columns c0 .. c0+CPL-1 (c0 = CPL * l, CPL even).
 // T_1^-1: x_i <- sum_{k >= i} (-1)^(k-i) x_k   (control/control.py:63-78)
-template <int G>
-__device__ __forceinline__ void t1_inv(double &x0, double &x1, int l)
+template <int G, int CPL>
+__device__ __forceinline__ void t1_inv(double (&x)[CPL], int l)
 {
-    const double z0 = x0, z1 = -x1;                 // column 2l is even
-    const double s = group_suffix<G>(z0 + z1, l);   // sum over columns >= 2l
-    x0 = s;
-    x1 = -(s - z0);
+    double z[CPL], tot = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        z[c] = (c & 1) ? -x[c] : x[c];             // (-1)^column, c0 is even
+        tot += z[c];
+    }
+    double s = group_suffix<G>(tot, l);             // sum over columns >= c0
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        x[c] = (c & 1) ? -s : s;
+        s -= z[c];
+    }
 }
 
 // T_2^-1: x_i <- sum_{k <= i} (-1)^(i-k) x_k   (control/control.py:81-96)
-template <int G>
-__device__ __forceinline__ void t2_inv(double &x0, double &x1, int l)
+template <int G, int CPL>
+__device__ __forceinline__ void t2_inv(double (&x)[CPL], int l)
 {
-    const double z0 = x0, z1 = -x1;
-    const double s = group_prefix<G>(z0 + z1, l);   // sum over columns <= 2l+1
-    x0 = s - z1;
-    x1 = -s;
+    double z[CPL], tot = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        z[c] = (c & 1) ? -x[c] : x[c];
+        tot += z[c];
+    }
+    double s = group_prefix<G>(tot, l) - tot;       // sum over columns < c0
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        s += z[c];
+        x[c] = (c & 1) ? -s : s;
+    }
+}
+
+// value of the previous time column (0 before the first)
+template <int G, int CPL>
+__device__ __forceinline__ void time_prev(const double (&a)[CPL], double (&out)[CPL], int l)
+{
+    const double t = __shfl_up_sync(0xffffffffu, a[CPL - 1], 1, G);
+    out[0] = l == 0 ? 0.0 : t;
+#pragma unroll
+    for (int c = 1; c < CPL; ++c) out[c] = a[c - 1];
 }
 
 struct RowMap {
@@ -70,7 +98,7 @@ struct RowMap {
     bool live;
 };
 
-template <int G>
+template <int G, int CPL>
 __device__ __forceinline__ RowMap row_map(int n_rows)
 {
     RowMap m;
@@ -80,31 +108,55 @@ __device__ __forceinline__ RowMap row_map(int n_rows)
     m.live = m.row < n_rows;
     m.r = m.live ? m.row : n_rows - 1;
     m.l = lane % G;
-    m.c0 = 2 * m.l;
+    m.c0 = CPL * m.l;
     return m;
 }
 
+template <int CPL>
+__device__ __forceinline__ void load_cols(const double *p, double (&x)[CPL])
+{
+#pragma unroll
+    for (int q = 0; q < CPL / 2; ++q) {
+        const double2 v = ldg2(p + 2 * q);
+        x[2 * q] = v.x;
+        x[2 * q + 1] = v.y;
+    }
+}
+
+template <int CPL>
+__device__ __forceinline__ void store_cols(double *p, const double (&x)[CPL])
+{
+#pragma unroll
+    for (int q = 0; q < CPL / 2; ++q) *reinterpret_cast<double2 *>(p + 2 * q) = make_double2(x[2 * q], x[2 * q + 1]);
+}
+
 // ------------------------------------------------------------------ u0_first
-template <bool CN, int G>
+template <bool CN, int G, int CPL>
 __global__ void __launch_bounds__(256) u0_first_kernel(const double *__restrict__ b0, const uint8_t *__restrict__ bc,
                                                       const double *__restrict__ dinv, double *__restrict__ btil,
                                                       double *__restrict__ p1, double c, int n_rows, int N, int ld)
 {
-    const RowMap m = row_map<G>(n_rows);
+    const RowMap m = row_map<G, CPL>(n_rows);
     const size_t off = (size_t)m.r * ld + m.c0;
-    double2 v = ldg2(b0 + off);
-    if (bc[m.r]) v = make_double2(0.0, 0.0);
-    if (CN) t1_inv<G>(v.x, v.y, m.l);
+    double v[CPL];
+    load_cols<CPL>(b0 + off, v);
+    if (bc[m.r]) {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] = 0.0;
+    }
+    if (CN) t1_inv<G, CPL>(v, m.l);
     if (!m.live) return;
-    *reinterpret_cast<double2 *>(btil + off) = v;
+    store_cols<CPL>(btil + off, v);
     const double s = c * dinv[m.r];
-    *reinterpret_cast<double2 *>(p1 + off) = make_double2(s * v.x, s * v.y);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) v[k] *= s;
+    store_cols<CPL>(p1 + off, v);
 }
 
 // ------------------------------------------------------------------ cheb_step
 // out = a p_prev + bq p_cur + c dinv (btil - M_bc p_cur); M_bc = M with constrained
 // rows/columns replaced by the identity (assemble(M, bcs), control/control.py:1971-1972)
-template <int G>
+template <int G, int CPL>
 __global__ void __launch_bounds__(256) cheb_step_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
                                                        const double *__restrict__ Mv, const uint8_t *__restrict__ bc,
                                                        const double *__restrict__ dinv, const double *__restrict__ btil,
@@ -112,140 +164,153 @@ __global__ void __launch_bounds__(256) cheb_step_kernel(const int *__restrict__ 
                                                        const double *__restrict__ halo, double *out, double a,
                                                        double bq, double c, int n_rows, int ld)
 {
-    const RowMap m = row_map<G>(n_rows);
+    const RowMap m = row_map<G, CPL>(n_rows);
     if (!m.live) return;
     const int r = m.r;
     const size_t off = (size_t)r * ld + m.c0;
-    double ax0 = 0.0, ax1 = 0.0;
-    const double2 pc = ldg2(p_cur + off);
+    double ax[CPL], pc[CPL];
+    load_cols<CPL>(p_cur + off, pc);
     if (bc[r]) {
-        ax0 = pc.x;
-        ax1 = pc.y;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) ax[k] = pc[k];
     } else {
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) ax[k] = 0.0;
         const int kb = __ldg(indptr + r), ke = __ldg(indptr + r + 1);
-#pragma unroll 4
+#pragma unroll 2
         for (int k = kb; k < ke; ++k) {
             const int col = __ldg(indices + k);
             const double mval = __ldg(Mv + k);
             const double *src = col < n_rows ? p_cur + (size_t)col * ld : halo + (size_t)(col - n_rows) * ld;
-            const double2 x = ldg2(src + m.c0);
-            ax0 = fma(mval, x.x, ax0);
-            ax1 = fma(mval, x.y, ax1);
+            double x[CPL];
+            load_cols<CPL>(src + m.c0, x);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) ax[q] = fma(mval, x[q], ax[q]);
         }
     }
-    const double2 bt = ldg2(btil + off);
+    double bt[CPL], o[CPL];
+    load_cols<CPL>(btil + off, bt);
     const double s = c * dinv[r];
-    double o0 = bq * pc.x + s * (bt.x - ax0);
-    double o1 = bq * pc.y + s * (bt.y - ax1);
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) o[k] = bq * pc[k] + s * (bt[k] - ax[k]);
     if (a != 0.0) {
-        const double2 pp = *reinterpret_cast<const double2 *>(p_prev + off);
-        o0 = fma(a, pp.x, o0);
-        o1 = fma(a, pp.y, o1);
+#pragma unroll
+        for (int q = 0; q < CPL / 2; ++q) {
+            const double2 pp = *reinterpret_cast<const double2 *>(p_prev + off + 2 * q);
+            o[2 * q] = fma(a, pp.x, o[2 * q]);
+            o[2 * q + 1] = fma(a, pp.y, o[2 * q + 1]);
+        }
     }
-    *reinterpret_cast<double2 *>(out + off) = make_double2(o0, o1);
+    store_cols<CPL>(out + off, o);
 }
 
 // ------------------------------------------------------------------ u0_final
-template <bool CN, int G>
+template <bool CN, int G, int CPL>
 __global__ void __launch_bounds__(256) u0_final_kernel(const double *__restrict__ p, const uint8_t *__restrict__ bc,
                                                       const double *wrap_b, double *__restrict__ u0, double sc,
                                                       double sc_last, int n_rows, int N, int ld)
 {
-    const RowMap m = row_map<G>(n_rows);
+    const RowMap m = row_map<G, CPL>(n_rows);
     const size_t off = (size_t)m.r * ld + m.c0;
-    double2 v = ldg2(p + off);
+    double v[CPL];
+    load_cols<CPL>(p + off, v);
     if (CN) {
-        v.x *= sc;
-        v.y *= sc;
-        t2_inv<G>(v.x, v.y, m.l);
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] *= sc;
+        t2_inv<G, CPL>(v, m.l);
     } else {
-        v.x *= (m.c0 == N - 1) ? sc_last : sc;
-        v.y *= (m.c0 + 1 == N - 1) ? sc_last : sc;
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] *= (m.c0 + k == N - 1) ? sc_last : sc;
     }
-    if (m.c0 >= N) v.x = 0.0;
-    if (m.c0 + 1 >= N) v.y = 0.0;
+#pragma unroll
+    for (int k = 0; k < CPL; ++k)
+        if (m.c0 + k >= N) v[k] = 0.0;
     if (!m.live) return;
-    if (bc[m.r]) v = wrap_b ? ldg2(wrap_b + off) : make_double2(0.0, 0.0);
-    *reinterpret_cast<double2 *>(u0 + off) = v;
+    if (bc[m.r]) {
+        if (wrap_b) load_cols<CPL>(wrap_b + off, v);
+        else {
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) v[k] = 0.0;
+        }
+    }
+    store_cols<CPL>(u0 + off, v);
 }
 
 // ------------------------------------------------------------------ schur_rhs
 // triangular mode: out = T_2^-1 mask(T_2 mask(L u_0) - b_1) (CN) / mask(L u_0 - b_1) (BE)
 // diagonal mode (u0 == nullptr): out = mask(b_1)
-template <bool CN, bool PER_LEVEL, int G>
+template <bool CN, bool PER_LEVEL, int G, int CPL>
 __global__ void __launch_bounds__(256) schur_rhs_kernel(const int *__restrict__ indptr, const int *__restrict__ indices,
                                                        const double *__restrict__ Mv, const double *__restrict__ Kv,
                                                        const uint8_t *__restrict__ bc, const double *__restrict__ u0,
                                                        const double *__restrict__ halo, const double *__restrict__ b1,
                                                        double *__restrict__ out, double tau, int n_rows, int N, int ld)
 {
-    const RowMap m = row_map<G>(n_rows);
+    const RowMap m = row_map<G, CPL>(n_rows);
     const int r = m.r;
     const size_t off = (size_t)r * ld + m.c0;
-    const bool first = m.l == 0;
-    double o0 = 0.0, o1 = 0.0;
+    double o[CPL], bb[CPL];
     const bool masked = bc[r] != 0;
+    load_cols<CPL>(b1 + off, bb);
     if (u0) {
-        double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0;
+        double mv[CPL], kv[CPL], mvp[CPL], kvp[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) mv[k] = kv[k] = 0.0;
         const int kb = __ldg(indptr + r), ke = __ldg(indptr + r + 1);
-#pragma unroll 2
         for (int k = kb; k < ke; ++k) {
             const int col = __ldg(indices + k);
             const double mval = __ldg(Mv + k);
             const double *src = col < n_rows ? u0 + (size_t)col * ld : halo + (size_t)(col - n_rows) * ld;
-            const double2 x = ldg2(src + m.c0);
-            mv0 = fma(mval, x.x, mv0);
-            mv1 = fma(mval, x.y, mv1);
-            if (PER_LEVEL) {
-                const double2 kk = ldg2(Kv + (size_t)k * ld + m.c0);
-                kv0 = fma(kk.x, x.x, kv0);
-                kv1 = fma(kk.y, x.y, kv1);
-            } else {
-                const double kk = __ldg(Kv + k);
-                kv0 = fma(kk, x.x, kv0);
-                kv1 = fma(kk, x.y, kv1);
+            double x[CPL], kk[CPL];
+            load_cols<CPL>(src + m.c0, x);
+            if (PER_LEVEL) load_cols<CPL>(Kv + (size_t)k * ld + m.c0, kk);
+            else {
+                const double ks = __ldg(Kv + k);
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) kk[q] = ks;
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                mv[q] = fma(mval, x[q], mv[q]);
+                kv[q] = fma(kk[q], x[q], kv[q]);
             }
         }
-        double t;
-        t = __shfl_up_sync(0xffffffffu, mv1, 1, G); const double mvp0 = first ? 0.0 : t;
-        if (CN) {
-            const double h = 0.5 * tau;
-            t = __shfl_up_sync(0xffffffffu, kv1, 1, G); const double kvp0 = first ? 0.0 : t;
-            // (L u)_i = (h K_{i+1} + M) u_i + (h K_i - M) u_{i-1}   (block_10, control.py:2942-2947)
-            o0 = (h * kv0 + mv0) + (h * kvp0 - mvp0);
-            o1 = (h * kv1 + mv1) + (h * kv0 - mv0);
-        } else {
-            // (L u)_i = (tau K_i + M) u_i - M u_{i-1}                (block_10, control.py:2912-2917)
-            o0 = (tau * kv0 + mv0) - mvp0;
-            o1 = (tau * kv1 + mv1) - mv0;
+        time_prev<G, CPL>(mv, mvp, m.l);
+        time_prev<G, CPL>(kv, kvp, m.l);
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            // CN: (L u)_i = (h K_{i+1} + M) u_i + (h K_i - M) u_{i-1}   (block_10, control.py:2942-2947)
+            // BE: (L u)_i = (tau K_i + M) u_i - M u_{i-1}                (block_10, control.py:2912-2917)
+            const double w = CN ? 0.5 * tau : tau;
+            o[q] = (w * kv[q] + mv[q]) + (CN ? (w * kvp[q] - mvp[q]) : -mvp[q]);
+            if (m.c0 + q >= N || masked) o[q] = 0.0;
         }
-        if (m.c0 >= N) o0 = 0.0;
-        if (m.c0 + 1 >= N) o1 = 0.0;
-        if (masked) { o0 = 0.0; o1 = 0.0; }
         if (CN) {   // T_2: add the previous block
-            t = __shfl_up_sync(0xffffffffu, o1, 1, G); const double op0 = first ? 0.0 : t;
-            const double n1 = o1 + o0;
-            o0 = o0 + op0;
-            o1 = n1;
-            if (m.c0 >= N) o0 = 0.0;
-            if (m.c0 + 1 >= N) o1 = 0.0;
+            double op[CPL];
+            time_prev<G, CPL>(o, op, m.l);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                o[q] += op[q];
+                if (m.c0 + q >= N) o[q] = 0.0;
+            }
         }
-        const double2 bb = ldg2(b1 + off);
-        o0 -= bb.x;
-        o1 -= bb.y;
-        if (masked) { o0 = 0.0; o1 = 0.0; }
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            o[q] -= bb[q];
+            if (masked) o[q] = 0.0;
+        }
         if (CN) {
-            t2_inv<G>(o0, o1, m.l);
-            if (m.c0 >= N) o0 = 0.0;
-            if (m.c0 + 1 >= N) o1 = 0.0;
+            t2_inv<G, CPL>(o, m.l);
+#pragma unroll
+            for (int q = 0; q < CPL; ++q)
+                if (m.c0 + q >= N) o[q] = 0.0;
         }
     } else {
-        const double2 bb = ldg2(b1 + off);
-        o0 = masked ? 0.0 : bb.x;
-        o1 = masked ? 0.0 : bb.y;
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) o[q] = masked ? 0.0 : bb[q];
     }
     if (!m.live) return;
-    *reinterpret_cast<double2 *>(out + off) = make_double2(o0, o1);
+    store_cols<CPL>(out + off, o);
 }
 
 // rows listed in bc_rows: u[row, :] = wrap_b ? wrap_b[row, :] : 0
@@ -292,25 +357,28 @@ __global__ void panel_ts_to_tf_kernel(const double *__restrict__ src, double *__
     }
 }
 
-inline int blocks_for(int n_rows, int G) { return ceil_div(n_rows, 8 * (32 / G)); }
+inline int blocks_for(int n_rows, int ld) { const int G = ld >= 64 ? 32 : ld / 2; return ceil_div(n_rows, 8 * (32 / G)); }
 
 }  // namespace
 
-#define DISPATCH_G(G, CALL)                                                                \
-    switch (G) {                                                                           \
-    case 4: { constexpr int GG = 4; CALL; } break;                                         \
-    case 8: { constexpr int GG = 8; CALL; } break;                                         \
-    case 16: { constexpr int GG = 16; CALL; } break;                                       \
-    default: { constexpr int GG = 32; CALL; } break;                                       \
+// (lanes per row, columns per lane) for a padded row length ld = G * CPL
+#define DISPATCH_G(LD, CALL)                                                               \
+    switch (LD) {                                                                          \
+    case 8: { constexpr int GG = 4, CC = 2; CALL; } break;                                 \
+    case 16: { constexpr int GG = 8, CC = 2; CALL; } break;                                \
+    case 32: { constexpr int GG = 16, CC = 2; CALL; } break;                               \
+    case 64: { constexpr int GG = 32, CC = 2; CALL; } break;                               \
+    case 128: { constexpr int GG = 32, CC = 4; CALL; } break;                              \
+    default: { constexpr int GG = 32, CC = 8; CALL; } break;                               \
     }
 
 int pcb_u0_first(ctl_handle_s *h, const double *b0, const double *dinv, double *btil, double *p1, double c)
 {
-    const int G = h->ld / 2, nb = blocks_for(h->n_loc, G);
+    const int G = h->ld, nb = blocks_for(h->n_loc, h->ld);
     if (h->cfg.CN) {
-        DISPATCH_G(G, (u0_first_kernel<true, GG><<<nb, 256, 0, h->stream>>>(b0, h->d_bcmask, dinv, btil, p1, c, h->n_loc, h->N, h->ld)));
+        DISPATCH_G(G, (u0_first_kernel<true, GG, CC><<<nb, 256, 0, h->stream>>>(b0, h->d_bcmask, dinv, btil, p1, c, h->n_loc, h->N, h->ld)));
     } else {
-        DISPATCH_G(G, (u0_first_kernel<false, GG><<<nb, 256, 0, h->stream>>>(b0, h->d_bcmask, dinv, btil, p1, c, h->n_loc, h->N, h->ld)));
+        DISPATCH_G(G, (u0_first_kernel<false, GG, CC><<<nb, 256, 0, h->stream>>>(b0, h->d_bcmask, dinv, btil, p1, c, h->n_loc, h->N, h->ld)));
     }
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -320,8 +388,8 @@ int pcb_u0_first(ctl_handle_s *h, const double *b0, const double *dinv, double *
 int pcb_cheb_step(ctl_handle_s *h, const double *dinv, const double *btil, const double *p_prev, const double *p_cur,
                   double *out, double a, double bq, double c)
 {
-    const int G = h->ld / 2, nb = blocks_for(h->n_loc, G);
-    DISPATCH_G(G, (cheb_step_kernel<GG><<<nb, 256, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M, h->d_bcmask, dinv, btil, p_prev,
+    const int G = h->ld, nb = blocks_for(h->n_loc, h->ld);
+    DISPATCH_G(G, (cheb_step_kernel<GG, CC><<<nb, 256, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M, h->d_bcmask, dinv, btil, p_prev,
                                                                  p_cur, h->d_halo, out, a, bq, c, h->n_loc, h->ld)));
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -330,11 +398,11 @@ int pcb_cheb_step(ctl_handle_s *h, const double *dinv, const double *btil, const
 
 int pcb_u0_final(ctl_handle_s *h, const double *p, const double *wrap_b, double *u0, double sc, double sc_last)
 {
-    const int G = h->ld / 2, nb = blocks_for(h->n_loc, G);
+    const int G = h->ld, nb = blocks_for(h->n_loc, h->ld);
     if (h->cfg.CN) {
-        DISPATCH_G(G, (u0_final_kernel<true, GG><<<nb, 256, 0, h->stream>>>(p, h->d_bcmask, wrap_b, u0, sc, sc_last, h->n_loc, h->N, h->ld)));
+        DISPATCH_G(G, (u0_final_kernel<true, GG, CC><<<nb, 256, 0, h->stream>>>(p, h->d_bcmask, wrap_b, u0, sc, sc_last, h->n_loc, h->N, h->ld)));
     } else {
-        DISPATCH_G(G, (u0_final_kernel<false, GG><<<nb, 256, 0, h->stream>>>(p, h->d_bcmask, wrap_b, u0, sc, sc_last, h->n_loc, h->N, h->ld)));
+        DISPATCH_G(G, (u0_final_kernel<false, GG, CC><<<nb, 256, 0, h->stream>>>(p, h->d_bcmask, wrap_b, u0, sc, sc_last, h->n_loc, h->N, h->ld)));
     }
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -343,10 +411,10 @@ int pcb_u0_final(ctl_handle_s *h, const double *p, const double *wrap_b, double 
 
 int pcb_schur_rhs(ctl_handle_s *h, const double *u0, const double *b1, double *out)
 {
-    const int G = h->ld / 2, nb = blocks_for(h->n_loc, G);
+    const int G = h->ld, nb = blocks_for(h->n_loc, h->ld);
     const bool cn = h->cfg.CN != 0, pl = h->per_level;
 #define SR(CNV, PLV)                                                                                                   \
-    DISPATCH_G(G, (schur_rhs_kernel<CNV, PLV, GG><<<nb, 256, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M, h->d_K, h->d_bcmask, \
+    DISPATCH_G(G, (schur_rhs_kernel<CNV, PLV, GG, CC><<<nb, 256, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M, h->d_K, h->d_bcmask, \
                                                                            u0, h->d_halo, b1, out, h->cfg.tau, h->n_loc, h->N, h->ld)))
     if (cn && pl) { SR(true, true); }
     else if (cn) { SR(true, false); }

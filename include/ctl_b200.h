@@ -13,7 +13,8 @@
  *                           doubles, [u_0 blocks | u_1 blocks]
  *                           (preconditioner/preconditioner.py:276-287, 658-704).
  *   CTL_LAYOUT_TIME_FASTEST the library's internal layout: two n x ld row-major panels
- *                           (state part, adjoint part), ld = ctl_ld() >= N, padding
+ *                           (state part, adjoint part), ld = ctl_ld() >= N (power of two,
+ *                           N <= 256), padding
  *                           columns are zero.  Used between library calls to avoid the
  *                           two transposes per call.
  * All `double*` vector arguments are DEVICE pointers unless the name ends in `_host`.

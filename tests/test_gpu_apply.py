@@ -114,7 +114,7 @@ def test_errors_are_reported_not_swallowed():
     from control_b200 import CtlError
     M, K, _, bd = fem.assemble_p1_2d(3, 3)
     with pytest.raises(CtlError):
-        _system(M, K, n_t=200, beta=1e-2, CN=True, bc_dofs=bd)      # more than 64 blocks
+        _system(M, K, n_t=300, beta=1e-2, CN=True, bc_dofs=bd)      # more than 256 blocks
     K2 = K.copy()
     K2.eliminate_zeros()
     if K2.nnz != M.nnz:
@@ -136,3 +136,19 @@ def test_tma_staged_apply_matches_literal_operator(tile_rows, monkeypatch):
     _check_apply(M, K2, 20, True, bd)                      # non-symmetric K
     M3, K3, _, bd3 = fem.assemble_p1_3d(6, 5, 4)
     _check_apply(M3, K3, 9, True, bd3)
+
+
+@pytest.mark.parametrize("CN", [True, False])
+@pytest.mark.parametrize("n_t", [66, 100, 129, 200, 256])
+def test_apply_more_than_64_time_blocks(CN, n_t):
+    """Wide kernels: every lane owns 4 (ld = 128) or 8 (ld = 256) consecutive time columns."""
+    M, K, _, bd = fem.assemble_p1_2d(6, 5, 2.0, 1.0)
+    _check_apply(M, K, n_t, CN, bd, tau_interval=(0.0, 2.0), seed=n_t)
+    if n_t == 100:
+        rng = np.random.default_rng(2)
+        Ks = []
+        for _ in range(n_t):
+            Ki = K.copy()
+            Ki.data = Ki.data * (1.0 + 0.2 * rng.standard_normal(Ki.nnz))
+            Ks.append(Ki)
+        _check_apply(M, Ks, n_t, CN, bd)

@@ -303,3 +303,31 @@ def test_accelerated_amg_solve_matches_oracle():
     g0, g1 = s.to_host_blocks(s.pc_apply(s.to_device(b0, b1), raw=True))
     assert _rel(g0, r0) < 1e-11 and _rel(g1, r1) < 1e-11
     s.close()
+
+
+@pytest.mark.parametrize("CN,n_t", [(True, 81), (False, 70), (True, 140)])
+def test_many_time_blocks_pc_and_solve(CN, n_t):
+    """N > 64: batched preconditioner kernels with 4 / 8 columns per lane, full solve."""
+    q = kat.heat_problem(9, n_t, CN, beta=1e-2)
+    s = _system(q, CN)
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"])
+    pc = _oracle_pc(q, CN, lambda_v_bounds=q["lambda_v_bounds"])
+    rng = np.random.default_rng(4)
+    b0 = rng.standard_normal((s.N, s.n))
+    b1 = rng.standard_normal((s.N, s.n))
+    b0[:, q["bdofs"]] = 0.0
+    b1[:, q["bdofs"]] = 0.0
+    r0, r1 = pc(b0, b1)
+    g0, g1 = s.to_host_blocks(s.pc_apply(s.to_device(b0, b1), raw=True))
+    assert _rel(g0, r0) < 1e-10 and _rel(g1, r1) < 1e-10
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-6,
+           "absolute_tolerance": 0.0, "gmres_restart": 100}
+    ref = ocontrol.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=n_t, CN=CN, time_interval=q["time_interval"],
+                                bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], lambda_v_bounds=q["lambda_v_bounds"],
+                                solver_parameters=sp_)
+    u0 = np.zeros((s.N, s.n))
+    u1 = np.zeros((s.N, s.n))
+    info = s.solve(u0, u1, ref["b_0"], ref["b_1"], solver_parameters=sp_, pc_fn="builtin")
+    assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1
+    assert _rel(u0, ref["v_blocks"]) < 1e-4
+    s.close()
