@@ -37,7 +37,7 @@ except Exception:                          # pragma: no cover
 
 
 DEFAULTS = dict(theta=0.08, max_levels=10, coarse_max=600, nu=3, lo=0.25, hi=1.0, cycles=4,
-                acc_lo=0.0, acc_hi=1.0)
+                acc_lo=0.0, acc_hi=1.0, dense_coarse=True)
 
 
 @_jit
@@ -173,7 +173,9 @@ def setup(A, **kw):
         A = (L.R @ (A @ P)).tocsr()
         A.sort_indices()
     last = levels[-1]
-    if last.A.shape[0] <= 4096:
+    # dense_coarse=False: the coarsest level is only smoothed (singular operators such as the
+    # Neumann pressure Laplacian of the Stokes preconditioner have no inverse)
+    if last.A.shape[0] <= 4096 and params["dense_coarse"]:
         last.Ainv = np.linalg.inv(last.A.toarray())
     return Hierarchy(levels, params)
 

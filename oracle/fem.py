@@ -212,3 +212,91 @@ def nonlinear_diffusion_p1_2d(nx, ny, lx=1.0, ly=1.0):
         return _csr_same_pattern(n, rows, cols, [Ke.ravel()])[0]
 
     return D_v
+
+
+def assemble_taylor_hood_2d(nx, ny, lx=1.0, ly=1.0):
+    """Taylor-Hood P2 (vector) - P1 on the triangle mesh of ``p1_triangle_mesh``: the spaces of
+    the reference's Stokes control tests (``space_v`` = VectorFunctionSpace P2, ``space_p`` = P1,
+    test/test_control.py:3045-3172; BASELINE config C4).  P2 nodes are the points of the
+    (2nx+1) x (2ny+1) lattice, velocity dofs are interleaved by component (dof = 2 node + comp,
+    Firedrake's block size 2).  Returns a dict with M_v, K_v (vector mass / vector Laplacian),
+    B (n_p x n_v, ``-inner(div(trial_v), test_p) * dx``, control/control.py:3708), M_p, K_p, the
+    velocity boundary dofs and the node coordinates."""
+    mx, my = 2 * nx + 1, 2 * ny + 1
+    i, j = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    i, j = i.ravel(), j.ravel()
+
+    def node(a, b):                      # lattice point (2i + a, 2j + b)
+        return (2 * j + b) * mx + (2 * i + a)
+
+    def vert(a, b):                      # P1 vertex (i + a, j + b)
+        return (j + b) * (nx + 1) + (i + a)
+    # lower-left triangles (v00, v10, v01) and upper-right ones (v10, v11, v01); local order:
+    # vertices 0,1,2 then midpoints of edges (1,2), (0,2), (0,1)
+    t2 = np.concatenate([
+        np.stack([node(0, 0), node(2, 0), node(0, 2), node(1, 1), node(0, 1), node(1, 0)], axis=1),
+        np.stack([node(2, 0), node(2, 2), node(0, 2), node(1, 2), node(1, 1), node(2, 1)], axis=1)], axis=0)
+    t1 = np.concatenate([np.stack([vert(0, 0), vert(1, 0), vert(0, 1)], axis=1),
+                         np.stack([vert(1, 0), vert(1, 1), vert(0, 1)], axis=1)], axis=0)
+    xs = np.linspace(0.0, lx, mx)
+    ys = np.linspace(0.0, ly, my)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords2 = np.stack([X.ravel(), Y.ravel()], axis=1)
+    p = coords2[t2[:, :3]]
+    e1 = p[:, 1] - p[:, 0]
+    e2 = p[:, 2] - p[:, 0]
+    det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.abs(det)
+    g = np.empty((t2.shape[0], 3, 2))    # gradients of the barycentric coordinates
+    g[:, 1, 0] = e2[:, 1] / det
+    g[:, 1, 1] = -e2[:, 0] / det
+    g[:, 2, 0] = -e1[:, 1] / det
+    g[:, 2, 1] = e1[:, 0] / det
+    g[:, 0] = -g[:, 1] - g[:, 2]
+    # degree-4 quadrature on the reference triangle (6 points), barycentric coordinates
+    a1, a2 = 0.445948490915965, 0.091576213509771
+    w1, w2 = 0.223381589678011, 0.109951743655322
+    lam = np.array([[1 - 2 * a1, a1, a1], [a1, 1 - 2 * a1, a1], [a1, a1, 1 - 2 * a1],
+                    [1 - 2 * a2, a2, a2], [a2, 1 - 2 * a2, a2], [a2, a2, 1 - 2 * a2]])
+    wq = np.array([w1, w1, w1, w2, w2, w2])
+    nq = lam.shape[0]
+    phi = np.empty((nq, 6))              # P2 basis at the quadrature points
+    dphi = np.empty((nq, 6, 3))          # d phi / d lambda_k
+    for q in range(nq):
+        l0, l1, l2 = lam[q]
+        phi[q] = [l0 * (2 * l0 - 1), l1 * (2 * l1 - 1), l2 * (2 * l2 - 1), 4 * l1 * l2, 4 * l0 * l2, 4 * l0 * l1]
+        dphi[q] = [[4 * l0 - 1, 0, 0], [0, 4 * l1 - 1, 0], [0, 0, 4 * l2 - 1],
+                   [0, 4 * l2, 4 * l1], [4 * l2, 0, 4 * l0], [4 * l1, 4 * l0, 0]]
+    grad = np.einsum("qak,tkd->tqad", dphi, g)                   # (nt, nq, 6, 2) physical gradients
+    Ms = np.einsum("q,qa,qb->ab", wq, phi, phi)[None] * area[:, None, None]
+    Ks = np.einsum("q,tqad,tqbd->tab", wq, grad, grad) * area[:, None, None]
+    # B[p, (a, d)] = - int psi_p d phi_a / d x_d
+    Bs = -np.einsum("q,qp,tqad->tpad", wq, lam, grad) * area[:, None, None, None]
+    n2 = mx * my
+    n1 = (nx + 1) * (ny + 1)
+    rows = np.repeat(t2, 6, axis=1).ravel()
+    cols = np.tile(t2, (1, 6)).ravel()
+    Msc, Ksc = _csr_same_pattern(n2, rows, cols, [np.broadcast_to(Ms, Ks.shape).ravel(), Ks.ravel()])
+    eye2 = sp.identity(2, format="csr")
+    M_v = sp.kron(Msc, eye2, format="csr")
+    K_v = sp.kron(Ksc, eye2, format="csr")
+    # keep the shared pattern exactly (kron of explicit zeros keeps them)
+    for A in (M_v, K_v):
+        A.sort_indices()
+        A.indices = A.indices.astype(np.int32)
+        A.indptr = A.indptr.astype(np.int32)
+    M_v = sp.csr_matrix((M_v.data, M_v.indices, M_v.indptr), shape=M_v.shape)
+    K_v = sp.csr_matrix((K_v.data, K_v.indices, K_v.indptr), shape=K_v.shape)
+    brow = np.repeat(t1[:, :, None, None], 6, axis=2).repeat(2, axis=3)
+    bcol = 2 * t2[:, None, :, None] + np.arange(2)[None, None, None, :]
+    bcol = np.broadcast_to(bcol, brow.shape)
+    B = sp.coo_matrix((Bs.ravel(), (brow.ravel(), bcol.ravel())), shape=(n1, 2 * n2)).tocsr()
+    B.sort_indices()
+    B = sp.csr_matrix((B.data, B.indices.astype(np.int32), B.indptr.astype(np.int32)), shape=B.shape)
+    M_p, K_p, coords1, _ = assemble_p1_2d(nx, ny, lx, ly)
+    x, y = coords2[:, 0], coords2[:, 1]
+    tol = 1e-12 * max(lx, ly)
+    bn = np.flatnonzero((x < tol) | (x > lx - tol) | (y < tol) | (y > ly - tol))
+    bd_v = np.sort(np.concatenate([2 * bn, 2 * bn + 1])).astype(np.int32)
+    return dict(M_v=M_v, K_v=K_v, B=B, M_p=M_p, K_p=K_p, bdofs_v=bd_v, coords_v=coords2, coords_p=coords1,
+                M_scalar=Msc, K_scalar=Ksc)

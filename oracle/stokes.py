@@ -1,0 +1,252 @@
+"""Instationary Stokes control: ``Control.Instationary.incompressible_linear_solve`` restated
+on assembled matrices (oracle; test infrastructure only).
+
+  * block structure and outer operator   control/control.py:3750-3957, 4273-4289 and
+    ``MultiBlockSystemMatrix.mult`` with sub-block T transforms,
+    preconditioner/preconditioner.py:375-543 (471-525 for the ``sub_n_blocks`` branch)
+  * ``ConstantNullspace``                preconditioner/preconditioner.py:133-155
+  * in-built pressure-Schur preconditioner  control/control.py:4299-4513 (CN), 4515-4687 (BE)
+  * solve driver                         control/control.py:4273-4297, 4688-4725
+
+Unknowns: ``x_0`` = (2N, n_v) blocks [v | zeta], ``x_1`` = (2N, n_p) blocks [mu | p] (the first
+N pressure blocks multiply B^T in the adjoint-equation rows, control/control.py:3765-3766).
+The inner solves on ``K_p`` are one AMG cycle of the stand-in AMG (hypre BoomerAMG x1 in the
+reference, control/control.py:4300-4309): parity with hypre is unpinned, as for the heat path.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import amg as _amg
+from . import kkt, krylov
+from .cheb import chebyshev
+from .control import system_solve
+from .pc import construct_pc
+
+
+class ConstantNullspace:
+    """preconditioner/preconditioner.py:133-155 (alpha = 1)."""
+
+    def __init__(self, alpha=1.0):
+        self.alpha = alpha
+
+    @staticmethod
+    def _mean(x):
+        return x.sum(axis=-1, keepdims=True) / float(x.shape[-1])
+
+    def project(self, x):
+        x -= self._mean(x)
+
+    def pre_mult_corrected_lhs(self, x):
+        xc = x.copy()
+        self.project(xc)
+        return xc
+
+    def post_mult_correct_lhs(self, x, y):
+        self.project(y)
+        y += self.alpha * self._mean(x)
+
+    def pc_pre_mult_corrected(self, b):
+        bc = b.copy()
+        self.project(bc)
+        return bc
+
+    def pc_post_mult_correct(self, u, b):
+        self.project(u)
+        u += self._mean(b)
+
+
+def _T(y, N, first, second):
+    y[:N] = first(y[:N])
+    y[N:] = second(y[N:])
+
+
+def stokes_apply_literal(heat_blocks, B, tau, N, CN, ns_v, ns_p, x0, x1):
+    """``mult`` of the outer system, block by block."""
+    b00, b01, b10, b11 = heat_blocks
+    xc0 = ns_v.pre_mult_corrected_lhs(x0)
+    xc1 = ns_p.pre_mult_corrected_lhs(x1)
+    y0 = np.zeros_like(x0)
+    y1 = np.zeros_like(x1)
+    for (i, j), A in b00.items():              # block_00 = the heat-type KKT with index offsets
+        if A is not None:
+            y0[i] += A @ xc0[j]
+    for (i, j), A in b01.items():
+        if A is not None:
+            y0[i] += A @ xc0[N + j]
+    for (i, j), A in b10.items():
+        if A is not None:
+            y0[N + i] += A @ xc0[j]
+    for (i, j), A in b11.items():
+        if A is not None:
+            y0[N + i] += A @ xc0[N + j]
+    for i in range(2 * N):                     # block_01 = diag(tau B^T), block_10 = diag(tau B)
+        y0[i] += tau * (B.T @ xc1[i])
+        y1[i] += tau * (B @ xc0[i])
+    if CN:                                     # preconditioner.py:471-525
+        _T(y0, N, kkt.apply_T_1, kkt.apply_T_2)
+        _T(y1, N, kkt.apply_T_2, kkt.apply_T_1)
+    ns_v.post_mult_correct_lhs(x0, y0)
+    ns_p.post_mult_correct_lhs(x1, y1)
+    return y0, y1
+
+
+def stokes_apply_fused(M_v, K_v, B, tau, beta, n_t, CN, bdofs_v, x0, x1):
+    """The same operator in the form the CUDA library implements: the fused heat-type KKT apply
+    on the velocity blocks plus the (transformed) divergence couplings."""
+    N = kkt.n_blocks(n_t, CN)
+    ns_p = ConstantNullspace()
+    xc0 = x0.copy()
+    xc0[:, bdofs_v] = 0.0
+    xc1 = ns_p.pre_mult_corrected_lhs(x1)
+    y0a, y0b = kkt.kkt_apply_fused(M_v, K_v, tau, beta, n_t, CN, bdofs_v, x0[:N], x0[N:])
+    g0 = tau * (B.T @ xc1.T).T                 # tau B^T x_1, block by block
+    y1 = tau * (B @ xc0.T).T
+    if CN:
+        _T(g0, N, kkt.apply_T_1, kkt.apply_T_2)
+        _T(y1, N, kkt.apply_T_2, kkt.apply_T_1)
+    g0[:, bdofs_v] = 0.0
+    y0 = np.concatenate([y0a, y0b]) + g0
+    ns_p.post_mult_correct_lhs(x1, y1)
+    return y0, y1
+
+
+def make_solver_p(M_p, K_p, lambda_p_bounds, amg_params=None):
+    """``solver_K_p`` (one AMG cycle on the Neumann Laplacian, control/control.py:4300-4309) and
+    ``solver_M_p`` (Chebyshev-20/Jacobi or one Jacobi sweep, 4311-4333), acting on (k, n_p)."""
+    params = dict(cycles=1, dense_coarse=False)
+    params.update(amg_params or {})
+    H = _amg.setup(K_p, **params)
+    dinv = 1.0 / M_p.diagonal()
+
+    def K_solve(Bk):
+        return np.stack([_amg.solve(H, b) for b in Bk])
+
+    if lambda_p_bounds is not None:
+        e_min, e_max = lambda_p_bounds
+
+        def M_solve(Bk):
+            return chebyshev(M_p, dinv, Bk.T, e_min, e_max, 20).T
+    else:
+        def M_solve(Bk):
+            return Bk * dinv[None, :]
+    return K_solve, M_solve, H
+
+
+def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, lambda_v_bounds=None,
+                        lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None, epsilon=1e-3):
+    """``pc_fn(b_0, b_1) -> (u_0, u_1)`` of control/control.py:4337-4513 (CN) / 4515-4687 (BE)."""
+    N = kkt.n_blocks(n_t, CN)
+    ns_v = kkt.DirichletBCNullspace(bdofs_v)
+    heat_pc = construct_pc(M_v, K_v, tau, beta, n_t, CN, bdofs_v, lambda_v_bounds=lambda_v_bounds,
+                           inner=inner, amg_params=amg_params, epsilon=epsilon)
+    K_solve, M_solve, _ = make_solver_p(M_p, K_p, lambda_p_bounds, amg_params_p)
+    pblocks = kkt.build_blocks(M_p, K_p, tau, beta, n_t, CN)       # block_*_int_p, 3805-3957
+    inner_parameters = {"preconditioner": True, "linear_solver": "gmres", "maximum_iterations": 5,
+                        "relative_tolerance": 0.0, "absolute_tolerance": 0.0}      # 4355-4361
+
+    def apply_heat(x0, x1):
+        return kkt.kkt_apply_fused(M_v, K_v, tau, beta, n_t, CN, bdofs_v, x0, x1)
+
+    def pc_fn(b_0, b_1):
+        n_v, n_p = M_v.shape[0], M_p.shape[0]
+        v, zeta, _ = system_solve(apply_heat, ns_v, np.zeros((N, n_v)), np.zeros((N, n_v)), b_0[:N], b_0[N:],
+                                  solver_parameters=inner_parameters, pc_fn=heat_pc)
+        u_0 = np.concatenate([v, zeta])
+        # u_1 = -b_1 + block_10 u_0, then the pressure Schur-complement approximation
+        h0 = tau * (B @ u_0[:N].T).T
+        h1 = tau * (B @ u_0[N:].T).T
+        if CN:
+            h0 = kkt.apply_T_2(h0)
+            h1 = kkt.apply_T_1(h1)
+        h0 -= b_1[:N]
+        h1 -= b_1[N:]
+        h0 *= 1.0 / tau ** 2
+        h1 *= 1.0 / tau ** 2
+        if CN:
+            h0 = kkt.apply_T_2_inv(h0)
+            h1 = kkt.apply_T_1_inv(h1)
+        u_p = K_solve(h0)
+        u_m = K_solve(h1)
+        p00, p01, p10, p11 = pblocks
+        c0 = np.zeros((N, n_p))
+        c1 = np.zeros((N, n_p))
+        for (i, j), A in p00.items():
+            if A is not None:
+                c0[i] += A @ u_p[j]
+        for (i, j), A in p01.items():
+            if A is not None:
+                c0[i] += A @ u_m[j]
+        for (i, j), A in p10.items():
+            if A is not None:
+                c1[i] += A @ u_p[j]
+        for (i, j), A in p11.items():
+            if A is not None:
+                c1[i] += A @ u_m[j]
+        u_1 = np.concatenate([M_solve(c0), M_solve(c1)])
+        return u_0, u_1
+
+    return pc_fn
+
+
+class _PairNullspace:
+    """Velocity blocks: Dirichlet; pressure blocks: constant (full_nullspace_0 / _1, 3628-3652)."""
+
+    def __init__(self, bdofs_v):
+        self.v = kkt.DirichletBCNullspace(bdofs_v)
+        self.p = ConstantNullspace()
+
+
+def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, b_0, b_1,
+                 solver_parameters=None, lambda_v_bounds=None, lambda_p_bounds=None, inner="amg",
+                 amg_params=None, amg_params_p=None, pc_fn=None):
+    """``MultiBlockSystem.solve`` of the outer Stokes system from a zero initial guess
+    (control/control.py:4273-4297, 4688-4693).  ``b_0`` (2N, n_v), ``b_1`` (2N, n_p) are the
+    final right-hand sides (T transforms already applied).  Returns (u_0, u_1, KSPResult)."""
+    t_0, T_f = time_interval
+    tau = (T_f - t_0) / (n_t - 1.0)
+    N = kkt.n_blocks(n_t, CN)
+    n_v, n_p = M_v.shape[0], M_p.shape[0]
+    ns = _PairNullspace(bdofs_v)
+    if pc_fn is None:
+        pc_fn = construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v,
+                                    lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds,
+                                    inner=inner, amg_params=amg_params, amg_params_p=amg_params_p)
+    if solver_parameters is None:                                # control/control.py:4291-4297
+        solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 100,
+                             "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0}
+    sp_ = solver_parameters
+    L0, L1 = 2 * N * n_v, 2 * N * n_p
+
+    def unpack(x):
+        return x[:L0].reshape(2 * N, n_v).copy(), x[L0:].reshape(2 * N, n_p).copy()
+
+    def pack(a0, a1):
+        return np.concatenate([a0.ravel(), a1.ravel()])
+
+    def A(x):
+        x0, x1 = unpack(x)
+        return pack(*stokes_apply_fused(M_v, K_v, B, tau, beta, n_t, CN, bdofs_v, x0, x1))
+
+    def P(x):                                                     # Preconditioner.apply, 562-656
+        c0, c1 = unpack(x)
+        d0 = ns.v.pc_pre_mult_corrected(c0)
+        d1 = ns.p.pc_pre_mult_corrected(c1)
+        w0, w1 = pc_fn(d0, d1)
+        w0, w1 = w0.copy(), w1.copy()
+        ns.v.pc_post_mult_correct(w0, c0)
+        ns.p.pc_post_mult_correct(w1, c1)
+        return pack(w0, w1)
+
+    c0, c1 = b_0.copy(), b_1.copy()
+    ns.v.project(c0)
+    ns.p.project(c1)
+    kw = dict(rtol=sp_["relative_tolerance"], atol=sp_["absolute_tolerance"], max_it=sp_.get("maximum_iterations", 1000))
+    ksp_type = sp_.get("linear_solver", "fgmres")
+    x, res = krylov.gmres(A, pack(c0, c1), np.zeros(L0 + L1), pc=P, flexible=(ksp_type == "fgmres"),
+                          restart=sp_.get("gmres_restart", 30), **kw)
+    u0, u1 = unpack(x)
+    ns.v.project(u0)
+    ns.p.project(u1)
+    if not sp_.get("preconditioner", False) and res.reason <= 0:
+        raise RuntimeError("Solver failed to converge")
+    return u0, u1, res

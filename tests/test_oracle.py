@@ -308,3 +308,60 @@ def test_non_linear_loop_picard_contracts_and_residual_is_consistent():
                                bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], solver_parameters=sp_,
                                lambda_v_bounds=q["lambda_v_bounds"], inner="exact")
     assert np.abs(lin["v"] - ref["v"]).max() < 1e-8 * np.abs(ref["v"]).max()
+
+
+def test_stokes_operator_literal_equals_fused_and_is_symmetric():
+    """Outer Stokes system (control/control.py:3750-3957, 4273-4289) with the sub-block T
+    transforms of preconditioner.py:471-525 and ConstantNullspace on the pressure blocks."""
+    from oracle import stokes
+    th = fem.assemble_taylor_hood_2d(4, 3, 1.0, 1.0)
+    Mv, Kv, B, Mp, bd = th["M_v"], th["K_v"], th["B"], th["M_p"], th["bdofs_v"]
+    n_v, n_p = Mv.shape[0], Mp.shape[0]
+    for CN in (True, False):
+        n_t, tau, beta = 4, 1.0 / 3.0, 1e-2
+        N = kkt.n_blocks(n_t, CN)
+        rng = np.random.default_rng(0)
+        x0 = rng.standard_normal((2 * N, n_v))
+        x1 = rng.standard_normal((2 * N, n_p))
+        hb = kkt.build_blocks(Mv, Kv, tau, beta, n_t, CN)
+        yl = stokes.stokes_apply_literal(hb, B, tau, N, CN, kkt.DirichletBCNullspace(bd),
+                                         stokes.ConstantNullspace(), x0, x1)
+        yf = stokes.stokes_apply_fused(Mv, Kv, B, tau, beta, n_t, CN, bd, x0, x1)
+        sc = max(np.abs(yl[0]).max(), np.abs(yl[1]).max())
+        assert np.abs(yl[0] - yf[0]).max() < 1e-14 * sc and np.abs(yl[1] - yf[1]).max() < 1e-14 * sc
+        # symmetric on the constrained subspace (zero velocity bcs, mean-free pressure blocks)
+        def proj(a0, a1):
+            a0 = a0.copy(); a1 = a1.copy()
+            a0[:, bd] = 0.0
+            a1 -= a1.mean(axis=1, keepdims=True)
+            return a0, a1
+        u = proj(x0, x1)
+        w = proj(rng.standard_normal((2 * N, n_v)), rng.standard_normal((2 * N, n_p)))
+        Au = stokes.stokes_apply_fused(Mv, Kv, B, tau, beta, n_t, CN, bd, *u)
+        Aw = stokes.stokes_apply_fused(Mv, Kv, B, tau, beta, n_t, CN, bd, *w)
+        lhs = (Au[0] * w[0]).sum() + (Au[1] * w[1]).sum()
+        rhs = (u[0] * Aw[0]).sum() + (u[1] * Aw[1]).sum()
+        assert abs(lhs - rhs) < 1e-11 * abs(lhs)
+
+
+def test_stokes_solve_recovers_manufactured_solution():
+    from oracle import stokes
+    th = fem.assemble_taylor_hood_2d(5, 5, 1.0, 1.0)
+    Mv, Kv, B, Mp, Kp, bd = th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], th["bdofs_v"]
+    n_t, beta, CN = 4, 1e-2, True
+    N = n_t - 1
+    rng = np.random.default_rng(1)
+    xr0 = rng.standard_normal((2 * N, Mv.shape[0]))
+    xr0[:, bd] = 0.0
+    xr1 = rng.standard_normal((2 * N, Mp.shape[0]))
+    xr1 -= xr1.mean(axis=1, keepdims=True)
+    tau = 1.0 / (n_t - 1)
+    b0, b1 = stokes.stokes_apply_fused(Mv, Kv, B, tau, beta, n_t, CN, bd, xr0, xr1)
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-10,
+           "absolute_tolerance": 0.0, "gmres_restart": 100}
+    u0, u1, res = stokes.stokes_solve(Mv, Kv, B, Mp, Kp, beta=beta, n_t=n_t, CN=CN, bdofs_v=bd, b_0=b0, b_1=b1,
+                                      solver_parameters=sp_, lambda_v_bounds=(0.3924, 2.0598),
+                                      lambda_p_bounds=(0.5, 2.0), inner="exact")
+    assert res.reason > 0
+    assert np.abs(u0 - xr0).max() < 1e-6 * np.abs(xr0).max()
+    assert np.abs(u1 - xr1).max() < 1e-4 * np.abs(xr1).max()
