@@ -48,6 +48,14 @@ class ctl_solve_result(C.Structure):
                 ("seconds_pc", C.c_double)]
 
 
+class ctl_stokes_pc_options(C.Structure):
+    _fields_ = [("velocity", ctl_pc_options), ("inner_its", C.c_int32), ("mass_p", C.c_int32),
+                ("mass_p_steps", C.c_int32), ("lambda_p_min", C.c_double), ("lambda_p_max", C.c_double),
+                ("amg_p_nu", C.c_int32), ("amg_p_max_levels", C.c_int32),
+                ("amg_p_coarse_max", C.c_int32), ("amg_p_cycles", C.c_int32),
+                ("amg_p_theta", C.c_double), ("amg_p_lo", C.c_double), ("amg_p_hi", C.c_double)]
+
+
 PC_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
 
 _H = C.c_void_p
@@ -91,6 +99,16 @@ SIGNATURES = {
                                   C.c_void_p]),
     "ctl_amg_get_aggregates": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p]),
     "ctl_amg_solve": (C.c_int, [_H, C.c_int32, _F64P, _F64P]),
+    "ctl_stokes_create": (C.c_int, [_H, _H, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_H)]),
+    "ctl_stokes_destroy": (C.c_int, [_H]),
+    "ctl_stokes_vec_len": (C.c_int64, [_H]),
+    "ctl_stokes_apply": (C.c_int, [_H, _F64P, _F64P]),
+    "ctl_stokes_pc_default_options": (C.c_int, [C.POINTER(ctl_stokes_pc_options)]),
+    "ctl_stokes_pc_setup": (C.c_int, [_H, C.POINTER(ctl_stokes_pc_options)]),
+    "ctl_stokes_pc_apply": (C.c_int, [_H, _F64P, _F64P]),
+    "ctl_stokes_pc_fn": (C.c_int, [_H, _F64P, _F64P]),
+    "ctl_stokes_solve": (C.c_int, [_H, _F64P, _F64P, C.POINTER(ctl_krylov_options),
+                                   C.POINTER(ctl_solve_result)]),
     "ctl_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ctl_comm_init": (C.c_int, [_H, C.c_void_p]),
     "ctl_kernel_launches": (C.c_int64, [_H]),

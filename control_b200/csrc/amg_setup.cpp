@@ -244,5 +244,5 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         A = std::move(Ac);
     }
     AmgLevelHost &last = levels.back();
-    if (last.A.n_rows <= 4096) dense_inverse(last.A, last.Ainv);
+    if (last.A.n_rows <= 4096 && p.dense_coarse) dense_inverse(last.A, last.Ainv);
 }

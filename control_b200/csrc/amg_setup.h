@@ -14,6 +14,7 @@ struct AmgParams {
     double lo = 0.25, hi = 1.0;
     int cycles = 4;      // see oracle/amg.py::solve for why not the reference's 2
     double acc_lo = 0.0, acc_hi = 1.0;   // > 0: Chebyshev-accelerated cycles (oracle/amg.py::solve)
+    bool dense_coarse = true;            // false: the coarsest level is only smoothed (singular operators)
 };
 
 struct AmgLevelHost {

@@ -124,6 +124,9 @@ int ctl_to_bm(ctl_handle_s *h, const double *src_tf, double *dst_bm);
 int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf);
 // pc.cu: Preconditioner.apply on time-fastest vectors
 int ctl_pc_apply_tf(ctl_handle_s *h, const double *b_tf, double *u_tf);
+// krylov.cu: MultiBlockSystem.solve on time-fastest vectors (u: initial guess in, solution out)
+int ctl_solve_tf(ctl_handle_s *h, const double *b_tf, double *u_tf, const ctl_krylov_options *opts,
+                 ctl_solve_result *result);
 
 // unit-private state teardown / invalidation
 void ctl_pc_free(ctl_handle_s *h);        // pc.cu

@@ -1,0 +1,160 @@
+"""Host-side mirror of the outer block system of instationary Stokes control.
+
+``StokesSystem`` plays the role of the ``MultiBlockSystem`` the reference builds in
+``Control.Instationary.incompressible_linear_solve`` (control/control.py:3592-4725, system
+construction at 4273-4289): block_00 = the heat-type KKT system on the velocity space,
+block_01 / block_10 = diag(tau B^T) / diag(tau B), block_11 = None, with sub-block T
+transforms (preconditioner/preconditioner.py:471-525), DirichletBCNullspace on the velocity
+blocks and ConstantNullspace on the pressure blocks.  It is constructed from the five
+spatial matrices the blocks are made of; every numeric operation runs in libctl_b200.so.
+
+Vectors at this boundary are block-major: ``x_0`` of shape (2N, n_v) = [v | zeta] and ``x_1``
+of shape (2N, n_p) = [mu | p], or one flat device vector [x_0 | x_1].
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .system import KSPInfo, MultiBlockSystem, _as_host_f64, csr_arrays
+
+__all__ = ["StokesSystem"]
+
+
+class StokesSystem:
+    def __init__(self, M_v, K_v, B, M_p, K_p, *, n_t, beta, CN, time_interval=(0.0, 1.0), bc_dofs_v=(),
+                 epsilon=1e-3, device=None):
+        self.velocity = MultiBlockSystem(M_v, K_v, n_t=n_t, beta=beta, CN=CN, time_interval=time_interval,
+                                         bc_dofs=bc_dofs_v, epsilon=epsilon, device=device)
+        self.pressure = MultiBlockSystem(M_p, K_p, n_t=n_t, beta=beta, CN=CN, time_interval=time_interval,
+                                         bc_dofs=(), epsilon=epsilon, device=self.velocity.device.index,
+                                         stream=self.velocity.stream)
+        self._lib = self.velocity._lib
+        self.device = self.velocity.device
+        self.N = self.velocity.N
+        self.n_v, self.n_p = self.velocity.n, self.pressure.n
+        self.tau = self.velocity.tau
+        indptr, indices, data = csr_arrays(B)
+        if indptr.size != self.n_p + 1 or (indices.size and int(indices.max()) >= self.n_v):
+            raise ValueError("B must be the n_p x n_v divergence matrix")
+        self._s = C.c_void_p()
+        self.velocity._check(self._lib.ctl_stokes_create(self.velocity._h, self.pressure._h, indptr.ctypes.data,
+                                                         indices.ctypes.data, data.ctypes.data, C.byref(self._s)))
+        self._pc_ready = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _call(self, fn, *args):
+        cur = torch.cuda.current_stream(self.device)
+        self.velocity.stream.wait_stream(cur)
+        rc = fn(self._s, *args)
+        cur.wait_stream(self.velocity.stream)
+        self.velocity._check(rc)
+
+    def close(self):
+        if getattr(self, "_s", None) is not None and self._s:
+            self._lib.ctl_stokes_destroy(self._s)
+            self._s = C.c_void_p()
+        for name in ("pressure", "velocity"):
+            sysm = getattr(self, name, None)
+            if sysm is not None:
+                sysm.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def vec_len(self):
+        return int(self._lib.ctl_stokes_vec_len(self._s))
+
+    def kernel_launches(self):
+        return int(self._lib.ctl_kernel_launches(self.velocity._h)) + int(self._lib.ctl_kernel_launches(self.pressure._h))
+
+    def to_device(self, x_0, x_1):
+        host = np.concatenate([np.asarray(_as_host_f64(x_0), dtype=np.float64).ravel(),
+                               np.asarray(_as_host_f64(x_1), dtype=np.float64).ravel()])
+        if host.size != self.vec_len():
+            raise ValueError(f"vector has {host.size} entries, expected {self.vec_len()}")
+        return torch.from_numpy(host).to(self.device)
+
+    def to_host_blocks(self, x_dev):
+        a = x_dev.detach().cpu().numpy()
+        L0 = 2 * self.N * self.n_v
+        return a[:L0].reshape(2 * self.N, self.n_v), a[L0:].reshape(2 * self.N, self.n_p)
+
+    # ------------------------------------------------------------------ operator / preconditioner
+    def apply(self, x_dev, y_dev=None):
+        """y = A x (MultiBlockSystemMatrix.mult, preconditioner/preconditioner.py:375-543)."""
+        if y_dev is None:
+            y_dev = torch.empty_like(x_dev)
+        self._call(self._lib.ctl_stokes_apply, x_dev.data_ptr(), y_dev.data_ptr())
+        return y_dev
+
+    def setup_preconditioner(self, *, lambda_v_bounds=None, lambda_p_bounds=None, inner_its=5, mass_p_steps=20,
+                             amg=None, amg_p=None):
+        """The in-built pressure-Schur preconditioner (control/control.py:4299-4687).  ``amg`` /
+        ``amg_p``: parameters of the AMG stand-in for the velocity sweeps / the K_p solves."""
+        o = L.ctl_stokes_pc_options()
+        self.velocity._check(self._lib.ctl_stokes_pc_default_options(C.byref(o)))
+        if lambda_v_bounds is not None:
+            o.velocity.solver_0 = L.CTL_S0_CHEBYSHEV
+            o.velocity.cheb_emin, o.velocity.cheb_emax = float(lambda_v_bounds[0]), float(lambda_v_bounds[1])
+        if lambda_p_bounds is not None:
+            o.mass_p = L.CTL_S0_CHEBYSHEV
+            o.lambda_p_min, o.lambda_p_max = float(lambda_p_bounds[0]), float(lambda_p_bounds[1])
+        o.inner_its = int(inner_its)
+        o.mass_p_steps = int(mass_p_steps)
+        names = (("cycles", "cycles"), ("nu", "nu"), ("max_levels", "max_levels"), ("coarse_max", "coarse_max"),
+                 ("theta", "theta"), ("lo", "lo"), ("hi", "hi"))
+        amg = dict(amg or {})
+        for key, field in names + (("acc_lo", "acc_lo"), ("acc_hi", "acc_hi")):
+            if key in amg:
+                setattr(o.velocity, "amg_" + field, amg.pop(key))
+        amg_p = dict(amg_p or {})
+        for key, field in names:
+            if key in amg_p:
+                setattr(o, "amg_p_" + field, amg_p.pop(key))
+        if amg or amg_p:
+            raise TypeError(f"unknown AMG options {sorted(amg) + sorted(amg_p)}")
+        self._call(self._lib.ctl_stokes_pc_setup, C.byref(o))
+        self._pc_ready = True
+
+    def pc_apply(self, b_dev, u_dev=None, raw=False):
+        """``Preconditioner.apply`` (raw=False) or the bare ``pc_fn`` (raw=True)."""
+        if u_dev is None:
+            u_dev = torch.zeros_like(b_dev)
+        fn = self._lib.ctl_stokes_pc_fn if raw else self._lib.ctl_stokes_pc_apply
+        self._call(fn, b_dev.data_ptr(), u_dev.data_ptr())
+        return u_dev
+
+    # ------------------------------------------------------------------ solve
+    def solve_device(self, b_dev, u_dev, *, solver_parameters=None, pc="builtin"):
+        if solver_parameters is None:                             # control/control.py:4291-4297
+            solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 100,
+                                 "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0}
+        kind = {"none": L.CTL_PC_NONE, "builtin": L.CTL_PC_BUILTIN}[pc]
+        if kind == L.CTL_PC_BUILTIN and not self._pc_ready:
+            raise L.CtlError("call setup_preconditioner() first")
+        o = self.velocity._krylov_options(solver_parameters, kind)
+        res = L.ctl_solve_result()
+        self._call(self._lib.ctl_stokes_solve, b_dev.data_ptr(), u_dev.data_ptr(), C.byref(o), C.byref(res))
+        return KSPInfo(res)
+
+    def solve(self, u_0, u_1, b_0, b_1, *, solver_parameters=None, pc_fn="builtin"):
+        """``MultiBlockSystem.solve`` of the outer system on host block arrays: ``u_0`` (2N, n_v)
+        and ``u_1`` (2N, n_p) carry the initial guess in and the solution out."""
+        pc = "none" if pc_fn is None else pc_fn
+        if pc not in ("none", "builtin"):
+            raise ValueError("the Stokes system takes pc_fn=None or 'builtin'")
+        b = self.to_device(b_0, b_1)
+        u = self.to_device(u_0, u_1)
+        info = self.solve_device(b, u, solver_parameters=solver_parameters, pc=pc)
+        r0, r1 = self.to_host_blocks(u)
+        np.copyto(_as_host_f64(u_0).reshape(r0.shape), r0)
+        np.copyto(_as_host_f64(u_1).reshape(r1.shape), r1)
+        sp = solver_parameters or {}
+        if not sp.get("preconditioner", False) and info.reason <= 0:   # preconditioner.py:756, 768-770
+            raise RuntimeError("Solver failed to converge")
+        return info

@@ -202,6 +202,47 @@ int ctl_amg_get_aggregates(ctl_handle h, int32_t hierarchy, int32_t level, int32
 /* x = AMG(b): `cycles` V-cycles from a zero guess on hierarchy `hierarchy`; device n-vectors */
 int ctl_amg_solve(ctl_handle h, int32_t hierarchy, const double *b, double *x);
 
+/* ==== Instationary Stokes control: Control.Instationary.incompressible_linear_solve
+ *      (control/control.py:3592-4725).  The outer system couples the heat-type KKT system of
+ *      the velocity space (block_00, control.py:3750-3957) with the divergence blocks
+ *      tau B^T / tau B (block_01 / block_10, 3755-3766) under sub-block T transforms
+ *      (preconditioner/preconditioner.py:471-525) and ConstantNullspace on the pressure blocks
+ *      (preconditioner.py:133-155).  It is described by TWO handles -- `velocity` (M_v, K_v,
+ *      velocity Dirichlet dofs) and `pressure` (M_p, K_p, no bcs), same n_t / tau / beta / CN /
+ *      device / stream -- plus the divergence matrix B (n_p x n_v CSR, host).  Vectors are
+ *      DEVICE pointers, block-major: [2N blocks of n_v (v | zeta) | 2N blocks of n_p (mu | p)].
+ *      Errors are reported through ctl_last_error(velocity).  Single GPU in this round. */
+typedef struct ctl_stokes_s *ctl_stokes;
+
+/* the in-built pressure-Schur preconditioner (control/control.py:4299-4687) */
+typedef struct {
+    ctl_pc_options velocity;   /* construct_pc of the inner heat-type solve (4346-4353)             */
+    int32_t inner_its;         /* GMRES iterations of the block_00 solve: 5 (4355-4361)             */
+    int32_t mass_p;            /* solver_M_p: CTL_S0_CHEBYSHEV (lambda_p_bounds) or CTL_S0_JACOBI   */
+    int32_t mass_p_steps;      /* 20 (4311-4333)                                                    */
+    double lambda_p_min, lambda_p_max;
+    /* solver_K_p: ONE cycle of the aggregation AMG on the Neumann Laplacian K_p, coarsest level
+     * smoothed only (stands in for hypre BoomerAMG x1, control/control.py:4300-4309) */
+    int32_t amg_p_nu, amg_p_max_levels, amg_p_coarse_max, amg_p_cycles;
+    double amg_p_theta, amg_p_lo, amg_p_hi;
+} ctl_stokes_pc_options;
+
+int ctl_stokes_create(ctl_handle velocity, ctl_handle pressure, const int32_t *B_indptr_host,
+                      const int32_t *B_indices_host, const double *B_values_host, ctl_stokes *out);
+int ctl_stokes_destroy(ctl_stokes s);
+int64_t ctl_stokes_vec_len(ctl_stokes s);      /* 2 N (n_v + n_p) */
+/* y = A x: MultiBlockSystemMatrix.mult with sub_n_blocks = 2 (preconditioner.py:375-543) */
+int ctl_stokes_apply(ctl_stokes s, const double *x, double *y);
+int ctl_stokes_pc_default_options(ctl_stokes_pc_options *opts);
+int ctl_stokes_pc_setup(ctl_stokes s, const ctl_stokes_pc_options *opts);
+/* Preconditioner.apply around pc_fn (with the nullspace wrapping) / the raw pc_fn */
+int ctl_stokes_pc_apply(ctl_stokes s, const double *b, double *u);
+int ctl_stokes_pc_fn(ctl_stokes s, const double *b, double *u);
+/* MultiBlockSystem.solve of the outer system (control/control.py:4273-4297, 4688-4693);
+ * opts->pc: CTL_PC_NONE or CTL_PC_BUILTIN */
+int ctl_stokes_solve(ctl_stokes s, const double *b, double *u, const ctl_krylov_options *opts,
+                     ctl_solve_result *result);
+
 /* ---- multi-GPU (one process per GPU): the 128-byte ncclUniqueId is created on rank 0
  *      with ctl_comm_unique_id and distributed by the caller (torch.distributed) */
 int ctl_comm_unique_id(void *id128_host);

@@ -22,7 +22,8 @@ def test_header_declares_the_path():
     names = declared_functions()
     for required in ("ctl_create", "ctl_destroy", "ctl_set_pattern", "ctl_set_values", "ctl_set_bc",
                      "ctl_kkt_apply", "ctl_pc_setup", "ctl_pc_apply", "ctl_solve", "ctl_solve_host",
-                     "ctl_last_error", "ctl_comm_init"):
+                     "ctl_last_error", "ctl_comm_init", "ctl_stokes_create", "ctl_stokes_apply",
+                     "ctl_stokes_pc_setup", "ctl_stokes_solve"):
         assert required in names
 
 
@@ -49,14 +50,15 @@ def test_struct_layouts_match_the_header():
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "s.c")
         open(src, "w").write(
-            '#include <stdio.h>\n#include "ctl_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n",'
+            '#include <stdio.h>\n#include "ctl_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
             'sizeof(ctl_config),sizeof(ctl_pc_options),sizeof(ctl_krylov_options),'
-            'sizeof(ctl_solve_result));return 0;}\n')
+            'sizeof(ctl_solve_result),sizeof(ctl_stokes_pc_options));return 0;}\n')
         exe = os.path.join(d, "s")
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(_lib.ctl_config), ctypes.sizeof(_lib.ctl_pc_options),
-                     ctypes.sizeof(_lib.ctl_krylov_options), ctypes.sizeof(_lib.ctl_solve_result)]
+                     ctypes.sizeof(_lib.ctl_krylov_options), ctypes.sizeof(_lib.ctl_solve_result),
+                     ctypes.sizeof(_lib.ctl_stokes_pc_options)]
 
 
 def test_create_without_gpu_fails_loudly():
