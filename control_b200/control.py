@@ -117,23 +117,15 @@ class Control:
             if self._system is not None:
                 self._system.close()
                 self._system = None
+            if getattr(self, "_stokes", None) is not None:
+                self._stokes.close()
+                self._stokes = None
 
-        # ------------------------------------------------------------------ linear_solve
-        def linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
-                         v_d=None, f=None, print_error=True, create_output=False, plots=False,
-                         pc_mode="triangular", **amg):
-            """control/control.py:2820-3375 (homogeneous Dirichlet data)."""
-            n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
-            M = self._M
+        def _build_rhs(self, v_0, v_d, f, K0, check_v_d, check_f):
+            """Right-hand sides of the heat-type rows (control/control.py:2990-3243; the Stokes
+            driver builds its velocity rows the same way, 3961-4243)."""
+            n_t, n, tau, CN, M = self._n_t, self._n, self.tau, self._CN, self._M
             N = n_t - 1 if CN else n_t
-            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
-            check_f, check_v_d = f is None, v_d is None
-            if check_f:
-                f = self.construct_f()
-            if check_v_d:
-                v_d = self.construct_v_d()
-            K = self._K_levels(self._v)                         # D_v at self._v, control.py:2884-2904
-            K0 = K if self._is_linear() else self.construct_D_v(v_0, self._time_interval[0])
             b_0 = np.zeros((N, n))
             b_1 = np.zeros((N, n))
             if not CN:                                          # control.py:2990-3130
@@ -165,6 +157,25 @@ class Control:
                     b_1[:] = f
                 b_0 = _apply_T_1(b_0)
                 b_1 = _apply_T_2(b_1)
+            return b_0, b_1
+
+        # ------------------------------------------------------------------ linear_solve
+        def linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
+                         v_d=None, f=None, print_error=True, create_output=False, plots=False,
+                         pc_mode="triangular", **amg):
+            """control/control.py:2820-3375 (homogeneous Dirichlet data)."""
+            n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
+            M = self._M
+            N = n_t - 1 if CN else n_t
+            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
+            check_f, check_v_d = f is None, v_d is None
+            if check_f:
+                f = self.construct_f()
+            if check_v_d:
+                v_d = self.construct_v_d()
+            K = self._K_levels(self._v)                         # D_v at self._v, control.py:2884-2904
+            K0 = K if self._is_linear() else self.construct_D_v(v_0, self._time_interval[0])
+            b_0, b_1 = self._build_rhs(v_0, v_d, f, K0, check_v_d, check_f)
             if solver_parameters is None:                       # control.py:3260-3266
                 solver_parameters = {"linear_solver": "gmres", "gmres_restart": 10, "maximum_iterations": 50,
                                      "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0,
@@ -195,6 +206,85 @@ class Control:
             else:
                 self._v, self._zeta = v, zeta
             self._bc(self._zeta)                                # set_zeta re-applies bcs, control.py:1847-1856
+            return self.last_ksp
+
+        # ------------------------------------------------------------------ Stokes control
+        def set_space_p(self, space_p):
+            """``space_p``: the assembled objects of the pressure space, a dict with the divergence
+            matrix ``B`` (n_p x n_v, ``-inner(div(v_trial), p_test) * dx``), the pressure mass
+            matrix ``M_p`` and the pressure Laplacian ``K_p`` (control/control.py:3709, 3746-3747)."""
+            self._space_p = space_p
+
+        def incompressible_linear_solve(self, nullspace_p=None, *, space_p=None, P=None, solver_parameters=None,
+                                        Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None, v_d=None,
+                                        f=None, div_v=None, div_zeta=None, print_error=True, create_output=False,
+                                        plots=False, amg=None, amg_p=None):
+            """control/control.py:3592-4725 (homogeneous Dirichlet velocity data, time-independent
+            linear forward operator).  ``nullspace_p``: None or "constant" -- the pressure blocks
+            carry ConstantNullspace as in every caller of the reference (test/test_control.py,
+            README.md).  Sets ``_v``, ``_zeta``, ``_p``, ``_mu`` and returns the KSP information."""
+            from .stokes import StokesSystem
+            if space_p is None:
+                space_p = getattr(self, "_space_p", None)
+                if space_p is None:
+                    raise ValueError("Undefined space_p")               # control.py:3604-3609
+            else:
+                self.set_space_p(space_p)
+            if nullspace_p not in (None, "constant"):
+                raise ValueError("only the constant pressure nullspace is supported")
+            if P is not None:
+                raise NotImplementedError("user preconditioners are not wired for the Stokes system")
+            if Multigrid:
+                raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
+            if not self._is_linear():
+                raise NotImplementedError("incompressible_linear_solve needs a linear forward operator")
+            n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
+            N = n_t - 1 if CN else n_t
+            n_p = space_p["M_p"].shape[0]
+            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
+            check_f, check_v_d = f is None, v_d is None
+            if check_f:
+                f = self.construct_f()
+            if check_v_d:
+                v_d = self.construct_v_d()
+            K = self._forward_matrix
+            b_0_0, b_0_1 = self._build_rhs(v_0, v_d, f, K, check_v_d, check_f)         # 3961-4243
+            b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)      # 4107-4128, 4207-4228
+            b_1_1 = np.zeros((N, n_p)) if div_zeta is None else np.array(div_zeta, dtype=float)
+            if CN:                                                                        # 4233-4234
+                b_1_0 = _apply_T_2(b_1_0)
+                b_1_1 = _apply_T_1(b_1_1)
+            b_0 = np.concatenate([b_0_0, b_0_1])
+            b_1 = np.concatenate([b_1_0, b_1_1])
+            if solver_parameters is None:                                                 # 4291-4297
+                solver_parameters = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 100,
+                                     "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0,
+                                     "monitor_convergence": print_error}
+            if getattr(self, "_stokes", None) is None:
+                self._stokes = StokesSystem(self._M, K, space_p["B"], space_p["M_p"], space_p["K_p"], n_t=n_t,
+                                            beta=self._beta, CN=CN, time_interval=self._time_interval,
+                                            bc_dofs_v=self._bc_dofs, device=self._dev["device"])
+            system = self._stokes
+            system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
+                                        amg_p=amg_p)
+            u_0 = np.zeros((2 * N, n))
+            u_1 = np.zeros((2 * N, n_p))
+            self.last_ksp = system.solve(u_0, u_1, b_0, b_1, solver_parameters=solver_parameters, pc_fn="builtin")
+            if solver_parameters.get("monitor_convergence", False):
+                for it, r_norm in enumerate(self.last_ksp.history):
+                    print(f"KSP: iteration {it:d}, residual norm {r_norm:.16e}")
+            if CN:                                                                        # 4705-4716
+                v_new = np.zeros((n_t, n))
+                zeta_new = np.zeros((n_t, n))
+                if check_f and check_v_d:
+                    v_new[0] = v_0
+                v_new[1:] = u_0[:N]
+                zeta_new[:-1] = u_0[N:]
+                self._v, self._zeta = v_new, zeta_new
+            else:                                                                         # 4717-4725
+                self._v, self._zeta = u_0[:N].copy(), u_0[N:].copy()
+            self._p, self._mu = u_1[N:].copy(), u_1[:N].copy()
+            self._bc(self._zeta)
             return self.last_ksp
 
         # ------------------------------------------------------------------ non_linear_solve

@@ -250,3 +250,40 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
     if not sp_.get("preconditioner", False) and res.reason <= 0:
         raise RuntimeError("Solver failed to converge")
     return u0, u1, res
+
+
+def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, v_d, f,
+                                v_0=None, div_v=None, div_zeta=None, solver_parameters=None, lambda_v_bounds=None,
+                                lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None):
+    """``Control.Instationary.incompressible_linear_solve`` for homogeneous Dirichlet velocity data
+    (control/control.py:3592-4725): right-hand sides (3961-4243; the velocity rows are those of
+    the heat problem, the pressure rows are zero unless div_v / div_zeta are given), outer solve,
+    unpacking (4705-4725).  ``v_d``, ``f``: (n_t, n_v) cofunction values.  Returns
+    (v, zeta, p, mu, KSPResult) with v, zeta of n_t levels and p, mu of N levels."""
+    t_0, T_f = time_interval
+    tau = (T_f - t_0) / (n_t - 1.0)
+    N = kkt.n_blocks(n_t, CN)
+    n_v, n_p = M_v.shape[0], M_p.shape[0]
+    if v_0 is None:
+        v_0 = np.zeros(n_v)
+    b_0_0, b_0_1 = kkt.build_rhs(M_v, K_v, tau, n_t, CN, bdofs_v, v_d, f, v_0)
+    b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)
+    b_1_1 = np.zeros((N, n_p)) if div_zeta is None else np.array(div_zeta, dtype=float)
+    if CN:                                                         # 4233-4234
+        b_1_0 = kkt.apply_T_2(b_1_0)
+        b_1_1 = kkt.apply_T_1(b_1_1)
+    u_0, u_1, res = stokes_solve(M_v, K_v, B, M_p, K_p, beta=beta, n_t=n_t, CN=CN, time_interval=time_interval,
+                                 bdofs_v=bdofs_v, b_0=np.concatenate([b_0_0, b_0_1]),
+                                 b_1=np.concatenate([b_1_0, b_1_1]), solver_parameters=solver_parameters,
+                                 lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, inner=inner,
+                                 amg_params=amg_params, amg_params_p=amg_params_p)
+    if CN:
+        v = np.zeros((n_t, n_v))
+        zeta = np.zeros((n_t, n_v))
+        v[0] = v_0
+        v[1:] = u_0[:N]
+        zeta[:-1] = u_0[N:]
+    else:
+        v, zeta = u_0[:N].copy(), u_0[N:].copy()
+    zeta[:, bdofs_v] = 0.0
+    return v, zeta, u_1[N:].copy(), u_1[:N].copy(), res

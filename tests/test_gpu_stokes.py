@@ -137,3 +137,37 @@ def test_stokes_rejects_mismatched_handles():
         L.check(a._h, rc)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_control_incompressible_linear_solve_matches_oracle(CN):
+    """The caller of the Stokes path: Control.Instationary.incompressible_linear_solve
+    (control/control.py:3592-4725) on assembled objects, against the oracle's restatement."""
+    import kat
+    from control_b200 import Control
+    q = kat.stokes_problem(6, 6, CN)
+    th = q["th"]
+    times = q["tau"] * np.arange(q["n_t"])
+    lookup = {round(float(t), 12): i for i, t in enumerate(times)}
+    c = Control.Instationary(q["M"], q["K"], desired_state=lambda t: (q["v_d"][lookup[round(float(t), 12)]],
+                                                                    q["v_hat"][lookup[round(float(t), 12)]]),
+                             force_f=lambda t: q["f"][lookup[round(float(t), 12)]], beta=q["beta"], CN=CN, n_t=q["n_t"],
+                             time_interval=q["time_interval"], bc_dofs=q["bdofs"])
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-8, "absolute_tolerance": 0.0,
+           "gmres_restart": 100}
+    info = c.incompressible_linear_solve("constant", space_p=dict(B=th["B"], M_p=th["M_p"], K_p=th["K_p"]),
+                                         solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"],
+                                         lambda_p_bounds=q["lambda_p_bounds"], amg=AMG, amg_p=AMG_P)
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], solver_parameters=sp_,
+        lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"], amg_params=AMG, amg_params_p=AMG_P)
+    assert info.reason == res.reason > 0
+    assert abs(info.its - res.its) <= max(1, int(0.03 * res.its))
+    assert _rel(c._v, v) < 1e-5 and _rel(c._zeta, zeta) < 1e-5        # solver tolerance 1e-8 x conditioning
+    assert _rel(c._p, p) < 1e-4 and _rel(c._mu, mu) < 1e-4
+    # the computed state is discretely divergence free (the constraint rows of the KKT system)
+    div = (th["B"] @ c._v[1:].T).T
+    div -= div.mean(axis=1, keepdims=True)
+    assert np.abs(div).max() < 1e-6 * np.abs(th["B"]).sum(axis=1).max() * np.abs(c._v).max()
+    c.close()

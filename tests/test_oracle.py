@@ -365,3 +365,23 @@ def test_stokes_solve_recovers_manufactured_solution():
     assert res.reason > 0
     assert np.abs(u0 - xr0).max() < 1e-6 * np.abs(xr0).max()
     assert np.abs(u1 - xr1).max() < 1e-4 * np.abs(xr1).max()
+
+
+def test_stokes_control_driver_gives_divergence_free_state():
+    """oracle/stokes.py::incompressible_linear_solve (control/control.py:3592-4725) on the
+    homogeneous-Dirichlet Stokes control problem of tests/kat.py."""
+    from oracle import stokes
+    q = kat.stokes_problem(4, 5, True)
+    th = q["th"]
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-8,
+           "absolute_tolerance": 0.0, "gmres_restart": 100}
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], beta=q["beta"], n_t=q["n_t"], CN=True,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], solver_parameters=sp_,
+        lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"], inner="exact")
+    assert res.reason > 0 and res.its < 40
+    div = (th["B"] @ v[1:].T).T
+    div -= div.mean(axis=1, keepdims=True)
+    assert np.abs(div).max() < 1e-7
+    assert np.abs(p.mean(axis=1)).max() < 1e-12 and np.abs(mu.mean(axis=1)).max() < 1e-12
+    assert np.abs(v[:, q["bdofs"]]).max() == 0.0
