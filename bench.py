@@ -27,7 +27,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "kkt_solve_time"
 UNIT = "s"
@@ -154,8 +153,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import kat
-    q = kat.heat_problem(args.nx, args.n_t, True)
+    from synthetic import problems
+    q = problems.heat_problem(args.nx, args.n_t, True)
     mode = "diagonal" if args.ksp == "minres" else "triangular"
     its = args.ref_its
     times = []
@@ -210,9 +209,9 @@ def main():
         return run_reference(args)
 
     import torch
-    import kat
+    from synthetic import problems
     from control_b200 import MultiBlockSystem, _lib as L
-    from oracle import kkt
+    from control_b200.control import build_rhs
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,7 +223,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    q = kat.heat_problem(args.nx, args.n_t, True)
+    q = problems.heat_problem(args.nx, args.n_t, True)
     mode = "diagonal" if args.ksp == "minres" else "triangular"
     s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=True,
                          time_interval=q["time_interval"], bc_dofs=q["bdofs"], device=local_rank,
@@ -234,8 +233,7 @@ def main():
     t0 = time.perf_counter()
     s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
     setup_s = time.perf_counter() - t0
-    b0, b1 = kkt.build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"],
-                           np.zeros(s.n))
+    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
     rows = slice(s.row_begin, s.row_begin + s.n_local)
     b0, b1 = np.ascontiguousarray(b0[:, rows]), np.ascontiguousarray(b1[:, rows])
     sp_ = solver_parameters(args.ksp, args.rtol)

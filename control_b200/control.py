@@ -18,7 +18,7 @@ import numpy as np
 
 from .system import MultiBlockSystem
 
-__all__ = ["Control"]
+__all__ = ["Control", "build_rhs"]
 
 
 def _apply_T_1(x):      # control/control.py:26-41
@@ -31,6 +31,50 @@ def _apply_T_2(x):      # control/control.py:44-59
     y = x.copy()
     y[1:] += x[:-1]
     return y
+
+
+def build_rhs(M, K0, tau, n_t, CN, bc_dofs, v_d, f, v_0, check_v_d=True, check_f=True):
+    """Right-hand sides of the heat-type rows (control/control.py:2990-3243; the Stokes driver
+    builds its velocity rows the same way, 3961-4243).  ``v_d``, ``f``: (n_t, n) cofunction values
+    (``M @ nodal``), or ready blocks (N, n) when the matching check_* is False; ``K0``: D_v at the
+    initial condition.  Returns the final (T-transformed) ``b_0``, ``b_1`` of shape (N, n)."""
+    n = M.shape[0]
+    N = n_t - 1 if CN else n_t
+    b_0 = np.zeros((N, n))
+    b_1 = np.zeros((N, n))
+
+    def bc(b):
+        b[..., bc_dofs] = 0.0
+    if not CN:                                          # control.py:2990-3130
+        if check_v_d:
+            b_0[:n_t - 1] = tau * v_d[:n_t - 1]
+            bc(b_0)
+        else:
+            b_0[:] = v_d
+        if check_f:
+            b_1[0] = tau * (K0 @ v_0) + M @ v_0
+            b_1[1:] = tau * f[1:]
+            bc(b_1)
+        else:
+            b_1[:] = f
+    else:                                               # control.py:3131-3243
+        if check_v_d:
+            b_0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+            bc(b_0)
+            b_0[0] -= 0.5 * tau * (M @ v_0)
+            bc(b_0[0])
+        else:
+            b_0[:] = v_d
+        if check_f:
+            b_1[:] = 0.5 * tau * (f[:-1] + f[1:])
+            bc(b_1)
+            b_1[0] -= 0.5 * tau * (K0 @ v_0) - M @ v_0
+            bc(b_1[0])
+        else:
+            b_1[:] = f
+        b_0 = _apply_T_1(b_0)
+        b_1 = _apply_T_2(b_1)
+    return b_0, b_1
 
 
 class Control:
@@ -122,42 +166,8 @@ class Control:
                 self._stokes = None
 
         def _build_rhs(self, v_0, v_d, f, K0, check_v_d, check_f):
-            """Right-hand sides of the heat-type rows (control/control.py:2990-3243; the Stokes
-            driver builds its velocity rows the same way, 3961-4243)."""
-            n_t, n, tau, CN, M = self._n_t, self._n, self.tau, self._CN, self._M
-            N = n_t - 1 if CN else n_t
-            b_0 = np.zeros((N, n))
-            b_1 = np.zeros((N, n))
-            if not CN:                                          # control.py:2990-3130
-                if check_v_d:
-                    b_0[:n_t - 1] = tau * v_d[:n_t - 1]
-                    self._bc(b_0)
-                else:
-                    b_0[:] = v_d
-                if check_f:
-                    b_1[0] = tau * (K0 @ v_0) + M @ v_0
-                    b_1[1:] = tau * f[1:]
-                    self._bc(b_1)
-                else:
-                    b_1[:] = f
-            else:                                               # control.py:3131-3243
-                if check_v_d:
-                    b_0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
-                    self._bc(b_0)
-                    b_0[0] -= 0.5 * tau * (M @ v_0)
-                    self._bc(b_0[0])
-                else:
-                    b_0[:] = v_d
-                if check_f:
-                    b_1[:] = 0.5 * tau * (f[:-1] + f[1:])
-                    self._bc(b_1)
-                    b_1[0] -= 0.5 * tau * (K0 @ v_0) - M @ v_0
-                    self._bc(b_1[0])
-                else:
-                    b_1[:] = f
-                b_0 = _apply_T_1(b_0)
-                b_1 = _apply_T_2(b_1)
-            return b_0, b_1
+            return build_rhs(self._M, K0, self.tau, self._n_t, self._CN, self._bc_dofs, v_d, f, v_0,
+                             check_v_d=check_v_d, check_f=check_f)
 
         # ------------------------------------------------------------------ linear_solve
         def linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,

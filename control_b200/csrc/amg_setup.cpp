@@ -148,8 +148,38 @@ static double gershgorin_rho(const HostCSR &A, std::vector<double> &dinv)
     return rho;
 }
 
-// Gauss-Jordan with partial pivoting on [A | I]; A is small (coarsest level)
-static void dense_inverse(const HostCSR &A, std::vector<double> &inv)
+// POWER_ITS steps of the power method on D^-1 A from a fixed start vector (oracle/amg.py::power_rho):
+// a lower estimate of lambda_max(D^-1 A)
+constexpr int POWER_ITS = 30;
+constexpr double POWER_SAFETY = 1.2;
+
+static double power_rho(const HostCSR &A, const std::vector<double> &dinv)
+{
+    const int n = A.n_rows;
+    std::vector<double> x(n), y(n);
+    for (int i = 0; i < n; ++i) x[i] = std::sin(0.37 * (double)i + 0.1) + 0.5 * std::cos(1.3 * (double)i);
+    double lam = 0.0;
+    for (int it = 0; it < POWER_ITS; ++it) {
+        double yy = 0.0, xx = 0.0;
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) s += A.values[k] * x[A.indices[k]];
+            y[i] = dinv[i] * s;
+            yy += y[i] * y[i];
+            xx += x[i] * x[i];
+        }
+        const double ny = std::sqrt(yy);
+        if (ny == 0.0) return 0.0;
+        lam = ny / std::sqrt(xx);
+        for (int i = 0; i < n; ++i) x[i] = y[i] / ny;
+    }
+    return lam;
+}
+
+// Gauss-Jordan with partial pivoting on [A + shift shift^T | I]; A is small (coarsest level).
+// shift empty: plain inverse.  shift = normalised kernel vector e of a singular symmetric A:
+// the result minus e e^T is the pseudo-inverse.
+static void dense_inverse(const HostCSR &A, const std::vector<double> &shift, std::vector<double> &inv)
 {
     const int n = A.n_rows;
     std::vector<double> a((size_t)n * n, 0.0);
@@ -158,6 +188,9 @@ static void dense_inverse(const HostCSR &A, std::vector<double> &inv)
         inv[(size_t)i * n + i] = 1.0;
         for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) a[(size_t)i * n + A.indices[k]] += A.values[k];
     }
+    if (!shift.empty())
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) a[(size_t)i * n + j] += shift[i] * shift[j];
     for (int c = 0; c < n; ++c) {
         int piv = c;
         for (int r = c + 1; r < n; ++r)
@@ -189,21 +222,27 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
 {
     levels.clear();
     HostCSR A = A0;
+    std::vector<double> cand(A.n_rows, 1.0);
     while (true) {
         levels.emplace_back();
         AmgLevelHost &L = levels.back();
         L.A = A;
         L.rho = gershgorin_rho(L.A, L.dinv);
+        L.rho = std::min(L.rho, POWER_SAFETY * power_rho(L.A, L.dinv));
         const int n = A.n_rows;
         if (n <= p.coarse_max || (int)levels.size() >= p.max_levels) break;
         std::vector<int> agg;
-        const int n_agg = aggregate(A, p.theta, agg);
+        const int n_agg = aggregate(A, p.theta * std::pow(p.theta_decay, (double)(levels.size() - 1)), agg);
         if (n_agg == 0 || n_agg >= 0.9 * n) break;
         L.agg = agg;
-        std::vector<double> t(n_agg, 0.0);
+        // tentative prolongator from the near-kernel candidate: T_jJ = cand_j / ||cand|agg_J||,
+        // coarse candidate = those norms
+        std::vector<double> norms(n_agg, 0.0), t(n, 0.0);
         for (int i = 0; i < n; ++i)
-            if (agg[i] >= 0) t[agg[i]] += 1.0;
-        for (int J = 0; J < n_agg; ++J) t[J] = 1.0 / std::sqrt(t[J]);
+            if (agg[i] >= 0) norms[agg[i]] += cand[i] * cand[i];
+        for (int J = 0; J < n_agg; ++J) norms[J] = std::sqrt(norms[J]);
+        for (int i = 0; i < n; ++i)
+            if (agg[i] >= 0) t[i] = cand[i] / norms[agg[i]];
         // P = T - diag(omega * dinv) (A T), explicit zeros of A skipped
         const double omega = 4.0 / (3.0 * L.rho);
         HostCSR &P = L.P;
@@ -216,19 +255,19 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
             // (A T)_iJ accumulated in CSR order of j
             for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
                 const double a = A.values[k];
-                const int J = agg[A.indices[k]];
+                const int j = A.indices[k], J = agg[j];
                 if (a == 0.0 || J < 0) continue;
                 auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
-                if (it == row.end()) row.emplace_back(J, a * t[J]);
-                else it->second += a * t[J];
+                if (it == row.end()) row.emplace_back(J, a * t[j]);
+                else it->second += a * t[j];
             }
             const double d = omega * L.dinv[i];
             for (auto &e : row) e.second = -(d * e.second);
             if (agg[i] >= 0) {
                 const int J = agg[i];
                 auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
-                if (it == row.end()) row.emplace_back(J, t[J]);
-                else it->second = t[J] + it->second;
+                if (it == row.end()) row.emplace_back(J, t[i]);
+                else it->second = t[i] + it->second;
             }
             std::sort(row.begin(), row.end());
             for (auto &e : row) {
@@ -242,7 +281,21 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         csr_matmat(A, P, AP);
         csr_matmat(L.R, AP, Ac);
         A = std::move(Ac);
+        cand = norms;
     }
     AmgLevelHost &last = levels.back();
-    if (last.A.n_rows <= 4096 && p.dense_coarse) dense_inverse(last.A, last.Ainv);
+    if (last.A.n_rows <= 4096 && p.coarse == AMG_COARSE_INVERSE) {
+        dense_inverse(last.A, {}, last.Ainv);
+    } else if (last.A.n_rows <= 4096 && p.coarse == AMG_COARSE_PINV_CONSTANT) {
+        // kernel of the coarsest Galerkin operator = the coarse image of the constants
+        const int nc = last.A.n_rows;
+        double nn = 0.0;
+        for (double c : cand) nn += c * c;
+        nn = std::sqrt(nn);
+        std::vector<double> e(nc);
+        for (int i = 0; i < nc; ++i) e[i] = cand[i] / nn;
+        dense_inverse(last.A, e, last.Ainv);
+        for (int i = 0; i < nc; ++i)
+            for (int j = 0; j < nc; ++j) last.Ainv[(size_t)i * nc + j] -= e[i] * e[j];
+    }
 }

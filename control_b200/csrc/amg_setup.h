@@ -6,15 +6,20 @@
 
 #include "common.cuh"
 
+enum { AMG_COARSE_INVERSE = 0,          // dense inverse
+       AMG_COARSE_PINV_CONSTANT = 1,    // pseudo-inverse, kernel = image of the constants (Neumann Laplacian)
+       AMG_COARSE_SMOOTH = 2 };         // smoother only
+
 struct AmgParams {
     double theta = 0.08;
+    double theta_decay = 0.5;   // strength threshold on level l: theta * theta_decay^l
     int max_levels = 10;
     int coarse_max = 600;   // dense inverse below this size (one GEMV instead of two more levels of launches)
     int nu = 3;
     double lo = 0.25, hi = 1.0;
-    int cycles = 4;      // see oracle/amg.py::solve for why not the reference's 2
+    int cycles = 3;      // see oracle/amg.py::solve for why not the reference's 2
     double acc_lo = 0.0, acc_hi = 1.0;   // > 0: Chebyshev-accelerated cycles (oracle/amg.py::solve)
-    bool dense_coarse = true;            // false: the coarsest level is only smoothed (singular operators)
+    int coarse = 0;                      // AMG_COARSE_*: what happens on the coarsest level
 };
 
 struct AmgLevelHost {

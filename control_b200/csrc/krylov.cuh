@@ -167,7 +167,8 @@ struct Solver {
     int gmres(const double *b, double *x)
     {
         const bool flexible = o.ksp_type == CTL_KSP_FGMRES;
-        const int m = std::max(1, o.restart);
+        // a restart length beyond max_it is never reached: do not allocate basis vectors for it
+        const int m = std::max(1, std::min(o.restart, std::max(1, o.max_it)));
         CTL_CHECK(m + 3 <= 256, CTL_ERR_ARG, "ctl_solve: gmres_restart above 253 is not supported");
         CTL_TRY(ensure_basis((size_t)(m + 1) + (flexible ? m : 0)));
         double **V = ks.basis.data();

@@ -3,7 +3,7 @@
 This package is a numpy/scipy restatement of the algorithm the reference executes
 through Firedrake/PETSc/hypre for ``Control.Instationary.linear_solve``:
 
-* ``fem``      structured-mesh assemblers standing in for Firedrake's ``assemble``
+* (the assembled input matrices come from the neutral ``synthetic`` package)
 * ``kkt``      block tables (control/control.py:2889-2978), the literal
                ``MultiBlockSystemMatrix.mult`` (preconditioner/preconditioner.py:375-543),
                ``T_1/T_2`` and inverses (control/control.py:26-96), nullspace

@@ -11,12 +11,18 @@ implements in C++ (setup, host) and CUDA (cycle), and is the oracle for THAT alg
 Parity of the AMG with hypre is unpinned (DESIGN.md section "AMG").
 
 Algorithm (identical, step for step, in control_b200/csrc/amg_setup.cpp):
-  strength   |a_ij|^2 >= theta^2 |a_ii a_jj|, j != i
+  strength   |a_ij|^2 >= theta_l^2 |a_ii a_jj|, j != i, theta_l = theta * theta_decay^level
   aggregate  three greedy passes in natural order (root + strong neighbours; join the
              aggregate of the strongest already-aggregated strong neighbour; leftovers);
              rows without strong neighbours (e.g. Dirichlet identity rows) stay out
-  prolong    P = (I - omega D^-1 A) T,  T_iJ = |agg_J|^-1/2,
-             omega = 4 / (3 rho),  rho = max_i sum_j |a_ij| / |a_ii|  (Gershgorin)
+  prolong    P = (I - omega D^-1 A) T,  T = the near-kernel candidate (constants on the finest
+             level) restricted to each aggregate and normalised; the coarse candidate is the
+             vector of those norms, so T cand_c = cand on every level
+             omega = 4 / (3 rho),  rho = bound on lambda_max(D^-1 A): the smaller of the
+             Gershgorin bound max_i sum_j |a_ij| / |a_ii| and 1.2 x a 30-step power-iteration
+             estimate from a fixed start vector (Gershgorin alone overestimates the Galerkin
+             operators by 30-50 %, which detunes both omega and the smoother interval: measured
+             V-cycle energy contraction at 512^2 0.34 -> 0.17)
   coarse     A_c = P^T A P; stop at n <= coarse_max (dense inverse) or max_levels
   smoother   Chebyshev (oracle/cheb.py) of degree nu on D^-1 A over [lo*rho, hi*rho]
   cycle      V(nu, nu); ``solve`` = ``cycles`` V-cycles from a zero guess, optionally
@@ -36,8 +42,8 @@ except Exception:                          # pragma: no cover
         return f
 
 
-DEFAULTS = dict(theta=0.08, max_levels=10, coarse_max=600, nu=3, lo=0.25, hi=1.0, cycles=4,
-                acc_lo=0.0, acc_hi=1.0, dense_coarse=True)
+DEFAULTS = dict(theta=0.08, theta_decay=0.5, max_levels=10, coarse_max=600, nu=3, lo=0.25, hi=1.0, cycles=3,
+                acc_lo=0.0, acc_hi=1.0, coarse="inverse")
 
 
 @_jit
@@ -125,6 +131,31 @@ def gershgorin_rho(A):
     return float(np.max(rowsum / d))
 
 
+POWER_ITS = 30
+POWER_SAFETY = 1.2
+
+
+def power_rho(A, dinv):
+    """POWER_ITS steps of the power method on D^-1 A from a fixed start vector; returns the last
+    Rayleigh-type quotient ||D^-1 A x|| / ||x|| (a lower estimate of lambda_max)."""
+    n = A.shape[0]
+    i = np.arange(n, dtype=np.float64)
+    x = np.sin(0.37 * i + 0.1) + 0.5 * np.cos(1.3 * i)
+    lam = 0.0
+    for _ in range(POWER_ITS):
+        y = dinv * (A @ x)
+        ny = float(np.sqrt(np.dot(y, y)))
+        if ny == 0.0:
+            return 0.0
+        lam = ny / float(np.sqrt(np.dot(x, x)))
+        x = y / ny
+    return lam
+
+
+def spectral_bound(A, dinv):
+    return min(gershgorin_rho(A), POWER_SAFETY * power_rho(A, dinv))
+
+
 class Level:
     __slots__ = ("A", "dinv", "rho", "P", "R", "agg", "Ainv")
 
@@ -144,24 +175,29 @@ def setup(A, **kw):
     levels = []
     A = sp.csr_matrix(A).astype(np.float64)
     A.sort_indices()
+    cand = np.ones(A.shape[0])
     while True:
         L = Level()
         L.A = A
         d = A.diagonal()
         L.dinv = 1.0 / d
-        L.rho = gershgorin_rho(A)
+        L.rho = spectral_bound(A, L.dinv)
         L.P = L.R = L.agg = L.Ainv = None
         levels.append(L)
         n = A.shape[0]
         if n <= params["coarse_max"] or len(levels) >= params["max_levels"]:
             break
-        agg, n_agg = aggregate(A, params["theta"])
+        agg, n_agg = aggregate(A, params["theta"] * params["theta_decay"] ** (len(levels) - 1))
         if n_agg == 0 or n_agg >= 0.9 * n:
             break
         L.agg = agg
-        sizes = np.bincount(agg[agg >= 0], minlength=n_agg).astype(np.float64)
+        # tentative prolongator from the near-kernel candidate (constants on the finest level):
+        # column j = the candidate restricted to aggregate j, normalised; the coarse candidate is
+        # the vector of those norms, so that T cand_coarse = cand exactly on every level
         rows = np.flatnonzero(agg >= 0)
-        T = sp.csr_matrix((1.0 / np.sqrt(sizes[agg[rows]]), (rows, agg[rows])), shape=(n, n_agg))
+        norms = np.sqrt(np.bincount(agg[rows], weights=cand[rows] ** 2, minlength=n_agg))
+        T = sp.csr_matrix((cand[rows] / norms[agg[rows]], (rows, agg[rows])), shape=(n, n_agg))
+        cand = norms
         omega = 4.0 / (3.0 * L.rho)
         Az = A.copy()
         Az.eliminate_zeros()
@@ -173,10 +209,16 @@ def setup(A, **kw):
         A = (L.R @ (A @ P)).tocsr()
         A.sort_indices()
     last = levels[-1]
-    # dense_coarse=False: the coarsest level is only smoothed (singular operators such as the
-    # Neumann pressure Laplacian of the Stokes preconditioner have no inverse)
-    if last.A.shape[0] <= 4096 and params["dense_coarse"]:
+    # coarse = "inverse": dense inverse; "pinv_constant": pseudo-inverse of a symmetric operator
+    # whose kernel is the constants (the Neumann pressure Laplacian of the Stokes preconditioner:
+    # the smoothed prolongators reproduce constants, so every Galerkin operator keeps that kernel),
+    # (A + e e^T)^-1 - e e^T with e = the normalised coarse image of the constants; "smooth": the coarsest level is only smoothed
+    if last.A.shape[0] <= 4096 and params["coarse"] == "inverse":
         last.Ainv = np.linalg.inv(last.A.toarray())
+    elif last.A.shape[0] <= 4096 and params["coarse"] == "pinv_constant":
+        e = cand / np.linalg.norm(cand)           # kernel of the coarsest Galerkin operator
+        E = np.outer(e, e)
+        last.Ainv = np.linalg.inv(last.A.toarray() + E) - E
     return Hierarchy(levels, params)
 
 
@@ -198,12 +240,12 @@ def vcycle(H, lvl, b, x=None):
 
 def solve(H, b, cycles=None):
     """``cycles`` V-cycles from a zero guess (the stand-in for
-    ``pc_hypre_boomeramg_max_iter``: 2, control/control.py:2065).  The default is FOUR
-    V(3,3) cycles, not two: a smoothed-aggregation cycle with polynomial smoothers contracts
-    more slowly than a BoomerAMG cycle, and the forward/backward time substitution amplifies
-    inner-solve errors (with two cycles the outer iteration count grows from 8 at 64^2 to
-    23 at 256^2 and stalls at 1024^2; with four V(3,3) cycles it stays within 6-11, against
-    6-7 with exact inner solves: DESIGN.md section "AMG").
+    ``pc_hypre_boomeramg_max_iter``: 2, control/control.py:2065).  The default is THREE
+    V(3,3) cycles, not two: this cycle contracts the energy norm by about 0.2 per cycle at
+    1024^2 (a BoomerAMG cycle: about 0.1), and the forward/backward time substitution of the
+    triangular preconditioner amplifies inner-solve errors.  Measured at config C2 (FGMRES,
+    rtol 1e-6): 24 / 11 / 8 outer iterations with 2 / 3 / 4 cycles, 6-7 with exact inner
+    solves; three cycles minimise the solve time (DESIGN.md section "AMG").
 
     With ``acc_lo > 0`` the cycles are Chebyshev-accelerated: the V-cycle B (zero guess) is
     the preconditioner of a ``cycles``-step Chebyshev semi-iteration on B A with spectrum

@@ -14,7 +14,7 @@ import scipy.sparse.linalg as spla
 
 from . import amg as _amg
 from .cheb import chebyshev
-from .fem import assemble_bc
+from synthetic.fem import assemble_bc
 from .kkt import apply_T_1_inv, apply_T_2, apply_T_2_inv, n_blocks
 
 

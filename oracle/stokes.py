@@ -10,7 +10,7 @@ on assembled matrices (oracle; test infrastructure only).
 
 Unknowns: ``x_0`` = (2N, n_v) blocks [v | zeta], ``x_1`` = (2N, n_p) blocks [mu | p] (the first
 N pressure blocks multiply B^T in the adjoint-equation rows, control/control.py:3765-3766).
-The inner solves on ``K_p`` are one AMG cycle of the stand-in AMG (hypre BoomerAMG x1 in the
+The inner solves on ``K_p`` are six cycles of the stand-in AMG (ONE hypre BoomerAMG cycle in the
 reference, control/control.py:4300-4309): parity with hypre is unpinned, as for the heat path.
 """
 import numpy as np
@@ -111,9 +111,10 @@ def stokes_apply_fused(M_v, K_v, B, tau, beta, n_t, CN, bdofs_v, x0, x1):
 
 
 def make_solver_p(M_p, K_p, lambda_p_bounds, amg_params=None):
-    """``solver_K_p`` (one AMG cycle on the Neumann Laplacian, control/control.py:4300-4309) and
+    """``solver_K_p`` (AMG cycles on the Neumann Laplacian; ONE BoomerAMG cycle in the reference,
+    control/control.py:4300-4309; six of the stand-in AMG here) and
     ``solver_M_p`` (Chebyshev-20/Jacobi or one Jacobi sweep, 4311-4333), acting on (k, n_p)."""
-    params = dict(cycles=1, dense_coarse=False)
+    params = dict(cycles=6, coarse="pinv_constant")       # see ctl_stokes_pc_default_options
     params.update(amg_params or {})
     H = _amg.setup(K_p, **params)
     dinv = 1.0 / M_p.diagonal()

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--be", action="store_true")
     args = ap.parse_args()
     from control_b200 import MultiBlockSystem, _lib as L
-    from oracle import fem
+    from synthetic import fem
     t = time.time()
     M, K, _, bd = fem.assemble_p1_2d(args.nx, args.nx, 2.0, 2.0)
     print(f"assembled n={M.shape[0]} nnz={M.nnz} in {time.time() - t:.1f}s", flush=True)

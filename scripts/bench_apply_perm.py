@@ -4,7 +4,7 @@ import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from control_b200 import MultiBlockSystem, _lib as L
-from oracle import fem
+from synthetic import fem
 nx = 1024
 M, K, _, bd = fem.assemble_p1_2d(nx, nx, 2.0, 2.0)
 n = M.shape[0]

@@ -26,9 +26,9 @@ def main():
     ap.add_argument("--dim", type=int, default=2)
     ap.add_argument("--amg", default="", help="comma list key=value of AMG options (cycles, nu, lo, hi, acc_lo, ...)")
     args = ap.parse_args()
-    import kat
+    from synthetic import problems as kat
     from control_b200 import MultiBlockSystem
-    from oracle import kkt
+    from control_b200.control import build_rhs
     t = time.time()
     q = kat.heat_problem(args.nx, args.n_t, not args.be) if args.dim == 2 else kat.heat_problem_3d(args.nx, args.n_t, not args.be)
     print(f"assembled n={q['M'].shape[0]} in {time.time() - t:.1f}s", flush=True)
@@ -44,7 +44,7 @@ def main():
     s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=args.mode, **amg)
     print(f"pc setup in {time.time() - t:.1f}s; levels:",
           [s._lib.ctl_amg_num_levels(s._h, i) for i in range(s._lib.ctl_amg_num_hierarchies(s._h))], flush=True)
-    b0, b1 = kkt.build_rhs(q["M"], q["K"], q["tau"], q["n_t"], not args.be, q["bdofs"], q["v_d"], q["f"],
+    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], not args.be, q["bdofs"], q["v_d"], q["f"],
                            np.zeros(s.n))
     b = s.to_device(b0, b1)
     sp_ = {"linear_solver": args.ksp, "gmres_restart": args.restart, "maximum_iterations": 60, "preconditioner": True,

@@ -1,4 +1,4 @@
-"""Structured-mesh finite-element assemblers (oracle; test infrastructure only).
+"""Structured-mesh finite-element assemblers (input generator: stands in for Firedrake assembly).
 
 Stand-ins for ``assemble(inner(trial, test) * dx)`` (mass ``M``, control/control.py:1562)
 and ``assemble(forward_form)`` for the Laplacian ``inner(grad(trial), grad(test)) * dx``

@@ -7,7 +7,8 @@ import pytest
 import torch
 
 import kat
-from oracle import fem, kkt
+from oracle import kkt
+from synthetic import fem
 
 pytestmark = pytest.mark.gpu
 

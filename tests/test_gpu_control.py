@@ -6,7 +6,7 @@ import pytest
 
 import kat
 from oracle import control as ocontrol
-from oracle import fem
+from synthetic import fem
 
 pytestmark = pytest.mark.gpu
 

@@ -5,7 +5,8 @@ import pytest
 
 import kat
 from oracle import control as ocontrol
-from oracle import fem, kkt
+from oracle import kkt
+from synthetic import fem
 
 pytestmark = pytest.mark.gpu
 

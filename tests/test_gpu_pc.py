@@ -8,7 +8,8 @@ import torch
 import kat
 from oracle import amg as oamg
 from oracle import control as ocontrol
-from oracle import fem, kkt
+from oracle import kkt
+from synthetic import fem
 from oracle import pc as opc
 
 pytestmark = pytest.mark.gpu

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from control_b200 import partition
-from oracle import fem
+from synthetic import fem
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

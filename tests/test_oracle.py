@@ -10,7 +10,8 @@ import pytest
 import scipy.sparse as sp
 
 import kat
-from oracle import amg, cheb, control, fem, kkt, krylov
+from oracle import amg, cheb, control, kkt, krylov
+from synthetic import fem
 
 
 # ---------------------------------------------------------------- assemblers
