@@ -528,6 +528,11 @@ int ctl_stokes_pc_default_options(ctl_stokes_pc_options *o)
 {
     if (!o) return CTL_ERR_ARG;
     ctl_pc_default_options(&o->velocity);
+    // the aggregation hierarchy of the vector-P2 velocity operator contracts more slowly than the P1
+    // one (energy norm, per V(3,3) cycle: 0.28 at 64^2, 0.34 at 128^2, worse at 512^2), and the inner
+    // GMRES runs a fixed five iterations: at config C4 three cycles need > 100 outer iterations,
+    // six need 18 (51.7 s against > 150 s)
+    o->velocity.amg_cycles = 6;
     AmgParams d;
     o->inner_its = 5;                   // control/control.py:4358
     o->mass_p = CTL_S0_JACOBI;

@@ -138,8 +138,10 @@ def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, l
     """``pc_fn(b_0, b_1) -> (u_0, u_1)`` of control/control.py:4337-4513 (CN) / 4515-4687 (BE)."""
     N = kkt.n_blocks(n_t, CN)
     ns_v = kkt.DirichletBCNullspace(bdofs_v)
+    vparams = dict(cycles=6)                      # ctl_stokes_pc_default_options: six cycles on the P2 operator
+    vparams.update(amg_params or {})
     heat_pc = construct_pc(M_v, K_v, tau, beta, n_t, CN, bdofs_v, lambda_v_bounds=lambda_v_bounds,
-                           inner=inner, amg_params=amg_params, epsilon=epsilon)
+                           inner=inner, amg_params=vparams, epsilon=epsilon)
     K_solve, M_solve, _ = make_solver_p(M_p, K_p, lambda_p_bounds, amg_params_p)
     pblocks = kkt.build_blocks(M_p, K_p, tau, beta, n_t, CN)       # block_*_int_p, 3805-3957
     inner_parameters = {"preconditioner": True, "linear_solver": "gmres", "maximum_iterations": 5,

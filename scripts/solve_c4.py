@@ -22,6 +22,10 @@ def main():
     ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--be", action="store_true")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--max_it", type=int, default=100)
+    ap.add_argument("--inner_its", type=int, default=5)
+    ap.add_argument("--amg", default="", help="comma list key=value: velocity AMG options")
+    ap.add_argument("--amg_p", default="", help="comma list key=value: K_p AMG options")
     args = ap.parse_args()
     from synthetic import problems
     from control_b200.control import build_rhs
@@ -36,12 +40,19 @@ def main():
                      time_interval=q["time_interval"], bc_dofs_v=q["bdofs"])
     print(f"system created in {time.time() - t:.1f}s", flush=True)
     t = time.time()
-    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    def parse(txt):
+        out = {}
+        for kv in filter(None, txt.split(",")):
+            k, v = kv.split("=")
+            out[k] = float(v) if "." in v else int(v)
+        return out
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+                           inner_its=args.inner_its, amg=parse(args.amg), amg_p=parse(args.amg_p))
     print(f"pc setup in {time.time() - t:.1f}s", flush=True)
     N = s.N
     b00, b01 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], not args.be, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n_v))
     b = s.to_device(np.concatenate([b00, b01]), np.zeros((2 * N, s.n_p)))
-    sp_ = {"linear_solver": "fgmres", "gmres_restart": args.restart, "maximum_iterations": 100, "preconditioner": True,
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": args.restart, "maximum_iterations": args.max_it, "preconditioner": True,
            "relative_tolerance": args.rtol, "absolute_tolerance": 0.0}
     for rep in range(args.reps):
         u = torch.zeros_like(b)
@@ -55,7 +66,7 @@ def main():
                           "mult_s": info.seconds_mult, "pc_s": info.seconds_pc, "n_mult": info.n_mult,
                           "n_pc": info.n_pc, "launches": s.kernel_launches() - l0,
                           "res": float(np.sqrt((r0 ** 2).sum() + (r1 ** 2).sum())),
-                          "hist": info.history[:3] + info.history[-2:]}), flush=True)
+                          "hist": info.history[:6] + info.history[-2:]}), flush=True)
     print("mem GB", torch.cuda.max_memory_allocated() / 1e9, torch.cuda.mem_get_info())
 
 
