@@ -190,12 +190,107 @@ def config_dict(args):
             "l2": "Krylov vectors (1.08 GB each) exceed L2; per-kernel micro-timings flush L2 between launches"}
 
 
+def run_stokes(args):
+    """--workload stokes: BASELINE config C4 (instationary Stokes control, Taylor-Hood P2-P1 on
+    512x512, n_t = 32, CN, FGMRES + pressure-Schur preconditioner), one GPU.  Opt-in: one solve
+    takes about a minute, so the default bench stays on config C2."""
+    import torch
+    from synthetic import problems
+    from control_b200.control import build_rhs
+    from control_b200.stokes import StokesSystem
+    assert args.gpus == 1, "the Stokes path is single-GPU in this round"
+    torch.cuda.set_device(0)
+    q = problems.stokes_problem(args.nx, args.n_t, True, beta=1.0)
+    th = q["th"]
+    s = StokesSystem(th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], n_t=q["n_t"], beta=q["beta"], CN=True,
+                     time_interval=q["time_interval"], bc_dofs_v=q["bdofs"])
+    t0 = time.perf_counter()
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    setup_s = time.perf_counter() - t0
+    N = s.N
+    b00, b01 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n_v))
+    b_np = np.concatenate([b00.ravel(), b01.ravel(), np.zeros(2 * N * s.n_p)])
+    b_host = torch.from_numpy(b_np).pin_memory()
+    u_host = torch.zeros_like(b_host).pin_memory()
+    b_dev = b_host.to(s.device)
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 30, "maximum_iterations": 100, "preconditioner": True,
+           "relative_tolerance": args.rtol, "absolute_tolerance": 0.0}
+
+    def solve_resident():
+        u = torch.zeros_like(b_dev)
+        return s.solve_device(b_dev, u, solver_parameters=sp_), u
+
+    def solve_e2e():
+        bd = b_host.to(s.device, non_blocking=True)
+        ud = u_host.to(s.device, non_blocking=True)
+        info = s.solve_device(bd, ud, solver_parameters=sp_)
+        u_host.copy_(ud, non_blocking=True)
+        torch.cuda.synchronize()
+        return info
+
+    for _ in range(args.warmup):
+        solve_resident()
+    torch.cuda.synchronize()
+    l0 = s.kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            info, u_last = solve_resident()
+        ev1.record()
+        torch.cuda.synchronize()
+    launches = s.kernel_launches() - l0
+    value = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+    r0, r1 = s.to_host_blocks(b_dev - s.apply(u_last))
+    r0[:, q["bdofs"]] = 0.0
+    r1 = r1 - r1.mean(axis=1, keepdims=True)
+    t0 = time.perf_counter()
+    solve_e2e()
+    e2e_s = time.perf_counter() - t0
+    peak, peak_src = measured_peak()
+    div = s.time_divergence_products(20)
+    micro = s.velocity.micro_benchmarks(flush_l2=True)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": value * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C4: instationary Stokes control, Taylor-Hood P2-P1 on {args.nx}x{args.nx} mesh of "
+                                   f"(0,2)^2, n_t={args.n_t}, trapezoidal (CN), beta=1, FGMRES(30) + in-built "
+                                   f"pressure-Schur preconditioner (5 inner GMRES iterations), rtol {args.rtol:g}",
+                       "n_v": s.n_v, "n_p": s.n_p, "n_t": args.n_t, "rtol": args.rtol,
+                       "l2": "Krylov vectors (1.2 GB each) exceed L2"},
+            "iterations": info.its, "converged_reason": info.reason,
+            "kkt_residual": float(np.sqrt((r0 ** 2).sum() + (r1 ** 2).sum())),
+            "rel_residual": info.rnorm / info.ref_norm if info.ref_norm else None,
+            "setup_s": setup_s, "pc_apply_ms": info.seconds_pc / max(1, info.n_pc) * 1e3,
+            "operator_apply_ms": info.seconds_mult / max(1, info.n_mult) * 1e3, "peak_source": peak_src,
+            "roofline": {"kernel": "sell_cheb_kernel, velocity AMG level 0 (smoother step of the time sweeps)",
+                         "bound": "hbm", "achieved": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6, "peak": peak,
+                         "unit": "GB/s", "frac": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6 / peak, "traffic": None,
+                         "alg_bytes_per_launch": micro["cheb_bytes"], "ms_per_launch": micro["cheb_ms"],
+                         "how": "CUDA events per launch, L2 flushed between launches"},
+            "roofline_spmm": {"kernel": "panel_spmm_kernel (tau B X on one time panel)", "bound": "hbm",
+                              "achieved": div["B_bytes"] / div["B_ms"] / 1e6, "peak": peak, "unit": "GB/s",
+                              "frac": div["B_bytes"] / div["B_ms"] / 1e6 / peak, "traffic": None,
+                              "alg_bytes_per_launch": div["B_bytes"], "ms_per_launch": div["B_ms"],
+                              "transposed": {"achieved": div["BT_bytes"] / div["BT_ms"] / 1e6,
+                                             "frac": div["BT_bytes"] / div["BT_ms"] / 1e6 / peak,
+                                             "alg_bytes_per_launch": div["BT_bytes"], "ms_per_launch": div["BT_ms"]},
+                              "how": "CUDA events around 20 back-to-back launches (panels exceed L2)"},
+            "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * b_host.numel() * 8,
+                    "d2h_bytes_per_step": b_host.numel() * 8},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "kernels": micro}
+    print(json.dumps(line), flush=True)
+    s.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="heat", choices=["heat", "stokes"],
+                    help="heat = config C2 (default, the metric's configuration); stokes = config C4 (opt-in)")
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--n_t", type=int, default=64)
     ap.add_argument("--ksp", default="minres", choices=["minres", "fgmres", "gmres"])
@@ -207,6 +302,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "stokes":
+        if args.nx == 1024 and args.n_t == 64:          # the heat defaults: switch to config C4's
+            args.nx, args.n_t = 512, 32
+        return run_stokes(args)
 
     import torch
     from synthetic import problems

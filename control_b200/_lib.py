@@ -109,6 +109,7 @@ SIGNATURES = {
     "ctl_stokes_pc_fn": (C.c_int, [_H, _F64P, _F64P]),
     "ctl_stokes_solve": (C.c_int, [_H, _F64P, _F64P, C.POINTER(ctl_krylov_options),
                                    C.POINTER(ctl_solve_result)]),
+    "ctl_stokes_time": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),
     "ctl_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ctl_comm_init": (C.c_int, [_H, C.c_void_p]),
     "ctl_kernel_launches": (C.c_int64, [_H]),

@@ -694,4 +694,49 @@ int ctl_stokes_solve(ctl_stokes S, const double *b, double *u, const ctl_krylov_
     });
 }
 
+int ctl_stokes_time(ctl_stokes S, int reps, double *out)
+{
+    if (!S) return CTL_ERR_ARG;
+    ctl_handle_s *h = S->hv, *hp = S->hp;
+    CTL_CHECK(out && reps > 0, CTL_ERR_ARG, "ctl_stokes_time: bad argument");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    double *xv = nullptr, *yv = nullptr, *xp = nullptr;
+    CTL_TRY(ctl_scratch_get(h, &xv));
+    CTL_TRY(ctl_scratch_get(h, &yv));
+    CTL_TRY(ctl_scratch_get(hp, &xp));
+    int rc = vec_zero(h, xv, h->vec_len());
+    if (rc == CTL_OK) rc = vec_zero(h, yv, h->vec_len());
+    if (rc == CTL_OK) rc = vec_zero(h, xp, hp->vec_len());
+    cudaEvent_t e0, e1;
+    CTL_CUDA(cudaEventCreate(&e0));
+    CTL_CUDA(cudaEventCreate(&e1));
+    const double tau = h->cfg.tau;
+    float ms[2] = {0.f, 0.f};
+    for (int which = 0; which < 2 && rc == CTL_OK; ++which) {
+        for (int pass = 0; pass < 2 && rc == CTL_OK; ++pass) {        // pass 0 warms up
+            cudaEventRecord(e0, h->stream);
+            for (int r = 0; r < reps && rc == CTL_OK; ++r)
+                rc = which == 0 ? panel_spmm(S, S->B, xv, nullptr, xp, tau, 1.0, T_TWO, T_NONE, false)
+                                : panel_spmm(S, S->BT, xp, nullptr, yv, tau, 1.0, T_ONE, T_NONE, true);
+            cudaEventRecord(e1, h->stream);
+            cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms[which], e0, e1);
+        }
+    }
+    const double n_v = h->n_loc, n_p = hp->n_loc, N = h->N;
+    std::vector<int> ptr_end(1);
+    cudaMemcpy(ptr_end.data(), S->B.ptr + S->B.n_rows, sizeof(int), cudaMemcpyDeviceToHost);
+    const double nnz = ptr_end[0];
+    out[0] = ms[0] / reps;
+    out[1] = 12.0 * nnz + 4.0 * (n_p + 1) + 8.0 * N * (n_v + n_p);
+    out[2] = ms[1] / reps;
+    out[3] = 12.0 * nnz + 4.0 * (n_v + 1) + 8.0 * N * (n_v + n_p) + 8.0 * N * n_v;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctl_scratch_put(h, xv);
+    ctl_scratch_put(h, yv);
+    ctl_scratch_put(hp, xp);
+    return rc;
+}
+
 }  // extern "C"

@@ -129,6 +129,13 @@ class StokesSystem:
         self._call(fn, b_dev.data_ptr(), u_dev.data_ptr())
         return u_dev
 
+    def time_divergence_products(self, reps=20):
+        """Average milliseconds and algorithmic bytes of the batched ``tau B X`` / ``Y += tau B^T X``
+        panel products (``ctl_stokes_time``)."""
+        out = (C.c_double * 4)()
+        self._call(self._lib.ctl_stokes_time, int(reps), out)
+        return {"B_ms": out[0], "B_bytes": out[1], "BT_ms": out[2], "BT_bytes": out[3]}
+
     # ------------------------------------------------------------------ solve
     def solve_device(self, b_dev, u_dev, *, solver_parameters=None, pc="builtin"):
         if solver_parameters is None:                             # control/control.py:4291-4297

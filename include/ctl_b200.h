@@ -242,6 +242,11 @@ int ctl_stokes_pc_fn(ctl_stokes s, const double *b, double *u);
  * opts->pc: CTL_PC_NONE or CTL_PC_BUILTIN */
 int ctl_stokes_solve(ctl_stokes s, const double *b, double *u, const ctl_krylov_options *opts,
                      ctl_solve_result *result);
+/* time `reps` back-to-back launches of the batched divergence products on one time panel (CUDA
+ * events on the stream; the panels exceed L2 at config C4).  out[0] = tau B X, average ms;
+ * out[1] = its algorithmic bytes (12 nnz_B + 4 (n_p + 1) + 8 N (n_v + n_p)); out[2] = Y += tau B^T X,
+ * ms; out[3] = its bytes (the same + 8 N n_v for the accumulate) */
+int ctl_stokes_time(ctl_stokes s, int reps, double *out4_host);
 
 /* ---- multi-GPU (one process per GPU): the 128-byte ncclUniqueId is created on rank 0
  *      with ctl_comm_unique_id and distributed by the caller (torch.distributed) */
