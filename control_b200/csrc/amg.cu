@@ -96,7 +96,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
     // launches, 1.56 ms against 1.27 ms per inner solve: the operations are bound by dependent memory
     // round trips, not by launch gaps)
     const char *fe = getenv("CTL_FUSED");
-    if (nl > FUSED_FROM && fe && fe[0] == '1') {
+    if (nl > FUSED_FROM && fe && (fe[0] == '1' || fe[0] == '2')) {
+        H.fused.cluster = fe[0] == '2' ? fused_cluster_size(h) : 0;      // 2: one thread-block cluster
         h->recorder = &H.fused;
         const int rc = vcycle(h, H, FUSED_FROM, H.dev[FUSED_FROM].b, H.dev[FUSED_FROM].x, true);
         h->recorder = nullptr;

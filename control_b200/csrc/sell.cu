@@ -434,6 +434,31 @@ __device__ __forceinline__ void fused_rows(const FusedOp &op, int gtid, int gthr
     }
 }
 
+__device__ __forceinline__ void fused_execute(const FusedOp &op, int gtid, int gthreads)
+{
+    if (op.type == FOP_DINV_SCALE) {
+        for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.c * op.dinv[r] * op.b[r];
+    } else if (op.type == FOP_COPY) {
+        for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.cur[r];
+    } else if (op.type == FOP_GEMV) {
+        const int lane = gtid & 31, warps = gthreads >> 5;
+        for (int row = gtid >> 5; row < op.n; row += warps) {
+            double acc = 0.0;
+            for (int j = lane; j < op.n; j += 32) acc = fma(__ldg(op.vals + (size_t)row * op.n + j), op.b[j], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) op.out[row] = acc;
+        }
+    } else {
+        switch (op.lanes) {
+        case 4: fused_rows<4>(op, gtid, gthreads); break;
+        case 8: fused_rows<8>(op, gtid, gthreads); break;
+        case 16: fused_rows<16>(op, gtid, gthreads); break;
+        default: fused_rows<32>(op, gtid, gthreads); break;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(FT) fused_tail_kernel(const FusedOp *__restrict__ ops, int n_ops)
 {
     cg::grid_group grid = cg::this_grid();
@@ -441,28 +466,24 @@ __global__ void __launch_bounds__(FT) fused_tail_kernel(const FusedOp *__restric
     const int gthreads = gridDim.x * FT;
     for (int i = 0; i < n_ops; ++i) {
         const FusedOp op = ops[i];
-        if (op.type == FOP_DINV_SCALE) {
-            for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.c * op.dinv[r] * op.b[r];
-        } else if (op.type == FOP_COPY) {
-            for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.cur[r];
-        } else if (op.type == FOP_GEMV) {
-            const int lane = gtid & 31, warps = gthreads >> 5;
-            for (int row = gtid >> 5; row < op.n; row += warps) {
-                double acc = 0.0;
-                for (int j = lane; j < op.n; j += 32) acc = fma(__ldg(op.vals + (size_t)row * op.n + j), op.b[j], acc);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                if (lane == 0) op.out[row] = acc;
-            }
-        } else {
-            switch (op.lanes) {
-            case 4: fused_rows<4>(op, gtid, gthreads); break;
-            case 8: fused_rows<8>(op, gtid, gthreads); break;
-            case 16: fused_rows<16>(op, gtid, gthreads); break;
-            default: fused_rows<32>(op, gtid, gthreads); break;
-            }
-        }
+        fused_execute(op, gtid, gthreads);
         grid.sync();
+    }
+}
+
+// The same program on ONE thread-block cluster: the operations of the small levels (<= 20 k rows,
+// matrices resident in L2) need a few thousand threads, and a cluster barrier costs a fraction of a
+// grid barrier or of a kernel boundary.
+__global__ void __launch_bounds__(FT) fused_cluster_kernel(const FusedOp *__restrict__ ops, int n_ops)
+{
+    cg::cluster_group cl = cg::this_cluster();
+    const int gtid = cl.block_rank() * FT + threadIdx.x;
+    const int gthreads = cl.num_blocks() * FT;
+    for (int i = 0; i < n_ops; ++i) {
+        const FusedOp op = ops[i];
+        fused_execute(op, gtid, gthreads);
+        __threadfence();
+        cl.sync();
     }
 }
 
@@ -503,23 +524,58 @@ int fused_run(ctl_handle_s *h, const FusedProgram &p)
     if (p.n_ops == 0) return CTL_OK;
     static int n_sm = 0;
     if (!n_sm) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    const FusedOp *ops = p.dev;
+    int n_ops = p.n_ops;
     cudaLaunchConfig_t cfg{};
-    static int n_cta = 0;
-    if (!n_cta) {
-        n_cta = 32;
-        if (const char *e = getenv("CTL_FUSED_CTAS")) n_cta = std::max(1, std::min(n_sm, atoi(e)));
-    }
-    cfg.gridDim = dim3(n_cta);
     cfg.blockDim = dim3(FT);
     cfg.stream = h->stream;
     cudaLaunchAttribute at;
-    at.id = cudaLaunchAttributeCooperative;
-    at.val.cooperative = 1;
     cfg.attrs = &at;
     cfg.numAttrs = 1;
-    const FusedOp *ops = p.dev;
-    int n_ops = p.n_ops;
-    CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_tail_kernel, ops, n_ops));
+    if (p.cluster > 0) {
+        cfg.gridDim = dim3(p.cluster);
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = p.cluster;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_cluster_kernel, ops, n_ops));
+    } else {
+        static int n_cta = 0;
+        if (!n_cta) {
+            n_cta = 32;
+            if (const char *e = getenv("CTL_FUSED_CTAS")) n_cta = std::max(1, std::min(n_sm, atoi(e)));
+        }
+        cfg.gridDim = dim3(n_cta);
+        at.id = cudaLaunchAttributeCooperative;
+        at.val.cooperative = 1;
+        CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_tail_kernel, ops, n_ops));
+    }
     h->launches++;
     return CTL_OK;
+}
+
+// largest cluster (16, else 8) of FT-thread CTAs the device can co-schedule for the fused kernel
+int fused_cluster_size(ctl_handle_s *h)
+{
+    for (int want : {16, 8}) {
+        if (want > 8 &&
+            cudaFuncSetAttribute(fused_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(want);
+        cfg.blockDim = dim3(FT);
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = want;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, fused_cluster_kernel, &cfg) == cudaSuccess && n > 0) return want;
+        cudaGetLastError();
+    }
+    return 0;
 }

@@ -57,9 +57,11 @@ struct FusedProgram {
     std::vector<FusedOp> host;
     FusedOp *dev = nullptr;
     int n_ops = 0;
+    int cluster = 0;     // > 0: run on one thread-block cluster of this many CTAs (else cooperative grid)
 };
 int fused_upload(ctl_handle_s *h, FusedProgram &p);
 int fused_run(ctl_handle_s *h, const FusedProgram &p);
+int fused_cluster_size(ctl_handle_s *h);
 void fused_free(FusedProgram &p);
 int vec_copy_n(ctl_handle_s *h, double *dst, const double *src, int n);   // recordable device copy
 void sell_free(SellMat &m);
