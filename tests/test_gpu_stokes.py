@@ -32,7 +32,7 @@ def _rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-@pytest.mark.parametrize("CN,n_t", [(True, 5), (True, 9), (False, 5), (False, 8), (True, 70)])
+@pytest.mark.parametrize("CN,n_t", [(True, 2), (False, 2), (True, 5), (True, 9), (False, 5), (False, 8), (True, 33), (True, 70)])
 def test_stokes_operator_matches_oracle(CN, n_t):
     q = _problem(5, n_t, CN)
     th, N = q["th"], q["N"]
