@@ -29,6 +29,7 @@ class ctl_pc_options(C.Structure):
     _fields_ = [("mode", C.c_int32), ("solver_0", C.c_int32),
                 ("cheb_emin", C.c_double), ("cheb_emax", C.c_double),
                 ("cheb_steps", C.c_int32), ("amg_cycles", C.c_int32), ("amg_nu", C.c_int32),
+                ("amg_nu_fine", C.c_int32),
                 ("amg_max_levels", C.c_int32), ("amg_coarse_max", C.c_int32),
                 ("amg_theta", C.c_double), ("amg_lo", C.c_double), ("amg_hi", C.c_double),
                 ("amg_acc_lo", C.c_double), ("amg_acc_hi", C.c_double)]

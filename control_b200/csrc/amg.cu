@@ -80,7 +80,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
                 CTL_TRY(sell_from_csr(h, Lh.R, Ld.R, l >= FUSED_FROM));
             }
             // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
-            H.bytes_per_cycle += spmv * (2 * p.nu) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
+            const int nu_l = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;
+            H.bytes_per_cycle += spmv * (2 * nu_l) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
         } else if (!Lh.Ainv.empty()) {
             CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
             H.bytes_per_cycle += 8ll * Ld.n * Ld.n;
@@ -147,18 +148,19 @@ static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, co
 {
     double scale;
     std::vector<double> om;
-    cheb_coefficients(p.lo * L.rho, p.hi * L.rho, p.nu, &scale, om);
+    const int nu = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;
+    cheb_coefficients(p.lo * L.rho, p.hi * L.rho, nu, &scale, om);
     // Where iterate p_k lives.  A step reads p_{k-1} through the gather (must not be the buffer
     // being written) and p_{k-2} element-wise (may be).  Zero guess: alternate x / t0 so that
     // p_nu lands in x.  Non-zero guess (p_0 = x): rotate x / t0 / t1 backwards from p_nu = x;
     // this never overwrites a buffer that is still gathered unless nu % 3 == 1, in which case
     // the iterates alternate t0 / x and one copy moves an odd-nu result back into x.
     double *buf3[3] = {x, L.t0, L.t1};
-    const bool rotate3 = !zero_guess && (p.nu % 3 != 1);
+    const bool rotate3 = !zero_guess && (nu % 3 != 1);
     auto where = [&](int k) -> double * {
         if (k == 0) return x;
-        if (zero_guess) return ((p.nu - k) & 1) ? L.t0 : x;
-        if (rotate3) return buf3[(p.nu - k) % 3];
+        if (zero_guess) return ((nu - k) & 1) ? L.t0 : x;
+        if (rotate3) return buf3[(nu - k) % 3];
         return (k & 1) ? L.t0 : x;
     };
     if (zero_guess) {
@@ -168,14 +170,14 @@ static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, co
         CTL_TRY(halo0(h, l, x));
         CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, where(1), 0.0, 1.0, scale));
     }
-    for (int k = 2; k <= p.nu; ++k) {
+    for (int k = 2; k <= nu; ++k) {
         const double w = om[k - 2];
         const bool no_prev = (k == 2 && zero_guess);
         CTL_TRY(halo0(h, l, where(k - 1)));
         CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, no_prev ? nullptr : where(k - 2), where(k - 1), where(k),
                                no_prev ? 0.0 : (1.0 - w), w, w * scale));
     }
-    if (where(p.nu) != x) CTL_TRY(vec_copy_n(h, x, where(p.nu), L.n));
+    if (where(nu) != x) CTL_TRY(vec_copy_n(h, x, where(nu), L.n));
     return CTL_OK;
 }
 

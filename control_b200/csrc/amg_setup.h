@@ -15,7 +15,8 @@ struct AmgParams {
     double theta_decay = 0.5;   // strength threshold on level l: theta * theta_decay^l
     int max_levels = 10;
     int coarse_max = 600;   // dense inverse below this size (one GEMV instead of two more levels of launches)
-    int nu = 3;
+    int nu = 3;          // smoother degree on levels >= 1
+    int nu_fine = 0;     // smoother degree on level 0 (0 = nu)
     double lo = 0.25, hi = 1.0;
     int cycles = 3;      // see oracle/amg.py::solve for why not the reference's 2
     double acc_lo = 0.0, acc_hi = 1.0;   // > 0: Chebyshev-accelerated cycles (oracle/amg.py::solve)

@@ -269,6 +269,7 @@ int ctl_pc_default_options(ctl_pc_options *o)
     o->cheb_steps = 20;                  // "ksp_max_it": 20, control/control.py:1980
     o->amg_cycles = d.cycles;            // stands in for "pc_hypre_boomeramg_max_iter": 2, control.py:2065
     o->amg_nu = d.nu;
+    o->amg_nu_fine = d.nu_fine;
     o->amg_max_levels = d.max_levels;
     o->amg_coarse_max = d.coarse_max;
     o->amg_theta = d.theta;
@@ -290,8 +291,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     if (opts->solver_0 == CTL_S0_CHEBYSHEV)
         CTL_CHECK(opts->cheb_emax > opts->cheb_emin && opts->cheb_emin > 0 && opts->cheb_steps >= 1, CTL_ERR_ARG,
                   "ctl_pc_setup: Chebyshev needs 0 < e_min < e_max and at least one step");
-    CTL_CHECK(opts->amg_cycles >= 1 && opts->amg_nu >= 1 && opts->amg_max_levels >= 1, CTL_ERR_ARG,
-              "ctl_pc_setup: bad AMG options");
+    CTL_CHECK(opts->amg_cycles >= 1 && opts->amg_nu >= 1 && opts->amg_nu_fine >= 0 && opts->amg_max_levels >= 1,
+              CTL_ERR_ARG, "ctl_pc_setup: bad AMG options");
     CTL_CHECK(opts->amg_acc_lo <= 0.0 || opts->amg_acc_hi > opts->amg_acc_lo, CTL_ERR_ARG,
               "ctl_pc_setup: AMG acceleration needs acc_lo < acc_hi");
     if (opts->mode == CTL_PCMODE_DIAGONAL)
@@ -307,6 +308,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     st.amg.max_levels = opts->amg_max_levels;
     st.amg.coarse_max = opts->amg_coarse_max;
     st.amg.nu = opts->amg_nu;
+    st.amg.nu_fine = opts->amg_nu_fine;
     st.amg.lo = opts->amg_lo;
     st.amg.hi = opts->amg_hi;
     st.amg.cycles = opts->amg_cycles;

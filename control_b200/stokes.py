@@ -109,7 +109,7 @@ class StokesSystem:
         names = (("cycles", "cycles"), ("nu", "nu"), ("max_levels", "max_levels"), ("coarse_max", "coarse_max"),
                  ("theta", "theta"), ("lo", "lo"), ("hi", "hi"))
         amg = dict(amg or {})
-        for key, field in names + (("acc_lo", "acc_lo"), ("acc_hi", "acc_hi")):
+        for key, field in names + (("nu_fine", "nu_fine"), ("acc_lo", "acc_lo"), ("acc_hi", "acc_hi")):
             if key in amg:
                 setattr(o.velocity, "amg_" + field, amg.pop(key))
         amg_p = dict(amg_p or {})

@@ -271,7 +271,8 @@ class MultiBlockSystem:
         else:
             o.solver_0 = L.CTL_S0_JACOBI
         o.cheb_steps = int(cheb_steps)
-        for key, field in (("cycles", "amg_cycles"), ("nu", "amg_nu"), ("max_levels", "amg_max_levels"),
+        for key, field in (("cycles", "amg_cycles"), ("nu", "amg_nu"), ("nu_fine", "amg_nu_fine"),
+                           ("max_levels", "amg_max_levels"),
                            ("coarse_max", "amg_coarse_max"), ("theta", "amg_theta"),
                            ("lo", "amg_lo"), ("hi", "amg_hi"), ("acc_lo", "amg_acc_lo"),
                            ("acc_hi", "amg_acc_hi")):

@@ -90,7 +90,8 @@ typedef struct {
     double cheb_emin, cheb_emax;   /* lambda_v_bounds                                      */
     int32_t cheb_steps;      /* ksp_max_it of solver_0: 20 (control/control.py:1980)       */
     int32_t amg_cycles;      /* V-cycles per inner solve (default 3; the reference: 2 of hypre) */
-    int32_t amg_nu;          /* Chebyshev smoother degree (pre = post)                     */
+    int32_t amg_nu;          /* Chebyshev smoother degree (pre = post) on levels >= 1      */
+    int32_t amg_nu_fine;     /* ... on the finest level (0 = amg_nu)                       */
     int32_t amg_max_levels;
     int32_t amg_coarse_max;  /* coarsest level solved with a dense inverse below this size */
     double amg_theta;        /* strength-of-connection threshold                           */

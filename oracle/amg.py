@@ -24,7 +24,7 @@ Algorithm (identical, step for step, in control_b200/csrc/amg_setup.cpp):
              operators by 30-50 %, which detunes both omega and the smoother interval: measured
              V-cycle energy contraction at 512^2 0.34 -> 0.17)
   coarse     A_c = P^T A P; stop at n <= coarse_max (dense inverse) or max_levels
-  smoother   Chebyshev (oracle/cheb.py) of degree nu on D^-1 A over [lo*rho, hi*rho]
+  smoother   Chebyshev (oracle/cheb.py) of degree nu (nu_fine on level 0) on D^-1 A over [lo*rho, hi*rho]
   cycle      V(nu, nu); ``solve`` = ``cycles`` V-cycles from a zero guess, optionally
              Chebyshev-accelerated over [acc_lo, acc_hi] (see ``solve``)
 """
@@ -42,7 +42,7 @@ except Exception:                          # pragma: no cover
         return f
 
 
-DEFAULTS = dict(theta=0.08, theta_decay=0.5, max_levels=10, coarse_max=600, nu=3, lo=0.25, hi=1.0, cycles=3,
+DEFAULTS = dict(theta=0.08, theta_decay=0.5, max_levels=10, coarse_max=600, nu=3, nu_fine=0, lo=0.25, hi=1.0, cycles=3,
                 acc_lo=0.0, acc_hi=1.0, coarse="inverse")
 
 
@@ -226,15 +226,16 @@ def vcycle(H, lvl, b, x=None):
     """One V(nu, nu) cycle on level ``lvl``; ``x`` None means zero initial guess."""
     L = H.levels[lvl]
     p = H.params
+    nu = p["nu_fine"] if (lvl == 0 and p["nu_fine"] > 0) else p["nu"]
     if lvl == len(H.levels) - 1:
         if L.Ainv is not None:
             return L.Ainv @ b
-        return chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
-    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
+        return chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, nu, x)
+    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, nu, x)
     r = b - mv(L.A, x)
     xc = vcycle(H, lvl + 1, mv(L.R, r), None)
     x = x + mv(L.P, xc)
-    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, p["nu"], x)
+    x = chebyshev(L.A, L.dinv, b, p["lo"] * L.rho, p["hi"] * L.rho, nu, x)
     return x
 
 

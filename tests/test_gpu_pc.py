@@ -306,6 +306,26 @@ def test_accelerated_amg_solve_matches_oracle():
     s.close()
 
 
+@pytest.mark.parametrize("params", [dict(nu=3, nu_fine=2, cycles=2, coarse_max=50),
+                                    dict(nu=2, nu_fine=4, cycles=1, coarse_max=50),
+                                    dict(nu=4, nu_fine=1, cycles=3, coarse_max=50)])
+def test_amg_with_separate_fine_level_degree(params):
+    """nu_fine: smoother degree on level 0 differs from the coarse levels (buffer rotation of the
+    smoother depends on the degree)."""
+    q = kat.heat_problem(40, 6, True)
+    s = _system(q, True)
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], **params)
+    c = 0.5 * s.tau / q["beta"] ** 0.5
+    A = fem.assemble_bc((0.5 * s.tau * q["K"] + (1 + c) * q["M"]).tocsr(), q["bdofs"])
+    H = oamg.setup(A, **params)
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(A.shape[0])
+    b[q["bdofs"]] = 0.0
+    x = s.amg_solve(torch.from_numpy(b).to(s.device)).cpu().numpy()
+    assert _rel(x, oamg.solve(H, b)) < 1e-11
+    s.close()
+
+
 @pytest.mark.parametrize("CN,n_t", [(True, 81), (False, 70), (True, 140)])
 def test_many_time_blocks_pc_and_solve(CN, n_t):
     """N > 64: batched preconditioner kernels with 4 / 8 columns per lane, full solve."""
