@@ -37,7 +37,14 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_cs
     pat->n_cols = A.n_cols;
     pat->nnz = A.nnz();
     out.pat = pat;
-    out.lanes = mean <= 6.0 ? 4 : (mean <= 16.0 ? 8 : (mean <= 48.0 ? 16 : 32));
+    // lanes per row: about a quarter of the mean row length.  Measured at C2 (inner solve, warm): 8 lanes
+    // for the 13-entry rows of level 1 = 0.918 ms, 16 lanes = 1.189 ms, 4 lanes = 0.843 ms: the narrow
+    // groups keep four times as many rows in flight, which is what these latency-bound kernels need.
+    out.lanes = mean <= 16.0 ? 4 : (mean <= 48.0 ? 8 : 16);
+    if (const char *e = getenv("CTL_CSR_LANES_SHIFT")) {          // experiment: wider / narrower row groups
+        const int sh = atoi(e);
+        out.lanes = std::max(2, std::min(32, sh >= 0 ? out.lanes << sh : out.lanes >> (-sh)));
+    }
     CTL_TRY(ctl_upload(h, &out.csr_ptr, A.indptr.data(), A.indptr.size()));
     CTL_TRY(ctl_upload(h, &out.csr_cols, A.indices.data(), A.indices.size()));
     CTL_TRY(ctl_upload(h, &out.csr_vals, A.values.data(), A.values.size()));
@@ -295,7 +302,8 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, con
     const int blocks = ceil_div(p.n_rows, ST);
     if (blocks == 0) return CTL_OK;
     if (A.lanes) {
-        if (A.lanes == 4) launch_csrv_spmv<4>(h, A, x, y, b, mode);
+        if (A.lanes == 2) launch_csrv_spmv<2>(h, A, x, y, b, mode);
+        else if (A.lanes == 4) launch_csrv_spmv<4>(h, A, x, y, b, mode);
         else if (A.lanes == 8) launch_csrv_spmv<8>(h, A, x, y, b, mode);
         else if (A.lanes == 16) launch_csrv_spmv<16>(h, A, x, y, b, mode);
         else launch_csrv_spmv<32>(h, A, x, y, b, mode);
@@ -332,7 +340,9 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
     if (blocks == 0) return CTL_OK;
     if (A.lanes) {
         const int n = p.n_rows;
-        if (A.lanes == 4)
+        if (A.lanes == 2)
+            pdl_launch(h, ceil_div((int64_t)n * 2, ST), ST, csrv_cheb_kernel<2>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
+        else if (A.lanes == 4)
             pdl_launch(h, ceil_div((int64_t)n * 4, ST), ST, csrv_cheb_kernel<4>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
         else if (A.lanes == 8)
             pdl_launch(h, ceil_div((int64_t)n * 8, ST), ST, csrv_cheb_kernel<8>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
@@ -451,6 +461,7 @@ __device__ __forceinline__ void fused_execute(const FusedOp &op, int gtid, int g
         }
     } else {
         switch (op.lanes) {
+        case 2: fused_rows<2>(op, gtid, gthreads); break;
         case 4: fused_rows<4>(op, gtid, gthreads); break;
         case 8: fused_rows<8>(op, gtid, gthreads); break;
         case 16: fused_rows<16>(op, gtid, gthreads); break;
