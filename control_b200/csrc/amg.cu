@@ -11,7 +11,16 @@
 #include "cheb_coefficients.h"
 
 // levels >= FUSED_FROM of a V-cycle run as one cooperative kernel (sell.cu: fused coarse tail)
-static constexpr int FUSED_FROM = 2;
+static int fused_from_level()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("CTL_FUSED_FROM");
+        v = e ? std::max(1, atoi(e)) : 2;
+    }
+    return v;
+}
+#define FUSED_FROM fused_from_level()
 
 static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
 {
