@@ -22,7 +22,10 @@ import this package, and only as the checker / CPU baseline.  The product
 
 Parity status: the operator, T-transforms, nullspace projections and RHS are pinned by
 re-creating the reference's analytic known-answer tests
-(test/test_control.py:1243-1444 BE, 1447-1655 CN).  Iteration counts, preconditioner
+(test/test_control.py:1243-1444 BE, 1447-1655 CN); the N = 1 block structure by
+test/test_control.py:26-119, and the Stokes divergence coupling, block ordering and
+ConstantNullspace (``oracle/stokes.py::stokes_apply_literal``) by test/test_control.py:232-358,
+all four to the reference's own 1e-13.  Iteration counts, preconditioner
 outputs and residual histories of the real Firedrake/PETSc/hypre stack are **parity
 unpinned** (the reference ships no golden vectors and cannot run in this image;
 BoomerAMG is replaced by the aggregation AMG in ``amg``).

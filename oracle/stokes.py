@@ -10,6 +10,10 @@ on assembled matrices (oracle; test infrastructure only).
 
 Unknowns: ``x_0`` = (2N, n_v) blocks [v | zeta], ``x_1`` = (2N, n_p) blocks [mu | p] (the first
 N pressure blocks multiply B^T in the adjoint-equation rows, control/control.py:3765-3766).
+Pinned: ``stokes_apply_literal`` and ``ConstantNullspace`` reproduce the reference's Stokes
+known-answer test (test/test_control.py:232-358, the stationary system = the same block structure
+with N = 1 and tau = 1) to 1e-13 (tests/test_oracle.py); the fused form equals the literal one to
+rounding.  Unpinned: everything the real PETSc/hypre stack decides (iteration counts, histories).
 The inner solves on ``K_p`` are six cycles of the stand-in AMG (ONE hypre BoomerAMG cycle in the
 reference, control/control.py:4300-4309): parity with hypre is unpinned, as for the heat path.
 """

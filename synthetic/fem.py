@@ -300,3 +300,71 @@ def assemble_taylor_hood_2d(nx, ny, lx=1.0, ly=1.0):
     bd_v = np.sort(np.concatenate([2 * bn, 2 * bn + 1])).astype(np.int32)
     return dict(M_v=M_v, K_v=K_v, B=B, M_p=M_p, K_p=K_p, bdofs_v=bd_v, coords_v=coords2, coords_p=coords1,
                 M_scalar=Msc, K_scalar=Ksc)
+
+
+def _p1_1d(nel, length):
+    """1-D P1 mass/stiffness on a uniform mesh."""
+    h = length / nel
+    Me = h / 6.0 * np.array([[2.0, 1.0], [1.0, 2.0]])
+    Ke = 1.0 / h * np.array([[1.0, -1.0], [-1.0, 1.0]])
+    n = nel + 1
+    M = sp.lil_matrix((n, n))
+    K = sp.lil_matrix((n, n))
+    for e in range(nel):
+        idx = np.arange(e, e + 2)
+        M[np.ix_(idx, idx)] += Me
+        K[np.ix_(idx, idx)] += Ke
+    return M.tocsr(), K.tocsr()
+
+
+def _p1_p2_1d(nel, length):
+    """1-D mixed matrices between P1 (rows) and P2 (columns) on the same uniform mesh:
+    G[c, a] = int psi_c phi_a dx, D[c, a] = int psi_c phi_a' dx (exact: 3-point Gauss)."""
+    h = length / nel
+    gp = 0.5 + 0.5 * np.array([-np.sqrt(0.6), 0.0, np.sqrt(0.6)])      # points on (0, 1)
+    gw = 0.5 * np.array([5.0 / 9.0, 8.0 / 9.0, 5.0 / 9.0])
+    psi = np.stack([1.0 - gp, gp])                                      # P1 on the reference interval
+    phi = np.stack([(1.0 - gp) * (1.0 - 2.0 * gp), 4.0 * gp * (1.0 - gp), gp * (2.0 * gp - 1.0)])
+    dphi = np.stack([4.0 * gp - 3.0, 4.0 - 8.0 * gp, 4.0 * gp - 1.0])  # d/ds
+    Ge = h * np.einsum("q,cq,aq->ca", gw, psi, phi)
+    De = np.einsum("q,cq,aq->ca", gw, psi, dphi)                        # h * (1/h)
+    G = sp.lil_matrix((nel + 1, 2 * nel + 1))
+    D = sp.lil_matrix((nel + 1, 2 * nel + 1))
+    for e in range(nel):
+        G[np.ix_(np.arange(e, e + 2), np.arange(2 * e, 2 * e + 3))] += Ge
+        D[np.ix_(np.arange(e, e + 2), np.arange(2 * e, 2 * e + 3))] += De
+    return G.tocsr(), D.tocsr()
+
+
+def assemble_q2q1_stokes_2d(nx, ny, lx=1.0, ly=1.0):
+    """Vector Q2 - Q1 on a uniform quadrilateral mesh: the spaces of the reference's Stokes
+    known-answer test (test/test_control.py:232-240).  Velocity dofs interleaved by component
+    (dof = 2 node + comp).  Returns a dict with M_v, L_v (vector mass / vector Laplacian), B
+    (n_p x n_v, ``-inner(div(trial_v), test_p) * dx``), M_p, L_p, the velocity boundary dofs and the
+    node coordinates of both spaces."""
+    M_s, L_s, coords_v, bd_nodes = assemble_q2_2d(nx, ny, lx, ly)
+    I2 = sp.identity(2, format="csr")
+    M_v = sp.kron(M_s, I2, format="csr")
+    L_v = sp.kron(L_s, I2, format="csr")
+    for A in (M_v, L_v):
+        A.sort_indices()
+    Mx1, Kx1 = _p1_1d(nx, lx)
+    My1, Ky1 = _p1_1d(ny, ly)
+    M_p = sp.kron(My1, Mx1, format="csr")
+    L_p = (sp.kron(My1, Kx1) + sp.kron(Ky1, Mx1)).tocsr()
+    Gx, Dx = _p1_p2_1d(nx, lx)
+    Gy, Dy = _p1_p2_1d(ny, ly)
+    Bx = -sp.kron(Gy, Dx, format="csr")            # -int d_x(phi) psi
+    By = -sp.kron(Dy, Gx, format="csr")            # -int d_y(phi) psi
+    n_p, n_s = Bx.shape
+    B = sp.lil_matrix((n_p, 2 * n_s))
+    B[:, 0::2] = Bx
+    B[:, 1::2] = By
+    B = B.tocsr()
+    B.sort_indices()
+    xs = np.linspace(0.0, lx, nx + 1)
+    ys = np.linspace(0.0, ly, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="xy")
+    coords_p = np.stack([X.ravel(), Y.ravel()], axis=1)
+    bdofs_v = np.sort(np.concatenate([2 * bd_nodes, 2 * bd_nodes + 1])).astype(np.int32)
+    return dict(M_v=M_v, L_v=L_v, B=B, M_p=M_p, L_p=L_p, bdofs_v=bdofs_v, coords_v=coords_v, coords_p=coords_p)

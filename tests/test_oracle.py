@@ -386,3 +386,88 @@ def test_stokes_control_driver_gives_divergence_free_state():
     assert np.abs(div).max() < 1e-7
     assert np.abs(p.mean(axis=1)).max() < 1e-12 and np.abs(mu.mean(axis=1)).max() < 1e-12
     assert np.abs(v[:, q["bdofs"]]).max() == 0.0
+
+
+def _dense_operator(apply, shapes):
+    """Matrix of a linear map on a pair of block arrays, column by column."""
+    (r0, c0), (r1, c1) = shapes
+    n = r0 * c0 + r1 * c1
+    A = np.zeros((n, n))
+    for k in range(n):
+        e = np.zeros(n)
+        e[k] = 1.0
+        y0, y1 = apply(e[:r0 * c0].reshape(r0, c0), e[r0 * c0:].reshape(r1, c1))
+        A[:, k] = np.concatenate([y0.ravel(), y1.ravel()])
+    return A
+
+
+def test_reference_stationary_known_answer():
+    """test/test_control.py:26-119 (``test_stationary_linear_control``): the N = 1 block system
+    [[M, K^T], [K, -M/beta]] (control/control.py:546-560), Q2 on 8x8 quads, no boundary conditions,
+    right-hand sides built from interpolated v_ref / zeta_ref; the reference asserts 1e-13."""
+    M, L, coords, _ = fem.assemble_q2_2d(8, 8)
+    K = (L + M).tocsr()                       # forw_diff_operator = grad-grad + mass (33-35)
+    beta = 1e-3
+    X0, X1 = coords[:, 0], coords[:, 1]
+    v_ref = X0 * np.exp(X1)
+    zeta_ref = np.sin(np.pi * X0) * np.sin(2.0 * np.pi * X1)
+    b_0 = M @ v_ref + K @ zeta_ref            # 81-84
+    b_1 = K @ v_ref - (1.0 / beta) * (M @ zeta_ref)        # 85-88
+    blocks = ({(0, 0): M}, {(0, 0): K.T.tocsr()}, {(0, 0): K}, {(0, 0): (-(1.0 / beta) * M).tocsr()})
+    ns = kkt.DirichletBCNullspace(np.zeros(0, dtype=np.int64))
+    n = M.shape[0]
+    A = _dense_operator(lambda x0, x1: kkt.kkt_apply_literal(blocks, ns, False, x0, x1), ((1, n), (1, n)))
+    x = np.linalg.solve(A, np.concatenate([b_0, b_1]))
+    assert kat.l2_error(M, x[None, :n], v_ref[None]) < 1e-13          # the reference's own bound (measured 1.8e-14)
+    assert kat.l2_error(M, x[None, n:], zeta_ref[None]) < 1e-13
+
+
+def test_reference_stationary_stokes_known_answer():
+    """test/test_control.py:232-358 (``test_stationary_incompressible_linear_control``): pins the
+    divergence coupling and ConstantNullspace of the Stokes block system.  The stationary system
+    (control/control.py:896-925) has the block structure of the instationary one with N = 1 and no
+    time scaling, so it runs through the SAME literal operator (oracle/stokes.py) that anchors the
+    instationary Stokes path: B orientation and sign, the [v | zeta] / [mu | p] ordering, block_01 =
+    diag(B^T), block_10 = diag(B), Dirichlet and constant nullspaces.  Vector Q2 - Q1 on 4x4 quads."""
+    from oracle import stokes
+    sq = fem.assemble_q2q1_stokes_2d(4, 4)
+    M, L, B, Mp, bd = sq["M_v"], sq["L_v"], sq["B"], sq["M_p"], sq["bdofs_v"]
+    K = (L + M).tocsr()
+    beta = 1e-3
+    x, y = sq["coords_v"][:, 0], sq["coords_v"][:, 1]
+    px, py = sq["coords_p"][:, 0], sq["coords_p"][:, 1]
+
+    def vec(cx, cy):
+        a = np.zeros(M.shape[0])
+        a[0::2], a[1::2] = cx, cy
+        return a
+    v_ref = vec(x * np.exp(y) * np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    zeta_ref = vec(np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    p_ref = np.sin(np.pi * px) * np.sin(2.0 * np.pi * py)
+    mu_ref = px * np.exp(py)
+    b_0 = M @ v_ref + K @ zeta_ref + B.T @ mu_ref                          # 293-296
+    b_1 = K @ v_ref - (1.0 / beta) * (M @ zeta_ref) + B.T @ p_ref           # 297-300
+    b_2 = B @ v_ref                                                         # 301
+    b_3 = B @ zeta_ref                                                      # 302
+    heat_blocks = ({(0, 0): M}, {(0, 0): K.T.tocsr()}, {(0, 0): K}, {(0, 0): (-(1.0 / beta) * M).tocsr()})
+    ns_v, ns_p = kkt.DirichletBCNullspace(bd), stokes.ConstantNullspace()
+    n_v, n_p = M.shape[0], Mp.shape[0]
+    A = _dense_operator(lambda x0, x1: stokes.stokes_apply_literal(heat_blocks, B, 1.0, 1, False, ns_v, ns_p, x0, x1),
+                        ((2, n_v), (2, n_p)))
+    # MultiBlockSystem.solve: project the right-hand side, solve, project the solution
+    c0 = np.stack([b_0, b_1])
+    c1 = np.stack([b_2, b_3])
+    ns_v.project(c0)
+    ns_p.project(c1)
+    sol = np.linalg.solve(A, np.concatenate([c0.ravel(), c1.ravel()]))
+    u0 = sol[:2 * n_v].reshape(2, n_v)
+    u1 = sol[2 * n_v:].reshape(2, n_p)
+    ns_v.project(u0)
+    ns_p.project(u1)
+    assert kat.l2_error(M, u0[:1], v_ref[None]) < 1e-13       # the reference's own bounds (measured 5e-15, 4e-16,
+    assert kat.l2_error(M, u0[1:], zeta_ref[None]) < 1e-13    # 6e-14, 5e-15)
+
+    def shift(q):                                             # 334-347: subtract assemble(q * dx) from every dof
+        return q - np.ones(n_p) @ (Mp @ q)
+    assert kat.l2_error(Mp, shift(u1[1])[None], shift(p_ref)[None]) < 1e-13
+    assert kat.l2_error(Mp, shift(u1[0])[None], shift(mu_ref)[None]) < 1e-13
