@@ -261,11 +261,13 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
 
 def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, v_d, f,
                                 v_0=None, div_v=None, div_zeta=None, solver_parameters=None, lambda_v_bounds=None,
-                                lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None):
+                                lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None,
+                                check_v_d=True, check_f=True):
     """``Control.Instationary.incompressible_linear_solve`` for homogeneous Dirichlet velocity data
     (control/control.py:3592-4725): right-hand sides (3961-4243; the velocity rows are those of
     the heat problem, the pressure rows are zero unless div_v / div_zeta are given), outer solve,
-    unpacking (4705-4725).  ``v_d``, ``f``: (n_t, n_v) cofunction values.  Returns
+    unpacking (4705-4725).  ``v_d``, ``f``: (n_t, n_v) cofunction values, or ready (N, n_v) blocks
+    when check_v_d / check_f are False (the ``v_d=`` / ``f=`` keywords of the reference).  Returns
     (v, zeta, p, mu, KSPResult) with v, zeta of n_t levels and p, mu of N levels."""
     t_0, T_f = time_interval
     tau = (T_f - t_0) / (n_t - 1.0)
@@ -273,7 +275,7 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
     n_v, n_p = M_v.shape[0], M_p.shape[0]
     if v_0 is None:
         v_0 = np.zeros(n_v)
-    b_0_0, b_0_1 = kkt.build_rhs(M_v, K_v, tau, n_t, CN, bdofs_v, v_d, f, v_0)
+    b_0_0, b_0_1 = kkt.build_rhs(M_v, K_v, tau, n_t, CN, bdofs_v, v_d, f, v_0, check_v_d=check_v_d, check_f=check_f)
     b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)
     b_1_1 = np.zeros((N, n_p)) if div_zeta is None else np.array(div_zeta, dtype=float)
     if CN:                                                         # 4233-4234
@@ -287,7 +289,8 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
     if CN:
         v = np.zeros((n_t, n_v))
         zeta = np.zeros((n_t, n_v))
-        v[0] = v_0
+        if check_v_d and check_f:
+            v[0] = v_0
         v[1:] = u_0[:N]
         zeta[:-1] = u_0[N:]
     else:

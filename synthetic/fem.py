@@ -350,8 +350,14 @@ def assemble_q2q1_stokes_2d(nx, ny, lx=1.0, ly=1.0):
         A.sort_indices()
     Mx1, Kx1 = _p1_1d(nx, lx)
     My1, Ky1 = _p1_1d(ny, ly)
-    M_p = sp.kron(My1, Mx1, format="csr")
-    L_p = (sp.kron(My1, Kx1) + sp.kron(Ky1, Mx1)).tocsr()
+    MM = sp.kron(My1, Mx1, format="coo")           # one shared pattern, explicit zeros kept (as assemble_q2_2d)
+    KM = sp.kron(My1, Kx1, format="coo")
+    MK = sp.kron(Ky1, Mx1, format="coo")
+    rows = np.concatenate([MM.row, KM.row, MK.row]).astype(np.int64)
+    cols = np.concatenate([MM.col, KM.col, MK.col]).astype(np.int64)
+    M_p, L_p = _csr_same_pattern(MM.shape[0], rows, cols,
+                                 [np.concatenate([MM.data, np.zeros(KM.nnz + MK.nnz)]),
+                                  np.concatenate([np.zeros(MM.nnz), KM.data, MK.data])])
     Gx, Dx = _p1_p2_1d(nx, lx)
     Gy, Dy = _p1_p2_1d(ny, ly)
     Bx = -sp.kron(Gy, Dx, format="csr")            # -int d_x(phi) psi

@@ -14,15 +14,10 @@ from synthetic import fem
 from synthetic.problems import heat_problem, heat_problem_3d, stokes_problem  # noqa: F401
 
 
-def instationary_kat(CN, mesh_size=3):
-    nx = 2 ** mesh_size
-    M, K, coords, bdofs = fem.assemble_q2_2d(nx, nx)
-    X0, X1 = coords[:, 0], coords[:, 1]
-    beta = 1e-3
-    n_t = 5
-    tau = 0.25
+def _kat_fields(X0, X1, tau, n_t=5):
+    """v_ref / zeta_ref of test/test_control.py:1263-1330 (BE) = 1467-1534 (CN) at the nodes."""
     pi, sin, exp = np.pi, np.sin, np.exp
-    n = M.shape[0]
+    n = X0.size
     v_ref = np.zeros((n_t, n))
     zeta_ref = np.zeros((n_t, n))
     v_ref[1] = tau * sin(3.0 * pi * X0) * sin(4.0 * pi * X1)
@@ -33,6 +28,13 @@ def instationary_kat(CN, mesh_size=3):
     zeta_ref[1] = tau * sin(3.0 * pi * X0) * sin(4.0 * pi * X1)
     zeta_ref[2] = tau ** 2.0 * sin(pi * X0) * sin(2.0 * pi * X1)
     zeta_ref[3] = tau ** 3.0 * sin(3.0 * pi * X0) * sin(4.0 * pi * X1)
+    return v_ref, zeta_ref
+
+
+def _kat_rows(M, K, v_ref, zeta_ref, CN, tau, beta):
+    """Untransformed right-hand-side rows built from the block stencils, exactly as the reference's
+    tests write them (test/test_control.py:1331-1408 BE, 1538-1620 CN)."""
+    n_t, n = v_ref.shape
     if not CN:
         N = n_t
         b_0 = np.zeros((N, n))
@@ -57,14 +59,27 @@ def instationary_kat(CN, mesh_size=3):
             b_0[i] = h * (M @ v_ref[i + 1]) + h * (M @ v_ref[i]) + h * (K @ zeta_ref[i]) \
                 + M @ zeta_ref[i] + h * (K @ zeta_ref[i + 1]) - M @ zeta_ref[i + 1]
         b_0[3] = h * (M @ v_ref[4]) + h * (M @ v_ref[3]) + h * (K @ zeta_ref[3]) + M @ zeta_ref[3]
-        # 1582-1620 (line 1613 assigns zeta_ref.sub(3), which equals v_ref.sub(3))
+        # 1582-1620
         b_1[0] = h * (K @ v_ref[1]) + M @ v_ref[1] - (h / beta) * (M @ zeta_ref[0]) \
             - (h / beta) * (M @ zeta_ref[1])
         for i in (1, 2):
             b_1[i] = h * (K @ v_ref[i + 1]) + M @ v_ref[i + 1] + h * (K @ v_ref[i]) \
                 - M @ v_ref[i] - (h / beta) * (M @ zeta_ref[i]) - (h / beta) * (M @ zeta_ref[i + 1])
-        b_1[3] = h * (K @ v_ref[4]) + M @ v_ref[4] + h * (K @ zeta_ref[3]) - M @ zeta_ref[3] \
+        # (the reference's line 1613 writes zeta_ref.sub(3) in the two middle terms; its fields have
+        # v_ref.sub(3) == zeta_ref.sub(3), and the block stencil is the one with v_ref)
+        b_1[3] = h * (K @ v_ref[4]) + M @ v_ref[4] + h * (K @ v_ref[3]) - M @ v_ref[3] \
             - (h / beta) * (M @ zeta_ref[3])
+    return b_0, b_1
+
+
+def instationary_kat(CN, mesh_size=3):
+    nx = 2 ** mesh_size
+    M, K, coords, bdofs = fem.assemble_q2_2d(nx, nx)
+    beta = 1e-3
+    n_t = 5
+    tau = 0.25
+    v_ref, zeta_ref = _kat_fields(coords[:, 0], coords[:, 1], tau, n_t)
+    b_0, b_1 = _kat_rows(M, K, v_ref, zeta_ref, CN, tau, beta)
     solver_parameters = {"linear_solver": "fgmres",            # 1418-1423 / 1629-1634
                          "fgmres_restart": 10,
                          "maximum_iterations": 500,
@@ -81,3 +96,43 @@ def l2_error(M, a, b):
     test/test_control.py:1438-1444 (mixed-space inner product = sum over blocks)."""
     d = a - b
     return float(np.sqrt(abs(sum(di @ (M @ di) for di in d))))
+
+
+def instationary_stokes_kat(CN, nx=4, beta=1e-2):
+    """A known-answer problem for the instationary Stokes system in the style of the reference's own
+    KATs (it ships none with assertions for this system: test/test_control.py:3045-3302 only run):
+    vector Q2 - Q1 on nx x nx quads of the unit square (the spaces of test/test_control.py:232-240),
+    n_t = 5, tau = 0.25, the analytic v_ref / zeta_ref of the heat KATs in both components, analytic
+    p_ref / mu_ref per time block, and right-hand sides built ROW BY ROW from the block stencils
+    (velocity rows: ``_kat_rows`` + tau B^T mu_i / tau B^T p_i; pressure rows tau B v_i / tau B zeta_i,
+    control/control.py:3750-3769), handed over as ready blocks (v_d=, f=, div_v=, div_zeta=), which
+    ``incompressible_linear_solve`` T-transforms itself (control/control.py:4230-4234)."""
+    sq = fem.assemble_q2q1_stokes_2d(nx, nx)
+    M, K, B, bd = sq["M_v"], sq["L_v"], sq["B"], sq["bdofs_v"]
+    n_t, tau = 5, 0.25
+    N = n_t - 1 if CN else n_t
+    x, y = sq["coords_v"][:, 0], sq["coords_v"][:, 1]
+    px, py = sq["coords_p"][:, 0], sq["coords_p"][:, 1]
+    va, za = _kat_fields(x, y, tau, n_t)
+    v_ref = np.zeros((n_t, M.shape[0]))
+    zeta_ref = np.zeros((n_t, M.shape[0]))
+    v_ref[:, 0::2], v_ref[:, 1::2] = va, 0.5 * za[::-1]          # second component: another mix of the same fields,
+    v_ref[0] = 0.0                                                # zero initial condition as in the heat KATs
+    zeta_ref[:, 0::2], zeta_ref[:, 1::2] = za, 0.5 * va[::-1]
+    if CN:
+        zeta_ref[n_t - 1] = 0.0                                   # CN unknowns: v_1..v_N, zeta_0..zeta_{N-1}
+    b_0, b_1 = _kat_rows(M, K, v_ref, zeta_ref, CN, tau, beta)
+    p_ref = np.stack([tau ** i * np.sin(np.pi * px) * np.sin(2.0 * np.pi * py) for i in range(N)])
+    mu_ref = np.stack([tau ** i * px * np.exp(py) for i in range(N)])
+    v_unknown = v_ref[1:] if CN else v_ref                        # unknown block i of the state
+    z_unknown = zeta_ref[:-1] if CN else zeta_ref
+    b_0 = b_0 + tau * (B.T @ mu_ref.T).T                          # block_01[(i, i)] = tau B^T on the first N rows
+    b_1 = b_1 + tau * (B.T @ p_ref.T).T
+    div_v = tau * (B @ v_unknown.T).T                             # block_10[(i, i)] = tau B
+    div_zeta = tau * (B @ z_unknown.T).T
+    solver_parameters = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 500,
+                         "relative_tolerance": 1.0e-13, "absolute_tolerance": 1.0e-14}
+    return dict(sq=sq, M=M, K=K, B=B, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN, N=N, v_ref=v_ref, zeta_ref=zeta_ref,
+                p_ref=p_ref, mu_ref=mu_ref, v_unknown=v_unknown, z_unknown=z_unknown, v_d=b_0, f=b_1, div_v=div_v,
+                div_zeta=div_zeta, lambda_v_bounds=(0.25, 1.5625), lambda_p_bounds=(0.25, 2.25),
+                solver_parameters=solver_parameters)

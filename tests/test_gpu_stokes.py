@@ -181,3 +181,34 @@ def test_control_incompressible_linear_solve_matches_oracle(CN):
     div -= div.mean(axis=1, keepdims=True)
     assert np.abs(div).max() < 1e-6 * np.abs(th["B"]).sum(axis=1).max() * np.abs(c._v).max()
     c.close()
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_instationary_stokes_known_answer_on_gpu(CN):
+    """The reference-style known-answer problem (tests/kat.py::instationary_stokes_kat: right-hand
+    sides built row by row from the block stencils, analytic v / zeta / p / mu) through the CUDA path:
+    Control.Instationary.incompressible_linear_solve with ready blocks (v_d=, f=, div_v=, div_zeta=)."""
+    import kat
+    from control_b200 import Control
+    q = kat.instationary_stokes_kat(CN)
+    sq = q["sq"]
+    c = Control.Instationary(q["M"], q["K"], beta=q["beta"], CN=CN, n_t=q["n_t"], time_interval=(0.0, 1.0),
+                             bc_dofs=q["bdofs"])
+    info = c.incompressible_linear_solve("constant", space_p=dict(B=q["B"], M_p=sq["M_p"], K_p=sq["L_p"]),
+                                         solver_parameters=q["solver_parameters"], v_d=q["v_d"], f=q["f"],
+                                         div_v=q["div_v"], div_zeta=q["div_zeta"],
+                                         lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    assert info.reason > 0
+    v_u = c._v[1:] if CN else c._v
+    z_u = c._zeta[:-1] if CN else c._zeta
+    scale = kat.l2_error(q["M"], q["v_unknown"], 0 * q["v_unknown"])
+    assert kat.l2_error(q["M"], v_u, q["v_unknown"]) < 1e-9 * scale        # solver tolerance 1e-13 x conditioning
+    assert kat.l2_error(q["M"], z_u, q["z_unknown"]) < 1e-9 * scale
+    Mp = sq["M_p"]
+
+    def shift(a):
+        return a - (a @ (Mp @ np.ones(Mp.shape[0])))[:, None]
+    pscale = kat.l2_error(Mp, shift(q["p_ref"]), 0 * q["p_ref"])
+    assert kat.l2_error(Mp, shift(c._p), shift(q["p_ref"])) < 1e-8 * pscale
+    assert kat.l2_error(Mp, shift(c._mu), shift(q["mu_ref"])) < 1e-8 * pscale
+    c.close()

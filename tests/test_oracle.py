@@ -471,3 +471,32 @@ def test_reference_stationary_stokes_known_answer():
         return q - np.ones(n_p) @ (Mp @ q)
     assert kat.l2_error(Mp, shift(u1[1])[None], shift(p_ref)[None]) < 1e-13
     assert kat.l2_error(Mp, shift(u1[0])[None], shift(mu_ref)[None]) < 1e-13
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_instationary_stokes_known_answer(CN):
+    """Reference-style KAT for the instationary Stokes system (tests/kat.py::instationary_stokes_kat):
+    right-hand sides built row by row from the block stencils, solved through the oracle's driver,
+    compared with the analytic fields."""
+    from oracle import stokes
+    q = kat.instationary_stokes_kat(CN)
+    sq = q["sq"]
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        q["M"], q["K"], q["B"], sq["M_p"], sq["L_p"], beta=q["beta"], n_t=q["n_t"], CN=CN, bdofs_v=q["bdofs"],
+        v_d=q["v_d"], f=q["f"], div_v=q["div_v"], div_zeta=q["div_zeta"], check_v_d=False, check_f=False,
+        solver_parameters=q["solver_parameters"], lambda_v_bounds=q["lambda_v_bounds"],
+        lambda_p_bounds=q["lambda_p_bounds"], inner="exact")
+    assert res.reason > 0
+    N = q["N"]
+    v_u = v[1:] if CN else v
+    z_u = zeta[:-1] if CN else zeta
+    scale = kat.l2_error(q["M"], q["v_unknown"], 0 * q["v_unknown"])
+    assert kat.l2_error(q["M"], v_u, q["v_unknown"]) < 1e-9 * scale        # solver tolerance 1e-13 x conditioning
+    assert kat.l2_error(q["M"], z_u, q["z_unknown"]) < 1e-9 * scale
+    Mp = sq["M_p"]
+
+    def shift(a):
+        return a - (a @ (Mp @ np.ones(Mp.shape[0])))[:, None]
+    pscale = kat.l2_error(Mp, shift(q["p_ref"]), 0 * q["p_ref"])
+    assert kat.l2_error(Mp, shift(p), shift(q["p_ref"])) < 1e-8 * pscale
+    assert kat.l2_error(Mp, shift(mu), shift(q["mu_ref"])) < 1e-8 * pscale
