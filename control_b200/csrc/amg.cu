@@ -36,7 +36,7 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
 {
     H.params = p;
     try {
-        amg_setup_host(A0, p, H.host);
+        if (H.host.empty()) amg_setup_host(A0, p, H.host);      // else: set up earlier (pc.cu builds many in parallel)
     } catch (const std::exception &e) {
         ctl_set_error(h, e.what());
         return CTL_ERR_STATE;

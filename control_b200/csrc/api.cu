@@ -147,6 +147,7 @@ int ctl_set_pattern(ctl_handle h, const int32_t *indptr, const int32_t *indices,
         }
     }
     h->h_indptr.assign(indptr, indptr + h->n + 1);
+    h->h_tperm.clear();
     h->h_indices.assign(indices, indices + nnz);
     h->h_M.clear();
     h->h_K.clear();

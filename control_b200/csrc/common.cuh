@@ -68,6 +68,7 @@ struct ctl_handle_s {
     std::vector<std::vector<double>> h_K;     // 1 (all levels) or n_t value arrays
     std::vector<std::vector<double>> h_KT;    // optional, same shape as h_K
     std::vector<int> h_bc;
+    std::vector<int> h_tperm;                 // global entry (r,c) -> entry index of (c,r); built on demand (pc.cu)
     std::vector<uint8_t> h_bcmask;            // global rows
 
     // local (this rank's rows) CSR in local column numbering: owned columns first, ghosts after

@@ -14,9 +14,11 @@
 //           are replayed from ONE CUDA graph (about 70 small kernels per time step).
 #include "pc.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "cheb_coefficients.h"
 #include "vec_ops.cuh"
@@ -45,6 +47,7 @@ void combine_global(ctl_handle_s *h, int level, bool transposed, double w, doubl
             if (w != 0.0) {
                 if (!transposed) kv = Kv[k];
                 else if (KTv) kv = (*KTv)[k];
+                else if (!h->h_tperm.empty()) kv = Kv[h->h_tperm[k]];
                 else {
                     // entry (c, r) of the structurally symmetric pattern
                     const int *b = ix.data() + ip[c], *e = ix.data() + ip[c + 1];
@@ -319,6 +322,17 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     const int N = h->N, nl = h->n_loc, rb = h->row_begin;
     const bool cn = h->cfg.CN != 0;
     const double tau = h->cfg.tau, beta = h->cfg.beta, eps = h->cfg.epsilon;
+    // transposed access into K without a stored K^T: one transposition map per pattern
+    if (h->h_KT.empty() && !h->k_symmetric && h->h_tperm.size() != h->h_indices.size()) {
+        const std::vector<int> &ip = h->h_indptr, &ix = h->h_indices;
+        h->h_tperm.resize(ix.size());
+        for (int r = 0; r < h->n; ++r)
+            for (int k = ip[r]; k < ip[r + 1]; ++k) {
+                const int c = ix[k];
+                const int *b = ix.data() + ip[c], *e = ix.data() + ip[c + 1];
+                h->h_tperm[k] = (int)(std::lower_bound(b, e, r) - ix.data());
+            }
+    }
 
     // Jacobi diagonal of assemble(M, bcs) and the list of constrained rows
     {
@@ -350,6 +364,10 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     const bool per_level = h->h_K.size() > 1;
     const bool sym = h->k_symmetric;
     std::map<std::tuple<int, int, double>, int> hier_index, off_index;
+    // distinct diagonal blocks are only REGISTERED here; their hierarchies are set up afterwards, all
+    // at once on the host threads (per-level K_i: 2N hierarchies per preconditioner setup)
+    struct PendingHier { int level; bool transposed; double w, m_coef; };
+    std::vector<PendingHier> pending;
     auto get_hier = [&](int level, bool transposed, double shift, double w, int *out) -> int {
         const auto key = std::make_tuple(per_level ? level : -1, (transposed && !sym) ? 1 : 0, shift);
         auto it = hier_index.find(key);
@@ -357,13 +375,12 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
             *out = it->second;
             return CTL_OK;
         }
-        std::vector<double> v;
-        combine_global(h, level, transposed && !sym, w, 1.0 + shift, true, v);
-        st.hier.emplace_back();
-        CTL_TRY(amg_build(h, global_csr(h, v), st.amg, st.fine, st.hier.back()));
-        *out = hier_index[key] = (int)st.hier.size() - 1;
+        pending.push_back({level, transposed && !sym, w, 1.0 + shift});
+        *out = hier_index[key] = (int)pending.size() - 1;
         return CTL_OK;
     };
+    struct PendingOff { int level; bool transposed; double w, m_coef; };
+    std::vector<PendingOff> pending_off;
     auto get_off = [&](int level, bool transposed, double w, double m_coef, int *out) -> int {
         const auto key = std::make_tuple(per_level ? level : -1, (transposed && !sym) ? 1 : 0, m_coef);
         auto it = off_index.find(key);
@@ -371,12 +388,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
             *out = it->second;
             return CTL_OK;
         }
-        std::vector<double> v;
-        combine_global(h, level, transposed && !sym, w, m_coef, false, v);
-        const std::vector<double> lv = local_values(h, v);
-        st.off.emplace_back();
-        CTL_TRY(sell_set_values(h, st.fine, lv.data(), st.off.back()));
-        *out = off_index[key] = (int)st.off.size() - 1;
+        pending_off.push_back({level, transposed && !sym, w, m_coef});
+        *out = off_index[key] = (int)pending_off.size() - 1;
         return CTL_OK;
     };
 
@@ -404,11 +417,53 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         }
     }
     if (opts->solver_0 == CTL_S0_AMG) {
-        std::vector<double> v;
-        combine_global(h, 0, false, 0.0, 1.0, true, v);
-        st.hier.emplace_back();
-        CTL_TRY(amg_build(h, global_csr(h, v), st.amg, st.fine, st.hier.back()));
-        st.h_mass = (int)st.hier.size() - 1;
+        pending.push_back({0, false, 0.0, 1.0});
+        st.h_mass = (int)pending.size() - 1;
+    }
+    // host setup of all hierarchies in parallel, then the device uploads one after the other
+    {
+        const int nh = (int)pending.size(), n_off = (int)pending_off.size();
+        st.hier.assign(nh, AmgHierarchyDev());
+        std::vector<std::string> errors(nh);
+        std::vector<std::vector<double>> off_values(n_off);
+        int n_threads = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("CTL_SETUP_THREADS")) n_threads = atoi(e);
+        n_threads = std::max(1, std::min(std::min(n_threads, nh + n_off), 32));
+        std::atomic<int> next{0};
+        auto worker = [&]() {
+            for (int i = next.fetch_add(1); i < nh + n_off; i = next.fetch_add(1)) {
+                if (i >= nh) {                      // an off-diagonal block: values on the local pattern
+                    const PendingOff &o = pending_off[i - nh];
+                    std::vector<double> v;
+                    combine_global(h, o.level, o.transposed, o.w, o.m_coef, false, v);
+                    off_values[i - nh] = local_values(h, v);
+                    continue;
+                }
+                try {
+                    std::vector<double> v;
+                    combine_global(h, pending[i].level, pending[i].transposed, pending[i].w, pending[i].m_coef, true, v);
+                    amg_setup_host(global_csr(h, v), st.amg, st.hier[i].host);
+                } catch (const std::exception &e) {
+                    errors[i] = e.what();
+                }
+            }
+        };
+        if (n_threads == 1) {
+            worker();
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+            for (auto &t : pool) t.join();
+        }
+        for (int i = 0; i < nh; ++i) {
+            CTL_CHECK(errors[i].empty(), CTL_ERR_STATE, errors[i]);
+            CTL_TRY(amg_build(h, st.hier[i].host[0].A, st.amg, st.fine, st.hier[i]));
+        }
+        st.off.assign(n_off, SellMat());
+        for (int i = 0; i < n_off; ++i) {
+            CTL_TRY(sell_set_values(h, st.fine, off_values[i].data(), st.off[i]));
+            off_values[i] = std::vector<double>();
+        }
     }
 
     // Experiment (CTL_L2_PERSIST=<MB>): pin the fine-level matrix of hierarchy 0 in the persisting L2 carve-out
