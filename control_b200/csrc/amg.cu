@@ -11,6 +11,12 @@
 #include "cheb_coefficients.h"
 
 // levels >= FUSED_FROM of a V-cycle run as one cooperative kernel (sell.cu: fused coarse tail)
+static bool fusion_enabled()
+{
+    const char *e = getenv("CTL_FUSED");
+    return e && (e[0] == '1' || e[0] == '2');
+}
+
 static int fused_from_level()
 {
     static int v = -1;
@@ -21,6 +27,8 @@ static int fused_from_level()
     return v;
 }
 #define FUSED_FROM fused_from_level()
+// the fused kernel reads CSR only; without it every matrix takes the format sell_from_csr picks
+#define FORCE_CSR(l) (fusion_enabled() && (l) >= FUSED_FROM)
 
 static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
 {
@@ -60,7 +68,7 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             for (size_t q = 0; q < lv.size(); ++q) lv[q] = Lh.A.values[h->loc_entry[q]];
             CTL_TRY(sell_set_values(h, fine_pattern, lv.data(), Ld.A));
         } else {
-            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A, l >= FUSED_FROM));
+            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A, FORCE_CSR(l)));
         }
         CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data() + rb, (size_t)Ld.n));
         CTL_TRY(dev_alloc(h, &Ld.r, Ld.n + ghosts));
@@ -85,8 +93,8 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
                 CTL_TRY(sell_from_csr(h, Pl, Ld.P));
                 CTL_TRY(sell_from_csr(h, Rl, Ld.R));
             } else {
-                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P, l >= FUSED_FROM));
-                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R, l >= FUSED_FROM));
+                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P, FORCE_CSR(l)));
+                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R, FORCE_CSR(l)));
             }
             // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
             const int nu_l = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;

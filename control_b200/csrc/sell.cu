@@ -27,7 +27,16 @@ void sell_free(SellMat &m)
 int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_csr)
 {
     const double mean = A.n_rows ? (double)A.nnz() / A.n_rows : 0.0;
-    if (mean <= 10.0 && !force_csr) {
+    // SELL-32 (one row per thread, coalesced) up to a mean row length of 24: measured at C2 against the
+    // CSR-vector kernels, inner solve 0.842 ms (threshold 10) -> 0.792 (14) -> 0.774 (20-24) -> 0.779 (40)
+    double sell_max_mean = 24.0;
+    if (const char *e = getenv("CTL_SELL_MAX_MEAN")) sell_max_mean = atof(e);      // experiment
+    // ... but only for levels with enough rows to fill the GPU with one row per thread: below ~50 k rows
+    // the CSR-vector kernels (several threads per row) win (19 k-row level as SELL: 0.833 ms per solve)
+    int sell_min_rows = 50000;
+    if (const char *e = getenv("CTL_SELL_MIN_ROWS")) sell_min_rows = atoi(e);      // experiment
+    const bool mesh_like = mean <= 10.0;          // fine-mesh stencils (short rows): always SELL
+    if ((mesh_like || (mean <= sell_max_mean && A.n_rows >= sell_min_rows)) && !force_csr) {
         std::shared_ptr<SellPattern> pat;
         CTL_TRY(sell_build_pattern(h, A, pat));
         return sell_set_values(h, pat, A.values.data(), out);
