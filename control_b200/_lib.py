@@ -92,6 +92,7 @@ SIGNATURES = {
                                  C.POINTER(ctl_solve_result)]),
     "ctl_kkt_residual_norm": (C.c_int, [_H, _F64P, _F64P, C.c_int, C.POINTER(C.c_double)]),
     "ctl_objective_host": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
+    "ctl_objective": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
     "ctl_amg_num_hierarchies": (C.c_int32, [_H]),
     "ctl_amg_num_levels": (C.c_int32, [_H, C.c_int32]),
     "ctl_amg_level_size": (C.c_int, [_H, C.c_int32, C.c_int32, _I32P, C.POINTER(C.c_int64),

@@ -117,6 +117,7 @@ int ctl_destroy(ctl_handle h)
     cudaFree(h->d_indptr);
     cudaFree(h->d_indices);
     cudaFree(h->d_M);
+    cudaFree(h->d_M_full);
     if (h->d_KT != h->d_K) cudaFree(h->d_KT);
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
@@ -166,6 +167,8 @@ int ctl_set_values(ctl_handle h, int which, int level, const double *values)
     if (which == CTL_MAT_M) {
         CTL_CHECK(level == -1, CTL_ERR_ARG, "ctl_set_values: the mass matrix has no time level");
         h->h_M.assign(values, values + nnz);
+        cudaFree(h->d_M_full);          // rebuilt on the next ctl_objective
+        h->d_M_full = nullptr;
     } else if (which == CTL_MAT_K || which == CTL_MAT_KT) {
         auto &dst = (which == CTL_MAT_K) ? h->h_K : h->h_KT;
         if (level == -1) {

@@ -80,6 +80,7 @@ struct ctl_handle_s {
     // device: shared pattern + value sets of the batched (time-fastest) kernels
     int *d_indptr = nullptr, *d_indices = nullptr;
     double *d_M = nullptr;      // BC columns zeroed
+    double *d_M_full = nullptr; // no elimination; uploaded on first use (objective.cu)
     double *d_K = nullptr;      // scalar per entry (time independent) or panel [nnz x ld]
     double *d_KT = nullptr;     // may alias d_K (symmetric, time independent)
     bool per_level = false;

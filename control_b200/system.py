@@ -410,6 +410,16 @@ class MultiBlockSystem:
         self._call(self._lib.ctl_kkt_residual_norm, b_dev.data_ptr(), x_dev.data_ptr(), layout, C.byref(out))
         return float(out.value)
 
+    def objective_device(self, v_dev, zeta_dev, v_hat_dev):
+        """J_h from device arrays of n_t levels x n (level-major), evaluated on the GPU."""
+        need = self.n_t * self.n
+        for t in (v_dev, zeta_dev, v_hat_dev):
+            if t.numel() != need or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("objective_device needs contiguous float64 CUDA tensors of n_t * n entries")
+        out = C.c_double()
+        self._call(self._lib.ctl_objective, v_dev.data_ptr(), zeta_dev.data_ptr(), v_hat_dev.data_ptr(), C.byref(out))
+        return float(out.value)
+
     def objective(self, v, zeta, v_hat):
         v = np.ascontiguousarray(v, dtype=np.float64)
         zeta = np.ascontiguousarray(zeta, dtype=np.float64)

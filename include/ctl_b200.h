@@ -190,6 +190,10 @@ int ctl_kkt_residual_norm(ctl_handle h, const double *b, const double *x, int la
 /* discrete objective J_h; v, zeta, v_hat: n_t levels x n, host */
 int ctl_objective_host(ctl_handle h, const double *v_host, const double *zeta_host,
                        const double *v_hat_host, double *out);
+/* the same on DEVICE arrays (n_t levels x n, level-major); the scalar is returned to the host.
+ * Single rank. */
+int ctl_objective(ctl_handle h, const double *v, const double *zeta, const double *v_hat,
+                  double *out_host);
 
 /* ---- AMG introspection (tests compare the hierarchy with the oracle's) */
 int32_t ctl_amg_num_hierarchies(ctl_handle h);

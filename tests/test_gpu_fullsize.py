@@ -83,6 +83,10 @@ def test_c2_solve_meets_tolerance_and_objective(c2):
     J_gpu = s.objective(v, zeta, q["v_hat"])
     J_ref = ocontrol.objective(q["M"], v, zeta, q["v_hat"], q["tau"], q["beta"], True)
     assert abs(J_gpu - J_ref) <= 1e-12 * abs(J_ref)
+    # the same on the device (ctl_objective): 64 levels x 1.05 M dofs without leaving HBM
+    J_dev = s.objective_device(torch.from_numpy(v).to(s.device), torch.from_numpy(zeta).to(s.device),
+                               torch.from_numpy(np.ascontiguousarray(q["v_hat"])).to(s.device))
+    assert abs(J_dev - J_ref) <= 1e-12 * abs(J_ref)
     # the optimal state tracks the desired state: J is far below J(v = 0, zeta = 0)
     J0 = ocontrol.objective(q["M"], 0 * v, 0 * zeta, q["v_hat"], q["tau"], q["beta"], True)
     assert J_gpu < 0.5 * J0
