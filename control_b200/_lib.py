@@ -93,6 +93,7 @@ SIGNATURES = {
     "ctl_kkt_residual_norm": (C.c_int, [_H, _F64P, _F64P, C.c_int, C.POINTER(C.c_double)]),
     "ctl_objective_host": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
     "ctl_objective": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
+    "ctl_build_rhs": (C.c_int, [_H, _F64P, _F64P, _F64P, _F64P]),
     "ctl_amg_num_hierarchies": (C.c_int32, [_H]),
     "ctl_amg_num_levels": (C.c_int32, [_H, C.c_int32]),
     "ctl_amg_level_size": (C.c_int, [_H, C.c_int32, C.c_int32, _I32P, C.POINTER(C.c_int64),

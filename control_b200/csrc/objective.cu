@@ -104,3 +104,129 @@ extern "C" int ctl_objective(ctl_handle h, const double *v, const double *zeta, 
     *out = J;
     return CTL_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Right-hand sides of linear_solve from NODAL data on the device (SURVEY.md "next" row f3;
+// control/control.py:2980-3243 for homogeneous Dirichlet data).  In the reference v_d and f are
+// cofunctions assembled by Firedrake, one FE assembly per time level; for data interpolated into the
+// space (README.md:33-60 and every test) they equal M v_hat_i and M f_i, so only nodal values need to
+// cross the boundary.  Block-major = level-major here, so every step is one kernel over rows x blocks.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// out[i][r] = alpha * sum_k M[r,k] (x[i + off][k] + (pair ? x[i + off + 1][k] : 0)); constrained rows 0
+__global__ void __launch_bounds__(QT) rhs_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
+                                                     const double *__restrict__ Mv, const uint8_t *__restrict__ bc,
+                                                     const double *__restrict__ x, double *__restrict__ out, int n,
+                                                     double alpha, int pair, int off)
+{
+    const int row = blockIdx.x * QT + threadIdx.x;
+    if (row >= n) return;
+    const int i = blockIdx.y;
+    double acc = 0.0;
+    if (!bc[row]) {
+        const double *x0 = x + (size_t)(i + off) * n, *x1 = x0 + n;
+        for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
+            const int c = cols[k];
+            acc = fma(Mv[k], pair ? x0[c] + x1[c] : x0[c], acc);
+        }
+        acc *= alpha;
+    }
+    out[(size_t)i * n + row] = acc;
+}
+
+// out[i] = in[i] + in[i + 1] (mode 1: T_1) / in[i] + in[i - 1] (mode 2: T_2) over N blocks of n
+__global__ void bm_time_transform_kernel(const double *__restrict__ in, double *__restrict__ out, int n, int N, int mode)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)N * n) return;
+    const int i = (int)(idx / n);
+    double v = in[idx];
+    if (mode == 1 && i + 1 < N) v += in[idx + n];
+    if (mode == 2 && i > 0) v += in[idx - n];
+    out[idx] = v;
+}
+
+// y[r] -= c[r] on unconstrained rows of one block
+__global__ void block_sub_kernel(double *__restrict__ y, const double *__restrict__ c, const uint8_t *__restrict__ bc, int n)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n && !bc[r]) y[r] -= c[r];
+}
+
+}  // namespace
+
+extern "C" int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_nodal, const double *v_0_host, double *b)
+{
+    CTL_CHECK(h && v_hat && f_nodal && b, CTL_ERR_ARG, "ctl_build_rhs: null argument");
+    CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_build_rhs: ctl_assemble has not been called");
+    CTL_CHECK(h->cfg.world == 1, CTL_ERR_ARG, "ctl_build_rhs: single-rank only");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    const int n = h->n, n_t = h->cfg.n_t, N = h->N;
+    const bool cn = h->cfg.CN != 0;
+    const double tau = h->cfg.tau;
+    if (!h->d_M_full) {
+        std::vector<double> buf(h->loc_entry.size());
+        for (size_t p = 0; p < buf.size(); ++p) buf[p] = h->h_M[h->loc_entry[p]];
+        CTL_TRY(ctl_upload(h, &h->d_M_full, buf.data(), buf.size()));
+    }
+    const int blocks = ceil_div(n, QT);
+    const size_t half = (size_t)N * n;
+    double *work = nullptr;                       // untransformed rows (CN) before T_1 / T_2
+    CTL_TRY(ctl_scratch_get(h, &work));           // a scratch vector holds at least 2 N n doubles
+    double *r0 = cn ? work : b, *r1 = cn ? work + half : b + half;
+    // M-weighted rows: CN h M (x_i + x_{i+1}), i < N;  BE tau M x_i, with b_0 row n_t - 1 = 0 and b_1 row 0 from v_0
+    const double alpha = cn ? 0.5 * tau : tau;
+    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, v_hat, r0, n,
+                                                          alpha, cn ? 1 : 0, 0);
+    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, f_nodal, r1, n,
+                                                          alpha, cn ? 1 : 0, 0);
+    h->launches += 2;
+    int rc = CTL_OK;
+    if (!cn) {
+        if (cudaMemsetAsync(r0 + (size_t)(n_t - 1) * n, 0, (size_t)n * sizeof(double), h->stream) != cudaSuccess ||
+            cudaMemsetAsync(r1, 0, (size_t)n * sizeof(double), h->stream) != cudaSuccess)
+            rc = CTL_ERR_CUDA;
+    }
+    // terms of the initial condition (control/control.py:3000-3004 BE, 3217-3240 CN), on the host:
+    // two products with one n-vector
+    if (rc == CTL_OK && v_0_host) {
+        const std::vector<double> &K0 = h->h_K[0];
+        std::vector<double> c0(n, 0.0), c1(n, 0.0);
+        for (int r = 0; r < n; ++r) {
+            double mv = 0.0, kv = 0.0;
+            for (int k = h->h_indptr[r]; k < h->h_indptr[r + 1]; ++k) {
+                const double x = v_0_host[h->h_indices[k]];
+                mv += h->h_M[k] * x;
+                kv += K0[k] * x;
+            }
+            if (cn) {
+                c0[r] = 0.5 * tau * mv;                 // b_0[0] -= h M v_0
+                c1[r] = 0.5 * tau * kv - mv;            // b_1[0] -= (h K_0 - M) v_0
+            } else {
+                c1[r] = -(tau * kv + mv);               // b_1[0]  = (tau K_0 + M) v_0
+            }
+        }
+        double *d_c = nullptr;
+        if (cudaMalloc((void **)&d_c, 2 * (size_t)n * sizeof(double)) != cudaSuccess) rc = CTL_ERR_CUDA;
+        if (rc == CTL_OK) {
+            cudaMemcpyAsync(d_c, c0.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+            cudaMemcpyAsync(d_c + n, c1.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+            if (cn) block_sub_kernel<<<ceil_div(n, 256), 256, 0, h->stream>>>(r0, d_c, h->d_bcmask, n);
+            block_sub_kernel<<<ceil_div(n, 256), 256, 0, h->stream>>>(r1, d_c + n, h->d_bcmask, n);
+            h->launches += cn ? 2 : 1;
+            cudaStreamSynchronize(h->stream);           // c0 / c1 are host temporaries
+            cudaFree(d_c);
+        }
+    }
+    if (rc == CTL_OK && cn) {                           // b_0 = T_1 rows, b_1 = T_2 rows (3242-3243)
+        const int tb = ceil_div((int64_t)half, 256);
+        bm_time_transform_kernel<<<tb, 256, 0, h->stream>>>(r0, b, n, N, 1);
+        bm_time_transform_kernel<<<tb, 256, 0, h->stream>>>(r1, b + half, n, N, 2);
+        h->launches += 2;
+    }
+    if (rc == CTL_OK && cudaGetLastError() != cudaSuccess) rc = CTL_ERR_CUDA;
+    if (rc != CTL_OK) ctl_set_error(h, "ctl_build_rhs: CUDA failure");
+    ctl_scratch_put(h, work);
+    return rc;
+}

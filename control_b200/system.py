@@ -420,6 +420,19 @@ class MultiBlockSystem:
         self._call(self._lib.ctl_objective, v_dev.data_ptr(), zeta_dev.data_ptr(), v_hat_dev.data_ptr(), C.byref(out))
         return float(out.value)
 
+    def build_rhs_device(self, v_hat_dev, f_nodal_dev, v_0=None):
+        """Block-major device right-hand side of ``linear_solve`` from nodal data on the device
+        (n_t levels x n each); ``v_0``: host initial condition or None (``ctl_build_rhs``)."""
+        need = self.n_t * self.n
+        for t in (v_hat_dev, f_nodal_dev):
+            if t.numel() != need or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+                raise ValueError("build_rhs_device needs contiguous float64 CUDA tensors of n_t * n entries")
+        b = self.new_vector()
+        v0 = None if v_0 is None else np.ascontiguousarray(v_0, dtype=np.float64)
+        self._call(self._lib.ctl_build_rhs, v_hat_dev.data_ptr(), f_nodal_dev.data_ptr(),
+                   None if v0 is None else v0.ctypes.data, b.data_ptr())
+        return b
+
     def objective(self, v, zeta, v_hat):
         v = np.ascontiguousarray(v, dtype=np.float64)
         zeta = np.ascontiguousarray(zeta, dtype=np.float64)

@@ -194,6 +194,12 @@ int ctl_objective_host(ctl_handle h, const double *v_host, const double *zeta_ho
  * Single rank. */
 int ctl_objective(ctl_handle h, const double *v, const double *zeta, const double *v_hat,
                   double *out_host);
+/* ---- right-hand sides of linear_solve from NODAL data (control/control.py:2980-3243, homogeneous
+ *      Dirichlet data): v_hat, f_nodal are DEVICE arrays of n_t levels x n (the reference's
+ *      cofunctions are M v_hat_i, M f_i for interpolated data); v_0_host: the initial condition
+ *      (n doubles, host) or NULL = 0; b: DEVICE block-major output, T_1 / T_2 applied.  Single rank. */
+int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_nodal, const double *v_0_host,
+                  double *b);
 
 /* ---- AMG introspection (tests compare the hierarchy with the oracle's) */
 int32_t ctl_amg_num_hierarchies(ctl_handle h);

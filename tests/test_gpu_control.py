@@ -87,3 +87,39 @@ def test_non_linear_solve_matches_oracle(CN, gauss_newton, max_it):
     if not gauss_newton:
         assert c.non_linear_history[-1] < 0.05 * c.non_linear_history[1]      # Picard contracts
     c.close()
+
+
+@pytest.mark.parametrize("CN", [True, False])
+@pytest.mark.parametrize("with_v0", [False, True])
+def test_device_rhs_from_nodal_data_matches_oracle(CN, with_v0):
+    """ctl_build_rhs: the right-hand sides of linear_solve
+    (control/control.py:2980-3243) assembled on the device from nodal v_hat / f, against the oracle's
+    restatement fed with the cofunctions M v_hat / M f; then the solve from that device vector."""
+    import torch
+    from control_b200 import MultiBlockSystem
+    from oracle import kkt
+    q = kat.heat_problem(14, 7, CN, beta=1e-2)
+    M, K, bd, n_t = q["M"], q["K"], q["bdofs"], q["n_t"]
+    rng = np.random.default_rng(11)
+    f_nodal = rng.standard_normal((n_t, M.shape[0]))               # general data, non-zero on the boundary
+    v_hat = q["v_hat"] + 0.1 * rng.standard_normal(q["v_hat"].shape)
+    v_0 = None
+    if with_v0:
+        v_0 = rng.standard_normal(M.shape[0])
+        v_0[bd] = 0.0
+    s = MultiBlockSystem(M, K, n_t=n_t, beta=q["beta"], CN=CN, time_interval=q["time_interval"], bc_dofs=bd)
+    b = s.build_rhs_device(torch.from_numpy(v_hat).to(s.device), torch.from_numpy(f_nodal).to(s.device), v_0)
+    b0, b1 = s.to_host_blocks(b)
+    r0, r1 = kkt.build_rhs(M, K, q["tau"], n_t, CN, bd, (M @ v_hat.T).T, (M @ f_nodal.T).T,
+                           np.zeros(M.shape[0]) if v_0 is None else v_0)
+    scale = max(np.abs(r0).max(), np.abs(r1).max())
+    assert np.abs(b0 - r0).max() <= 1e-13 * scale and np.abs(b1 - r1).max() <= 1e-13 * scale
+    # and straight into a device solve
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], coarse_max=60)
+    u = s.new_vector()
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-8, "absolute_tolerance": 0.0,
+           "gmres_restart": 100}
+    info = s.solve_device(b, u, solver_parameters=sp_)
+    assert info.reason > 0
+    assert s.residual_norm(b, u) <= 1e-6 * float(b.norm())
+    s.close()
