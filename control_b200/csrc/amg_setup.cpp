@@ -4,8 +4,49 @@
 #include "amg_setup.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
+
+#include <thread>
+
+namespace {
+// Rows [0, n) in contiguous blocks on up to `threads` host threads; fn(block, begin, end).  Every row is
+// computed exactly as in the sequential code, so results do not depend on the thread count.
+template <typename F>
+void parallel_row_blocks(int n, int threads, F fn)
+{
+    const int T = (n < 20000 || threads <= 1) ? 1 : threads;
+    if (T == 1) {
+        fn(0, 0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < T; ++t) {
+        const int b = (int)((int64_t)n * t / T), e = (int)((int64_t)n * (t + 1) / T);
+        pool.emplace_back([=, &fn]() { fn(t, b, e); });
+    }
+    for (auto &th : pool) th.join();
+}
+
+int row_block_count(int n, int threads) { return (n < 20000 || threads <= 1) ? 1 : threads; }
+
+// CTL_SETUP_TIMING=1: phase times of the host setup on stderr
+struct PhaseTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    PhaseTimer() : on(getenv("CTL_SETUP_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what, int level)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ctl setup] level %d %-12s %.3f s\n", level, what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
 
 void csr_transpose(const HostCSR &A, HostCSR &At)
 {
@@ -27,37 +68,51 @@ void csr_transpose(const HostCSR &A, HostCSR &At)
 
 // Gustavson SpGEMM; accumulation order = ascending k of A's row, then B's row order
 // (the order scipy's csr_matmat uses), columns of C sorted.
-void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C)
+void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C, int threads)
 {
     C.n_rows = A.n_rows;
     C.n_cols = B.n_cols;
     C.indptr.assign(A.n_rows + 1, 0);
-    C.indices.clear();
-    C.values.clear();
-    std::vector<double> acc(B.n_cols, 0.0);
-    std::vector<int> mark(B.n_cols, -1), cols;
-    for (int i = 0; i < A.n_rows; ++i) {
-        cols.clear();
-        for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
-            const int j = A.indices[k];
-            const double a = A.values[k];
-            for (int q = B.indptr[j]; q < B.indptr[j + 1]; ++q) {
-                const int c = B.indices[q];
-                if (mark[c] != i) {
-                    mark[c] = i;
-                    acc[c] = 0.0;
-                    cols.push_back(c);
+    const int T = row_block_count(A.n_rows, threads);
+    std::vector<std::vector<int>> bi(T);
+    std::vector<std::vector<double>> bv(T);
+    parallel_row_blocks(A.n_rows, threads, [&](int t, int r0, int r1) {
+        std::vector<double> acc(B.n_cols, 0.0);
+        std::vector<int> mark(B.n_cols, -1), cols;
+        std::vector<int> &oi = bi[t];
+        std::vector<double> &ov = bv[t];
+        oi.reserve((size_t)(A.indptr[r1] - A.indptr[r0]) * 2);      // fewer regrowths (and their page faults)
+        ov.reserve((size_t)(A.indptr[r1] - A.indptr[r0]) * 2);
+        for (int i = r0; i < r1; ++i) {
+            cols.clear();
+            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+                const int j = A.indices[k];
+                const double a = A.values[k];
+                for (int q = B.indptr[j]; q < B.indptr[j + 1]; ++q) {
+                    const int c = B.indices[q];
+                    if (mark[c] != i) {
+                        mark[c] = i;
+                        acc[c] = 0.0;
+                        cols.push_back(c);
+                    }
+                    acc[c] += a * B.values[q];
                 }
-                acc[c] += a * B.values[q];
             }
+            std::sort(cols.begin(), cols.end());
+            for (int c : cols) {
+                oi.push_back(c);
+                ov.push_back(acc[c]);
+            }
+            C.indptr[i + 1] = (int)cols.size();
         }
-        std::sort(cols.begin(), cols.end());
-        for (int c : cols) {
-            C.indices.push_back(c);
-            C.values.push_back(acc[c]);
-        }
-        C.indptr[i + 1] = (int)C.indices.size();
-    }
+    });
+    for (int i = 0; i < A.n_rows; ++i) C.indptr[i + 1] += C.indptr[i];
+    C.indices.resize(C.indptr[A.n_rows]);
+    C.values.resize(C.indptr[A.n_rows]);
+    parallel_row_blocks(A.n_rows, threads, [&](int t, int r0, int) {
+        std::copy(bi[t].begin(), bi[t].end(), C.indices.begin() + C.indptr[r0]);
+        std::copy(bv[t].begin(), bv[t].end(), C.values.begin() + C.indptr[r0]);
+    });
 }
 
 // oracle/amg.py:_aggregate
@@ -153,24 +208,32 @@ static double gershgorin_rho(const HostCSR &A, std::vector<double> &dinv)
 constexpr int POWER_ITS = 30;
 constexpr double POWER_SAFETY = 1.2;
 
-static double power_rho(const HostCSR &A, const std::vector<double> &dinv)
+// stop_at > 0: the caller only needs min(stop_at, POWER_SAFETY * estimate), so the iteration ends as soon
+// as the estimate is large enough for the minimum to be stop_at (the fine-mesh matrix, whose Gershgorin
+// bound is sharp, leaves after a few steps instead of 30 products with 7 M entries)
+static double power_rho(const HostCSR &A, const std::vector<double> &dinv, double stop_at, int threads)
 {
     const int n = A.n_rows;
     std::vector<double> x(n), y(n);
     for (int i = 0; i < n; ++i) x[i] = std::sin(0.37 * (double)i + 0.1) + 0.5 * std::cos(1.3 * (double)i);
     double lam = 0.0;
     for (int it = 0; it < POWER_ITS; ++it) {
-        double yy = 0.0, xx = 0.0;
+        parallel_row_blocks(n, threads, [&](int, int r0, int r1) {
+            for (int i = r0; i < r1; ++i) {
+                double s = 0.0;
+                for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) s += A.values[k] * x[A.indices[k]];
+                y[i] = dinv[i] * s;
+            }
+        });
+        double yy = 0.0, xx = 0.0;               // sequential sums: the result must not depend on the thread count
         for (int i = 0; i < n; ++i) {
-            double s = 0.0;
-            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) s += A.values[k] * x[A.indices[k]];
-            y[i] = dinv[i] * s;
             yy += y[i] * y[i];
             xx += x[i] * x[i];
         }
         const double ny = std::sqrt(yy);
         if (ny == 0.0) return 0.0;
         lam = ny / std::sqrt(xx);
+        if (stop_at > 0.0 && POWER_SAFETY * lam >= stop_at) return lam;
         for (int i = 0; i < n; ++i) x[i] = y[i] / ny;
     }
     return lam;
@@ -218,23 +281,33 @@ static void dense_inverse(const HostCSR &A, const std::vector<double> &shift, st
     }
 }
 
-void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelHost> &levels)
+void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelHost> &levels, int threads)
 {
+    if (threads <= 0) {
+        threads = (int)std::thread::hardware_concurrency();
+        if (const char *e = getenv("CTL_SETUP_THREADS")) threads = atoi(e);
+        threads = std::max(1, std::min(threads, 32));
+    }
     levels.clear();
     HostCSR A = A0;
     std::vector<double> cand(A.n_rows, 1.0);
+    PhaseTimer timer;
     while (true) {
         levels.emplace_back();
         AmgLevelHost &L = levels.back();
+        const int lvl = (int)levels.size() - 1;
         L.A = A;
+        timer.lap("copy", lvl);
         L.rho = gershgorin_rho(L.A, L.dinv);
-        L.rho = std::min(L.rho, POWER_SAFETY * power_rho(L.A, L.dinv));
+        L.rho = std::min(L.rho, POWER_SAFETY * power_rho(L.A, L.dinv, L.rho, threads));
+        timer.lap("rho", lvl);
         const int n = A.n_rows;
         if (n <= p.coarse_max || (int)levels.size() >= p.max_levels) break;
         std::vector<int> agg;
         const int n_agg = aggregate(A, p.theta * std::pow(p.theta_decay, (double)(levels.size() - 1)), agg);
         if (n_agg == 0 || n_agg >= 0.9 * n) break;
         L.agg = agg;
+        timer.lap("aggregate", lvl);
         // tentative prolongator from the near-kernel candidate: T_jJ = cand_j / ||cand|agg_J||,
         // coarse candidate = those norms
         std::vector<double> norms(n_agg, 0.0), t(n, 0.0);
@@ -249,37 +322,55 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         P.n_rows = n;
         P.n_cols = n_agg;
         P.indptr.assign(n + 1, 0);
-        std::vector<std::pair<int, double>> row;
-        for (int i = 0; i < n; ++i) {
-            row.clear();
-            // (A T)_iJ accumulated in CSR order of j
-            for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
-                const double a = A.values[k];
-                const int j = A.indices[k], J = agg[j];
-                if (a == 0.0 || J < 0) continue;
-                auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
-                if (it == row.end()) row.emplace_back(J, a * t[j]);
-                else it->second += a * t[j];
-            }
-            const double d = omega * L.dinv[i];
-            for (auto &e : row) e.second = -(d * e.second);
-            if (agg[i] >= 0) {
-                const int J = agg[i];
-                auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
-                if (it == row.end()) row.emplace_back(J, t[i]);
-                else it->second = t[i] + it->second;
-            }
-            std::sort(row.begin(), row.end());
-            for (auto &e : row) {
-                P.indices.push_back(e.first);
-                P.values.push_back(e.second);
-            }
-            P.indptr[i + 1] = (int)P.indices.size();
+        {
+            const int T = row_block_count(n, threads);
+            std::vector<std::vector<int>> bi(T);
+            std::vector<std::vector<double>> bv(T);
+            parallel_row_blocks(n, threads, [&](int tb, int r0, int r1) {
+                std::vector<std::pair<int, double>> row;
+                for (int i = r0; i < r1; ++i) {
+                    row.clear();
+                    // (A T)_iJ accumulated in CSR order of j
+                    for (int k = A.indptr[i]; k < A.indptr[i + 1]; ++k) {
+                        const double a = A.values[k];
+                        const int j = A.indices[k], J = agg[j];
+                        if (a == 0.0 || J < 0) continue;
+                        auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
+                        if (it == row.end()) row.emplace_back(J, a * t[j]);
+                        else it->second += a * t[j];
+                    }
+                    const double d = omega * L.dinv[i];
+                    for (auto &e : row) e.second = -(d * e.second);
+                    if (agg[i] >= 0) {
+                        const int J = agg[i];
+                        auto it = std::find_if(row.begin(), row.end(), [J](const std::pair<int, double> &e) { return e.first == J; });
+                        if (it == row.end()) row.emplace_back(J, t[i]);
+                        else it->second = t[i] + it->second;
+                    }
+                    std::sort(row.begin(), row.end());
+                    for (auto &e : row) {
+                        bi[tb].push_back(e.first);
+                        bv[tb].push_back(e.second);
+                    }
+                    P.indptr[i + 1] = (int)row.size();
+                }
+            });
+            for (int i = 0; i < n; ++i) P.indptr[i + 1] += P.indptr[i];
+            P.indices.resize(P.indptr[n]);
+            P.values.resize(P.indptr[n]);
+            parallel_row_blocks(n, threads, [&](int tb, int r0, int) {
+                std::copy(bi[tb].begin(), bi[tb].end(), P.indices.begin() + P.indptr[r0]);
+                std::copy(bv[tb].begin(), bv[tb].end(), P.values.begin() + P.indptr[r0]);
+            });
         }
+        timer.lap("prolongator", lvl);
         csr_transpose(P, L.R);
+        timer.lap("transpose", lvl);
         HostCSR AP, Ac;
-        csr_matmat(A, P, AP);
-        csr_matmat(L.R, AP, Ac);
+        csr_matmat(A, P, AP, threads);
+        timer.lap("A*P", lvl);
+        csr_matmat(L.R, AP, Ac, threads);
+        timer.lap("R*(AP)", lvl);
         A = std::move(Ac);
         cand = norms;
     }

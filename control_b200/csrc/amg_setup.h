@@ -33,8 +33,10 @@ struct AmgLevelHost {
 };
 
 // A must have sorted column indices.  Returns the levels, finest first.
-void amg_setup_host(const HostCSR &A, const AmgParams &p, std::vector<AmgLevelHost> &levels);
+// threads: host threads for the row-parallel phases (0 = all hardware threads, CTL_SETUP_THREADS); the
+// result does not depend on it
+void amg_setup_host(const HostCSR &A, const AmgParams &p, std::vector<AmgLevelHost> &levels, int threads = 0);
 
 // helpers shared with tests / other units
 void csr_transpose(const HostCSR &A, HostCSR &At);
-void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C);
+void csr_matmat(const HostCSR &A, const HostCSR &B, HostCSR &C, int threads = 1);

@@ -428,6 +428,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         std::vector<std::vector<double>> off_values(n_off);
         int n_threads = (int)std::thread::hardware_concurrency();
         if (const char *e = getenv("CTL_SETUP_THREADS")) n_threads = atoi(e);
+        const int hw_threads = std::max(1, std::min(n_threads, 32));
         n_threads = std::max(1, std::min(std::min(n_threads, nh + n_off), 32));
         std::atomic<int> next{0};
         auto worker = [&]() {
@@ -442,7 +443,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
                 try {
                     std::vector<double> v;
                     combine_global(h, pending[i].level, pending[i].transposed, pending[i].w, pending[i].m_coef, true, v);
-                    amg_setup_host(global_csr(h, v), st.amg, st.hier[i].host);
+                    // the workers share the host: each hierarchy gets its share of the threads
+                    amg_setup_host(global_csr(h, v), st.amg, st.hier[i].host, std::max(1, hw_threads / n_threads));
                 } catch (const std::exception &e) {
                     errors[i] = e.what();
                 }

@@ -135,9 +135,11 @@ POWER_ITS = 30
 POWER_SAFETY = 1.2
 
 
-def power_rho(A, dinv):
+def power_rho(A, dinv, stop_at=0.0):
     """POWER_ITS steps of the power method on D^-1 A from a fixed start vector; returns the last
-    Rayleigh-type quotient ||D^-1 A x|| / ||x|| (a lower estimate of lambda_max)."""
+    Rayleigh-type quotient ||D^-1 A x|| / ||x|| (a lower estimate of lambda_max).  With
+    ``stop_at`` > 0 it ends as soon as POWER_SAFETY x the estimate reaches ``stop_at``: the caller
+    takes min(stop_at, POWER_SAFETY x estimate), which is ``stop_at`` from then on."""
     n = A.shape[0]
     i = np.arange(n, dtype=np.float64)
     x = np.sin(0.37 * i + 0.1) + 0.5 * np.cos(1.3 * i)
@@ -148,12 +150,15 @@ def power_rho(A, dinv):
         if ny == 0.0:
             return 0.0
         lam = ny / float(np.sqrt(np.dot(x, x)))
+        if stop_at > 0.0 and POWER_SAFETY * lam >= stop_at:
+            return lam
         x = y / ny
     return lam
 
 
 def spectral_bound(A, dinv):
-    return min(gershgorin_rho(A), POWER_SAFETY * power_rho(A, dinv))
+    g = gershgorin_rho(A)
+    return min(g, POWER_SAFETY * power_rho(A, dinv, g))
 
 
 class Level:
