@@ -113,6 +113,8 @@ SIGNATURES = {
     "ctl_stokes_solve": (C.c_int, [_H, _F64P, _F64P, C.POINTER(ctl_krylov_options),
                                    C.POINTER(ctl_solve_result)]),
     "ctl_stokes_time": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),
+    "ctl_amg_setup_probe": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(ctl_pc_options),
+                                      C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ctl_comm_unique_id": (C.c_int, [C.c_void_p]),
     "ctl_comm_init": (C.c_int, [_H, C.c_void_p]),
     "ctl_kernel_launches": (C.c_int64, [_H]),

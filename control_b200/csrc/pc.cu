@@ -283,6 +283,49 @@ int ctl_pc_default_options(ctl_pc_options *o)
     return CTL_OK;
 }
 
+int ctl_amg_setup_probe(const int32_t *indptr, const int32_t *indices, const double *values, int32_t n,
+                        const ctl_pc_options *opts, int32_t *n_levels, int32_t *level_n, int64_t *level_nnz,
+                        double *level_rho, int32_t *aggregates)
+{
+    if (!indptr || !indices || !values || n <= 0 || !n_levels) return CTL_ERR_ARG;
+    AmgParams p;
+    if (opts) {
+        p.theta = opts->amg_theta;
+        p.max_levels = opts->amg_max_levels;
+        p.coarse_max = opts->amg_coarse_max;
+        p.nu = opts->amg_nu;
+        p.nu_fine = opts->amg_nu_fine;
+        p.lo = opts->amg_lo;
+        p.hi = opts->amg_hi;
+        p.cycles = opts->amg_cycles;
+    }
+    HostCSR A;
+    A.n_rows = A.n_cols = n;
+    A.indptr.assign(indptr, indptr + n + 1);
+    A.indices.assign(indices, indices + indptr[n]);
+    A.values.assign(values, values + indptr[n]);
+    std::vector<AmgLevelHost> levels;
+    try {
+        amg_setup_host(A, p, levels);
+    } catch (const std::exception &) {
+        return CTL_ERR_STATE;
+    }
+    *n_levels = (int32_t)levels.size();
+    for (size_t l = 0; l < levels.size() && l < 16; ++l) {
+        if (level_n) level_n[l] = levels[l].A.n_rows;
+        if (level_nnz) {             // entries that are not (numerically) zero: explicit zeros are a storage detail
+            double amax = 0.0;
+            for (double v : levels[l].A.values) amax = std::max(amax, std::fabs(v));
+            int64_t cnt = 0;
+            for (double v : levels[l].A.values) cnt += std::fabs(v) > 1e-13 * amax;
+            level_nnz[l] = cnt;
+        }
+        if (level_rho) level_rho[l] = levels[l].rho;
+    }
+    if (aggregates && !levels[0].agg.empty()) std::copy(levels[0].agg.begin(), levels[0].agg.end(), aggregates);
+    return CTL_OK;
+}
+
 int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
 {
     CTL_CHECK(h && opts, CTL_ERR_ARG, "ctl_pc_setup: null argument");

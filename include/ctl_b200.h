@@ -259,6 +259,14 @@ int ctl_stokes_solve(ctl_stokes s, const double *b, double *u, const ctl_krylov_
  * ms; out[3] = its bytes (the same + 8 N n_v for the accumulate) */
 int ctl_stokes_time(ctl_stokes s, int reps, double *out4_host);
 
+/* ---- host-only probe of the AMG setup (no GPU needed; the CPU test-suite compares it with the oracle):
+ *      sets up the hierarchy of the n x n CSR matrix with the AMG options of `opts` (NULL = defaults) and
+ *      reports up to 16 levels: rows, entries above 1e-13 x the largest one, spectral bound rho, and the
+ *      aggregate id of every fine row */
+int ctl_amg_setup_probe(const int32_t *indptr_host, const int32_t *indices_host, const double *values_host,
+                        int32_t n, const ctl_pc_options *opts, int32_t *n_levels, int32_t *level_n16,
+                        int64_t *level_nnz16, double *level_rho16, int32_t *aggregates_n);
+
 /* ---- multi-GPU (one process per GPU): the 128-byte ncclUniqueId is created on rank 0
  *      with ctl_comm_unique_id and distributed by the caller (torch.distributed) */
 int ctl_comm_unique_id(void *id128_host);
