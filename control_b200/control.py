@@ -33,33 +33,52 @@ def _apply_T_2(x):      # control/control.py:44-59
     return y
 
 
-def build_rhs(M, K0, tau, n_t, CN, bc_dofs, v_d, f, v_0, check_v_d=True, check_f=True):
+def build_rhs(M, K0, tau, n_t, CN, bc_dofs, v_d, f, v_0, check_v_d=True, check_f=True, bc_values=None,
+              K_levels=None):
     """Right-hand sides of the heat-type rows (control/control.py:2990-3243; the Stokes driver
     builds its velocity rows the same way, 3961-4243).  ``v_d``, ``f``: (n_t, n) cofunction values
     (``M @ nodal``), or ready blocks (N, n) when the matching check_* is False; ``K0``: D_v at the
-    initial condition.  Returns the final (T-transformed) ``b_0``, ``b_1`` of shape (N, n)."""
+    initial condition.  ``bc_values`` (n_t, len(bc_dofs)): inhomogeneous, time-dependent Dirichlet
+    data of the state, lifted into the right-hand sides as the reference does with ``v_inhom``
+    (control/control.py:2993-3124 BE, 3137-3212 CN); ``K_levels``: D_v per time level for those terms
+    (default: ``K0`` at every level).  Returns the final (T-transformed) ``b_0``, ``b_1`` of shape (N, n)."""
     n = M.shape[0]
     N = n_t - 1 if CN else n_t
     b_0 = np.zeros((N, n))
     b_1 = np.zeros((N, n))
+    lift = None
+    if bc_values is not None:
+        lift = np.zeros((n_t, n))
+        lift[:, bc_dofs] = np.asarray(bc_values, dtype=float)
+    Kl = [K0] * n_t if K_levels is None else list(K_levels)
 
     def bc(b):
         b[..., bc_dofs] = 0.0
     if not CN:                                          # control.py:2990-3130
         if check_v_d:
             b_0[:n_t - 1] = tau * v_d[:n_t - 1]
+            if lift is not None:
+                b_0[:n_t - 1] -= tau * (M @ lift[:n_t - 1].T).T
             bc(b_0)
         else:
             b_0[:] = v_d
         if check_f:
             b_1[0] = tau * (K0 @ v_0) + M @ v_0
             b_1[1:] = tau * f[1:]
+            if lift is not None:
+                for i in range(n_t):
+                    b_1[i] -= tau * (Kl[i] @ lift[i]) + M @ lift[i]
+                    if i > 0:
+                        b_1[i] += M @ lift[i - 1]
             bc(b_1)
         else:
             b_1[:] = f
     else:                                               # control.py:3131-3243
         if check_v_d:
             b_0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+            if lift is not None:
+                b_0[:] -= 0.5 * tau * (M @ lift[1:].T).T
+                b_0[1:] -= 0.5 * tau * (M @ lift[1:-1].T).T
             bc(b_0)
             b_0[0] -= 0.5 * tau * (M @ v_0)
             bc(b_0[0])
@@ -67,6 +86,11 @@ def build_rhs(M, K0, tau, n_t, CN, bc_dofs, v_d, f, v_0, check_v_d=True, check_f
             b_0[:] = v_d
         if check_f:
             b_1[:] = 0.5 * tau * (f[:-1] + f[1:])
+            if lift is not None:
+                for i in range(N):
+                    b_1[i] -= 0.5 * tau * (Kl[i + 1] @ lift[i + 1]) + M @ lift[i + 1]
+                    if i > 0:
+                        b_1[i] -= 0.5 * tau * (Kl[i] @ lift[i]) - M @ lift[i]
             bc(b_1)
             b_1[0] -= 0.5 * tau * (K0 @ v_0) - M @ v_0
             bc(b_1[0])
@@ -81,12 +105,14 @@ class Control:
     class Instationary:
         def __init__(self, M, forward_matrix, *, desired_state=None, force_f=None, force_function=None,
                      beta=1.0e-3, Gauss_Newton=False, CN=True, n_t=20, initial_condition=None,
-                     time_interval=(0.0, 1.0), bc_dofs=(), device=None, rank=0, world=1):
+                     time_interval=(0.0, 1.0), bc_dofs=(), bc_values=None, device=None, rank=0, world=1):
             """``M``: mass matrix (scipy CSR).  ``forward_matrix(v_i, t, gauss_newton)`` -> CSR
             on M's pattern: the matrix ``D_v`` of ``construct_D_v`` (control.py:1887-1896) at
             state ``v_i`` and time ``t``; a plain CSR matrix means a linear, time-independent
             operator.  ``desired_state(t)`` -> (M @ v_hat(t), v_hat(t)), the two returns of
-            the reference's callable (control.py:1929-1931); ``force_f(t)`` -> M @ f(t)."""
+            the reference's callable (control.py:1929-1931); ``force_f(t)`` -> M @ f(t).
+            ``bc_values``: None (homogeneous Dirichlet data) or a callable ``t -> values at bc_dofs``
+            (the reference's time-dependent ``bcs_v(space, t)``, control/control.py:1504-1530)."""
             if force_f is not None and force_function is not None:
                 raise TypeError("give either force_f or force_function")
             self._M = M.tocsr()
@@ -99,6 +125,7 @@ class Control:
             self._n_t = int(n_t)
             self._time_interval = tuple(time_interval)
             self._bc_dofs = np.ascontiguousarray(bc_dofs, dtype=np.int32)
+            self._bc_values = bc_values
             self._initial_condition = initial_condition
             self._n = self._M.shape[0]
             self._v = np.zeros((self._n_t, self._n))          # control.py:1569-1597
@@ -165,9 +192,16 @@ class Control:
                 self._stokes.close()
                 self._stokes = None
 
-        def _build_rhs(self, v_0, v_d, f, K0, check_v_d, check_f):
+        def _dirichlet_data(self):
+            """(n_t, len(bc_dofs)) boundary values of the state per time level, or None."""
+            if self._bc_values is None:
+                return None
+            return np.stack([np.asarray(self._bc_values(t), dtype=float) for t in self._times()])
+
+        def _build_rhs(self, v_0, v_d, f, K0, check_v_d, check_f, K_levels=None):
             return build_rhs(self._M, K0, self.tau, self._n_t, self._CN, self._bc_dofs, v_d, f, v_0,
-                             check_v_d=check_v_d, check_f=check_f)
+                             check_v_d=check_v_d, check_f=check_f, bc_values=self._dirichlet_data(),
+                             K_levels=K_levels)
 
         # ------------------------------------------------------------------ linear_solve
         def linear_solve(self, *, P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
@@ -185,7 +219,8 @@ class Control:
                 v_d = self.construct_v_d()
             K = self._K_levels(self._v)                         # D_v at self._v, control.py:2884-2904
             K0 = K if self._is_linear() else self.construct_D_v(v_0, self._time_interval[0])
-            b_0, b_1 = self._build_rhs(v_0, v_d, f, K0, check_v_d, check_f)
+            b_0, b_1 = self._build_rhs(v_0, v_d, f, K0, check_v_d, check_f,
+                                       K_levels=None if self._is_linear() else K)
             if solver_parameters is None:                       # control.py:3260-3266
                 solver_parameters = {"linear_solver": "gmres", "gmres_restart": 10, "maximum_iterations": 50,
                                      "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0,
@@ -216,6 +251,9 @@ class Control:
             else:
                 self._v, self._zeta = v, zeta
             self._bc(self._zeta)                                # set_zeta re-applies bcs, control.py:1847-1856
+            g = self._dirichlet_data()
+            if g is not None:                                   # set_v re-applies the (inhomogeneous) bcs, 1836-1845
+                self._v[:, self._bc_dofs] = g
             return self.last_ksp
 
         # ------------------------------------------------------------------ Stokes control
@@ -248,6 +286,8 @@ class Control:
                 raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
             if not self._is_linear():
                 raise NotImplementedError("incompressible_linear_solve needs a linear forward operator")
+            if self._bc_values is not None:
+                raise NotImplementedError("incompressible_linear_solve with inhomogeneous Dirichlet data is not wired yet")
             n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
             N = n_t - 1 if CN else n_t
             n_p = space_p["M_p"].shape[0]
@@ -341,6 +381,8 @@ class Control:
             """control/control.py:3377-3590: Picard / Gauss-Newton loop.  Every outer iteration
             hands new ``K_i`` values to the GPU (``MultiBlockSystem.set_K``) and solves for
             the increment."""
+            if self._bc_values is not None:
+                raise NotImplementedError("non_linear_solve with inhomogeneous Dirichlet data is not wired yet")
             n_t, n = self._n_t, self._n
             v_old = self._v.copy()
             zeta_old = self._zeta.copy()

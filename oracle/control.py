@@ -84,9 +84,11 @@ def system_solve(apply_A, nullspace, u_0, u_1, b_0, b_1, *, solver_parameters, p
 def linear_solve(M, K_levels, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs,
                  v_d=None, f=None, v_0=None, check_v_d=True, check_f=True,
                  P=None, solver_parameters=None, Multigrid=False, lambda_v_bounds=None,
-                 inner="amg", amg_params=None, pc_mode="triangular", literal=False):
+                 inner="amg", amg_params=None, pc_mode="triangular", literal=False, bc_values=None):
     """``Instationary.linear_solve`` on assembled matrices.  Returns a dict with the
-    unpacked n_t-level ``v``/``zeta``, the raw block solution and the KSP result."""
+    unpacked n_t-level ``v``/``zeta``, the raw block solution and the KSP result.
+    ``bc_values`` (n_t, len(bdofs)): inhomogeneous Dirichlet data of the state, lifted into the
+    right-hand sides and re-imposed on the solution (``set_v``, control/control.py:1836-1845)."""
     t_0, T_f = time_interval
     tau = (T_f - t_0) / (n_t - 1.0)
     n = M.shape[0]
@@ -98,7 +100,7 @@ def linear_solve(M, K_levels, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs,
         K_list = list(K_levels)
     nullspace = kkt.DirichletBCNullspace(bdofs)
     b_0, b_1 = kkt.build_rhs(M, K_list, tau, n_t, CN, bdofs, v_d, f, v_0,
-                             check_v_d=check_v_d, check_f=check_f)
+                             check_v_d=check_v_d, check_f=check_f, bc_values=bc_values)
     if literal:
         blocks = kkt.build_blocks(M, K_list, tau, beta, n_t, CN)
 
@@ -133,6 +135,8 @@ def linear_solve(M, K_levels, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs,
     kkt_res = np.sqrt(np.linalg.norm(c0 - y0) ** 2 + np.linalg.norm(c1 - y1) ** 2)
     v_full, zeta_full = kkt.unpack_solution(v, zeta, n_t, CN,
                                             v_0 if (check_f and check_v_d) else None)
+    if bc_values is not None:
+        v_full[:, bdofs] = bc_values
     return dict(v=v_full, zeta=zeta_full, v_blocks=v, zeta_blocks=zeta, ksp=res,
                 kkt_residual=kkt_res, b_0=b_0, b_1=b_1, tau=tau, pc_fn=pc_fn)
 

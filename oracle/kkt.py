@@ -200,38 +200,62 @@ def kkt_apply_fused(M, K_levels, tau, beta, n_t, CN, bdofs, x0, x1, eps_unused=N
 
 
 # --------------------------------------------------------------------------------------
-# Right-hand side: control/control.py:2980-3243 (homogeneous Dirichlet data)
+# Right-hand side: control/control.py:2980-3243
 # --------------------------------------------------------------------------------------
-def build_rhs(M, K_levels, tau, n_t, CN, bdofs, v_d, f, v_0, check_v_d=True, check_f=True):
+def build_rhs(M, K_levels, tau, n_t, CN, bdofs, v_d, f, v_0, check_v_d=True, check_f=True, bc_values=None):
     """v_d, f: (n_t, n) cofunction values (already tested against the basis, i.e.
     ``M @ nodal``), or, when check_* is False, the ready right-hand-side blocks (N, n)
-    that are passed through untouched (control/control.py:3008, 3031, 3169, 3216)."""
+    that are passed through untouched (control/control.py:3008, 3031, 3169, 3216).
+    ``bc_values`` (n_t, len(bdofs)): inhomogeneous, time-dependent Dirichlet data of the state; the
+    reference lifts them into the right-hand sides (``v_inhom``, control/control.py:2993-3124 BE,
+    3137-3212 CN) and solves with homogenised conditions."""
     if sp.issparse(K_levels):
         K_levels = [K_levels] * n_t
     N = n_blocks(n_t, CN)
     n = M.shape[0]
     b_0 = np.zeros((N, n))
     b_1 = np.zeros((N, n))
+    g = None
+    if bc_values is not None:
+        g = np.zeros((n_t, n))
+        g[:, bdofs] = bc_values
     if not CN:
         if check_v_d:
             b_0[:n_t - 1] = tau * v_d[:n_t - 1]
+            if g is not None:                           # 2993-3001, 3043-3053
+                b_0[:n_t - 1] -= tau * (M @ g[:n_t - 1].T).T
             b_0[:, bdofs] = 0.0
         else:
             b_0[:] = v_d
         if check_f:
             b_1[0] = (tau * K_levels[0] + M) @ v_0
             b_1[1:] = tau * f[1:]
+            if g is not None:                           # 3014-3023, 3062-3088, 3100-3124
+                for i in range(n_t):
+                    b_1[i] -= (tau * K_levels[i] + M) @ g[i]
+                    if i > 0:
+                        b_1[i] += M @ g[i - 1]
             b_1[:, bdofs] = 0.0
         else:
             b_1[:] = f
     else:
         if check_v_d:
             b_0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+            if g is not None:                           # 3137-3163
+                for i in range(N):
+                    b_0[i] -= 0.5 * tau * (M @ g[i + 1])
+                    if i > 0:
+                        b_0[i] -= 0.5 * tau * (M @ g[i])
             b_0[:, bdofs] = 0.0
         else:
             b_0[:] = v_d
         if check_f:
             b_1[:] = 0.5 * tau * (f[:-1] + f[1:])
+            if g is not None:                           # 3173-3212
+                for i in range(N):
+                    b_1[i] -= (0.5 * tau * K_levels[i + 1] + M) @ g[i + 1]
+                    if i > 0:
+                        b_1[i] -= (0.5 * tau * K_levels[i] - M) @ g[i]
             b_1[:, bdofs] = 0.0
         else:
             b_1[:] = f

@@ -108,3 +108,28 @@ def test_host_amg_setup_matches_oracle_without_a_gpu(nx, coarse_max):
         assert [int(v) for v in lz[:nl.value]] == [int((abs(L.A.data) > 1e-13 * abs(L.A.data).max()).sum()) for L in H.levels]
         assert np.array_equal(agg, H.levels[0].agg)
         assert np.allclose(lr[:nl.value], [L.rho for L in H.levels], rtol=1e-12, atol=0.0)
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_host_rhs_with_inhomogeneous_dirichlet_data_matches_oracle(CN):
+    """control_b200.control.build_rhs (host vector algebra of the caller, control/control.py:2980-3243,
+    including the ``v_inhom`` lifting of time-dependent Dirichlet data and per-level K_i) against the
+    oracle's restatement -- no GPU involved."""
+    import numpy as np
+    from control_b200.control import build_rhs
+    from oracle import kkt
+    from synthetic import fem
+    M, K, coords, bd = fem.assemble_p1_2d(7, 6, 2.0, 1.0)
+    n, n_t = M.shape[0], 6
+    tau = 0.2
+    rng = np.random.default_rng(2)
+    Ks = [(K + 0.1 * i * M).tocsr() for i in range(n_t)]
+    v_d = rng.standard_normal((n_t, n))
+    f = rng.standard_normal((n_t, n))
+    g = rng.standard_normal((n_t, bd.size))
+    v_0 = rng.standard_normal(n)
+    for bc_values in (None, g):
+        a0, a1 = build_rhs(M, Ks[0], tau, n_t, CN, bd, v_d, f, v_0, bc_values=bc_values, K_levels=Ks)
+        r0, r1 = kkt.build_rhs(M, Ks, tau, n_t, CN, bd, v_d, f, v_0, bc_values=bc_values)
+        assert np.abs(a0 - r0).max() <= 1e-13 * np.abs(r0).max()
+        assert np.abs(a1 - r1).max() <= 1e-13 * np.abs(r1).max()

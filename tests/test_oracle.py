@@ -500,3 +500,67 @@ def test_instationary_stokes_known_answer(CN):
     pscale = kat.l2_error(Mp, shift(q["p_ref"]), 0 * q["p_ref"])
     assert kat.l2_error(Mp, shift(p), shift(q["p_ref"])) < 1e-8 * pscale
     assert kat.l2_error(Mp, shift(mu), shift(q["mu_ref"])) < 1e-8 * pscale
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_inhomogeneous_dirichlet_lifting_against_direct_solve(CN):
+    """Time-dependent inhomogeneous Dirichlet data (control/control.py:2993-3124 BE, 3137-3212 CN): the
+    lifted right-hand sides + homogenised solve must give the solution of the un-eliminated block system
+    with the boundary rows replaced by v = g, zeta = 0 (assembled explicitly and solved directly)."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    M, K, coords, bd = fem.assemble_p1_2d(6, 5, 2.0, 1.0)
+    n, n_t, beta = M.shape[0], 5, 1e-2
+    tau = 1.0 / (n_t - 1)
+    N = kkt.n_blocks(n_t, CN)
+    rng = np.random.default_rng(4)
+    v_d = (M @ rng.standard_normal((n_t, n)).T).T
+    f = (M @ rng.standard_normal((n_t, n)).T).T
+    x, y = coords[bd, 0], coords[bd, 1]
+    g = np.stack([(1.0 + t) * np.sin(x + 2.0 * y) + t for t in tau * np.arange(n_t)])      # (n_t, n_bc)
+    v_0 = rng.standard_normal(n)
+    v_0[bd] = g[0]
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 200, "maximum_iterations": 400, "relative_tolerance": 1e-13,
+           "absolute_tolerance": 0.0}
+    r = control.linear_solve(M, K, beta=beta, n_t=n_t, CN=CN, bdofs=bd, v_d=v_d, f=f, v_0=v_0, bc_values=g,
+                             solver_parameters=sp_, lambda_v_bounds=(0.5, 2.0), inner="exact")
+    assert r["ksp"].reason > 0
+    # ---- the same problem without elimination
+    b00, b01, b10, b11 = kkt.build_blocks(M, [K] * n_t, tau, beta, n_t, CN)
+
+    def big(d):
+        rows = [[d.get((i, j)) for j in range(N)] for i in range(N)]
+        return sp.bmat([[a if a is not None else sp.csr_matrix((n, n)) for a in row] for row in rows], format="lil")
+    A = sp.bmat([[big(b00), big(b01)], [big(b10), big(b11)]], format="lil")
+    rhs0 = np.zeros((N, n))
+    rhs1 = np.zeros((N, n))
+    if CN:
+        rhs0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+        rhs1[:] = 0.5 * tau * (f[:-1] + f[1:])
+        rhs0[0] -= 0.5 * tau * (M @ v_0)
+        rhs1[0] -= (0.5 * tau * K - M) @ v_0
+        levels = np.arange(1, n_t)            # unknown block i = state at level i + 1
+    else:
+        rhs0[:n_t - 1] = tau * v_d[:n_t - 1]
+        rhs1[0] = (tau * K + M) @ v_0
+        rhs1[1:] = tau * f[1:]
+        levels = np.arange(n_t)
+    b = np.concatenate([rhs0.ravel(), rhs1.ravel()])
+    for i in range(N):
+        for k, dof in enumerate(bd):
+            r0 = i * n + dof                  # adjoint-equation row -> zeta_i = 0 on the boundary
+            A[r0, :] = 0.0
+            A[r0, N * n + i * n + dof] = 1.0
+            b[r0] = 0.0
+            r1 = N * n + i * n + dof          # state-equation row -> v_i = g on the boundary
+            A[r1, :] = 0.0
+            A[r1, i * n + dof] = 1.0
+            b[r1] = g[levels[i], k]
+    sol = spla.spsolve(A.tocsc(), b)
+    v_dir = sol[:N * n].reshape(N, n)
+    z_dir = sol[N * n:].reshape(N, n)
+    v_lift = r["v"][1:] if CN else r["v"]
+    z_lift = r["zeta"][:-1] if CN else r["zeta"]
+    assert np.abs(v_lift - v_dir).max() < 1e-9 * np.abs(v_dir).max()
+    assert np.abs(z_lift - z_dir).max() < 1e-9 * np.abs(z_dir).max()
+    assert np.array_equal(r["v"][1:][:, bd] if CN else r["v"][:, bd], g[1:] if CN else g)
