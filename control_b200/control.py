@@ -267,8 +267,9 @@ class Control:
                                         Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None, v_d=None,
                                         f=None, div_v=None, div_zeta=None, print_error=True, create_output=False,
                                         plots=False, amg=None, amg_p=None):
-            """control/control.py:3592-4725 (homogeneous Dirichlet velocity data, time-independent
-            linear forward operator).  ``nullspace_p``: None or "constant" -- the pressure blocks
+            """control/control.py:3592-4725 (time-independent linear forward operator; Dirichlet velocity
+            data homogeneous or, through ``bc_values`` of the constructor, inhomogeneous and time
+            dependent).  ``nullspace_p``: None or "constant" -- the pressure blocks
             carry ConstantNullspace as in every caller of the reference (test/test_control.py,
             README.md).  Sets ``_v``, ``_zeta``, ``_p``, ``_mu`` and returns the KSP information."""
             from .stokes import StokesSystem
@@ -286,8 +287,6 @@ class Control:
                 raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
             if not self._is_linear():
                 raise NotImplementedError("incompressible_linear_solve needs a linear forward operator")
-            if self._bc_values is not None:
-                raise NotImplementedError("incompressible_linear_solve with inhomogeneous Dirichlet data is not wired yet")
             n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
             N = n_t - 1 if CN else n_t
             n_p = space_p["M_p"].shape[0]
@@ -300,6 +299,11 @@ class Control:
             K = self._forward_matrix
             b_0_0, b_0_1 = self._build_rhs(v_0, v_d, f, K, check_v_d, check_f)         # 3961-4243
             b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)      # 4107-4128, 4207-4228
+            g = self._dirichlet_data()
+            if div_v is None and g is not None:                 # b_1_0[i] -= tau B v_inhom (4107-4119, 4207-4219)
+                lift = np.zeros((n_t, n))
+                lift[:, self._bc_dofs] = g
+                b_1_0 -= tau * (space_p["B"] @ (lift[1:] if CN else lift).T).T
             b_1_1 = np.zeros((N, n_p)) if div_zeta is None else np.array(div_zeta, dtype=float)
             if CN:                                                                        # 4233-4234
                 b_1_0 = _apply_T_2(b_1_0)
@@ -335,6 +339,8 @@ class Control:
                 self._v, self._zeta = u_0[:N].copy(), u_0[N:].copy()
             self._p, self._mu = u_1[N:].copy(), u_1[:N].copy()
             self._bc(self._zeta)
+            if g is not None:                                   # set_v re-applies the (inhomogeneous) bcs
+                self._v[:, self._bc_dofs] = g
             return self.last_ksp
 
         # ------------------------------------------------------------------ non_linear_solve

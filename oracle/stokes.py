@@ -262,12 +262,15 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
 def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, v_d, f,
                                 v_0=None, div_v=None, div_zeta=None, solver_parameters=None, lambda_v_bounds=None,
                                 lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None,
-                                check_v_d=True, check_f=True):
+                                check_v_d=True, check_f=True, bc_values=None):
     """``Control.Instationary.incompressible_linear_solve`` for homogeneous Dirichlet velocity data
     (control/control.py:3592-4725): right-hand sides (3961-4243; the velocity rows are those of
     the heat problem, the pressure rows are zero unless div_v / div_zeta are given), outer solve,
     unpacking (4705-4725).  ``v_d``, ``f``: (n_t, n_v) cofunction values, or ready (N, n_v) blocks
-    when check_v_d / check_f are False (the ``v_d=`` / ``f=`` keywords of the reference).  Returns
+    when check_v_d / check_f are False (the ``v_d=`` / ``f=`` keywords of the reference).
+    ``bc_values`` (n_t, len(bdofs_v)): inhomogeneous time-dependent velocity data, lifted into the
+    velocity rows as in the heat problem and into the divergence rows, ``b_1_0[i] -= tau B v_inhom``
+    (control/control.py:4107-4119 BE, 4207-4219 CN), and re-imposed on the solution.  Returns
     (v, zeta, p, mu, KSPResult) with v, zeta of n_t levels and p, mu of N levels."""
     t_0, T_f = time_interval
     tau = (T_f - t_0) / (n_t - 1.0)
@@ -275,8 +278,13 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
     n_v, n_p = M_v.shape[0], M_p.shape[0]
     if v_0 is None:
         v_0 = np.zeros(n_v)
-    b_0_0, b_0_1 = kkt.build_rhs(M_v, K_v, tau, n_t, CN, bdofs_v, v_d, f, v_0, check_v_d=check_v_d, check_f=check_f)
+    b_0_0, b_0_1 = kkt.build_rhs(M_v, K_v, tau, n_t, CN, bdofs_v, v_d, f, v_0, check_v_d=check_v_d, check_f=check_f,
+                                 bc_values=bc_values)
     b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)
+    if div_v is None and bc_values is not None:
+        g = np.zeros((n_t, n_v))
+        g[:, bdofs_v] = bc_values
+        b_1_0 -= tau * (B @ (g[1:] if CN else g).T).T
     b_1_1 = np.zeros((N, n_p)) if div_zeta is None else np.array(div_zeta, dtype=float)
     if CN:                                                         # 4233-4234
         b_1_0 = kkt.apply_T_2(b_1_0)
@@ -296,4 +304,6 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
     else:
         v, zeta = u_0[:N].copy(), u_0[N:].copy()
     zeta[:, bdofs_v] = 0.0
+    if bc_values is not None:
+        v[:, bdofs_v] = bc_values
     return v, zeta, u_1[N:].copy(), u_1[:N].copy(), res

@@ -212,3 +212,44 @@ def test_instationary_stokes_known_answer_on_gpu(CN):
     assert kat.l2_error(Mp, shift(c._p), shift(q["p_ref"])) < 1e-8 * pscale
     assert kat.l2_error(Mp, shift(c._mu), shift(q["mu_ref"])) < 1e-8 * pscale
     c.close()
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_stokes_control_with_inhomogeneous_velocity_data(CN):
+    """Time-dependent inhomogeneous Dirichlet velocity data (the setting of the reference's own
+    instationary Stokes tests, test/test_control.py:3045-3302) through the CUDA path against the oracle,
+    whose lifting is checked against a direct un-eliminated solve in tests/test_oracle.py."""
+    import kat
+    from control_b200 import Control
+    q = kat.stokes_problem(5, 5, CN)
+    th, bd = q["th"], q["bdofs"]
+    n_v = q["M"].shape[0]
+    comp = (bd % 2 == 0)
+
+    def bc_values(t):
+        return (1.0 + t) * np.where(comp, 1.0, 0.5)          # a constant vector field: zero net flux
+    times = q["tau"] * np.arange(q["n_t"])
+    g = np.stack([bc_values(t) for t in times])
+    v_0 = np.zeros(n_v)
+    v_0[0::2], v_0[1::2] = 1.0, 0.5
+    idx = {round(float(t), 12): i for i, t in enumerate(times)}
+    c = Control.Instationary(q["M"], q["K"], desired_state=lambda t: (q["v_d"][idx[round(float(t), 12)]],
+                                                                    q["v_hat"][idx[round(float(t), 12)]]),
+                             force_f=lambda t: q["f"][idx[round(float(t), 12)]], beta=q["beta"], CN=CN, n_t=q["n_t"],
+                             time_interval=q["time_interval"], bc_dofs=bd, bc_values=bc_values, initial_condition=v_0)
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 300, "relative_tolerance": 1e-9, "absolute_tolerance": 0.0,
+           "gmres_restart": 100}
+    info = c.incompressible_linear_solve("constant", space_p=dict(B=th["B"], M_p=th["M_p"], K_p=th["K_p"]),
+                                         solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"],
+                                         lambda_p_bounds=q["lambda_p_bounds"], amg=AMG, amg_p=AMG_P)
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+        time_interval=q["time_interval"], bdofs_v=bd, v_d=q["v_d"], f=q["f"], v_0=v_0, bc_values=g,
+        solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+        amg_params=AMG, amg_params_p=AMG_P)
+    assert info.reason == res.reason > 0
+    assert abs(info.its - res.its) <= max(1, int(0.03 * res.its))
+    assert _rel(c._v, v) < 1e-5 and _rel(c._zeta, zeta) < 1e-5
+    assert _rel(c._p, p) < 1e-4 and _rel(c._mu, mu) < 1e-4
+    assert np.array_equal(c._v[1:][:, bd], g[1:])
+    c.close()

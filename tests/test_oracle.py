@@ -564,3 +564,81 @@ def test_inhomogeneous_dirichlet_lifting_against_direct_solve(CN):
     assert np.abs(v_lift - v_dir).max() < 1e-9 * np.abs(v_dir).max()
     assert np.abs(z_lift - z_dir).max() < 1e-9 * np.abs(z_dir).max()
     assert np.array_equal(r["v"][1:][:, bd] if CN else r["v"][:, bd], g[1:] if CN else g)
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_stokes_inhomogeneous_dirichlet_lifting_against_direct_solve(CN):
+    """Inhomogeneous velocity data in the Stokes driver (control/control.py:3961-4243): lifted right-hand
+    sides + homogenised solve against the un-eliminated outer block system with the boundary rows replaced
+    (v = g, zeta = 0), solved by dense least squares (the pressures are determined up to one constant per
+    block).  Boundary data with zero net flux (a constant vector field), so the system is consistent."""
+    from oracle import stokes
+    th = fem.assemble_taylor_hood_2d(3, 3, 1.0, 1.0)
+    M, K, B, Mp, Kp, bd = th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], th["bdofs_v"]
+    n_v, n_p, n_t, beta = M.shape[0], Mp.shape[0], 4, 1e-1
+    tau = 1.0 / (n_t - 1)
+    N = kkt.n_blocks(n_t, CN)
+    rng = np.random.default_rng(8)
+    v_d = (M @ rng.standard_normal((n_t, n_v)).T).T
+    f = (M @ rng.standard_normal((n_t, n_v)).T).T
+    comp = (bd % 2 == 0)
+    g = np.stack([(1.0 + t) * np.where(comp, 1.0, 0.5) for t in tau * np.arange(n_t)])        # constant field x (1 + t)
+    v_0 = np.zeros(n_v)
+    v_0[0::2], v_0[1::2] = 1.0, 0.5                                   # the same field in the interior at t = 0
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 300, "maximum_iterations": 600, "relative_tolerance": 1e-12,
+           "absolute_tolerance": 0.0}
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        M, K, B, Mp, Kp, beta=beta, n_t=n_t, CN=CN, bdofs_v=bd, v_d=v_d, f=f, v_0=v_0, bc_values=g,
+        solver_parameters=sp_, lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0), inner="exact",
+        amg_params_p=dict(coarse_max=10 ** 6))
+    assert res.reason > 0
+    # ---- un-eliminated outer system: [[KKT, tau B^T (x) I], [tau B (x) I, 0]] on x = [v | zeta | mu | p]
+    b00, b01, b10, b11 = kkt.build_blocks(M, [K] * n_t, tau, beta, n_t, CN)
+    L0 = N * n_v
+    A = np.zeros((2 * L0 + 2 * N * n_p, 2 * L0 + 2 * N * n_p))
+    for d, (ro, co) in ((b00, (0, 0)), (b01, (0, L0)), (b10, (L0, 0)), (b11, (L0, L0))):
+        for (i, j), blk in d.items():
+            if blk is not None:
+                A[ro + i * n_v:ro + (i + 1) * n_v, co + j * n_v:co + (j + 1) * n_v] += blk.toarray()
+    Bd = B.toarray()
+    P0 = 2 * L0
+    for i in range(2 * N):
+        A[i * n_v:(i + 1) * n_v, P0 + i * n_p:P0 + (i + 1) * n_p] += tau * Bd.T
+        A[P0 + i * n_p:P0 + (i + 1) * n_p, i * n_v:(i + 1) * n_v] += tau * Bd
+    rhs0 = np.zeros((N, n_v))
+    rhs1 = np.zeros((N, n_v))
+    if CN:
+        rhs0[:] = 0.5 * tau * (v_d[:-1] + v_d[1:])
+        rhs1[:] = 0.5 * tau * (f[:-1] + f[1:])
+        rhs0[0] -= 0.5 * tau * (M @ v_0)
+        rhs1[0] -= (0.5 * tau * K - M) @ v_0
+        levels = np.arange(1, n_t)
+    else:
+        rhs0[:n_t - 1] = tau * v_d[:n_t - 1]
+        rhs1[0] = (tau * K + M) @ v_0
+        rhs1[1:] = tau * f[1:]
+        levels = np.arange(n_t)
+    b = np.concatenate([rhs0.ravel(), rhs1.ravel(), np.zeros(2 * N * n_p)])
+    for i in range(N):
+        for k, dof in enumerate(bd):
+            r0 = i * n_v + dof
+            A[r0, :] = 0.0
+            A[r0, L0 + i * n_v + dof] = 1.0
+            b[r0] = 0.0
+            r1 = L0 + i * n_v + dof
+            A[r1, :] = 0.0
+            A[r1, i * n_v + dof] = 1.0
+            b[r1] = g[levels[i], k]
+    sol = np.linalg.lstsq(A, b, rcond=None)[0]
+    assert np.linalg.norm(A @ sol - b) < 1e-10 * np.linalg.norm(b)            # consistent system
+    v_dir = sol[:L0].reshape(N, n_v)
+    z_dir = sol[L0:2 * L0].reshape(N, n_v)
+    pr = sol[P0:].reshape(2 * N, n_p)
+    v_l = v[1:] if CN else v
+    z_l = zeta[:-1] if CN else zeta
+    assert np.abs(v_l - v_dir).max() < 1e-8 * np.abs(v_dir).max()
+    assert np.abs(z_l - z_dir).max() < 1e-8 * max(np.abs(z_dir).max(), 1e-300)
+    mu_dir, p_dir = pr[:N], pr[N:]
+    c = lambda a: a - a.mean(axis=1, keepdims=True)                           # noqa: E731
+    assert np.abs(c(p) - c(p_dir)).max() < 1e-7 * max(np.abs(c(p_dir)).max(), 1e-300)
+    assert np.abs(c(mu) - c(mu_dir)).max() < 1e-7 * max(np.abs(c(mu_dir)).max(), 1e-300)
