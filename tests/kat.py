@@ -136,3 +136,45 @@ def instationary_stokes_kat(CN, nx=4, beta=1e-2):
                 p_ref=p_ref, mu_ref=mu_ref, v_unknown=v_unknown, z_unknown=z_unknown, v_d=b_0, f=b_1, div_v=div_v,
                 div_zeta=div_zeta, lambda_v_bounds=(0.25, 1.5625), lambda_p_bounds=(0.25, 2.25),
                 solver_parameters=solver_parameters)
+
+
+def reference_stokes_exact_problem(CN):
+    """The problem of the reference's two instationary Stokes tests with an exact solution
+    (test/test_control.py:3045-3172 BE: 8x8 quads, n_t = 20; 3175-3302 CN: 16x16 quads, n_t = 10): vector
+    Q2 - Q1 on (0, 2)^2, beta = 1, K = vector Laplacian, the analytic desired state and force of the test
+    (interpolated, then tested with the mass matrix), time-dependent inhomogeneous Dirichlet data = the
+    exact velocity, initial condition = the exact velocity at t = 0, Chebyshev bounds (0.25, 1.5625) /
+    (0.25, 2.25).  The reference only runs these (no assertion); the exact velocity is returned so that
+    the discretisation error can be looked at."""
+    nx = 16 if CN else 8
+    n_t = 10 if CN else 20
+    sq = fem.assemble_q2q1_stokes_2d(nx, nx, 2.0, 2.0)
+    M = sq["M_v"]
+    x, y = sq["coords_v"][:, 0] - 1.0, sq["coords_v"][:, 1] - 1.0
+    T_f, beta = 1.0, 1.0
+    tau = T_f / (n_t - 1.0)
+    times = tau * np.arange(n_t)
+
+    def vec(cx, cy):
+        a = np.zeros(M.shape[0])
+        a[0::2], a[1::2] = cx, cy
+        return a
+    v_d_help = vec(4.0 * beta * y * (2.0 * (3.0 * x * x - 1.0) * (y * y - 1.0) + 3.0 * (x * x - 1.0) ** 2),
+                   -4.0 * beta * x * (3.0 * (y * y - 1.0) ** 2 + 2.0 * (x * x - 1.0) * (3.0 * y * y - 1.0)))
+    f_help = vec(2.0 * y * (x ** 2 - 1.0) ** 2 * (y ** 2 - 1.0), -2.0 * x * (x ** 2 - 1.0) * (y ** 2 - 1.0) ** 2)
+    v_hat, f_nodal, true_v = [], [], []
+    for t in times:
+        e = np.exp(T_f - t)
+        v_hat.append(vec(e * (x * y ** 3 + 2.0 * beta * y * (((x * x - 1.0) ** 2) * (y * y - 7.0)
+                                                          - 4.0 * (3.0 * x * x - 1.0) * (y * y - 1.0) + 2.0)),
+                         e * (0.25 * (x ** 4 - y ** 4) - 2.0 * beta * x * (((y * y - 1.0) ** 2) * (x * x - 7.0)
+                                                                       - 4.0 * (x * x - 1.0) * (3.0 * y * y - 1.0) - 2.0)))
+                     + v_d_help)
+        f_nodal.append(vec(e * (-x * y ** 3 - 2.0 * y * (x * x - 1.0) ** 2 * (y * y - 1.0)),
+                           e * (0.25 * (y ** 4 - x ** 4) + 2.0 * x * (x * x - 1.0) * (y * y - 1.0) ** 2)) + f_help)
+        true_v.append(vec(e * x * y ** 3, 0.25 * e * (x ** 4 - y ** 4)))
+    v_hat, f_nodal, true_v = np.stack(v_hat), np.stack(f_nodal), np.stack(true_v)
+    bd = sq["bdofs_v"]
+    return dict(sq=sq, M=M, K=sq["L_v"], B=sq["B"], bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN,
+                time_interval=(0.0, T_f), v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T, true_v=true_v,
+                bc_values=true_v[:, bd], v_0=true_v[0], lambda_v_bounds=(0.25, 1.5625), lambda_p_bounds=(0.25, 2.25))

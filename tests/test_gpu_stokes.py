@@ -253,3 +253,34 @@ def test_stokes_control_with_inhomogeneous_velocity_data(CN):
     assert _rel(c._p, p) < 1e-4 and _rel(c._mu, mu) < 1e-4
     assert np.array_equal(c._v[1:][:, bd], g[1:])
     c.close()
+
+
+@pytest.mark.parametrize("CN", [False, True])
+def test_reference_instationary_stokes_exact_solution_problem_on_gpu(CN):
+    """The reference's two instationary Stokes tests (test/test_control.py:3045-3302) through the CUDA
+    path with the reference's default solver parameters: converges, matches the oracle, and reproduces
+    the analytic velocity up to the discretisation error."""
+    import kat
+    from control_b200 import Control
+    q = kat.reference_stokes_exact_problem(CN)
+    sq, bd = q["sq"], q["bdofs"]
+    times = q["tau"] * np.arange(q["n_t"])
+    idx = {round(float(t), 12): i for i, t in enumerate(times)}
+    c = Control.Instationary(q["M"], q["K"], desired_state=lambda t: (q["v_d"][idx[round(float(t), 12)]],
+                                                                    q["v_hat"][idx[round(float(t), 12)]]),
+                             force_f=lambda t: q["f"][idx[round(float(t), 12)]], beta=q["beta"], CN=CN, n_t=q["n_t"],
+                             time_interval=q["time_interval"], bc_dofs=bd,
+                             bc_values=lambda t: q["bc_values"][idx[round(float(t), 12)]], initial_condition=q["v_0"])
+    info = c.incompressible_linear_solve("constant", space_p=dict(B=q["B"], M_p=sq["M_p"], K_p=sq["L_p"]),
+                                         lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+                                         print_error=False)
+    assert info.reason > 0 and info.its <= 40
+    err = kat.l2_error(q["M"], c._v, q["true_v"]) / kat.l2_error(q["M"], q["true_v"], 0 * q["true_v"])
+    assert err < (1e-4 if CN else 1e-3)
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        q["M"], q["K"], q["B"], sq["M_p"], sq["L_p"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+        time_interval=q["time_interval"], bdofs_v=bd, v_d=q["v_d"], f=q["f"], v_0=q["v_0"],
+        bc_values=q["bc_values"], lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    assert abs(info.its - res.its) <= 1
+    assert _rel(c._v, v) < 1e-4          # both stop at rtol 1e-6
+    c.close()

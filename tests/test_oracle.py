@@ -642,3 +642,22 @@ def test_stokes_inhomogeneous_dirichlet_lifting_against_direct_solve(CN):
     c = lambda a: a - a.mean(axis=1, keepdims=True)                           # noqa: E731
     assert np.abs(c(p) - c(p_dir)).max() < 1e-7 * max(np.abs(c(p_dir)).max(), 1e-300)
     assert np.abs(c(mu) - c(mu_dir)).max() < 1e-7 * max(np.abs(c(mu_dir)).max(), 1e-300)
+
+
+@pytest.mark.parametrize("CN", [False, True])
+def test_reference_instationary_stokes_exact_solution_problem(CN):
+    """test/test_control.py:3045-3172 (BE) and 3175-3302 (CN) re-created (tests/kat.py): the reference
+    only runs them; here the run must converge within the reference's default solver parameters
+    (FGMRES, 100 iterations, rtol 1e-6, control/control.py:4291-4297) AND reproduce the analytic velocity
+    up to the discretisation error."""
+    from oracle import stokes
+    q = kat.reference_stokes_exact_problem(CN)
+    sq = q["sq"]
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        q["M"], q["K"], q["B"], sq["M_p"], sq["L_p"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"],
+        bc_values=q["bc_values"], lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+        inner="exact")                                       # solver_parameters=None: the reference's defaults
+    assert res.reason > 0 and res.its <= 40
+    err = kat.l2_error(q["M"], v, q["true_v"]) / kat.l2_error(q["M"], q["true_v"], 0 * q["true_v"])
+    assert err < (1e-4 if CN else 1e-3)                      # measured 3.1e-5 (CN, 16x16, n_t=10), 4.2e-4 (BE, 8x8, n_t=20)
