@@ -178,3 +178,33 @@ def reference_stokes_exact_problem(CN):
     return dict(sq=sq, M=M, K=sq["L_v"], B=sq["B"], bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN,
                 time_interval=(0.0, T_f), v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T, true_v=true_v,
                 bc_values=true_v[:, bd], v_0=true_v[0], lambda_v_bounds=(0.25, 1.5625), lambda_p_bounds=(0.25, 2.25))
+
+
+def mms_heat_problem(N, n_t=100, CN=True):
+    """The manufactured solution of the reference's heat-control convergence studies
+    (test/test_control.py:1983-2138 CN / 1658-1826 BE, degree 1): P1 on an N x N mesh of (0, 2)^2,
+    beta = 1, t_f = 2, v = 1 + (c_1 + c_2(t)) cos cos, zeta = (e^{t_f} - e^t) cos cos, f = 0, Dirichlet
+    data v = 1 on the boundary (inhomogeneous), initial condition = v(0).  The reference prints observed
+    orders without asserting them."""
+    M, K, coords, bd = fem.assemble_p1_2d(N, N, 2.0, 2.0)
+    x, y = coords[:, 0] - 1.0, coords[:, 1] - 1.0
+    beta, t_f = 1.0, 2.0
+    tau = t_f / (n_t - 1.0)
+    times = tau * np.arange(n_t)
+    cc = np.cos(0.5 * np.pi * x) * np.cos(0.5 * np.pi * y)
+    pi2 = np.pi * np.pi
+
+    def v_exact(t):
+        return 1.0 + ((2.0 / (pi2 * beta)) * np.exp(t_f) - (2.0 / ((2.0 + pi2) * beta)) * np.exp(t)) * cc
+
+    def zeta_exact(t):
+        return (np.exp(t_f) - np.exp(t)) * cc
+
+    def v_hat(t):                                   # desired state, test/test_control.py:2016-2022
+        c = (2.0 / (pi2 * beta) + 0.5 * pi2) * np.exp(t_f) + (1.0 - 2.0 / ((2.0 + pi2) * beta) - 0.5 * pi2) * np.exp(t)
+        return 1.0 + c * cc
+    vh = np.stack([v_hat(t) for t in times])
+    return dict(M=M, K=K, coords=coords, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN, time_interval=(0.0, t_f),
+                v_hat=vh, v_d=(M @ vh.T).T, f=np.zeros((n_t, M.shape[0])), v_0=v_exact(0.0),
+                bc_values=np.ones((n_t, bd.size)), v_exact=np.stack([v_exact(t) for t in times]),
+                zeta_exact=np.stack([zeta_exact(t) for t in times]))

@@ -158,3 +158,28 @@ def test_linear_solve_with_inhomogeneous_dirichlet_data(CN):
     assert np.abs(c._zeta - ref["zeta"]).max() < tol * np.abs(ref["zeta"]).max()
     assert np.array_equal(c._v[1:, bd], g[1:])
     c.close()
+
+
+def test_reference_mms_heat_problem_on_gpu():
+    """The manufactured heat-control problem of the reference's convergence studies
+    (test/test_control.py:1983-2138) on a 16 x 16 mesh with n_t = 100 -- 99 time blocks, i.e. the wide
+    (ld = 128) kernels -- and inhomogeneous Dirichlet data: same discretisation error as the oracle."""
+    from control_b200 import Control
+    q = kat.mms_heat_problem(16, 100, True)
+    times = q["tau"] * np.arange(q["n_t"])
+
+    def level(t):
+        return int(round(t / q["tau"]))
+    c = Control.Instationary(q["M"], q["K"], desired_state=lambda t: (q["v_d"][level(t)], q["v_hat"][level(t)]),
+                             force_f=lambda t: q["f"][level(t)], beta=q["beta"], n_t=q["n_t"], CN=True,
+                             time_interval=q["time_interval"], bc_dofs=q["bdofs"],
+                             bc_values=lambda t: q["bc_values"][level(t)], initial_condition=q["v_0"])
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 200, "relative_tolerance": 1e-10,
+           "absolute_tolerance": 1e-10}
+    info = c.linear_solve(solver_parameters=sp_, lambda_v_bounds=(0.5, 2.0), print_error=False)
+    assert info.reason > 0
+    ev = np.sqrt(q["tau"]) * kat.l2_error(q["M"], c._v, q["v_exact"])
+    ez = np.sqrt(q["tau"]) * kat.l2_error(q["M"], c._zeta, q["zeta_exact"])
+    assert abs(ev - 0.02218281663521956) < 1e-6 and abs(ez - 0.05136980559114903) < 1e-6      # the oracle's errors
+    assert len(times) == 100
+    c.close()

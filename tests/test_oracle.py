@@ -661,3 +661,23 @@ def test_reference_instationary_stokes_exact_solution_problem(CN):
     assert res.reason > 0 and res.its <= 40
     err = kat.l2_error(q["M"], v, q["true_v"]) / kat.l2_error(q["M"], q["true_v"], 0 * q["true_v"])
     assert err < (1e-4 if CN else 1e-3)                      # measured 3.1e-5 (CN, 16x16, n_t=10), 4.2e-4 (BE, 8x8, n_t=20)
+
+
+def test_reference_mms_heat_convergence_study():
+    """test/test_control.py:1983-2138 (CN, degree 1) re-created with its manufactured solution,
+    inhomogeneous Dirichlet data (v = 1 on the boundary) and n_t = 100: the reference prints the observed
+    orders; here they are asserted (P1: second order in the L2-in-space, l2-in-time norm of the test)."""
+    errs = []
+    for N in (4, 8, 16):
+        q = kat.mms_heat_problem(N, 100, True)
+        sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 200, "relative_tolerance": 1e-10,
+               "absolute_tolerance": 1e-10}                     # the test's solver_parameters (2074-2079)
+        r = control.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=True, time_interval=q["time_interval"],
+                                 bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"], bc_values=q["bc_values"],
+                                 solver_parameters=sp_, inner="exact")
+        assert r["ksp"].reason > 0
+        errs.append((np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["v"], q["v_exact"]),
+                     np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["zeta"], q["zeta_exact"])))
+    e = np.array(errs)
+    orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
+    assert (orders[0] > 1.6).all() and (orders[1] > 1.85).all()          # measured 1.72 / 1.79 and 1.93 / 1.95
