@@ -374,3 +374,34 @@ def assemble_q2q1_stokes_2d(nx, ny, lx=1.0, ly=1.0):
     coords_p = np.stack([X.ravel(), Y.ravel()], axis=1)
     bdofs_v = np.sort(np.concatenate([2 * bd_nodes, 2 * bd_nodes + 1])).astype(np.int32)
     return dict(M_v=M_v, L_v=L_v, B=B, M_p=M_p, L_p=L_p, bdofs_v=bdofs_v, coords_v=coords_v, coords_p=coords_p)
+
+
+def assemble_convection_p1_2d(nx, ny, lx, ly, wind):
+    """P1 convection matrix ``inner(dot(grad(trial), wind), test) * dx`` on the mesh of
+    ``assemble_p1_2d`` (same sparsity pattern, explicit zeros kept), e.g. the forward operator of the
+    reference's convection-diffusion studies (test/test_control.py:2693-2705).  ``wind(x, y)`` returns the
+    two components at the given points; edge-midpoint quadrature (exact for quadratic integrands)."""
+    coords, tris = p1_triangle_mesh(nx, ny, lx, ly)
+    n = coords.shape[0]
+    p = coords[tris]
+    e1 = p[:, 1] - p[:, 0]
+    e2 = p[:, 2] - p[:, 0]
+    det = e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]
+    area = 0.5 * np.abs(det)
+    g = np.empty((tris.shape[0], 3, 2))
+    g[:, 1, 0] = e2[:, 1] / det
+    g[:, 1, 1] = -e2[:, 0] / det
+    g[:, 2, 0] = -e1[:, 1] / det
+    g[:, 2, 1] = e1[:, 0] / det
+    g[:, 0] = -g[:, 1] - g[:, 2]
+    bary = np.array([[0.5, 0.5, 0.0], [0.0, 0.5, 0.5], [0.5, 0.0, 0.5]])       # quadrature points = edge midpoints
+    Ce = np.zeros((tris.shape[0], 3, 3))
+    for q in range(3):
+        xq = np.einsum("a,tad->td", bary[q], p)
+        wx, wy = wind(xq[:, 0], xq[:, 1])
+        wg = wx[:, None] * g[:, :, 0] + wy[:, None] * g[:, :, 1]                # wind . grad(phi_j), (nt, 3)
+        Ce += (area / 3.0)[:, None, None] * bary[q][None, :, None] * wg[:, None, :]   # phi_i(x_q) * (w . grad phi_j)
+    rows = np.repeat(tris, 3, axis=1).ravel()
+    cols = np.tile(tris, (1, 3)).ravel()
+    (C,) = _csr_same_pattern(n, rows, cols, [Ce.ravel()])
+    return C

@@ -9,6 +9,7 @@ T_1 / T_2 itself, control/control.py:3242-3243), FGMRES to 1e-14, Chebyshev boun
 (0.25, 1.5625).
 """
 import numpy as np
+import scipy.sparse as sp
 
 from synthetic import fem
 from synthetic.problems import heat_problem, heat_problem_3d, stokes_problem  # noqa: F401
@@ -208,3 +209,42 @@ def mms_heat_problem(N, n_t=100, CN=True):
                 v_hat=vh, v_d=(M @ vh.T).T, f=np.zeros((n_t, M.shape[0])), v_0=v_exact(0.0),
                 bc_values=np.ones((n_t, bd.size)), v_exact=np.stack([v_exact(t) for t in times]),
                 zeta_exact=np.stack([zeta_exact(t) for t in times]))
+
+
+def mms_convection_diffusion_problem(N, n_t=100, CN=True):
+    """The manufactured solution of the reference's convection-diffusion control studies
+    (test/test_control.py:2675-2857 CN / 2297-2492 BE, degree 1): the fields of ``mms_heat_problem`` with the
+    time-dependent, divergence-free wind cos(pi t / 2) (2 y (1 - x^2), -2 x (1 - y^2)) in the forward
+    operator, i.e. one NON-SYMMETRIC matrix K_i = L + C(t_i) per time level; desired state and force carry
+    the convection of zeta and v (2707-2717, 2763-2774)."""
+    q = mms_heat_problem(N, n_t, CN)
+    M, L, coords = q["M"], q["K"], q["coords"]
+    x, y = coords[:, 0] - 1.0, coords[:, 1] - 1.0
+    tau, t_f, beta = q["tau"], 2.0, q["beta"]
+    times = tau * np.arange(n_t)
+    pi2 = np.pi * np.pi
+
+    def wind_at(t):
+        a = np.cos(0.5 * np.pi * t)
+        return lambda X, Y: (a * 2.0 * (Y - 1.0) * (1.0 - (X - 1.0) ** 2), -a * 2.0 * (X - 1.0) * (1.0 - (Y - 1.0) ** 2))
+    K_levels = []
+    for t in times:
+        C = fem.assemble_convection_p1_2d(N, N, 2.0, 2.0, wind_at(t))
+        assert np.array_equal(C.indices, M.indices) and np.array_equal(L.indices, M.indices)
+        K_levels.append(sp.csr_matrix((L.data + C.data, M.indices, M.indptr), shape=M.shape))
+    sx, cx = np.sin(0.5 * np.pi * x), np.cos(0.5 * np.pi * x)
+    sy, cy = np.sin(0.5 * np.pi * y), np.cos(0.5 * np.pi * y)
+    gx, gy = -0.5 * np.pi * sx * cy, -0.5 * np.pi * cx * sy          # gradient of cos cos
+    v_hat, f_nodal = [], []
+    for t in times:
+        a = np.cos(0.5 * np.pi * t)
+        wx, wy = a * 2.0 * y * (1.0 - x * x), -a * 2.0 * x * (1.0 - y * y)
+        conv_cc = gx * wx + gy * wy                                  # wind . grad(cos cos)
+        cz = np.exp(t_f) - np.exp(t)
+        cv = (2.0 / (pi2 * beta)) * np.exp(t_f) - (2.0 / ((2.0 + pi2) * beta)) * np.exp(t)
+        v_hat.append(q["v_hat"][len(v_hat)] - cz * conv_cc)          # 2707-2724
+        f_nodal.append(cv * conv_cc)                                 # 2769-2774
+    v_hat, f_nodal = np.stack(v_hat), np.stack(f_nodal)
+    q = dict(q)
+    q.update(K_levels=K_levels, v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T)
+    return q
