@@ -423,3 +423,8 @@ class Control:
                 if k + 1 > max_non_linear_iter:
                     break
             return k
+
+
+from .stationary import Stationary as _Stationary  # noqa: E402
+
+Control.Stationary = _Stationary            # control/control.py:100 (heat-type drivers; N = 1 case of the same handle)

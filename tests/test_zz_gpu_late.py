@@ -39,3 +39,74 @@ def test_reference_mms_convection_diffusion_problem_on_gpu():
     ez = np.sqrt(q["tau"]) * kat.l2_error(q["M"], c._zeta, q["zeta_exact"])
     assert abs(ev - 0.022182639553203404) < 1e-6 and abs(ez - 0.05137767135076495) < 1e-6     # the oracle's errors
     c.close()
+
+
+def test_reference_stationary_known_answer_on_gpu():
+    """test/test_control.py:26-119 (``test_stationary_linear_control``) through ``Control.Stationary`` on the
+    device: Q2 on 8x8 quads, no boundary conditions, ready right-hand sides, the test's solver parameters and
+    Chebyshev bounds; the reference asserts 1e-13 (5e-13 here, as for the instationary KATs on the GPU)."""
+    from control_b200 import Control
+    from oracle import stationary
+    from synthetic import fem
+    M, L, coords, _ = fem.assemble_q2_2d(8, 8)
+    K = (L + M).tocsr()
+    beta = 1e-3
+    X0, X1 = coords[:, 0], coords[:, 1]
+    v_ref = X0 * np.exp(X1)
+    zeta_ref = np.sin(np.pi * X0) * np.sin(2.0 * np.pi * X1)
+    b_0 = M @ v_ref + K @ zeta_ref
+    b_1 = K @ v_ref - (1.0 / beta) * (M @ zeta_ref)
+    sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 500, "relative_tolerance": 1e-14,
+           "absolute_tolerance": 1e-14, "monitor_convergence": False}
+    c = Control.Stationary(M, K, beta=beta)
+    info = c.linear_solve(lambda_v_bounds=(0.25, 1.5625), solver_parameters=sp_, v_d=b_0, f=b_1, print_error=False)
+    assert info.reason > 0
+    assert kat.l2_error(M, c._v[None], v_ref[None]) < 5e-13
+    assert kat.l2_error(M, c._zeta[None], zeta_ref[None]) < 5e-13
+    ref = stationary.linear_solve(M, K, beta=beta, bdofs=[], v_d=b_0, f=b_1, check_v_d=False, check_f=False,
+                                  lambda_v_bounds=(0.25, 1.5625), solver_parameters=sp_)
+    assert abs(info.its - ref["ksp"].its) <= 2                  # rtol 1e-14: on the rounding floor
+    c.close()
+
+
+def test_stationary_inhomogeneous_and_non_linear_on_gpu():
+    """``Control.Stationary`` with inhomogeneous Dirichlet data (linear solve) and the Picard / Gauss-Newton loop
+    (control/control.py:630-800) against the oracle's direct restatement of the stationary drivers."""
+    from control_b200 import Control
+    from oracle import stationary
+    from synthetic import fem
+    nx = 8
+    M, L, coords, bd = fem.assemble_p1_2d(nx, nx, 1.0, 1.0)
+    n = M.shape[0]
+    x, y = coords[:, 0], coords[:, 1]
+    v_hat = np.sin(np.pi * x) * np.sin(np.pi * y) * np.exp(x + y)
+    beta = 1e-2
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-10, "absolute_tolerance": 0.0}
+    # linear, inhomogeneous data
+    D_v = (L + 2.0 * M).tocsr()
+    g = np.cos(3.0 * x[bd]) + y[bd]
+    f = M @ (x * y)
+    c = Control.Stationary(M, D_v, desired_state=lambda: (M @ v_hat, v_hat), force_f=lambda: f, beta=beta,
+                           bc_dofs=bd, bc_values=g)
+    info = c.linear_solve(solver_parameters=sp_, lambda_v_bounds=(0.5, 2.0), print_error=False)
+    ref = stationary.linear_solve(M, D_v, beta=beta, bdofs=bd, v_d=M @ v_hat, f=f, bc_values=g, solver_parameters=sp_,
+                                  lambda_v_bounds=(0.5, 2.0))
+    assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1
+    assert np.abs(c._v - ref["v"]).max() < 1e-7 * np.abs(ref["v"]).max()
+    assert np.abs(c._zeta - ref["zeta"]).max() < 1e-7 * np.abs(ref["zeta"]).max()
+    assert np.array_equal(c._v[bd], g)
+    c.close()
+    # non-linear diffusion, Picard and Gauss-Newton
+    D = fem.nonlinear_diffusion_p1_2d(nx, nx, 1.0, 1.0)
+    for gauss_newton in (False, True):
+        c = Control.Stationary(M, D, desired_state=lambda: (M @ v_hat, v_hat), beta=beta, Gauss_Newton=gauss_newton,
+                               bc_dofs=bd)
+        k = c.non_linear_solve(solver_parameters=sp_, lambda_v_bounds=(0.5, 2.0), max_non_linear_iter=30,
+                               print_error_non_linear=False)
+        out = stationary.non_linear_solve(M, lambda v: D(v, gauss_newton), beta=beta, bdofs=bd, v_d=M @ v_hat,
+                                          f=np.zeros(n), solver_parameters=sp_, lambda_v_bounds=(0.5, 2.0),
+                                          max_non_linear_iter=30)
+        assert k == out["iterations"]
+        assert np.allclose(c.non_linear_history, out["history"], rtol=1e-4)
+        assert np.abs(c._v - out["v"]).max() < 1e-5 * np.abs(out["v"]).max()
+        c.close()
