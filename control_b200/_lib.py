@@ -107,6 +107,7 @@ SIGNATURES = {
     "ctl_stokes_vec_len": (C.c_int64, [_H]),
     "ctl_stokes_apply": (C.c_int, [_H, _F64P, _F64P]),
     "ctl_stokes_pc_default_options": (C.c_int, [C.POINTER(ctl_stokes_pc_options)]),
+    "ctl_stokes_set_laplacian_p": (C.c_int, [_H, C.c_void_p]),
     "ctl_stokes_pc_setup": (C.c_int, [_H, C.POINTER(ctl_stokes_pc_options)]),
     "ctl_stokes_pc_apply": (C.c_int, [_H, _F64P, _F64P]),
     "ctl_stokes_pc_fn": (C.c_int, [_H, _F64P, _F64P]),

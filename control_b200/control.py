@@ -260,16 +260,19 @@ class Control:
         def set_space_p(self, space_p):
             """``space_p``: the assembled objects of the pressure space, a dict with the divergence
             matrix ``B`` (n_p x n_v, ``-inner(div(v_trial), p_test) * dx``), the pressure mass
-            matrix ``M_p`` and the pressure Laplacian ``K_p`` (control/control.py:3709, 3746-3747)."""
+            matrix ``M_p`` and the pressure Laplacian ``K_p`` (control/control.py:3709, 3746-3747).
+            Optional ``forward_matrix_p(v_i, t, gauss_newton)`` -> CSR on M_p's pattern: the forward form
+            on the pressure space at the velocity state ``v_i`` (``D_p_i``, control/control.py:3787-3789);
+            needed when the forward operator is not the Stokes one (Navier-Stokes Picard iterations)."""
             self._space_p = space_p
 
         def incompressible_linear_solve(self, nullspace_p=None, *, space_p=None, P=None, solver_parameters=None,
                                         Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None, v_d=None,
                                         f=None, div_v=None, div_zeta=None, print_error=True, create_output=False,
                                         plots=False, amg=None, amg_p=None):
-            """control/control.py:3592-4725 (time-independent linear forward operator; Dirichlet velocity
-            data homogeneous or, through ``bc_values`` of the constructor, inhomogeneous and time
-            dependent).  ``nullspace_p``: None or "constant" -- the pressure blocks
+            """control/control.py:3592-4725 (Dirichlet velocity data homogeneous or, through ``bc_values``
+            of the constructor, inhomogeneous and time dependent; a callable forward matrix is evaluated
+            at the current ``_v`` per time level, with ``space_p["forward_matrix_p"]`` on the pressure space).  ``nullspace_p``: None or "constant" -- the pressure blocks
             carry ConstantNullspace as in every caller of the reference (test/test_control.py,
             README.md).  Sets ``_v``, ``_zeta``, ``_p``, ``_mu`` and returns the KSP information."""
             from .stokes import StokesSystem
@@ -285,8 +288,6 @@ class Control:
                 raise NotImplementedError("user preconditioners are not wired for the Stokes system")
             if Multigrid:
                 raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
-            if not self._is_linear():
-                raise NotImplementedError("incompressible_linear_solve needs a linear forward operator")
             n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
             N = n_t - 1 if CN else n_t
             n_p = space_p["M_p"].shape[0]
@@ -296,8 +297,18 @@ class Control:
                 f = self.construct_f()
             if check_v_d:
                 v_d = self.construct_v_d()
-            K = self._forward_matrix
-            b_0_0, b_0_1 = self._build_rhs(v_0, v_d, f, K, check_v_d, check_f)         # 3961-4243
+            K = self._K_levels(self._v)                             # D_v_i at the current state, 3780-3785
+            D_p = None
+            if self._is_linear():
+                K0 = K
+            else:
+                K0 = self.construct_D_v(v_0, self._time_interval[0])
+                fp = space_p.get("forward_matrix_p")
+                if fp is None:
+                    raise ValueError("a non-linear forward operator needs space_p['forward_matrix_p']")
+                D_p = [fp(self._v[i], t, self._Gauss_Newton) for i, t in enumerate(self._times())]      # 3787-3789
+            b_0_0, b_0_1 = self._build_rhs(v_0, v_d, f, K0, check_v_d, check_f,
+                                           K_levels=None if self._is_linear() else K)  # 3961-4243
             b_1_0 = np.zeros((N, n_p)) if div_v is None else np.array(div_v, dtype=float)      # 4107-4128, 4207-4228
             g = self._dirichlet_data()
             if div_v is None and g is not None:                 # b_1_0[i] -= tau B v_inhom (4107-4119, 4207-4219)
@@ -317,7 +328,9 @@ class Control:
             if getattr(self, "_stokes", None) is None:
                 self._stokes = StokesSystem(self._M, K, space_p["B"], space_p["M_p"], space_p["K_p"], n_t=n_t,
                                             beta=self._beta, CN=CN, time_interval=self._time_interval,
-                                            bc_dofs_v=self._bc_dofs, device=self._dev["device"])
+                                            bc_dofs_v=self._bc_dofs, device=self._dev["device"], D_p=D_p)
+            elif not self._is_linear():
+                self._stokes.set_forward(K, D_p)
             system = self._stokes
             system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
                                         amg_p=amg_p)
@@ -342,6 +355,84 @@ class Control:
             if g is not None:                                   # set_v re-applies the (inhomogeneous) bcs
                 self._v[:, self._bc_dofs] = g
             return self.last_ksp
+
+        def incompressible_non_linear_solve(self, nullspace_p=None, *, space_p=None, P=None, solver_parameters=None,
+                                            Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None,
+                                            max_non_linear_iter=10, relative_non_linear_tol=10.0**-5,
+                                            absolute_non_linear_tol=10.0**-8, print_error_linear=False,
+                                            print_error_non_linear=True, create_output=False, plots=False,
+                                            amg=None, amg_p=None):
+            """control/control.py:4886-5219: Picard loop of Navier-Stokes control.  Every outer iteration
+            re-linearises the forward operator around the new velocity on both spaces, hands the values to
+            the GPU and solves the outer Stokes-type system for the increment there."""
+            if space_p is None:
+                space_p = getattr(self, "_space_p", None)
+                if space_p is None:
+                    raise ValueError("Undefined space_p")               # 4904-4910
+            else:
+                self.set_space_p(space_p)
+            n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
+            N = n_t - 1 if CN else n_t
+            B = space_p["B"]
+            n_p = space_p["M_p"].shape[0]
+            v_old = self._v.copy()
+            zeta_old = self._zeta.copy()
+            p_old = np.array(getattr(self, "_p", np.zeros((N, n_p))), dtype=float)
+            mu_old = np.array(getattr(self, "_mu", np.zeros((N, n_p))), dtype=float)
+            v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
+            if CN:
+                v_old[0] = v_0                                          # 4968-4969
+            zeta_old[n_t - 1] = 0.0
+            f = self.construct_f()
+            v_d = self.construct_v_d()
+            g = self._dirichlet_data()
+            self._v, self._zeta = v_old.copy(), zeta_old.copy()
+
+            def res_eval():                                             # 4979-5072
+                r00, r01 = self.non_linear_res_eval(v_old, zeta_old, v_0, v_d, f)
+                r00 -= tau * (B.T @ mu_old.T).T
+                r01 -= tau * (B.T @ p_old.T).T
+                self._bc(r00)
+                self._bc(r01)
+                r10 = -(B @ (v_old[1:] if CN else v_old).T).T
+                r11 = -(B @ (zeta_old[:-1] if CN else zeta_old).T).T
+                return r00, r01, r10, r11
+
+            def norm(parts):
+                return float(np.sqrt(sum((a ** 2).sum() for a in parts)))
+
+            r = res_eval()
+            norm_0 = norm(r)
+            norm_k, k = norm_0, 0
+            self.non_linear_history = [norm_0]
+            self.inner_iterations = []
+            if print_error_non_linear:
+                print(f"Initial non-linear residual: {norm_0:.16e}")
+            while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+                ksp = self.incompressible_linear_solve(nullspace_p, space_p=space_p, P=P,
+                                                       solver_parameters=solver_parameters, Multigrid=Multigrid,
+                                                       lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds,
+                                                       v_d=r[0], f=r[1], div_v=tau * r[2], div_zeta=tau * r[3],
+                                                       print_error=print_error_linear, amg=amg, amg_p=amg_p)
+                self.inner_iterations.append(ksp.its)
+                v_old = v_old + self._v                                 # 5127-5160
+                if g is not None:
+                    v_old[:, self._bc_dofs] = g
+                p_old = p_old + self._p
+                zeta_old = zeta_old + self._zeta
+                self._bc(zeta_old)
+                mu_old = mu_old + self._mu
+                self._v, self._zeta = v_old.copy(), zeta_old.copy()
+                self._p, self._mu = p_old.copy(), mu_old.copy()
+                r = res_eval()
+                norm_k = norm(r)
+                k += 1
+                self.non_linear_history.append(norm_k)
+                if print_error_non_linear:
+                    print(f"Non-linear solver: iteration {k:d}, non-linear residual norm {norm_k:.16e}")
+                if k + 1 > max_non_linear_iter:
+                    break
+            return k
 
         # ------------------------------------------------------------------ non_linear_solve
         def non_linear_res_eval(self, v_old, zeta_old, v_0, v_d, f):

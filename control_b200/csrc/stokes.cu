@@ -39,6 +39,7 @@ struct ctl_stokes_s {
     std::shared_ptr<SellPattern> fine_p;
     AmgHierarchyDev Kp;
     bool have_Kp = false;
+    std::vector<double> h_Kp_solver;   // ctl_stokes_set_laplacian_p: matrix of solver_K_p when it is not hp's K
     double *d_mp_dinv = nullptr;  // 1 / diag(M_p)
     double *ts_b = nullptr, *ts_x = nullptr;     // [2N][n_p] time-slowest columns of the K_p solves
     double *d_part = nullptr;     // partial column sums, [2 panels][blocks][ld]
@@ -552,6 +553,17 @@ int ctl_stokes_pc_default_options(ctl_stokes_pc_options *o)
     return CTL_OK;
 }
 
+int ctl_stokes_set_laplacian_p(ctl_stokes S, const double *values_host)
+{
+    if (!S) return CTL_ERR_ARG;
+    if (values_host)
+        S->h_Kp_solver.assign(values_host, values_host + S->hp->h_indices.size());
+    else
+        S->h_Kp_solver.clear();
+    S->pc_ready = false;
+    return CTL_OK;
+}
+
 int ctl_stokes_pc_setup(ctl_stokes S, const ctl_stokes_pc_options *opts)
 {
     if (!S) return CTL_ERR_ARG;
@@ -587,7 +599,7 @@ int ctl_stokes_pc_setup(ctl_stokes S, const ctl_stokes_pc_options *opts)
         Kp.n_rows = Kp.n_cols = n_p;
         Kp.indptr = hp->h_indptr;
         Kp.indices = hp->h_indices;
-        Kp.values = hp->h_K[0];
+        Kp.values = S->h_Kp_solver.empty() ? hp->h_K[0] : S->h_Kp_solver;
         if (!S->fine_p) {
             const int rc = sell_build_pattern(hp, hp->loc, S->fine_p);
             if (rc != CTL_OK) {

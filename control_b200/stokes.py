@@ -24,12 +24,17 @@ __all__ = ["StokesSystem"]
 
 class StokesSystem:
     def __init__(self, M_v, K_v, B, M_p, K_p, *, n_t, beta, CN, time_interval=(0.0, 1.0), bc_dofs_v=(),
-                 epsilon=1e-3, device=None):
+                 epsilon=1e-3, device=None, D_p=None):
+        """``K_v``: the forward matrix on the velocity space (one matrix or n_t matrices ``D_v_i``).  ``K_p``: the
+        pressure Laplacian ``solver_K_p`` inverts (control/control.py:3746, 4300-4309).  ``D_p``: the forward
+        form on the PRESSURE space (``D_p_i``, control/control.py:3787-3789; one matrix or n_t matrices) of the
+        pressure-space KKT multiply; default ``K_p`` (the Stokes forward operator)."""
         self.velocity = MultiBlockSystem(M_v, K_v, n_t=n_t, beta=beta, CN=CN, time_interval=time_interval,
                                          bc_dofs=bc_dofs_v, epsilon=epsilon, device=device)
-        self.pressure = MultiBlockSystem(M_p, K_p, n_t=n_t, beta=beta, CN=CN, time_interval=time_interval,
-                                         bc_dofs=(), epsilon=epsilon, device=self.velocity.device.index,
-                                         stream=self.velocity.stream)
+        self.pressure = MultiBlockSystem(M_p, K_p if D_p is None else D_p, n_t=n_t, beta=beta, CN=CN,
+                                         time_interval=time_interval, bc_dofs=(), epsilon=epsilon,
+                                         device=self.velocity.device.index, stream=self.velocity.stream)
+        self._K_p_solver = None if D_p is None else np.ascontiguousarray(self.pressure._same_pattern(K_p))
         self._lib = self.velocity._lib
         self.device = self.velocity.device
         self.N = self.velocity.N
@@ -41,6 +46,19 @@ class StokesSystem:
         self._s = C.c_void_p()
         self.velocity._check(self._lib.ctl_stokes_create(self.velocity._h, self.pressure._h, indptr.ctypes.data,
                                                          indices.ctypes.data, data.ctypes.data, C.byref(self._s)))
+        if self._K_p_solver is not None:
+            self.velocity._check(self._lib.ctl_stokes_set_laplacian_p(self._s, self._K_p_solver.ctypes.data))
+        self._pc_ready = False
+
+    def set_forward(self, K_v, D_p=None):
+        """New forward matrices of a Picard iteration (control/control.py:5109-5118: every outer iteration
+        re-linearises around the new velocity): velocity-space ``D_v_i`` and, when given, pressure-space
+        ``D_p_i``.  The Laplacian of ``solver_K_p`` stays."""
+        self.velocity.set_K(K_v)
+        if D_p is not None:
+            if self._K_p_solver is None:
+                raise ValueError("construct the StokesSystem with D_p= to change the pressure-space forward matrices")
+            self.pressure.set_K(D_p)
         self._pc_ready = False
 
     # ------------------------------------------------------------------ plumbing

@@ -245,6 +245,13 @@ int64_t ctl_stokes_vec_len(ctl_stokes s);      /* 2 N (n_v + n_p) */
 /* y = A x: MultiBlockSystemMatrix.mult with sub_n_blocks = 2 (preconditioner.py:375-543) */
 int ctl_stokes_apply(ctl_stokes s, const double *x, double *y);
 int ctl_stokes_pc_default_options(ctl_stokes_pc_options *opts);
+/* Values (HOST, on the pressure handle's pattern) of the Laplacian `K_p = inner(grad(p_trial), grad(p_test)) dx`
+ * that solver_K_p inverts (control/control.py:3746, 4300-4309).  Without this call the forward matrix of the
+ * pressure handle is used, which is the same matrix for the Stokes forward operator.  Needed when the forward
+ * form restricted to the pressure space (block_10_int_p = tau D_p_i + M_p, control/control.py:3787-3789) is NOT
+ * the Laplacian: Navier-Stokes Picard iterations (per-level convection-diffusion D_p_i), forward forms with a
+ * reaction term.  NULL restores the default.  Call before ctl_stokes_pc_setup. */
+int ctl_stokes_set_laplacian_p(ctl_stokes s, const double *values_host);
 int ctl_stokes_pc_setup(ctl_stokes s, const ctl_stokes_pc_options *opts);
 /* Preconditioner.apply around pc_fn (with the nullspace wrapping) / the raw pc_fn */
 int ctl_stokes_pc_apply(ctl_stokes s, const double *b, double *u);

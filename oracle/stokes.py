@@ -138,8 +138,12 @@ def make_solver_p(M_p, K_p, lambda_p_bounds, amg_params=None):
 
 
 def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, lambda_v_bounds=None,
-                        lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None, epsilon=1e-3):
-    """``pc_fn(b_0, b_1) -> (u_0, u_1)`` of control/control.py:4337-4513 (CN) / 4515-4687 (BE)."""
+                        lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None, epsilon=1e-3,
+                        D_p=None):
+    """``pc_fn(b_0, b_1) -> (u_0, u_1)`` of control/control.py:4337-4513 (CN) / 4515-4687 (BE).
+    ``K_p``: the Laplacian ``solver_K_p`` inverts (3746, 4300-4309); ``D_p``: the forward form on the pressure
+    space per time level (``D_p_i``, 3787-3789, 3926-3928; one matrix or n_t matrices) of the pressure-space
+    KKT multiply -- default ``K_p``, which is what the Stokes forward operator gives."""
     N = kkt.n_blocks(n_t, CN)
     ns_v = kkt.DirichletBCNullspace(bdofs_v)
     vparams = dict(cycles=6)                      # ctl_stokes_pc_default_options: six cycles on the P2 operator
@@ -147,7 +151,7 @@ def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, l
     heat_pc = construct_pc(M_v, K_v, tau, beta, n_t, CN, bdofs_v, lambda_v_bounds=lambda_v_bounds,
                            inner=inner, amg_params=vparams, epsilon=epsilon)
     K_solve, M_solve, _ = make_solver_p(M_p, K_p, lambda_p_bounds, amg_params_p)
-    pblocks = kkt.build_blocks(M_p, K_p, tau, beta, n_t, CN)       # block_*_int_p, 3805-3957
+    pblocks = kkt.build_blocks(M_p, K_p if D_p is None else D_p, tau, beta, n_t, CN)       # block_*_int_p, 3805-3957
     inner_parameters = {"preconditioner": True, "linear_solver": "gmres", "maximum_iterations": 5,
                         "relative_tolerance": 0.0, "absolute_tolerance": 0.0}      # 4355-4361
 
@@ -205,7 +209,7 @@ class _PairNullspace:
 
 def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, b_0, b_1,
                  solver_parameters=None, lambda_v_bounds=None, lambda_p_bounds=None, inner="amg",
-                 amg_params=None, amg_params_p=None, pc_fn=None):
+                 amg_params=None, amg_params_p=None, pc_fn=None, D_p=None):
     """``MultiBlockSystem.solve`` of the outer Stokes system from a zero initial guess
     (control/control.py:4273-4297, 4688-4693).  ``b_0`` (2N, n_v), ``b_1`` (2N, n_p) are the
     final right-hand sides (T transforms already applied).  Returns (u_0, u_1, KSPResult)."""
@@ -217,7 +221,7 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
     if pc_fn is None:
         pc_fn = construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v,
                                     lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds,
-                                    inner=inner, amg_params=amg_params, amg_params_p=amg_params_p)
+                                    inner=inner, amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p)
     if solver_parameters is None:                                # control/control.py:4291-4297
         solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 100,
                              "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0}
@@ -262,7 +266,7 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
 def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, v_d, f,
                                 v_0=None, div_v=None, div_zeta=None, solver_parameters=None, lambda_v_bounds=None,
                                 lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None,
-                                check_v_d=True, check_f=True, bc_values=None):
+                                check_v_d=True, check_f=True, bc_values=None, D_p=None):
     """``Control.Instationary.incompressible_linear_solve`` for homogeneous Dirichlet velocity data
     (control/control.py:3592-4725): right-hand sides (3961-4243; the velocity rows are those of
     the heat problem, the pressure rows are zero unless div_v / div_zeta are given), outer solve,
@@ -293,7 +297,7 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
                                  bdofs_v=bdofs_v, b_0=np.concatenate([b_0_0, b_0_1]),
                                  b_1=np.concatenate([b_1_0, b_1_1]), solver_parameters=solver_parameters,
                                  lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, inner=inner,
-                                 amg_params=amg_params, amg_params_p=amg_params_p)
+                                 amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p)
     if CN:
         v = np.zeros((n_t, n_v))
         zeta = np.zeros((n_t, n_v))
@@ -307,3 +311,69 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
     if bc_values is not None:
         v[:, bdofs_v] = bc_values
     return v, zeta, u_1[N:].copy(), u_1[:N].copy(), res
+
+
+def incompressible_non_linear_solve(M_v, D_v, B, M_p, K_p, D_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v,
+                                    v_d, f, v_0=None, bc_values=None, solver_parameters=None, lambda_v_bounds=None,
+                                    lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None,
+                                    max_non_linear_iter=10, relative_non_linear_tol=1e-5,
+                                    absolute_non_linear_tol=1e-8):
+    """``Control.Instationary.incompressible_non_linear_solve`` (control/control.py:4886-5219): Picard loop of
+    Navier-Stokes control.  ``D_v(v_i, t)`` / ``D_p(v_i, t)``: the matrix of ``construct_D_v`` on the velocity /
+    pressure space at the velocity state ``v_i`` (1887-1896 with ``v_trial, v_test`` / ``p_trial, p_test``,
+    3780-3789).  ``v_d``, ``f``: (n_t, n_v) assembled desired state / force.  Returns a dict with the final
+    iterates, the residual-norm history and the inner iteration counts."""
+    from .control import non_linear_res_eval
+    t_0, T_f = time_interval
+    tau = (T_f - t_0) / (n_t - 1.0)
+    times = t_0 + tau * np.arange(n_t)
+    N = kkt.n_blocks(n_t, CN)
+    n_v, n_p = M_v.shape[0], M_p.shape[0]
+    v_0 = np.zeros(n_v) if v_0 is None else v_0
+    v_old = np.zeros((n_t, n_v))
+    zeta_old = np.zeros((n_t, n_v))
+    p_old = np.zeros((N, n_p))
+    mu_old = np.zeros((N, n_p))
+    if CN:
+        v_old[0] = v_0                                           # 4968-4969
+
+    def res_eval():                                              # 4979-5072
+        r00, r01 = non_linear_res_eval(M_v, D_v, times, tau, beta, n_t, CN, bdofs_v, v_old, zeta_old, v_0, v_d, f)
+        r00 -= tau * (B.T @ mu_old.T).T
+        r01 -= tau * (B.T @ p_old.T).T
+        r00[:, bdofs_v] = 0.0
+        r01[:, bdofs_v] = 0.0
+        r10 = -(B @ (v_old[1:] if CN else v_old).T).T            # CN: v_old.sub(i + 1), zeta_old.sub(i)
+        r11 = -(B @ (zeta_old[:-1] if CN else zeta_old).T).T
+        return r00, r01, r10, r11
+
+    def norm(parts):
+        return float(np.sqrt(sum((a ** 2).sum() for a in parts)))
+
+    r = res_eval()
+    norm_0 = norm(r)
+    norm_k, k = norm_0, 0
+    history, inner_its = [norm_0], []
+    while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+        K_levels = [D_v(v_old[i], times[i]) for i in range(n_t)]
+        P_levels = [D_p(v_old[i], times[i]) for i in range(n_t)]
+        dv, dzeta, dp, dmu, res = incompressible_linear_solve(
+            M_v, K_levels, B, M_p, K_p, beta=beta, n_t=n_t, CN=CN, time_interval=time_interval, bdofs_v=bdofs_v,
+            v_d=r[0], f=r[1], div_v=tau * r[2], div_zeta=tau * r[3], check_v_d=False, check_f=False,
+            solver_parameters=solver_parameters, lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds,
+            inner=inner, amg_params=amg_params, amg_params_p=amg_params_p, D_p=P_levels)
+        inner_its.append(res.its)
+        v_old = v_old + dv                                       # 5127-5160
+        if bc_values is not None:
+            v_old[:, bdofs_v] = bc_values
+        p_old = p_old + dp
+        zeta_old = zeta_old + dzeta
+        zeta_old[:, bdofs_v] = 0.0
+        mu_old = mu_old + dmu
+        r = res_eval()
+        norm_k = norm(r)
+        k += 1
+        history.append(norm_k)
+        if k + 1 > max_non_linear_iter:
+            break
+    return dict(v=v_old, zeta=zeta_old, p=p_old, mu=mu_old, history=history, iterations=k, inner_its=inner_its)

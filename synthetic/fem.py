@@ -405,3 +405,74 @@ def assemble_convection_p1_2d(nx, ny, lx, ly, wind):
     cols = np.tile(tris, (1, 3)).ravel()
     (C,) = _csr_same_pattern(n, rows, cols, [Ce.ravel()])
     return C
+
+
+def convection_q2_2d(nx, ny, lx=1.0, ly=1.0):
+    """Assembler of the Q2 convection matrix ``inner(dot(grad(trial), w), test) * dx`` for a NODAL (Q2) wind
+    ``w`` on the mesh and numbering of ``assemble_q2_2d`` -- the Picard linearisation of the Navier-Stokes
+    forward operator in the reference's tests (test/test_control.py:4297-4302).  Returns ``C(wx, wy)`` -> scalar
+    CSR on the pattern of the Q2 mass matrix (explicit zeros kept); the vector-valued operator is
+    ``kron(C, I_2)`` on the pattern of ``assemble_q2q1_stokes_2d``'s ``M_v``.  4 x 4 Gauss points per cell
+    (exact: the integrand has degree 6 per direction)."""
+    hx, hy = lx / nx, ly / ny
+    gp, gw = np.polynomial.legendre.leggauss(4)
+    s = 0.5 * (gp + 1.0)                                   # points on (0, 1)
+    w1 = 0.5 * gw
+    # 1-D quadratic shape functions at nodes 0, 1/2, 1 and their derivatives, evaluated at s
+    N1 = np.stack([(1.0 - s) * (1.0 - 2.0 * s), 4.0 * s * (1.0 - s), s * (2.0 * s - 1.0)])        # (3, q)
+    D1 = np.stack([4.0 * s - 3.0, 4.0 - 8.0 * s, 4.0 * s - 1.0])
+    # 2-D shape functions, local node a = 3 * ay + ax, at quadrature point (qy, qx)
+    phi = np.einsum("bq,ap->bapq", N1, N1).reshape(9, 4, 4)            # N_ay(s_qy) N_ax(s_qx)
+    dphix = np.einsum("bq,ap->bapq", N1, D1).reshape(9, 4, 4) / hx
+    dphiy = np.einsum("bq,ap->bapq", D1, N1).reshape(9, 4, 4) / hy
+    wq = np.einsum("q,p->qp", w1, w1) * hx * hy
+    mx = 2 * nx + 1
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    base = (2 * ey.ravel()) * mx + 2 * ex.ravel()                      # lower-left node of every cell
+    loc = (np.arange(3)[:, None] * mx + np.arange(3)[None, :]).ravel()  # a = 3 ay + ax
+    cells = base[:, None] + loc[None, :]                               # (ncell, 9) global nodes
+    n = mx * (2 * ny + 1)
+    rows = np.repeat(cells, 9, axis=1).ravel()
+    cols = np.tile(cells, (1, 9)).ravel()
+    T_x = np.einsum("iqp,jqp,kqp,qp->kij", phi, dphix, phi, wq)        # sum_q phi_i dphix_j phi_k w
+    T_y = np.einsum("iqp,jqp,kqp,qp->kij", phi, dphiy, phi, wq)
+
+    def C(wx, wy):
+        Ce = np.einsum("ck,kij->cij", wx[cells], T_x) + np.einsum("ck,kij->cij", wy[cells], T_y)
+        return _csr_same_pattern(n, rows, cols, [Ce.ravel()])[0]
+    return C
+
+
+def convection_q1_q2wind_2d(nx, ny, lx=1.0, ly=1.0):
+    """The same convection form on the Q1 (pressure) space with the Q2 nodal wind of the velocity space:
+    ``construct_D_v(p_trial, p_test, v_n_help, t)`` of the reference's pressure-space blocks
+    (control/control.py:3787-3789) for a Navier-Stokes forward operator.  Returns ``C(wx, wy)`` -> CSR on the
+    pattern of ``assemble_q2q1_stokes_2d``'s ``M_p``; ``wx, wy`` are the wind components at the Q2 nodes.
+    3 x 3 Gauss points per cell (exact: degree 4 per direction)."""
+    hx, hy = lx / nx, ly / ny
+    gp, gw = np.polynomial.legendre.leggauss(3)
+    s = 0.5 * (gp + 1.0)
+    w1 = 0.5 * gw
+    N2 = np.stack([(1.0 - s) * (1.0 - 2.0 * s), 4.0 * s * (1.0 - s), s * (2.0 * s - 1.0)])        # wind, quadratic
+    N1 = np.stack([1.0 - s, s])                                                                   # pressure, linear
+    D1 = np.stack([-np.ones_like(s), np.ones_like(s)])
+    wind = np.einsum("bq,ap->bapq", N2, N2).reshape(9, 3, 3)
+    psi = np.einsum("bq,ap->bapq", N1, N1).reshape(4, 3, 3)
+    dpsix = np.einsum("bq,ap->bapq", N1, D1).reshape(4, 3, 3) / hx
+    dpsiy = np.einsum("bq,ap->bapq", D1, N1).reshape(4, 3, 3) / hy
+    wq = np.einsum("q,p->qp", w1, w1) * hx * hy
+    mx2, mx1 = 2 * nx + 1, nx + 1
+    ex, ey = np.meshgrid(np.arange(nx), np.arange(ny), indexing="xy")
+    ex, ey = ex.ravel(), ey.ravel()
+    cells2 = ((2 * ey) * mx2 + 2 * ex)[:, None] + (np.arange(3)[:, None] * mx2 + np.arange(3)[None, :]).ravel()[None, :]
+    cells1 = (ey * mx1 + ex)[:, None] + (np.arange(2)[:, None] * mx1 + np.arange(2)[None, :]).ravel()[None, :]
+    n = mx1 * (ny + 1)
+    rows = np.repeat(cells1, 4, axis=1).ravel()
+    cols = np.tile(cells1, (1, 4)).ravel()
+    T_x = np.einsum("iqp,jqp,kqp,qp->kij", psi, dpsix, wind, wq)
+    T_y = np.einsum("iqp,jqp,kqp,qp->kij", psi, dpsiy, wind, wq)
+
+    def C(wx, wy):
+        Ce = np.einsum("ck,kij->cij", wx[cells2], T_x) + np.einsum("ck,kij->cij", wy[cells2], T_y)
+        return _csr_same_pattern(n, rows, cols, [Ce.ravel()])[0]
+    return C

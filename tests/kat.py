@@ -248,3 +248,49 @@ def mms_convection_diffusion_problem(N, n_t=100, CN=True):
     q = dict(q)
     q.update(K_levels=K_levels, v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T)
     return q
+
+
+def reference_navier_stokes_problem(CN, nx=8, n_t=10):
+    """The problem of the reference's instationary Navier-Stokes control tests (test/test_control.py:4171-4268
+    BE, 4271-4368 CN; they run ``incompressible_non_linear_solve`` and assert nothing): (0, 2)^2, n_t = 10 on
+    (0, 2), beta = 1e-3, nu = 1/100, forward form ``nu grad.grad + dot(grad(trial), u) . test`` (Picard), lid
+    velocity (min(t, 1), 0) on the top edge and no-slip elsewhere, the two counter-rotating vortices as desired
+    state, zero force and initial condition.  Vector Q2 - Q1 on quadrilaterals here (the reference: P2 - P1
+    on triangles).  ``D_v(v_i, t)`` / ``D_p(v_i, t)`` are the matrices of ``construct_D_v`` on the velocity /
+    pressure space at the velocity iterate."""
+    sq = fem.assemble_q2q1_stokes_2d(nx, nx, 2.0, 2.0)
+    M = sq["M_v"]
+    n_v = M.shape[0]
+    xs, ys = sq["coords_v"][:, 0], sq["coords_v"][:, 1]
+    x, y = xs - 1.0, ys - 1.0
+    T_f, beta, nu = 2.0, 1.0e-3, 1.0 / 100.0
+    tau = T_f / (n_t - 1.0)
+    times = tau * np.arange(n_t)
+    a, b = (100.0 / 49.0) ** 2, (100.0 / 99.0) ** 2
+    c_1 = 1.0 - np.sqrt(a * (x - 0.5) ** 2 + b * y ** 2)
+    c_2 = 1.0 - np.sqrt(a * (x + 0.5) ** 2 + b * y ** 2)
+    shape = np.zeros(n_v)                                          # 4304-4328
+    shape[0::2] = np.where(c_1 >= 0.0, c_1 * b * y, np.where(c_2 >= 0.0, -c_2 * b * y, 0.0))
+    shape[1::2] = np.where(c_1 >= 0.0, -c_1 * a * (x - 0.5), np.where(c_2 >= 0.0, c_2 * a * (x + 0.5), 0.0))
+    v_hat = np.cos(0.5 * np.pi * times)[:, None] * shape[None, :]
+    bd = sq["bdofs_v"]
+    top = np.abs(ys[bd // 2] - 2.0) < 1e-12                       # boundary id 4 of RectangleMesh: y = ly
+    g = np.zeros((n_t, bd.size))
+    g[:, top & (bd % 2 == 0)] = np.minimum(times, 1.0)[:, None]    # 4282-4289
+    conv_v = fem.convection_q2_2d(nx, nx, 2.0, 2.0)
+    conv_p = fem.convection_q1_q2wind_2d(nx, nx, 2.0, 2.0)
+    I2 = sp.identity(2, format="csr")
+    L_v, L_p = sq["L_v"], sq["L_p"]
+
+    def D_v(v_i, t):
+        C = sp.kron(conv_v(v_i[0::2], v_i[1::2]), I2, format="csr")
+        C.sort_indices()
+        assert np.array_equal(C.indices, M.indices)
+        return sp.csr_matrix((nu * L_v.data + C.data, M.indices, M.indptr), shape=M.shape)
+
+    def D_p(v_i, t):
+        C = conv_p(v_i[0::2], v_i[1::2])
+        return sp.csr_matrix((nu * L_p.data + C.data, L_p.indices, L_p.indptr), shape=L_p.shape)
+    return dict(sq=sq, M=M, B=sq["B"], D_v=D_v, D_p=D_p, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN,
+                time_interval=(0.0, T_f), v_hat=v_hat, v_d=(M @ v_hat.T).T, f=np.zeros((n_t, n_v)), bc_values=g,
+                lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0))

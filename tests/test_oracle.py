@@ -704,3 +704,32 @@ def test_reference_mms_convection_diffusion_convergence_study():
     orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
     assert (orders[0] > 1.6).all() and (orders[1] > 1.85).all()          # measured 1.72 / 1.79 and 1.93 / 1.95
     assert abs(e[2, 0] - 0.0221826) < 1e-6 and abs(e[2, 1] - 0.0513777) < 1e-6
+
+
+@pytest.mark.parametrize("CN", [True, False])
+def test_reference_navier_stokes_picard_loop(CN):
+    """test/test_control.py:4171-4368 (``test_instationary_Navier_Stokes_BE/CN``: they run
+    ``incompressible_non_linear_solve`` and assert nothing) re-created on 4 x 4 Q2-Q1 cells: the Picard loop
+    converges to the reference's tolerance within its 10 iterations, the converged state is discretely
+    divergence free and carries the lid velocity."""
+    from oracle import stokes
+    q = kat.reference_navier_stokes_problem(CN, nx=4)
+    sq = q["sq"]
+    sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 100, "relative_tolerance": 1e-8,
+           "absolute_tolerance": 0.0}                                       # the test's parameters (4340-4345)
+    out = stokes.incompressible_non_linear_solve(
+        q["M"], q["D_v"], q["B"], sq["M_p"], sq["L_p"], q["D_p"], beta=q["beta"], n_t=q["n_t"], CN=CN,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], bc_values=q["bc_values"],
+        solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+        relative_non_linear_tol=1e-5, max_non_linear_iter=10)
+    h = out["history"]
+    assert out["iterations"] < 10 and h[-1] <= 1e-5 * h[0]
+    v = out["v"]
+    div = (q["B"] @ (v[1:] if CN else v).T).T
+    assert np.abs(div).max() < 1e-6 * np.abs(q["B"]).sum(axis=1).max() * np.abs(v).max()
+    assert np.array_equal(v[:, q["bdofs"]], q["bc_values"]) and np.abs(v).max() > 0.5      # the lid drives the flow
+    # the convection matters: it is not small against the viscous term at the converged state
+    t_mid = 0.5 * q["time_interval"][1]
+    conv = (q["D_v"](v[-1], t_mid) - q["D_v"](0.0 * v[-1], t_mid)) @ v[-1]
+    visc = q["D_v"](0.0 * v[-1], t_mid) @ v[-1]
+    assert np.linalg.norm(conv) > 0.1 * np.linalg.norm(visc)

@@ -110,3 +110,36 @@ def test_stationary_inhomogeneous_and_non_linear_on_gpu():
         assert np.allclose(c.non_linear_history, out["history"], rtol=1e-4)
         assert np.abs(c._v - out["v"]).max() < 1e-5 * np.abs(out["v"]).max()
         c.close()
+
+
+def test_navier_stokes_picard_loop_on_gpu():
+    """``Control.Instationary.incompressible_non_linear_solve`` (control/control.py:4886-5219) on the problem of
+    the reference's Navier-Stokes tests (test/test_control.py:4271-4368), 4 x 4 Q2-Q1 cells, CN: per-level
+    non-symmetric ``D_v_i`` on the velocity handle AND ``D_p_i`` on the pressure handle, the Laplacian of
+    ``solver_K_p`` set separately (``ctl_stokes_set_laplacian_p``).  Residual history and iterates against the
+    oracle's restatement of the loop."""
+    from control_b200 import Control
+    from oracle import stokes
+    q = kat.reference_navier_stokes_problem(True, nx=4, n_t=6)
+    sq = q["sq"]
+
+    def level(t):
+        return int(round(t / q["tau"]))
+    c = Control.Instationary(q["M"], lambda v_i, t, gauss_newton: q["D_v"](v_i, t),
+                             desired_state=lambda t: (q["v_d"][level(t)], q["v_hat"][level(t)]), beta=q["beta"],
+                             n_t=q["n_t"], CN=True, time_interval=q["time_interval"], bc_dofs=q["bdofs"],
+                             bc_values=lambda t: q["bc_values"][level(t)])
+    space_p = dict(B=q["B"], M_p=sq["M_p"], K_p=sq["L_p"], forward_matrix_p=lambda v_i, t, gauss_newton: q["D_p"](v_i, t))
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-8, "absolute_tolerance": 0.0}
+    k = c.incompressible_non_linear_solve("constant", space_p=space_p, solver_parameters=sp_,
+                                          lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"],
+                                          print_error_non_linear=False)
+    out = stokes.incompressible_non_linear_solve(
+        q["M"], q["D_v"], q["B"], sq["M_p"], sq["L_p"], q["D_p"], beta=q["beta"], n_t=q["n_t"], CN=True,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], bc_values=q["bc_values"],
+        solver_parameters=sp_, lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    assert k == out["iterations"]
+    assert np.allclose(c.non_linear_history, out["history"], rtol=1e-3)
+    assert np.abs(c._v - out["v"]).max() < 1e-5 * np.abs(out["v"]).max()
+    assert max(abs(a - b) for a, b in zip(c.inner_iterations, out["inner_its"])) <= 2
+    c.close()
