@@ -92,6 +92,9 @@ class Stationary:
         if self._system is not None:
             self._system.close()
             self._system = None
+        if getattr(self, "_stokes", None) is not None:
+            self._stokes.close()
+            self._stokes = None
 
     def print_error(self):                              # control/control.py:303-312
         if self._true_v is None:
@@ -150,6 +153,165 @@ class Stationary:
         if print_error:
             self.print_error()
         return self.last_ksp
+
+    # ------------------------------------------------------------------ Stokes / Navier-Stokes control
+    def set_space_p(self, space_p):
+        """``space_p``: dict with the divergence matrix ``B`` (n_p x n_v), the pressure mass matrix ``M_p``, the
+        pressure Laplacian ``K_p`` and ``forward_matrix_p``: the forward form on the pressure space -- a CSR
+        matrix on M_p's pattern or a callable ``(v, gauss_newton) -> CSR`` (``block_10_p``,
+        control/control.py:971); default ``K_p`` (the Stokes forward operator)."""
+        self._space_p = space_p
+
+    def _D_p(self, space_p, v_old):
+        fp = space_p.get("forward_matrix_p")
+        if fp is None:
+            return space_p["K_p"]
+        return fp(v_old, self._Gauss_Newton) if callable(fp) else fp
+
+    def incompressible_linear_solve(self, nullspace_p=None, *, space_p=None, P=None, solver_parameters=None,
+                                    Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None, v_d=None, f=None,
+                                    div_v=None, div_zeta=None, print_error=True, create_output=False, plots=False,
+                                    amg=None, amg_p=None):
+        """control/control.py:802-1201.  The outer system [[KKT_v, B^T], [B, 0]] runs on the instationary Stokes
+        handle with one time block (n_t = 2, tau = 2, forward matrices shifted by the mass matrices, see the module
+        header): that system couples with ``tau B`` = 2 B, so the divergence rows are handed over scaled by 2 and
+        the pressures come back scaled by 1/2 -- a diagonal scaling of the unknowns under which the in-built
+        preconditioner (986-1084 = control/control.py:4337-4513 with one block) is consistent."""
+        from .stokes import StokesSystem
+        if space_p is None:
+            space_p = getattr(self, "_space_p", None)
+            if space_p is None:
+                raise ValueError("Undefined space_p")                   # 815-819
+        else:
+            self.set_space_p(space_p)
+        if nullspace_p not in (None, "constant"):
+            raise ValueError("only the constant pressure nullspace is supported")
+        if P is not None:
+            raise NotImplementedError("user preconditioners are not wired for the Stokes system")
+        if Multigrid:
+            raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
+        n, M, B = self._n, self._M, space_p["B"]
+        M_p = space_p["M_p"].tocsr()
+        n_p = M_p.shape[0]
+        D_v = self.construct_D_v(self._v)
+        D_p = self._D_p(space_p, self._v).tocsr()
+        v_inhom = None
+        if self._bc_values is not None:
+            v_inhom = np.zeros(n)
+            v_inhom[self._bc_dofs] = self._bc_values
+        if f is None:                                   # construct_f, 326-336
+            b_01 = self._assembled_force()
+            if v_inhom is not None:
+                b_01 = b_01 - D_v @ v_inhom
+                self._bc(b_01)
+        else:
+            b_01 = np.array(f, dtype=float)
+        if v_d is None:                                 # construct_v_d, 338-349
+            b_00 = self._assembled_desired_state()
+            if v_inhom is not None:
+                b_00 = b_00 - M @ v_inhom
+                self._bc(b_00)
+        else:
+            b_00 = np.array(v_d, dtype=float)
+        if div_v is None:                               # 866-873
+            b_10 = np.zeros(n_p) if v_inhom is None else -(B @ v_inhom)
+        else:
+            b_10 = np.array(div_v, dtype=float)
+        b_11 = np.zeros(n_p) if div_zeta is None else np.array(div_zeta, dtype=float)
+        if solver_parameters is None:                   # 1088-1094
+            solver_parameters = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 50,
+                                 "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0,
+                                 "monitor_convergence": print_error}
+        K_shift = self._shifted(D_v)
+        D_p_shift = sp.csr_matrix((D_p.data - M_p.data, M_p.indices, M_p.indptr), shape=M_p.shape)
+        if getattr(self, "_stokes", None) is None:
+            self._stokes = StokesSystem(M, K_shift, B, M_p, space_p["K_p"], n_t=2, beta=self._beta, CN=True,
+                                        time_interval=(0.0, 2.0), bc_dofs_v=self._bc_dofs, device=self._device,
+                                        D_p=D_p_shift)
+        else:
+            self._stokes.set_forward(K_shift, D_p_shift)
+        system = self._stokes
+        system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
+                                    amg_p=amg_p)
+        u_0 = np.zeros((2, n))
+        u_1 = np.zeros((2, n_p))
+        self.last_ksp = system.solve(u_0, u_1, np.stack([b_00, b_01]), 2.0 * np.stack([b_10, b_11]),
+                                     solver_parameters=solver_parameters, pc_fn="builtin")
+        v, zeta = u_0[0].copy(), u_0[1].copy()
+        if v_inhom is not None:                         # 1107-1110
+            v = v + v_inhom
+        v[self._bc_dofs] = 0.0 if self._bc_values is None else self._bc_values
+        self._bc(zeta)
+        self._v, self._zeta = v, zeta
+        self._p, self._mu = 2.0 * u_1[1], 2.0 * u_1[0]  # 1111-1112: p = u_1.sub(1), mu = u_1.sub(0)
+        if print_error:
+            self.print_error()
+        return self.last_ksp
+
+    def incompressible_non_linear_solve(self, nullspace_p=None, *, space_p=None, P=None, solver_parameters=None,
+                                        Multigrid=False, lambda_v_bounds=None, lambda_p_bounds=None,
+                                        max_non_linear_iter=10, relative_non_linear_tol=10.0**-5,
+                                        absolute_non_linear_tol=10.0**-8, print_error_linear=False,
+                                        print_error_non_linear=True, create_output=False, plots=False, amg=None,
+                                        amg_p=None):
+        """control/control.py:1203-1486: Picard loop of stationary Navier-Stokes control."""
+        if space_p is None:
+            space_p = getattr(self, "_space_p", None)
+            if space_p is None:
+                raise ValueError("Undefined space_p")
+        else:
+            self.set_space_p(space_p)
+        B = space_p["B"]
+        n_p = space_p["M_p"].shape[0]
+        v_old, zeta_old = self._v.copy(), self._zeta.copy()
+        p_old = np.array(getattr(self, "_p", np.zeros(n_p)), dtype=float)
+        mu_old = np.array(getattr(self, "_mu", np.zeros(n_p)), dtype=float)
+        f = self._assembled_force()
+        v_d = self._assembled_desired_state()
+
+        def res_eval():                                 # 1272-1319
+            r00, r01 = self.non_linear_res_eval(v_d, f, v_old, zeta_old, self.construct_D_v(v_old))
+            r00 = r00 - B.T @ mu_old
+            r01 = r01 - B.T @ p_old
+            self._bc(r00)
+            self._bc(r01)
+            return r00, r01, -(B @ v_old), -(B @ zeta_old)
+
+        def norm(parts):
+            return float(np.sqrt(sum(a @ a for a in parts)))
+
+        r = res_eval()
+        norm_0 = norm(r)
+        norm_k, k = norm_0, 0
+        self.non_linear_history = [norm_0]
+        self.inner_iterations = []
+        if print_error_non_linear:
+            print(f"Initial non-linear residual: {norm_0:.16e}")
+        while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+            ksp = self.incompressible_linear_solve(nullspace_p, space_p=space_p, P=P, solver_parameters=solver_parameters,
+                                                   Multigrid=Multigrid, lambda_v_bounds=lambda_v_bounds,
+                                                   lambda_p_bounds=lambda_p_bounds, v_d=r[0], f=r[1], div_v=r[2],
+                                                   div_zeta=r[3], print_error=print_error_linear, amg=amg, amg_p=amg_p)
+            self.inner_iterations.append(ksp.its)
+            v_old = v_old + self._v
+            if self._bc_values is not None:
+                v_old[self._bc_dofs] = self._bc_values
+            zeta_old = zeta_old + self._zeta
+            self._bc(zeta_old)
+            p_old = p_old + self._p
+            mu_old = mu_old + self._mu
+            self._v, self._zeta, self._p, self._mu = v_old.copy(), zeta_old.copy(), p_old.copy(), mu_old.copy()
+            r = res_eval()
+            norm_k = norm(r)
+            k += 1
+            self.non_linear_history.append(norm_k)
+            if print_error_non_linear:
+                print(f"Non-linear solver: iteration {k:d}, non-linear residual norm {norm_k:.16e}")
+            if k + 1 > max_non_linear_iter:
+                break
+        if print_error_non_linear:
+            self.print_error()
+        return k
 
     # ------------------------------------------------------------------ non_linear_solve
     def non_linear_res_eval(self, v_d, f, v_old, zeta_old, D_v):

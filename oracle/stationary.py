@@ -147,3 +147,168 @@ def non_linear_solve(M, D_v_of, *, beta, bdofs, v_d, f, v_init=None, zeta_init=N
         if k + 1 > max_non_linear_iter:
             break
     return dict(v=v_old, zeta=zeta_old, history=history, iterations=k, inner_its=inner_its)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Stationary Stokes control: ``Control.Stationary.incompressible_linear_solve`` (control/control.py:802-1201)
+# --------------------------------------------------------------------------------------------------------------
+def stokes_apply(M_v, D_v, B, beta, ns_v, ns_p, x0, x1):
+    """``mult`` of the outer system of 885-925: block_00 = [[M_v, D_v^T], [D_v, -M_v/beta]], block_01 =
+    diag(B^T), block_10 = diag(B), no time scaling -- the literal operator of oracle/stokes.py with N = 1,
+    tau = 1 (the form pinned by the reference's stationary Stokes known-answer test)."""
+    from .stokes import stokes_apply_literal
+    heat_blocks = ({(0, 0): M_v}, {(0, 0): D_v.T.tocsr()}, {(0, 0): D_v}, {(0, 0): (-(1.0 / beta) * M_v).tocsr()})
+    return stokes_apply_literal(heat_blocks, B, 1.0, 1, False, ns_v, ns_p, x0, x1)
+
+
+def construct_stokes_pc(M_v, D_v, B, M_p, K_p, D_p, beta, bdofs_v, *, lambda_v_bounds=None, lambda_p_bounds=None,
+                        inner="amg", amg_params=None, amg_params_p=None):
+    """``pc_fn`` of 986-1110: five GMRES iterations on the velocity KKT block with ``Stationary.construct_pc``,
+    ``solver_K_p`` on ``B u_0 - b_1``, the pressure-space KKT multiply [[M_p, D_p^T], [D_p, -M_p/beta]]
+    (block_*_p, 968-984; ``D_p`` = the forward form on the pressure space), ``solver_M_p``."""
+    from .stokes import make_solver_p
+    ns_v = kkt.DirichletBCNullspace(bdofs_v)
+    vparams = dict(cycles=6)                   # as oracle/stokes.py: six cycles on the vector operator
+    vparams.update(amg_params or {})
+    inner_pc = construct_pc(M_v, D_v, beta, bdofs_v, lambda_v_bounds=lambda_v_bounds, inner=inner, amg_params=vparams)
+    K_solve, M_solve, _ = make_solver_p(M_p, K_p, lambda_p_bounds, amg_params_p)
+    inner_parameters = {"preconditioner": True, "linear_solver": "gmres", "maximum_iterations": 5,
+                        "relative_tolerance": 0.0, "absolute_tolerance": 0.0}          # 1000-1005
+    n_v = M_v.shape[0]
+
+    def pc_fn(b_0, b_1):
+        v, zeta, _ = system_solve(lambda x0, x1: apply_A(M_v, D_v, beta, ns_v, x0, x1), ns_v, np.zeros((1, n_v)),
+                                  np.zeros((1, n_v)), b_0[:1], b_0[1:], solver_parameters=inner_parameters,
+                                  pc_fn=inner_pc)
+        u_0 = np.concatenate([v, zeta])
+        h = (B @ u_0.T).T - b_1                                 # 1023-1034
+        w = K_solve(h)                                          # 1042-1052
+        c0 = M_p @ w[0] + D_p.T @ w[1]                          # 1064-1069
+        c1 = D_p @ w[0] - (1.0 / beta) * (M_p @ w[1])
+        return u_0, M_solve(np.stack([c0, c1]))                 # 1074-1084
+    return pc_fn
+
+
+def incompressible_linear_solve(M_v, D_v, B, M_p, K_p, *, beta, bdofs_v, v_d, f, div_v=None, div_zeta=None, D_p=None,
+                                check_v_d=True, check_f=True, bc_values=None, solver_parameters=None,
+                                lambda_v_bounds=None, lambda_p_bounds=None, inner="amg", amg_params=None,
+                                amg_params_p=None):
+    """``Stationary.incompressible_linear_solve``.  Returns (v, zeta, p, mu, KSPResult)."""
+    from . import krylov
+    from .stokes import ConstantNullspace
+    n_v, n_p = M_v.shape[0], M_p.shape[0]
+    bdofs_v = np.asarray(bdofs_v, dtype=np.int64)
+    ns_v, ns_p = kkt.DirichletBCNullspace(bdofs_v), ConstantNullspace()
+    D_p = K_p if D_p is None else D_p
+    v_inhom = None
+    if bc_values is not None:
+        v_inhom = np.zeros(n_v)
+        v_inhom[bdofs_v] = bc_values
+    b00, b01 = np.array(v_d, dtype=float), np.array(f, dtype=float)
+    if v_inhom is not None and check_f:                         # construct_f, 326-336
+        b01 -= D_v @ v_inhom
+        b01[bdofs_v] = 0.0
+    if v_inhom is not None and check_v_d:                       # construct_v_d, 338-349
+        b00 -= M_v @ v_inhom
+        b00[bdofs_v] = 0.0
+    if div_v is None:                                           # 866-873
+        b10 = np.zeros(n_p) if v_inhom is None else -(B @ v_inhom)
+    else:
+        b10 = np.array(div_v, dtype=float)
+    b11 = np.zeros(n_p) if div_zeta is None else np.array(div_zeta, dtype=float)
+    pc_fn = construct_stokes_pc(M_v, D_v, B, M_p, K_p, D_p, beta, bdofs_v, lambda_v_bounds=lambda_v_bounds,
+                                lambda_p_bounds=lambda_p_bounds, inner=inner, amg_params=amg_params,
+                                amg_params_p=amg_params_p)
+    if solver_parameters is None:                               # 1088-1094
+        solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 50, "relative_tolerance": 1.0e-6,
+                             "absolute_tolerance": 0.0}
+    sp_ = solver_parameters
+    L0 = 2 * n_v
+
+    def unpack(x):
+        return x[:L0].reshape(2, n_v).copy(), x[L0:].reshape(2, n_p).copy()
+
+    def pack(a0, a1):
+        return np.concatenate([a0.ravel(), a1.ravel()])
+
+    def A(x):
+        return pack(*stokes_apply(M_v, D_v, B, beta, ns_v, ns_p, *unpack(x)))
+
+    def P(x):                                                   # Preconditioner.apply, preconditioner.py:562-656
+        c0, c1 = unpack(x)
+        w0, w1 = pc_fn(ns_v.pc_pre_mult_corrected(c0), ns_p.pc_pre_mult_corrected(c1))
+        w0, w1 = w0.copy(), w1.copy()
+        ns_v.pc_post_mult_correct(w0, c0)
+        ns_p.pc_post_mult_correct(w1, c1)
+        return pack(w0, w1)
+
+    c0, c1 = np.stack([b00, b01]), np.stack([b10, b11])
+    ns_v.project(c0)
+    ns_p.project(c1)
+    x, res = krylov.gmres(A, pack(c0, c1), np.zeros(L0 + 2 * n_p), pc=P,
+                          flexible=(sp_.get("linear_solver", "fgmres") == "fgmres"), restart=sp_.get("gmres_restart", 30),
+                          rtol=sp_["relative_tolerance"], atol=sp_["absolute_tolerance"],
+                          max_it=sp_.get("maximum_iterations", 1000))
+    u0, u1 = unpack(x)
+    ns_v.project(u0)
+    ns_p.project(u1)
+    if not sp_.get("preconditioner", False) and res.reason <= 0:
+        raise RuntimeError("Solver failed to converge")
+    v, zeta = u0[0], u0[1]
+    if v_inhom is not None:                                     # 1107-1110
+        v = v + v_inhom
+    v[bdofs_v] = 0.0 if bc_values is None else bc_values        # set_v / set_zeta, 264-283
+    zeta[bdofs_v] = 0.0
+    return v, zeta, u1[1].copy(), u1[0].copy(), res
+
+
+def incompressible_non_linear_solve(M_v, D_v_of, B, M_p, K_p, D_p_of, *, beta, bdofs_v, v_d, f, bc_values=None,
+                                    solver_parameters=None, lambda_v_bounds=None, lambda_p_bounds=None, inner="amg",
+                                    amg_params=None, amg_params_p=None, max_non_linear_iter=10,
+                                    relative_non_linear_tol=1e-5, absolute_non_linear_tol=1e-8):
+    """``Stationary.incompressible_non_linear_solve`` (control/control.py:1203-1486): Picard loop of stationary
+    Navier-Stokes control.  ``D_v_of(v)`` / ``D_p_of(v)``: ``construct_D_v`` on the velocity / pressure space at
+    the velocity state ``v``."""
+    n_v, n_p = M_v.shape[0], M_p.shape[0]
+    bdofs_v = np.asarray(bdofs_v, dtype=np.int64)
+    v_old, zeta_old = np.zeros(n_v), np.zeros(n_v)
+    p_old, mu_old = np.zeros(n_p), np.zeros(n_p)
+
+    def res_eval(D_v):                                          # 1272-1319
+        r00, r01 = non_linear_res_eval(M_v, D_v, beta, bdofs_v, v_d, f, v_old, zeta_old)
+        r00 = r00 - B.T @ mu_old
+        r01 = r01 - B.T @ p_old
+        r00[bdofs_v] = 0.0
+        r01[bdofs_v] = 0.0
+        return r00, r01, -(B @ v_old), -(B @ zeta_old)
+
+    def norm(parts):
+        return float(np.sqrt(sum(a @ a for a in parts)))
+
+    D_v = D_v_of(v_old)
+    r = res_eval(D_v)
+    norm_0 = norm(r)
+    norm_k, k = norm_0, 0
+    history, inner_its = [norm_0], []
+    while norm_k > relative_non_linear_tol * norm_0 and norm_k > absolute_non_linear_tol:
+        dv, dzeta, dp, dmu, res = incompressible_linear_solve(
+            M_v, D_v, B, M_p, K_p, beta=beta, bdofs_v=bdofs_v, v_d=r[0], f=r[1], div_v=r[2], div_zeta=r[3],
+            D_p=D_p_of(v_old), check_v_d=False, check_f=False, bc_values=bc_values, solver_parameters=solver_parameters,
+            lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, inner=inner, amg_params=amg_params,
+            amg_params_p=amg_params_p)
+        inner_its.append(res.its)
+        v_old = v_old + dv
+        if bc_values is not None:
+            v_old[bdofs_v] = bc_values
+        zeta_old = zeta_old + dzeta
+        zeta_old[bdofs_v] = 0.0
+        p_old = p_old + dp
+        mu_old = mu_old + dmu
+        D_v = D_v_of(v_old)
+        r = res_eval(D_v)
+        norm_k = norm(r)
+        k += 1
+        history.append(norm_k)
+        if k + 1 > max_non_linear_iter:
+            break
+    return dict(v=v_old, zeta=zeta_old, p=p_old, mu=mu_old, history=history, iterations=k, inner_its=inner_its)

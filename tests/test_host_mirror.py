@@ -189,3 +189,84 @@ def test_navier_stokes_picard_loop_host_logic(fake_device, CN):
     assert _rel(c._v, out["v"]) < 1e-9 and _rel(c._zeta, out["zeta"]) < 1e-9
     assert _rel(c._p, out["p"]) < 1e-8 and _rel(c._mu, out["mu"]) < 1e-8
     assert np.array_equal(c._v[:, q["bdofs"]], q["bc_values"])
+
+
+def _stationary_stokes_kat():
+    """test/test_control.py:232-358: vector Q2 - Q1 on 4 x 4 quads, forward form grad.grad + mass, analytic fields."""
+    sq = fem.assemble_q2q1_stokes_2d(4, 4)
+    M, L, B, Mp, Lp = sq["M_v"], sq["L_v"], sq["B"], sq["M_p"], sq["L_p"]
+    K = (L + M).tocsr()
+    beta = 1e-3
+    x, y = sq["coords_v"][:, 0], sq["coords_v"][:, 1]
+    px, py = sq["coords_p"][:, 0], sq["coords_p"][:, 1]
+
+    def vec(cx, cy):
+        a = np.zeros(M.shape[0])
+        a[0::2], a[1::2] = cx, cy
+        return a
+    v_ref = vec(x * np.exp(y) * np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    zeta_ref = vec(np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    p_ref = np.sin(np.pi * px) * np.sin(2.0 * np.pi * py)
+    mu_ref = px * np.exp(py)
+    rhs = dict(v_d=M @ v_ref + K @ zeta_ref + B.T @ mu_ref, f=K @ v_ref - (1.0 / beta) * (M @ zeta_ref) + B.T @ p_ref,
+               div_v=B @ v_ref, div_zeta=B @ zeta_ref)
+    return dict(sq=sq, M=M, K=K, B=B, Mp=Mp, Lp=Lp, D_p=(Lp + Mp).tocsr(), beta=beta, rhs=rhs, v_ref=v_ref,
+                zeta_ref=zeta_ref, p_ref=p_ref, mu_ref=mu_ref, bd=sq["bdofs_v"])
+
+
+def test_stationary_stokes_known_answer_through_both_drivers(fake_device):
+    """The reference's stationary Stokes known-answer test through (a) the oracle's literal restatement of
+    ``Stationary.incompressible_linear_solve`` and (b) the host mirror, which maps the system onto the
+    instationary Stokes handle (one block, tau = 2, shifted forward matrices, divergence rows scaled by 2):
+    both reproduce the analytic fields (the reference asserts 1e-13; 5e-13 here, the attainable error at
+    rtol 1e-14), and agree with each other."""
+    Control = fake_device
+    k = _stationary_stokes_kat()
+    sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 500, "relative_tolerance": 1e-14,
+           "absolute_tolerance": 1e-14}
+    bounds = dict(lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0))
+    v, zeta, p, mu, res = stationary.incompressible_linear_solve(
+        k["M"], k["K"], k["B"], k["Mp"], k["Lp"], beta=k["beta"], bdofs_v=k["bd"], D_p=k["D_p"], check_v_d=False,
+        check_f=False, solver_parameters=sp_, **bounds, **k["rhs"])
+    c = Control.Stationary(k["M"], k["K"], beta=k["beta"], bc_dofs=k["bd"])
+    space_p = dict(B=k["B"], M_p=k["Mp"], K_p=k["Lp"], forward_matrix_p=k["D_p"])
+    info = c.incompressible_linear_solve("constant", space_p=space_p, solver_parameters=sp_, print_error=False,
+                                         **bounds, **k["rhs"])
+    assert res.reason > 0 and info.reason > 0 and abs(info.its - res.its) <= 3
+    M, Mp = k["M"], k["Mp"]
+
+    def shift(q):                                             # test/test_control.py:334-347
+        return q - np.ones(Mp.shape[0]) @ (Mp @ q)
+    for vv, zz, pp, mm in ((v, zeta, p, mu), (c._v, c._zeta, c._p, c._mu)):
+        assert kat.l2_error(M, vv[None], k["v_ref"][None]) < 5e-13
+        assert kat.l2_error(M, zz[None], k["zeta_ref"][None]) < 5e-13
+        # pressures: the Krylov solve stops at 1e-14 x |b| with |b| ~ 1/beta = 1e3 (measured errors up to 9e-13; the
+        # dense direct solve of the same operator in tests/test_oracle.py reaches the reference's 1e-13)
+        assert kat.l2_error(Mp, shift(pp)[None], shift(k["p_ref"])[None]) < 3e-12
+        assert kat.l2_error(Mp, shift(mm)[None], shift(k["mu_ref"])[None]) < 3e-12
+
+
+def test_stationary_navier_stokes_picard_loop_host_logic(fake_device):
+    """``Stationary.incompressible_non_linear_solve`` (control/control.py:1203-1486), lid-driven cavity with the
+    forward form of the reference's Navier-Stokes tests, host mirror (mapped onto the instationary handle)
+    against the oracle's literal restatement."""
+    Control = fake_device
+    q = kat.reference_navier_stokes_problem(True, nx=4)
+    sq = q["sq"]
+    g = q["bc_values"][-1]
+    v_d, v_hat = q["v_d"][0], q["v_hat"][0]
+    sp_ = dict(SP, relative_tolerance=1e-9)
+    bounds = dict(lambda_v_bounds=q["lambda_v_bounds"], lambda_p_bounds=q["lambda_p_bounds"])
+    out = stationary.incompressible_non_linear_solve(
+        q["M"], lambda v: q["D_v"](v, 0.0), q["B"], sq["M_p"], sq["L_p"], lambda v: q["D_p"](v, 0.0), beta=q["beta"],
+        bdofs_v=q["bdofs"], v_d=v_d, f=np.zeros(q["M"].shape[0]), bc_values=g, solver_parameters=sp_, **bounds)
+    c = Control.Stationary(q["M"], lambda v, gauss_newton: q["D_v"](v, 0.0), desired_state=lambda: (v_d, v_hat),
+                           beta=q["beta"], bc_dofs=q["bdofs"], bc_values=g)
+    space_p = dict(B=q["B"], M_p=sq["M_p"], K_p=sq["L_p"], forward_matrix_p=lambda v, gauss_newton: q["D_p"](v, 0.0))
+    k = c.incompressible_non_linear_solve("constant", space_p=space_p, solver_parameters=sp_,
+                                          print_error_non_linear=False, **bounds)
+    assert k == out["iterations"] and out["history"][-1] <= 1e-5 * out["history"][0]
+    assert np.allclose(c.non_linear_history, out["history"], rtol=1e-4)
+    assert _rel(c._v, out["v"]) < 1e-6 and _rel(c._zeta, out["zeta"]) < 1e-6
+    pm = out["p"] - out["p"].mean()
+    assert np.abs((c._p - c._p.mean()) - pm).max() < 1e-5 * np.abs(pm).max()

@@ -143,3 +143,45 @@ def test_navier_stokes_picard_loop_on_gpu():
     assert np.abs(c._v - out["v"]).max() < 1e-5 * np.abs(out["v"]).max()
     assert max(abs(a - b) for a, b in zip(c.inner_iterations, out["inner_its"])) <= 2
     c.close()
+
+
+def test_reference_stationary_stokes_known_answer_on_gpu():
+    """test/test_control.py:232-358 (``test_stationary_incompressible_linear_control``) through
+    ``Control.Stationary.incompressible_linear_solve`` on the device (the outer system mapped onto the
+    instationary Stokes handle with one time block): vector Q2 - Q1 on 4 x 4 quads, forward form grad.grad +
+    mass on both spaces, analytic fields, the test's tolerances for the solve (1e-14)."""
+    from control_b200 import Control
+    from synthetic import fem
+    sq = fem.assemble_q2q1_stokes_2d(4, 4)
+    M, L, B, Mp, Lp, bd = sq["M_v"], sq["L_v"], sq["B"], sq["M_p"], sq["L_p"], sq["bdofs_v"]
+    K = (L + M).tocsr()
+    beta = 1e-3
+    x, y = sq["coords_v"][:, 0], sq["coords_v"][:, 1]
+    px, py = sq["coords_p"][:, 0], sq["coords_p"][:, 1]
+
+    def vec(cx, cy):
+        a = np.zeros(M.shape[0])
+        a[0::2], a[1::2] = cx, cy
+        return a
+    v_ref = vec(x * np.exp(y) * np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    zeta_ref = vec(np.sin(np.pi * x) * np.sin(2.0 * np.pi * y), np.sin(3.0 * np.pi * x) * np.sin(4.0 * np.pi * y))
+    p_ref = np.sin(np.pi * px) * np.sin(2.0 * np.pi * py)
+    mu_ref = px * np.exp(py)
+    sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 500, "relative_tolerance": 1e-14,
+           "absolute_tolerance": 1e-14}
+    c = Control.Stationary(M, K, beta=beta, bc_dofs=bd)
+    space_p = dict(B=B, M_p=Mp, K_p=Lp, forward_matrix_p=(Lp + Mp).tocsr())
+    info = c.incompressible_linear_solve("constant", space_p=space_p, solver_parameters=sp_, print_error=False,
+                                         lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0),
+                                         v_d=M @ v_ref + K @ zeta_ref + B.T @ mu_ref,
+                                         f=K @ v_ref - (1.0 / beta) * (M @ zeta_ref) + B.T @ p_ref,
+                                         div_v=B @ v_ref, div_zeta=B @ zeta_ref)
+    assert info.reason > 0
+
+    def shift(q):
+        return q - np.ones(Mp.shape[0]) @ (Mp @ q)
+    assert kat.l2_error(M, c._v[None], v_ref[None]) < 5e-13
+    assert kat.l2_error(M, c._zeta[None], zeta_ref[None]) < 5e-13
+    assert kat.l2_error(Mp, shift(c._p)[None], shift(p_ref)[None]) < 3e-12
+    assert kat.l2_error(Mp, shift(c._mu)[None], shift(mu_ref)[None]) < 3e-12
+    c.close()
