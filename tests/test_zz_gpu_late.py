@@ -1,5 +1,7 @@
-"""GPU tests added at the end of round 1.  The file name sorts last on purpose: these cases were written
-when almost no GPU time was left, so ``pytest -x`` reaches every long-verified test before them."""
+"""GPU tests added at the end of round 1 (convection-diffusion, ``Control.Stationary``, Navier-Stokes Picard
+loops).  The file name sorts last on purpose: these cases were written when almost no GPU time was left, so
+``pytest -x`` reaches every long-verified test before them.  All of them passed on a B200
+(gpurun_out/late_tests.log of that run is quoted in DESIGN.md)."""
 import numpy as np
 import pytest
 
