@@ -478,9 +478,8 @@ class Control:
             """control/control.py:3377-3590: Picard / Gauss-Newton loop.  Every outer iteration
             hands new ``K_i`` values to the GPU (``MultiBlockSystem.set_K``) and solves for
             the increment."""
-            if self._bc_values is not None:
-                raise NotImplementedError("non_linear_solve with inhomogeneous Dirichlet data is not wired yet")
             n_t, n = self._n_t, self._n
+            g = self._dirichlet_data()
             v_old = self._v.copy()
             zeta_old = self._zeta.copy()
             v_0 = np.zeros(n) if self._initial_condition is None else np.asarray(self._initial_condition, float)
@@ -502,6 +501,8 @@ class Control:
                                   lambda_v_bounds=lambda_v_bounds, v_d=rhs_0, f=rhs_1,
                                   print_error=print_error_linear, **amg)
                 v_old = v_old + self._v
+                if g is not None:                               # control.py:3480-3483
+                    v_old[:, self._bc_dofs] = g
                 zeta_old = zeta_old + self._zeta
                 self._bc(zeta_old)
                 self._v, self._zeta = v_old.copy(), zeta_old.copy()

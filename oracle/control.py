@@ -197,9 +197,12 @@ def non_linear_res_eval(M, D_v, times, tau, beta, n_t, CN, bdofs, v_old, zeta_ol
 
 def non_linear_solve(M, D_v, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs, v_d, f, v_0=None,
                      solver_parameters=None, lambda_v_bounds=None, inner="amg", amg_params=None,
-                     max_non_linear_iter=10, relative_non_linear_tol=1e-5, absolute_non_linear_tol=1e-8):
+                     max_non_linear_iter=10, relative_non_linear_tol=1e-5, absolute_non_linear_tol=1e-8,
+                     bc_values=None):
     """``Instationary.non_linear_solve`` (control/control.py:3377-3590).  Returns a dict with
-    the final iterate, the residual-norm history and the inner iteration counts."""
+    the final iterate, the residual-norm history and the inner iteration counts.  ``bc_values``
+    (n_t, len(bdofs)): inhomogeneous Dirichlet data, re-imposed on the iterate after every update
+    (3480-3483)."""
     t_0, T_f = time_interval
     tau = (T_f - t_0) / (n_t - 1.0)
     times = t_0 + tau * np.arange(n_t)
@@ -223,6 +226,8 @@ def non_linear_solve(M, D_v, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs, 
                            inner=inner, amg_params=amg_params)
         inner_its.append(out["ksp"].its)
         v_old = v_old + out["v"]
+        if bc_values is not None:
+            v_old[:, bdofs] = bc_values
         zeta_old = zeta_old + out["zeta"]
         zeta_old[:, bdofs] = 0.0
         rhs_0, rhs_1 = non_linear_res_eval(M, D_v, times, tau, beta, n_t, CN, bdofs, v_old, zeta_old, v_0, v_d, f)

@@ -270,3 +270,36 @@ def test_stationary_navier_stokes_picard_loop_host_logic(fake_device):
     assert _rel(c._v, out["v"]) < 1e-6 and _rel(c._zeta, out["zeta"]) < 1e-6
     pm = out["p"] - out["p"].mean()
     assert np.abs((c._p - c._p.mean()) - pm).max() < 1e-5 * np.abs(pm).max()
+
+
+@pytest.mark.parametrize("CN,gauss_newton", [(True, False), (False, False), (True, True)])
+def test_instationary_non_linear_loop_with_inhomogeneous_data_host_logic(fake_device, CN, gauss_newton):
+    """``Control.Instationary.non_linear_solve`` (control/control.py:3377-3590) with time-dependent inhomogeneous
+    Dirichlet data (re-imposed on the iterate after every update, 3480-3483) and the non-linear diffusion
+    operator of BASELINE config C5, against oracle/control.py::non_linear_solve."""
+    Control = fake_device
+    nx, n_t = 6, 5
+    q = kat.heat_problem(nx, n_t, CN, beta=1e-2)
+    Dv = fem.nonlinear_diffusion_p1_2d(nx, nx, 2.0, 2.0)
+    times = q["tau"] * np.arange(n_t)
+    xb, yb = q["coords"][q["bdofs"], 0], q["coords"][q["bdofs"], 1]
+    g = 0.3 * np.stack([np.cos(xb + t) + 0.5 * yb for t in times])
+
+    def level(t):
+        return int(round(t / q["tau"]))
+    c = Control.Instationary(q["M"], lambda v, t, gn: Dv(v, gn), desired_state=lambda t: (q["v_d"][level(t)], q["v_hat"][level(t)]),
+                             force_f=lambda t: q["f"][level(t)], beta=q["beta"], Gauss_Newton=gauss_newton, n_t=n_t,
+                             CN=CN, time_interval=q["time_interval"], bc_dofs=q["bdofs"],
+                             bc_values=lambda t: g[level(t)])
+    k = c.non_linear_solve(lambda_v_bounds=q["lambda_v_bounds"], solver_parameters=SP, max_non_linear_iter=6,
+                           print_error_non_linear=False)
+    ref = ocontrol.non_linear_solve(q["M"], lambda v, t: Dv(v, gauss_newton), beta=q["beta"], n_t=n_t, CN=CN,
+                                    time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"],
+                                    solver_parameters=SP, lambda_v_bounds=q["lambda_v_bounds"], max_non_linear_iter=6,
+                                    bc_values=g)
+    assert k == ref["iterations"] and k >= 2
+    assert np.allclose(c.non_linear_history, ref["history"], rtol=1e-8)
+    assert _rel(c._v, ref["v"]) < 1e-9 and _rel(c._zeta, ref["zeta"]) < 1e-9
+    assert np.array_equal(c._v[1:, q["bdofs"]], g[1:])
+    if not gauss_newton:                                  # (the Gauss-Newton variant of the reference evaluates the
+        assert ref["history"][-1] < 0.2 * ref["history"][0]   # residual with the Jacobian, DESIGN.md section 1 row a11)
