@@ -122,6 +122,9 @@ int ctl_destroy(ctl_handle h)
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
     cudaFree(h->d_bc_rows_all);
+    cudaFree(h->d_gptr);
+    cudaFree(h->d_gcols);
+    cudaFree(h->d_gvals);
     cudaFree(h->d_tile_uptr);
     cudaFree(h->d_tile_ucols);
     cudaFree(h->d_tile_slot);
@@ -242,6 +245,10 @@ static int build_local_pattern(ctl_handle_s *h)
         h->max_row_len = std::max(h->max_row_len, ip[g + 1] - ip[g]);
     }
     if (const char *e = getenv("CTL_KKT_UNSTAGED")) h->force_unstaged = (e[0] == '1');
+    if (const char *e = getenv("CTL_KKT_GROUP")) {
+        const int R = atoi(e);
+        h->group_R = (R == 2 || R == 4) ? R : 0;
+    }
     {   // gather chunk with the fewest padding slots over all rows (ties: the larger chunk)
         const int cand[4] = {4, 5, 7, 8};
         long best = -1;
@@ -373,7 +380,47 @@ int ctl_assemble(ctl_handle h)
         h->k_symmetric = sym;
         if (sym) h->d_KT = h->d_K;
         else CTL_TRY(ctl_upload(h, &h->d_KT, bt.data(), bt.size()));
+        // row-group plan (opt-in): union of the columns of R consecutive rows, R value pairs per union entry
+        h->group_ready = false;
+        if (h->group_R > 0 && sym && h->n_halo == 0 && h->ld == 64) {
+            const int R = h->group_R;
+            const int ng = (nl + R - 1) / R;
+            std::vector<int> gptr(ng + 1, 0), gcols, tmp;
+            std::vector<double> gvals;
+            gcols.reserve((size_t)nnz);
+            gvals.reserve((size_t)nnz * 2 * R);
+            int umax = 0;
+            for (int g = 0; g < ng; ++g) {
+                const int ra = g * R, rb_ = std::min(nl, ra + R);
+                tmp.assign(h->loc.indices.begin() + h->loc.indptr[ra], h->loc.indices.begin() + h->loc.indptr[rb_]);
+                std::sort(tmp.begin(), tmp.end());
+                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+                const size_t base = gcols.size();
+                gcols.insert(gcols.end(), tmp.begin(), tmp.end());
+                gvals.resize((base + tmp.size()) * 2 * R, 0.0);
+                for (int r = ra; r < rb_; ++r)
+                    for (int p = h->loc.indptr[r]; p < h->loc.indptr[r + 1]; ++p) {
+                        const size_t u = base + (std::lower_bound(tmp.begin(), tmp.end(), h->loc.indices[p]) - tmp.begin());
+                        const double mval = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
+                        gvals[(u * R + (r - ra)) * 2 + 0] += mval;      // += : duplicate entries of a row accumulate
+                        gvals[(u * R + (r - ra)) * 2 + 1] += buf[p];
+                    }
+                gptr[g + 1] = (int)gcols.size();
+                umax = std::max(umax, (int)tmp.size());
+            }
+            cudaFree(h->d_gptr);
+            cudaFree(h->d_gcols);
+            cudaFree(h->d_gvals);
+            h->d_gptr = h->d_gcols = nullptr;
+            h->d_gvals = nullptr;
+            CTL_TRY(ctl_upload(h, &h->d_gptr, gptr.data(), gptr.size()));
+            CTL_TRY(ctl_upload(h, &h->d_gcols, gcols.data(), gcols.size()));
+            CTL_TRY(ctl_upload(h, &h->d_gvals, gvals.data(), gvals.size()));
+            h->group_umax = umax;
+            h->group_ready = true;
+        }
     } else {
+        h->group_ready = false;
         // panels [nnz][ld]: column j of the K panel multiplies column j of X_v, i.e. level
         // j+1 for CN (block j holds v_{j+1}) and level j for BE; the K^T panel holds level j
         const int ld = h->ld, N = h->N;

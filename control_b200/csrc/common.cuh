@@ -96,6 +96,14 @@ struct ctl_handle_s {
     int *d_tile_ucols = nullptr;           // runs (first column, length, first slot) x 3, then per-block unique counts
     uint8_t *d_tile_slot = nullptr;        // per local CSR entry
     bool k_symmetric = false;
+    // row-group plan of the grouped KKT apply (kkt_apply.cu, opt-in CTL_KKT_GROUP=2|4): R consecutive rows
+    // share one gather of the UNION of their columns; per union entry R (m, k) value pairs (zero where a
+    // row does not have the column).  Built at ctl_assemble for a time-independent symmetric K, one rank.
+    int group_R = 0;               // requested rows per group (0 = off)
+    bool group_ready = false;
+    int group_umax = 0;            // longest union list
+    int *d_gptr = nullptr, *d_gcols = nullptr;
+    double *d_gvals = nullptr;     // [entries][R] double2 (m, k)
     uint8_t *d_bcmask = nullptr;   // local rows (owned + ghost)
     int *d_bc_rows_all = nullptr;  // list of constrained owned rows
     int n_bc_all = 0;

@@ -743,6 +743,168 @@ void launch_wide(const KktArgs &a, bool per_level, bool sym, bool halo, int rows
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Grouped-rows variant (opt-in, CTL_KKT_GROUP=2|4; ld = 64, one rank, time-independent symmetric K).
+// The staged kernel above is bound by the L1 data pipe: every row gathers its own 7 X row segments
+// (2 panels x 512 B each) although consecutive rows of a mesh matrix share most of their columns.
+// Here a warp owns R consecutive rows and gathers the UNION of their columns once (host-built plan,
+// api.cu: 10 columns instead of 14 for R = 2 on the P1 triangle stencil, 16 instead of 28 for R = 4);
+// every union entry carries R (m, k) pairs -- zero where a row lacks the column -- so the gathered
+// segment feeds R rows from registers.  On-chip gather traffic drops by 29 % / 43 %, matrix bytes
+// grow (36 B per union entry against 20 B per CSR entry: +2 % / +6 % of the HBM traffic of an apply),
+// DFMA count grows by the zero entries.  Same time stencil / T_1, T_2 / Dirichlet epilogue per row.
+// ---------------------------------------------------------------------------------------
+template <bool CN>
+__device__ __forceinline__ void kkt_row_epilogue(const KktArgs &a, const int r, const int lane, const double mv0,
+                                                 const double mv1, const double kv0, const double kv1, const double mz0,
+                                                 const double mz1, const double kz0, const double kz1)
+{
+    constexpr int G = 32;
+    const unsigned full = 0xffffffffu;
+    const int c0 = 2 * lane;
+    const bool first = (lane == 0), last = (lane == G - 1);
+    const int N = a.N;
+    const bool in0 = c0 < N, in1 = c0 + 1 < N;
+    const double tau = a.tau, beta = a.beta;
+    double y00, y01, y10, y11;
+    if (CN) {
+        const double h = 0.5 * tau, hb = h / beta;
+        double t;
+        t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+        t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
+        t = __shfl_down_sync(full, kz0, 1, G); const double kzn1 = last ? 0.0 : t;
+        t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+        double r00 = h * (mvp0 + mv0) + h * (kz0 + kz1) + mz0 - mz1;
+        double r01 = h * (mv0 + mv1) + h * (kz1 + kzn1) + mz1 - mzn1;
+        double r10 = h * (kvp0 + kv0) - mvp0 + mv0 - hb * (mz0 + mz1);
+        double r11 = h * (kv0 + kv1) - mv0 + mv1 - hb * (mz1 + mzn1);
+        if (!in0) { r00 = 0.0; r10 = 0.0; }
+        if (!in1) { r01 = 0.0; r11 = 0.0; }
+        t = __shfl_down_sync(full, r00, 1, G); const double r0n = last ? 0.0 : t;
+        t = __shfl_up_sync(full, r11, 1, G);   const double r1p = first ? 0.0 : t;
+        y00 = r00 + r01;
+        y01 = r01 + r0n;
+        y10 = r10 + r1p;
+        y11 = r11 + r10;
+    } else {
+        const double tb = tau / beta;
+        double t;
+        t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+        t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+        y00 = tau * kz0 + mz0 + ((c0 < N - 1) ? (tau * mv0 - mz1) : 0.0);
+        y01 = tau * kz1 + mz1 + ((c0 + 1 < N - 1) ? (tau * mv1 - mzn1) : 0.0);
+        y10 = tau * kv0 + mv0 + ((c0 >= 1) ? (-mvp0 - tb * mz0) : 0.0);
+        y11 = tau * kv1 + mv1 + (-mv0 - tb * mz1);
+    }
+    if (!in0) { y00 = 0.0; y10 = 0.0; }
+    if (!in1) { y01 = 0.0; y11 = 0.0; }
+    const size_t ro = (size_t)r * a.ld + c0;
+    if (a.bcmask[r]) {
+        const double2 xv = ldg2(a.xv + ro);
+        const double2 xz = ldg2(a.xz + ro);
+        y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
+    }
+    __stcs(reinterpret_cast<double2 *>(a.y0 + ro), make_double2(y00, y01));
+    __stcs(reinterpret_cast<double2 *>(a.y1 + ro), make_double2(y10, y11));
+}
+
+template <bool CN, int R, int SC>
+__global__ void __launch_bounds__(256) kkt_apply_group_kernel(const KktArgs a, const int *__restrict__ gptr,
+                                                             const int *__restrict__ gcols,
+                                                             const double2 *__restrict__ gvals,
+                                                             const int groups_per_cta, const int cap)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [(cap+1) * R] double2 (m, k) | [cap+1] unsigned byte offset of the gathered X row | [groups+1] int
+    double2 *s_val = reinterpret_cast<double2 *>(smem_raw);
+    unsigned *s_off = reinterpret_cast<unsigned *>(s_val + (size_t)(cap + 1) * R);
+    int *s_ptr = reinterpret_cast<int *>(s_off + (cap + 1));
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int n_groups = (a.n_rows + R - 1) / R;
+    const int g0 = blockIdx.x * groups_per_cta;
+    const int ng = min(groups_per_cta, n_groups - g0);
+    const char *__restrict__ xv_b = reinterpret_cast<const char *>(a.xv);
+    const char *__restrict__ xz_b = reinterpret_cast<const char *>(a.xz);
+    const unsigned lane_b = (unsigned)lane * 16u;
+    const unsigned row_b = (unsigned)a.ld * 8u;
+
+    for (int i = threadIdx.x; i <= ng; i += blockDim.x) s_ptr[i] = __ldg(gptr + g0 + i);
+    __syncthreads();
+    const int kb = s_ptr[0];
+    const int cnt = s_ptr[ng] - kb;
+    for (int k = threadIdx.x; k < cnt; k += blockDim.x) s_off[k] = (unsigned)__ldg(gcols + kb + k) * row_b;
+    for (int k = threadIdx.x; k < cnt * R; k += blockDim.x) s_val[k] = __ldg(gvals + (size_t)kb * R + k);
+    if (threadIdx.x == 0) {          // sentinel entry: zero values, a valid row to gather
+        s_off[cap] = 0u;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s_val[(size_t)cap * R + q] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    for (int g = wid; g < ng; g += nwarps) {
+        const int kbeg = s_ptr[g] - kb, kend = s_ptr[g + 1] - kb;
+        double mv0[R], mv1[R], kv0[R], kv1[R], mz0[R], mz1[R], kz0[R], kz1[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) mv0[q] = mv1[q] = kv0[q] = kv1[q] = mz0[q] = mz1[q] = kz0[q] = kz1[q] = 0.0;
+        for (int k0 = kbeg; k0 < kend; k0 += SC) {
+            unsigned off[SC];
+            int kk[SC];
+#pragma unroll
+            for (int j = 0; j < SC; ++j) {
+                kk[j] = (k0 + j < kend) ? k0 + j : cap;
+                off[j] = s_off[kk[j]];
+            }
+            double2 xv[SC], xz[SC];
+#pragma unroll
+            for (int j = 0; j < SC; ++j) {
+                const unsigned o = off[j] + lane_b;
+                xv[j] = __ldg(reinterpret_cast<const double2 *>(xv_b + o));
+                xz[j] = __ldg(reinterpret_cast<const double2 *>(xz_b + o));
+            }
+#pragma unroll
+            for (int j = 0; j < SC; ++j) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const double2 mk = s_val[(size_t)kk[j] * R + q];
+                    mv0[q] = fma(mk.x, xv[j].x, mv0[q]);
+                    mv1[q] = fma(mk.x, xv[j].y, mv1[q]);
+                    mz0[q] = fma(mk.x, xz[j].x, mz0[q]);
+                    mz1[q] = fma(mk.x, xz[j].y, mz1[q]);
+                    kv0[q] = fma(mk.y, xv[j].x, kv0[q]);
+                    kv1[q] = fma(mk.y, xv[j].y, kv1[q]);
+                    kz0[q] = fma(mk.y, xz[j].x, kz0[q]);
+                    kz1[q] = fma(mk.y, xz[j].y, kz1[q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const int r = (g0 + g) * R + q;
+            if (r < a.n_rows)        // warp-uniform
+                kkt_row_epilogue<CN>(a, r, lane, mv0[q], mv1[q], kv0[q], kv1[q], mz0[q], mz1[q], kz0[q], kz1[q]);
+        }
+    }
+}
+
+template <bool CN, int R>
+void launch_group_r(const KktArgs &a, const ctl_handle_s *h, cudaStream_t s)
+{
+    const int gpc = 64 / R;                                  // 64 rows per CTA
+    const int cap = gpc * h->group_umax;
+    const int n_groups = ceil_div(a.n_rows, R);
+    const int blocks = ceil_div(n_groups, gpc);
+    const size_t smem = (size_t)(cap + 1) * (16 * R + 4) + (size_t)(gpc + 1) * 4;
+    const double2 *gv = reinterpret_cast<const double2 *>(h->d_gvals);
+    // gather chunk with the least padding for the longest union list (ties: the larger chunk)
+    const int u = h->group_umax;
+    const int p4 = ceil_div(u, 4) * 4, p5 = ceil_div(u, 5) * 5, p8 = ceil_div(u, 8) * 8;
+    if (p5 < p4 && p5 <= p8) kkt_apply_group_kernel<CN, R, 5><<<blocks, 256, smem, s>>>(a, h->d_gptr, h->d_gcols, gv, gpc, cap);
+    else if (p8 <= p4 && R == 2) kkt_apply_group_kernel<CN, R, 8><<<blocks, 256, smem, s>>>(a, h->d_gptr, h->d_gcols, gv, gpc, cap);
+    else kkt_apply_group_kernel<CN, R, 4><<<blocks, 256, smem, s>>>(a, h->d_gptr, h->d_gcols, gv, gpc, cap);
+}
+
 template <bool CN, bool PER_LEVEL>
 void launch_g(const KktArgs &a, int G, cudaStream_t s)
 {
@@ -797,6 +959,19 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
         const bool sym = h->d_KT == h->d_K;
         if (h->cfg.CN) launch_wide<true>(a, h->per_level, sym, halo, rows_per_cta, rows_per_cta * max_len, h->stream);
         else launch_wide<false>(a, h->per_level, sym, halo, rows_per_cta, rows_per_cta * max_len, h->stream);
+        h->launches++;
+        CTL_CUDA(cudaGetLastError());
+        return CTL_OK;
+    }
+    if (h->group_ready && !h->force_unstaged && !halo && !h->per_level && h->ld == 64 && h->d_KT == h->d_K && fits &&
+        (size_t)(64 / h->group_R * h->group_umax + 1) * (16 * h->group_R + 4) <= 40 * 1024) {
+        if (h->cfg.CN) {
+            if (h->group_R == 4) launch_group_r<true, 4>(a, h, h->stream);
+            else launch_group_r<true, 2>(a, h, h->stream);
+        } else {
+            if (h->group_R == 4) launch_group_r<false, 4>(a, h, h->stream);
+            else launch_group_r<false, 2>(a, h, h->stream);
+        }
         h->launches++;
         CTL_CUDA(cudaGetLastError());
         return CTL_OK;

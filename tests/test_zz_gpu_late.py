@@ -187,3 +187,22 @@ def test_reference_stationary_stokes_known_answer_on_gpu():
     assert kat.l2_error(Mp, shift(c._p)[None], shift(p_ref)[None]) < 3e-12
     assert kat.l2_error(Mp, shift(c._mu)[None], shift(mu_ref)[None]) < 3e-12
     c.close()
+
+
+@pytest.mark.parametrize("R", ["2", "4"])
+def test_grouped_rows_apply_matches_literal_operator(R, monkeypatch):
+    """The opt-in grouped-rows KKT-apply kernel (CTL_KKT_GROUP=2|4: R consecutive rows share one gather of the
+    union of their columns; ld = 64 only) against the literal block-by-block operator: CN and BE, row counts that
+    are not multiples of R, Dirichlet rows, a 3-D tetrahedral stencil, no constrained dofs."""
+    from test_gpu_apply import _check_apply
+    from synthetic import fem
+    monkeypatch.setenv("CTL_KKT_GROUP", R)
+    M, K, _, bd = fem.assemble_p1_2d(23, 17, 2.0, 1.0)              # n = 432
+    M2, K2, _, bd2 = fem.assemble_p1_2d(6, 8, 1.0, 1.0)             # n = 63: last group incomplete
+    M3, K3, _, bd3 = fem.assemble_p1_3d(6, 5, 4)
+    for CN in (True, False):
+        for n_t in (40, 64):
+            _check_apply(M, K, n_t, CN, bd, tau_interval=(0.0, 2.0), seed=n_t)
+        _check_apply(M2, K2, 50, CN, bd2)
+        _check_apply(M2, K2, 50, CN, np.zeros(0, dtype=np.int32))
+        _check_apply(M3, K3, 64 if CN else 63, CN, bd3)
