@@ -286,8 +286,6 @@ class Control:
                 raise ValueError("only the constant pressure nullspace is supported")
             if P is not None:
                 raise NotImplementedError("user preconditioners are not wired for the Stokes system")
-            if Multigrid:
-                raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
             n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
             N = n_t - 1 if CN else n_t
             n_p = space_p["M_p"].shape[0]
@@ -333,7 +331,7 @@ class Control:
                 self._stokes.set_forward(K, D_p)
             system = self._stokes
             system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
-                                        amg_p=amg_p)
+                                        amg_p=amg_p, Multigrid=Multigrid)
             u_0 = np.zeros((2 * N, n))
             u_1 = np.zeros((2 * N, n_p))
             self.last_ksp = system.solve(u_0, u_1, b_0, b_1, solver_parameters=solver_parameters, pc_fn="builtin")

@@ -188,8 +188,6 @@ class Stationary:
             raise ValueError("only the constant pressure nullspace is supported")
         if P is not None:
             raise NotImplementedError("user preconditioners are not wired for the Stokes system")
-        if Multigrid:
-            raise NotImplementedError("Multigrid=True is not wired for the Stokes system")
         n, M, B = self._n, self._M, space_p["B"]
         M_p = space_p["M_p"].tocsr()
         n_p = M_p.shape[0]
@@ -232,7 +230,7 @@ class Stationary:
             self._stokes.set_forward(K_shift, D_p_shift)
         system = self._stokes
         system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
-                                    amg_p=amg_p)
+                                    amg_p=amg_p, Multigrid=Multigrid)
         u_0 = np.zeros((2, n))
         u_1 = np.zeros((2, n_p))
         self.last_ksp = system.solve(u_0, u_1, np.stack([b_00, b_01]), 2.0 * np.stack([b_10, b_11]),

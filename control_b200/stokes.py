@@ -111,12 +111,14 @@ class StokesSystem:
         return y_dev
 
     def setup_preconditioner(self, *, lambda_v_bounds=None, lambda_p_bounds=None, inner_its=5, mass_p_steps=20,
-                             amg=None, amg_p=None):
+                             amg=None, amg_p=None, Multigrid=False):
         """The in-built pressure-Schur preconditioner (control/control.py:4299-4687).  ``amg`` /
         ``amg_p``: parameters of the AMG stand-in for the velocity sweeps / the K_p solves."""
         o = L.ctl_stokes_pc_options()
         self.velocity._check(self._lib.ctl_stokes_pc_default_options(C.byref(o)))
-        if lambda_v_bounds is not None:
+        if Multigrid:                                   # construct_pc(Multigrid, ...), control/control.py:1954-1965
+            o.velocity.solver_0 = L.CTL_S0_AMG
+        elif lambda_v_bounds is not None:
             o.velocity.solver_0 = L.CTL_S0_CHEBYSHEV
             o.velocity.cheb_emin, o.velocity.cheb_emax = float(lambda_v_bounds[0]), float(lambda_v_bounds[1])
         if lambda_p_bounds is not None:

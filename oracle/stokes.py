@@ -139,7 +139,7 @@ def make_solver_p(M_p, K_p, lambda_p_bounds, amg_params=None):
 
 def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, lambda_v_bounds=None,
                         lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None, epsilon=1e-3,
-                        D_p=None):
+                        D_p=None, Multigrid=False):
     """``pc_fn(b_0, b_1) -> (u_0, u_1)`` of control/control.py:4337-4513 (CN) / 4515-4687 (BE).
     ``K_p``: the Laplacian ``solver_K_p`` inverts (3746, 4300-4309); ``D_p``: the forward form on the pressure
     space per time level (``D_p_i``, 3787-3789, 3926-3928; one matrix or n_t matrices) of the pressure-space
@@ -149,7 +149,7 @@ def construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v, *, l
     vparams = dict(cycles=6)                      # ctl_stokes_pc_default_options: six cycles on the P2 operator
     vparams.update(amg_params or {})
     heat_pc = construct_pc(M_v, K_v, tau, beta, n_t, CN, bdofs_v, lambda_v_bounds=lambda_v_bounds,
-                           inner=inner, amg_params=vparams, epsilon=epsilon)
+                           Multigrid=Multigrid, inner=inner, amg_params=vparams, epsilon=epsilon)
     K_solve, M_solve, _ = make_solver_p(M_p, K_p, lambda_p_bounds, amg_params_p)
     pblocks = kkt.build_blocks(M_p, K_p if D_p is None else D_p, tau, beta, n_t, CN)       # block_*_int_p, 3805-3957
     inner_parameters = {"preconditioner": True, "linear_solver": "gmres", "maximum_iterations": 5,
@@ -209,7 +209,7 @@ class _PairNullspace:
 
 def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, b_0, b_1,
                  solver_parameters=None, lambda_v_bounds=None, lambda_p_bounds=None, inner="amg",
-                 amg_params=None, amg_params_p=None, pc_fn=None, D_p=None):
+                 amg_params=None, amg_params_p=None, pc_fn=None, D_p=None, Multigrid=False):
     """``MultiBlockSystem.solve`` of the outer Stokes system from a zero initial guess
     (control/control.py:4273-4297, 4688-4693).  ``b_0`` (2N, n_v), ``b_1`` (2N, n_p) are the
     final right-hand sides (T transforms already applied).  Returns (u_0, u_1, KSPResult)."""
@@ -221,7 +221,8 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
     if pc_fn is None:
         pc_fn = construct_stokes_pc(M_v, K_v, B, M_p, K_p, tau, beta, n_t, CN, bdofs_v,
                                     lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds,
-                                    inner=inner, amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p)
+                                    inner=inner, amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p,
+                                    Multigrid=Multigrid)
     if solver_parameters is None:                                # control/control.py:4291-4297
         solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 100,
                              "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0}
@@ -266,7 +267,7 @@ def stokes_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.
 def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_interval=(0.0, 1.0), bdofs_v, v_d, f,
                                 v_0=None, div_v=None, div_zeta=None, solver_parameters=None, lambda_v_bounds=None,
                                 lambda_p_bounds=None, inner="amg", amg_params=None, amg_params_p=None,
-                                check_v_d=True, check_f=True, bc_values=None, D_p=None):
+                                check_v_d=True, check_f=True, bc_values=None, D_p=None, Multigrid=False):
     """``Control.Instationary.incompressible_linear_solve`` for homogeneous Dirichlet velocity data
     (control/control.py:3592-4725): right-hand sides (3961-4243; the velocity rows are those of
     the heat problem, the pressure rows are zero unless div_v / div_zeta are given), outer solve,
@@ -297,7 +298,7 @@ def incompressible_linear_solve(M_v, K_v, B, M_p, K_p, *, beta, n_t, CN, time_in
                                  bdofs_v=bdofs_v, b_0=np.concatenate([b_0_0, b_0_1]),
                                  b_1=np.concatenate([b_1_0, b_1_1]), solver_parameters=solver_parameters,
                                  lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, inner=inner,
-                                 amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p)
+                                 amg_params=amg_params, amg_params_p=amg_params_p, D_p=D_p, Multigrid=Multigrid)
     if CN:
         v = np.zeros((n_t, n_v))
         zeta = np.zeros((n_t, n_v))

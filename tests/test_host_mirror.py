@@ -69,8 +69,9 @@ class FakeStokesSystem:
             self.D_p = D_p
         self.pc_kw = None
 
-    def setup_preconditioner(self, *, lambda_v_bounds=None, lambda_p_bounds=None, amg=None, amg_p=None):
-        self.pc_kw = dict(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg_params=amg, amg_params_p=amg_p)
+    def setup_preconditioner(self, *, lambda_v_bounds=None, lambda_p_bounds=None, amg=None, amg_p=None, Multigrid=False):
+        self.pc_kw = dict(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg_params=amg, amg_params_p=amg_p,
+                          Multigrid=Multigrid)
 
     def solve(self, u_0, u_1, b_0, b_1, *, solver_parameters, pc_fn):
         assert pc_fn == "builtin" and self.pc_kw is not None

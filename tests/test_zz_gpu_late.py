@@ -206,3 +206,32 @@ def test_grouped_rows_apply_matches_literal_operator(R, monkeypatch):
         _check_apply(M2, K2, 50, CN, bd2)
         _check_apply(M2, K2, 50, CN, np.zeros(0, dtype=np.int32))
         _check_apply(M3, K3, 64 if CN else 63, CN, bd3)
+
+
+def test_stokes_control_with_multigrid_mass_solver():
+    """``incompressible_linear_solve(Multigrid=True)``: the (1,1) block of the inner heat-type preconditioner is
+    solved with AMG cycles on ``M_v`` instead of Chebyshev (control/control.py:1954-1965 inside 4346-4353)."""
+    from control_b200 import Control
+    from oracle import stokes
+    q = kat.stokes_problem(6, 6, True)
+    th = q["th"]
+    times = q["tau"] * np.arange(q["n_t"])
+    lookup = {round(float(t), 12): i for i, t in enumerate(times)}
+    c = Control.Instationary(q["M"], q["K"], desired_state=lambda t: (q["v_d"][lookup[round(float(t), 12)]],
+                                                                    q["v_hat"][lookup[round(float(t), 12)]]),
+                             force_f=lambda t: q["f"][lookup[round(float(t), 12)]], beta=q["beta"], CN=True, n_t=q["n_t"],
+                             time_interval=q["time_interval"], bc_dofs=q["bdofs"])
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 200, "relative_tolerance": 1e-8, "absolute_tolerance": 0.0,
+           "gmres_restart": 100}
+    amg, amg_p = dict(coarse_max=40), dict(coarse_max=20)
+    info = c.incompressible_linear_solve("constant", space_p=dict(B=th["B"], M_p=th["M_p"], K_p=th["K_p"]),
+                                         solver_parameters=sp_, Multigrid=True, lambda_p_bounds=q["lambda_p_bounds"],
+                                         amg=amg, amg_p=amg_p)
+    v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+        th["M_v"], th["K_v"], th["B"], th["M_p"], th["K_p"], beta=q["beta"], n_t=q["n_t"], CN=True,
+        time_interval=q["time_interval"], bdofs_v=q["bdofs"], v_d=q["v_d"], f=q["f"], solver_parameters=sp_,
+        Multigrid=True, lambda_p_bounds=q["lambda_p_bounds"], amg_params=amg, amg_params_p=amg_p)
+    assert info.reason == res.reason > 0
+    assert abs(info.its - res.its) <= max(1, int(0.03 * res.its))
+    assert np.abs(c._v - v).max() < 1e-5 * np.abs(v).max() and np.abs(c._zeta - zeta).max() < 1e-5 * np.abs(zeta).max()
+    c.close()
