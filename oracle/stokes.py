@@ -18,7 +18,6 @@ The inner solves on ``K_p`` are six cycles of the stand-in AMG (ONE hypre Boomer
 reference, control/control.py:4300-4309): parity with hypre is unpinned, as for the heat path.
 """
 import numpy as np
-import scipy.sparse as sp
 
 from . import amg as _amg
 from . import kkt, krylov
