@@ -266,7 +266,10 @@ static int build_local_pattern(ctl_handle_s *h)
         if (const char *e = getenv("CTL_KKT_CHUNK")) h->gather_chunk = atoi(e);
     }
     h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
-    if (const char *e = getenv("CTL_KKT_TMA")) h->no_tma = !(e[0] == '1');
+    if (const char *e = getenv("CTL_KKT_TMA")) {
+        h->no_tma = !(e[0] == '1' || e[0] == '2');
+        h->tma_pipe = (e[0] == '2');
+    }
     // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows
     {
         int TR = 32;

@@ -88,6 +88,7 @@ struct ctl_handle_s {
     int gather_chunk = 4;       // entries per gather pass of the staged KKT apply (4, 5, 7 or 8: least padding)
     bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
     bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
+    bool tma_pipe = false;         // CTL_KKT_TMA=2: persistent two-stage variant (next tile copied while this one is consumed)
     // TMA tile plan of the fused KKT apply (kkt_apply.cu): row blocks of TILE_ROWS rows, the
     // unique columns each block gathers, and for every CSR entry its slot in that list
     int tile_rows = 0, tile_umax = 0;      // 0 = no plan (fallback to the LDG-gather kernel)

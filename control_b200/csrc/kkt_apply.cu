@@ -557,6 +557,230 @@ __global__ void __launch_bounds__(TR * 8, 512 / (TR * 8) * 2) kkt_apply_tma_kern
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Persistent two-stage variant of the TMA-staged kernel (opt-in, CTL_KKT_TMA=2; written at the end of
+// round 1 when no GPU time was left: compiled, NOT yet run -- first item of the next round).  The
+// one-shot kernel above copies a tile and then consumes it, relying on a second resident CTA for overlap;
+// here every CTA loops over row blocks and the bulk copies of block i+1 are issued into the other stage
+// BEFORE block i is consumed, so a whole tile (55-104 KB per SM, no registers) is in flight while the SM
+// computes -- the "independent gathers in flight" that bound the LDG kernel.
+// Stage reuse is ordered by the __syncthreads() that ends an iteration; each stage has its own mbarrier,
+// whose k-th use completes phase k & 1.
+// ---------------------------------------------------------------------------------------
+template <bool CN, bool SYM, bool HALO, int G, int TR>
+__global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArgs a, const int cap, const int umax,
+                                                                   const int n_blocks)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ld = a.ld;
+    const unsigned row_b = (unsigned)ld * 8u;
+    const size_t tile_b = (size_t)umax * row_b;
+    // layout: stage 0 [tile_v | tile_z] | stage 1 [tile_v | tile_z] | mk [cap+1] double2 | kt [cap+1] double (!SYM)
+    //         | off [cap+1] unsigned | ptr [TR+1] int | 2 mbarriers
+    unsigned char *tiles = smem_raw;
+    double2 *s_mk = reinterpret_cast<double2 *>(tiles + 4 * tile_b);
+    double *s_kt = reinterpret_cast<double *>(s_mk + (cap + 1));
+    unsigned *s_off = reinterpret_cast<unsigned *>(SYM ? s_kt : s_kt + (cap + 1));
+    int *s_ptr = reinterpret_cast<int *>(s_off + (cap + 1));
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(s_ptr + (TR + 1)) + 7) & ~(uintptr_t)7);
+
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int sub = lane / G, l = lane % G;
+    const int c0 = 2 * l;
+    const unsigned mbar_s0 = smem_u32(mbar), mbar_s1 = smem_u32(mbar + 1);
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // producer (warp 0): arm the stage's barrier with the byte count, then one bulk copy per run and panel
+    auto issue_tile = [&](const int blk, const int st) {
+        const unsigned mb = st ? mbar_s1 : mbar_s0;
+        unsigned char *tv = tiles + (size_t)st * 2 * tile_b;
+        unsigned char *tz = tv + tile_b;
+        const int ub = __ldg(a.tile_uptr + blk);
+        const int n_runs = __ldg(a.tile_uptr + blk + 1) - ub;
+        const int U = __ldg(a.tile_ucols + a.tile_count_off + blk);
+        if (lane == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * (unsigned)U * row_b)
+                         : "memory");
+        __syncwarp();
+        for (int u = lane; u < n_runs; u += 32) {
+            const int c = __ldg(a.tile_ucols + 3 * (ub + u));
+            const unsigned bytes = (unsigned)__ldg(a.tile_ucols + 3 * (ub + u) + 1) * row_b;
+            const size_t dst = (size_t)__ldg(a.tile_ucols + 3 * (ub + u) + 2) * row_b;
+            const double *sv, *sz;
+            if (HALO && c >= a.n_own_cols) {
+                sv = a.hv + (size_t)(c - a.n_own_cols) * ld;
+                sz = a.hz + (size_t)(c - a.n_own_cols) * ld;
+            } else {
+                sv = a.xv + (size_t)c * ld;
+                sz = a.xz + (size_t)c * ld;
+            }
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tv + dst)),
+                         "l"(sv), "r"(bytes), "r"(mb)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(tz + dst)),
+                         "l"(sz), "r"(bytes), "r"(mb)
+                         : "memory");
+        }
+    };
+
+    const unsigned full = 0xffffffffu;
+    const bool first = (l == 0), last = (l == G - 1);
+    const int N = a.N;
+    const bool in0 = c0 < N, in1 = c0 + 1 < N;
+    const double tau = a.tau, beta = a.beta;
+    const unsigned lane_b = (unsigned)c0 * 8u;
+    const int nwarps = blockDim.x >> 5;
+
+    if (wid == 0 && (int)blockIdx.x < n_blocks) issue_tile(blockIdx.x, 0);
+    int it = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        const int st = it & 1;
+        const unsigned phase = (unsigned)(it >> 1) & 1u;
+        const int nb = blk + gridDim.x;
+        // stage st^1 was last read in iteration it-1, which ended with a __syncthreads(): safe to overwrite
+        if (wid == 0 && nb < n_blocks) issue_tile(nb, st ^ 1);
+        const int r0 = blk * TR;
+        const int nrows = min(TR, a.n_rows - r0);
+        for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
+        __syncthreads();
+        const int kb = s_ptr[0];
+        const int cnt = s_ptr[nrows] - kb;
+        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+            s_off[k] = (unsigned)__ldg(a.tile_slot + kb + k) * row_b;
+            s_mk[k] = make_double2(__ldg(a.Mv + kb + k), __ldg(a.Kv + kb + k));
+            if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+        }
+        if (threadIdx.x == 0) {
+            s_off[cap] = 0u;
+            s_mk[cap] = make_double2(0.0, 0.0);
+            if (!SYM) s_kt[cap] = 0.0;
+        }
+        __syncthreads();
+        {   // wait for this stage's tile
+            const unsigned mb = st ? mbar_s1 : mbar_s0;
+            unsigned done = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done)
+                             : "r"(mb), "r"(phase)
+                             : "memory");
+            }
+        }
+        const unsigned char *tile_v = tiles + (size_t)st * 2 * tile_b;
+        const unsigned char *tile_z = tile_v + tile_b;
+        for (int base = wid * RPW; base < nrows; base += nwarps * RPW) {
+            const int lr_raw = base + sub;
+            const bool live = lr_raw < nrows;
+            const int lr = live ? lr_raw : nrows - 1;
+            const int r = r0 + lr;
+            const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
+            double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
+            for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
+#pragma unroll
+                for (int j = 0; j < SCHUNK; ++j) {
+                    const int kk = (k0 + j < kend) ? k0 + j : cap;
+                    const unsigned o = s_off[kk] + lane_b;
+                    const double2 xv = *reinterpret_cast<const double2 *>(tile_v + o);
+                    const double2 xz = *reinterpret_cast<const double2 *>(tile_z + o);
+                    const double2 mk = s_mk[kk];
+                    const double kt = SYM ? mk.y : s_kt[kk];
+                    mv0 = fma(mk.x, xv.x, mv0);
+                    mv1 = fma(mk.x, xv.y, mv1);
+                    mz0 = fma(mk.x, xz.x, mz0);
+                    mz1 = fma(mk.x, xz.y, mz1);
+                    kv0 = fma(mk.y, xv.x, kv0);
+                    kv1 = fma(mk.y, xv.y, kv1);
+                    kz0 = fma(kt, xz.x, kz0);
+                    kz1 = fma(kt, xz.y, kz1);
+                }
+            }
+            double y00, y01, y10, y11;
+            if (CN) {
+                const double h = 0.5 * tau, hb = h / beta;
+                double t;
+                t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+                t = __shfl_up_sync(full, kv1, 1, G);   const double kvp0 = first ? 0.0 : t;
+                t = __shfl_down_sync(full, kz0, 1, G); const double kzn1 = last ? 0.0 : t;
+                t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+                double r00 = h * (mvp0 + mv0) + h * (kz0 + kz1) + mz0 - mz1;
+                double r01 = h * (mv0 + mv1) + h * (kz1 + kzn1) + mz1 - mzn1;
+                double r10 = h * (kvp0 + kv0) - mvp0 + mv0 - hb * (mz0 + mz1);
+                double r11 = h * (kv0 + kv1) - mv0 + mv1 - hb * (mz1 + mzn1);
+                if (!in0) { r00 = 0.0; r10 = 0.0; }
+                if (!in1) { r01 = 0.0; r11 = 0.0; }
+                t = __shfl_down_sync(full, r00, 1, G); const double r0n = last ? 0.0 : t;
+                t = __shfl_up_sync(full, r11, 1, G);   const double r1p = first ? 0.0 : t;
+                y00 = r00 + r01;
+                y01 = r01 + r0n;
+                y10 = r10 + r1p;
+                y11 = r11 + r10;
+            } else {
+                const double tb = tau / beta;
+                double t;
+                t = __shfl_up_sync(full, mv1, 1, G);   const double mvp0 = first ? 0.0 : t;
+                t = __shfl_down_sync(full, mz0, 1, G); const double mzn1 = last ? 0.0 : t;
+                y00 = tau * kz0 + mz0 + ((c0 < N - 1) ? (tau * mv0 - mz1) : 0.0);
+                y01 = tau * kz1 + mz1 + ((c0 + 1 < N - 1) ? (tau * mv1 - mzn1) : 0.0);
+                y10 = tau * kv0 + mv0 + ((c0 >= 1) ? (-mvp0 - tb * mz0) : 0.0);
+                y11 = tau * kv1 + mv1 + (-mv0 - tb * mz1);
+            }
+            if (!in0) { y00 = 0.0; y10 = 0.0; }
+            if (!in1) { y01 = 0.0; y11 = 0.0; }
+            if (live) {
+                const size_t ro = (size_t)r * ld + c0;
+                if (a.bcmask[r]) {
+                    const double2 xv = ldg2(a.xv + ro);
+                    const double2 xz = ldg2(a.xz + ro);
+                    y00 = xv.x; y01 = xv.y; y10 = xz.x; y11 = xz.y;
+                }
+                __stcs(reinterpret_cast<double2 *>(a.y0 + ro), make_double2(y00, y01));
+                __stcs(reinterpret_cast<double2 *>(a.y1 + ro), make_double2(y10, y11));
+            }
+        }
+        __syncthreads();      // every read of stage st and of the CSR staging is done
+    }
+}
+
+template <bool CN, bool SYM, bool HALO, int G, int TR>
+cudaError_t launch_tma_pipe_gt(const KktArgs &a, int cap, int umax, cudaStream_t s)
+{
+    const int n_blocks = ceil_div(a.n_rows, TR);
+    const size_t smem = (size_t)4 * umax * a.ld * 8 + (size_t)(cap + 1) * (16 + (SYM ? 0 : 8) + 4) + (TR + 1) * 4 + 32;
+    auto kern = kkt_apply_tma_pipe_kernel<CN, SYM, HALO, G, TR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    const int grid = std::min(n_blocks, n_sm * per_sm);
+    kern<<<grid, TR * 8, smem, s>>>(a, cap, umax, n_blocks);
+    return cudaSuccess;
+}
+
+template <bool CN, bool SYM, bool HALO>
+cudaError_t launch_tma_pipe(const KktArgs &a, int G, int cap, int umax, int tile_rows, cudaStream_t s)
+{
+    // ld = 64 (G = 32) only: the configuration the pipeline is meant for
+    if (G != 32) return cudaErrorInvalidValue;
+    if (tile_rows == 16) return launch_tma_pipe_gt<CN, SYM, HALO, 32, 16>(a, cap, umax, s);
+    return launch_tma_pipe_gt<CN, SYM, HALO, 32, 32>(a, cap, umax, s);
+}
+
 template <bool CN, bool SYM, bool HALO, int G, int TR>
 cudaError_t launch_tma_gt(const KktArgs &a, int cap, int umax, cudaStream_t s)
 {
@@ -984,7 +1208,19 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     const int tcap = h->tile_rows * max_len;
     const size_t tma_smem = (size_t)2 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 16;
     const bool use_tma = h->tile_rows > 0 && !h->per_level && !h->force_unstaged && !h->no_tma && tma_smem <= 113 * 1024;
-    if (use_tma) {
+    const size_t pipe_smem = (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 32;
+    if (h->tma_pipe && h->tile_rows > 0 && !h->per_level && !h->force_unstaged && G == 32 && pipe_smem <= 227 * 1024) {
+        const bool sym = h->d_KT == h->d_K;
+        cudaError_t e;
+        if (h->cfg.CN) {
+            if (sym) e = halo ? launch_tma_pipe<true, true, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma_pipe<true, true, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma_pipe<true, false, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma_pipe<true, false, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+        } else {
+            if (sym) e = halo ? launch_tma_pipe<false, true, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma_pipe<false, true, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma_pipe<false, false, true>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream) : launch_tma_pipe<false, false, false>(a, G, tcap, h->tile_umax, h->tile_rows, h->stream);
+        }
+        CTL_CUDA(e);
+    } else if (use_tma) {
         const bool sym = h->d_KT == h->d_K;
         cudaError_t e;
         if (h->cfg.CN) {

@@ -235,3 +235,25 @@ def test_stokes_control_with_multigrid_mass_solver():
     assert abs(info.its - res.its) <= max(1, int(0.03 * res.its))
     assert np.abs(c._v - v).max() < 1e-5 * np.abs(v).max() and np.abs(c._zeta - zeta).max() < 1e-5 * np.abs(zeta).max()
     c.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CTL_RUN_UNVERIFIED") != "1",
+                    reason="persistent two-stage TMA kernel: compiled at the end of round 1, not yet run on hardware "
+                           "(set CTL_RUN_UNVERIFIED=1 to run it)")
+@pytest.mark.parametrize("tile_rows", ["32", "16"])
+def test_pipelined_tma_apply_matches_literal_operator(tile_rows, monkeypatch):
+    """The opt-in persistent two-stage TMA kernel (CTL_KKT_TMA=2): more row blocks than CTAs (several pipeline
+    iterations per CTA, both barrier phases), CN and BE, non-symmetric K, a 3-D stencil."""
+    from test_gpu_apply import _check_apply
+    from synthetic import fem
+    monkeypatch.setenv("CTL_KKT_TMA", "2")
+    monkeypatch.setenv("CTL_TILE_ROWS", tile_rows)
+    M, K, _, bd = fem.assemble_p1_2d(160, 150, 2.0, 1.0)            # 24,311 rows: > 148 x 2 blocks of 32 rows
+    for CN in (True, False):
+        _check_apply(M, K, 64, CN, bd, tau_interval=(0.0, 2.0), seed=1)
+        _check_apply(M, K, 40, CN, bd, tau_interval=(0.0, 2.0), seed=2)
+    K2 = K.copy()
+    K2.data = K2.data * (1.0 + 0.2 * np.random.default_rng(1).standard_normal(K2.nnz))
+    _check_apply(M, K2, 50, True, bd)
+    M3, K3, _, bd3 = fem.assemble_p1_3d(12, 11, 10)
+    _check_apply(M3, K3, 64, True, bd3)
