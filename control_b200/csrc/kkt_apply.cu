@@ -558,8 +558,9 @@ __global__ void __launch_bounds__(TR * 8, 512 / (TR * 8) * 2) kkt_apply_tma_kern
 }
 
 // ---------------------------------------------------------------------------------------
-// Persistent two-stage variant of the TMA-staged kernel (opt-in, CTL_KKT_TMA=2; written at the end of
-// round 1 when no GPU time was left: compiled, NOT yet run -- first item of the next round).  The
+// Persistent two-stage variant of the TMA-staged kernel (opt-in, CTL_KKT_TMA=2; end of round 1: bit-identical
+// to the staged kernel on a B200 but 2.2x slower in this first form -- the CSR slice of a block is still staged
+// with two dependent global round trips inside the single resident CTA).  The
 // one-shot kernel above copies a tile and then consumes it, relying on a second resident CTA for overlap;
 // here every CTA loops over row blocks and the bulk copies of block i+1 are issued into the other stage
 // BEFORE block i is consumed, so a whole tile (55-104 KB per SM, no registers) is in flight while the SM
