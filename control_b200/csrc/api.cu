@@ -122,6 +122,8 @@ int ctl_destroy(ctl_handle h)
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
     cudaFree(h->d_bc_rows_all);
+    cudaFree(h->d_rec);
+    cudaFree(h->d_rec_off);
     cudaFree(h->d_gptr);
     cudaFree(h->d_gcols);
     cudaFree(h->d_gvals);
@@ -267,8 +269,9 @@ static int build_local_pattern(ctl_handle_s *h)
     }
     h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
     if (const char *e = getenv("CTL_KKT_TMA")) {
-        h->no_tma = !(e[0] == '1' || e[0] == '2');
-        h->tma_pipe = (e[0] == '2');
+        h->no_tma = !(e[0] == '1' || e[0] == '2' || e[0] == '3');
+        h->tma_pipe = (e[0] == '2' || e[0] == '3');
+        h->tma_rec = (e[0] == '3');
     }
     // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows
     {
@@ -318,6 +321,7 @@ static int build_local_pattern(ctl_handle_s *h)
             CTL_TRY(ctl_upload(h, &h->d_tile_slot, slot.data(), slot.size()));
             h->tile_rows = TR;
             h->tile_umax = umax;
+            if (h->tma_rec) h->h_tile_slot = slot;
         }
     }
     // note: local column order within a row is no longer sorted when ghosts precede owned
@@ -422,8 +426,47 @@ int ctl_assemble(ctl_handle h)
             h->group_umax = umax;
             h->group_ready = true;
         }
+        // record stream of the CTL_KKT_TMA=3 kernel: the CSR slice of every row block in the layout the kernel
+        // reads from shared memory, so that it arrives with one bulk copy (16-byte aligned offsets and sizes)
+        h->rec_max = 0;
+        if (h->tma_rec && h->tile_rows > 0 && !h->h_tile_slot.empty() && h->ld == 64) {
+            const int TR = h->tile_rows;
+            const int nblk = (nl + TR - 1) / TR;
+            const size_t row_b = (size_t)h->ld * 8;
+            auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+            const size_t hdr = up16((size_t)(TR + 1) * 4);
+            std::vector<int> roff(nblk + 1, 0);
+            std::vector<uint8_t> rec;
+            rec.reserve((size_t)nnz * (sym ? 20 : 28) + (size_t)nblk * (hdr + 64));
+            for (int b = 0; b < nblk; ++b) {
+                const int r0 = b * TR, r1 = std::min(nl, r0 + TR);
+                const int kb = h->loc.indptr[r0], cnt = h->loc.indptr[r1] - kb;
+                const size_t o_mk = hdr, o_kt = o_mk + (size_t)(cnt + 1) * 16;
+                const size_t o_off = sym ? o_kt : o_kt + up16((size_t)(cnt + 1) * 8);
+                const size_t bytes = o_off + up16((size_t)(cnt + 1) * 4);
+                const size_t base = rec.size();
+                rec.resize(base + bytes, 0);
+                int *ptr = reinterpret_cast<int *>(rec.data() + base);
+                for (int i = 0; i <= TR; ++i) ptr[i] = h->loc.indptr[std::min(r0 + i, r1)] - kb;
+                double *mk = reinterpret_cast<double *>(rec.data() + base + o_mk);
+                double *kt = reinterpret_cast<double *>(rec.data() + base + o_kt);
+                unsigned *off = reinterpret_cast<unsigned *>(rec.data() + base + o_off);
+                for (int k = 0; k < cnt; ++k) {
+                    const int64_t p = kb + k;
+                    mk[2 * k] = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
+                    mk[2 * k + 1] = buf[p];
+                    if (!sym) kt[k] = bt[p];
+                    off[k] = (unsigned)h->h_tile_slot[p] * (unsigned)row_b;
+                }
+                roff[b + 1] = (int)((base + bytes) / 16);
+                h->rec_max = std::max(h->rec_max, (int)bytes);
+            }
+            CTL_TRY(ctl_upload(h, &h->d_rec, rec.data(), rec.size()));
+            CTL_TRY(ctl_upload(h, &h->d_rec_off, roff.data(), roff.size()));
+        }
     } else {
         h->group_ready = false;
+        h->rec_max = 0;
         // panels [nnz][ld]: column j of the K panel multiplies column j of X_v, i.e. level
         // j+1 for CN (block j holds v_{j+1}) and level j for BE; the K^T panel holds level j
         const int ld = h->ld, N = h->N;

@@ -88,7 +88,14 @@ struct ctl_handle_s {
     int gather_chunk = 4;       // entries per gather pass of the staged KKT apply (4, 5, 7 or 8: least padding)
     bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
     bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
-    bool tma_pipe = false;         // CTL_KKT_TMA=2: persistent two-stage variant (next tile copied while this one is consumed)
+    bool tma_pipe = false;         // CTL_KKT_TMA=2|3: persistent two-stage variant (next tile copied while this one is consumed)
+    bool tma_rec = false;          // CTL_KKT_TMA=3: ... and the CSR slice of a row block arrives as ONE bulk copy too
+    // record stream of CTL_KKT_TMA=3 (built at ctl_assemble): per row block a 16-byte aligned record
+    // [int ptr[TR+1] | double2 (m,k)[cnt+1] | double kt[cnt+1] (non-symmetric K) | unsigned off[cnt+1]], entry cnt = zero sentinel
+    std::vector<uint8_t> h_tile_slot;      // host copy of d_tile_slot
+    uint8_t *d_rec = nullptr;
+    int *d_rec_off = nullptr;              // n_blocks + 1 offsets in units of 16 bytes
+    int rec_max = 0;                       // longest record in bytes
     // TMA tile plan of the fused KKT apply (kkt_apply.cu): row blocks of TILE_ROWS rows, the
     // unique columns each block gathers, and for every CSR entry its slot in that list
     int tile_rows = 0, tile_umax = 0;      // 0 = no plan (fallback to the LDG-gather kernel)

@@ -45,6 +45,9 @@ struct KktArgs {
     const int *tile_uptr, *tile_ucols;   // TMA tile plan (see common.cuh)
     int tile_count_off;
     const uint8_t *tile_slot;
+    const uint8_t *rec;           // record stream (CTL_KKT_TMA=3), see common.cuh
+    const int *rec_off;           // per row block, units of 16 bytes
+    int rec_max;
 };
 
 __device__ __forceinline__ double2 ldg2(const double *p)
@@ -568,7 +571,10 @@ __global__ void __launch_bounds__(TR * 8, 512 / (TR * 8) * 2) kkt_apply_tma_kern
 // Stage reuse is ordered by the __syncthreads() that ends an iteration; each stage has its own mbarrier,
 // whose k-th use completes phase k & 1.
 // ---------------------------------------------------------------------------------------
-template <bool CN, bool SYM, bool HALO, int G, int TR>
+// REC (CTL_KKT_TMA=3): the CSR slice of a row block is not staged by the CTA (two dependent global round trips
+// per block, what made the first form slow) but arrives as ONE more bulk copy of the block's record (api.cu) into
+// the stage, counted on the same mbarrier: an iteration is then issue-next / wait / consume / barrier.
+template <bool CN, bool SYM, bool HALO, int G, int TR, bool REC>
 __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArgs a, const int cap, const int umax,
                                                                    const int n_blocks)
 {
@@ -576,15 +582,19 @@ __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArg
     const int ld = a.ld;
     const unsigned row_b = (unsigned)ld * 8u;
     const size_t tile_b = (size_t)umax * row_b;
-    // layout: stage 0 [tile_v | tile_z] | stage 1 [tile_v | tile_z] | mk [cap+1] double2 | kt [cap+1] double (!SYM)
-    //         | off [cap+1] unsigned | ptr [TR+1] int | 2 mbarriers
+    // layout !REC: stage 0 [tile_v | tile_z] | stage 1 [tile_v | tile_z] | mk [cap+1] double2 | kt [cap+1] double
+    //              (!SYM) | off [cap+1] unsigned | ptr [TR+1] int | 2 mbarriers
+    // layout  REC: stage 0 [tile_v | tile_z | record] | stage 1 [...] | 2 mbarriers
+    const size_t stage_b = 2 * tile_b + (REC ? (size_t)a.rec_max : 0);
     unsigned char *tiles = smem_raw;
-    double2 *s_mk = reinterpret_cast<double2 *>(tiles + 4 * tile_b);
+    double2 *s_mk = reinterpret_cast<double2 *>(tiles + 2 * stage_b);
     double *s_kt = reinterpret_cast<double *>(s_mk + (cap + 1));
     unsigned *s_off = reinterpret_cast<unsigned *>(SYM ? s_kt : s_kt + (cap + 1));
     int *s_ptr = reinterpret_cast<int *>(s_off + (cap + 1));
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(s_ptr + (TR + 1)) + 7) & ~(uintptr_t)7);
+    unsigned long long *mbar = REC ? reinterpret_cast<unsigned long long *>(tiles + 2 * stage_b)
+                                   : reinterpret_cast<unsigned long long *>(
+                                         (reinterpret_cast<uintptr_t>(s_ptr + (TR + 1)) + 7) & ~(uintptr_t)7);
+    constexpr unsigned HDR = ((TR + 1) * 4 + 15) & ~15;
 
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -602,14 +612,28 @@ __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArg
     // producer (warp 0): arm the stage's barrier with the byte count, then one bulk copy per run and panel
     auto issue_tile = [&](const int blk, const int st) {
         const unsigned mb = st ? mbar_s1 : mbar_s0;
-        unsigned char *tv = tiles + (size_t)st * 2 * tile_b;
+        unsigned char *tv = tiles + (size_t)st * stage_b;
         unsigned char *tz = tv + tile_b;
         const int ub = __ldg(a.tile_uptr + blk);
         const int n_runs = __ldg(a.tile_uptr + blk + 1) - ub;
         const int U = __ldg(a.tile_ucols + a.tile_count_off + blk);
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(2u * (unsigned)U * row_b)
+        unsigned rec_bytes = 0;
+        size_t rec_src = 0;
+        if (REC) {
+            const int o0 = __ldg(a.rec_off + blk), o1 = __ldg(a.rec_off + blk + 1);
+            rec_src = (size_t)o0 * 16;
+            rec_bytes = (unsigned)(o1 - o0) * 16u;
+        }
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb),
+                         "r"(2u * (unsigned)U * row_b + rec_bytes)
                          : "memory");
+            if (REC)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(tz + tile_b)),
+                             "l"(a.rec + rec_src), "r"(rec_bytes), "r"(mb)
+                             : "memory");
+        }
         __syncwarp();
         for (int u = lane; u < n_runs; u += 32) {
             const int c = __ldg(a.tile_ucols + 3 * (ub + u));
@@ -652,21 +676,24 @@ __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArg
         if (wid == 0 && nb < n_blocks) issue_tile(nb, st ^ 1);
         const int r0 = blk * TR;
         const int nrows = min(TR, a.n_rows - r0);
-        for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
-        __syncthreads();
-        const int kb = s_ptr[0];
-        const int cnt = s_ptr[nrows] - kb;
-        for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
-            s_off[k] = (unsigned)__ldg(a.tile_slot + kb + k) * row_b;
-            s_mk[k] = make_double2(__ldg(a.Mv + kb + k), __ldg(a.Kv + kb + k));
-            if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+        int kb = 0, sentinel = cap;
+        if (!REC) {
+            for (int i = threadIdx.x; i <= nrows; i += blockDim.x) s_ptr[i] = __ldg(a.indptr + r0 + i);
+            __syncthreads();
+            kb = s_ptr[0];
+            const int cnt = s_ptr[nrows] - kb;
+            for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+                s_off[k] = (unsigned)__ldg(a.tile_slot + kb + k) * row_b;
+                s_mk[k] = make_double2(__ldg(a.Mv + kb + k), __ldg(a.Kv + kb + k));
+                if (!SYM) s_kt[k] = __ldg(a.KTv + kb + k);
+            }
+            if (threadIdx.x == 0) {
+                s_off[cap] = 0u;
+                s_mk[cap] = make_double2(0.0, 0.0);
+                if (!SYM) s_kt[cap] = 0.0;
+            }
+            __syncthreads();
         }
-        if (threadIdx.x == 0) {
-            s_off[cap] = 0u;
-            s_mk[cap] = make_double2(0.0, 0.0);
-            if (!SYM) s_kt[cap] = 0.0;
-        }
-        __syncthreads();
         {   // wait for this stage's tile
             const unsigned mb = st ? mbar_s1 : mbar_s0;
             unsigned done = 0;
@@ -677,24 +704,39 @@ __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArg
                              : "memory");
             }
         }
-        const unsigned char *tile_v = tiles + (size_t)st * 2 * tile_b;
+        const unsigned char *tile_v = tiles + (size_t)st * stage_b;
         const unsigned char *tile_z = tile_v + tile_b;
+        // where this block's CSR slice lives: the CTA-staged arrays, or the record that came with the tile
+        const int *b_ptr = s_ptr;
+        const double2 *b_mk = s_mk;
+        const double *b_kt = s_kt;
+        const unsigned *b_off = s_off;
+        if (REC) {
+            const unsigned char *rec = tile_z + tile_b;
+            b_ptr = reinterpret_cast<const int *>(rec);
+            const int cnt = b_ptr[TR];
+            sentinel = cnt;                                   // entry cnt of a record is the zero sentinel
+            b_mk = reinterpret_cast<const double2 *>(rec + HDR);
+            b_kt = reinterpret_cast<const double *>(rec + HDR + (size_t)(cnt + 1) * 16);
+            b_off = reinterpret_cast<const unsigned *>(
+                rec + HDR + (size_t)(cnt + 1) * 16 + (SYM ? 0 : (((size_t)(cnt + 1) * 8 + 15) & ~(size_t)15)));
+        }
         for (int base = wid * RPW; base < nrows; base += nwarps * RPW) {
             const int lr_raw = base + sub;
             const bool live = lr_raw < nrows;
             const int lr = live ? lr_raw : nrows - 1;
             const int r = r0 + lr;
-            const int kbeg = s_ptr[lr] - kb, kend = s_ptr[lr + 1] - kb;
+            const int kbeg = b_ptr[lr] - kb, kend = b_ptr[lr + 1] - kb;
             double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
             for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
 #pragma unroll
                 for (int j = 0; j < SCHUNK; ++j) {
-                    const int kk = (k0 + j < kend) ? k0 + j : cap;
-                    const unsigned o = s_off[kk] + lane_b;
+                    const int kk = (k0 + j < kend) ? k0 + j : sentinel;
+                    const unsigned o = b_off[kk] + lane_b;
                     const double2 xv = *reinterpret_cast<const double2 *>(tile_v + o);
                     const double2 xz = *reinterpret_cast<const double2 *>(tile_z + o);
-                    const double2 mk = s_mk[kk];
-                    const double kt = SYM ? mk.y : s_kt[kk];
+                    const double2 mk = b_mk[kk];
+                    const double kt = SYM ? mk.y : b_kt[kk];
                     mv0 = fma(mk.x, xv.x, mv0);
                     mv1 = fma(mk.x, xv.y, mv1);
                     mz0 = fma(mk.x, xz.x, mz0);
@@ -752,12 +794,13 @@ __global__ void __launch_bounds__(TR * 8) kkt_apply_tma_pipe_kernel(const KktArg
     }
 }
 
-template <bool CN, bool SYM, bool HALO, int G, int TR>
+template <bool CN, bool SYM, bool HALO, int G, int TR, bool REC>
 cudaError_t launch_tma_pipe_gt(const KktArgs &a, int cap, int umax, cudaStream_t s)
 {
     const int n_blocks = ceil_div(a.n_rows, TR);
-    const size_t smem = (size_t)4 * umax * a.ld * 8 + (size_t)(cap + 1) * (16 + (SYM ? 0 : 8) + 4) + (TR + 1) * 4 + 32;
-    auto kern = kkt_apply_tma_pipe_kernel<CN, SYM, HALO, G, TR>;
+    const size_t smem = REC ? (size_t)4 * umax * a.ld * 8 + (size_t)2 * a.rec_max + 32
+                            : (size_t)4 * umax * a.ld * 8 + (size_t)(cap + 1) * (16 + (SYM ? 0 : 8) + 4) + (TR + 1) * 4 + 32;
+    auto kern = kkt_apply_tma_pipe_kernel<CN, SYM, HALO, G, TR, REC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     static int n_sm = 0;
@@ -778,8 +821,12 @@ cudaError_t launch_tma_pipe(const KktArgs &a, int G, int cap, int umax, int tile
 {
     // ld = 64 (G = 32) only: the configuration the pipeline is meant for
     if (G != 32) return cudaErrorInvalidValue;
-    if (tile_rows == 16) return launch_tma_pipe_gt<CN, SYM, HALO, 32, 16>(a, cap, umax, s);
-    return launch_tma_pipe_gt<CN, SYM, HALO, 32, 32>(a, cap, umax, s);
+    if (a.rec) {
+        if (tile_rows == 16) return launch_tma_pipe_gt<CN, SYM, HALO, 32, 16, true>(a, cap, umax, s);
+        return launch_tma_pipe_gt<CN, SYM, HALO, 32, 32, true>(a, cap, umax, s);
+    }
+    if (tile_rows == 16) return launch_tma_pipe_gt<CN, SYM, HALO, 32, 16, false>(a, cap, umax, s);
+    return launch_tma_pipe_gt<CN, SYM, HALO, 32, 32, false>(a, cap, umax, s);
 }
 
 template <bool CN, bool SYM, bool HALO, int G, int TR>
@@ -1209,7 +1256,12 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     const int tcap = h->tile_rows * max_len;
     const size_t tma_smem = (size_t)2 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 16;
     const bool use_tma = h->tile_rows > 0 && !h->per_level && !h->force_unstaged && !h->no_tma && tma_smem <= 113 * 1024;
-    const size_t pipe_smem = (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 32;
+    const bool use_rec = h->tma_rec && h->d_rec && h->rec_max > 0;
+    a.rec = use_rec ? h->d_rec : nullptr;
+    a.rec_off = h->d_rec_off;
+    a.rec_max = h->rec_max;
+    const size_t pipe_smem = use_rec ? (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)2 * h->rec_max + 32
+                                     : (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 32;
     if (h->tma_pipe && h->tile_rows > 0 && !h->per_level && !h->force_unstaged && G == 32 && pipe_smem <= 227 * 1024) {
         const bool sym = h->d_KT == h->d_K;
         cudaError_t e;
