@@ -289,14 +289,16 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         threads = std::max(1, std::min(threads, 32));
     }
     levels.clear();
-    HostCSR A = A0;
-    std::vector<double> cand(A.n_rows, 1.0);
+    levels.reserve((size_t)std::max(1, p.max_levels));      // references to a level stay valid while the next is built
+    HostCSR next = A0;                                       // the one copy: the caller keeps its matrix
+    std::vector<double> cand(A0.n_rows, 1.0);
     PhaseTimer timer;
     while (true) {
         levels.emplace_back();
         AmgLevelHost &L = levels.back();
         const int lvl = (int)levels.size() - 1;
-        L.A = A;
+        L.A = std::move(next);
+        const HostCSR &A = L.A;
         timer.lap("copy", lvl);
         L.rho = gershgorin_rho(L.A, L.dinv);
         L.rho = std::min(L.rho, POWER_SAFETY * power_rho(L.A, L.dinv, L.rho, threads));
@@ -371,7 +373,7 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         timer.lap("A*P", lvl);
         csr_matmat(L.R, AP, Ac, threads);
         timer.lap("R*(AP)", lvl);
-        A = std::move(Ac);
+        next = std::move(Ac);
         cand = norms;
     }
     AmgLevelHost &last = levels.back();

@@ -140,3 +140,44 @@ def test_stationary_non_linear_loop_converges_and_residual_is_consistent(gauss_n
                                             out["v"], out["zeta"])
     assert np.sqrt(r0 @ r0 + r1 @ r1) == pytest.approx(h[-1], rel=1e-12)
     assert np.abs(out["v"]).max() > 0.05          # the state is far enough from zero for the non-linearity to act
+
+
+def test_stationary_kkt_solution_minimises_the_reduced_functional():
+    """Formulation check in the spirit of test/test_control.py:554-707 (which compares with an L-BFGS minimisation
+    of the reduced functional through tlm_adjoint): the solution (v, zeta) of the block system, with the control
+    u = zeta / beta (test/test_control.py:625), is the minimiser of
+        J(u) = 1/2 (v(u) - v_hat)^T M (v(u) - v_hat) + beta/2 u^T M u,   K v(u) = f + M u  (interior rows, v = 0 on
+    the boundary) -- its gradient vanishes and J grows in every direction.  Same operator as the reference's test:
+    grad.grad + 2 mass, beta = 1, zero Dirichlet data, zero force."""
+    import scipy.sparse.linalg as spla
+    M, L, coords, bd = fem.assemble_p1_2d(8, 8, 1.0, 1.0)
+    K = (L + 2.0 * M).tocsr()
+    n = M.shape[0]
+    inter = np.setdiff1d(np.arange(n), bd)
+    x, y = coords[:, 0], coords[:, 1]
+    v_hat = np.sin(np.pi * x) * np.sin(np.pi * y) * np.exp(x + y)
+    beta = 1.0
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 500, "relative_tolerance": 1e-14, "absolute_tolerance": 1e-14}
+    r = stationary.linear_solve(M, K, beta=beta, bdofs=bd, v_d=M @ v_hat, f=np.zeros(n), solver_parameters=sp_,
+                                inner="exact")
+    lu = spla.splu(K[inter][:, inter].tocsc())
+    M_II = M[inter][:, inter]
+
+    def state(u_I):
+        v = np.zeros(n)
+        v[inter] = lu.solve(M_II @ u_I)
+        return v
+
+    def J(u_I):
+        d = state(u_I) - v_hat
+        return 0.5 * d @ (M @ d) + 0.5 * beta * u_I @ (M_II @ u_I)
+    u_I = r["zeta"][inter] / beta
+    assert np.abs(state(u_I) - r["v"]).max() < 1e-11 * np.abs(r["v"]).max()      # the state equation row
+    # gradient: M_II K_II^-T (M (v - v_hat))_I + beta M_II u
+    d = state(u_I) - v_hat
+    g = M_II @ lu.solve((M @ d)[inter], trans="T") + beta * (M_II @ u_I)
+    assert np.abs(g).max() < 1e-11 * np.abs(beta * (M_II @ u_I)).max()
+    rng = np.random.default_rng(0)
+    J0 = J(u_I)
+    for _ in range(5):
+        assert J(u_I + 1e-3 * rng.standard_normal(u_I.size)) > J0
