@@ -294,3 +294,25 @@ def reference_navier_stokes_problem(CN, nx=8, n_t=10):
     return dict(sq=sq, M=M, B=sq["B"], D_v=D_v, D_p=D_p, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=CN,
                 time_interval=(0.0, T_f), v_hat=v_hat, v_d=(M @ v_hat.T).T, f=np.zeros((n_t, n_v)), bc_values=g,
                 lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0))
+
+
+def mms_heat_problem_linear_in_time(N, n_t=10):
+    """The manufactured solution of ``test_MMS_instationary_heat_control_BE_convergence_FE``
+    (test/test_control.py:1658-1826, degree 1): v = 1 + (t_f - t) cos cos, zeta = (t_f - t) cos cos on (0, 2)^2,
+    beta = 1, t_f = 2, n_t = 10, backward Euler -- LINEAR in time, so the time discretisation is exact and the
+    error is the spatial one.  Desired state ``zeta_space - lapl(zeta) + v`` (1695-1708), force
+    ``-v_space - lapl(v) - zeta / beta`` (1726-1739), Dirichlet data v = 1, initial condition v(0)."""
+    M, K, coords, bd = fem.assemble_p1_2d(N, N, 2.0, 2.0)
+    x, y = coords[:, 0] - 1.0, coords[:, 1] - 1.0
+    beta, t_f = 1.0, 2.0
+    tau = t_f / (n_t - 1.0)
+    times = tau * np.arange(n_t)
+    cc = np.cos(0.5 * np.pi * x) * np.cos(0.5 * np.pi * y)
+    lam = 0.5 * np.pi * np.pi                                     # -lapl(cos cos) = lam cos cos
+    v_exact = np.stack([1.0 + (t_f - t) * cc for t in times])
+    zeta_exact = np.stack([(t_f - t) * cc for t in times])
+    v_hat = np.stack([cc + lam * (t_f - t) * cc + 1.0 + (t_f - t) * cc for t in times])
+    f_nodal = np.stack([-cc + lam * (t_f - t) * cc - (t_f - t) * cc / beta for t in times])
+    return dict(M=M, K=K, coords=coords, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=False, time_interval=(0.0, t_f),
+                v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T, v_0=v_exact[0],
+                bc_values=np.ones((n_t, bd.size)), v_exact=v_exact, zeta_exact=zeta_exact)

@@ -733,3 +733,50 @@ def test_reference_navier_stokes_picard_loop(CN):
     conv = (q["D_v"](v[-1], t_mid) - q["D_v"](0.0 * v[-1], t_mid)) @ v[-1]
     visc = q["D_v"](0.0 * v[-1], t_mid) @ v[-1]
     assert np.linalg.norm(conv) > 0.1 * np.linalg.norm(visc)
+
+
+def test_reference_mms_heat_convergence_in_time():
+    """test/test_control.py:1829-1980 (BE) and 2140-2294 (CN), degree 1: the manufactured heat-control solution on a
+    fixed mesh with n_t doubled.  The reference prints the observed orders (250 x 250 cells); here, on 64 x 64 cells:
+    backward Euler is first order in both fields, the trapezoidal rule at least second order in the adjoint until
+    the spatial error takes over, and an order of magnitude more accurate than backward Euler at equal n_t."""
+    N = 64
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 200, "relative_tolerance": 1e-10,
+           "absolute_tolerance": 1e-10}
+    errs = {}
+    for CN, levels in ((False, (4, 8, 16)), (True, (4, 8))):
+        for n_t in levels:
+            q = kat.mms_heat_problem(N, n_t, CN)
+            r = control.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=n_t, CN=CN, time_interval=q["time_interval"],
+                                     bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"], bc_values=q["bc_values"],
+                                     solver_parameters=sp_, inner="exact")
+            assert r["ksp"].reason > 0
+            errs[(CN, n_t)] = (np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["v"], q["v_exact"]),
+                               np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["zeta"], q["zeta_exact"]))
+    be = np.array([errs[(False, n)] for n in (4, 8, 16)])
+    o_be = np.log(be[:-1] / be[1:]) / np.log(2.0)
+    assert (o_be > 0.95).all() and (o_be < 1.2).all(), o_be                   # measured 1.06 / 1.10, 1.01 / 1.02
+    cn = np.array([errs[(True, n)] for n in (4, 8)])
+    assert np.log(cn[0, 1] / cn[1, 1]) / np.log(2.0) > 2.0                     # adjoint: measured 2.96
+    assert (cn[1] < 0.1 * be[1]).all()
+
+
+def test_reference_mms_heat_be_convergence_study():
+    """test/test_control.py:1658-1826 (backward Euler, degree 1) re-created: a manufactured solution that is linear
+    in time (exact for backward Euler), inhomogeneous Dirichlet data, n_t = 10; the reference prints the observed
+    orders, here second order in space is asserted -- it exercises the BE right-hand sides and lifting
+    (control/control.py:2990-3130) end to end."""
+    errs = []
+    for N in (4, 8, 16):
+        q = kat.mms_heat_problem_linear_in_time(N)
+        sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 200, "relative_tolerance": 1e-10,
+               "absolute_tolerance": 1e-10}
+        r = control.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=False, time_interval=q["time_interval"],
+                                 bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"], bc_values=q["bc_values"],
+                                 solver_parameters=sp_, inner="exact")
+        assert r["ksp"].reason > 0
+        errs.append((np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["v"], q["v_exact"]),
+                     np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["zeta"], q["zeta_exact"])))
+    e = np.array(errs)
+    orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
+    assert (orders[0] > 1.7).all() and (orders[1] > 1.9).all(), orders          # measured 1.77 / 1.81 and 1.94 / 1.95
