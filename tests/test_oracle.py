@@ -780,3 +780,39 @@ def test_reference_mms_heat_be_convergence_study():
     e = np.array(errs)
     orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
     assert (orders[0] > 1.7).all() and (orders[1] > 1.9).all(), orders          # measured 1.77 / 1.81 and 1.94 / 1.95
+
+
+@pytest.mark.parametrize("CN", [True, False])
+@pytest.mark.parametrize("gauss_newton", [False, True])
+def test_non_linear_residual_is_rhs_minus_operator(CN, gauss_newton):
+    """``non_linear_res_eval`` (control/control.py:2442-2818) row by row equals, after the T_1 / T_2 transforms that
+    ``linear_solve`` applies to ready right-hand sides, the right-hand side of ``linear_solve`` built with D_v at the
+    iterate minus the KKT operator applied to the iterate: T r = b(K(v_old), v_0, v_d, f) - A(K(v_old)) x_old.
+    So the residual of the outer loop needs no kernel of its own on the device (``ctl_build_rhs`` - ``ctl_kkt_apply``):
+    DESIGN.md section 7."""
+    from control_b200.control import build_rhs
+    nx, n_t = 6, 5
+    q = kat.heat_problem(nx, n_t, CN, beta=1e-2)
+    Dv = fem.nonlinear_diffusion_p1_2d(nx, nx, 2.0, 2.0)
+    M, bd, tau, beta = q["M"], q["bdofs"], q["tau"], q["beta"]
+    n = M.shape[0]
+    rng = np.random.default_rng(1)
+    times = tau * np.arange(n_t)
+    v_0 = 0.3 * rng.standard_normal(n)
+    v_old, zeta_old = 0.3 * rng.standard_normal((n_t, n)), 0.3 * rng.standard_normal((n_t, n))
+    for a in (v_0, v_old, zeta_old):
+        a[..., bd] = 0.0
+    if CN:
+        v_old[0] = v_0
+    zeta_old[n_t - 1] = 0.0
+
+    def D(v, t):
+        return Dv(v, gauss_newton)
+    r0, r1 = control.non_linear_res_eval(M, D, times, tau, beta, n_t, CN, bd, v_old, zeta_old, v_0, q["v_d"], q["f"])
+    K_levels = [D(v_old[i], times[i]) for i in range(n_t)]
+    b0, b1 = build_rhs(M, D(v_0, 0.0), tau, n_t, CN, bd, q["v_d"], q["f"], v_0)
+    x0, x1 = (v_old[1:], zeta_old[:-1]) if CN else (v_old, zeta_old)
+    t0, t1 = (kkt.apply_T_1(r0), kkt.apply_T_2(r1)) if CN else (r0, r1)
+    y0, y1 = kkt.kkt_apply_fused(M, K_levels, tau, beta, n_t, CN, bd, x0, x1)
+    assert np.abs(b0 - y0 - t0).max() < 1e-14 * np.abs(t0).max()
+    assert np.abs(b1 - y1 - t1).max() < 1e-14 * np.abs(t1).max()
