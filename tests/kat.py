@@ -316,3 +316,25 @@ def mms_heat_problem_linear_in_time(N, n_t=10):
     return dict(M=M, K=K, coords=coords, bdofs=bd, beta=beta, n_t=n_t, tau=tau, CN=False, time_interval=(0.0, t_f),
                 v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T, v_0=v_exact[0],
                 bc_values=np.ones((n_t, bd.size)), v_exact=v_exact, zeta_exact=zeta_exact)
+
+
+def stokes_mms_fields(N, beta=1e-3):
+    """Fields of test/test_control.py:361-551 on vector Q2 - Q1, (0, 2)^2 (coordinates shifted to (-1, 1)^2)."""
+    sq = fem.assemble_q2q1_stokes_2d(N, N, 2.0, 2.0)
+    M = sq["M_v"]
+    x, y = sq["coords_v"][:, 0] - 1.0, sq["coords_v"][:, 1] - 1.0
+    px, py = sq["coords_p"][:, 0] - 1.0, sq["coords_p"][:, 1] - 1.0
+
+    def vec(cx, cy):
+        a = np.zeros(M.shape[0])
+        a[0::2], a[1::2] = cx, cy
+        return a
+    v = vec(x * y ** 3, 0.25 * (x ** 4 - y ** 4))                                  # div v = 0, -lapl v + grad p = 0
+    zeta = vec(2.0 * beta * y * (x ** 2 - 1.0) ** 2 * (y ** 2 - 1.0), -2.0 * beta * x * (x ** 2 - 1.0) * (y ** 2 - 1.0) ** 2)
+    lap_zeta = vec(2.0 * beta * (y * (y ** 2 - 1.0) * (12.0 * x ** 2 - 4.0) + 6.0 * y * (x ** 2 - 1.0) ** 2),
+                   -2.0 * beta * (x * (x ** 2 - 1.0) * (12.0 * y ** 2 - 4.0) + 6.0 * x * (y ** 2 - 1.0) ** 2))
+    grad_mu = vec(4.0 * beta * y, 4.0 * beta * x)
+    v_hat = -lap_zeta + grad_mu + v                                                # 403-405
+    f_nodal = -zeta / beta                                                          # -lapl v + grad p - zeta / beta, 424-425
+    return dict(sq=sq, M=M, v=v, zeta=zeta, lap_zeta=lap_zeta, grad_mu=grad_mu, p=3.0 * px ** 2 * py - py ** 3, mu=4.0 * beta * px * py, v_hat=v_hat,
+                f_nodal=f_nodal, beta=beta)

@@ -816,3 +816,34 @@ def test_non_linear_residual_is_rhs_minus_operator(CN, gauss_newton):
     y0, y1 = kkt.kkt_apply_fused(M, K_levels, tau, beta, n_t, CN, bd, x0, x1)
     assert np.abs(b0 - y0 - t0).max() < 1e-14 * np.abs(t0).max()
     assert np.abs(b1 - y1 - t1).max() < 1e-14 * np.abs(t1).max()
+
+
+def test_reference_mms_instationary_stokes_be_convergence_study():
+    """test/test_control.py:3305-3543 (backward Euler, degree 2; Q2 - Q1 here) re-created: the manufactured
+    stationary Stokes fields times (t_f - t) -- linear in time, exact for backward Euler -- with time-dependent
+    inhomogeneous velocity data, beta = 1e-3, n_t = 10.  The reference prints the observed orders of the velocity
+    and its adjoint; asserted here (at least third order)."""
+    from oracle import stokes
+    t_f, n_t = 2.0, 10
+    tau = t_f / (n_t - 1.0)
+    s = t_f - tau * np.arange(n_t)
+    errs = []
+    for N in (2, 4, 8):
+        m = kat.stokes_mms_fields(N)
+        sq, M, bd, beta = m["sq"], m["M"], m["sq"]["bdofs_v"], m["beta"]
+        v_exact = s[:, None] * m["v"][None]
+        zeta_exact = s[:, None] * m["zeta"][None]
+        v_hat = v_exact + m["zeta"][None] + s[:, None] * (-m["lap_zeta"] + m["grad_mu"])[None]      # 3388-3400
+        f_nodal = -m["v"][None] - zeta_exact / beta                                                   # 3432-3447
+        sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 200, "relative_tolerance": 1e-10,
+               "absolute_tolerance": 1e-10}
+        v, zeta, p, mu, res = stokes.incompressible_linear_solve(
+            M, sq["L_v"], sq["B"], sq["M_p"], sq["L_p"], beta=beta, n_t=n_t, CN=False, time_interval=(0.0, t_f),
+            bdofs_v=bd, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T, v_0=v_exact[0], bc_values=v_exact[:, bd],
+            solver_parameters=sp_, lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0))
+        assert res.reason > 0
+        errs.append((np.sqrt(tau) * kat.l2_error(M, v, v_exact), np.sqrt(tau) * kat.l2_error(M, zeta, zeta_exact)))
+    e = np.array(errs)
+    orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
+    assert (orders[-1] > 2.7).all(), orders          # measured 3.7 / 5.0 and 4.0 / 4.6 (nodal errors in the mass norm)
+    assert e[-1, 0] < 5e-4 and e[-1, 1] < 3e-6       # N = 8: 2.4e-4, 1.2e-6

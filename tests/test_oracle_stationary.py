@@ -183,28 +183,6 @@ def test_stationary_kkt_solution_minimises_the_reduced_functional():
         assert J(u_I + 1e-3 * rng.standard_normal(u_I.size)) > J0
 
 
-def _stokes_mms(N, beta=1e-3):
-    """Fields of test/test_control.py:361-551 on vector Q2 - Q1, (0, 2)^2 (coordinates shifted to (-1, 1)^2)."""
-    sq = fem.assemble_q2q1_stokes_2d(N, N, 2.0, 2.0)
-    M = sq["M_v"]
-    x, y = sq["coords_v"][:, 0] - 1.0, sq["coords_v"][:, 1] - 1.0
-    px, py = sq["coords_p"][:, 0] - 1.0, sq["coords_p"][:, 1] - 1.0
-
-    def vec(cx, cy):
-        a = np.zeros(M.shape[0])
-        a[0::2], a[1::2] = cx, cy
-        return a
-    v = vec(x * y ** 3, 0.25 * (x ** 4 - y ** 4))                                  # div v = 0, -lapl v + grad p = 0
-    zeta = vec(2.0 * beta * y * (x ** 2 - 1.0) ** 2 * (y ** 2 - 1.0), -2.0 * beta * x * (x ** 2 - 1.0) * (y ** 2 - 1.0) ** 2)
-    lap_zeta = vec(2.0 * beta * (y * (y ** 2 - 1.0) * (12.0 * x ** 2 - 4.0) + 6.0 * y * (x ** 2 - 1.0) ** 2),
-                   -2.0 * beta * (x * (x ** 2 - 1.0) * (12.0 * y ** 2 - 4.0) + 6.0 * x * (y ** 2 - 1.0) ** 2))
-    grad_mu = vec(4.0 * beta * y, 4.0 * beta * x)
-    v_hat = -lap_zeta + grad_mu + v                                                # 403-405
-    f_nodal = -zeta / beta                                                          # -lapl v + grad p - zeta / beta, 424-425
-    return dict(sq=sq, M=M, v=v, zeta=zeta, p=3.0 * px ** 2 * py - py ** 3, mu=4.0 * beta * px * py, v_hat=v_hat,
-                f_nodal=f_nodal, beta=beta)
-
-
 def test_reference_mms_stationary_stokes_control_convergence():
     """test/test_control.py:361-551 (degree 2; Q2 - Q1 here): manufactured stationary Stokes control problem with
     inhomogeneous Dirichlet velocity data, beta = 1e-3, the test's solver parameters and Chebyshev bounds.  The
@@ -213,7 +191,7 @@ def test_reference_mms_stationary_stokes_control_convergence():
     (control/control.py:326-349, 866-873)."""
     errs = []
     for N in (2, 4, 8):
-        m = _stokes_mms(N)
+        m = kat.stokes_mms_fields(N)
         sq, M, bd = m["sq"], m["M"], m["sq"]["bdofs_v"]
         sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 200, "relative_tolerance": 1e-10,
                "absolute_tolerance": 1e-10}
