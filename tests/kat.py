@@ -338,3 +338,33 @@ def stokes_mms_fields(N, beta=1e-3):
     f_nodal = -zeta / beta                                                          # -lapl v + grad p - zeta / beta, 424-425
     return dict(sq=sq, M=M, v=v, zeta=zeta, lap_zeta=lap_zeta, grad_mu=grad_mu, p=3.0 * px ** 2 * py - py ** 3, mu=4.0 * beta * px * py, v_hat=v_hat,
                 f_nodal=f_nodal, beta=beta)
+
+
+def mms_convection_diffusion_problem_be(N, n_t=10):
+    """``test_MMS_instationary_convection_diffusion_control_BE_convergence_FE`` (test/test_control.py:2297-2492,
+    degree 1): the linear-in-time fields of ``mms_heat_problem_linear_in_time`` with the time-dependent wind of the
+    convection-diffusion studies in the forward operator (one non-symmetric ``K_i`` per level); the desired state
+    loses, the force gains the convection of zeta / v (2342-2358, 2376-2395)."""
+    q = dict(mms_heat_problem_linear_in_time(N, n_t))
+    M, L, coords = q["M"], q["K"], q["coords"]
+    x, y = coords[:, 0] - 1.0, coords[:, 1] - 1.0
+    tau, t_f = q["tau"], 2.0
+    times = tau * np.arange(n_t)
+    sx, cx = np.sin(0.5 * np.pi * x), np.cos(0.5 * np.pi * x)
+    sy, cy = np.sin(0.5 * np.pi * y), np.cos(0.5 * np.pi * y)
+    gx, gy = -0.5 * np.pi * sx * cy, -0.5 * np.pi * cx * sy          # gradient of cos cos
+    K_levels, v_hat, f_nodal = [], q["v_hat"].copy(), np.zeros_like(q["v_hat"])
+    lam = 0.5 * np.pi * np.pi
+    cc = cx * cy
+    for i, t in enumerate(times):
+        a = np.cos(0.5 * np.pi * t)
+        C = fem.assemble_convection_p1_2d(
+            N, N, 2.0, 2.0, lambda X, Y, a=a: (a * 2.0 * (Y - 1.0) * (1.0 - (X - 1.0) ** 2),
+                                               -a * 2.0 * (X - 1.0) * (1.0 - (Y - 1.0) ** 2)))
+        assert np.array_equal(C.indices, M.indices)
+        K_levels.append(sp.csr_matrix((L.data + C.data, M.indices, M.indptr), shape=M.shape))
+        conv_cc = gx * (a * 2.0 * y * (1.0 - x * x)) + gy * (-a * 2.0 * x * (1.0 - y * y))
+        v_hat[i] -= (t_f - t) * conv_cc
+        f_nodal[i] = -cc + lam * (t_f - t) * cc + (t_f - t) * conv_cc - (t_f - t) * cc / q["beta"]
+    q.update(K_levels=K_levels, v_hat=v_hat, v_d=(M @ v_hat.T).T, f=(M @ f_nodal.T).T)
+    return q

@@ -847,3 +847,23 @@ def test_reference_mms_instationary_stokes_be_convergence_study():
     orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
     assert (orders[-1] > 2.7).all(), orders          # measured 3.7 / 5.0 and 4.0 / 4.6 (nodal errors in the mass norm)
     assert e[-1, 0] < 5e-4 and e[-1, 1] < 3e-6       # N = 8: 2.4e-4, 1.2e-6
+
+
+def test_reference_mms_convection_diffusion_be_convergence_study():
+    """test/test_control.py:2297-2492 (backward Euler, degree 1) re-created: linear-in-time manufactured fields,
+    time-dependent wind (one non-symmetric ``K_i`` per level), inhomogeneous Dirichlet data lifted with the per-level
+    matrices (control/control.py:3067-3124); second order in space asserted."""
+    errs = []
+    for N in (4, 8, 16):
+        q = kat.mms_convection_diffusion_problem_be(N)
+        sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 300, "relative_tolerance": 1e-10,
+               "absolute_tolerance": 1e-10}
+        r = control.linear_solve(q["M"], q["K_levels"], beta=q["beta"], n_t=q["n_t"], CN=False,
+                                 time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"],
+                                 bc_values=q["bc_values"], solver_parameters=sp_, inner="exact")
+        assert r["ksp"].reason > 0
+        errs.append((np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["v"], q["v_exact"]),
+                     np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["zeta"], q["zeta_exact"])))
+    e = np.array(errs)
+    orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
+    assert (orders[0] > 1.6).all() and (orders[1] > 1.85).all(), orders        # measured 1.77 / 1.81 and 1.94 / 1.95
