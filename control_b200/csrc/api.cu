@@ -269,9 +269,10 @@ static int build_local_pattern(ctl_handle_s *h)
     }
     h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
     if (const char *e = getenv("CTL_KKT_TMA")) {
-        h->no_tma = !(e[0] == '1' || e[0] == '2' || e[0] == '3');
-        h->tma_pipe = (e[0] == '2' || e[0] == '3');
-        h->tma_rec = (e[0] == '3');
+        h->no_tma = !(e[0] >= '1' && e[0] <= '4');
+        h->tma_pipe = (e[0] == '2' || e[0] == '3' || e[0] == '4');
+        h->tma_rec = (e[0] == '3' || e[0] == '4');
+        h->tma_ws = (e[0] == '4');
     }
     // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows
     {

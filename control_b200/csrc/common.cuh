@@ -89,7 +89,8 @@ struct ctl_handle_s {
     bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
     bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
     bool tma_pipe = false;         // CTL_KKT_TMA=2|3: persistent two-stage variant (next tile copied while this one is consumed)
-    bool tma_rec = false;          // CTL_KKT_TMA=3: ... and the CSR slice of a row block arrives as ONE bulk copy too
+    bool tma_rec = false;          // CTL_KKT_TMA=3|4: ... and the CSR slice of a row block arrives as ONE bulk copy too
+    bool tma_ws = false;           // CTL_KKT_TMA=4: warp-specialised producer / consumers, no block barrier in the loop
     // record stream of CTL_KKT_TMA=3 (built at ctl_assemble): per row block a 16-byte aligned record
     // [int ptr[TR+1] | double2 (m,k)[cnt+1] | double kt[cnt+1] (non-symmetric K) | unsigned off[cnt+1]], entry cnt = zero sentinel
     std::vector<uint8_t> h_tile_slot;      // host copy of d_tile_slot

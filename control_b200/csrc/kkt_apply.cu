@@ -1177,6 +1177,168 @@ void launch_group_r(const KktArgs &a, const ctl_handle_s *h, cudaStream_t s)
     else kkt_apply_group_kernel<CN, R, 4><<<blocks, 256, smem, s>>>(a, h->d_gptr, h->d_gcols, gv, gpc, cap);
 }
 
+// ---------------------------------------------------------------------------------------
+// Warp-specialised form of the record-fed TMA pipeline (opt-in, CTL_KKT_TMA=4; ld = 64; compiled at the end of
+// round 1, NOT yet run).  Warp 0 only produces: for every row block of this CTA it waits until the stage is
+// free (`empty` mbarrier, one arrival per consumer warp), then issues the bulk copies of the X tile and of the
+// block's CSR record (`full` mbarrier, transaction count).  TR / 4 consumer warps wait on `full`, consume the
+// stage from shared memory and release it.  No __syncthreads() inside the loop: the producer's dependent
+// global loads (run table, record offsets) and the copies of block i+1 overlap the consumption of block i.
+// ---------------------------------------------------------------------------------------
+template <bool CN, bool SYM, bool HALO, int TR>
+__global__ void __launch_bounds__(TR * 8 + 32) kkt_apply_tma_ws_kernel(const KktArgs a, const int umax, const int n_blocks)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ld = a.ld;
+    const unsigned row_b = (unsigned)ld * 8u;
+    const size_t tile_b = (size_t)umax * row_b;
+    const size_t stage_b = 2 * tile_b + (size_t)a.rec_max;         // [tile_v | tile_z | record]
+    unsigned char *tiles = smem_raw;
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tiles + 2 * stage_b);   // full[2], empty[2]
+    constexpr unsigned HDR = ((TR + 1) * 4 + 15) & ~15;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int n_cons = (blockDim.x >> 5) - 1;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 0)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + 2)), "r"(n_cons));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar + 3)), "r"(n_cons));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto wait_parity = [](const unsigned mb, const unsigned parity) {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done)
+                         : "r"(mb), "r"(parity)
+                         : "memory");
+        }
+    };
+
+    if (wid == 0) {
+        // ------------------------------------------------------------------ producer
+        int it = 0;
+        for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const int st = it & 1;
+            const unsigned full_mb = smem_u32(mbar + st), empty_mb = smem_u32(mbar + 2 + st);
+            if (it >= 2) wait_parity(empty_mb, (unsigned)((it >> 1) + 1) & 1u);     // use (it/2 - 1) of the stage released
+            unsigned char *tv = tiles + (size_t)st * stage_b;
+            unsigned char *tz = tv + tile_b;
+            const int ub = __ldg(a.tile_uptr + blk);
+            const int n_runs = __ldg(a.tile_uptr + blk + 1) - ub;
+            const int U = __ldg(a.tile_ucols + a.tile_count_off + blk);
+            const int o0 = __ldg(a.rec_off + blk), o1 = __ldg(a.rec_off + blk + 1);
+            const unsigned rec_bytes = (unsigned)(o1 - o0) * 16u;
+            if (lane == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_mb),
+                             "r"(2u * (unsigned)U * row_b + rec_bytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(tz + tile_b)),
+                             "l"(a.rec + (size_t)o0 * 16), "r"(rec_bytes), "r"(full_mb)
+                             : "memory");
+            }
+            __syncwarp();
+            for (int u = lane; u < n_runs; u += 32) {
+                const int c = __ldg(a.tile_ucols + 3 * (ub + u));
+                const unsigned bytes = (unsigned)__ldg(a.tile_ucols + 3 * (ub + u) + 1) * row_b;
+                const size_t dst = (size_t)__ldg(a.tile_ucols + 3 * (ub + u) + 2) * row_b;
+                const double *sv, *sz;
+                if (HALO && c >= a.n_own_cols) {
+                    sv = a.hv + (size_t)(c - a.n_own_cols) * ld;
+                    sz = a.hz + (size_t)(c - a.n_own_cols) * ld;
+                } else {
+                    sv = a.xv + (size_t)c * ld;
+                    sz = a.xz + (size_t)c * ld;
+                }
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(tv + dst)),
+                             "l"(sv), "r"(bytes), "r"(full_mb)
+                             : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_u32(tz + dst)),
+                             "l"(sz), "r"(bytes), "r"(full_mb)
+                             : "memory");
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const unsigned lane_b = (unsigned)lane * 16u;
+    const int cw = wid - 1;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        const int st = it & 1;
+        wait_parity(smem_u32(mbar + st), (unsigned)(it >> 1) & 1u);
+        const int r0 = blk * TR;
+        const int nrows = min(TR, a.n_rows - r0);
+        const unsigned char *tile_v = tiles + (size_t)st * stage_b;
+        const unsigned char *tile_z = tile_v + tile_b;
+        const unsigned char *rec = tile_z + tile_b;
+        const int *b_ptr = reinterpret_cast<const int *>(rec);
+        const int cnt = b_ptr[TR];                                    // entry cnt of a record is the zero sentinel
+        const double2 *b_mk = reinterpret_cast<const double2 *>(rec + HDR);
+        const double *b_kt = reinterpret_cast<const double *>(rec + HDR + (size_t)(cnt + 1) * 16);
+        const unsigned *b_off = reinterpret_cast<const unsigned *>(
+            rec + HDR + (size_t)(cnt + 1) * 16 + (SYM ? 0 : (((size_t)(cnt + 1) * 8 + 15) & ~(size_t)15)));
+        for (int lr = cw; lr < nrows; lr += n_cons) {
+            const int kbeg = b_ptr[lr], kend = b_ptr[lr + 1];
+            double mv0 = 0, mv1 = 0, kv0 = 0, kv1 = 0, mz0 = 0, mz1 = 0, kz0 = 0, kz1 = 0;
+            for (int k0 = kbeg; k0 < kend; k0 += SCHUNK) {
+#pragma unroll
+                for (int j = 0; j < SCHUNK; ++j) {
+                    const int kk = (k0 + j < kend) ? k0 + j : cnt;
+                    const unsigned o = b_off[kk] + lane_b;
+                    const double2 xv = *reinterpret_cast<const double2 *>(tile_v + o);
+                    const double2 xz = *reinterpret_cast<const double2 *>(tile_z + o);
+                    const double2 mk = b_mk[kk];
+                    const double kt = SYM ? mk.y : b_kt[kk];
+                    mv0 = fma(mk.x, xv.x, mv0);
+                    mv1 = fma(mk.x, xv.y, mv1);
+                    mz0 = fma(mk.x, xz.x, mz0);
+                    mz1 = fma(mk.x, xz.y, mz1);
+                    kv0 = fma(mk.y, xv.x, kv0);
+                    kv1 = fma(mk.y, xv.y, kv1);
+                    kz0 = fma(kt, xz.x, kz0);
+                    kz1 = fma(kt, xz.y, kz1);
+                }
+            }
+            kkt_row_epilogue<CN>(a, r0 + lr, lane, mv0, mv1, kv0, kv1, mz0, mz1, kz0, kz1);
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar + 2 + st)) : "memory");
+    }
+}
+
+template <bool CN, bool SYM, bool HALO, int TR>
+cudaError_t launch_tma_ws_t(const KktArgs &a, int umax, cudaStream_t s)
+{
+    const int n_blocks = ceil_div(a.n_rows, TR);
+    const size_t smem = (size_t)4 * umax * a.ld * 8 + (size_t)2 * a.rec_max + 64;
+    auto kern = kkt_apply_tma_ws_kernel<CN, SYM, HALO, TR>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (n_sm <= 0) n_sm = 148;
+    const int per_sm = std::max(1, (int)((227 * 1024) / (smem + 1024)));
+    kern<<<std::min(n_blocks, n_sm * per_sm), TR * 8 + 32, smem, s>>>(a, umax, n_blocks);
+    return cudaSuccess;
+}
+
+template <bool CN, bool SYM, bool HALO>
+cudaError_t launch_tma_ws(const KktArgs &a, int umax, int tile_rows, cudaStream_t s)
+{
+    if (tile_rows == 16) return launch_tma_ws_t<CN, SYM, HALO, 16>(a, umax, s);
+    return launch_tma_ws_t<CN, SYM, HALO, 32>(a, umax, s);
+}
+
 template <bool CN, bool PER_LEVEL>
 void launch_g(const KktArgs &a, int G, cudaStream_t s)
 {
@@ -1262,7 +1424,19 @@ int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf)
     a.rec_max = h->rec_max;
     const size_t pipe_smem = use_rec ? (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)2 * h->rec_max + 32
                                      : (size_t)4 * h->tile_umax * h->ld * 8 + (size_t)(tcap + 1) * 28 + 33 * 4 + 32;
-    if (h->tma_pipe && h->tile_rows > 0 && !h->per_level && !h->force_unstaged && G == 32 && pipe_smem <= 227 * 1024) {
+    if (h->tma_ws && use_rec && h->tile_rows > 0 && !h->per_level && !h->force_unstaged && G == 32 &&
+        pipe_smem + 32 <= 227 * 1024) {
+        const bool sym = h->d_KT == h->d_K;
+        cudaError_t e;
+        if (h->cfg.CN) {
+            if (sym) e = halo ? launch_tma_ws<true, true, true>(a, h->tile_umax, h->tile_rows, h->stream) : launch_tma_ws<true, true, false>(a, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma_ws<true, false, true>(a, h->tile_umax, h->tile_rows, h->stream) : launch_tma_ws<true, false, false>(a, h->tile_umax, h->tile_rows, h->stream);
+        } else {
+            if (sym) e = halo ? launch_tma_ws<false, true, true>(a, h->tile_umax, h->tile_rows, h->stream) : launch_tma_ws<false, true, false>(a, h->tile_umax, h->tile_rows, h->stream);
+            else e = halo ? launch_tma_ws<false, false, true>(a, h->tile_umax, h->tile_rows, h->stream) : launch_tma_ws<false, false, false>(a, h->tile_umax, h->tile_rows, h->stream);
+        }
+        CTL_CUDA(e);
+    } else if (h->tma_pipe && h->tile_rows > 0 && !h->per_level && !h->force_unstaged && G == 32 && pipe_smem <= 227 * 1024) {
         const bool sym = h->d_KT == h->d_K;
         cudaError_t e;
         if (h->cfg.CN) {

@@ -239,13 +239,13 @@ def test_stokes_control_with_multigrid_mass_solver():
 
 @pytest.mark.skipif(__import__("os").environ.get("CTL_RUN_UNVERIFIED") != "1",
                     reason="persistent two-stage TMA kernels (experiments): mode 2 ran bit-identical to the default kernel on "
-                           "a B200 at 512^2 CN (profiles/r01_kkt_apply_tma_pipe.txt); mode 3 and these further shapes have "
+                           "a B200 at 512^2 CN (profiles/r01_kkt_apply_tma_pipe.txt); modes 3, 4 and these further shapes have "
                            "not run on hardware yet (set CTL_RUN_UNVERIFIED=1 to run them)")
 @pytest.mark.parametrize("tile_rows", ["32", "16"])
-@pytest.mark.parametrize("mode", ["2", "3"])
+@pytest.mark.parametrize("mode", ["2", "3", "4"])
 def test_pipelined_tma_apply_matches_literal_operator(mode, tile_rows, monkeypatch):
     """The opt-in persistent two-stage TMA kernels (CTL_KKT_TMA=2; =3: the CSR slice of a row block arrives as one
-    more bulk copy): more row blocks than CTAs (several pipeline iterations per CTA, both barrier phases), CN and
+    more bulk copy; =4: warp-specialised producer / consumers): more row blocks than CTAs (several pipeline iterations per CTA, both barrier phases), CN and
     BE, non-symmetric K, a 3-D stencil."""
     from test_gpu_apply import _check_apply
     from synthetic import fem
