@@ -214,3 +214,52 @@ def test_reference_mms_stationary_stokes_control_convergence():
     # rates): v 3.6 / 4.0, zeta 5.1 / 4.7, p 4.1 / 3.8, mu 4.2 / 4.1; errors at N = 8: 1.5e-4, 6.9e-7, 1.8e-3, 5.9e-5
     assert (orders[-1, :2] > 2.7).all() and (orders[-1, 2:] > 1.7).all(), orders
     assert e[-1, 0] < 3e-4 and e[-1, 2] < 4e-3
+
+
+def test_reference_mms_stationary_navier_stokes_control():
+    """test/test_control.py:1095-1240 (degree 2; Q2 - Q1 here): manufactured stationary Navier-Stokes control
+    problem -- nu = 1/100, v = (x y^3, (x^4 - y^4) / 4) on (-1, 1)^2 as desired state, exact state and Dirichlet
+    data, zeta = 0, force -nu/2 div(grad v + grad v^T) + (grad v) v, beta = 1e-3 -- through the Picard loop
+    ``Stationary.incompressible_non_linear_solve`` with the test's tolerances (1e-9, at most 10 iterations).  The
+    reference prints the observed orders; asserted here: the loop converges, the velocity error decreases at
+    least with third order and the adjoint stays at the level of the velocity error times beta."""
+    import scipy.sparse as sp
+    nu, beta = 1.0 / 100.0, 1e-3
+    errs = []
+    for N in (2, 4, 8):
+        sq = fem.assemble_q2q1_stokes_2d(N, N, 2.0, 2.0)
+        M, bd = sq["M_v"], sq["bdofs_v"]
+        x, y = sq["coords_v"][:, 0] - 1.0, sq["coords_v"][:, 1] - 1.0
+        v1, v2 = x * y ** 3, 0.25 * (x ** 4 - y ** 4)
+        v = np.zeros(M.shape[0])
+        v[0::2], v[1::2] = v1, v2
+        f_nodal = np.zeros_like(v)
+        f_nodal[0::2] = -0.5 * nu * (6.0 * x * y) + (y ** 3 * v1 + 3.0 * x * y ** 2 * v2)
+        f_nodal[1::2] = -0.5 * nu * (3.0 * x ** 2 - 3.0 * y ** 2) + (x ** 3 * v1 - y ** 3 * v2)
+        conv_v, conv_p = fem.convection_q2_2d(N, N, 2.0, 2.0), fem.convection_q1_q2wind_2d(N, N, 2.0, 2.0)
+        I2 = sp.identity(2, format="csr")
+        L_v, L_p = sq["L_v"], sq["L_p"]
+
+        def D_v(w):
+            C = sp.kron(conv_v(w[0::2], w[1::2]), I2, format="csr")
+            C.sort_indices()
+            return sp.csr_matrix((nu * L_v.data + C.data, M.indices, M.indptr), shape=M.shape)
+
+        def D_p(w):
+            C = conv_p(w[0::2], w[1::2])
+            return sp.csr_matrix((nu * L_p.data + C.data, L_p.indices, L_p.indptr), shape=L_p.shape)
+        sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 500, "relative_tolerance": 1e-10,
+               "absolute_tolerance": 1e-10}
+        out = stationary.incompressible_non_linear_solve(
+            M, D_v, sq["B"], sq["M_p"], L_p, D_p, beta=beta, bdofs_v=bd, v_d=M @ v, f=M @ f_nodal, bc_values=v[bd],
+            solver_parameters=sp_, lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0), max_non_linear_iter=10,
+            relative_non_linear_tol=1e-9, absolute_non_linear_tol=1e-9)
+        h = out["history"]
+        assert h[-1] < 1e-5 * h[0], h
+        errs.append((kat.l2_error(M, out["v"][None], v[None]), kat.l2_error(M, out["zeta"][None], 0.0 * v[None]),
+                     out["iterations"]))
+    e = np.array(errs)
+    orders = np.log(e[:-1, 0] / e[1:, 0]) / np.log(2.0)
+    assert (orders > 3.0).all(), orders                 # measured 4.09, 4.00 (nodal norm); errors 2.4e-2, 1.4e-3, 8.7e-5
+    assert (e[:, 1] < 2e-5).all() and e[2, 1] < e[0, 1]     # the adjoint tends to zero (1.3e-5, 8.4e-6, 2.7e-6)
+    assert (e[:, 2] <= 6).all()                          # 4, 5, 6 Picard iterations to 1e-9
