@@ -867,3 +867,53 @@ def test_reference_mms_convection_diffusion_be_convergence_study():
     e = np.array(errs)
     orders = np.log(e[:-1] / e[1:]) / np.log(2.0)
     assert (orders[0] > 1.6).all() and (orders[1] > 1.85).all(), orders        # measured 1.77 / 1.81 and 1.94 / 1.95
+
+
+def test_reference_mms_instationary_navier_stokes_be():
+    """test/test_control.py:4371-4553 (backward Euler, degree 2; Q2 - Q1 here, n_t = 10 instead of 30: the fields are
+    linear in time, so backward Euler is exact in time): manufactured instationary Navier-Stokes control problem,
+    nu = 1/50, v = (t_f - t) (x y^3, (x^4 - y^4) / 4), zeta = 0, time-dependent Dirichlet data, through the Picard loop
+    ``incompressible_non_linear_solve`` with the test's tolerances.  Asserted: the loop converges within the test's 10
+    iterations, the velocity error falls with at least third order, the adjoint stays small."""
+    import scipy.sparse as sp
+    from oracle import stokes
+    nu, beta, t_f, n_t = 1.0 / 50.0, 1e-3, 2.0, 10
+    tau = t_f / (n_t - 1.0)
+    s = t_f - tau * np.arange(n_t)
+    errs = []
+    for N in (2, 4):
+        sq = fem.assemble_q2q1_stokes_2d(N, N, 2.0, 2.0)
+        M, bd = sq["M_v"], sq["bdofs_v"]
+        x, y = sq["coords_v"][:, 0] - 1.0, sq["coords_v"][:, 1] - 1.0
+        v1, v2 = x * y ** 3, 0.25 * (x ** 4 - y ** 4)
+        vs, lap, conv = np.zeros(M.shape[0]), np.zeros(M.shape[0]), np.zeros(M.shape[0])
+        vs[0::2], vs[1::2] = v1, v2
+        lap[0::2], lap[1::2] = 6.0 * x * y, 3.0 * x ** 2 - 3.0 * y ** 2
+        conv[0::2], conv[1::2] = y ** 3 * v1 + 3.0 * x * y ** 2 * v2, x ** 3 * v1 - y ** 3 * v2          # (grad v_s) v_s
+        v_exact = s[:, None] * vs[None]
+        f_nodal = -0.5 * nu * s[:, None] * lap[None] + (s ** 2)[:, None] * conv[None] - vs[None]        # 4432-4443
+        conv_v, conv_p = fem.convection_q2_2d(N, N, 2.0, 2.0), fem.convection_q1_q2wind_2d(N, N, 2.0, 2.0)
+        I2 = sp.identity(2, format="csr")
+        L_v, L_p = sq["L_v"], sq["L_p"]
+
+        def D_v(w, t):
+            C = sp.kron(conv_v(w[0::2], w[1::2]), I2, format="csr")
+            C.sort_indices()
+            return sp.csr_matrix((nu * L_v.data + C.data, M.indices, M.indptr), shape=M.shape)
+
+        def D_p(w, t):
+            C = conv_p(w[0::2], w[1::2])
+            return sp.csr_matrix((nu * L_p.data + C.data, L_p.indices, L_p.indptr), shape=L_p.shape)
+        sp_ = {"linear_solver": "fgmres", "fgmres_restart": 10, "maximum_iterations": 200, "relative_tolerance": 1e-7,
+               "absolute_tolerance": 1e-7}
+        out = stokes.incompressible_non_linear_solve(
+            M, D_v, sq["B"], sq["M_p"], L_p, D_p, beta=beta, n_t=n_t, CN=False, time_interval=(0.0, t_f), bdofs_v=bd,
+            v_d=(M @ v_exact.T).T, f=(M @ f_nodal.T).T, v_0=v_exact[0], bc_values=v_exact[:, bd], solver_parameters=sp_,
+            lambda_v_bounds=(0.3924, 2.0598), lambda_p_bounds=(0.5, 2.0), max_non_linear_iter=10,
+            relative_non_linear_tol=1e-6, absolute_non_linear_tol=1e-6)
+        errs.append((np.sqrt(tau) * kat.l2_error(M, out["v"], v_exact), np.sqrt(tau) * kat.l2_error(M, out["zeta"], 0.0 * v_exact),
+                     out["iterations"], out["history"][-1] / out["history"][0]))
+    e = np.array(errs)
+    assert (e[:, 2] < 10).all()                                  # 7, 8 Picard iterations
+    assert np.log(e[0, 0] / e[1, 0]) / np.log(2.0) > 3.0            # measured 4.08 (4.2e-2 -> 2.5e-3, nodal norm)
+    assert e[1, 1] < 1e-4 and e[1, 1] < e[0, 1]                     # adjoint -> 0 (4.7e-4 -> 4.2e-5)
