@@ -917,3 +917,28 @@ def test_reference_mms_instationary_navier_stokes_be():
     assert (e[:, 2] < 10).all()                                  # 7, 8 Picard iterations
     assert np.log(e[0, 0] / e[1, 0]) / np.log(2.0) > 3.0            # measured 4.08 (4.2e-2 -> 2.5e-3, nodal norm)
     assert e[1, 1] < 1e-4 and e[1, 1] < e[0, 1]                     # adjoint -> 0 (4.7e-4 -> 4.2e-5)
+
+
+def test_reference_mms_convection_diffusion_convergence_in_time():
+    """test/test_control.py:2494-2672 (BE) and 2860-3042 (CN), degree 1, on 48 x 48 cells instead of 250 x 250: the
+    exp-in-time manufactured solution with the time-dependent wind (per-level non-symmetric ``K_i``), n_t doubled.
+    Backward Euler: first order; trapezoidal rule: at least second order in the adjoint and far more accurate."""
+    N = 48
+    sp_ = {"linear_solver": "fgmres", "gmres_restart": 100, "maximum_iterations": 300, "relative_tolerance": 1e-10,
+           "absolute_tolerance": 1e-10}
+    errs = {}
+    for CN, levels in ((False, (4, 8, 16)), (True, (4, 8))):
+        for n_t in levels:
+            q = kat.mms_convection_diffusion_problem(N, n_t, CN)
+            r = control.linear_solve(q["M"], q["K_levels"], beta=q["beta"], n_t=n_t, CN=CN, time_interval=q["time_interval"],
+                                     bdofs=q["bdofs"], v_d=q["v_d"], f=q["f"], v_0=q["v_0"], bc_values=q["bc_values"],
+                                     solver_parameters=sp_, inner="exact")
+            assert r["ksp"].reason > 0
+            errs[(CN, n_t)] = (np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["v"], q["v_exact"]),
+                               np.sqrt(q["tau"]) * kat.l2_error(q["M"], r["zeta"], q["zeta_exact"]))
+    be = np.array([errs[(False, n)] for n in (4, 8, 16)])
+    o_be = np.log(be[:-1] / be[1:]) / np.log(2.0)
+    cn = np.array([errs[(True, n)] for n in (4, 8)])
+    assert (o_be > 0.9).all() and (o_be < 1.25).all(), o_be                  # measured 1.05 / 1.09, 0.98 / 1.00
+    assert np.log(cn[0, 1] / cn[1, 1]) / np.log(2.0) > 2.0                     # adjoint: measured 2.83
+    assert (cn[1] < 0.15 * be[1]).all()
