@@ -265,18 +265,17 @@ static void dense_inverse(const HostCSR &A, const std::vector<double> &shift, st
                 std::swap(inv[(size_t)piv * n + j], inv[(size_t)c * n + j]);
             }
         const double d = 1.0 / a[(size_t)c * n + c];
-        for (int j = 0; j < n; ++j) {
-            a[(size_t)c * n + j] *= d;
-            inv[(size_t)c * n + j] *= d;
-        }
+        // columns < c of the pivot row are already eliminated (exact zeros): skipping them changes nothing
+        for (int j = c; j < n; ++j) a[(size_t)c * n + j] *= d;
+        for (int j = 0; j < n; ++j) inv[(size_t)c * n + j] *= d;
         for (int r = 0; r < n; ++r) {
             if (r == c) continue;
             const double f = a[(size_t)r * n + c];
             if (f == 0.0) continue;
-            for (int j = 0; j < n; ++j) {
-                a[(size_t)r * n + j] -= f * a[(size_t)c * n + j];
-                inv[(size_t)r * n + j] -= f * inv[(size_t)c * n + j];
-            }
+            const double *ac = &a[(size_t)c * n], *ic = &inv[(size_t)c * n];
+            double *ar = &a[(size_t)r * n], *ir = &inv[(size_t)r * n];
+            for (int j = c; j < n; ++j) ar[j] -= f * ac[j];
+            for (int j = 0; j < n; ++j) ir[j] -= f * ic[j];
         }
     }
 }
@@ -391,4 +390,5 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         for (int i = 0; i < nc; ++i)
             for (int j = 0; j < nc; ++j) last.Ainv[(size_t)i * nc + j] -= e[i] * e[j];
     }
+    timer.lap("coarse solve", (int)levels.size() - 1);
 }
