@@ -1,0 +1,20 @@
+"""Host-side C++ of the library checked without a GPU: ``tests/native/amg_host_check.cu`` includes
+``csrc/amg_setup.cpp`` directly (its static helpers become visible), is compiled with nvcc as host code and run."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc")
+def test_host_amg_setup_native_checks(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    exe = str(tmp_path / "amg_host_check")
+    subprocess.check_call([nvcc, "-std=c++17", "-O2", "-x", "cu", "-w", "-I", os.path.join(ROOT, "control_b200", "csrc"),
+                           "-o", exe, os.path.join(ROOT, "tests", "native", "amg_host_check.cu")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "coarse inverse residual" in out.stdout
