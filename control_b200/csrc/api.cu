@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "kkt_plan.h"
 
 static thread_local std::string g_create_error;
 
@@ -431,37 +432,12 @@ int ctl_assemble(ctl_handle h)
         // reads from shared memory, so that it arrives with one bulk copy (16-byte aligned offsets and sizes)
         h->rec_max = 0;
         if (h->tma_rec && h->tile_rows > 0 && !h->h_tile_slot.empty() && h->ld == 64) {
-            const int TR = h->tile_rows;
-            const int nblk = (nl + TR - 1) / TR;
-            const size_t row_b = (size_t)h->ld * 8;
-            auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
-            const size_t hdr = up16((size_t)(TR + 1) * 4);
-            std::vector<int> roff(nblk + 1, 0);
+            std::vector<double> mz(nnz);
+            for (int64_t p = 0; p < nnz; ++p) mz[p] = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
             std::vector<uint8_t> rec;
-            rec.reserve((size_t)nnz * (sym ? 20 : 28) + (size_t)nblk * (hdr + 64));
-            for (int b = 0; b < nblk; ++b) {
-                const int r0 = b * TR, r1 = std::min(nl, r0 + TR);
-                const int kb = h->loc.indptr[r0], cnt = h->loc.indptr[r1] - kb;
-                const size_t o_mk = hdr, o_kt = o_mk + (size_t)(cnt + 1) * 16;
-                const size_t o_off = sym ? o_kt : o_kt + up16((size_t)(cnt + 1) * 8);
-                const size_t bytes = o_off + up16((size_t)(cnt + 1) * 4);
-                const size_t base = rec.size();
-                rec.resize(base + bytes, 0);
-                int *ptr = reinterpret_cast<int *>(rec.data() + base);
-                for (int i = 0; i <= TR; ++i) ptr[i] = h->loc.indptr[std::min(r0 + i, r1)] - kb;
-                double *mk = reinterpret_cast<double *>(rec.data() + base + o_mk);
-                double *kt = reinterpret_cast<double *>(rec.data() + base + o_kt);
-                unsigned *off = reinterpret_cast<unsigned *>(rec.data() + base + o_off);
-                for (int k = 0; k < cnt; ++k) {
-                    const int64_t p = kb + k;
-                    mk[2 * k] = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
-                    mk[2 * k + 1] = buf[p];
-                    if (!sym) kt[k] = bt[p];
-                    off[k] = (unsigned)h->h_tile_slot[p] * (unsigned)row_b;
-                }
-                roff[b + 1] = (int)((base + bytes) / 16);
-                h->rec_max = std::max(h->rec_max, (int)bytes);
-            }
+            std::vector<int> roff;
+            h->rec_max = kkt_build_block_records(h->tile_rows, nl, h->loc.indptr.data(), h->h_tile_slot.data(), mz.data(),
+                                                 buf.data(), sym ? nullptr : bt.data(), (size_t)h->ld * 8, rec, roff);
             CTL_TRY(ctl_upload(h, &h->d_rec, rec.data(), rec.size()));
             CTL_TRY(ctl_upload(h, &h->d_rec_off, roff.data(), roff.size()));
         }

@@ -10,11 +10,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc")
-def test_host_amg_setup_native_checks(tmp_path):
+@pytest.mark.parametrize("name,expect", [("amg_host_check", "coarse inverse residual"), ("kkt_record_check", "max diff")])
+def test_host_native_checks(tmp_path, name, expect):
+    """amg_host_check: pivoted dense inverse + one complete hierarchy; kkt_record_check: the block records of the
+    TMA-fed KKT-apply variants read back the way the kernels read them (csrc/kkt_plan.h)."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    exe = str(tmp_path / "amg_host_check")
+    exe = str(tmp_path / name)
     subprocess.check_call([nvcc, "-std=c++17", "-O2", "-x", "cu", "-w", "-I", os.path.join(ROOT, "control_b200", "csrc"),
-                           "-o", exe, os.path.join(ROOT, "tests", "native", "amg_host_check.cu")])
+                           "-o", exe, os.path.join(ROOT, "tests", "native", name + ".cu")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "coarse inverse residual" in out.stdout
+    assert expect in out.stdout
