@@ -1,8 +1,21 @@
 // Aggregation-AMG V-cycle on the device: the inner solver of the
 // Schur-complement time sweeps, standing in for "preonly + hypre boomeramg, max_iter 2"
 // (control/control.py:2056-2067 and the nine other sites).  The hierarchy is set up on
-// the host once per distinct matrix (amg_setup.cpp); a cycle is a fixed sequence of SELL
+// the host once per distinct matrix (amg_setup.cpp); a cycle is a fixed sequence of
 // SpMV-family kernels (sell.cu), so the time sweeps can be captured in a CUDA graph.
+//
+// Launches per V(nu, nu) cycle and level (the sweeps are bound by the number of dependent launches):
+//   pre-smoothing    zero guess: the first TWO Chebyshev steps are one kernel (p1 = s D^-1 b is formed on the fly
+//                    and never stored), so nu = 3 costs 2 launches; non-zero guess: nu launches
+//   residual + restriction   level 0: two kernels; levels >= 1: one kernel, R b - (R A) x
+//   coarse solve     dense inverse (one GEMV) below coarse_max rows
+//   prolongation     one kernel, out of place (x' = x + P x_c) so that every kernel is idempotent: on several
+//                    GPUs the boundary rows of a product are computed twice (halo.cuh)
+//   post-smoothing   nu launches
+// Multi-GPU: every level above `rep_min` rows per rank is distributed by rows; each kernel pushes the boundary
+// rows of its output to the ranks that gather them and waits for its own ghosts (halo.cuh); the first level below
+// the threshold receives its right-hand side through a replicating exchange and everything below it runs
+// redundantly on every rank.
 #include "amg.cuh"
 
 #include <cstdlib>
@@ -10,25 +23,8 @@
 
 #include "cheb_coefficients.h"
 
-// levels >= FUSED_FROM of a V-cycle run as one cooperative kernel (sell.cu: fused coarse tail)
-static bool fusion_enabled()
-{
-    const char *e = getenv("CTL_FUSED");
-    return e && (e[0] == '1' || e[0] == '2');
-}
-
-static int fused_from_level()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("CTL_FUSED_FROM");
-        v = e ? std::max(1, atoi(e)) : 2;
-    }
-    return v;
-}
-#define FUSED_FROM fused_from_level()
-// the fused kernel reads CSR only; without it every matrix takes the format sell_from_csr picks
-#define FORCE_CSR(l) (fusion_enabled() && (l) >= FUSED_FROM)
+int amg_build_distributed(ctl_handle_s *h, const AmgParams &p, const std::shared_ptr<SellPattern> &fine_pattern,
+                          AmgHierarchyDev &H);      // halo.cu
 
 static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
 {
@@ -37,7 +33,41 @@ static int dev_alloc(ctl_handle_s *h, double **p, size_t n)
     return CTL_OK;
 }
 
-static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, double *x, bool zero_guess);
+// work vectors of one level (after the matrices and dinv are in place)
+int amg_level_vectors(ctl_handle_s *h, AmgLevelDev &L, int level)
+{
+    CTL_TRY(dev_alloc(h, &L.r, L.n));
+    CTL_TRY(dev_alloc(h, &L.t0, L.n));
+    CTL_TRY(dev_alloc(h, &L.t1, L.n));
+    CTL_TRY(dev_alloc(h, &L.t2, L.n));
+    if (level > 0) {
+        CTL_TRY(dev_alloc(h, &L.x, L.n));
+        CTL_TRY(dev_alloc(h, &L.b, L.n));
+    }
+    return CTL_OK;
+}
+
+int64_t amg_cycle_bytes(const AmgHierarchyDev &H)
+{
+    // per cycle and level: 2 nu smoother products (2 nu - 1 on the zero-guess side) + residual, restriction,
+    // prolongation; each product streams its matrix once plus the vectors it touches
+    const AmgParams &p = H.params;
+    const int nl = (int)H.dev.size();
+    int64_t bytes = 0;
+    for (int l = 0; l < nl; ++l) {
+        const AmgLevelDev &L = H.dev[l];
+        if (l + 1 < nl) {
+            const int nu_l = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;
+            bytes += (L.A.bytes_per_pass + 40ll * L.n) * (2 * nu_l);
+            bytes += L.P.bytes_per_pass + L.R.bytes_per_pass + 32ll * L.n;
+        } else if (L.Ainv) {
+            bytes += 8ll * L.n * L.n;
+        } else {
+            bytes += (L.A.bytes_per_pass + 40ll * L.n) * p.nu;
+        }
+    }
+    return bytes;
+}
 
 int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
               const std::shared_ptr<SellPattern> &fine_pattern, AmgHierarchyDev &H)
@@ -51,90 +81,39 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
     }
     const int nl = (int)H.host.size();
     H.dev.assign(nl, AmgLevelDev());
-    H.bytes_per_cycle = 0;
-    for (int l = 0; l < nl; ++l) {
-        AmgLevelHost &Lh = H.host[l];
-        AmgLevelDev &Ld = H.dev[l];
-        // level 0 is distributed by rows (this rank's block, ghost columns appended); the
-        // coarse levels are replicated on every rank
-        const bool dist0 = (l == 0);
-        const int rb = dist0 ? h->row_begin : 0;
-        Ld.n = dist0 ? h->n_loc : Lh.A.n_rows;
-        const int ghosts = dist0 ? h->n_halo : 0;
-        Ld.rho = Lh.rho;
-        if (dist0) {
-            CTL_CHECK(fine_pattern != nullptr, CTL_ERR_ARG, "amg_build: level 0 needs the mesh pattern");
-            std::vector<double> lv(h->loc_entry.size());
-            for (size_t q = 0; q < lv.size(); ++q) lv[q] = Lh.A.values[h->loc_entry[q]];
-            CTL_TRY(sell_set_values(h, fine_pattern, lv.data(), Ld.A));
-        } else {
-            CTL_TRY(sell_from_csr(h, Lh.A, Ld.A, FORCE_CSR(l)));
-        }
-        CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data() + rb, (size_t)Ld.n));
-        CTL_TRY(dev_alloc(h, &Ld.r, Ld.n + ghosts));
-        CTL_TRY(dev_alloc(h, &Ld.t0, Ld.n + ghosts));
-        CTL_TRY(dev_alloc(h, &Ld.t1, Ld.n + ghosts));
-        if (l > 0) {
-            CTL_TRY(dev_alloc(h, &Ld.x, Ld.n));
-            CTL_TRY(dev_alloc(h, &Ld.b, Ld.n));
-        }
-        const int64_t spmv = 12 * Lh.A.nnz() + 4ll * (Ld.n + 1) + 16ll * Ld.n;
-        if (l + 1 < nl) {
-            if (dist0 && h->cfg.world > 1) {
-                HostCSR Pl, Rl;               // rows of P owned by this rank, and their transpose
-                Pl.n_rows = Ld.n;
-                Pl.n_cols = Lh.P.n_cols;
-                Pl.indptr.assign(Ld.n + 1, 0);
-                const int k0 = Lh.P.indptr[rb];
-                for (int r = 0; r <= Ld.n; ++r) Pl.indptr[r] = Lh.P.indptr[rb + r] - k0;
-                Pl.indices.assign(Lh.P.indices.begin() + k0, Lh.P.indices.begin() + Lh.P.indptr[rb + Ld.n]);
-                Pl.values.assign(Lh.P.values.begin() + k0, Lh.P.values.begin() + Lh.P.indptr[rb + Ld.n]);
-                csr_transpose(Pl, Rl);
-                CTL_TRY(sell_from_csr(h, Pl, Ld.P));
-                CTL_TRY(sell_from_csr(h, Rl, Ld.R));
-            } else {
-                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P, FORCE_CSR(l)));
-                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R, FORCE_CSR(l)));
-            }
-            // per cycle: (2 nu - 1 or 2 nu) smoother products + 1 residual, restriction, prolongation
-            const int nu_l = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;
-            H.bytes_per_cycle += spmv * (2 * nu_l) + 2 * (12 * Lh.P.nnz() + 16ll * Ld.n);
-        } else if (!Lh.Ainv.empty()) {
-            CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
-            H.bytes_per_cycle += 8ll * Ld.n * Ld.n;
-        } else {
-            H.bytes_per_cycle += spmv * p.nu;
-        }
-    }
-    H.fused_from = 0;
-    if (h->cfg.world > 1)
+    if (h->cfg.world > 1) {
         CTL_CHECK(nl > 1, CTL_ERR_ARG, "amg_build: the problem is too small for a multi-rank hierarchy (single level)");
-    // record the sub-cycle below level FUSED_FROM - 1 once (zero guess at entry, exactly what vcycle() issues)
-    // (opt-in, CTL_FUSED=1: round-1 measurement showed the cooperative kernel slower than the separate
-    // launches, 1.56 ms against 1.27 ms per inner solve: the operations are bound by dependent memory
-    // round trips, not by launch gaps)
-    const char *fe = getenv("CTL_FUSED");
-    if (nl > FUSED_FROM && fe && (fe[0] == '1' || fe[0] == '2')) {
-        H.fused.cluster = fe[0] == '2' ? fused_cluster_size(h) : 0;      // 2: one thread-block cluster
-        h->recorder = &H.fused;
-        const int rc = vcycle(h, H, FUSED_FROM, H.dev[FUSED_FROM].b, H.dev[FUSED_FROM].x, true);
-        h->recorder = nullptr;
-        CTL_TRY(rc);
-        CTL_TRY(fused_upload(h, H.fused));
-        H.fused_from = FUSED_FROM;
+        CTL_TRY(amg_build_distributed(h, p, fine_pattern, H));
+    } else {
+        for (int l = 0; l < nl; ++l) {
+            AmgLevelHost &Lh = H.host[l];
+            AmgLevelDev &Ld = H.dev[l];
+            Ld.n = Lh.A.n_rows;
+            Ld.rho = Lh.rho;
+            if (l == 0 && fine_pattern) CTL_TRY(sell_set_values(h, fine_pattern, Lh.A.values.data(), Ld.A));
+            else CTL_TRY(sell_from_csr(h, Lh.A, Ld.A));
+            CTL_TRY(ctl_upload(h, &Ld.dinv, Lh.dinv.data(), (size_t)Ld.n));
+            CTL_TRY(amg_level_vectors(h, Ld, l));
+            if (l + 1 < nl) {
+                CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
+                CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
+                if (!Lh.RA.indptr.empty() && Ld.R.lanes > 0) CTL_TRY(sell_from_csr(h, Lh.RA, Ld.RA, Ld.R.lanes));
+            } else if (!Lh.Ainv.empty()) {
+                CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
+            }
+        }
     }
+    H.bytes_per_cycle = amg_cycle_bytes(H);
     if (p.acc_lo > 0.0) {
-        CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n + h->n_halo));
-        CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n + h->n_halo));
-        CTL_TRY(dev_alloc(h, &H.acc_p, H.dev[0].n + h->n_halo));
+        CTL_TRY(dev_alloc(h, &H.acc_r, H.dev[0].n));
+        CTL_TRY(dev_alloc(h, &H.acc_z, H.dev[0].n));
+        CTL_TRY(dev_alloc(h, &H.acc_p, H.dev[0].n));
     }
     return CTL_OK;
 }
 
 void amg_free(AmgHierarchyDev &H)
 {
-    fused_free(H.fused);
-    H.fused_from = 0;
     cudaFree(H.acc_r);
     cudaFree(H.acc_z);
     cudaFree(H.acc_p);
@@ -143,79 +122,127 @@ void amg_free(AmgHierarchyDev &H)
         sell_free(L.A);
         sell_free(L.P);
         sell_free(L.R);
+        sell_free(L.RA);
         cudaFree(L.dinv);
         cudaFree(L.x);
         cudaFree(L.b);
         cudaFree(L.r);
         cudaFree(L.t0);
         cudaFree(L.t1);
+        cudaFree(L.t2);
         cudaFree(L.Ainv);
     }
     H.dev.clear();
     H.host.clear();
+    H.spaces.clear();
 }
 
-// nu Chebyshev steps on D^-1 A over [lo rho, hi rho] (oracle/cheb.py::chebyshev), result in x.
-// Iterates alternate between x and t0; for a non-zero guess and odd nu one copy moves the
-// result back into x.
-// ghost entries of a level-0 vector must be current before a product with the distributed A
-static inline int halo0(ctl_handle_s *h, int l, double *v) { return l == 0 ? ctl_halo_exchange_vec(h, v) : CTL_OK; }
+// a level vector as a kernel gathers it: owned entries + the ghosts of the plan's last exchange
+static GVec gathered(const AmgLevelDev &L, HaloPlan *plan, const double *v, const SellMat &consumer)
+{
+    if (!plan) return GVec(v);
+    return GVec(v, halo_ghost(plan), halo_wait_for(plan, consumer.skip_lo, consumer.skip_hi));
+}
 
-static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, const double *b, double *x, bool zero_guess)
+// nu Chebyshev steps on D^-1 A over [lo rho, hi rho] (oracle/cheb.py::chebyshev).
+//   x_in == nullptr: zero initial guess; otherwise p_0 = x_in (its boundary rows already pushed on L.px).
+// The result lands in x_out, which may be x_in.  No kernel overwrites one of its inputs: intermediate iterates
+// rotate through t0 / t1 / t2 (p_k in W[(k - 1) % 3]; the prolongation leaves p_0 in t2, first rewritten at k = 3,
+// when p_0 is dead).  Every iterate that a later kernel gathers is pushed on L.px.
+static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, const GVec &b, const double *x_in, double *x_out)
 {
     double scale;
     std::vector<double> om;
     const int nu = (l == 0 && p.nu_fine > 0) ? p.nu_fine : p.nu;
     cheb_coefficients(p.lo * L.rho, p.hi * L.rho, nu, &scale, om);
-    // Where iterate p_k lives.  A step reads p_{k-1} through the gather (must not be the buffer
-    // being written) and p_{k-2} element-wise (may be).  Zero guess: alternate x / t0 so that
-    // p_nu lands in x.  Non-zero guess (p_0 = x): rotate x / t0 / t1 backwards from p_nu = x;
-    // this never overwrites a buffer that is still gathered unless nu % 3 == 1, in which case
-    // the iterates alternate t0 / x and one copy moves an odd-nu result back into x.
-    double *buf3[3] = {x, L.t0, L.t1};
-    const bool rotate3 = !zero_guess && (nu % 3 != 1);
+    double *W[3] = {L.t0, L.t1, L.t2};
+    const bool zero = (x_in == nullptr);
     auto where = [&](int k) -> double * {
-        if (k == 0) return x;
-        if (zero_guess) return ((nu - k) & 1) ? L.t0 : x;
-        if (rotate3) return buf3[(nu - k) % 3];
-        return (k & 1) ? L.t0 : x;
+        if (k == nu) return x_out;
+        return W[(k - 1) % 3];
     };
-    if (zero_guess) {
-        CTL_TRY(vec_dinv_scale(h, L.dinv, b, where(1), scale, L.n));
+    if (zero && nu == 1) {
+        const HaloPush push = halo_push(L.px);
+        return vec_dinv_scale(h, L.dinv, b.x, x_out, scale, L.n, push);
+    }
+    if (!zero && nu == 1 && x_in == x_out) {      // the one step would overwrite the vector it gathers
+        CTL_CHECK(!L.px, CTL_ERR_STATE, "smooth: degree 1 in place is not available on several GPUs");
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b.x, nullptr, GVec(x_in), L.t0, 0.0, 1.0, scale));
+        return vec_copy_n(h, x_out, L.t0, L.n);
+    }
+    int k0;      // first step that still has to be taken
+    if (zero) {
+        // p_2 = w p_1 + w s D^-1 (b - A p_1), p_1 = s D^-1 b formed on the fly
+        const GVec dinv = L.px ? GVec(L.dinv, L.dinv + L.n, HaloWait()) : GVec(L.dinv);
+        const HaloPush push = halo_push(L.px);
+        CTL_TRY(sell_cheb_first2(h, L.A, dinv, b, where(2), scale, om[0], push));
+        k0 = 3;
     } else {
-        // p_1 = x + scale D^-1 (b - A x)
-        CTL_TRY(halo0(h, l, x));
-        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, nullptr, x, where(1), 0.0, 1.0, scale));
+        // p_1 = x + s D^-1 (b - A x)
+        const GVec cur = gathered(L, L.px, x_in, L.A);
+        const HaloPush push = halo_push(L.px);
+        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b.x, nullptr, cur, where(1), 0.0, 1.0, scale, 0.0, push));
+        k0 = 2;
     }
-    for (int k = 2; k <= nu; ++k) {
+    for (int k = k0; k <= nu; ++k) {
         const double w = om[k - 2];
-        const bool no_prev = (k == 2 && zero_guess);
-        CTL_TRY(halo0(h, l, where(k - 1)));
-        CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b, no_prev ? nullptr : where(k - 2), where(k - 1), where(k),
-                               no_prev ? 0.0 : (1.0 - w), w, w * scale));
+        const GVec cur = gathered(L, L.px, where(k - 1), L.A);
+        const HaloPush push = halo_push(L.px);
+        if (zero && k == 3) {
+            // p_{k-2} = p_1 was never stored: the kernel rebuilds it from b
+            CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b.x, nullptr, cur, where(k), 1.0 - w, w, w * scale, scale, push));
+        } else {
+            const double *prev = (k == 2) ? x_in : where(k - 2);
+            CTL_TRY(sell_cheb_step(h, L.A, L.dinv, b.x, prev, cur, where(k), 1.0 - w, w, w * scale, 0.0, push));
+        }
     }
-    if (where(nu) != x) CTL_TRY(vec_copy_n(h, x, where(nu), L.n));
     return CTL_OK;
 }
 
-static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const double *b, double *x, bool zero_guess)
+// one V-cycle on level l: x <- cycle(b, x) (x_is_zero: x holds nothing yet).  b: the level's right-hand side with
+// its ghosts (multi-GPU) as the kernels gather it.
+static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const GVec &b, double *x, bool x_is_zero)
 {
     AmgLevelDev &L = H.dev[l];
     const int last = (int)H.dev.size() - 1;
     if (l == last) {
-        if (L.Ainv) return dense_gemv(h, L.Ainv, b, x, L.n);
-        return smooth(h, H.params, L, l, b, x, zero_guess);
+        if (L.Ainv) return dense_gemv(h, L.Ainv, b.x, x, L.n, b.wait);
+        return smooth(h, H.params, L, l, b, x_is_zero ? nullptr : x, x);
     }
     AmgLevelDev &C = H.dev[l + 1];
-    CTL_TRY(smooth(h, H.params, L, l, b, x, zero_guess));
-    CTL_TRY(halo0(h, l, x));
-    CTL_TRY(sell_spmv(h, L.A, x, L.r, b, SELL_RESIDUAL));
-    CTL_TRY(sell_spmv(h, L.R, L.r, C.b, nullptr, SELL_ASSIGN));
-    if (l == 0) CTL_TRY(ctl_allreduce_sum(h, C.b, C.n));      // partial restrictions of the row blocks
-    if (H.fused_from == l + 1 && !h->recorder) CTL_TRY(fused_run(h, H.fused));
-    else CTL_TRY(vcycle(h, H, l + 1, C.b, C.x, true));
-    CTL_TRY(sell_spmv(h, L.P, C.x, x, nullptr, SELL_ADD));
-    CTL_TRY(smooth(h, H.params, L, l, b, x, false));
+    CTL_TRY(smooth(h, H.params, L, l, b, x_is_zero ? nullptr : x, x));
+    // right-hand side of the coarse level: the restricted residual.  Its producer pushes what the coarse level's
+    // first kernels gather (distributed coarse level) or replicates it (first replicated level).
+    double *cb = C.b;
+    HaloPush cpush;
+    if (C.prep) {
+        cb = halo_full_next(C.prep);
+        cpush = halo_push(C.prep);
+    } else if (C.pb) {
+        cpush = halo_push(C.pb);
+    }
+    if (L.RA.valid()) {
+        const GVec gb = L.pb ? GVec(b.x, halo_ghost(L.pb), HaloWait()) : GVec(b.x);
+        const GVec gx = gathered(L, L.px, x, L.RA);
+        CTL_TRY(csrv_restrict_residual(h, L.R, L.RA, gb, gx, cb, cpush));
+    } else {
+        // (the gathered vector is described BEFORE the next exchange of its plan is drawn: both read the plan's counter)
+        HaloPlan *plan_r = L.pr ? L.pr : L.px;
+        const GVec gx = gathered(L, L.px, x, L.A);
+        const HaloPush push_r = halo_push(plan_r);
+        CTL_TRY(sell_spmv(h, L.A, gx, L.r, b.x, SELL_RESIDUAL, push_r));
+        const GVec gr = gathered(L, plan_r, L.r, L.R);
+        CTL_TRY(sell_spmv(h, L.R, gr, cb, nullptr, SELL_ASSIGN, cpush));
+    }
+    GVec gcb(cb);
+    if (C.prep) gcb = GVec(halo_full_last(C.prep), nullptr, halo_wait_for(C.prep, 0, 0));
+    else if (C.pb) gcb = GVec(cb, halo_ghost(C.pb), halo_wait_for(C.pb, C.A.skip_lo, C.A.skip_hi));
+    CTL_TRY(vcycle(h, H, l + 1, gcb, C.x, true));
+    // x' = x + P x_c, out of place into t2; then the post-smoothing brings the result back into x
+    const GVec gxc = gathered(C, C.px, C.x, L.P);
+    const HaloPush push_x = halo_push(L.px);
+    CTL_TRY(sell_spmv(h, L.P, gxc, L.t2, x, SELL_BPLUS, push_x));
+    CTL_TRY(smooth(h, H.params, L, l, b, L.t2, x));
     return CTL_OK;
 }
 
@@ -234,29 +261,32 @@ __global__ void lincomb3_kernel(double *out, double a, const double *x, double b
 }
 }  // namespace
 
-int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x)
+int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x, bool b_exchanged)
 {
     const AmgParams &p = H.params;
+    AmgLevelDev &L0 = H.dev[0];
+    if (L0.pb && !b_exchanged) CTL_TRY(halo_exchange_now(h, L0.pb, b));
+    const GVec gb = L0.pb ? GVec(b, halo_ghost(L0.pb), halo_wait_for(L0.pb, L0.A.skip_lo, L0.A.skip_hi)) : GVec(b);
     if (p.acc_lo <= 0.0) {
-        for (int c = 0; c < p.cycles; ++c) CTL_TRY(vcycle(h, H, 0, b, x, c == 0));
+        for (int c = 0; c < p.cycles; ++c) CTL_TRY(vcycle(h, H, 0, gb, x, c == 0));
         return CTL_OK;
     }
-    // Chebyshev semi-iteration on (V-cycle * A) over [acc_lo, acc_hi]: oracle/amg.py::solve
-    const int n = H.dev[0].n;
+    // Chebyshev semi-iteration on (V-cycle * A) over [acc_lo, acc_hi]: oracle/amg.py::solve (one GPU only)
+    CTL_CHECK(!L0.px, CTL_ERR_STATE, "amg_solve: accelerated cycles are not available on several GPUs");
+    const int n = L0.n;
     double scale;
     std::vector<double> om;
     cheb_coefficients(p.acc_lo, p.acc_hi, p.cycles, &scale, om);
     double *buf[2] = {x, H.acc_p};
     auto slot = [&](int k) { return (p.cycles - k) & 1; };      // p_cycles lands in x
     const int blocks = ceil_div(n, 256);
-    CTL_TRY(vcycle(h, H, 0, b, H.acc_z, true));
+    CTL_TRY(vcycle(h, H, 0, gb, H.acc_z, true));
     pdl_launch(h, blocks, 256, lincomb3_kernel, buf[slot(1)], 0.0, nullptr, 0.0, nullptr, scale, H.acc_z, n);
     h->launches++;
     for (int k = 2; k <= p.cycles; ++k) {
         const double w = om[k - 2];
-        CTL_TRY(halo0(h, 0, buf[slot(k - 1)]));
-        CTL_TRY(sell_spmv(h, H.dev[0].A, buf[slot(k - 1)], H.acc_r, b, SELL_RESIDUAL));
-        CTL_TRY(vcycle(h, H, 0, H.acc_r, H.acc_z, true));
+        CTL_TRY(sell_spmv(h, L0.A, GVec(buf[slot(k - 1)]), H.acc_r, b, SELL_RESIDUAL));
+        CTL_TRY(vcycle(h, H, 0, GVec(H.acc_r), H.acc_z, true));
         pdl_launch(h, blocks, 256, lincomb3_kernel, buf[slot(k)], 1.0 - w, k == 2 ? nullptr : buf[slot(k - 2)], w,
                                                       buf[slot(k - 1)], w * scale, H.acc_z, n);
         h->launches++;

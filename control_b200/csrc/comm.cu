@@ -12,52 +12,11 @@
 //     replicated on every rank).
 // The exchange plan needs no communication: every rank holds the global sparsity pattern
 // and derives, deterministically, both what it needs and what each peer needs from it.
-#include <nccl.h>
-
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
-#include "common.cuh"
-
-struct CommState {
-    ncclComm_t comm = nullptr;
-    int rank = 0, world = 1;
-    std::vector<int> peers;               // ranks we exchange with
-    std::vector<int> recv_off, recv_cnt;  // ghost segment of each peer (rows)
-    std::vector<int> send_off, send_cnt;  // segment of each peer in the packed send list
-    int n_send = 0;
-    int *d_send_rows = nullptr;           // owned local rows to pack, peer after peer
-    double *d_sendbuf = nullptr;          // [2][n_send x ld]
-    // peer-to-peer path of the single-vector exchange (the latency-critical one inside the
-    // time sweeps): boundary values are stored straight into the neighbour's mailbox over
-    // NVLink and signalled with a sequence number; no NCCL kernel, no host involvement
-    bool p2p = false;
-    std::vector<int> peer_halo_n, peer_dst_off;   // host: per peer, its ghost count and where my rows land in it
-    double *mailbox = nullptr;                    // local, [2 slots][n_halo]
-    unsigned long long *flags = nullptr;          // local, [world]: flags[p] = last sequence peer p delivered
-    unsigned long long *d_seq = nullptr;          // local sequence counter
-    int *d_p2p_err = nullptr;
-    struct PeerDesc *d_peers = nullptr;
-    std::vector<void *> opened;                   // cudaIpcOpenMemHandle results
-};
-
-struct PeerDesc {
-    double *mailbox;               // peer's mailbox (mapped)
-    unsigned long long *flags;     // peer's flag array (mapped)
-    int send_off, send_cnt;        // my packed send list segment
-    int dst_off, halo_n;           // offset inside the peer's ghost ordering, peer's ghost count (slot stride)
-    int peer_rank;
-};
-
-#define CTL_NCCL(call)                                                                     \
-    do {                                                                                   \
-        ncclResult_t r__ = (call);                                                         \
-        if (r__ != ncclSuccess) {                                                          \
-            ctl_set_error(h, std::string(#call) + ": " + ncclGetErrorString(r__));         \
-            return CTL_ERR_NCCL;                                                           \
-        }                                                                                  \
-    } while (0)
+#include "comm.cuh"
 
 void ctl_comm_free(ctl_handle_s *h)
 {
@@ -65,12 +24,9 @@ void ctl_comm_free(ctl_handle_s *h)
     CommState &c = *h->comm;
     cudaFree(c.d_send_rows);
     cudaFree(c.d_sendbuf);
-    for (void *p : c.opened) cudaIpcCloseMemHandle(p);
-    cudaFree(c.mailbox);
-    cudaFree(c.flags);
-    cudaFree(c.d_seq);
-    cudaFree(c.d_p2p_err);
-    cudaFree(c.d_peers);
+    cudaFree(c.d_epoch);
+    cudaFree(c.d_err);
+    cudaFree(c.d_barrier);
     if (c.comm) ncclCommDestroy(c.comm);
     h->comm.reset();
 }
@@ -110,16 +66,12 @@ static int build_plan(ctl_handle_s *h, CommState &c)
         owner_range(n, world, p, &pb, &pc);
         // what p needs from me: columns in my range referenced by p's rows (sorted, unique):
         // exactly the segment of p's ghost list that I own, in p's ghost order
-        std::vector<int> need, pghost;
+        std::vector<int> need;
         for (int r = pb; r < pb + pc; ++r)
-            for (int k = ip[r]; k < ip[r + 1]; ++k) {
+            for (int k = ip[r]; k < ip[r + 1]; ++k)
                 if (ix[k] >= my_b && ix[k] < my_b + my_c) need.push_back(ix[k]);
-                if (ix[k] < pb || ix[k] >= pb + pc) pghost.push_back(ix[k]);
-            }
         std::sort(need.begin(), need.end());
         need.erase(std::unique(need.begin(), need.end()), need.end());
-        std::sort(pghost.begin(), pghost.end());
-        pghost.erase(std::unique(pghost.begin(), pghost.end()), pghost.end());
         // what I need from p: my ghosts in p's range (halo_global is sorted by global id)
         const auto lo = std::lower_bound(h->halo_global.begin(), h->halo_global.end(), pb);
         const auto hi = std::lower_bound(h->halo_global.begin(), h->halo_global.end(), pb + pc);
@@ -130,8 +82,6 @@ static int build_plan(ctl_handle_s *h, CommState &c)
         c.recv_cnt.push_back(rc);
         c.send_off.push_back((int)send_rows.size());
         c.send_cnt.push_back((int)need.size());
-        c.peer_halo_n.push_back((int)pghost.size());
-        c.peer_dst_off.push_back((int)(std::lower_bound(pghost.begin(), pghost.end(), my_b) - pghost.begin()));
         for (int g : need) send_rows.push_back(g - my_b);
     }
     c.n_send = (int)send_rows.size();
@@ -182,158 +132,18 @@ int ctl_halo_exchange_panel(ctl_handle_s *h, const double *panel_tf)
     return exchange_panels(h, panel_tf, 1);
 }
 
-namespace {
-
-// One CTA per rank.  Phase 1: store my boundary values into every neighbour's mailbox slot and
-// publish the sequence number.  Phase 2: wait for every neighbour's number, then move the slot
-// into the ghost region of x.  Two slots (sequence parity) are enough: a neighbour can only be
-// one exchange ahead, because finishing exchange s+1 needs my flag s+1, which I publish after
-// I have emptied slot s.
-__global__ void __launch_bounds__(1024) halo_p2p_kernel(double *x, int n_loc, int n_halo, const int *__restrict__ send_rows,
-                                                       const PeerDesc *__restrict__ peers, int n_peers, const double *mailbox,
-                                                       volatile unsigned long long *my_flags, unsigned long long *seq_counter,
-                                                       int my_rank, int *err)
-{
-    __shared__ unsigned long long s_seq;
-    if (threadIdx.x == 0) s_seq = *seq_counter + 1ull;
-    __syncthreads();
-    const unsigned long long seq = s_seq;
-    const int slot = (int)(seq & 1ull);
-    for (int i = 0; i < n_peers; ++i) {
-        const PeerDesc p = peers[i];
-        double *dst = p.mailbox + (size_t)slot * p.halo_n + p.dst_off;
-        for (int j = threadIdx.x; j < p.send_cnt; j += blockDim.x) dst[j] = x[send_rows[p.send_off + j]];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < n_peers) {
-        *reinterpret_cast<volatile unsigned long long *>(peers[threadIdx.x].flags + my_rank) = seq;
-        // wait for the neighbour's delivery of the same exchange (bounded: never hang the GPU)
-        const int pr = peers[threadIdx.x].peer_rank;
-        long spins = 0;
-        while (my_flags[pr] < seq) {
-            __nanosleep(40);
-            if (++spins > 50000000L) {
-                *err = 1;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    const double *src = mailbox + (size_t)slot * n_halo;
-    for (int j = threadIdx.x; j < n_halo; j += blockDim.x) x[n_loc + j] = __ldcv(src + j);
-    if (threadIdx.x == 0) *seq_counter = seq;
-}
-
-}  // namespace
-
-static int setup_p2p(ctl_handle_s *h, CommState &c)
-{
-    if (const char *e = getenv("CTL_NO_P2P"))
-        if (e[0] == '1') return CTL_OK;
-    const int world = c.world;
-    const size_t mb = (size_t)2 * std::max(h->n_halo, 1) * sizeof(double);
-    CTL_CUDA(cudaMalloc((void **)&c.mailbox, mb));
-    CTL_CUDA(cudaMemset(c.mailbox, 0, mb));
-    CTL_CUDA(cudaMalloc((void **)&c.flags, world * sizeof(unsigned long long)));
-    CTL_CUDA(cudaMemset(c.flags, 0, world * sizeof(unsigned long long)));
-    CTL_CUDA(cudaMalloc((void **)&c.d_seq, sizeof(unsigned long long)));
-    CTL_CUDA(cudaMemset(c.d_seq, 0, sizeof(unsigned long long)));
-    CTL_CUDA(cudaMalloc((void **)&c.d_p2p_err, sizeof(int)));
-    CTL_CUDA(cudaMemset(c.d_p2p_err, 0, sizeof(int)));
-    // exchange the IPC handles of (mailbox, flags) through the NCCL communicator itself
-    struct Handles {
-        cudaIpcMemHandle_t mailbox, flags;
-    } mine;
-    if (cudaIpcGetMemHandle(&mine.mailbox, c.mailbox) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, c.flags) != cudaSuccess) {
-        cudaGetLastError();
-        return CTL_OK;          // no IPC (e.g. restricted container): stay on the NCCL path
-    }
-    Handles *d_all = nullptr;
-    CTL_CUDA(cudaMalloc((void **)&d_all, world * sizeof(Handles)));
-    CTL_CUDA(cudaMemcpy(d_all + c.rank, &mine, sizeof(Handles), cudaMemcpyHostToDevice));
-    CTL_NCCL(ncclAllGather(d_all + c.rank, d_all, sizeof(Handles), ncclChar, c.comm, h->stream));
-    CTL_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<Handles> all(world);
-    CTL_CUDA(cudaMemcpy(all.data(), d_all, world * sizeof(Handles), cudaMemcpyDeviceToHost));
-    cudaFree(d_all);
-    std::vector<PeerDesc> descs;
-    bool ok = true;
-    for (size_t i = 0; i < c.peers.size() && ok; ++i) {
-        const int p = c.peers[i];
-        void *pm = nullptr, *pf = nullptr;
-        if (cudaIpcOpenMemHandle(&pm, all[p].mailbox, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
-            cudaIpcOpenMemHandle(&pf, all[p].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            ok = false;
-            break;
-        }
-        c.opened.push_back(pm);
-        c.opened.push_back(pf);
-        PeerDesc d;
-        d.mailbox = (double *)pm;
-        d.flags = (unsigned long long *)pf;
-        d.send_off = c.send_off[i];
-        d.send_cnt = c.send_cnt[i];
-        d.dst_off = c.peer_dst_off[i];
-        d.halo_n = c.peer_halo_n[i];
-        d.peer_rank = p;
-        descs.push_back(d);
-    }
-    // every rank must take the same path: agree through an all-reduce of the success flags
-    int *d_ok = nullptr;
-    CTL_CUDA(cudaMalloc((void **)&d_ok, sizeof(int)));
-    const int mine_ok = ok ? 1 : 0;
-    CTL_CUDA(cudaMemcpy(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
-    CTL_NCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.comm, h->stream));
-    CTL_CUDA(cudaStreamSynchronize(h->stream));
-    int all_ok = 0;
-    CTL_CUDA(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
-    cudaFree(d_ok);
-    if (!all_ok || c.peers.size() > 1024) return CTL_OK;
-    CTL_CUDA(cudaMalloc((void **)&c.d_peers, std::max<size_t>(descs.size(), 1) * sizeof(PeerDesc)));
-    CTL_CUDA(cudaMemcpy(c.d_peers, descs.data(), descs.size() * sizeof(PeerDesc), cudaMemcpyHostToDevice));
-    c.p2p = true;
-    return CTL_OK;
-}
-
-// single spatial vector with ghost entries appended behind the n_loc owned ones
-int ctl_halo_exchange_vec(ctl_handle_s *h, double *x)
-{
-    if (!h->comm || h->n_halo == 0) return CTL_OK;
-    CommState &c = *h->comm;
-    if (c.p2p) {
-        halo_p2p_kernel<<<1, 1024, 0, h->stream>>>(x, h->n_loc, h->n_halo, c.d_send_rows, c.d_peers, (int)c.peers.size(), c.mailbox,
-                                                  c.flags, c.d_seq, c.rank, c.d_p2p_err);
-        h->launches++;
-        CTL_CUDA(cudaGetLastError());
-        return CTL_OK;
-    }
-    if (c.n_send > 0) {
-        pack_rows_kernel<<<ceil_div(c.n_send, 256), 256, 0, h->stream>>>(x, c.d_send_rows, c.n_send, 1, c.d_sendbuf);
-        h->launches++;
-        CTL_CUDA(cudaGetLastError());
-    }
-    CTL_NCCL(ncclGroupStart());
-    for (size_t i = 0; i < c.peers.size(); ++i) {
-        if (c.send_cnt[i])
-            CTL_NCCL(ncclSend(c.d_sendbuf + c.send_off[i], (size_t)c.send_cnt[i], ncclDouble, c.peers[i], c.comm, h->stream));
-        if (c.recv_cnt[i])
-            CTL_NCCL(ncclRecv(x + h->n_loc + c.recv_off[i], (size_t)c.recv_cnt[i], ncclDouble, c.peers[i], c.comm, h->stream));
-    }
-    CTL_NCCL(ncclGroupEnd());
-    return CTL_OK;
-}
-
-// has a peer-to-peer exchange given up waiting (bounded spin)?  Called at the end of a solve.
+// has a device-side wait of the sweep kernels given up (bounded spin, halo.cuh)?  Called by every public entry
+// point that runs sweeps; the flag is cleared once reported.
 int ctl_comm_check(ctl_handle_s *h)
 {
-    if (!h->comm || !h->comm->p2p) return CTL_OK;
+    if (!h->comm || !h->comm->d_err) return CTL_OK;
     int err = 0;
-    CTL_CUDA(cudaMemcpyAsync(&err, h->comm->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CTL_CUDA(cudaMemcpyAsync(&err, h->comm->d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CTL_CUDA(cudaStreamSynchronize(h->stream));
-    CTL_CHECK(err == 0, CTL_ERR_NCCL, "peer-to-peer halo exchange timed out waiting for a neighbour");
+    if (err != 0) {
+        CTL_CUDA(cudaMemsetAsync(h->comm->d_err, 0, sizeof(int), h->stream));
+        CTL_CHECK(false, CTL_ERR_NCCL, "halo exchange timed out waiting for a neighbour (CTL_HALO_TIMEOUT_MS)");
+    }
     return CTL_OK;
 }
 
@@ -371,7 +181,17 @@ int ctl_comm_init(ctl_handle h, const void *id128)
     memcpy(&id, id128, sizeof(id));
     CTL_NCCL(ncclCommInitRank(&c.comm, c.world, id, c.rank));
     CTL_TRY(build_plan(h, c));
-    return setup_p2p(h, c);
+    // device words of the in-kernel exchange (halo.cu)
+    CTL_CUDA(cudaMalloc((void **)&c.d_epoch, sizeof(unsigned long long)));
+    CTL_CUDA(cudaMemset(c.d_epoch, 0, sizeof(unsigned long long)));
+    CTL_CUDA(cudaMalloc((void **)&c.d_err, sizeof(int)));
+    CTL_CUDA(cudaMemset(c.d_err, 0, sizeof(int)));
+    CTL_CUDA(cudaMalloc((void **)&c.d_barrier, sizeof(int)));
+    CTL_CUDA(cudaMemset(c.d_barrier, 0, sizeof(int)));
+    long long ms = 20000;
+    if (const char *e = getenv("CTL_HALO_TIMEOUT_MS")) ms = std::max(1ll, atoll(e));
+    c.max_spins = ms * 2000;      // one spin is a 20 ns sleep plus an L2 read: about half a microsecond
+    return CTL_OK;
 }
 
 }  // extern "C"

@@ -92,6 +92,8 @@ void ctl_pc_free(ctl_handle_s *h)
     cudaFree(st.B);
     cudaFree(st.Uf);
     cudaFree(st.Ub);
+    cudaFree(st.W);
+    halo_arena_free(h, st.arena);
     h->pc.reset();
 }
 
@@ -101,43 +103,57 @@ int ctl_pc_invalidate(ctl_handle_s *h)
     return CTL_OK;
 }
 
+// a sweep vector with its ghosts behind the owned entries (multi-GPU: completed by halo_persist right after the
+// solve that produced it, so later products need not wait)
+static GVec ts_vec(const PcState &st, const double *v, int n_loc)
+{
+    if (!st.px0) return GVec(v);
+    return GVec(v, v + n_loc, HaloWait());
+}
+
 static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
 {
-    const int N = h->N;
+    const int N = h->N, nl = h->n_loc;
     const size_t S = st.ts_stride;
     const bool cn = h->cfg.CN != 0;
     const double tau = h->cfg.tau, eps = h->cfg.epsilon;
-    // forward sweep (control/control.py:2053-2116 CN, 2241-2328 BE)
+    CTL_TRY(halo_epoch_begin(h));
+    // forward sweep (control/control.py:2053-2116 CN, 2241-2328 BE).  The right-hand side of a step is formed out of
+    // place (W = b_i -/+ Off u_{i-1}) by the kernel that also pushes its boundary rows to the neighbours.
     for (int i = 0; i < N; ++i) {
-        double *bi = st.B + i * S;
+        const double *bi = st.B + i * S;
         if (i > 0) {
-            const double *up = st.Uf + (i - 1) * S;
-            if (cn) CTL_TRY(sell_spmv(h, st.off[st.fwd_off[i]], up, bi, nullptr, SELL_SUB));
-            else CTL_TRY(sell_spmv(h, st.Msell, up, bi, nullptr, SELL_ADD));     // b_i -= (-M) u_{i-1}
+            const GVec up = ts_vec(st, st.Uf + (i - 1) * S, nl);
+            const HaloPush push = halo_push(st.pb0);
+            if (cn) CTL_TRY(sell_spmv(h, st.off[st.fwd_off[i]], up, st.W, bi, SELL_RESIDUAL, push));
+            else CTL_TRY(sell_spmv(h, st.Msell, up, st.W, bi, SELL_BPLUS, push));     // b_i - (-M) u_{i-1}
+            CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], st.W, st.Uf + i * S, true));
+        } else {
+            CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], bi, st.Uf + i * S, false));
         }
-        CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], bi, st.Uf + i * S));
-        CTL_TRY(ctl_halo_exchange_vec(h, st.Uf + i * S));      // later products read its ghost entries
+        CTL_TRY(halo_persist(h, st.px0, st.Uf + i * S + nl));      // later products read its ghost entries
     }
     // middle scaling fused with the backward right-hand sides
     // (control/control.py:2118-2133 + 2158-2168 CN; 2330-2350 + 2375-2385 BE)
     for (int i = N - 1; i >= 0; --i) {
         double *bi = st.B + i * S;
-        const double *ui = st.Uf + i * S;
-        const double *un = i + 1 < N ? st.Ub + (i + 1) * S : nullptr;
+        const GVec ui = ts_vec(st, st.Uf + i * S, nl);
+        const GVec un = i + 1 < N ? ts_vec(st, st.Ub + (i + 1) * S, nl) : GVec();
+        const HaloPush push = halo_push(st.pb0);
         if (cn) {
             // b_i = tau/2 M (T_2 u)_i - (L_hat^T)_{i,i+1} u_{i+1}; the block-diagonal variant has
             // no T_2 / T_2^-1 pair (oracle/pc.py::construct_pc_diagonal)
             const bool t2 = st.opts.mode == CTL_PCMODE_TRIANGULAR;
-            const double *up = (t2 && i > 0) ? st.Uf + (i - 1) * S : nullptr;
-            const SellMat &offm = un ? st.off[st.bwd_off[i]] : st.Msell;
-            CTL_TRY(sell_spmv2(h, st.Msell, offm, ui, up, un, bi, 0.5 * tau, -1.0));
+            const GVec up = (t2 && i > 0) ? ts_vec(st, st.Uf + (i - 1) * S, nl) : GVec();
+            const SellMat &offm = un.x ? st.off[st.bwd_off[i]] : st.Msell;
+            CTL_TRY(sell_spmv2(h, st.Msell, offm, ui, up, un, bi, 0.5 * tau, -1.0, push));
         } else {
             // b_i = tau M u_i (eps tau for the last block) - (-M) u_{i+1}
             const double a = (i == N - 1) ? eps * tau : tau;
-            CTL_TRY(sell_spmv2(h, st.Msell, st.Msell, ui, nullptr, un, bi, a, 1.0));
+            CTL_TRY(sell_spmv2(h, st.Msell, st.Msell, ui, GVec(), un, bi, a, 1.0, push));
         }
-        CTL_TRY(amg_solve(h, st.hier[st.bwd_h[i]], bi, st.Ub + i * S));
-        if (i > 0) CTL_TRY(ctl_halo_exchange_vec(h, st.Ub + i * S));
+        CTL_TRY(amg_solve(h, st.hier[st.bwd_h[i]], bi, st.Ub + i * S, true));
+        if (i > 0) CTL_TRY(halo_persist(h, st.px0, st.Ub + i * S + nl));
     }
     return CTL_OK;
 }
@@ -210,6 +226,7 @@ static int pc_fn_tf(ctl_handle_s *h, const double *b, double *u, bool wrap)
             // Multigrid=True: AMG on assemble(M, bcs), column by column
             if ((rc = pcb_u0_first(h, b0, st.d_mass_dinv, btil, pa, 1.0)) != CTL_OK) break;
             if ((rc = pcb_panel_to_ts(h, btil, st.B, st.ts_stride)) != CTL_OK) break;
+            if ((rc = halo_epoch_begin(h)) != CTL_OK) break;
             for (int i = 0; i < h->N && rc == CTL_OK; ++i)
                 rc = amg_solve(h, st.hier[st.h_mass], st.B + i * st.ts_stride, st.Uf + i * st.ts_stride);
             if (rc != CTL_OK) break;
@@ -247,7 +264,10 @@ static int pc_entry(ctl_handle_s *h, const double *b, double *u, int layout, boo
     CTL_CHECK(h && b && u, CTL_ERR_ARG, "ctl_pc_apply: null argument");
     CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_pc_apply: ctl_assemble has not been called");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
-    if (layout == CTL_LAYOUT_TIME_FASTEST) return pc_fn_tf(h, b, u, wrap);
+    if (layout == CTL_LAYOUT_TIME_FASTEST) {
+        CTL_TRY(pc_fn_tf(h, b, u, wrap));
+        return ctl_comm_check(h);
+    }
     double *bt = nullptr, *ut = nullptr;
     CTL_TRY(ctl_scratch_get(h, &bt));
     CTL_TRY(ctl_scratch_get(h, &ut));
@@ -256,6 +276,7 @@ static int pc_entry(ctl_handle_s *h, const double *b, double *u, int layout, boo
     if (rc == CTL_OK) rc = ctl_to_bm(h, ut, u);
     ctl_scratch_put(h, bt);
     ctl_scratch_put(h, ut);
+    if (rc == CTL_OK) rc = ctl_comm_check(h);
     return rc;
 }
 
@@ -361,6 +382,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     st.amg.acc_lo = opts->amg_acc_lo;
     st.amg.acc_hi = opts->amg_acc_hi;
     if (const char *e = getenv("CTL_NO_GRAPH")) st.use_graph = !(e[0] == '1');
+    if (const char *e = getenv("CTL_AMG_RR")) st.amg.fuse_rr = atoi(e) != 0;      // experiment: fused restricted residual
 
     const int N = h->N, nl = h->n_loc, rb = h->row_begin;
     const bool cn = h->cfg.CN != 0;
@@ -396,11 +418,40 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     }
 
     CTL_TRY(sell_build_pattern(h, h->loc, st.fine));
+    // multi-GPU: exchange geometry of everything that gathers through the mesh pattern, and the two level-0
+    // exchange streams (iterates, right-hand sides) every hierarchy shares
+    int mesh_skip_lo = 0, mesh_skip_hi = 0;
+    if (h->cfg.world > 1) {
+        std::vector<int> part0(h->cfg.world + 1, 0);
+        for (int r = 0; r < h->cfg.world; ++r) {
+            const int base = h->n / h->cfg.world, rem = h->n % h->cfg.world;
+            part0[r + 1] = part0[r] + base + (r < rem ? 1 : 0);
+        }
+        SpaceConsumer mesh;
+        mesh.n_rows = h->n;
+        mesh.indptr = h->h_indptr.data();
+        mesh.indices = h->h_indices.data();
+        mesh.row_part = part0.data();
+        auto geom = std::make_shared<HaloGeom>();
+        halo_geometry(h->cfg.world, h->cfg.rank, part0, {mesh}, false, *geom);
+        CTL_TRY(halo_space_upload(h, geom, st.mesh_space));
+        st.px0 = halo_arena_add(h, st.arena, st.mesh_space);
+        st.pb0 = halo_arena_add(h, st.arena, st.mesh_space);
+        halo_skip_range(h->loc, h->n_loc, &mesh_skip_lo, &mesh_skip_hi);
+    }
+    auto mesh_matrix = [&](SellMat &m) {
+        if (h->cfg.world > 1) {
+            m.n_own = h->n_loc;
+            m.skip_lo = mesh_skip_lo;
+            m.skip_hi = mesh_skip_hi;
+        }
+    };
     std::vector<double> vals;
     combine_global(h, 0, false, 0.0, 1.0, false, vals);
     {
         const std::vector<double> lv = local_values(h, vals);
         CTL_TRY(sell_set_values(h, st.fine, lv.data(), st.Msell));
+        mesh_matrix(st.Msell);
     }
 
     // distinct diagonal blocks -> AMG hierarchies; distinct off-diagonal blocks -> SELL
@@ -507,32 +558,10 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         st.off.assign(n_off, SellMat());
         for (int i = 0; i < n_off; ++i) {
             CTL_TRY(sell_set_values(h, st.fine, off_values[i].data(), st.off[i]));
+            mesh_matrix(st.off[i]);
             off_values[i] = std::vector<double>();
         }
-    }
-
-    // Experiment (CTL_L2_PERSIST=<MB>): pin the fine-level matrix of hierarchy 0 in the persisting L2 carve-out
-    if (const char *e = getenv("CTL_L2_PERSIST")) {
-        const size_t want = (size_t)atoi(e) << 20;
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, h->cfg.device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, h->cfg.device);
-        const size_t carve = std::min<size_t>(want, (size_t)max_persist);
-        fprintf(stderr, "[ctl] L2 persist: max carve-out %d MB, max window %d MB, using %zu MB\n", max_persist >> 20,
-                max_window >> 20, carve >> 20);
-        if (want > 0 && !st.hier.empty()) {
-            CTL_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve));
-            const SellMat &A0 = st.hier[0].dev[0].A;
-            const size_t bytes = (size_t)A0.pat->n_stored * sizeof(double);
-            cudaStreamAttrValue attr;
-            memset(&attr, 0, sizeof(attr));
-            attr.accessPolicyWindow.base_ptr = A0.vals;
-            attr.accessPolicyWindow.num_bytes = std::min(bytes, (size_t)max_window);
-            attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)carve / (double)bytes);
-            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            CTL_CUDA(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-        }
+        if (h->cfg.world > 1) CTL_TRY(halo_arena_finalize(h, st.arena));
     }
 
     st.ts_stride = (size_t)nl + h->n_halo;
@@ -543,6 +572,8 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     CTL_CUDA(cudaMemsetAsync(st.B, 0, ts_bytes, h->stream));
     CTL_CUDA(cudaMemsetAsync(st.Uf, 0, ts_bytes, h->stream));
     CTL_CUDA(cudaMemsetAsync(st.Ub, 0, ts_bytes, h->stream));
+    CTL_CUDA(cudaMalloc((void **)&st.W, st.ts_stride * sizeof(double)));
+    CTL_CUDA(cudaMemsetAsync(st.W, 0, st.ts_stride * sizeof(double), h->stream));
     CTL_CUDA(cudaStreamSynchronize(h->stream));
     st.ready = true;
     return CTL_OK;
@@ -605,14 +636,9 @@ int ctl_amg_solve(ctl_handle h, int32_t hi, const double *b, double *x)
 {
     CTL_CHECK(h && h->pc && hi >= 0 && hi < (int)h->pc->hier.size() && b && x, CTL_ERR_ARG, "ctl_amg_solve: bad argument");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
-    if (h->n_halo == 0) return amg_solve(h, h->pc->hier[hi], b, x);
-    // distributed level 0: the cycle needs ghost space behind the owned entries
-    PcState &st = *h->pc;
-    const size_t nb = (size_t)h->n_loc * sizeof(double);
-    CTL_CUDA(cudaMemcpyAsync(st.B, b, nb, cudaMemcpyDeviceToDevice, h->stream));
-    CTL_TRY(amg_solve(h, st.hier[hi], st.B, st.Uf));
-    CTL_CUDA(cudaMemcpyAsync(x, st.Uf, nb, cudaMemcpyDeviceToDevice, h->stream));
-    return CTL_OK;
+    CTL_TRY(halo_epoch_begin(h));
+    CTL_TRY(amg_solve(h, h->pc->hier[hi], b, x, false));
+    return ctl_comm_check(h);
 }
 
 int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
@@ -625,15 +651,18 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
     const int n = L0.n;
     double *x = nullptr, *b = nullptr, *flush = nullptr;
     const size_t flush_bytes = 256u << 20;
-    CTL_CUDA(cudaMalloc((void **)&x, (size_t)n * sizeof(double)));
-    CTL_CUDA(cudaMalloc((void **)&b, (size_t)n * sizeof(double)));
+    const size_t nv = (size_t)n + L0.n_ghost;      // ghost entries behind the owned ones (multi-GPU; left at zero)
+    CTL_CUDA(cudaMalloc((void **)&x, nv * sizeof(double)));
+    CTL_CUDA(cudaMalloc((void **)&b, nv * sizeof(double)));
+    CTL_CUDA(cudaMemset(b, 0, nv * sizeof(double)));
     if (flush_l2) CTL_CUDA(cudaMalloc((void **)&flush, flush_bytes));
     {
         std::vector<double> hb(n);
         for (int i = 0; i < n; ++i) hb[i] = std::sin(0.37 * i) + 0.1;
         CTL_CUDA(cudaMemcpy(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-        CTL_CUDA(cudaMemset(x, 0, (size_t)n * sizeof(double)));
+        CTL_CUDA(cudaMemset(x, 0, nv * sizeof(double)));
     }
+    const GVec gb = L0.px ? GVec(b, b + n, HaloWait()) : GVec(b);
     cudaEvent_t e0, e1;
     CTL_CUDA(cudaEventCreate(&e0));
     CTL_CUDA(cudaEventCreate(&e1));
@@ -644,14 +673,14 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
     int64_t launches_solve = 0;
     int rc = CTL_OK;
     auto timed = [&](int which, bool with_kernel, float *ms) -> int {
-        int r2 = CTL_OK;
+        int r2 = which == 2 ? halo_epoch_begin(h) : CTL_OK;      // every rank times the same sequence
         cudaEventRecord(e0, h->stream);
         for (int r = 0; r < reps && r2 == CTL_OK; ++r) {
             if (flush) cudaMemsetAsync(flush, r & 0xff, flush_bytes, h->stream);
             if (!with_kernel) continue;
             const int64_t l0 = h->launches;
-            if (which == 0) r2 = sell_cheb_step(h, L0.A, L0.dinv, b, x, b, L0.t0, 0.3, 0.7, 0.1);
-            else if (which == 1) r2 = sell_spmv(h, L0.A, b, L0.r, x, SELL_RESIDUAL);
+            if (which == 0) r2 = sell_cheb_step(h, L0.A, L0.dinv, b, x, gb, L0.t0, 0.3, 0.7, 0.1);
+            else if (which == 1) r2 = sell_spmv(h, L0.A, gb, L0.r, x, SELL_RESIDUAL);
             else r2 = amg_solve(h, H, b, x);
             launches_solve = h->launches - l0;
         }
@@ -667,11 +696,11 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
         if (rc == CTL_OK) rc = timed(which, false, &without_k);
         acc[which] = with_k - (flush ? without_k : 0.f);
     }
-    const double nnz = (double)L0.A.pat->nnz;
+    const double mat = (double)L0.A.bytes_per_pass;      // matrix stream of the format in use (sell_format.h)
     out[0] = acc[0] / reps;
-    out[1] = 12.0 * nnz + 40.0 * n;          // values + indices + dinv, b, p_prev, p_cur, out
+    out[1] = mat + 40.0 * n;                 // matrix + dinv, b, p_prev, p_cur, out
     out[2] = acc[1] / reps;
-    out[3] = 12.0 * nnz + 24.0 * n;          // values + indices + b, x, r
+    out[3] = mat + 24.0 * n;                 // matrix + b, x, r
     out[4] = acc[2] / reps;
     out[5] = (double)H.bytes_per_cycle * H.params.cycles;
     out[6] = (double)launches_solve;

@@ -5,6 +5,7 @@
 
 #include "amg.cuh"
 #include "common.cuh"
+#include "halo_host.cuh"
 
 // pc_batched.cu: one-panel kernels in the time-fastest layout
 int pcb_u0_first(ctl_handle_s *h, const double *b0, const double *dinv, double *btil, double *p1, double c);
@@ -32,7 +33,13 @@ struct PcState {
     std::vector<int> fwd_off, bwd_off;      // off-diagonal matrix used at each time step (-1: none)
 
     size_t ts_stride = 0;                   // row length of the time-slowest sweep arrays
-    double *B = nullptr, *Uf = nullptr, *Ub = nullptr;   // [N][ts_stride]
+    double *B = nullptr, *Uf = nullptr, *Ub = nullptr;   // [N][ts_stride]: owned rows, then the ghosts (multi-GPU)
+    double *W = nullptr;                    // [ts_stride] right-hand side of the current forward step
+
+    // multi-GPU: device-initiated exchange of the sweep kernels (halo.cuh)
+    HaloArena arena;                        // ghost slots and flags of every exchange stream, IPC-shared
+    std::shared_ptr<HaloSpace> mesh_space;  // who gathers what through the mesh pattern
+    HaloPlan *px0 = nullptr, *pb0 = nullptr;   // level-0 iterates / right-hand sides (shared by all hierarchies)
     cudaGraphExec_t sweep_graph = nullptr;
     bool use_graph = true;
     int64_t sweep_launches = 0;             // kernels inside one sweep graph

@@ -1,30 +1,143 @@
-// SELL-32 construction and the single-column SpMV kernel family (see sell.cuh).
-// All kernels: one thread per row, 128 threads per CTA, HBM/L2-bound streaming of
-// (4 + 8) bytes per stored entry plus the gathered x.
+// Single-column sparse products of the time sweeps and the AMG cycles (see sell.cuh): SELL-32 kernels (one thread
+// per row) and CSR-vector kernels (T lanes per row) over the exact compressed formats of sell_format.h, with the
+// device-initiated halo exchange of halo.cuh folded into every kernel.  Everything here is bound by the matrix /
+// vector stream (HBM, or L2 once the compressed matrix stays resident) and by launch latency on the coarse levels;
+// nothing is a dense contraction.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "sell.cuh"
 
 SellPattern::~SellPattern()
 {
-    cudaFree(slice_ptr);
+    cudaFree(sp);
     cudaFree(cols);
+    cudaFree(dcol);
 }
 
 void sell_free(SellMat &m)
 {
     cudaFree(m.vals);
+    cudaFree(m.vcode);
+    cudaFree(m.vdict);
+    cudaFree(m.code);
+    cudaFree(m.dict);
     cudaFree(m.csr_ptr);
     cudaFree(m.csr_cols);
+    cudaFree(m.csr_rbase);
+    cudaFree(m.csr_dcol);
     cudaFree(m.csr_vals);
-    m.vals = m.csr_vals = nullptr;
-    m.csr_ptr = m.csr_cols = nullptr;
-    m.lanes = 0;
-    m.pat.reset();
+    m = SellMat();
 }
 
-int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_csr)
+MatView SellMat::view() const
+{
+    MatView v;
+    v.fmt = fmt;
+    v.n_rows = pat->n_rows;
+    v.n_own = n_own > 0 ? n_own : pat->n_cols;
+    if (lanes) {
+        v.ptr = csr_ptr;
+        v.rbase = csr_rbase;
+        v.cols = csr_cols;
+        v.dcol = csr_dcol;
+        v.vals = csr_vals;
+    } else {
+        v.sp = pat->sp;
+        v.cols = pat->cols;
+        v.dcol = pat->dcol;
+        v.vals = vals;
+    }
+    v.vcode = vcode;
+    v.vdict = vdict;
+    v.code = code;
+    v.dict = dict;
+    return v;
+}
+
+int sell_max_fmt()
+{
+    static int v = -1;
+    if (v < 0) {
+        v = FMT_DICT8;
+        if (const char *e = getenv("CTL_SELL_FMT")) {      // experiment / tests: cap the automatic choice
+            if (!strcmp(e, "f64")) v = FMT_F64;
+            else if (!strcmp(e, "d16")) v = FMT_D16;
+            else if (!strcmp(e, "pk")) v = FMT_PK;
+            else if (!strcmp(e, "dict16")) v = FMT_DICT16;
+        }
+    }
+    return v;
+}
+
+// matrices whose stream exceeds this many bytes are read evict-first: they cannot stay in L2 next to the
+// vectors of their level, and must not flush the coarse levels out of it
+static int64_t stream_threshold()
+{
+    static int64_t v = -1;
+    if (v < 0) {
+        v = 40ll << 20;
+        if (const char *e = getenv("CTL_STREAM_MB")) v = (int64_t)atoi(e) << 20;
+    }
+    return v;
+}
+
+template <typename T>
+static int upload_vec(ctl_handle_s *h, T **dst, const std::vector<T> &src)
+{
+    if (*dst) {
+        cudaFree(*dst);
+        *dst = nullptr;
+    }
+    if (src.empty()) return CTL_OK;
+    CTL_CUDA(cudaMalloc((void **)dst, src.size() * sizeof(T)));
+    CTL_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CTL_CUDA(cudaStreamSynchronize(h->stream));
+    return CTL_OK;
+}
+
+int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPattern> &out)
+{
+    auto p = std::make_shared<SellPattern>();
+    SfCsr a;
+    a.n_rows = A.n_rows;
+    a.n_cols = A.n_cols;
+    a.indptr = A.indptr.data();
+    a.indices = A.indices.data();
+    sf_sell_layout(a, p->host);
+    if (sell_max_fmt() < FMT_D16) p->host.dcol.clear();
+    p->n_rows = A.n_rows;
+    p->n_cols = A.n_cols;
+    p->n_slices = p->host.n_slices;
+    p->n_stored = p->host.n_stored;
+    p->nnz = p->host.nnz;
+    CTL_TRY(upload_vec(h, &p->sp, p->host.sp));
+    CTL_TRY(upload_vec(h, &p->cols, p->host.cols));
+    CTL_TRY(upload_vec(h, &p->dcol, p->host.dcol));
+    out = p;
+    return CTL_OK;
+}
+
+int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values, SellMat &out)
+{
+    SfSellValues V;
+    sf_sell_values(pat->host, csr_values, sell_max_fmt(), V);
+    out.pat = pat;
+    out.fmt = V.fmt;
+    out.lanes = 0;
+    out.bytes_per_pass = V.bytes_per_pass;
+    out.stream = V.bytes_per_pass > stream_threshold();
+    CTL_TRY(upload_vec(h, &out.vals, V.vals));
+    CTL_TRY(upload_vec(h, &out.vcode, V.vcode));
+    CTL_TRY(upload_vec(h, &out.vdict, V.vdict));
+    CTL_TRY(upload_vec(h, &out.dict, V.dict));
+    if (V.fmt == FMT_DICT8) CTL_TRY(upload_vec(h, (uint8_t **)&out.code, V.code8));
+    else if (V.fmt == FMT_DICT16) CTL_TRY(upload_vec(h, (uint16_t **)&out.code, V.code16));
+    return CTL_OK;
+}
+
+int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lanes)
 {
     const double mean = A.n_rows ? (double)A.nnz() / A.n_rows : 0.0;
     // SELL-32 (one row per thread, coalesced) up to a mean row length of 24: measured at C2 against the
@@ -36,7 +149,7 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_cs
     int sell_min_rows = 50000;
     if (const char *e = getenv("CTL_SELL_MIN_ROWS")) sell_min_rows = atoi(e);      // experiment
     const bool mesh_like = mean <= 10.0;          // fine-mesh stencils (short rows): always SELL
-    if ((mesh_like || (mean <= sell_max_mean && A.n_rows >= sell_min_rows)) && !force_csr) {
+    if (force_lanes == 0 && (mesh_like || (mean <= sell_max_mean && A.n_rows >= sell_min_rows))) {
         std::shared_ptr<SellPattern> pat;
         CTL_TRY(sell_build_pattern(h, A, pat));
         return sell_set_values(h, pat, A.values.data(), out);
@@ -52,550 +165,508 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, bool force_cs
     out.lanes = mean <= 16.0 ? 4 : (mean <= 48.0 ? 8 : 16);
     if (const char *e = getenv("CTL_CSR_LANES_SHIFT")) {          // experiment: wider / narrower row groups
         const int sh = atoi(e);
-        out.lanes = std::max(2, std::min(32, sh >= 0 ? out.lanes << sh : out.lanes >> (-sh)));
+        out.lanes = std::max(4, std::min(16, sh >= 0 ? out.lanes << sh : out.lanes >> (-sh)));
     }
-    CTL_TRY(ctl_upload(h, &out.csr_ptr, A.indptr.data(), A.indptr.size()));
-    CTL_TRY(ctl_upload(h, &out.csr_cols, A.indices.data(), A.indices.size()));
-    CTL_TRY(ctl_upload(h, &out.csr_vals, A.values.data(), A.values.size()));
-    return CTL_OK;
-}
-
-int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPattern> &out)
-{
-    auto p = std::make_shared<SellPattern>();
-    p->n_rows = A.n_rows;
-    p->n_cols = A.n_cols;
-    p->n_slices = ceil_div(A.n_rows, 32);
-    p->nnz = A.nnz();
-    std::vector<int> sptr(p->n_slices + 1, 0);
-    for (int s = 0; s < p->n_slices; ++s) {
-        int w = 0;
-        for (int r = 32 * s; r < std::min(A.n_rows, 32 * s + 32); ++r) w = std::max(w, A.indptr[r + 1] - A.indptr[r]);
-        sptr[s + 1] = sptr[s] + 32 * w;
+    if (force_lanes) out.lanes = force_lanes;
+    SfCsr a;
+    a.n_rows = A.n_rows;
+    a.n_cols = A.n_cols;
+    a.indptr = A.indptr.data();
+    a.indices = A.indices.data();
+    SfCsrvData D;
+    sf_csrv_data(a, A.values.data(), std::min(sell_max_fmt(), (int)FMT_PK), D);
+    out.fmt = D.fmt;
+    out.bytes_per_pass = D.bytes_per_pass;
+    out.stream = D.bytes_per_pass > stream_threshold();
+    CTL_TRY(upload_vec(h, &out.csr_ptr, A.indptr));
+    CTL_TRY(upload_vec(h, &out.csr_cols, A.indices));
+    CTL_TRY(upload_vec(h, &out.csr_rbase, D.rbase));
+    CTL_TRY(upload_vec(h, &out.csr_dcol, D.dcol));
+    if (D.fmt == FMT_PK) {
+        CTL_TRY(upload_vec(h, &out.vcode, D.vcode));
+        CTL_TRY(upload_vec(h, &out.vdict, D.vdict));
+    } else {
+        CTL_TRY(upload_vec(h, &out.csr_vals, A.values));
     }
-    p->n_stored = sptr[p->n_slices];
-    std::vector<int> cols((size_t)p->n_stored);
-    p->csr_to_sell.resize(A.nnz());
-    for (int s = 0; s < p->n_slices; ++s) {
-        const int w = (sptr[s + 1] - sptr[s]) / 32;
-        for (int lane = 0; lane < 32; ++lane) {
-            const int r = 32 * s + lane;
-            const int len = r < A.n_rows ? A.indptr[r + 1] - A.indptr[r] : 0;
-            for (int k = 0; k < w; ++k) {
-                const int64_t pos = (int64_t)sptr[s] + 32 * k + lane;
-                if (k < len) {
-                    cols[pos] = A.indices[A.indptr[r] + k];
-                    p->csr_to_sell[A.indptr[r] + k] = pos;
-                } else {
-                    cols[pos] = r < A.n_rows ? std::min(r, A.n_cols - 1) : 0;
-                }
-            }
-        }
-    }
-    CTL_TRY(ctl_upload(h, &p->slice_ptr, sptr.data(), sptr.size()));
-    CTL_TRY(ctl_upload(h, &p->cols, cols.data(), cols.size()));
-    out = p;
-    return CTL_OK;
-}
-
-int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values,
-                    SellMat &out)
-{
-    std::vector<double> v((size_t)pat->n_stored, 0.0);
-    for (size_t k = 0; k < pat->csr_to_sell.size(); ++k) v[pat->csr_to_sell[k]] = csr_values[k];
-    out.pat = pat;
-    CTL_TRY(ctl_upload(h, &out.vals, v.data(), v.size()));
     return CTL_OK;
 }
 
 namespace {
 
-constexpr int ST = 128;
+constexpr int ST = 128;      // threads per CTA of every kernel in this file
+constexpr int SC = 8;        // SELL entries fetched per thread before the first dependent gather
 
-// One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is
-// divergence free; entries are fetched in chunks of SC with all index/value loads issued
-// before the dependent gathers of x (memory-level parallelism instead of a serial
-// load -> gather -> fma chain per entry).
-constexpr int SC = 8;
-__device__ __forceinline__ double sell_row_dot(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
-                                               const double *__restrict__ vals, const double *__restrict__ x,
-                                               int row)
+// ---- a gathered vector on the device
+struct DVec {
+    const double *x, *ghost;
+    int n_own;
+    __device__ __forceinline__ double operator()(int c) const { return halo_gather(x, ghost, n_own, c); }
+};
+
+// One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is divergence free;
+// entries are fetched in chunks of SC with all stream loads issued before the dependent gathers
+// (memory-level parallelism instead of a serial load -> gather -> fma chain per entry).
+template <int FMT, bool STREAM, typename G>
+__device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g)
 {
     const int s = row >> 5, lane = row & 31;
-    const int beg = __ldg(slice_ptr + s) + lane, end = __ldg(slice_ptr + s + 1);
+    const int2 s0 = __ldg(A.sp + s);
+    const int end = __ldg(reinterpret_cast<const int *>(A.sp + s + 1));
     double acc = 0.0;
-    for (int p0 = beg; p0 < end; p0 += 32 * SC) {
+    for (int p0 = s0.x + lane; p0 < end; p0 += 32 * SC) {
+        SfRaw raw[SC];
+#pragma unroll
+        for (int j = 0; j < SC; ++j) {
+            const int p = p0 + 32 * j;
+            if (p < end) raw[j] = sf_load<FMT, STREAM>(A, p);
+        }
         int c[SC];
         double v[SC];
 #pragma unroll
         for (int j = 0; j < SC; ++j) {
             const int p = p0 + 32 * j;
-            const bool ok = p < end;
-            // streamed once per pass: evict-first, so that the 88 MB fine matrix does not flush the
-            // coarse levels and the vectors out of L2 between two uses
-            c[j] = ok ? __ldcs(cols + p) : 0;
-            v[j] = ok ? __ldcs(vals + p) : 0.0;
+            if (p < end) {
+                sf_decode<FMT>(A, raw[j], p, row, s0.y, c[j], v[j]);
+            } else {
+                c[j] = 0;
+                v[j] = 0.0;
+            }
         }
         double xv[SC];
 #pragma unroll
-        for (int j = 0; j < SC; ++j) xv[j] = __ldg(x + c[j]);
+        for (int j = 0; j < SC; ++j) xv[j] = g(c[j]);
 #pragma unroll
         for (int j = 0; j < SC; ++j) acc = fma(v[j], xv[j], acc);
     }
     return acc;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(ST) sell_spmv_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
-                                                      const double *__restrict__ vals, const double *__restrict__ x,
-                                                      const double *b, double *y, int n_rows)
+// format known only at run time (kernels that are not hot enough for one instantiation per format)
+template <typename G>
+__device__ __forceinline__ double sell_row_dot_rt(const MatView &A, int row, G g)
 {
-    pdl_sync();
-    const int row = blockIdx.x * ST + threadIdx.x;
-    if (row >= n_rows) return;
-    const double ax = sell_row_dot(slice_ptr, cols, vals, x, row);
-    if (MODE == SELL_ASSIGN) y[row] = ax;
-    else if (MODE == SELL_RESIDUAL) y[row] = b[row] - ax;
-    else if (MODE == SELL_ADD) y[row] += ax;
-    else y[row] -= ax;
-}
-
-__global__ void __launch_bounds__(ST) sell_cheb_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
-                                                      const double *__restrict__ vals, const double *__restrict__ dinv,
-                                                      const double *__restrict__ b, const double *p_prev,
-                                                      const double *__restrict__ p_cur, double *out, double a,
-                                                      double bq, double c, int n_rows)
-{
-    pdl_sync();
-    const int row = blockIdx.x * ST + threadIdx.x;
-    if (row >= n_rows) return;
-    const double ax = sell_row_dot(slice_ptr, cols, vals, p_cur, row);
-    double r = bq * p_cur[row] + c * dinv[row] * (b[row] - ax);
-    if (a != 0.0) r = fma(a, p_prev[row], r);
-    out[row] = r;
-}
-
-__global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
-                                                       double *__restrict__ out, double c, int n)
-{
-    pdl_sync();
-    const int i = blockIdx.x * ST + threadIdx.x;
-    if (i < n) out[i] = c * dinv[i] * b[i];
-}
-
-// one warp per row of a small dense matrix
-__global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
-                                                       double *__restrict__ y, int n)
-{
-    pdl_sync();
-    const int row = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    double acc = 0.0;
-    for (int j = lane; j < n; j += 32) acc = fma(A[(size_t)row * n + j], b[j], acc);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[row] = acc;
-}
-
-__global__ void __launch_bounds__(ST) sell_spmv2_kernel(const int *__restrict__ slice_ptr, const int *__restrict__ cols,
-                                                       const double *__restrict__ v1, const double *__restrict__ v2,
-                                                       const double *__restrict__ x1, const double *__restrict__ x2,
-                                                       const double *__restrict__ x3, double *__restrict__ y,
-                                                       double alpha, double beta, int n_rows)
-{
-    pdl_sync();
-    const int row = blockIdx.x * ST + threadIdx.x;
-    if (row >= n_rows) return;
-    const int s = row >> 5, lane = row & 31;
-    const int beg = __ldg(slice_ptr + s), end = __ldg(slice_ptr + s + 1);
-    double acc1 = 0.0, acc2 = 0.0;
-    for (int p = beg + lane; p < end; p += 32) {
-        const int c = __ldcs(cols + p);
-        double xa = __ldg(x1 + c);
-        if (x2) xa += __ldg(x2 + c);
-        acc1 = fma(__ldcs(v1 + p), xa, acc1);
-        if (x3) acc2 = fma(__ldcs(v2 + p), __ldg(x3 + c), acc2);
+    switch (A.fmt) {
+    case FMT_F64: return sell_row_dot<FMT_F64, false>(A, row, g);
+    case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g);
+    case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g);
+    case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g);
+    default: return sell_row_dot<FMT_DICT8, false>(A, row, g);
     }
-    y[row] = alpha * acc1 + beta * acc2;
 }
 
-// ---- CSR-vector variants: T lanes per row, shuffle reduction
-// STREAM: the matrix is large and read once per pass (fine-level restriction): evict-first loads
-template <int T, bool STREAM>
-__device__ __forceinline__ double csr_row_dot(const int *__restrict__ ptr, const int *__restrict__ cols,
-                                              const double *__restrict__ vals, const double *__restrict__ x,
-                                              int row, int lane)
+// T lanes of a warp share one CSR row; the result is valid on every lane of the group.  A lane fetches its
+// entries in chunks of CU with the stream loads issued before the dependent gathers (the rows of the restrictions
+// and of R A are long: a serial load -> gather chain per entry is what these latency-bound kernels cannot afford).
+constexpr int CU = 4;
+template <int T, int FMT, bool STREAM, typename G>
+__device__ __forceinline__ double csrv_row_dot_f(const MatView &A, int row, int sub, G g)
 {
-    const int beg = __ldg(ptr + row), end = __ldg(ptr + row + 1);
+    const int beg = __ldg(A.ptr + row), end = __ldg(A.ptr + row + 1);
+    const int base = (FMT == FMT_F64) ? 0 : __ldg(A.rbase + row);
     double acc = 0.0;
-    for (int p = beg + lane; p < end; p += T) {
-        const int c = STREAM ? __ldcs(cols + p) : __ldg(cols + p);
-        const double v = STREAM ? __ldcs(vals + p) : __ldg(vals + p);
-        acc = fma(v, __ldg(x + c), acc);
+    for (int p0 = beg + sub; p0 < end; p0 += CU * T) {
+        SfRaw raw[CU];
+#pragma unroll
+        for (int j = 0; j < CU; ++j)
+            if (p0 + j * T < end) raw[j] = sf_load<FMT, STREAM>(A, p0 + j * T);
+        int c[CU];
+        double v[CU];
+#pragma unroll
+        for (int j = 0; j < CU; ++j) {
+            if (p0 + j * T < end) {
+                sf_decode<FMT>(A, raw[j], p0 + j * T, row, base, c[j], v[j]);
+            } else {
+                c[j] = 0;
+                v[j] = 0.0;
+            }
+        }
+        double xv[CU];
+#pragma unroll
+        for (int j = 0; j < CU; ++j) xv[j] = g(c[j]);
+#pragma unroll
+        for (int j = 0; j < CU; ++j) acc = fma(v[j], xv[j], acc);
     }
 #pragma unroll
     for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
     return acc;
 }
 
-template <int MODE, int T, bool STREAM>
-__global__ void __launch_bounds__(ST) csrv_spmv_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
-                                                      const double *__restrict__ vals, const double *__restrict__ x,
-                                                      const double *b, double *y, int n_rows)
+template <int T, bool STREAM, typename G>
+__device__ __forceinline__ double csrv_row_dot(const MatView &A, int row, int sub, G g)
 {
-    pdl_sync();
-    const int t = blockIdx.x * ST + threadIdx.x;
-    const int row = t / T, lane = t % T;
-    const int r = row < n_rows ? row : n_rows - 1;       // whole warp takes part in the shuffles
-    const double ax = csr_row_dot<T, STREAM>(ptr, cols, vals, x, r, lane);
-    if (row >= n_rows || lane != 0) return;
-    if (MODE == SELL_ASSIGN) y[row] = ax;
-    else if (MODE == SELL_RESIDUAL) y[row] = b[row] - ax;
-    else if (MODE == SELL_ADD) y[row] += ax;
-    else y[row] -= ax;
+    if (A.fmt == FMT_F64) return csrv_row_dot_f<T, FMT_F64, STREAM>(A, row, sub, g);
+    if (A.fmt == FMT_D16) return csrv_row_dot_f<T, FMT_D16, STREAM>(A, row, sub, g);
+    return csrv_row_dot_f<T, FMT_PK, STREAM>(A, row, sub, g);
 }
 
-template <int T>
-__global__ void __launch_bounds__(ST) csrv_cheb_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
-                                                      const double *__restrict__ vals, const double *__restrict__ dinv,
-                                                      const double *__restrict__ b, const double *p_prev,
-                                                      const double *__restrict__ p_cur, double *out, double a,
-                                                      double bq, double c, int n_rows)
+// Row assignment shared by every kernel: the push CTAs (halo.cuh) come first and compute the listed boundary
+// rows, one chunk of <= 32 rows per warp; the regular CTAs compute ST / T consecutive rows each.  f(row) is
+// evaluated by all T lanes of a row's group and returns the value to store in out[row].
+template <int T, typename F>
+__device__ __forceinline__ void run_rows(int n_rows, const HaloWait &w0, const HaloWait &w1, const HaloPush &push,
+                                         double *out, F f)
 {
-    pdl_sync();
-    const int t = blockIdx.x * ST + threadIdx.x;
-    const int row = t / T, lane = t % T;
-    const int r = row < n_rows ? row : n_rows - 1;
-    const double ax = csr_row_dot<T, false>(ptr, cols, vals, p_cur, r, lane);
-    if (row >= n_rows || lane != 0) return;
-    double v = bq * p_cur[row] + c * dinv[row] * (b[row] - ax);
-    if (a != 0.0) v = fma(a, p_prev[row], v);
-    out[row] = v;
-}
-
-template <int T, bool STREAM>
-void launch_csrv_spmv_s(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
-{
-    const int n = A.pat->n_rows, blocks = ceil_div((int64_t)n * T, ST);
-    switch (mode) {
-    case SELL_ASSIGN: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ASSIGN, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_RESIDUAL, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    case SELL_ADD: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_ADD, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    default: pdl_launch(h, blocks, ST, csrv_spmv_kernel<SELL_SUB, T, STREAM>, A.csr_ptr, A.csr_cols, A.csr_vals, x, b, y, n); break;
-    }
-}
-
-template <int T>
-void launch_csrv_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
-{
-    // matrices above 32 MB (fine-level restriction) stream through L2 with evict-first
-    if (A.pat->nnz * 12 > (32ll << 20)) launch_csrv_spmv_s<T, true>(h, A, x, y, b, mode);
-    else launch_csrv_spmv_s<T, false>(h, A, x, y, b, mode);
-}
-
-}  // namespace
-
-int sell_spmv(ctl_handle_s *h, const SellMat &A, const double *x, double *y, const double *b, int mode)
-{
-    if (h->recorder) {
-        CTL_CHECK(A.lanes > 0, CTL_ERR_STATE, "fused tail: matrix is not in CSR form");
-        FusedOp op{};
-        op.type = FOP_SPMV; op.n = A.pat->n_rows; op.lanes = A.lanes; op.mode = mode;
-        op.ptr = A.csr_ptr; op.cols = A.csr_cols; op.vals = A.csr_vals;
-        op.cur = x; op.b = b; op.out = y;
-        h->recorder->host.push_back(op);
-        return CTL_OK;
-    }
-    const SellPattern &p = *A.pat;
-    const int blocks = ceil_div(p.n_rows, ST);
-    if (blocks == 0) return CTL_OK;
-    if (A.lanes) {
-        if (A.lanes == 2) launch_csrv_spmv<2>(h, A, x, y, b, mode);
-        else if (A.lanes == 4) launch_csrv_spmv<4>(h, A, x, y, b, mode);
-        else if (A.lanes == 8) launch_csrv_spmv<8>(h, A, x, y, b, mode);
-        else if (A.lanes == 16) launch_csrv_spmv<16>(h, A, x, y, b, mode);
-        else launch_csrv_spmv<32>(h, A, x, y, b, mode);
-        h->launches++;
-        CTL_CUDA(cudaGetLastError());
-        return CTL_OK;
-    }
-    switch (mode) {
-    case SELL_ASSIGN: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_ASSIGN>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    case SELL_RESIDUAL: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_RESIDUAL>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    case SELL_ADD: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_ADD>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    default: pdl_launch(h, blocks, ST, sell_spmv_kernel<SELL_SUB>, p.slice_ptr, p.cols, A.vals, x, b, y, p.n_rows); break;
-    }
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const double *b,
-                   const double *p_prev, const double *p_cur, double *out, double a, double bq, double c)
-{
-    if (h->recorder) {
-        CTL_CHECK(A.lanes > 0, CTL_ERR_STATE, "fused tail: matrix is not in CSR form");
-        FusedOp op{};
-        op.type = FOP_CHEB; op.n = A.pat->n_rows; op.lanes = A.lanes;
-        op.ptr = A.csr_ptr; op.cols = A.csr_cols; op.vals = A.csr_vals;
-        op.dinv = dinv; op.b = b; op.prev = p_prev; op.cur = p_cur; op.out = out;
-        op.a = a; op.bq = bq; op.c = c;
-        h->recorder->host.push_back(op);
-        return CTL_OK;
-    }
-    const SellPattern &p = *A.pat;
-    const int blocks = ceil_div(p.n_rows, ST);
-    if (blocks == 0) return CTL_OK;
-    if (A.lanes) {
-        const int n = p.n_rows;
-        if (A.lanes == 2)
-            pdl_launch(h, ceil_div((int64_t)n * 2, ST), ST, csrv_cheb_kernel<2>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
-        else if (A.lanes == 4)
-            pdl_launch(h, ceil_div((int64_t)n * 4, ST), ST, csrv_cheb_kernel<4>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
-        else if (A.lanes == 8)
-            pdl_launch(h, ceil_div((int64_t)n * 8, ST), ST, csrv_cheb_kernel<8>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
-        else if (A.lanes == 16)
-            pdl_launch(h, ceil_div((int64_t)n * 16, ST), ST, csrv_cheb_kernel<16>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
-        else
-            pdl_launch(h, ceil_div((int64_t)n * 32, ST), ST, csrv_cheb_kernel<32>, A.csr_ptr, A.csr_cols, A.csr_vals, dinv, b, p_prev, p_cur, out, a, bq, c, n);
-        h->launches++;
-        CTL_CUDA(cudaGetLastError());
-        return CTL_OK;
-    }
-    pdl_launch(h, blocks, ST, sell_cheb_kernel, p.slice_ptr, p.cols, A.vals, dinv, b, p_prev, p_cur, out, a,
-                                                   bq, c, p.n_rows);
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n)
-{
-    if (h->recorder) {
-        FusedOp op{};
-        op.type = FOP_DINV_SCALE; op.n = n; op.dinv = dinv; op.b = b; op.out = out; op.c = c;
-        h->recorder->host.push_back(op);
-        return CTL_OK;
-    }
-    if (n == 0) return CTL_OK;
-    pdl_launch(h, ceil_div(n, ST), ST, dinv_scale_kernel, dinv, b, out, c, n);
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
-{
-    if (h->recorder) {
-        FusedOp op{};
-        op.type = FOP_GEMV; op.n = n; op.vals = Ainv; op.b = b; op.out = y;
-        h->recorder->host.push_back(op);
-        return CTL_OK;
-    }
-    if (n == 0) return CTL_OK;
-    pdl_launch(h, ceil_div(n, ST / 32), ST, dense_gemv_kernel, Ainv, b, y, n);
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const double *x1, const double *x2,
-               const double *x3, double *y, double alpha, double beta)
-{
-    const SellPattern &p = *A1.pat;
-    const int blocks = ceil_div(p.n_rows, ST);
-    if (blocks == 0) return CTL_OK;
-    pdl_launch(h, blocks, ST, sell_spmv2_kernel, p.slice_ptr, p.cols, A1.vals, A2.vals, x1, x2, x3, y, alpha,
-                                                    beta, p.n_rows);
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-// ---------------------------------------------------------------------------------------
-// Fused coarse tail.  Below the second AMG level every operation is a few microseconds of
-// dependent L2 round trips on a few thousand rows, and a V-cycle issues about ten of them
-// per level: as separate kernels (even inside a CUDA graph) each costs about 5 us.  The
-// recorded program of the sub-cycle (same primitives, same order, same arithmetic) runs as
-// ONE cooperative kernel with a grid barrier between operations.
-// ---------------------------------------------------------------------------------------
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
-
-namespace {
-
-constexpr int FT = 1024;    // threads per CTA of the fused kernel
-
-template <int T>
-__device__ __forceinline__ void fused_rows(const FusedOp &op, int gtid, int gthreads)
-{
-    const int lane = gtid % T;
-    const int groups = gthreads / T;
-    const int n_pad = (op.n + groups - 1) / groups * groups;      // every thread joins the shuffles
-    for (int row = gtid / T; row < n_pad; row += groups) {
-        const bool live = row < op.n;
-        const int r = live ? row : op.n - 1;
-        const int beg = __ldg(op.ptr + r), end = __ldg(op.ptr + r + 1);
-        double acc = 0.0;
-        for (int p = beg + lane; p < end; p += T) acc = fma(__ldg(op.vals + p), op.cur[__ldg(op.cols + p)], acc);
-#pragma unroll
-        for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
-        if (!live || lane != 0) continue;
-        if (op.type == FOP_CHEB) {
-            double v = op.bq * op.cur[r] + op.c * op.dinv[r] * (op.b[r] - acc);
-            if (op.a != 0.0) v = fma(op.a, op.prev[r], v);
-            op.out[r] = v;
-        } else if (op.mode == SELL_ASSIGN) op.out[r] = acc;
-        else if (op.mode == SELL_RESIDUAL) op.out[r] = op.b[r] - acc;
-        else if (op.mode == SELL_ADD) op.out[r] += acc;
-        else op.out[r] -= acc;
-    }
-}
-
-__device__ __forceinline__ void fused_execute(const FusedOp &op, int gtid, int gthreads)
-{
-    if (op.type == FOP_DINV_SCALE) {
-        for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.c * op.dinv[r] * op.b[r];
-    } else if (op.type == FOP_COPY) {
-        for (int r = gtid; r < op.n; r += gthreads) op.out[r] = op.cur[r];
-    } else if (op.type == FOP_GEMV) {
-        const int lane = gtid & 31, warps = gthreads >> 5;
-        for (int row = gtid >> 5; row < op.n; row += warps) {
-            double acc = 0.0;
-            for (int j = lane; j < op.n; j += 32) acc = fma(__ldg(op.vals + (size_t)row * op.n + j), op.b[j], acc);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) op.out[row] = acc;
+    constexpr int RPC = ST / T;
+    const int lane = threadIdx.x & 31;
+    const int n_pc = (push.n_chunks + ST / 32 - 1) / (ST / 32);
+    if ((int)blockIdx.x < n_pc) {
+        halo_wait(w0, -1, -1);
+        halo_wait(w1, -1, -1);
+        const int ci = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
+        if (ci >= push.n_chunks) return;
+        const PushChunk ch = push.chunks[ci];
+#pragma unroll 1
+        for (int pass = 0; pass < T; ++pass) {
+            const int idx = pass * (32 / T) + lane / T;
+            const bool live = idx < ch.count;
+            const int row = push.rows[ch.start + (live ? idx : 0)];
+            const double v = f(row);
+            if (live && (lane % T) == 0) {
+                out[row] = v;
+                for (int d = 0; d < ch.n_dst; ++d) {
+                    const PushDst t = push.dsts[ch.dst_begin + d];
+                    t.base[(long long)push.slot * t.stride + t.pos[idx]] = v;
+                }
+            }
         }
+        halo_push_publish(push, ch, lane);
+        return;
+    }
+    const int r0 = ((int)blockIdx.x - n_pc) * RPC;
+    const int r1 = min(r0 + RPC, n_rows);
+    halo_wait(w0, r0, r1);
+    halo_wait(w1, r0, r1);
+    const int row = r0 + (int)threadIdx.x / T;
+    if (T == 1) {
+        if (row < n_rows) out[row] = f(row);
     } else {
-        switch (op.lanes) {
-        case 2: fused_rows<2>(op, gtid, gthreads); break;
-        case 4: fused_rows<4>(op, gtid, gthreads); break;
-        case 8: fused_rows<8>(op, gtid, gthreads); break;
-        case 16: fused_rows<16>(op, gtid, gthreads); break;
-        default: fused_rows<32>(op, gtid, gthreads); break;
-        }
+        const bool live = row < n_rows;
+        const double v = f(live ? row : n_rows - 1);
+        if (live && (threadIdx.x % T) == 0) out[row] = v;
     }
 }
 
-__global__ void __launch_bounds__(FT) fused_tail_kernel(const FusedOp *__restrict__ ops, int n_ops)
+// kernel-side modes: y = A x | b - A x | b + sign A x (ADD / SUB arrive as b = y)
+__device__ __forceinline__ double apply_mode(int mode, double ax, const double *b, int row)
 {
-    cg::grid_group grid = cg::this_grid();
-    const int gtid = blockIdx.x * FT + threadIdx.x;
-    const int gthreads = gridDim.x * FT;
-    for (int i = 0; i < n_ops; ++i) {
-        const FusedOp op = ops[i];
-        fused_execute(op, gtid, gthreads);
-        grid.sync();
-    }
+    if (mode == SELL_ASSIGN) return ax;
+    if (mode == SELL_RESIDUAL) return b[row] - ax;
+    return b[row] + ax;      // SELL_BPLUS
 }
 
-// The same program on ONE thread-block cluster: the operations of the small levels (<= 20 k rows,
-// matrices resident in L2) need a few thousand threads, and a cluster barrier costs a fraction of a
-// grid barrier or of a kernel boundary.
-__global__ void __launch_bounds__(FT) fused_cluster_kernel(const FusedOp *__restrict__ ops, int n_ops)
+// ---------------------------------------------------------------- SELL kernels
+template <int FMT, bool STREAM>
+__global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloWait w, const double *b,
+                                                      double *y, int mode, double sign, const HaloPush push)
 {
-    cg::cluster_group cl = cg::this_cluster();
-    const int gtid = cl.block_rank() * FT + threadIdx.x;
-    const int gthreads = cl.num_blocks() * FT;
-    for (int i = 0; i < n_ops; ++i) {
-        const FusedOp op = ops[i];
-        fused_execute(op, gtid, gthreads);
-        __threadfence();
-        cl.sync();
-    }
+    pdl_sync();
+    run_rows<1>(A.n_rows, w, HaloWait(), push, y, [&](int row) {
+        const double ax = sign * sell_row_dot<FMT, STREAM>(A, row, x);
+        return apply_mode(mode, ax, b, row);
+    });
 }
+
+template <int FMT, bool STREAM>
+__global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
+                                                      const double *__restrict__ b, const double *p_prev, const DVec p_cur,
+                                                      const HaloWait w, double *out, double a, double bq, double c,
+                                                      double prev_scale, const HaloPush push)
+{
+    pdl_sync();
+    run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
+        const double ax = sell_row_dot<FMT, STREAM>(A, row, p_cur);
+        const double di = dinv[row], bi = b[row];
+        double r = bq * p_cur.x[row] + c * di * (bi - ax);
+        if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
+        else if (a != 0.0) r = fma(a, p_prev[row], r);
+        return r;
+    });
+}
+
+template <int FMT, bool STREAM>
+__global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloWait w,
+                                                        double *out, double s, double wgt, const HaloPush push)
+{
+    pdl_sync();
+    run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
+        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return s * dinv(c) * b(c); });
+        const double di = dinv.x[row], bi = b.x[row];
+        const double p1 = s * di * bi;
+        return wgt * p1 + (wgt * s) * di * (bi - ax);
+    });
+}
+
+__global__ void __launch_bounds__(ST) sell_spmv2_kernel(const MatView A1, const MatView A2, const DVec x1, const DVec x2,
+                                                       const DVec x3, double *y, double alpha, double beta,
+                                                       const HaloWait w, const HaloPush push)
+{
+    pdl_sync();
+    run_rows<1>(A1.n_rows, w, HaloWait(), push, y, [&](int row) {
+        double acc1;
+        if (x2.x) acc1 = sell_row_dot_rt(A1, row, [&](int c) { return x1(c) + x2(c); });
+        else acc1 = sell_row_dot_rt(A1, row, x1);
+        double acc2 = 0.0;
+        if (x3.x) acc2 = sell_row_dot_rt(A2, row, x3);
+        return alpha * acc1 + beta * acc2;
+    });
+}
+
+__global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
+                                                       double *__restrict__ out, double c, int n, const HaloPush push)
+{
+    pdl_sync();
+    run_rows<1>(n, HaloWait(), HaloWait(), push, out, [&](int row) { return c * dinv[row] * b[row]; });
+}
+
+// one warp per row of a small dense matrix
+__global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
+                                                       double *__restrict__ y, int n, const HaloWait w)
+{
+    pdl_sync();
+    halo_wait(w, -1, -1);
+    const int row = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const double *a = A + (size_t)row * n;
+    double acc0 = 0.0, acc1 = 0.0;
+    int j = lane;
+    for (; j + 32 < n; j += 64) {
+        acc0 = fma(__ldg(a + j), b[j], acc0);
+        acc1 = fma(__ldg(a + j + 32), b[j + 32], acc1);
+    }
+    if (j < n) acc0 = fma(__ldg(a + j), b[j], acc0);
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[row] = acc;
+}
+
+// ---------------------------------------------------------------- CSR-vector kernels
+template <int T, bool STREAM>
+__global__ void __launch_bounds__(ST) csrv_spmv_kernel(const MatView A, const DVec x, const HaloWait w, const double *b,
+                                                      double *y, int mode, double sign, const HaloPush push)
+{
+    pdl_sync();
+    const int sub = threadIdx.x % T;
+    run_rows<T>(A.n_rows, w, HaloWait(), push, y, [&](int row) {
+        const double ax = sign * csrv_row_dot<T, STREAM>(A, row, sub, x);
+        return apply_mode(mode, ax, b, row);
+    });
+}
+
+template <int T>
+__global__ void __launch_bounds__(ST) csrv_cheb_kernel(const MatView A, const double *__restrict__ dinv,
+                                                      const double *__restrict__ b, const double *p_prev, const DVec p_cur,
+                                                      const HaloWait w, double *out, double a, double bq, double c,
+                                                      double prev_scale, const HaloPush push)
+{
+    pdl_sync();
+    const int sub = threadIdx.x % T;
+    run_rows<T>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
+        const double ax = csrv_row_dot<T, false>(A, row, sub, p_cur);
+        const double di = dinv[row], bi = b[row];
+        double r = bq * p_cur.x[row] + c * di * (bi - ax);
+        if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
+        else if (a != 0.0) r = fma(a, p_prev[row], r);
+        return r;
+    });
+}
+
+template <int T>
+__global__ void __launch_bounds__(ST) csrv_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloWait w,
+                                                        double *out, double s, double wgt, const HaloPush push)
+{
+    pdl_sync();
+    const int sub = threadIdx.x % T;
+    run_rows<T>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
+        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int c) { return s * dinv(c) * b(c); });
+        const double di = dinv.x[row], bi = b.x[row];
+        const double p1 = s * di * bi;
+        return wgt * p1 + (wgt * s) * di * (bi - ax);
+    });
+}
+
+// y = R b - RA x: the residual of a coarse level restricted without storing it
+template <int T>
+__global__ void __launch_bounds__(ST) csrv_rr_kernel(const MatView R, const MatView RA, const DVec b, const DVec x,
+                                                    const HaloWait wb, const HaloWait wx, double *y, const HaloPush push)
+{
+    pdl_sync();
+    const int sub = threadIdx.x % T;
+    run_rows<T>(R.n_rows, wb, wx, push, y, [&](int row) {
+        const double rb = csrv_row_dot<T, false>(R, row, sub, b);
+        const double rax = csrv_row_dot<T, false>(RA, row, sub, x);
+        return rb - rax;
+    });
+}
+
+DVec dvec(const GVec &g, const MatView &A)
+{
+    DVec d;
+    d.x = g.x;
+    d.ghost = g.ghost;
+    d.n_own = A.n_own;
+    return d;
+}
+
+int grid_for(int n_rows, int T, const HaloPush &push) { return ceil_div((int64_t)n_rows * T, ST) + halo_push_ctas(push, ST); }
+
+#define SELL_DISPATCH(KERNEL, A, ...)                                                                       \
+    do {                                                                                                    \
+        const int grid__ = grid_for((A).pat->n_rows, 1, push);                                              \
+        if (grid__ == 0) return CTL_OK;                                                                     \
+        const bool st__ = (A).stream;                                                                       \
+        switch ((A).fmt) {                                                                                  \
+        case FMT_F64:                                                                                       \
+            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_F64, true>, __VA_ARGS__);                        \
+            else pdl_launch(h, grid__, ST, KERNEL<FMT_F64, false>, __VA_ARGS__);                            \
+            break;                                                                                          \
+        case FMT_D16:                                                                                       \
+            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_D16, true>, __VA_ARGS__);                        \
+            else pdl_launch(h, grid__, ST, KERNEL<FMT_D16, false>, __VA_ARGS__);                            \
+            break;                                                                                          \
+        case FMT_PK:                                                                                        \
+            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_PK, true>, __VA_ARGS__);                         \
+            else pdl_launch(h, grid__, ST, KERNEL<FMT_PK, false>, __VA_ARGS__);                             \
+            break;                                                                                          \
+        case FMT_DICT16:                                                                                    \
+            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_DICT16, true>, __VA_ARGS__);                     \
+            else pdl_launch(h, grid__, ST, KERNEL<FMT_DICT16, false>, __VA_ARGS__);                         \
+            break;                                                                                          \
+        default:                                                                                            \
+            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_DICT8, true>, __VA_ARGS__);                      \
+            else pdl_launch(h, grid__, ST, KERNEL<FMT_DICT8, false>, __VA_ARGS__);                          \
+            break;                                                                                          \
+        }                                                                                                   \
+    } while (0)
+
+#define CSRV_DISPATCH(KERNEL, A, ...)                                                                       \
+    do {                                                                                                    \
+        const int grid__ = grid_for((A).pat->n_rows, (A).lanes, push);                                      \
+        if (grid__ == 0) return CTL_OK;                                                                     \
+        if ((A).lanes == 4) pdl_launch(h, grid__, ST, KERNEL<4>, __VA_ARGS__);                              \
+        else if ((A).lanes == 8) pdl_launch(h, grid__, ST, KERNEL<8>, __VA_ARGS__);                         \
+        else pdl_launch(h, grid__, ST, KERNEL<16>, __VA_ARGS__);                                            \
+    } while (0)
 
 }  // namespace
+
+int sell_spmv(ctl_handle_s *h, const SellMat &A, const GVec &x, double *y, const double *b, int mode, const HaloPush &push)
+{
+    // y (+)= / -= A x: expressed as y = b +/- A x with b = y; aliasing is not idempotent, so a pushing launch
+    // (whose boundary rows are computed twice) must not use it
+    double sign = 1.0;
+    int kmode = mode;
+    if (mode == SELL_ADD || mode == SELL_SUB) {
+        b = y;
+        kmode = SELL_BPLUS;
+        sign = mode == SELL_SUB ? -1.0 : 1.0;
+    }
+    CTL_CHECK(kmode == SELL_ASSIGN || b != nullptr, CTL_ERR_ARG, "sell_spmv: this mode needs b");
+    CTL_CHECK(push.n_chunks == 0 || b != y, CTL_ERR_STATE, "sell_spmv: an in-place product cannot push its boundary rows");
+    const MatView V = A.view();
+    const DVec dx = dvec(x, V);
+    if (A.lanes) {
+        const int grid = grid_for(A.pat->n_rows, A.lanes, push);
+        if (grid == 0) return CTL_OK;
+#define CSRV_SPMV(T)                                                                                                 \
+    do {                                                                                                             \
+        if (A.stream) pdl_launch(h, grid, ST, csrv_spmv_kernel<T, true>, V, dx, x.wait, b, y, kmode, sign, push);    \
+        else pdl_launch(h, grid, ST, csrv_spmv_kernel<T, false>, V, dx, x.wait, b, y, kmode, sign, push);            \
+    } while (0)
+        if (A.lanes == 4) CSRV_SPMV(4);
+        else if (A.lanes == 8) CSRV_SPMV(8);
+        else CSRV_SPMV(16);
+#undef CSRV_SPMV
+    } else {
+        SELL_DISPATCH(sell_spmv_kernel, A, V, dx, x.wait, b, y, kmode, sign, push);
+    }
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const double *b, const double *p_prev,
+                   const GVec &p_cur, double *out, double a, double bq, double c, double prev_scale, const HaloPush &push)
+{
+    CTL_CHECK(push.n_chunks == 0 || (out != p_prev && out != p_cur.x), CTL_ERR_STATE,
+              "sell_cheb_step: a pushing step must not overwrite its inputs");
+    const MatView V = A.view();
+    const DVec dx = dvec(p_cur, V);
+    if (A.lanes) CSRV_DISPATCH(csrv_cheb_kernel, A, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
+    else SELL_DISPATCH(sell_cheb_kernel, A, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int sell_cheb_first2(ctl_handle_s *h, const SellMat &A, const GVec &dinv, const GVec &b, double *out, double s, double w,
+                     const HaloPush &push)
+{
+    const MatView V = A.view();
+    const DVec dd = dvec(dinv, V), db = dvec(b, V);
+    if (A.lanes) CSRV_DISPATCH(csrv_first2_kernel, A, V, dd, db, b.wait, out, s, w, push);
+    else SELL_DISPATCH(sell_first2_kernel, A, V, dd, db, b.wait, out, s, w, push);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n, const HaloPush &push)
+{
+    const int grid = grid_for(n, 1, push);
+    if (grid == 0) return CTL_OK;
+    pdl_launch(h, grid, ST, dinv_scale_kernel, dinv, b, out, c, n, push);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, const HaloWait &wait)
+{
+    if (n == 0) return CTL_OK;
+    pdl_launch(h, ceil_div(n, ST / 32), ST, dense_gemv_kernel, Ainv, b, y, n, wait);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec &x1, const GVec &x2, const GVec &x3,
+               double *y, double alpha, double beta, const HaloPush &push)
+{
+    CTL_CHECK(A1.lanes == 0 && A2.lanes == 0, CTL_ERR_STATE, "sell_spmv2: SELL matrices only");
+    const int grid = grid_for(A1.pat->n_rows, 1, push);
+    if (grid == 0) return CTL_OK;
+    const MatView V1 = A1.view(), V2 = A2.view();
+    // at most one of the gathered vectors arrives with this launch (the others were completed earlier)
+    HaloWait w = x1.wait;
+    if (x2.wait.n_flags) w = x2.wait;
+    if (x3.wait.n_flags) w = x3.wait;
+    pdl_launch(h, grid, ST, sell_spmv2_kernel, V1, V2, dvec(x1, V1), dvec(x2, V1), dvec(x3, V2), y, alpha, beta, w, push);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
+
+int csrv_restrict_residual(ctl_handle_s *h, const SellMat &R, const SellMat &RA, const GVec &b, const GVec &x, double *y,
+                           const HaloPush &push)
+{
+    CTL_CHECK(R.lanes > 0 && RA.lanes > 0, CTL_ERR_STATE, "csrv_restrict_residual: CSR-vector matrices only");
+    const MatView VR = R.view(), VA = RA.view();
+    const DVec db = dvec(b, VR), dx = dvec(x, VA);
+    const int lanes = R.lanes;
+    const int grid = grid_for(R.pat->n_rows, lanes, push);
+    if (grid == 0) return CTL_OK;
+    if (lanes == 4) pdl_launch(h, grid, ST, csrv_rr_kernel<4>, VR, VA, db, dx, b.wait, x.wait, y, push);
+    else if (lanes == 8) pdl_launch(h, grid, ST, csrv_rr_kernel<8>, VR, VA, db, dx, b.wait, x.wait, y, push);
+    else pdl_launch(h, grid, ST, csrv_rr_kernel<16>, VR, VA, db, dx, b.wait, x.wait, y, push);
+    h->launches++;
+    CTL_CUDA(cudaGetLastError());
+    return CTL_OK;
+}
 
 int vec_copy_n(ctl_handle_s *h, double *dst, const double *src, int n)
 {
-    if (h->recorder) {
-        FusedOp op{};
-        op.type = FOP_COPY; op.n = n; op.cur = src; op.out = dst;
-        h->recorder->host.push_back(op);
-        return CTL_OK;
-    }
     CTL_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     return CTL_OK;
-}
-
-int fused_upload(ctl_handle_s *h, FusedProgram &p)
-{
-    p.n_ops = (int)p.host.size();
-    if (p.n_ops == 0) return CTL_OK;
-    CTL_CUDA(cudaMalloc((void **)&p.dev, p.host.size() * sizeof(FusedOp)));
-    CTL_CUDA(cudaMemcpyAsync(p.dev, p.host.data(), p.host.size() * sizeof(FusedOp), cudaMemcpyHostToDevice, h->stream));
-    CTL_CUDA(cudaStreamSynchronize(h->stream));
-    return CTL_OK;
-}
-
-void fused_free(FusedProgram &p)
-{
-    cudaFree(p.dev);
-    p.dev = nullptr;
-    p.n_ops = 0;
-    p.host.clear();
-}
-
-int fused_run(ctl_handle_s *h, const FusedProgram &p)
-{
-    if (p.n_ops == 0) return CTL_OK;
-    static int n_sm = 0;
-    if (!n_sm) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->cfg.device);
-    const FusedOp *ops = p.dev;
-    int n_ops = p.n_ops;
-    cudaLaunchConfig_t cfg{};
-    cfg.blockDim = dim3(FT);
-    cfg.stream = h->stream;
-    cudaLaunchAttribute at;
-    cfg.attrs = &at;
-    cfg.numAttrs = 1;
-    if (p.cluster > 0) {
-        cfg.gridDim = dim3(p.cluster);
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = p.cluster;
-        at.val.clusterDim.y = 1;
-        at.val.clusterDim.z = 1;
-        CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_cluster_kernel, ops, n_ops));
-    } else {
-        static int n_cta = 0;
-        if (!n_cta) {
-            n_cta = 32;
-            if (const char *e = getenv("CTL_FUSED_CTAS")) n_cta = std::max(1, std::min(n_sm, atoi(e)));
-        }
-        cfg.gridDim = dim3(n_cta);
-        at.id = cudaLaunchAttributeCooperative;
-        at.val.cooperative = 1;
-        CTL_CUDA(cudaLaunchKernelEx(&cfg, fused_tail_kernel, ops, n_ops));
-    }
-    h->launches++;
-    return CTL_OK;
-}
-
-// largest cluster (16, else 8) of FT-thread CTAs the device can co-schedule for the fused kernel
-int fused_cluster_size(ctl_handle_s *h)
-{
-    for (int want : {16, 8}) {
-        if (want > 8 &&
-            cudaFuncSetAttribute(fused_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-            cudaGetLastError();
-            continue;
-        }
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(want);
-        cfg.blockDim = dim3(FT);
-        cudaLaunchAttribute at;
-        at.id = cudaLaunchAttributeClusterDimension;
-        at.val.clusterDim.x = want;
-        at.val.clusterDim.y = 1;
-        at.val.clusterDim.z = 1;
-        cfg.attrs = &at;
-        cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, fused_cluster_kernel, &cfg) == cudaSuccess && n > 0) return want;
-        cudaGetLastError();
-    }
-    return 0;
 }

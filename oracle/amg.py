@@ -42,7 +42,7 @@ except Exception:                          # pragma: no cover
         return f
 
 
-DEFAULTS = dict(theta=0.08, theta_decay=0.5, max_levels=10, coarse_max=600, nu=3, nu_fine=0, lo=0.25, hi=1.0, cycles=3,
+DEFAULTS = dict(theta=0.08, theta_decay=0.5, max_levels=10, coarse_max=2500, nu=3, nu_fine=0, lo=0.25, hi=1.0, cycles=3,
                 acc_lo=0.0, acc_hi=1.0, coarse="inverse")
 
 

@@ -10,10 +10,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"), reason="needs nvcc")
-@pytest.mark.parametrize("name,expect", [("amg_host_check", "coarse inverse residual"), ("kkt_record_check", "max diff")])
+@pytest.mark.parametrize("name,expect", [("amg_host_check", "coarse inverse residual"),
+                                         ("sell_format_check", "sell format check: 0 failures"),
+                                         ("halo_geom_check", "halo geometry check: 0 failures")])
 def test_host_native_checks(tmp_path, name, expect):
-    """amg_host_check: pivoted dense inverse + one complete hierarchy; kkt_record_check: the block records of the
-    TMA-fed KKT-apply variants read back the way the kernels read them (csrc/kkt_plan.h)."""
+    """amg_host_check: pivoted dense inverse + one complete hierarchy; sell_format_check: every exact matrix format
+    read back with the kernels' own decode functions (csrc/sell_format.h); halo_geom_check: all ranks of a partition
+    played in one process, distributed V-cycle through the exchange geometry against the serial cycle (csrc/halo_geom.h)."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     exe = str(tmp_path / name)
     subprocess.check_call([nvcc, "-std=c++17", "-O2", "-x", "cu", "-w", "-I", os.path.join(ROOT, "control_b200", "csrc"),
