@@ -7,7 +7,8 @@
 // Launches per V(nu, nu) cycle and level (the sweeps are bound by the number of dependent launches):
 //   pre-smoothing    zero guess: the first TWO Chebyshev steps are one kernel (p1 = s D^-1 b is formed on the fly
 //                    and never stored), so nu = 3 costs 2 launches; non-zero guess: nu launches
-//   residual + restriction   level 0: two kernels; levels >= 1: one kernel, R b - (R A) x
+//   residual + restriction   two kernels (restricting b - A x in ONE kernel through a precomputed R A was measured:
+//                    its rows are so long that the kernel costs more than the two it replaces, 30 us against 9 + 7)
 //   coarse solve     dense inverse (one GEMV) below coarse_max rows
 //   prolongation     one kernel, out of place (x' = x + P x_c) so that every kernel is idempotent: on several
 //                    GPUs the boundary rows of a product are computed twice (halo.cuh)
@@ -97,7 +98,6 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
             if (l + 1 < nl) {
                 CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
                 CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
-                if (!Lh.RA.indptr.empty() && Ld.R.lanes > 0) CTL_TRY(sell_from_csr(h, Lh.RA, Ld.RA, Ld.R.lanes));
             } else if (!Lh.Ainv.empty()) {
                 CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
             }
@@ -122,7 +122,6 @@ void amg_free(AmgHierarchyDev &H)
         sell_free(L.A);
         sell_free(L.P);
         sell_free(L.R);
-        sell_free(L.RA);
         cudaFree(L.dinv);
         cudaFree(L.x);
         cudaFree(L.b);
@@ -221,11 +220,7 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const GVec &b, dou
     } else if (C.pb) {
         cpush = halo_push(C.pb);
     }
-    if (L.RA.valid()) {
-        const GVec gb = L.pb ? GVec(b.x, halo_ghost(L.pb), HaloWait()) : GVec(b.x);
-        const GVec gx = gathered(L, L.px, x, L.RA);
-        CTL_TRY(csrv_restrict_residual(h, L.R, L.RA, gb, gx, cb, cpush));
-    } else {
+    {
         // (the gathered vector is described BEFORE the next exchange of its plan is drawn: both read the plan's counter)
         HaloPlan *plan_r = L.pr ? L.pr : L.px;
         const GVec gx = gathered(L, L.px, x, L.A);

@@ -9,7 +9,6 @@ struct AmgLevelDev {
     bool distributed = false;
     double rho = 0.0;
     SellMat A, P, R;
-    SellMat RA;                           // R A of the NEXT coarser restriction: levels >= 1 restrict b - A x in one kernel
     double *dinv = nullptr;               // n + n_ghost (the ghost part is filled once at setup)
     double *x = nullptr, *b = nullptr;    // owned on levels >= 1 (level 0 uses the caller's)
     double *r = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;   // residual / smoother work vectors

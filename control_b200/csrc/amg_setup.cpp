@@ -372,10 +372,6 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         timer.lap("A*P", lvl);
         csr_matmat(L.R, AP, Ac, threads);
         timer.lap("R*(AP)", lvl);
-        if (lvl >= 1 && p.fuse_rr) {
-            csr_matmat(L.R, A, L.RA, threads);
-            timer.lap("R*A", lvl);
-        }
         next = std::move(Ac);
         cand = norms;
     }

@@ -16,7 +16,6 @@ struct AmgParams {
     int max_levels = 10;
     int coarse_max = 2500;  // dense inverse below this size: ONE 2205^2 GEMV (39 MB, L2-resident) at C2 instead of two
                             // more levels of ~10 dependent launches each (round 2; was 600)
-    int fuse_rr = 1;        // levels >= 1: restricted residual in one kernel through R A (0: residual, then restriction)
     int nu = 3;          // smoother degree on levels >= 1
     int nu_fine = 0;     // smoother degree on level 0 (0 = nu)
     double lo = 0.25, hi = 1.0;
@@ -31,7 +30,6 @@ struct AmgLevelHost {
     double rho = 0.0;          // Gershgorin bound of D^-1 A
     std::vector<int> agg;      // aggregate id per row (-1 = not aggregated); empty on the last level
     HostCSR P, R;              // prolongation (n x n_coarse) and R = P^T; empty on the last level
-    HostCSR RA;                // R A (levels >= 1 with a coarser level): the residual is restricted as R b - (R A) x
     std::vector<double> Ainv;  // dense inverse, row-major (last level, n <= 4096)
 };
 

@@ -360,10 +360,6 @@ int amg_build_distributed(ctl_handle_s *h, const AmgParams &p, const std::shared
             finish_matrix(Dl.P, Dl.P_own, Ld.P);
             CTL_TRY(sell_from_csr(h, Dl.R, Ld.R));
             finish_matrix(Dl.R, Dl.R_own, Ld.R);
-            if (!Dl.RA.indptr.empty() && Ld.R.lanes > 0) {
-                CTL_TRY(sell_from_csr(h, Dl.RA, Ld.RA, Ld.R.lanes));
-                finish_matrix(Dl.RA, Dl.R_own, Ld.RA);
-            }
         } else if (!Dl.Ainv.empty()) {
             CTL_TRY(ctl_upload(h, &Ld.Ainv, Dl.Ainv.data(), Dl.Ainv.size()));
         }

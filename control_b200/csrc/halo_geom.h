@@ -197,7 +197,8 @@ HostCSR halo_extract(const HostCSR &G, int n_rows, RowFn global_row, ColFn colma
 // ---------------------------------------------------------------------------------------------------------
 // The hierarchy of one rank: which levels are distributed, the exchange geometry of each vector space, and the
 // local row blocks of every matrix in local numbering.
-//   levels 0 .. L_rep - 1   distributed by rows (level 0: the handle's partition; others: even split)
+//   levels 0 .. L_rep - 1   distributed by rows (level 0: the handle's partition; others: ownership follows the
+//                           aggregates, coarse unknowns renumbered rank after rank)
 //   level  L_rep            the first replicated level: its right-hand side is computed by owners and replicated;
 //                           numbered own rows first, the others in global order behind (= the slot layout)
 //   levels > L_rep          replicated, natural numbering
@@ -205,7 +206,7 @@ HostCSR halo_extract(const HostCSR &G, int n_rows, RowFn global_row, ColFn colma
 struct DistLevel {
     bool distributed = false;
     int n = 0, n_ghost = 0;
-    HostCSR A, P, R, RA;             // local blocks (P, R, RA empty where the hierarchy has none)
+    HostCSR A, P, R;                 // local blocks (P, R empty where the hierarchy has none)
     int A_own = 0, P_own = 0, R_own = 0;      // owned columns of each block's column space (0: all columns are local)
     std::vector<double> dinv;        // own rows, then the ghosts
     std::vector<double> Ainv;        // dense inverse in local numbering (last level)
@@ -219,19 +220,108 @@ struct DistHierarchy {
     std::shared_ptr<HaloGeom> space_r0;      // level-0 residual as the restriction gathers it
 };
 
-inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHost> &host, int rep_min,
+inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHost> &host_in, int rep_min,
                                 const std::shared_ptr<HaloGeom> &mesh_space, DistHierarchy &D)
 {
-    const int nl = (int)host.size();
+    const int nl = (int)host_in.size();
     int L_rep = nl;
     for (int l = 1; l < nl; ++l)
-        if (host[l].A.n_rows < (int64_t)rep_min * world || !host[l].Ainv.empty()) {
+        if (host_in[l].A.n_rows < (int64_t)rep_min * world || !host_in[l].Ainv.empty()) {
             L_rep = l;
             break;
         }
     D.L_rep = L_rep;
-    D.part.resize(nl);
-    for (int l = 0; l < nl; ++l) D.part[l] = halo_even_split(host[l].A.n_rows, world);
+    // Ownership of the coarse levels FOLLOWS the fine level: an aggregate belongs to the rank that owns most of its
+    // members, and the coarse unknowns are renumbered rank after rank (the set-up numbers the aggregates of its
+    // third pass behind all others, so contiguous blocks of the original numbering would scatter a rank's coarse
+    // rows over the whole mesh: long ghost lists, every CTA waiting).  perm[l][old] = new.
+    D.part.assign(nl, std::vector<int>());
+    D.part[0] = halo_even_split(host_in[0].A.n_rows, world);
+    std::vector<std::vector<int>> perm(nl);
+    for (int l = 1; l < nl; ++l) {
+        const int n_l = host_in[l].A.n_rows;
+        if (l > L_rep) {
+            D.part[l] = halo_even_split(n_l, world);      // replicated, natural numbering: the partition is not used
+            continue;
+        }
+        const std::vector<int> &agg = host_in[l - 1].agg;
+        const std::vector<int> &pf = D.part[l - 1];
+        std::vector<int> votes((size_t)n_l * world, 0);
+        for (int i = 0; i < (int)agg.size(); ++i) {
+            if (agg[i] < 0) continue;
+            const int inew = perm[l - 1].empty() ? i : perm[l - 1][i];
+            const int o = (int)(std::upper_bound(pf.begin(), pf.end(), inew) - pf.begin()) - 1;
+            votes[(size_t)agg[i] * world + o]++;
+        }
+        std::vector<int> owner(n_l, 0);
+        D.part[l].assign(world + 1, 0);
+        for (int J = 0; J < n_l; ++J) {
+            int best = 0;
+            for (int r = 1; r < world; ++r)
+                if (votes[(size_t)J * world + r] > votes[(size_t)J * world + best]) best = r;
+            owner[J] = best;
+            D.part[l][best + 1]++;
+        }
+        for (int r = 0; r < world; ++r) D.part[l][r + 1] += D.part[l][r];
+        std::vector<int> next(D.part[l].begin(), D.part[l].end() - 1);
+        perm[l].resize(n_l);
+        for (int J = 0; J < n_l; ++J) perm[l][J] = next[owner[J]]++;
+    }
+    // the hierarchy in the new numbering (levels without a permutation are taken as they are)
+    auto permuted = [](const HostCSR &G, const std::vector<int> &rp, const std::vector<int> &cp) {
+        HostCSR Q;
+        Q.n_rows = G.n_rows;
+        Q.n_cols = G.n_cols;
+        Q.indptr.assign(G.n_rows + 1, 0);
+        for (int r = 0; r < G.n_rows; ++r) Q.indptr[(rp.empty() ? r : rp[r]) + 1] = G.indptr[r + 1] - G.indptr[r];
+        for (int r = 0; r < G.n_rows; ++r) Q.indptr[r + 1] += Q.indptr[r];
+        Q.indices.resize(G.indices.size());
+        Q.values.resize(G.values.size());
+        for (int r = 0; r < G.n_rows; ++r) {
+            int q = Q.indptr[rp.empty() ? r : rp[r]];
+            for (int k = G.indptr[r]; k < G.indptr[r + 1]; ++k, ++q) {
+                Q.indices[q] = cp.empty() ? G.indices[k] : cp[G.indices[k]];
+                Q.values[q] = G.values[k];
+            }
+        }
+        return Q;
+    };
+    std::vector<AmgLevelHost> hostp(nl);
+    for (int l = 0; l < nl; ++l) {
+        const AmgLevelHost &Li = host_in[l];
+        AmgLevelHost &Lo = hostp[l];
+        const std::vector<int> none;
+        const std::vector<int> &pl = perm[l], &pn = (l + 1 < nl) ? perm[l + 1] : none;
+        Lo.rho = Li.rho;
+        if (pl.empty() && pn.empty() && l > 0) {
+            Lo.A = Li.A;
+            Lo.P = Li.P;
+            Lo.R = Li.R;
+            Lo.dinv = Li.dinv;
+            Lo.Ainv = Li.Ainv;
+            continue;
+        }
+        if (l == 0) {      // level 0 keeps its numbering and is read through the handle's mesh pattern: sizes only
+            Lo.A.n_rows = Li.A.n_rows;
+            Lo.A.n_cols = Li.A.n_cols;
+        } else {
+            Lo.A = pl.empty() ? Li.A : permuted(Li.A, pl, pl);
+        }
+        if (l + 1 < nl) {
+            Lo.P = permuted(Li.P, pl, pn);
+            Lo.R = permuted(Li.R, pn, pl);
+        }
+        Lo.dinv.resize(Li.dinv.size());
+        for (size_t i = 0; i < Li.dinv.size(); ++i) Lo.dinv[pl.empty() ? i : pl[i]] = Li.dinv[i];
+        if (!Li.Ainv.empty()) {
+            const int n = Li.A.n_rows;
+            Lo.Ainv.resize(Li.Ainv.size());
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j)
+                    Lo.Ainv[(size_t)(pl.empty() ? i : pl[i]) * n + (pl.empty() ? j : pl[j])] = Li.Ainv[(size_t)i * n + j];
+        }
+    }
+    const std::vector<AmgLevelHost> &host = hostp;
     const std::vector<std::vector<int>> &part = D.part;
     D.levels.assign(nl, DistLevel());
     std::vector<std::shared_ptr<HaloGeom>> space(nl);
@@ -246,7 +336,6 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
         cons.push_back(halo_consumer(host[l - 1].P, part[l - 1]));
         if (l + 1 < nl) {
             cons.push_back(halo_consumer(host[l].R, part[l + 1]));
-            if (!host[l].RA.indptr.empty()) cons.push_back(halo_consumer(host[l].RA, part[l + 1]));
         }
         space[l] = std::make_shared<HaloGeom>();
         halo_geometry(world, me, part[l], cons, false, *space[l]);
@@ -308,7 +397,6 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
                 Ld.R = halo_extract(Lh.R, nr, rrow_of(l), colmap(l), ncols_l);
             }
             Ld.R_own = dist ? Ld.n : 0;
-            if (!Lh.RA.indptr.empty()) Ld.RA = halo_extract(Lh.RA, nr, rrow_of(l), colmap(l), ncols_l);
         } else if (!Lh.Ainv.empty()) {
             const int n = Ld.n;
             Ld.Ainv.resize((size_t)n * n);

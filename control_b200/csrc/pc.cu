@@ -382,7 +382,6 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     st.amg.acc_lo = opts->amg_acc_lo;
     st.amg.acc_hi = opts->amg_acc_hi;
     if (const char *e = getenv("CTL_NO_GRAPH")) st.use_graph = !(e[0] == '1');
-    if (const char *e = getenv("CTL_AMG_RR")) st.amg.fuse_rr = atoi(e) != 0;      // experiment: fused restricted residual
 
     const int N = h->N, nl = h->n_loc, rb = h->row_begin;
     const bool cn = h->cfg.CN != 0;

@@ -23,6 +23,8 @@ void sell_free(SellMat &m)
     cudaFree(m.vdict);
     cudaFree(m.code);
     cudaFree(m.dict);
+    cudaFree(m.sp4);
+    cudaFree(m.stab);
     cudaFree(m.csr_ptr);
     cudaFree(m.csr_cols);
     cudaFree(m.csr_rbase);
@@ -53,6 +55,14 @@ MatView SellMat::view() const
     v.vdict = vdict;
     v.code = code;
     v.dict = dict;
+    v.sp4 = sp4;
+    v.stab = stab;
+    v.ps_off = ps_off;
+    v.ps_w = ps_w;
+    for (int k = 0; k < ps_w && k < 8; ++k) {
+        v.ps_delta[k] = ps[k].delta;
+        v.ps_v[k] = ps[k].v;
+    }
     return v;
 }
 
@@ -60,13 +70,36 @@ int sell_max_fmt()
 {
     static int v = -1;
     if (v < 0) {
-        v = FMT_DICT8;
+        v = FMT_STENCIL;
         if (const char *e = getenv("CTL_SELL_FMT")) {      // experiment / tests: cap the automatic choice
             if (!strcmp(e, "f64")) v = FMT_F64;
             else if (!strcmp(e, "d16")) v = FMT_D16;
             else if (!strcmp(e, "pk")) v = FMT_PK;
             else if (!strcmp(e, "dict16")) v = FMT_DICT16;
+            else if (!strcmp(e, "dict8")) v = FMT_DICT8;
         }
+    }
+    return v;
+}
+
+// cap for the matrices that own their pattern (coarse AMG operators, transfers): CTL_SELL_FMT_COARSE
+static int sell_max_fmt_coarse()
+{
+    static int v = -1;
+    if (v < 0) {
+        // measured at C2 (round 2, profiles/r02_inner_solve_variants.txt): on the Galerkin levels and the transfer
+        // operators the dictionary formats cost more instructions than their bytes save (everything there is
+        // L2-resident and latency bound): inner solve 0.81 ms (dictionaries) / 0.73 (16-bit offsets) / 0.67 (plain)
+        v = FMT_F64;
+        if (const char *e = getenv("CTL_SELL_FMT_COARSE")) {
+            if (!strcmp(e, "f64")) v = FMT_F64;
+            else if (!strcmp(e, "d16")) v = FMT_D16;
+            else if (!strcmp(e, "pk")) v = FMT_PK;
+            else if (!strcmp(e, "dict16")) v = FMT_DICT16;
+            else if (!strcmp(e, "dict8")) v = FMT_DICT8;
+            else if (!strcmp(e, "stencil")) v = FMT_STENCIL;
+        }
+        v = std::min(v, sell_max_fmt());
     }
     return v;
 }
@@ -119,10 +152,19 @@ int sell_build_pattern(ctl_handle_s *h, const HostCSR &A, std::shared_ptr<SellPa
     return CTL_OK;
 }
 
+static int sell_set_values_cap(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values, SellMat &out,
+                               int max_fmt);
+
 int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values, SellMat &out)
 {
+    return sell_set_values_cap(h, pat, csr_values, out, sell_max_fmt());
+}
+
+static int sell_set_values_cap(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, const double *csr_values, SellMat &out,
+                               int max_fmt)
+{
     SfSellValues V;
-    sf_sell_values(pat->host, csr_values, sell_max_fmt(), V);
+    sf_sell_values(pat->host, csr_values, max_fmt, V);
     out.pat = pat;
     out.fmt = V.fmt;
     out.lanes = 0;
@@ -132,8 +174,13 @@ int sell_set_values(ctl_handle_s *h, const std::shared_ptr<SellPattern> &pat, co
     CTL_TRY(upload_vec(h, &out.vcode, V.vcode));
     CTL_TRY(upload_vec(h, &out.vdict, V.vdict));
     CTL_TRY(upload_vec(h, &out.dict, V.dict));
+    CTL_TRY(upload_vec(h, &out.sp4, V.sp4));
+    CTL_TRY(upload_vec(h, &out.stab, V.stab));
+    out.ps_off = V.ps_off;
+    out.ps_w = V.ps_w;
+    for (int k = 0; k < V.ps_w && k < 8; ++k) out.ps[k] = V.stab[V.ps_off + k];
     if (V.fmt == FMT_DICT8) CTL_TRY(upload_vec(h, (uint8_t **)&out.code, V.code8));
-    else if (V.fmt == FMT_DICT16) CTL_TRY(upload_vec(h, (uint16_t **)&out.code, V.code16));
+    else if (V.fmt == FMT_DICT16 || V.fmt == FMT_STENCIL) CTL_TRY(upload_vec(h, (uint16_t **)&out.code, V.code16));
     return CTL_OK;
 }
 
@@ -152,7 +199,7 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
     if (force_lanes == 0 && (mesh_like || (mean <= sell_max_mean && A.n_rows >= sell_min_rows))) {
         std::shared_ptr<SellPattern> pat;
         CTL_TRY(sell_build_pattern(h, A, pat));
-        return sell_set_values(h, pat, A.values.data(), out);
+        return sell_set_values_cap(h, pat, A.values.data(), out, sell_max_fmt_coarse());
     }
     auto pat = std::make_shared<SellPattern>();     // sizes only; no SELL arrays
     pat->n_rows = A.n_rows;
@@ -174,7 +221,7 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
     a.indptr = A.indptr.data();
     a.indices = A.indices.data();
     SfCsrvData D;
-    sf_csrv_data(a, A.values.data(), std::min(sell_max_fmt(), (int)FMT_PK), D);
+    sf_csrv_data(a, A.values.data(), std::min(sell_max_fmt_coarse(), (int)FMT_PK), D);
     out.fmt = D.fmt;
     out.bytes_per_pass = D.bytes_per_pass;
     out.stream = D.bytes_per_pass > stream_threshold();
@@ -203,12 +250,60 @@ struct DVec {
     __device__ __forceinline__ double operator()(int c) const { return halo_gather(x, ghost, n_own, c); }
 };
 
+// FMT_STENCIL: a slice whose 32 rows share one stencil reads (delta_k, value_k) through warp-uniform loads and
+// gathers x[row + delta_k] (coalesced); the other slices take the per-entry DICT16 path.
+template <typename G>
+__device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row, G g)
+{
+    const int s = row >> 5, lane = row & 31;
+    const int4 s0 = __ldg(A.sp4 + s);
+    double acc = 0.0;
+    if (s0.z == A.ps_off) {
+        // the most frequent stencil: offsets and values are kernel parameters, the only loads are the gathers
+        double xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = (j < A.ps_w) ? g(row + A.ps_delta[j]) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < A.ps_w) acc = fma(A.ps_v[j], xv[j], acc);
+        return acc;
+    }
+    if (s0.z >= 0) {
+        // offsets first (warp-uniform 4-byte loads), then all gathers of the chunk, the values only when they are
+        // multiplied: few live registers, all gathers in flight together
+        const DictEnt *st = A.stab + s0.z;
+        for (int k0 = 0; k0 < s0.y; k0 += SC) {
+            int d[SC];
+#pragma unroll
+            for (int j = 0; j < SC; ++j)
+                if (k0 + j < s0.y) d[j] = __ldg(&st[k0 + j].delta);
+            double xv[SC];
+#pragma unroll
+            for (int j = 0; j < SC; ++j) xv[j] = (k0 + j < s0.y) ? g(row + d[j]) : 0.0;
+#pragma unroll
+            for (int j = 0; j < SC; ++j)
+                if (k0 + j < s0.y) acc = fma(__ldg(&st[k0 + j].v), xv[j], acc);
+        }
+        return acc;
+    }
+    // the few slices at mesh / partition boundaries: per-entry codes, one entry at a time
+    const int end = s0.x + 32 * s0.y;
+    const uint16_t *code = reinterpret_cast<const uint16_t *>(A.code);
+#pragma unroll 1
+    for (int p = s0.x + lane; p < end; p += 32) {
+        const DictEnt e = sf_dict(A.dict, __ldg(code + p));
+        acc = fma(e.v, g(row + e.delta), acc);
+    }
+    return acc;
+}
+
 // One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is divergence free;
 // entries are fetched in chunks of SC with all stream loads issued before the dependent gathers
 // (memory-level parallelism instead of a serial load -> gather -> fma chain per entry).
 template <int FMT, bool STREAM, typename G>
 __device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g)
 {
+    if (FMT == FMT_STENCIL) return sell_row_dot_stencil(A, row, g);
     const int s = row >> 5, lane = row & 31;
     const int2 s0 = __ldg(A.sp + s);
     const int end = __ldg(reinterpret_cast<const int *>(A.sp + s + 1));
@@ -250,6 +345,7 @@ __device__ __forceinline__ double sell_row_dot_rt(const MatView &A, int row, G g
     case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g);
     case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g);
     case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g);
+    case FMT_STENCIL: return sell_row_dot_stencil(A, row, g);
     default: return sell_row_dot<FMT_DICT8, false>(A, row, g);
     }
 }
@@ -355,18 +451,19 @@ __device__ __forceinline__ double apply_mode(int mode, double ax, const double *
 }
 
 // ---------------------------------------------------------------- SELL kernels
-template <int FMT, bool STREAM>
+// GH: the gathered vector has ghost entries (several GPUs); without them the gather is a plain read-only load
+template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloWait w, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
     pdl_sync();
     run_rows<1>(A.n_rows, w, HaloWait(), push, y, [&](int row) {
-        const double ax = sign * sell_row_dot<FMT, STREAM>(A, row, x);
+        const double ax = sign * sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return GH ? x(c) : __ldg(x.x + c); });
         return apply_mode(mode, ax, b, row);
     });
 }
 
-template <int FMT, bool STREAM>
+template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
                                                       const double *__restrict__ b, const double *p_prev, const DVec p_cur,
                                                       const HaloWait w, double *out, double a, double bq, double c,
@@ -374,7 +471,7 @@ __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const do
 {
     pdl_sync();
     run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = sell_row_dot<FMT, STREAM>(A, row, p_cur);
+        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return GH ? p_cur(c) : __ldg(p_cur.x + c); });
         const double di = dinv[row], bi = b[row];
         double r = bq * p_cur.x[row] + c * di * (bi - ax);
         if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
@@ -383,13 +480,15 @@ __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const do
     });
 }
 
-template <int FMT, bool STREAM>
+template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloWait w,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
     pdl_sync();
     run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return s * dinv(c) * b(c); });
+        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) {
+            return GH ? s * dinv(c) * b(c) : s * __ldg(dinv.x + c) * __ldg(b.x + c);
+        });
         const double di = dinv.x[row], bi = b.x[row];
         const double p1 = s * di * bi;
         return wgt * p1 + (wgt * s) * di * (bi - ax);
@@ -418,27 +517,49 @@ __global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict
     run_rows<1>(n, HaloWait(), HaloWait(), push, out, [&](int row) { return c * dinv[row] * b[row]; });
 }
 
-// one warp per row of a small dense matrix
+// Small dense matrix (the coarsest level: 2205 rows at C2, 39 MB, L2-resident): one CTA per GR rows, so that b is
+// read once per GR rows and every thread keeps GR independent 16-byte loads in flight
+constexpr int GR = 4;
 __global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
                                                        double *__restrict__ y, int n, const HaloWait w)
 {
     pdl_sync();
     halo_wait(w, -1, -1);
-    const int row = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    const double *a = A + (size_t)row * n;
-    double acc0 = 0.0, acc1 = 0.0;
-    int j = lane;
-    for (; j + 32 < n; j += 64) {
-        acc0 = fma(__ldg(a + j), b[j], acc0);
-        acc1 = fma(__ldg(a + j + 32), b[j + 32], acc1);
-    }
-    if (j < n) acc0 = fma(__ldg(a + j), b[j], acc0);
-    double acc = acc0 + acc1;
+    __shared__ double part[GR][ST / 32];
+    const int r0 = blockIdx.x * GR;
+    double acc[GR];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) y[row] = acc;
+    for (int q = 0; q < GR; ++q) acc[q] = 0.0;
+    if ((n & 1) == 0) {      // rows start 16-byte aligned
+        const double2 *b2 = reinterpret_cast<const double2 *>(b);
+        const int n2 = n >> 1;
+        for (int j = threadIdx.x; j < n2; j += ST) {
+            const double2 bv = b2[j];
+            double2 av[GR];
+#pragma unroll
+            for (int q = 0; q < GR; ++q)
+                av[q] = (r0 + q < n) ? __ldg(reinterpret_cast<const double2 *>(A + (size_t)(r0 + q) * n) + j) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (int q = 0; q < GR; ++q) acc[q] = fma(av[q].y, bv.y, fma(av[q].x, bv.x, acc[q]));
+        }
+    } else {
+        for (int j = threadIdx.x; j < n; j += ST) {
+            const double bv = b[j];
+#pragma unroll
+            for (int q = 0; q < GR; ++q)
+                if (r0 + q < n) acc[q] = fma(__ldg(A + (size_t)(r0 + q) * n + j), bv, acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < GR; ++q) {
+        double s = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((threadIdx.x & 31) == 0) part[q][threadIdx.x >> 5] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < GR && r0 + threadIdx.x < n)
+        y[r0 + threadIdx.x] = (part[threadIdx.x][0] + part[threadIdx.x][1]) + (part[threadIdx.x][2] + part[threadIdx.x][3]);
 }
 
 // ---------------------------------------------------------------- CSR-vector kernels
@@ -486,20 +607,6 @@ __global__ void __launch_bounds__(ST) csrv_first2_kernel(const MatView A, const 
     });
 }
 
-// y = R b - RA x: the residual of a coarse level restricted without storing it
-template <int T>
-__global__ void __launch_bounds__(ST) csrv_rr_kernel(const MatView R, const MatView RA, const DVec b, const DVec x,
-                                                    const HaloWait wb, const HaloWait wx, double *y, const HaloPush push)
-{
-    pdl_sync();
-    const int sub = threadIdx.x % T;
-    run_rows<T>(R.n_rows, wb, wx, push, y, [&](int row) {
-        const double rb = csrv_row_dot<T, false>(R, row, sub, b);
-        const double rax = csrv_row_dot<T, false>(RA, row, sub, x);
-        return rb - rax;
-    });
-}
-
 DVec dvec(const GVec &g, const MatView &A)
 {
     DVec d;
@@ -511,32 +618,31 @@ DVec dvec(const GVec &g, const MatView &A)
 
 int grid_for(int n_rows, int T, const HaloPush &push) { return ceil_div((int64_t)n_rows * T, ST) + halo_push_ctas(push, ST); }
 
-#define SELL_DISPATCH(KERNEL, A, ...)                                                                       \
+#define SELL_LAUNCH_GH(KERNEL, FMT, STREAM, ...)                                                            \
+    do {                                                                                                    \
+        if (gh__) pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, true>, __VA_ARGS__);                        \
+        else pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, false>, __VA_ARGS__);                            \
+    } while (0)
+
+#define SELL_LAUNCH_ST(KERNEL, FMT, ...)                                                                    \
+    do {                                                                                                    \
+        if (st__) SELL_LAUNCH_GH(KERNEL, FMT, true, __VA_ARGS__);                                           \
+        else SELL_LAUNCH_GH(KERNEL, FMT, false, __VA_ARGS__);                                               \
+    } while (0)
+
+// gh__: a gathered vector comes with ghost entries
+#define SELL_DISPATCH(KERNEL, A, GHOSTS, ...)                                                               \
     do {                                                                                                    \
         const int grid__ = grid_for((A).pat->n_rows, 1, push);                                              \
         if (grid__ == 0) return CTL_OK;                                                                     \
-        const bool st__ = (A).stream;                                                                       \
+        const bool st__ = (A).stream, gh__ = (GHOSTS);                                                      \
         switch ((A).fmt) {                                                                                  \
-        case FMT_F64:                                                                                       \
-            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_F64, true>, __VA_ARGS__);                        \
-            else pdl_launch(h, grid__, ST, KERNEL<FMT_F64, false>, __VA_ARGS__);                            \
-            break;                                                                                          \
-        case FMT_D16:                                                                                       \
-            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_D16, true>, __VA_ARGS__);                        \
-            else pdl_launch(h, grid__, ST, KERNEL<FMT_D16, false>, __VA_ARGS__);                            \
-            break;                                                                                          \
-        case FMT_PK:                                                                                        \
-            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_PK, true>, __VA_ARGS__);                         \
-            else pdl_launch(h, grid__, ST, KERNEL<FMT_PK, false>, __VA_ARGS__);                             \
-            break;                                                                                          \
-        case FMT_DICT16:                                                                                    \
-            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_DICT16, true>, __VA_ARGS__);                     \
-            else pdl_launch(h, grid__, ST, KERNEL<FMT_DICT16, false>, __VA_ARGS__);                         \
-            break;                                                                                          \
-        default:                                                                                            \
-            if (st__) pdl_launch(h, grid__, ST, KERNEL<FMT_DICT8, true>, __VA_ARGS__);                      \
-            else pdl_launch(h, grid__, ST, KERNEL<FMT_DICT8, false>, __VA_ARGS__);                          \
-            break;                                                                                          \
+        case FMT_F64: SELL_LAUNCH_ST(KERNEL, FMT_F64, __VA_ARGS__); break;                                  \
+        case FMT_D16: SELL_LAUNCH_ST(KERNEL, FMT_D16, __VA_ARGS__); break;                                  \
+        case FMT_PK: SELL_LAUNCH_ST(KERNEL, FMT_PK, __VA_ARGS__); break;                                    \
+        case FMT_DICT16: SELL_LAUNCH_GH(KERNEL, FMT_DICT16, false, __VA_ARGS__); break;                     \
+        case FMT_STENCIL: SELL_LAUNCH_GH(KERNEL, FMT_STENCIL, false, __VA_ARGS__); break;                   \
+        default: SELL_LAUNCH_GH(KERNEL, FMT_DICT8, false, __VA_ARGS__); break;                              \
         }                                                                                                   \
     } while (0)
 
@@ -579,7 +685,7 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const GVec &x, double *y, const
         else CSRV_SPMV(16);
 #undef CSRV_SPMV
     } else {
-        SELL_DISPATCH(sell_spmv_kernel, A, V, dx, x.wait, b, y, kmode, sign, push);
+        SELL_DISPATCH(sell_spmv_kernel, A, x.ghost != nullptr, V, dx, x.wait, b, y, kmode, sign, push);
     }
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -594,7 +700,7 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
     const MatView V = A.view();
     const DVec dx = dvec(p_cur, V);
     if (A.lanes) CSRV_DISPATCH(csrv_cheb_kernel, A, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
-    else SELL_DISPATCH(sell_cheb_kernel, A, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
+    else SELL_DISPATCH(sell_cheb_kernel, A, p_cur.ghost != nullptr, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -606,7 +712,7 @@ int sell_cheb_first2(ctl_handle_s *h, const SellMat &A, const GVec &dinv, const 
     const MatView V = A.view();
     const DVec dd = dvec(dinv, V), db = dvec(b, V);
     if (A.lanes) CSRV_DISPATCH(csrv_first2_kernel, A, V, dd, db, b.wait, out, s, w, push);
-    else SELL_DISPATCH(sell_first2_kernel, A, V, dd, db, b.wait, out, s, w, push);
+    else SELL_DISPATCH(sell_first2_kernel, A, b.ghost != nullptr || dinv.ghost != nullptr, V, dd, db, b.wait, out, s, w, push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -625,7 +731,7 @@ int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double 
 int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, const HaloWait &wait)
 {
     if (n == 0) return CTL_OK;
-    pdl_launch(h, ceil_div(n, ST / 32), ST, dense_gemv_kernel, Ainv, b, y, n, wait);
+    pdl_launch(h, ceil_div(n, GR), ST, dense_gemv_kernel, Ainv, b, y, n, wait);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -643,23 +749,6 @@ int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec
     if (x2.wait.n_flags) w = x2.wait;
     if (x3.wait.n_flags) w = x3.wait;
     pdl_launch(h, grid, ST, sell_spmv2_kernel, V1, V2, dvec(x1, V1), dvec(x2, V1), dvec(x3, V2), y, alpha, beta, w, push);
-    h->launches++;
-    CTL_CUDA(cudaGetLastError());
-    return CTL_OK;
-}
-
-int csrv_restrict_residual(ctl_handle_s *h, const SellMat &R, const SellMat &RA, const GVec &b, const GVec &x, double *y,
-                           const HaloPush &push)
-{
-    CTL_CHECK(R.lanes > 0 && RA.lanes > 0, CTL_ERR_STATE, "csrv_restrict_residual: CSR-vector matrices only");
-    const MatView VR = R.view(), VA = RA.view();
-    const DVec db = dvec(b, VR), dx = dvec(x, VA);
-    const int lanes = R.lanes;
-    const int grid = grid_for(R.pat->n_rows, lanes, push);
-    if (grid == 0) return CTL_OK;
-    if (lanes == 4) pdl_launch(h, grid, ST, csrv_rr_kernel<4>, VR, VA, db, dx, b.wait, x.wait, y, push);
-    else if (lanes == 8) pdl_launch(h, grid, ST, csrv_rr_kernel<8>, VR, VA, db, dx, b.wait, x.wait, y, push);
-    else pdl_launch(h, grid, ST, csrv_rr_kernel<16>, VR, VA, db, dx, b.wait, x.wait, y, push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;

@@ -37,6 +37,10 @@ struct SellMat {
     double *vdict = nullptr;
     void *code = nullptr;
     DictEnt *dict = nullptr;
+    int4 *sp4 = nullptr;               // FMT_STENCIL
+    DictEnt *stab = nullptr;
+    int ps_off = -2, ps_w = 0;         // FMT_STENCIL: most frequent stencil (kernel-parameter copy in view())
+    DictEnt ps[8];
     // CSR-vector form (lanes > 0): owns all of its arrays
     int lanes = 0;
     int *csr_ptr = nullptr, *csr_cols = nullptr, *csr_rbase = nullptr;
@@ -49,7 +53,7 @@ struct SellMat {
     MatView view() const;
 };
 
-// largest format the automatic choice may pick (CTL_SELL_FMT=f64|d16|pk|dict16|dict8, default dict8)
+// largest format the automatic choice may pick (CTL_SELL_FMT=f64|d16|pk|dict16|dict8|stencil, default stencil)
 int sell_max_fmt();
 
 // build the pattern from a host CSR (column indices need not be sorted)
@@ -101,7 +105,4 @@ int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, 
 //   y = alpha * A1 (x1 + x2) + beta * A2 x3      (x2, x3 may be null)
 int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec &x1, const GVec &x2, const GVec &x3,
                double *y, double alpha, double beta, const HaloPush &push = HaloPush());
-// restricted residual in one kernel (coarse levels): y = R b - RA x, both matrices CSR-vector with the same rows
-int csrv_restrict_residual(ctl_handle_s *h, const SellMat &R, const SellMat &RA, const GVec &b, const GVec &x, double *y,
-                           const HaloPush &push = HaloPush());
 int vec_copy_n(ctl_handle_s *h, double *dst, const double *src, int n);

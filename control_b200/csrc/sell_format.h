@@ -10,6 +10,11 @@
 //   FMT_PK      uint16 (column - base) + uint16 value code -> fp64 table       4 B   few distinct values (P, R on uniform meshes)
 //   FMT_DICT16  uint16 code -> (column - row, fp64 value) table                2 B   translation-invariant stencils
 //   FMT_DICT8   uint8  code -> (column - row, fp64 value) table                1 B   ... with at most 256 distinct pairs
+//   FMT_STENCIL DICT16 whose SELL slices mostly consist of 32 rows with the SAME sequence of (column - row, value)
+//               pairs (the interior of a uniform mesh in its natural numbering): such a slice stores one stencil
+//               id, its rows gather x[row + delta_k] with warp-uniform delta_k and value_k -- about 5 instructions
+//               per entry instead of 20, which is what bounds these kernels once the matrix stream is gone.
+//               The other slices (mesh boundary, partition boundary) keep their per-entry DICT16 codes.
 //
 // 16-bit column offsets that do not fit (0xFFFF) escape to the int32 column array, which is always kept.
 // Which format a matrix gets is decided from its entries alone (sell_choose_*): a mesh matrix assembled on a uniform
@@ -32,7 +37,7 @@
 #define SF_HD inline
 #endif
 
-enum SellFmt { FMT_F64 = 0, FMT_D16 = 1, FMT_PK = 2, FMT_DICT16 = 3, FMT_DICT8 = 4 };
+enum SellFmt { FMT_F64 = 0, FMT_D16 = 1, FMT_PK = 2, FMT_DICT16 = 3, FMT_DICT8 = 4, FMT_STENCIL = 5 };
 constexpr unsigned SF_ESCAPE = 0xFFFFu;
 
 struct alignas(16) DictEnt {
@@ -54,8 +59,15 @@ struct MatView {
     const double *vals = nullptr;     // F64 / D16
     const uint16_t *vcode = nullptr;  // PK
     const double *vdict = nullptr;    // PK
-    const void *code = nullptr;       // DICT8 / DICT16
-    const DictEnt *dict = nullptr;    // DICT8 / DICT16
+    const void *code = nullptr;       // DICT8 / DICT16 / STENCIL (non-uniform slices)
+    const DictEnt *dict = nullptr;    // DICT8 / DICT16 / STENCIL
+    const int4 *sp4 = nullptr;        // STENCIL: per slice (first stored position, width, stencil offset or -1, 0)
+    const DictEnt *stab = nullptr;    // STENCIL: the stencils, `width` entries each
+    // STENCIL: the most frequent stencil travels with the kernel parameters (constant bank: its offsets and values
+    // cost no load instructions); ps_off = its offset in stab (-2: none), at most 8 entries
+    int ps_off = -2, ps_w = 0;
+    int ps_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ps_v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 template <bool STREAM, typename T>
@@ -141,7 +153,7 @@ struct SfCsr {                       // borrowed CSR arrays
 };
 
 // SELL-32 layout of a pattern: entry k of row r is stored at sp[r / 32].x + 32 k + r % 32.  Padding entries have
-// the row's own index as column (clamped into the column range) and value 0.
+// value 0 and the first column of their row.
 struct SfSellLayout {
     int n_rows = 0, n_cols = 0, n_slices = 0;
     int64_t n_stored = 0, nnz = 0;
@@ -149,7 +161,6 @@ struct SfSellLayout {
     std::vector<int> cols;                // n_stored
     std::vector<uint16_t> dcol;           // n_stored, empty when the 16-bit offsets are not worth it
     std::vector<int64_t> csr_to_sell;     // CSR entry -> stored position
-    std::vector<int> row_of;              // not stored: row of stored position p is 32 * slice + (p - sp.x) % 32
 };
 
 inline void sf_sell_layout(const SfCsr &A, SfSellLayout &L)
@@ -171,10 +182,18 @@ inline void sf_sell_layout(const SfCsr &A, SfSellLayout &L)
     for (int s = 0; s < L.n_slices; ++s) {
         const int w = (L.sp[s + 1].x - L.sp[s].x) / 32;
         int base = INT32_MAX;
+        // padding entries (value 0) point at a column the row gathers anyway: the row's first column, or the
+        // slice's first column for an empty row -- close to the real columns, so that they never need an escape
+        int slice_first = 0;
+        for (int r = 32 * s; r < std::min(A.n_rows, 32 * s + 32); ++r)
+            if (A.indptr[r + 1] > A.indptr[r]) {
+                slice_first = A.indices[A.indptr[r]];
+                break;
+            }
         for (int lane = 0; lane < 32; ++lane) {
             const int r = 32 * s + lane;
             const int len = r < A.n_rows ? A.indptr[r + 1] - A.indptr[r] : 0;
-            const int pad = std::min(std::max(r < A.n_rows ? r : A.n_rows - 1, 0), A.n_cols - 1);
+            const int pad = len > 0 ? A.indices[A.indptr[r]] : slice_first;
             for (int k = 0; k < w; ++k) {
                 const int64_t pos = (int64_t)L.sp[s].x + 32 * k + lane;
                 if (k < len) {
@@ -249,7 +268,11 @@ struct SfSellValues {
     std::vector<double> vdict;       // PK
     std::vector<uint16_t> code16;    // DICT16
     std::vector<uint8_t> code8;      // DICT8
-    std::vector<DictEnt> dict;       // DICT8 / DICT16
+    std::vector<DictEnt> dict;       // DICT8 / DICT16 / STENCIL
+    std::vector<int4> sp4;           // STENCIL
+    std::vector<DictEnt> stab;       // STENCIL
+    int ps_off = -2, ps_w = 0;       // STENCIL: most frequent stencil (offset in stab, width), -2: none with <= 8 entries
+    double uniform_fraction = 0.0;   // share of the slices whose 32 rows carry one stencil
     int64_t bytes_per_pass = 0;      // matrix stream bytes of one product
 };
 
@@ -279,6 +302,61 @@ inline void sf_sell_values(const SfSellLayout &L, const double *csr_values, int 
         }
         if (ok) {
             V.dict = tab.entries();
+            // slices whose 32 rows carry the same code sequence
+            if (max_fmt >= FMT_STENCIL && L.n_slices > 0) {
+                std::vector<int4> sp4((size_t)L.n_slices);
+                std::vector<std::pair<std::vector<uint16_t>, int>> known;      // few distinct stencils: linear search
+                std::vector<int64_t> known_count;
+                std::vector<DictEnt> stab;
+                int64_t n_uniform = 0, general_stored = 0;
+                std::vector<uint16_t> seq;
+                for (int s = 0; s < L.n_slices; ++s) {
+                    const int start = L.sp[s].x, w = (L.sp[s + 1].x - start) / 32;
+                    bool uni = 32 * s + 32 <= L.n_rows && w > 0;
+                    for (int k = 0; k < w && uni; ++k)
+                        for (int lane = 1; lane < 32; ++lane)
+                            if (code[start + 32 * k + lane] != code[start + 32 * k]) {
+                                uni = false;
+                                break;
+                            }
+                    int off = -1;
+                    if (uni) {
+                        seq.resize(w);
+                        for (int k = 0; k < w; ++k) seq[k] = code[start + 32 * k];
+                        for (size_t q = 0; q < known.size(); ++q)
+                            if (known[q].first == seq) {
+                                off = known[q].second;
+                                known_count[q]++;
+                                break;
+                            }
+                        if (off < 0 && known.size() < 4096) {
+                            off = (int)stab.size();
+                            for (int k = 0; k < w; ++k) stab.push_back(V.dict[seq[k]]);
+                            known.emplace_back(seq, off);
+                            known_count.push_back(1);
+                        }
+                    }
+                    if (off >= 0) ++n_uniform;
+                    else general_stored += 32 * w;
+                    sp4[s] = make_int4(start, w, off, 0);
+                }
+                V.uniform_fraction = (double)n_uniform / L.n_slices;
+                if (V.uniform_fraction >= 0.5) {
+                    V.fmt = FMT_STENCIL;
+                    int64_t best = 0;
+                    for (size_t q = 0; q < known.size(); ++q)
+                        if (known[q].first.size() <= 8 && known_count[q] > best) {
+                            best = known_count[q];
+                            V.ps_off = known[q].second;
+                            V.ps_w = (int)known[q].first.size();
+                        }
+                    V.sp4.swap(sp4);
+                    V.stab.swap(stab);
+                    V.code16.swap(code);
+                    V.bytes_per_pass = 2 * general_stored + 16ll * L.n_slices;
+                    return;
+                }
+            }
             if (V.dict.size() <= 256 && max_fmt >= FMT_DICT8) {
                 V.fmt = FMT_DICT8;
                 V.code8.resize((size_t)ns);

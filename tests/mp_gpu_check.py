@@ -25,8 +25,12 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+    # a small dense coarsest level, so that the hierarchy has several levels at this size; MP_NX / CTL_AMG_REP_MIN
+    # choose how many of them are distributed (halo.cu)
+    amg = dict(coarse_max=int(os.environ.get("MP_COARSE_MAX", "30")))
+    nx = int(os.environ.get("MP_NX", "40"))
     for CN in (True, False):
-        q = kat.heat_problem(40, 9, CN, beta=1e-3)
+        q = kat.heat_problem(nx, 9, CN, beta=1e-3)
         n = q["M"].shape[0]
         s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=CN,
                              time_interval=q["time_interval"], bc_dofs=q["bdofs"], rank=rank, world=world)
@@ -41,9 +45,9 @@ def main():
         e_apply = max(rel(g0, loc(y0)), rel(g1, loc(y1)))
         assert e_apply < 1e-13, e_apply
         # preconditioner
-        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"])
+        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], **amg)
         pc = opc.construct_pc(q["M"], q["K"], q["tau"], q["beta"], q["n_t"], CN, q["bdofs"],
-                              lambda_v_bounds=q["lambda_v_bounds"])
+                              lambda_v_bounds=q["lambda_v_bounds"], amg_params=amg)
         b0, b1 = x0.copy(), x1.copy()
         b0[:, q["bdofs"]] = 0.0
         b1[:, q["bdofs"]] = 0.0
@@ -57,7 +61,7 @@ def main():
                "absolute_tolerance": 0.0, "gmres_restart": 100}
         ref = ocontrol.linear_solve(q["M"], q["K"], beta=q["beta"], n_t=q["n_t"], CN=CN,
                                     time_interval=q["time_interval"], bdofs=q["bdofs"], v_d=q["v_d"],
-                                    f=q["f"], lambda_v_bounds=q["lambda_v_bounds"], solver_parameters=sp_)
+                                    f=q["f"], lambda_v_bounds=q["lambda_v_bounds"], solver_parameters=sp_, amg_params=amg)
         u0 = np.zeros((s.N, s.n_local))
         u1 = np.zeros((s.N, s.n_local))
         info = s.solve(u0, u1, loc(ref["b_0"]), loc(ref["b_1"]), solver_parameters=sp_, pc_fn="builtin")
@@ -65,7 +69,7 @@ def main():
         assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1, (info.its, ref["ksp"].its)
         assert e_sol < (1e-6 if CN else 1e-4), e_sol
         if rank == 0:
-            print(f"CN={CN} world={world}: apply {e_apply:.1e} pc {e_pc:.1e} solve its {info.its}/{ref['ksp'].its} "
+            print(f"CN={CN} world={world} nx={nx} levels {s._lib.ctl_amg_num_levels(s._h, 0)}: apply {e_apply:.1e} pc {e_pc:.1e} solve its {info.its}/{ref['ksp'].its} "
                   f"diff {e_sol:.1e}", flush=True)
         s.close()
     dist.barrier()

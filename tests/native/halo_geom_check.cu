@@ -193,20 +193,7 @@ struct Emu {
         Vecs x = cheb(l, b, x0);
         // restricted residual; rows: own slice of level l + 1 while that level takes part in an exchange
         Vecs cb(world), ghost(world), gb(world);
-        const bool fused = !D[0].levels[l].RA.indptr.empty();
-        if (fused) {
-            if (dist) {
-                exchange(world, spaces(l), b, gb);
-                exchange(world, spaces(l), x, ghost);
-            }
-            for (int r = 0; r < world; ++r) {
-                const DistLevel &L = D[r].levels[l];
-                const std::vector<double> rb = spmv_local(L.R, L.R_own, b[r], gb[r]);
-                const std::vector<double> rax = spmv_local(L.RA, L.R_own, x[r], ghost[r]);
-                cb[r].resize(rb.size());
-                for (size_t i = 0; i < rb.size(); ++i) cb[r][i] = rb[i] - rax[i];
-            }
-        } else {
+        {
             Vecs res(world);
             if (dist) exchange(world, spaces(l), x, ghost);
             for (int r = 0; r < world; ++r) {
@@ -274,10 +261,9 @@ int main()
     std::vector<double> b(n);
     for (double &v : b) v = u(gen);
 
-    for (int fuse = 0; fuse < 2; ++fuse) {
+    for (int fuse = 0; fuse < 1; ++fuse) {
         AmgParams p;
         p.coarse_max = 40;
-        p.fuse_rr = fuse;
         std::vector<AmgLevelHost> H;
         amg_setup_host(A, p, H, 1);
         const int nl = (int)H.size();
@@ -303,6 +289,16 @@ int main()
                             CHECK(a->ghosts == c->ghosts && a->send_rows == c->send_rows && a->n_flags == c->n_flags, "pictures differ (world %d level %d)", world, l);
                         }
                     }
+                if (rep_min == 1) {
+                    printf("   world %d ghost entries per rank:", world);
+                    for (int me = 0; me < world; ++me) {
+                        printf(" [rank %d: r0 %d", me, D[me].space_r0 ? D[me].space_r0->n_ghost() : 0);
+                        for (int l = 0; l < nl; ++l)
+                            if (D[me].levels[l].space && !D[me].levels[l].space->replicate) printf(", level %d %d of %d", l, D[me].levels[l].n_ghost, D[me].levels[l].n);
+                        printf("]");
+                    }
+                    printf("\n");
+                }
                 Emu E{world, H, p, D};
                 for (int me = 0; me < world; ++me) {
                     const std::shared_ptr<HaloGeom> mesh = D[me].levels[0].space;
@@ -322,7 +318,7 @@ int main()
                 double err = 0.0;
                 for (int me = 0; me < world; ++me)
                     for (int i = 0; i < (int)x2[me].size(); ++i) err = std::max(err, std::fabs(x2[me][i] - ref2[part0[me] + i]));
-                printf("fuse_rr %d world %d rep_min %6d: levels %d, first replicated %d, max diff vs serial cycle %.3e\n", fuse, world,
+                printf("world %d rep_min %6d: levels %d, first replicated %d, max diff vs serial cycle %.3e\n", world,
                        rep_min, nl, D[0].L_rep, err / refmax);
                 CHECK(err <= 1e-12 * refmax, "distributed cycle differs from the serial one");
             }

@@ -44,6 +44,28 @@ static double sell_row(const MatView &A, int row, const std::vector<double> &x)
     return acc;
 }
 
+// FMT_STENCIL: the kernel's two paths (sell.cu::sell_row_dot_stencil)
+static double sell_row_stencil(const MatView &A, int row, const std::vector<double> &x, long long *uniform_rows)
+{
+    const int s = row >> 5, lane = row & 31;
+    const int4 s0 = A.sp4[s];
+    double acc = 0.0;
+    if (s0.z >= 0) {
+        ++*uniform_rows;
+        for (int k = 0; k < s0.y; ++k) {
+            const DictEnt e = A.stab[s0.z + k];
+            acc = fma(e.v, x[row + e.delta], acc);
+        }
+        return acc;
+    }
+    const uint16_t *code = reinterpret_cast<const uint16_t *>(A.code);
+    for (int p = s0.x + lane; p < s0.x + 32 * s0.y; p += 32) {
+        const DictEnt e = A.dict[code[p]];
+        acc = fma(e.v, x[row + e.delta], acc);
+    }
+    return acc;
+}
+
 template <int FMT>
 static double csrv_row(const MatView &A, int row, const std::vector<double> &x)
 {
@@ -63,7 +85,7 @@ static int fails = 0;
 
 static const char *fmt_name(int f)
 {
-    static const char *n[] = {"F64", "D16", "PK", "DICT16", "DICT8"};
+    static const char *n[] = {"F64", "D16", "PK", "DICT16", "DICT8", "STENCIL"};
     return n[f];
 }
 
@@ -81,7 +103,7 @@ static void check_sell(const char *what, const Csr &A, int expect_fmt)
     a.indices = A.ix.data();
     SfSellLayout L;
     sf_sell_layout(a, L);
-    for (int cap = FMT_F64; cap <= FMT_DICT8; ++cap) {
+    for (int cap = FMT_F64; cap <= FMT_STENCIL; ++cap) {
         SfSellValues V;
         sf_sell_values(L, A.v.data(), cap, V);
         MatView M;
@@ -96,6 +118,9 @@ static void check_sell(const char *what, const Csr &A, int expect_fmt)
         M.vdict = V.vdict.data();
         M.code = V.fmt == FMT_DICT8 ? (const void *)V.code8.data() : (const void *)V.code16.data();
         M.dict = V.dict.data();
+        M.sp4 = V.sp4.data();
+        M.stab = V.stab.data();
+        long long uniform_rows = 0;
         double worst = 0.0;
         for (int r = 0; r < A.n_rows; ++r) {
             double y;
@@ -104,6 +129,7 @@ static void check_sell(const char *what, const Csr &A, int expect_fmt)
             case FMT_D16: y = sell_row<FMT_D16>(M, r, x); break;
             case FMT_PK: y = sell_row<FMT_PK>(M, r, x); break;
             case FMT_DICT16: y = sell_row<FMT_DICT16>(M, r, x); break;
+            case FMT_STENCIL: y = sell_row_stencil(M, r, x, &uniform_rows); break;
             default: y = sell_row<FMT_DICT8>(M, r, x); break;
             }
             worst = std::max(worst, std::fabs(y - ref[r]));
@@ -112,9 +138,10 @@ static void check_sell(const char *what, const Csr &A, int expect_fmt)
             printf("FAIL %s cap %s got %s: max diff %.3e\n", what, fmt_name(cap), fmt_name(V.fmt), worst);
             ++fails;
         }
-        if (cap == FMT_DICT8) {
-            printf("%-28s SELL: automatic format %-6s %5.2f bytes / nonzero (stored %lld, nnz %lld)\n", what, fmt_name(V.fmt),
-                   (double)V.bytes_per_pass / (double)L.nnz, (long long)L.n_stored, (long long)L.nnz);
+        if (cap == FMT_STENCIL) {
+            printf("%-28s SELL: automatic format %-7s %5.2f bytes / nonzero (stored %lld, nnz %lld, rows in uniform slices %.0f %%)\n",
+                   what, fmt_name(V.fmt), (double)V.bytes_per_pass / (double)L.nnz, (long long)L.n_stored, (long long)L.nnz,
+                   100.0 * uniform_rows / A.n_rows);
             if (expect_fmt >= 0 && V.fmt != expect_fmt) {
                 printf("FAIL %s: expected %s\n", what, fmt_name(expect_fmt));
                 ++fails;
@@ -193,8 +220,8 @@ static Csr mesh_stencil(int nx, int ny, bool random_values, int ghost_cols)
 
 int main()
 {
-    check_sell("uniform 7-point stencil", mesh_stencil(300, 217, false, 0), FMT_DICT8);
-    check_sell("stencil + ghost columns", mesh_stencil(300, 230, false, 300), FMT_DICT8);
+    check_sell("uniform 7-point stencil", mesh_stencil(300, 217, false, 0), FMT_STENCIL);
+    check_sell("stencil + ghost columns", mesh_stencil(300, 230, false, 300), FMT_STENCIL);
     check_sell("random values (small)", mesh_stencil(97, 53, true, 0), FMT_DICT16);      // fewer than 65536 entries
     check_sell("random values", mesh_stencil(397, 253, true, 0), FMT_D16);
     {
