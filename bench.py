@@ -96,92 +96,107 @@ class ClockSampler:
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def solver_parameters(ksp, rtol):
-    return {"linear_solver": ksp, "gmres_restart": 30, "maximum_iterations": 200,
+def solver_parameters(ksp, rtol, restart=30):
+    return {"linear_solver": ksp, "gmres_restart": restart, "maximum_iterations": 200,
             "relative_tolerance": rtol, "absolute_tolerance": 0.0, "preconditioner": True}
 
 
 # --------------------------------------------------------------------------------------
-# CPU oracle sample: one Krylov iteration (KKT apply + preconditioner apply) at the full
-# spatial size on n_s of the N time blocks, scaled to a whole solve.
+# CPU arm: the reference's algorithm in C / OpenMP (oracle/c/pc_omp.c through oracle/fastpc.py) on all host cores.
+# One step = ONE complete Krylov iteration at the full size on ALL time blocks (operator apply + preconditioner
+# apply + the iteration's vector work), scaled by the iteration count of the solve (its + 1 applications).
 # --------------------------------------------------------------------------------------
-class CpuSample:
-    """Oracle preconditioner + operator on `n_blocks_sample` time blocks; AMG set up once."""
+ITERATION_COUNTS = os.path.join(ROOT, "profiles", "iteration_counts.json")
 
-    def __init__(self, q_full, n_blocks_sample, mode):
-        from oracle import pc as opc
-        self.q = q_full
-        self.ns = n_blocks_sample
-        M, K, bd, beta = q_full["M"], q_full["K"], q_full["bdofs"], q_full["beta"]
-        tau = q_full["tau"]
-        n_t_s = n_blocks_sample + 1
-        n = M.shape[0]
-        if mode == "diagonal":
-            self.pc = opc.construct_pc_diagonal(M, K, tau, beta, n_t_s, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
-        else:
-            self.pc = opc.construct_pc(M, K, tau, beta, n_t_s, True, bd, lambda_v_bounds=q_full["lambda_v_bounds"])
+
+def problem_key(args):
+    return f"{args.workload}/{args.nx}/{args.n_t}/{args.ksp}/{args.rtol:g}"
+
+
+def known_iterations(args):
+    """Iteration count of the GPU arm on this configuration (same algorithm, same count): measured by this file's
+    GPU arm and committed in profiles/iteration_counts.json; --ref_its overrides."""
+    if args.ref_its is not None:
+        return args.ref_its, "--ref_its"
+    try:
+        return int(json.load(open(ITERATION_COUNTS))[problem_key(args)]), "profiles/iteration_counts.json (GPU arm)"
+    except Exception:
+        return 15, "assumed (no GPU record for this configuration)"
+
+
+class CpuArm:
+    def __init__(self, q, args, mode, CN):
+        from oracle import fastpc
+        self.threads = fastpc.set_threads()      # explicitly all cores: torchrun exports OMP_NUM_THREADS=1
+        self.fastpc = fastpc
+        self.pc = fastpc.FastPc(q["M"], q["K"], q["tau"], q["beta"], q["n_t"], CN, q["bdofs"],
+                                lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
         rng = np.random.default_rng(0)
-        self.x0 = rng.standard_normal((n_blocks_sample, n))
-        self.x1 = rng.standard_normal((n_blocks_sample, n))
-        self.x0[:, bd] = 0.0
-        self.x1[:, bd] = 0.0
-        self.pc(self.x0, self.x1)          # untimed: AMG setup + numba compilation happen on first use
+        N, n = self.pc.N, self.pc.n
+        self.x0 = rng.standard_normal((N, n))
+        self.x1 = rng.standard_normal((N, n))
+        self.x0[:, q["bdofs"]] = 0.0
+        self.x1[:, q["bdofs"]] = 0.0
+        # vector work of one iteration on the stacked vector: MINRES 2 inner products + 6 updates; (F)GMRES(m)
+        # on average m / 2 + 1 of each
+        self.n_dots, self.n_axpys = (2, 6) if args.ksp == "minres" else (args.restart // 2 + 1, args.restart // 2 + 1)
+        self.iteration()      # untimed: page faults, thread start-up
 
-    def run(self, its):
-        from oracle import fastmv, kkt
-        q = self.q
-        M, K, bd, beta, tau = q["M"], q["K"], q["bdofs"], q["beta"], q["tau"]
+    def iteration(self):
         t0 = time.perf_counter()
-        y0, y1 = kkt.kkt_apply_fused(M, K, tau, beta, self.ns + 1, True, bd, self.x0, self.x1)
-        t_apply = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        self.pc(y0, y1)
-        t_pc = time.perf_counter() - t0
-        scale = (q["n_t"] - 1) / self.ns
-        per_iter = (t_apply + t_pc) * scale
-        return {"threads": fastmv.threads(), "seconds_sample": t_apply + t_pc, "seconds_per_iteration_full": per_iter,
-                "value": per_iter * (its + 1), "kkt_apply_s_full": t_apply * scale, "pc_apply_s_full": t_pc * scale}
+        y0, y1 = self.pc.kkt_apply(self.x0, self.x1)
+        t1 = time.perf_counter()
+        u0, u1 = self.pc.pc_apply(y0, y1)
+        t2 = time.perf_counter()
+        self.fastpc.vector_work(u0.reshape(-1), y0.reshape(-1), self.n_dots, self.n_axpys)
+        t3 = time.perf_counter()
+        return {"kkt_apply_s": t1 - t0, "pc_apply_s": t2 - t1, "vector_s": t3 - t2, "iteration_s": t3 - t0}
 
-
-def cpu_sample(q_full, n_blocks_sample, its, mode):
-    return CpuSample(q_full, n_blocks_sample, mode).run(its)
+    def sample_text(self, args, its, its_source):
+        return (f"1 complete {args.ksp} iteration (operator apply + in-built preconditioner apply + the iteration's "
+                f"inner products / updates) at the full size on ALL {self.pc.N} time blocks, x{its + 1} applications "
+                f"for a solve of {its} iterations [{its_source}]; the reference's algorithm restated in C / OpenMP "
+                f"(oracle/c/pc_omp.c, checked against the numpy oracle), AMG set-up once and untimed, "
+                f"{self.threads} OpenMP threads on {os.cpu_count()} host cores")
 
 
 def run_reference(args):
-    """--impl reference: the reference's algorithm on the host cores (oracle port: the real
+    """--impl reference: the reference's algorithm on the host cores (C / OpenMP port: the real
     Firedrake/PETSc/hypre stack cannot be installed here)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from synthetic import problems
-    q = problems.heat_problem(args.nx, args.n_t, True)
+    c3 = args.workload == "c3"
+    q = problems.heat_problem_3d(args.nx, args.n_t, False) if c3 else problems.heat_problem(args.nx, args.n_t, True)
     mode = "diagonal" if args.ksp == "minres" else "triangular"
-    its = args.ref_its
-    times = []
-    info = None
-    sampler = CpuSample(q, args.sample_blocks, mode)
+    its, its_source = known_iterations(args)
+    arm = CpuArm(q, args, mode, not c3)
+    times, parts = [], None
     for i in range(args.warmup + args.steps):
-        info = sampler.run(its)
+        parts = arm.iteration()
         if i >= args.warmup:
-            times.append(info["value"])
+            times.append(parts["iteration_s"] * (its + 1))
     val = float(np.mean(times))
-    cores = info["threads"]
-    sample = (f"1 {args.ksp} iteration (KKT apply + preconditioner apply, AMG set up once, untimed) at "
-              f"the full {args.nx}^2 spatial size on {args.sample_blocks} of {args.n_t - 1} time blocks, "
-              f"scaled x{(args.n_t - 1) / args.sample_blocks:.3g} to all blocks and x{its + 1} "
-              f"to a solve of {its} iterations; numpy/scipy oracle, sparse products on {cores} OpenMP threads "
-              f"(oracle/c/spmv_omp.c), vector updates single threaded")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": val * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": config_dict(args),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": config_dict(args), "iterations": its,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": arm.threads, "kind": "port",
+                             "sample": arm.sample_text(args, its, its_source), **parts},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def config_dict(args):
+    if args.workload == "c3":
+        return {"workload": f"C3: 3-D heat control, P1 tetrahedra on the {args.nx}^3 unit-cube mesh, n_t={args.n_t}, "
+                            f"backward Euler, beta=1e-4, {args.ksp}({args.restart}) + in-built block lower-triangular "
+                            f"preconditioner (the reference's default Krylov parameters, control/control.py:3260-3266), "
+                            f"rtol {args.rtol:g}, rows block-partitioned over {args.gpus} GPU(s)",
+                "n": (args.nx + 1) ** 3, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol,
+                "l2": "Krylov vectors (1.1 GB each) exceed L2; per-kernel micro-timings flush L2 between launches"}
     return {"workload": f"C2: 2-D heat control, P1 on {args.nx}x{args.nx} mesh of (0,2)^2, n_t={args.n_t}, "
                         f"trapezoidal (CN), beta=1e-4, {args.ksp} + in-built block preconditioner "
                         f"({'block-diagonal SPD variant' if args.ksp == 'minres' else 'block lower-triangular'}), "
@@ -289,18 +304,26 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="heat", choices=["heat", "stokes"],
-                    help="heat = config C2 (default, the metric's configuration); stokes = config C4 (opt-in)")
+    ap.add_argument("--workload", default="heat", choices=["heat", "c3", "stokes"],
+                    help="heat = config C2 (default, the metric's configuration); c3 = config C3 (3-D, backward Euler, "
+                         "the configuration BASELINE names for 8 GPUs); stokes = config C4 (opt-in)")
+    ap.add_argument("--restart", type=int, default=30)
     ap.add_argument("--nx", type=int, default=1024)
     ap.add_argument("--n_t", type=int, default=64)
     ap.add_argument("--ksp", default="minres", choices=["minres", "fgmres", "gmres"])
     ap.add_argument("--rtol", type=float, default=1e-6)
-    ap.add_argument("--sample_blocks", type=int, default=4)
-    ap.add_argument("--ref_its", type=int, default=15,
-                    help="iterations assumed by the reference arm (the measured count of the GPU arm on the same config: 15 for minres, 11 for fgmres)")
+    ap.add_argument("--ref_its", type=int, default=None,
+                    help="iteration count the reference arm scales its one timed iteration by (default: the GPU arm's "
+                         "measured count for this configuration, profiles/iteration_counts.json)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_alt", action="store_true", help="skip the FGMRES + triangular PC side measurement")
     args = ap.parse_args()
+    if args.workload == "c3":
+        # config C3 and the reference's default Krylov parameters (control/control.py:3260-3266): GMRES(10)
+        if args.nx == 1024 and args.n_t == 64:
+            args.nx, args.n_t = 128, 32
+        if args.ksp == "minres":
+            args.ksp, args.restart = "gmres", 10
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "stokes":
@@ -323,9 +346,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    q = problems.heat_problem(args.nx, args.n_t, True)
+    c3 = args.workload == "c3"
+    q = problems.heat_problem_3d(args.nx, args.n_t, False) if c3 else problems.heat_problem(args.nx, args.n_t, True)
+    CN = not c3
     mode = "diagonal" if args.ksp == "minres" else "triangular"
-    s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=True,
+    s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=CN,
                          time_interval=q["time_interval"], bc_dofs=q["bdofs"], device=local_rank,
                          rank=rank, world=world)
     if world > 1:
@@ -333,10 +358,10 @@ def main():
     t0 = time.perf_counter()
     s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
     setup_s = time.perf_counter() - t0
-    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
+    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], CN, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
     rows = slice(s.row_begin, s.row_begin + s.n_local)
     b0, b1 = np.ascontiguousarray(b0[:, rows]), np.ascontiguousarray(b1[:, rows])
-    sp_ = solver_parameters(args.ksp, args.rtol)
+    sp_ = solver_parameters(args.ksp, args.rtol, args.restart)
     b_dev = s.to_device(b0, b1)
     b_host = torch.from_numpy(np.concatenate([b0.ravel(), b1.ravel()])).pin_memory()
     u_host = torch.zeros_like(b_host).pin_memory()
@@ -449,16 +474,12 @@ def main():
                                          "kkt_residual": s.residual_norm(b_dev, u2)}
     if rank == 0 and not args.no_cpu_baseline:
         t0 = time.perf_counter()
-        cb = cpu_sample(q, args.sample_blocks, info.its, mode)
-        line["cpu_baseline"] = {
-            "value": cb["value"], "unit": UNIT, "cores": cb["threads"], "kind": "port",
-            "sample": (f"1 {args.ksp} iteration (KKT apply + preconditioner apply; AMG setup untimed) at the full "
-                       f"{args.nx}^2 size on {args.sample_blocks} of {N} time blocks = {cb['seconds_sample']:.1f} s, "
-                       f"scaled x{N / args.sample_blocks:.3g} x{info.its + 1} applications; numpy/scipy oracle, "
-                       f"sparse products on {cb['threads']} OpenMP threads, vector updates single threaded; "
-                       f"{os.cpu_count()} cores on the box"),
-            "kkt_apply_s": cb["kkt_apply_s_full"], "pc_apply_s": cb["pc_apply_s_full"],
-            "wall_s": time.perf_counter() - t0}
+        arm = CpuArm(q, args, mode, CN)
+        parts = arm.iteration()
+        line["cpu_baseline"] = {"value": parts["iteration_s"] * (info.its + 1), "unit": UNIT, "cores": arm.threads,
+                                "kind": "port", "sample": arm.sample_text(args, info.its, "this run's GPU arm"),
+                                **parts, "wall_s": time.perf_counter() - t0}
+        del arm
     if rank == 0:
         print(json.dumps(line), flush=True)
     s.close()

@@ -15,8 +15,8 @@
 //   post-smoothing   nu launches
 // Multi-GPU: every level above `rep_min` rows per rank is distributed by rows; each kernel pushes the boundary
 // rows of its output to the ranks that gather them and waits for its own ghosts (halo.cuh); the first level below
-// the threshold receives its right-hand side through a replicating exchange and everything below it runs
-// redundantly on every rank.
+// the threshold receives its right-hand side through a replicating exchange (owners compute their rows, push them to
+// everybody, one small kernel unpacks the arrivals) and everything below it runs redundantly on every rank.
 #include "amg.cuh"
 
 #include <cstdlib>
@@ -137,10 +137,10 @@ void amg_free(AmgHierarchyDev &H)
 }
 
 // a level vector as a kernel gathers it: owned entries + the ghosts of the plan's last exchange
-static GVec gathered(const AmgLevelDev &L, HaloPlan *plan, const double *v, const SellMat &consumer)
+static GVec gathered(const AmgLevelDev &, HaloPlan *plan, const double *v, const SellMat &)
 {
     if (!plan) return GVec(v);
-    return GVec(v, halo_ghost(plan), halo_wait_for(plan, consumer.skip_lo, consumer.skip_hi));
+    return GVec(v, halo_ll(plan), halo_idx1(plan));
 }
 
 // nu Chebyshev steps on D^-1 A over [lo rho, hi rho] (oracle/cheb.py::chebyshev).
@@ -172,7 +172,7 @@ static int smooth(ctl_handle_s *h, const AmgParams &p, AmgLevelDev &L, int l, co
     int k0;      // first step that still has to be taken
     if (zero) {
         // p_2 = w p_1 + w s D^-1 (b - A p_1), p_1 = s D^-1 b formed on the fly
-        const GVec dinv = L.px ? GVec(L.dinv, L.dinv + L.n, HaloWait()) : GVec(L.dinv);
+        const GVec dinv = L.px ? GVec(L.dinv, L.dinv + L.n) : GVec(L.dinv);
         const HaloPush push = halo_push(L.px);
         CTL_TRY(sell_cheb_first2(h, L.A, dinv, b, where(2), scale, om[0], push));
         k0 = 3;
@@ -205,21 +205,17 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const GVec &b, dou
     AmgLevelDev &L = H.dev[l];
     const int last = (int)H.dev.size() - 1;
     if (l == last) {
-        if (L.Ainv) return dense_gemv(h, L.Ainv, b.x, x, L.n, b.wait);
+        if (L.Ainv) return dense_gemv(h, L.Ainv, b.x, x, L.n);
         return smooth(h, H.params, L, l, b, x_is_zero ? nullptr : x, x);
     }
     AmgLevelDev &C = H.dev[l + 1];
     CTL_TRY(smooth(h, H.params, L, l, b, x_is_zero ? nullptr : x, x));
     // right-hand side of the coarse level: the restricted residual.  Its producer pushes what the coarse level's
     // first kernels gather (distributed coarse level) or replicates it (first replicated level).
-    double *cb = C.b;
     HaloPush cpush;
-    if (C.prep) {
-        cb = halo_full_next(C.prep);
-        cpush = halo_push(C.prep);
-    } else if (C.pb) {
-        cpush = halo_push(C.pb);
-    }
+    if (C.prep) cpush = halo_push(C.prep);
+    else if (C.pb) cpush = halo_push(C.pb);
+    double *cb = C.b;
     {
         // (the gathered vector is described BEFORE the next exchange of its plan is drawn: both read the plan's counter)
         HaloPlan *plan_r = L.pr ? L.pr : L.px;
@@ -230,8 +226,8 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const GVec &b, dou
         CTL_TRY(sell_spmv(h, L.R, gr, cb, nullptr, SELL_ASSIGN, cpush));
     }
     GVec gcb(cb);
-    if (C.prep) gcb = GVec(halo_full_last(C.prep), nullptr, halo_wait_for(C.prep, 0, 0));
-    else if (C.pb) gcb = GVec(cb, halo_ghost(C.pb), halo_wait_for(C.pb, C.A.skip_lo, C.A.skip_hi));
+    if (C.prep) CTL_TRY(halo_unpack(h, C.prep, cb + C.prep->n_own));      // the other ranks' rows behind my own
+    else if (C.pb) gcb = GVec(cb, halo_ll(C.pb), halo_idx1(C.pb));
     CTL_TRY(vcycle(h, H, l + 1, gcb, C.x, true));
     // x' = x + P x_c, out of place into t2; then the post-smoothing brings the result back into x
     const GVec gxc = gathered(C, C.px, C.x, L.P);
@@ -261,7 +257,7 @@ int amg_solve(ctl_handle_s *h, AmgHierarchyDev &H, const double *b, double *x, b
     const AmgParams &p = H.params;
     AmgLevelDev &L0 = H.dev[0];
     if (L0.pb && !b_exchanged) CTL_TRY(halo_exchange_now(h, L0.pb, b));
-    const GVec gb = L0.pb ? GVec(b, halo_ghost(L0.pb), halo_wait_for(L0.pb, L0.A.skip_lo, L0.A.skip_hi)) : GVec(b);
+    const GVec gb = L0.pb ? GVec(b, halo_ll(L0.pb), halo_idx1(L0.pb)) : GVec(b);
     if (p.acc_lo <= 0.0) {
         for (int c = 0; c < p.cycles; ++c) CTL_TRY(vcycle(h, H, 0, gb, x, c == 0));
         return CTL_OK;

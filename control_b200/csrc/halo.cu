@@ -1,8 +1,8 @@
 // Device-initiated halo exchange, host side (see halo.cuh for the protocol) and the distributed AMG hierarchy.
 //
 // Why three slots are enough.  Let kernel k of a rank push exchange k of a space and kernel k+1 gather it.  A can
-// start kernel k+1 only after its own kernel k, and gathers in it only after B's push k has arrived, i.e. after
-// B's kernel k has STARTED (the push warps run first).  So when A pushes exchange k+1 (slot (k+1) % 3), B is at
+// start kernel k+1 only after its own kernel k, and its boundary rows complete in it only after B's push k has
+// arrived, i.e. after B's kernel k has STARTED (the push warps run first).  So when A pushes exchange k+1 (slot (k+1) % 3), B is at
 // least inside kernel k, whose regular CTAs may still read slot (k-1) % 3 and will read slot k % 3 next: both
 // differ from the slot being written.  A cannot push exchange k+2 before B's push k+1 arrived, i.e. before B's
 // kernel k has completed, which ends B's last read of slot (k-1) % 3 = (k+2) % 3.
@@ -80,12 +80,9 @@ HaloPlan *halo_arena_add(ctl_handle_s *h, HaloArena &a, const std::shared_ptr<Ha
     in.sp = sp;
     in.plan.reset(new HaloPlan());
     in.slot_off.resize(world);
-    in.flag_off.resize(world);
     for (int r = 0; r < world; ++r) {
         in.slot_off[r] = a.cursor[r];
-        a.cursor[r] += align256((size_t)3 * g.stride(r) * sizeof(double));
-        in.flag_off[r] = a.cursor[r];
-        a.cursor[r] += align256((size_t)g.n_flags[r] * sizeof(unsigned long long));
+        a.cursor[r] += align256((size_t)3 * g.stride(r) * sizeof(ulonglong2));
     }
     HaloPlan &p = *in.plan;
     p.n_own = g.n_own();
@@ -95,10 +92,6 @@ HaloPlan *halo_arena_add(ctl_handle_s *h, HaloArena &a, const std::shared_ptr<Ha
     p.d_rows = sp->d_rows;
     p.n_chunks = (int)g.chunks[g.me].size();
     p.stride = g.stride(g.me);
-    p.n_flags = g.n_flags[g.me];
-    p.d_epoch = h->comm->d_epoch;
-    p.d_err = h->comm->d_err;
-    p.max_spins = h->comm->max_spins;
     a.inst.push_back(std::move(in));
     return a.inst.back().plan.get();
 }
@@ -162,8 +155,7 @@ int halo_arena_finalize(ctl_handle_s *h, HaloArena &a)
     for (HaloArena::Inst &in : a.inst) {
         const HaloGeom &sp = *in.sp->g;
         HaloPlan &p = *in.plan;
-        p.slots = (double *)(a.base + in.slot_off[me]);
-        p.flags = (unsigned long long *)(a.base + in.flag_off[me]);
+        p.slots = (ulonglong2 *)(a.base + in.slot_off[me]);
         std::vector<PushDst> dsts;
         const std::vector<HaloGeom::Chunk> &mine_chunks = sp.chunks[me];
         int pair = 0;
@@ -171,8 +163,7 @@ int halo_arena_finalize(ctl_handle_s *h, HaloArena &a)
             for (size_t d = 0; d < ch.dst.size(); ++d, ++pair) {
                 const int r = ch.dst[d];
                 PushDst t;
-                t.base = (double *)(a.peer_base[r] + in.slot_off[r]) + (sp.replicate ? sp.n_own(r) : 0);
-                t.flag = (unsigned long long *)(a.peer_base[r] + in.flag_off[r]) + ch.flag[d];
+                t.base = (ulonglong2 *)(a.peer_base[r] + in.slot_off[r]);
                 t.stride = sp.stride(r);
                 t.pos = in.sp->d_pos + (size_t)pair * 32;
                 dsts.push_back(t);
@@ -191,6 +182,17 @@ int halo_arena_finalize(ctl_handle_s *h, HaloArena &a)
 // ---------------------------------------------------------------------------------------------------------
 // plan instances
 // ---------------------------------------------------------------------------------------------------------
+HaloCtx halo_ctx(const ctl_handle_s *h)
+{
+    HaloCtx c;
+    if (h->comm && h->comm->d_epoch) {
+        c.epoch = h->comm->d_epoch;
+        c.err = h->comm->d_err;
+        c.max_spins = h->comm->max_spins;
+    }
+    return c;
+}
+
 HaloPush halo_push(HaloPlan *p)
 {
     HaloPush q;
@@ -198,61 +200,43 @@ HaloPush halo_push(HaloPlan *p)
     q.chunks = p->d_chunks;
     q.dsts = p->d_dsts;
     q.rows = p->d_rows;
-    q.epoch = p->d_epoch;
     q.n_chunks = p->n_chunks;
     q.slot = (int)(p->idx % 3);
-    q.seq = p->idx + 1;
+    q.idx1 = p->idx + 1;
+    q.all_rows = p->replicate ? 1 : 0;
     p->idx++;
     return q;
 }
 
-const double *halo_ghost(const HaloPlan *p) { return p->slots + (long long)((p->idx + 2) % 3) * p->stride; }
-
-HaloWait halo_wait_for(const HaloPlan *p, int skip_lo, int skip_hi)
-{
-    HaloWait w;
-    w.flags = p->flags;
-    w.epoch = p->d_epoch;
-    w.err = p->d_err;
-    w.n_flags = p->n_flags;
-    w.seq = p->idx;          // the last exchange had index idx - 1, i.e. sequence number idx
-    w.skip_lo = skip_lo;
-    w.skip_hi = skip_hi;
-    w.max_spins = p->max_spins;
-    return w;
-}
-
-double *halo_full_next(HaloPlan *p) { return p->slots + (long long)(p->idx % 3) * p->stride; }
-const double *halo_full_last(const HaloPlan *p) { return p->slots + (long long)((p->idx + 2) % 3) * p->stride; }
+const ulonglong2 *halo_ll(const HaloPlan *p) { return p->slots + (long long)((p->idx + 2) % 3) * p->stride; }
+unsigned halo_idx1(const HaloPlan *p) { return p->idx; }      // the last exchange had index idx - 1
 
 namespace {
 
 __global__ void epoch_bump_kernel(unsigned long long *epoch) { *epoch += 1ull; }
 
 // boundary rows of an existing vector: push warps only
-__global__ void __launch_bounds__(128) halo_push_kernel(const double *__restrict__ x, const HaloPush push)
+__global__ void __launch_bounds__(128) halo_push_kernel(const double *__restrict__ x, const HaloCtx ctx, const HaloPush push)
 {
     pdl_sync();
     const int ci = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (ci >= push.n_chunks) return;
     const PushChunk ch = push.chunks[ci];
-    if (lane < ch.count) {
-        const double v = x[push.rows[ch.start + lane]];
-        for (int d = 0; d < ch.n_dst; ++d) {
-            const PushDst t = push.dsts[ch.dst_begin + d];
-            t.base[(long long)push.slot * t.stride + t.pos[lane]] = v;
-        }
+    if (lane >= ch.count) return;
+    const unsigned seq = halo_epoch_bits(ctx) | push.idx1;
+    const double v = x[push.rows[ch.start + lane]];
+    for (int d = 0; d < ch.n_dst; ++d) {
+        const PushDst t = push.dsts[ch.dst_begin + d];
+        halo_ll_store(t.base + (long long)push.slot * t.stride + t.pos[lane], v, seq);
     }
-    halo_push_publish(push, ch, lane);
 }
 
-__global__ void __launch_bounds__(128) halo_persist_kernel(const HaloWait w, const double *slot, double *tail, int n)
+__global__ void __launch_bounds__(128) halo_unpack_kernel(const ulonglong2 *slot, unsigned idx1, const HaloCtx ctx, double *dst, int n)
 {
     pdl_sync();
-    halo_wait(w, -1, -1);
     const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i < n) tail[i] = __ldcg(slot + i);
+    if (i < n) dst[i] = halo_ll_read(slot + i, halo_epoch_bits(ctx) | idx1, ctx);
 }
 
 }  // namespace
@@ -262,16 +246,16 @@ int halo_exchange_now(ctl_handle_s *h, HaloPlan *p, const double *x)
     if (!p) return CTL_OK;
     const HaloPush push = halo_push(p);
     if (push.n_chunks == 0) return CTL_OK;
-    pdl_launch(h, (push.n_chunks + 3) / 4, 128, halo_push_kernel, x, push);
+    pdl_launch(h, (push.n_chunks + 3) / 4, 128, halo_push_kernel, x, halo_ctx(h), push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
 }
 
-int halo_persist(ctl_handle_s *h, HaloPlan *p, double *x_tail)
+int halo_unpack(ctl_handle_s *h, HaloPlan *p, double *dst)
 {
     if (!p || p->n_ghost == 0) return CTL_OK;
-    pdl_launch(h, (p->n_ghost + 127) / 128, 128, halo_persist_kernel, halo_wait_for(p, 0, 0), halo_ghost(p), x_tail, p->n_ghost);
+    pdl_launch(h, (p->n_ghost + 127) / 128, 128, halo_unpack_kernel, halo_ll(p), halo_idx1(p), halo_ctx(h), dst, p->n_ghost);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -294,12 +278,9 @@ int halo_epoch_begin(ctl_handle_s *h)
 // ---------------------------------------------------------------------------------------------------------
 int amg_level_vectors(ctl_handle_s *h, AmgLevelDev &L, int level);      // amg.cu
 
-static void finish_matrix(const HostCSR &local, int n_own_cols, SellMat &M)
+static void finish_matrix(const HostCSR &, int n_own_cols, SellMat &M)
 {
-    if (n_own_cols > 0) {
-        M.n_own = n_own_cols;
-        halo_skip_range(local, n_own_cols, &M.skip_lo, &M.skip_hi);
-    }
+    if (n_own_cols > 0) M.n_own = n_own_cols;      // columns behind it are ghosts
 }
 
 int amg_build_distributed(ctl_handle_s *h, const AmgParams &p, const std::shared_ptr<SellPattern> &fine_pattern,
@@ -313,10 +294,16 @@ int amg_build_distributed(ctl_handle_s *h, const AmgParams &p, const std::shared
     PcState &st = *h->pc;
     const int world = h->cfg.world, me = h->cfg.rank;
     const int nl = (int)H.host.size();
-    int rep_min = 1024;      // a level with fewer rows per rank than this (and everything below it) is replicated
-    if (const char *e = getenv("CTL_AMG_REP_MIN")) rep_min = std::max(1, atoi(e));
+    // A coarse level with fewer matrix entries per rank than this (and everything below it) is replicated.  Measured
+    // at C2 on 2 GPUs (profiles/r02_multi_gpu.txt): a product with the 2.3 M entries of the first Galerkin level
+    // takes ~5 us on one GPU and an exchange puts ~5 us of NVLink latency on the critical path, so distributing
+    // that level costs more than it saves (inner solve 1.12 ms against 0.70 ms with only the fine level
+    // distributed); a level pays once its products are stream bound (3-D: 18.5 M entries on the first level of C3).
+    int64_t rep_nnz = 2000000;
+    if (const char *e = getenv("CTL_AMG_REP_NNZ")) rep_nnz = std::max(1ll, atoll(e));
+    if (const char *e = getenv("CTL_AMG_REP_MIN")) rep_nnz = std::max(1ll, atoll(e));      // (older name, tests)
     DistHierarchy D;
-    amg_distribute_host(world, me, H.host, rep_min, st.mesh_space->g, D);
+    amg_distribute_host(world, me, H.host, rep_nnz, st.mesh_space->g, D);
     CTL_CHECK(D.part[0][me] == h->row_begin && D.part[0][me + 1] - D.part[0][me] == h->n_loc, CTL_ERR_STATE,
               "amg_build: level-0 partition differs from the handle's");
     CTL_CHECK(st.mesh_space->g->ghosts[me] == h->halo_global, CTL_ERR_STATE, "amg_build: mesh ghosts differ from the handle's");

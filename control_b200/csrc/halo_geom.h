@@ -220,13 +220,14 @@ struct DistHierarchy {
     std::shared_ptr<HaloGeom> space_r0;      // level-0 residual as the restriction gathers it
 };
 
-inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHost> &host_in, int rep_min,
+// rep_nnz: a coarse level with fewer matrix entries per rank than this (and everything below it) is replicated
+inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHost> &host_in, int64_t rep_nnz,
                                 const std::shared_ptr<HaloGeom> &mesh_space, DistHierarchy &D)
 {
     const int nl = (int)host_in.size();
     int L_rep = nl;
     for (int l = 1; l < nl; ++l)
-        if (host_in[l].A.n_rows < (int64_t)rep_min * world || !host_in[l].Ainv.empty()) {
+        if (host_in[l].A.nnz() < rep_nnz * world || !host_in[l].Ainv.empty()) {
             L_rep = l;
             break;
         }

@@ -21,12 +21,12 @@ struct HaloSpace {
 // upload the send side of a geometry
 int halo_space_upload(ctl_handle_s *h, const std::shared_ptr<HaloGeom> &g, std::shared_ptr<HaloSpace> &out);
 
-// One cudaMalloc per rank, opened by every peer through CUDA IPC: the slots and flags of every plan instance.
+// One cudaMalloc per rank, opened by every peer through CUDA IPC: the ghost slots of every plan instance.
 struct HaloArena {
     struct Inst {
         std::shared_ptr<HaloSpace> sp;
         std::unique_ptr<HaloPlan> plan;
-        std::vector<size_t> slot_off, flag_off;   // [rank] byte offsets inside that rank's arena
+        std::vector<size_t> slot_off;             // [rank] byte offset inside that rank's arena
         PushDst *d_dsts = nullptr;
     };
     std::vector<size_t> cursor;                   // [rank] bytes claimed so far

@@ -108,7 +108,7 @@ int ctl_pc_invalidate(ctl_handle_s *h)
 static GVec ts_vec(const PcState &st, const double *v, int n_loc)
 {
     if (!st.px0) return GVec(v);
-    return GVec(v, v + n_loc, HaloWait());
+    return GVec(v, v + n_loc);
 }
 
 static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
@@ -131,7 +131,7 @@ static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
         } else {
             CTL_TRY(amg_solve(h, st.hier[st.fwd_h[i]], bi, st.Uf + i * S, false));
         }
-        CTL_TRY(halo_persist(h, st.px0, st.Uf + i * S + nl));      // later products read its ghost entries
+        CTL_TRY(halo_unpack(h, st.px0, st.Uf + i * S + nl));      // later products read its ghost entries
     }
     // middle scaling fused with the backward right-hand sides
     // (control/control.py:2118-2133 + 2158-2168 CN; 2330-2350 + 2375-2385 BE)
@@ -153,7 +153,7 @@ static int enqueue_sweeps(ctl_handle_s *h, PcState &st)
             CTL_TRY(sell_spmv2(h, st.Msell, st.Msell, ui, GVec(), un, bi, a, 1.0, push));
         }
         CTL_TRY(amg_solve(h, st.hier[st.bwd_h[i]], bi, st.Ub + i * S, true));
-        if (i > 0) CTL_TRY(halo_persist(h, st.px0, st.Ub + i * S + nl));
+        if (i > 0) CTL_TRY(halo_unpack(h, st.px0, st.Ub + i * S + nl));
     }
     return CTL_OK;
 }
@@ -419,7 +419,6 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
     CTL_TRY(sell_build_pattern(h, h->loc, st.fine));
     // multi-GPU: exchange geometry of everything that gathers through the mesh pattern, and the two level-0
     // exchange streams (iterates, right-hand sides) every hierarchy shares
-    int mesh_skip_lo = 0, mesh_skip_hi = 0;
     if (h->cfg.world > 1) {
         std::vector<int> part0(h->cfg.world + 1, 0);
         for (int r = 0; r < h->cfg.world; ++r) {
@@ -436,14 +435,9 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         CTL_TRY(halo_space_upload(h, geom, st.mesh_space));
         st.px0 = halo_arena_add(h, st.arena, st.mesh_space);
         st.pb0 = halo_arena_add(h, st.arena, st.mesh_space);
-        halo_skip_range(h->loc, h->n_loc, &mesh_skip_lo, &mesh_skip_hi);
     }
     auto mesh_matrix = [&](SellMat &m) {
-        if (h->cfg.world > 1) {
-            m.n_own = h->n_loc;
-            m.skip_lo = mesh_skip_lo;
-            m.skip_hi = mesh_skip_hi;
-        }
+        if (h->cfg.world > 1) m.n_own = h->n_loc;
     };
     std::vector<double> vals;
     combine_global(h, 0, false, 0.0, 1.0, false, vals);
@@ -661,7 +655,7 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
         CTL_CUDA(cudaMemcpy(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
         CTL_CUDA(cudaMemset(x, 0, nv * sizeof(double)));
     }
-    const GVec gb = L0.px ? GVec(b, b + n, HaloWait()) : GVec(b);
+    const GVec gb = L0.px ? GVec(b, b + n) : GVec(b);
     cudaEvent_t e0, e1;
     CTL_CUDA(cudaEventCreate(&e0));
     CTL_CUDA(cudaEventCreate(&e1));

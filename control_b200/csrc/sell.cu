@@ -59,9 +59,11 @@ MatView SellMat::view() const
     v.stab = stab;
     v.ps_off = ps_off;
     v.ps_w = ps_w;
-    for (int k = 0; k < ps_w && k < 8; ++k) {
+    v.ps_dmax = 0;
+    for (int k = 0; k < ps_w && k < SF_PS; ++k) {
         v.ps_delta[k] = ps[k].delta;
         v.ps_v[k] = ps[k].v;
+        v.ps_dmax = std::max(v.ps_dmax, ps[k].delta);
     }
     return v;
 }
@@ -82,7 +84,19 @@ int sell_max_fmt()
     return v;
 }
 
-// cap for the matrices that own their pattern (coarse AMG operators, transfers): CTL_SELL_FMT_COARSE
+// cap for the matrices that own their pattern (coarse AMG operators, transfers) while they are small enough to
+// stay in L2: CTL_SELL_FMT_COARSE.  Larger ones (3-D: the first Galerkin level of C3 has 18.5 M entries, 222 MB
+// plain) are bound by their stream and take the most compact exact format like the fine level.
+static int64_t coarse_plain_limit()
+{
+    static int64_t v = -1;
+    if (v < 0) {
+        v = 64ll << 20;
+        if (const char *e = getenv("CTL_COARSE_PLAIN_MB")) v = (int64_t)atoi(e) << 20;
+    }
+    return v;
+}
+
 static int sell_max_fmt_coarse()
 {
     static int v = -1;
@@ -178,7 +192,7 @@ static int sell_set_values_cap(ctl_handle_s *h, const std::shared_ptr<SellPatter
     CTL_TRY(upload_vec(h, &out.stab, V.stab));
     out.ps_off = V.ps_off;
     out.ps_w = V.ps_w;
-    for (int k = 0; k < V.ps_w && k < 8; ++k) out.ps[k] = V.stab[V.ps_off + k];
+    for (int k = 0; k < V.ps_w && k < SF_PS; ++k) out.ps[k] = V.stab[V.ps_off + k];
     if (V.fmt == FMT_DICT8) CTL_TRY(upload_vec(h, (uint8_t **)&out.code, V.code8));
     else if (V.fmt == FMT_DICT16 || V.fmt == FMT_STENCIL) CTL_TRY(upload_vec(h, (uint16_t **)&out.code, V.code16));
     return CTL_OK;
@@ -196,10 +210,14 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
     int sell_min_rows = 50000;
     if (const char *e = getenv("CTL_SELL_MIN_ROWS")) sell_min_rows = atoi(e);      // experiment
     const bool mesh_like = mean <= 10.0;          // fine-mesh stencils (short rows): always SELL
-    if (force_lanes == 0 && (mesh_like || (mean <= sell_max_mean && A.n_rows >= sell_min_rows))) {
+    // ... and so is a level with long rows once it has enough of them (3-D: the first Galerkin level of C3, 248 k rows
+    // of 75 entries): one thread per row streams coalesced indices and values (16-bit offsets: 10 B per entry),
+    // where the lane-per-entry CSR kernel took 91 us per product for the same 18.5 M entries
+    const bool many_rows = A.n_rows >= 100000;
+    if (force_lanes == 0 && (mesh_like || many_rows || (mean <= sell_max_mean && A.n_rows >= sell_min_rows))) {
         std::shared_ptr<SellPattern> pat;
         CTL_TRY(sell_build_pattern(h, A, pat));
-        return sell_set_values_cap(h, pat, A.values.data(), out, sell_max_fmt_coarse());
+        return sell_set_values_cap(h, pat, A.values.data(), out, 12 * A.nnz() > coarse_plain_limit() ? sell_max_fmt() : sell_max_fmt_coarse());
     }
     auto pat = std::make_shared<SellPattern>();     // sizes only; no SELL arrays
     pat->n_rows = A.n_rows;
@@ -221,7 +239,7 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
     a.indptr = A.indptr.data();
     a.indices = A.indices.data();
     SfCsrvData D;
-    sf_csrv_data(a, A.values.data(), std::min(sell_max_fmt_coarse(), (int)FMT_PK), D);
+    sf_csrv_data(a, A.values.data(), std::min(12 * A.nnz() > coarse_plain_limit() ? sell_max_fmt() : sell_max_fmt_coarse(), (int)FMT_PK), D);
     out.fmt = D.fmt;
     out.bytes_per_pass = D.bytes_per_pass;
     out.stream = D.bytes_per_pass > stream_threshold();
@@ -243,29 +261,52 @@ namespace {
 constexpr int ST = 128;      // threads per CTA of every kernel in this file
 constexpr int SC = 8;        // SELL entries fetched per thread before the first dependent gather
 
-// ---- a gathered vector on the device
+// ---- a gathered vector on the device: owned entries, and the ghosts either plainly stored (completed earlier) or
+// in the slot of the exchange that delivers them (halo.cuh)
 struct DVec {
     const double *x, *ghost;
+    const ulonglong2 *ll;
     int n_own;
-    __device__ __forceinline__ double operator()(int c) const { return halo_gather(x, ghost, n_own, c); }
+    unsigned idx1;
 };
+
+// seq_hi: the epoch bits of the running sequence numbers (halo_epoch_bits), read once per thread
+__device__ __forceinline__ double dvec_get(const DVec &v, int c, unsigned seq_hi, const HaloCtx &ctx)
+{
+    if (c < v.n_own) return __ldg(v.x + c);
+    if (v.ll) return halo_ll_read(v.ll + (c - v.n_own), seq_hi | v.idx1, ctx);
+    return __ldcg(v.ghost + (c - v.n_own));
+}
 
 // FMT_STENCIL: a slice whose 32 rows share one stencil reads (delta_k, value_k) through warp-uniform loads and
 // gathers x[row + delta_k] (coalesced); the other slices take the per-entry DICT16 path.
-template <typename G>
-__device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row, G g)
+// g: gather of a column that may be a ghost; g_own: gather of a column known to be owned (no ghost test)
+template <typename G, typename G0>
+__device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row, G g, G0 g_own)
 {
     const int s = row >> 5, lane = row & 31;
     const int4 s0 = __ldg(A.sp4 + s);
     double acc = 0.0;
     if (s0.z == A.ps_off) {
         // the most frequent stencil: offsets and values are kernel parameters, the only loads are the gathers
-        double xv[8];
+        // (in two halves of 8: a P1 triangle stencil has 7 entries, a P1 tetrahedron stencil 15)
+        const bool own = (s << 5) + 31 + A.ps_dmax < A.n_own;      // the whole slice stays inside the owned columns
 #pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = (j < A.ps_w) ? g(row + A.ps_delta[j]) : 0.0;
+        for (int h0 = 0; h0 < SF_PS; h0 += 8) {
+            if (h0 < A.ps_w) {
+                double xv[8];
+                if (own) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < A.ps_w) acc = fma(A.ps_v[j], xv[j], acc);
+                    for (int j = 0; j < 8; ++j) xv[j] = (h0 + j < A.ps_w) ? g_own(row + A.ps_delta[h0 + j]) : 0.0;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xv[j] = (h0 + j < A.ps_w) ? g(row + A.ps_delta[h0 + j]) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (h0 + j < A.ps_w) acc = fma(A.ps_v[h0 + j], xv[j], acc);
+            }
+        }
         return acc;
     }
     if (s0.z >= 0) {
@@ -300,10 +341,10 @@ __device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row
 // One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is divergence free;
 // entries are fetched in chunks of SC with all stream loads issued before the dependent gathers
 // (memory-level parallelism instead of a serial load -> gather -> fma chain per entry).
-template <int FMT, bool STREAM, typename G>
-__device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g)
+template <int FMT, bool STREAM, typename G, typename G0>
+__device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g, G0 g_own)
 {
-    if (FMT == FMT_STENCIL) return sell_row_dot_stencil(A, row, g);
+    if (FMT == FMT_STENCIL) return sell_row_dot_stencil(A, row, g, g_own);
     const int s = row >> 5, lane = row & 31;
     const int2 s0 = __ldg(A.sp + s);
     const int end = __ldg(reinterpret_cast<const int *>(A.sp + s + 1));
@@ -341,12 +382,12 @@ template <typename G>
 __device__ __forceinline__ double sell_row_dot_rt(const MatView &A, int row, G g)
 {
     switch (A.fmt) {
-    case FMT_F64: return sell_row_dot<FMT_F64, false>(A, row, g);
-    case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g);
-    case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g);
-    case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g);
-    case FMT_STENCIL: return sell_row_dot_stencil(A, row, g);
-    default: return sell_row_dot<FMT_DICT8, false>(A, row, g);
+    case FMT_F64: return sell_row_dot<FMT_F64, false>(A, row, g, g);
+    case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g, g);
+    case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g, g);
+    case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g, g);
+    case FMT_STENCIL: return sell_row_dot_stencil(A, row, g, g);
+    default: return sell_row_dot<FMT_DICT8, false>(A, row, g, g);
     }
 }
 
@@ -396,21 +437,20 @@ __device__ __forceinline__ double csrv_row_dot(const MatView &A, int row, int su
 }
 
 // Row assignment shared by every kernel: the push CTAs (halo.cuh) come first and compute the listed boundary
-// rows, one chunk of <= 32 rows per warp; the regular CTAs compute ST / T consecutive rows each.  f(row) is
-// evaluated by all T lanes of a row's group and returns the value to store in out[row].
+// rows, one chunk of <= 32 rows per warp, storing them locally and into the ghost slots of the ranks that gather
+// them; the regular CTAs compute ST / T consecutive rows each.  f(row) is evaluated by all T lanes of a row's
+// group and returns the value to store in out[row].
 template <int T, typename F>
-__device__ __forceinline__ void run_rows(int n_rows, const HaloWait &w0, const HaloWait &w1, const HaloPush &push,
-                                         double *out, F f)
+__device__ __forceinline__ void run_rows(int n_rows, const HaloPush &push, unsigned seq_hi, double *out, F f)
 {
     constexpr int RPC = ST / T;
     const int lane = threadIdx.x & 31;
     const int n_pc = (push.n_chunks + ST / 32 - 1) / (ST / 32);
     if ((int)blockIdx.x < n_pc) {
-        halo_wait(w0, -1, -1);
-        halo_wait(w1, -1, -1);
         const int ci = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
         if (ci >= push.n_chunks) return;
         const PushChunk ch = push.chunks[ci];
+        const unsigned seq = seq_hi | push.idx1;
 #pragma unroll 1
         for (int pass = 0; pass < T; ++pass) {
             const int idx = pass * (32 / T) + lane / T;
@@ -421,17 +461,14 @@ __device__ __forceinline__ void run_rows(int n_rows, const HaloWait &w0, const H
                 out[row] = v;
                 for (int d = 0; d < ch.n_dst; ++d) {
                     const PushDst t = push.dsts[ch.dst_begin + d];
-                    t.base[(long long)push.slot * t.stride + t.pos[idx]] = v;
+                    halo_ll_store(t.base + (long long)push.slot * t.stride + t.pos[idx], v, seq);
                 }
             }
         }
-        halo_push_publish(push, ch, lane);
         return;
     }
+    if (push.all_rows) return;
     const int r0 = ((int)blockIdx.x - n_pc) * RPC;
-    const int r1 = min(r0 + RPC, n_rows);
-    halo_wait(w0, r0, r1);
-    halo_wait(w1, r0, r1);
     const int row = r0 + (int)threadIdx.x / T;
     if (T == 1) {
         if (row < n_rows) out[row] = f(row);
@@ -453,12 +490,15 @@ __device__ __forceinline__ double apply_mode(int mode, double ax, const double *
 // ---------------------------------------------------------------- SELL kernels
 // GH: the gathered vector has ghost entries (several GPUs); without them the gather is a plain read-only load
 template <int FMT, bool STREAM, bool GH>
-__global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloWait w, const double *b,
+__global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
     pdl_sync();
-    run_rows<1>(A.n_rows, w, HaloWait(), push, y, [&](int row) {
-        const double ax = sign * sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return GH ? x(c) : __ldg(x.x + c); });
+    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    run_rows<1>(A.n_rows, push, hi, y, [&](int row) {
+        const double ax = sign * sell_row_dot<FMT, STREAM>(
+                                     A, row, [&](int c) { return GH ? dvec_get(x, c, hi, ctx) : __ldg(x.x + c); },
+                                     [&](int c) { return __ldg(x.x + c); });
         return apply_mode(mode, ax, b, row);
     });
 }
@@ -466,12 +506,15 @@ __global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DV
 template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
                                                       const double *__restrict__ b, const double *p_prev, const DVec p_cur,
-                                                      const HaloWait w, double *out, double a, double bq, double c,
+                                                      const HaloCtx ctx, double *out, double a, double bq, double c,
                                                       double prev_scale, const HaloPush push)
 {
     pdl_sync();
-    run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) { return GH ? p_cur(c) : __ldg(p_cur.x + c); });
+    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
+        const double ax = sell_row_dot<FMT, STREAM>(
+            A, row, [&](int cc) { return GH ? dvec_get(p_cur, cc, hi, ctx) : __ldg(p_cur.x + cc); },
+            [&](int cc) { return __ldg(p_cur.x + cc); });
         const double di = dinv[row], bi = b[row];
         double r = bq * p_cur.x[row] + c * di * (bi - ax);
         if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
@@ -481,14 +524,16 @@ __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const do
 }
 
 template <int FMT, bool STREAM, bool GH>
-__global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloWait w,
+__global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
     pdl_sync();
-    run_rows<1>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = sell_row_dot<FMT, STREAM>(A, row, [&](int c) {
-            return GH ? s * dinv(c) * b(c) : s * __ldg(dinv.x + c) * __ldg(b.x + c);
-        });
+    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
+        const double ax = sell_row_dot<FMT, STREAM>(
+            A, row,
+            [&](int c) { return GH ? s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx) : s * __ldg(dinv.x + c) * __ldg(b.x + c); },
+            [&](int c) { return s * __ldg(dinv.x + c) * __ldg(b.x + c); });
         const double di = dinv.x[row], bi = b.x[row];
         const double p1 = s * di * bi;
         return wgt * p1 + (wgt * s) * di * (bi - ax);
@@ -497,34 +542,36 @@ __global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const 
 
 __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const MatView A1, const MatView A2, const DVec x1, const DVec x2,
                                                        const DVec x3, double *y, double alpha, double beta,
-                                                       const HaloWait w, const HaloPush push)
+                                                       const HaloCtx ctx, const HaloPush push)
 {
     pdl_sync();
-    run_rows<1>(A1.n_rows, w, HaloWait(), push, y, [&](int row) {
+    const unsigned hi = halo_epoch_bits(ctx);
+    run_rows<1>(A1.n_rows, push, hi, y, [&](int row) {
         double acc1;
-        if (x2.x) acc1 = sell_row_dot_rt(A1, row, [&](int c) { return x1(c) + x2(c); });
-        else acc1 = sell_row_dot_rt(A1, row, x1);
+        if (x2.x) acc1 = sell_row_dot_rt(A1, row, [&](int c) { return dvec_get(x1, c, hi, ctx) + dvec_get(x2, c, hi, ctx); });
+        else acc1 = sell_row_dot_rt(A1, row, [&](int c) { return dvec_get(x1, c, hi, ctx); });
         double acc2 = 0.0;
-        if (x3.x) acc2 = sell_row_dot_rt(A2, row, x3);
+        if (x3.x) acc2 = sell_row_dot_rt(A2, row, [&](int c) { return dvec_get(x3, c, hi, ctx); });
         return alpha * acc1 + beta * acc2;
     });
 }
 
 __global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
-                                                       double *__restrict__ out, double c, int n, const HaloPush push)
+                                                       double *__restrict__ out, double c, int n, const HaloCtx ctx,
+                                                       const HaloPush push)
 {
     pdl_sync();
-    run_rows<1>(n, HaloWait(), HaloWait(), push, out, [&](int row) { return c * dinv[row] * b[row]; });
+    const unsigned hi = push.n_chunks ? halo_epoch_bits(ctx) : 0u;
+    run_rows<1>(n, push, hi, out, [&](int row) { return c * dinv[row] * b[row]; });
 }
 
 // Small dense matrix (the coarsest level: 2205 rows at C2, 39 MB, L2-resident): one CTA per GR rows, so that b is
 // read once per GR rows and every thread keeps GR independent 16-byte loads in flight
 constexpr int GR = 4;
 __global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
-                                                       double *__restrict__ y, int n, const HaloWait w)
+                                                       double *__restrict__ y, int n)
 {
     pdl_sync();
-    halo_wait(w, -1, -1);
     __shared__ double part[GR][ST / 32];
     const int r0 = blockIdx.x * GR;
     double acc[GR];
@@ -564,13 +611,14 @@ __global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict
 
 // ---------------------------------------------------------------- CSR-vector kernels
 template <int T, bool STREAM>
-__global__ void __launch_bounds__(ST) csrv_spmv_kernel(const MatView A, const DVec x, const HaloWait w, const double *b,
+__global__ void __launch_bounds__(ST) csrv_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
     pdl_sync();
+    const unsigned hi = halo_epoch_bits(ctx);
     const int sub = threadIdx.x % T;
-    run_rows<T>(A.n_rows, w, HaloWait(), push, y, [&](int row) {
-        const double ax = sign * csrv_row_dot<T, STREAM>(A, row, sub, x);
+    run_rows<T>(A.n_rows, push, hi, y, [&](int row) {
+        const double ax = sign * csrv_row_dot<T, STREAM>(A, row, sub, [&](int c) { return dvec_get(x, c, hi, ctx); });
         return apply_mode(mode, ax, b, row);
     });
 }
@@ -578,13 +626,14 @@ __global__ void __launch_bounds__(ST) csrv_spmv_kernel(const MatView A, const DV
 template <int T>
 __global__ void __launch_bounds__(ST) csrv_cheb_kernel(const MatView A, const double *__restrict__ dinv,
                                                       const double *__restrict__ b, const double *p_prev, const DVec p_cur,
-                                                      const HaloWait w, double *out, double a, double bq, double c,
+                                                      const HaloCtx ctx, double *out, double a, double bq, double c,
                                                       double prev_scale, const HaloPush push)
 {
     pdl_sync();
+    const unsigned hi = halo_epoch_bits(ctx);
     const int sub = threadIdx.x % T;
-    run_rows<T>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = csrv_row_dot<T, false>(A, row, sub, p_cur);
+    run_rows<T>(A.n_rows, push, hi, out, [&](int row) {
+        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int cc) { return dvec_get(p_cur, cc, hi, ctx); });
         const double di = dinv[row], bi = b[row];
         double r = bq * p_cur.x[row] + c * di * (bi - ax);
         if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
@@ -594,13 +643,14 @@ __global__ void __launch_bounds__(ST) csrv_cheb_kernel(const MatView A, const do
 }
 
 template <int T>
-__global__ void __launch_bounds__(ST) csrv_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloWait w,
+__global__ void __launch_bounds__(ST) csrv_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
     pdl_sync();
+    const unsigned hi = halo_epoch_bits(ctx);
     const int sub = threadIdx.x % T;
-    run_rows<T>(A.n_rows, w, HaloWait(), push, out, [&](int row) {
-        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int c) { return s * dinv(c) * b(c); });
+    run_rows<T>(A.n_rows, push, hi, out, [&](int row) {
+        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int c) { return s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx); });
         const double di = dinv.x[row], bi = b.x[row];
         const double p1 = s * di * bi;
         return wgt * p1 + (wgt * s) * di * (bi - ax);
@@ -612,11 +662,20 @@ DVec dvec(const GVec &g, const MatView &A)
     DVec d;
     d.x = g.x;
     d.ghost = g.ghost;
+    d.ll = g.ll;
     d.n_own = A.n_own;
+    d.idx1 = g.idx1;
     return d;
 }
 
-int grid_for(int n_rows, int T, const HaloPush &push) { return ceil_div((int64_t)n_rows * T, ST) + halo_push_ctas(push, ST); }
+bool has_ghosts(const GVec &g) { return g.ghost != nullptr || g.ll != nullptr; }
+
+// push CTAs first; a replicating exchange pushes every row, so the regular CTAs are not launched at all
+int grid_for(int n_rows, int T, const HaloPush &push)
+{
+    if (push.all_rows) return halo_push_ctas(push, ST);
+    return ceil_div((int64_t)n_rows * T, ST) + halo_push_ctas(push, ST);
+}
 
 #define SELL_LAUNCH_GH(KERNEL, FMT, STREAM, ...)                                                            \
     do {                                                                                                    \
@@ -672,20 +731,21 @@ int sell_spmv(ctl_handle_s *h, const SellMat &A, const GVec &x, double *y, const
     CTL_CHECK(push.n_chunks == 0 || b != y, CTL_ERR_STATE, "sell_spmv: an in-place product cannot push its boundary rows");
     const MatView V = A.view();
     const DVec dx = dvec(x, V);
+    const HaloCtx ctx = halo_ctx(h);
     if (A.lanes) {
         const int grid = grid_for(A.pat->n_rows, A.lanes, push);
         if (grid == 0) return CTL_OK;
 #define CSRV_SPMV(T)                                                                                                 \
     do {                                                                                                             \
-        if (A.stream) pdl_launch(h, grid, ST, csrv_spmv_kernel<T, true>, V, dx, x.wait, b, y, kmode, sign, push);    \
-        else pdl_launch(h, grid, ST, csrv_spmv_kernel<T, false>, V, dx, x.wait, b, y, kmode, sign, push);            \
+        if (A.stream) pdl_launch(h, grid, ST, csrv_spmv_kernel<T, true>, V, dx, ctx, b, y, kmode, sign, push);       \
+        else pdl_launch(h, grid, ST, csrv_spmv_kernel<T, false>, V, dx, ctx, b, y, kmode, sign, push);               \
     } while (0)
         if (A.lanes == 4) CSRV_SPMV(4);
         else if (A.lanes == 8) CSRV_SPMV(8);
         else CSRV_SPMV(16);
 #undef CSRV_SPMV
     } else {
-        SELL_DISPATCH(sell_spmv_kernel, A, x.ghost != nullptr, V, dx, x.wait, b, y, kmode, sign, push);
+        SELL_DISPATCH(sell_spmv_kernel, A, has_ghosts(x), V, dx, ctx, b, y, kmode, sign, push);
     }
     h->launches++;
     CTL_CUDA(cudaGetLastError());
@@ -699,8 +759,9 @@ int sell_cheb_step(ctl_handle_s *h, const SellMat &A, const double *dinv, const 
               "sell_cheb_step: a pushing step must not overwrite its inputs");
     const MatView V = A.view();
     const DVec dx = dvec(p_cur, V);
-    if (A.lanes) CSRV_DISPATCH(csrv_cheb_kernel, A, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
-    else SELL_DISPATCH(sell_cheb_kernel, A, p_cur.ghost != nullptr, V, dinv, b, p_prev, dx, p_cur.wait, out, a, bq, c, prev_scale, push);
+    const HaloCtx ctx = halo_ctx(h);
+    if (A.lanes) CSRV_DISPATCH(csrv_cheb_kernel, A, V, dinv, b, p_prev, dx, ctx, out, a, bq, c, prev_scale, push);
+    else SELL_DISPATCH(sell_cheb_kernel, A, has_ghosts(p_cur), V, dinv, b, p_prev, dx, ctx, out, a, bq, c, prev_scale, push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -711,8 +772,9 @@ int sell_cheb_first2(ctl_handle_s *h, const SellMat &A, const GVec &dinv, const 
 {
     const MatView V = A.view();
     const DVec dd = dvec(dinv, V), db = dvec(b, V);
-    if (A.lanes) CSRV_DISPATCH(csrv_first2_kernel, A, V, dd, db, b.wait, out, s, w, push);
-    else SELL_DISPATCH(sell_first2_kernel, A, b.ghost != nullptr || dinv.ghost != nullptr, V, dd, db, b.wait, out, s, w, push);
+    const HaloCtx ctx = halo_ctx(h);
+    if (A.lanes) CSRV_DISPATCH(csrv_first2_kernel, A, V, dd, db, ctx, out, s, w, push);
+    else SELL_DISPATCH(sell_first2_kernel, A, has_ghosts(b) || has_ghosts(dinv), V, dd, db, ctx, out, s, w, push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -722,16 +784,16 @@ int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double 
 {
     const int grid = grid_for(n, 1, push);
     if (grid == 0) return CTL_OK;
-    pdl_launch(h, grid, ST, dinv_scale_kernel, dinv, b, out, c, n, push);
+    pdl_launch(h, grid, ST, dinv_scale_kernel, dinv, b, out, c, n, halo_ctx(h), push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
 }
 
-int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, const HaloWait &wait)
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
 {
     if (n == 0) return CTL_OK;
-    pdl_launch(h, ceil_div(n, GR), ST, dense_gemv_kernel, Ainv, b, y, n, wait);
+    pdl_launch(h, ceil_div(n, GR), ST, dense_gemv_kernel, Ainv, b, y, n);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
@@ -744,11 +806,7 @@ int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec
     const int grid = grid_for(A1.pat->n_rows, 1, push);
     if (grid == 0) return CTL_OK;
     const MatView V1 = A1.view(), V2 = A2.view();
-    // at most one of the gathered vectors arrives with this launch (the others were completed earlier)
-    HaloWait w = x1.wait;
-    if (x2.wait.n_flags) w = x2.wait;
-    if (x3.wait.n_flags) w = x3.wait;
-    pdl_launch(h, grid, ST, sell_spmv2_kernel, V1, V2, dvec(x1, V1), dvec(x2, V1), dvec(x3, V2), y, alpha, beta, w, push);
+    pdl_launch(h, grid, ST, sell_spmv2_kernel, V1, V2, dvec(x1, V1), dvec(x2, V1), dvec(x3, V2), y, alpha, beta, halo_ctx(h), push);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;

@@ -40,13 +40,12 @@ struct SellMat {
     int4 *sp4 = nullptr;               // FMT_STENCIL
     DictEnt *stab = nullptr;
     int ps_off = -2, ps_w = 0;         // FMT_STENCIL: most frequent stencil (kernel-parameter copy in view())
-    DictEnt ps[8];
+    DictEnt ps[SF_PS];
     // CSR-vector form (lanes > 0): owns all of its arrays
     int lanes = 0;
     int *csr_ptr = nullptr, *csr_cols = nullptr, *csr_rbase = nullptr;
     uint16_t *csr_dcol = nullptr;
     double *csr_vals = nullptr;
-    int skip_lo = 0, skip_hi = 0;      // multi-GPU: rows in [skip_lo, skip_hi) gather no ghost column (their CTAs do not wait)
 
     int n_rows() const { return pat->n_rows; }
     bool valid() const { return pat != nullptr; }
@@ -73,15 +72,18 @@ enum SellMode {
     SELL_BPLUS = 4        // y  = b + A x
 };
 
-// A gathered vector: owned entries and (multi-GPU) the ghost entries behind them.  `wait` = the exchange whose
-// arrival the kernel has to see before it gathers (none when the ghosts were completed earlier).
+// A gathered vector: owned entries and (multi-GPU) its ghost entries, either stored plainly (completed earlier) or
+// still in the slot of the exchange that delivers them (`ll`, with the exchange's index + 1: the gathering kernel
+// spins on the entries it reads, halo.cuh).
 struct GVec {
     const double *x = nullptr;
     const double *ghost = nullptr;
-    HaloWait wait;
+    const ulonglong2 *ll = nullptr;
+    unsigned idx1 = 0;
     GVec() {}
     GVec(const double *x_) : x(x_) {}
-    GVec(const double *x_, const double *g_, const HaloWait &w) : x(x_), ghost(g_), wait(w) {}
+    GVec(const double *x_, const double *g_) : x(x_), ghost(g_) {}
+    GVec(const double *x_, const ulonglong2 *ll_, unsigned idx1_) : x(x_), ll(ll_), idx1(idx1_) {}
 };
 
 int sell_spmv(ctl_handle_s *h, const SellMat &A, const GVec &x, double *y, const double *b, int mode,
@@ -100,7 +102,7 @@ int sell_cheb_first2(ctl_handle_s *h, const SellMat &A, const GVec &dinv, const 
 int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n,
                    const HaloPush &push = HaloPush());
 // y = Ainv b, dense row-major n x n
-int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, const HaloWait &wait = HaloWait());
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n);
 // two-matrix product on one shared row set (backward-sweep right-hand side, pc.cu):
 //   y = alpha * A1 (x1 + x2) + beta * A2 x3      (x2, x3 may be null)
 int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec &x1, const GVec &x2, const GVec &x3,

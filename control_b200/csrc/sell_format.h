@@ -39,6 +39,11 @@
 
 enum SellFmt { FMT_F64 = 0, FMT_D16 = 1, FMT_PK = 2, FMT_DICT16 = 3, FMT_DICT8 = 4, FMT_STENCIL = 5 };
 constexpr unsigned SF_ESCAPE = 0xFFFFu;
+constexpr int SF_PS = 16;         // longest stencil that can travel with the kernel parameters
+// Dictionaries must stay L1-resident: a lookup with 32 different codes per warp is a gather, and a gather from L2
+// costs as much as the one from x it feeds (measured: a 9175-pair dictionary made the 175 k-row level of C2 slower than
+// the plain format).  4096 entries = 32 KB (values) / 64 KB (pairs).
+constexpr int SF_DICT_MAX = 4096;
 
 struct alignas(16) DictEnt {
     int delta;       // column - row
@@ -64,10 +69,11 @@ struct MatView {
     const int4 *sp4 = nullptr;        // STENCIL: per slice (first stored position, width, stencil offset or -1, 0)
     const DictEnt *stab = nullptr;    // STENCIL: the stencils, `width` entries each
     // STENCIL: the most frequent stencil travels with the kernel parameters (constant bank: its offsets and values
-    // cost no load instructions); ps_off = its offset in stab (-2: none), at most 8 entries
+    // cost no load instructions); ps_off = its offset in stab (-2: none), at most SF_PS entries (15 = P1 tetrahedra)
     int ps_off = -2, ps_w = 0;
-    int ps_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double ps_v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int ps_dmax = 0;                  // largest offset of that stencil: rows below n_own - ps_dmax gather no ghost
+    int ps_delta[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double ps_v[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 template <bool STREAM, typename T>
@@ -271,7 +277,7 @@ struct SfSellValues {
     std::vector<DictEnt> dict;       // DICT8 / DICT16 / STENCIL
     std::vector<int4> sp4;           // STENCIL
     std::vector<DictEnt> stab;       // STENCIL
-    int ps_off = -2, ps_w = 0;       // STENCIL: most frequent stencil (offset in stab, width), -2: none with <= 8 entries
+    int ps_off = -2, ps_w = 0;       // STENCIL: most frequent stencil (offset in stab, width), -2: none short enough
     double uniform_fraction = 0.0;   // share of the slices whose 32 rows carry one stencil
     int64_t bytes_per_pass = 0;      // matrix stream bytes of one product
 };
@@ -284,7 +290,7 @@ inline void sf_sell_values(const SfSellLayout &L, const double *csr_values, int 
     V = SfSellValues();
     // 1. (column - row, value) dictionary: square-ish matrices only (the padding entries point at their own row)
     if (max_fmt >= FMT_DICT16 && L.n_cols >= L.n_rows) {
-        SfPairTable tab(65536);
+        SfPairTable tab(SF_DICT_MAX);
         std::vector<uint16_t> code((size_t)ns);
         std::vector<double> sv((size_t)ns, 0.0);
         for (int64_t k = 0; k < L.nnz; ++k) sv[L.csr_to_sell[k]] = csr_values[k];
@@ -345,7 +351,7 @@ inline void sf_sell_values(const SfSellLayout &L, const double *csr_values, int 
                     V.fmt = FMT_STENCIL;
                     int64_t best = 0;
                     for (size_t q = 0; q < known.size(); ++q)
-                        if (known[q].first.size() <= 8 && known_count[q] > best) {
+                        if ((int)known[q].first.size() <= SF_PS && known_count[q] > best) {
                             best = known_count[q];
                             V.ps_off = known[q].second;
                             V.ps_w = (int)known[q].first.size();
@@ -372,7 +378,7 @@ inline void sf_sell_values(const SfSellLayout &L, const double *csr_values, int 
     }
     // 2. value dictionary next to 16-bit column offsets
     if (max_fmt >= FMT_PK && !L.dcol.empty()) {
-        SfPairTable tab(65536);
+        SfPairTable tab(SF_DICT_MAX);
         std::vector<uint16_t> code((size_t)ns, 0);
         bool ok = tab.code(0, 0.0) == 0;          // padding entries: code 0 = 0.0
         for (int64_t k = 0; k < L.nnz && ok; ++k) {
@@ -440,7 +446,7 @@ inline void sf_csrv_data(const SfCsr &A, const double *values, int max_fmt, SfCs
     D.fmt = FMT_D16;
     D.bytes_per_pass = 10 * nnz;
     if (max_fmt < FMT_PK) return;
-    SfPairTable tab(65536);
+    SfPairTable tab(SF_DICT_MAX);
     std::vector<uint16_t> code((size_t)nnz);
     for (int64_t k = 0; k < nnz; ++k) {
         const int c = tab.code(0, values[k]);

@@ -222,7 +222,14 @@ int main()
 {
     check_sell("uniform 7-point stencil", mesh_stencil(300, 217, false, 0), FMT_STENCIL);
     check_sell("stencil + ghost columns", mesh_stencil(300, 230, false, 300), FMT_STENCIL);
-    check_sell("random values (small)", mesh_stencil(97, 53, true, 0), FMT_DICT16);      // fewer than 65536 entries
+    check_sell("random values (small)", mesh_stencil(97, 53, true, 0), FMT_D16);      // more pairs than a dictionary may hold
+    {
+        // a few hundred distinct (offset, value) pairs, rows all different: per-entry dictionary codes
+        Csr A = mesh_stencil(120, 90, false, 0);
+        for (int r = 0; r < A.n_rows; ++r)
+            for (int k = A.ip[r]; k < A.ip[r + 1]; ++k) A.v[k] = 0.25 * (double)((r * 31 + 7 * (k - A.ip[r])) % 300) - 20.0;
+        check_sell("300 values x 7 offsets", A, FMT_DICT16);
+    }
     check_sell("random values", mesh_stencil(397, 253, true, 0), FMT_D16);
     {
         // prolongation-like: n x n/6, 3 entries per row, 40 distinct values
