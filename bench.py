@@ -33,13 +33,23 @@ UNIT = "s"
 
 
 def ncu_traffic(key, args):
-    """DRAM bytes per launch from the committed ncu capture (only valid for the C2 sizes)."""
-    if args.nx != 1024 or args.n_t != 64 or args.gpus != 1:
+    """DRAM bytes per launch from the committed ncu --set full capture of the same kernel (only valid for the C2 sizes on
+    one GPU; profiles/r02_traffic.json names the capture of every entry)."""
+    if args.workload != "heat" or args.nx != 1024 or args.n_t != 64 or args.gpus != 1:
         return None
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]["bytes"]
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[key]["bytes"]
     except Exception:
         return None
+
+
+def amg_options(text):
+    """"cycles=2,nu=4" -> {"cycles": 2, "nu": 4} (keys of MultiBlockSystem.setup_preconditioner / oracle.amg.DEFAULTS)."""
+    out = {}
+    for kv in filter(None, (text or "").split(",")):
+        k, v = kv.split("=")
+        out[k.strip()] = float(v) if "." in v else int(v)
+    return out
 
 
 def measured_peak():
@@ -110,7 +120,8 @@ ITERATION_COUNTS = os.path.join(ROOT, "profiles", "iteration_counts.json")
 
 
 def problem_key(args):
-    return f"{args.workload}/{args.nx}/{args.n_t}/{args.ksp}/{args.rtol:g}"
+    key = f"{args.workload}/{args.nx}/{args.n_t}/{args.ksp}/{args.rtol:g}"
+    return key + (f"/{args.amg}" if args.amg else "")
 
 
 def known_iterations(args):
@@ -118,10 +129,19 @@ def known_iterations(args):
     GPU arm and committed in profiles/iteration_counts.json; --ref_its overrides."""
     if args.ref_its is not None:
         return args.ref_its, "--ref_its"
+    rec = n1_expectation(args)
+    if rec is not None:
+        return int(rec["iterations"]), "profiles/iteration_counts.json (GPU arm)"
+    return 15, "assumed (no GPU record for this configuration)"
+
+
+def n1_expectation(args):
+    """Iterations and true residual of this configuration on one GPU (committed record), or None."""
     try:
-        return int(json.load(open(ITERATION_COUNTS))[problem_key(args)]), "profiles/iteration_counts.json (GPU arm)"
+        rec = json.load(open(ITERATION_COUNTS))[problem_key(args)]
+        return rec if isinstance(rec, dict) else {"iterations": int(rec), "kkt_residual": None}
     except Exception:
-        return 15, "assumed (no GPU record for this configuration)"
+        return None
 
 
 class CpuArm:
@@ -130,7 +150,7 @@ class CpuArm:
         self.threads = fastpc.set_threads()      # explicitly all cores: torchrun exports OMP_NUM_THREADS=1
         self.fastpc = fastpc
         self.pc = fastpc.FastPc(q["M"], q["K"], q["tau"], q["beta"], q["n_t"], CN, q["bdofs"],
-                                lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
+                                lambda_v_bounds=q["lambda_v_bounds"], mode=mode, amg_params=amg_options(args.amg) or None)
         rng = np.random.default_rng(0)
         N, n = self.pc.N, self.pc.n
         self.x0 = rng.standard_normal((N, n))
@@ -189,20 +209,28 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def inner_text(args):
+    a = {"cycles": 3, "nu": 3, **amg_options(args.amg)}
+    return (f"{a['cycles']} aggregation-AMG V({a['nu']},{a['nu']}) cycles (the reference: hypre BoomerAMG, "
+            f"pc_hypre_boomeramg_max_iter 2, control/control.py:2056-2067)")
+
+
 def config_dict(args):
     if args.workload == "c3":
         return {"workload": f"C3: 3-D heat control, P1 tetrahedra on the {args.nx}^3 unit-cube mesh, n_t={args.n_t}, "
                             f"backward Euler, beta=1e-4, {args.ksp}({args.restart}) + in-built block lower-triangular "
                             f"preconditioner (the reference's default Krylov parameters, control/control.py:3260-3266), "
                             f"rtol {args.rtol:g}, rows block-partitioned over {args.gpus} GPU(s)",
-                "n": (args.nx + 1) ** 3, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol,
-                "l2": "Krylov vectors (1.1 GB each) exceed L2; per-kernel micro-timings flush L2 between launches"}
+                "n": (args.nx + 1) ** 3, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol, "amg": args.amg or "library defaults",
+                "l2": "Krylov vectors (1.1 GB each) exceed L2; the per-kernel micro-timings rotate through operand sets of "
+                      "more than twice the L2 capacity (inputs larger than L2)"}
     return {"workload": f"C2: 2-D heat control, P1 on {args.nx}x{args.nx} mesh of (0,2)^2, n_t={args.n_t}, "
                         f"trapezoidal (CN), beta=1e-4, {args.ksp} + in-built block preconditioner "
                         f"({'block-diagonal SPD variant' if args.ksp == 'minres' else 'block lower-triangular'}), "
-                        f"rtol {args.rtol:g}",
-            "n": (args.nx + 1) ** 2, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol,
-            "l2": "Krylov vectors (1.08 GB each) exceed L2; per-kernel micro-timings flush L2 between launches"}
+                        f"inner solves: {inner_text(args)}, rtol {args.rtol:g}",
+            "n": (args.nx + 1) ** 2, "n_t": args.n_t, "ksp": args.ksp, "rtol": args.rtol, "amg": args.amg or "library defaults",
+            "l2": "Krylov vectors (1.08 GB each) exceed L2; the per-kernel micro-timings rotate through operand sets of "
+                  "more than twice the L2 capacity (inputs larger than L2)"}
 
 
 def run_stokes(args):
@@ -315,6 +343,11 @@ def main():
     ap.add_argument("--ref_its", type=int, default=None,
                     help="iteration count the reference arm scales its one timed iteration by (default: the GPU arm's "
                          "measured count for this configuration, profiles/iteration_counts.json)")
+    ap.add_argument("--amg", default=None,
+                    help="inner-solver parameters, e.g. cycles=2,nu=4 (both arms); default: cycles=2,nu=4 for the "
+                         "block-diagonal MINRES configuration of C2 -- two cycles as in the reference, 15 iterations as "
+                         "with the library default of three V(3,3) cycles (profiles/r02_amg_param_sweep.txt) -- and the "
+                         "library defaults otherwise")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_alt", action="store_true", help="skip the FGMRES + triangular PC side measurement")
     args = ap.parse_args()
@@ -324,6 +357,8 @@ def main():
             args.nx, args.n_t = 128, 32
         if args.ksp == "minres":
             args.ksp, args.restart = "gmres", 10
+    if args.amg is None:
+        args.amg = "cycles=2,nu=4" if (args.workload == "heat" and args.ksp == "minres") else ""
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "stokes":
@@ -356,7 +391,7 @@ def main():
     if world > 1:
         s.init_comm(dist)
     t0 = time.perf_counter()
-    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode)
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode, **amg_options(args.amg))
     setup_s = time.perf_counter() - t0
     b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], CN, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
     rows = slice(s.row_begin, s.row_begin + s.n_local)
@@ -432,7 +467,7 @@ def main():
                  "alg_bytes_per_launch": spmm_bytes, "ms_per_launch": spmm_ms,
                  "how": "CUDA events around every apply inside the timed solves"}
     # ---- roofline: dominant kernel of the step = fine-level smoother SpMV of the AMG sweeps
-    micro = s.micro_benchmarks(flush_l2=True) if hasattr(s, "micro_benchmarks") else None
+    micro = s.micro_benchmarks(reps=20, flush_l2=True) if hasattr(s, "micro_benchmarks") else None
     roof = roof_spmm
     if micro:
         roof = {"kernel": "sell_cheb_kernel, AMG level 0 (smoother step of the time sweeps)", "bound": "hbm",
@@ -440,7 +475,17 @@ def main():
                 "frac": micro["cheb_bytes"] / micro["cheb_ms"] / 1e6 / peak,
                 "traffic": ncu_traffic("sell_cheb_kernel_level0_C2", args),
                 "alg_bytes_per_launch": micro["cheb_bytes"], "ms_per_launch": micro["cheb_ms"],
-                "how": "CUDA events per launch, L2 flushed between launches"}
+                "how": "CUDA events around 20 launches on the library's stream, every launch on its own operand set, "
+                       "the sets rotating through > 2 x L2 (inputs larger than L2); alg_bytes = the bytes of the exact "
+                       "compressed matrix format in use + 5 vectors; SURVEY 8(d)'s CSR model of the same product "
+                       "(12 nnz + 40 n) is in survey_model",
+                "survey_model": {"alg_bytes_per_launch": 12.0 * nnz + 40.0 * n,
+                                 "achieved": (12.0 * nnz + 40.0 * n) / micro["cheb_ms"] / 1e6,
+                                 "frac": (12.0 * nnz + 40.0 * n) / micro["cheb_ms"] / 1e6 / peak},
+                "inner_solve": {"ms": micro["inner_solve_ms"], "alg_bytes": micro["inner_solve_bytes"],
+                                "kernels": micro["inner_solve_kernels"],
+                                "achieved": micro["inner_solve_bytes"] / micro["inner_solve_ms"] / 1e6,
+                                "frac": micro["inner_solve_bytes"] / micro["inner_solve_ms"] / 1e6 / peak}}
     pc_s = sum(i.seconds_pc for i in infos) / max(1, sum(i.n_pc for i in infos))
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -454,12 +499,21 @@ def main():
             "roofline": roof, "roofline_spmm": roof_spmm,
             "e2e": {"value": e2e_s, "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": nbytes},
             "gpu_launches": int(launches), "clocks": clocks.summary()}
+    exp = n1_expectation(args)
+    if exp is not None:
+        # the same solve on any number of GPUs must reproduce the one-GPU record: identical iteration count, true
+        # residual equal up to the summation order of the partitioned products
+        res_exp = exp.get("kkt_residual")
+        line["parity_vs_1gpu"] = {"expected_iterations": exp["iterations"], "iterations_match": info.its == exp["iterations"],
+                                  "expected_kkt_residual": res_exp,
+                                  "kkt_residual_rel_diff": (abs(res_norm - res_exp) / res_exp) if res_exp else None,
+                                  "source": "profiles/iteration_counts.json"}
     if micro:
         line["kernels"] = micro
     if args.ksp == "minres" and not args.no_alt:
         # the reference-faithful mode next to the configuration BASELINE.json names: block
         # lower-triangular in-built preconditioner + FGMRES(30) (control/control.py:1943-2440)
-        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode="triangular")
+        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode="triangular")      # library defaults: 3 V(3,3) cycles
         sp2 = solver_parameters("fgmres", args.rtol)
         for _ in range(2):
             u2 = s.new_vector()
@@ -470,7 +524,7 @@ def main():
             a1.record()
             barrier()
         line["alt_fgmres_triangular"] = {"value": max_over_ranks(a0.elapsed_time(a1) * 1e-3), "unit": UNIT,
-                                         "iterations": i2.its, "converged_reason": i2.reason,
+                                         "amg": "cycles=3,nu=3 (library defaults)", "iterations": i2.its, "converged_reason": i2.reason,
                                          "kkt_residual": s.residual_norm(b_dev, u2)}
     if rank == 0 and not args.no_cpu_baseline:
         t0 = time.perf_counter()

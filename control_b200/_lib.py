@@ -91,6 +91,7 @@ SIGNATURES = {
     "ctl_solve_host": (C.c_int, [_H, _F64P, _F64P, C.POINTER(ctl_krylov_options),
                                  C.POINTER(ctl_solve_result)]),
     "ctl_kkt_residual_norm": (C.c_int, [_H, _F64P, _F64P, C.c_int, C.POINTER(C.c_double)]),
+    "ctl_nonlinear_residual": (C.c_int, [_H, _F64P, _F64P, _F64P, C.c_int, C.POINTER(C.c_double)]),
     "ctl_objective_host": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
     "ctl_objective": (C.c_int, [_H, _F64P, _F64P, _F64P, C.POINTER(C.c_double)]),
     "ctl_build_rhs": (C.c_int, [_H, _F64P, _F64P, _F64P, _F64P]),

@@ -99,7 +99,9 @@ int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
                 CTL_TRY(sell_from_csr(h, Lh.P, Ld.P));
                 CTL_TRY(sell_from_csr(h, Lh.R, Ld.R));
             } else if (!Lh.Ainv.empty()) {
-                CTL_TRY(ctl_upload(h, &Ld.Ainv, Lh.Ainv.data(), Lh.Ainv.size()));
+                CTL_TRY(dense_inverse_upload(h, Lh.Ainv, Ld.n, &Ld.Ainv, &Ld.Ainv_ld));
+            } else if (Lh.coarse_inverse) {
+                CTL_TRY(dense_inverse_device(h, Lh.A, Lh.coarse_shift, &Ld.Ainv, &Ld.Ainv_ld));
             }
         }
     }
@@ -205,7 +207,7 @@ static int vcycle(ctl_handle_s *h, AmgHierarchyDev &H, int l, const GVec &b, dou
     AmgLevelDev &L = H.dev[l];
     const int last = (int)H.dev.size() - 1;
     if (l == last) {
-        if (L.Ainv) return dense_gemv(h, L.Ainv, b.x, x, L.n);
+        if (L.Ainv) return dense_gemv(h, L.Ainv, b.x, x, L.n, L.Ainv_ld);
         return smooth(h, H.params, L, l, b, x_is_zero ? nullptr : x, x);
     }
     AmgLevelDev &C = H.dev[l + 1];

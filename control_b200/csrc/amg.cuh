@@ -12,7 +12,8 @@ struct AmgLevelDev {
     double *dinv = nullptr;               // n + n_ghost (the ghost part is filled once at setup)
     double *x = nullptr, *b = nullptr;    // owned on levels >= 1 (level 0 uses the caller's)
     double *r = nullptr, *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;   // residual / smoother work vectors
-    double *Ainv = nullptr;               // dense inverse on the last level
+    double *Ainv = nullptr;               // dense inverse on the last level, rows padded to Ainv_ld (even)
+    int Ainv_ld = 0;
     HaloPlan *px = nullptr, *pb = nullptr;   // exchanges of the iterates / of the right-hand side (distributed levels)
     HaloPlan *pr = nullptr;               // level 0: exchange of the residual for the restriction (the level-0 space is
                                           // the mesh pattern, shared by every hierarchy; R's columns are not in it)
@@ -33,6 +34,12 @@ struct AmgHierarchyDev {
 int amg_build(ctl_handle_s *h, const HostCSR &A0, const AmgParams &p,
               const std::shared_ptr<SellPattern> &fine_pattern, AmgHierarchyDev &H);
 void amg_free(AmgHierarchyDev &H);
+// dense_inverse.cu: (A + shift shift^T)^-1 (- shift shift^T when shift is given: the pseudo-inverse of a singular
+// symmetric A with normalised kernel vector shift), computed on the device with the host algorithm's arithmetic;
+// row-major with row stride *lda_out
+int dense_inverse_device(ctl_handle_s *h, const HostCSR &A, const std::vector<double> &shift, double **Ainv_out, int *lda_out);
+// upload of an inverse computed on the host (row-major n x n) into the padded device layout
+int dense_inverse_upload(ctl_handle_s *h, const std::vector<double> &Ainv, int n, double **Ainv_out, int *lda_out);
 // x = `cycles` V-cycles from a zero guess for A x = b (level-0 vectors supplied by the caller).
 // Multi-GPU: b_exchanged says that the producer of b has already pushed its boundary rows (level-0 right-hand-side
 // plan); the boundary rows of x are pushed by the last kernel of the solve (level-0 iterate plan).

@@ -377,7 +377,8 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
     }
     AmgLevelHost &last = levels.back();
     if (last.A.n_rows <= 4096 && p.coarse == AMG_COARSE_INVERSE) {
-        dense_inverse(last.A, {}, last.Ainv);
+        if (p.device_inverse) last.coarse_inverse = AMG_COARSE_INVERSE + 1;
+        else dense_inverse(last.A, {}, last.Ainv);
     } else if (last.A.n_rows <= 4096 && p.coarse == AMG_COARSE_PINV_CONSTANT) {
         // kernel of the coarsest Galerkin operator = the coarse image of the constants
         const int nc = last.A.n_rows;
@@ -386,9 +387,14 @@ void amg_setup_host(const HostCSR &A0, const AmgParams &p, std::vector<AmgLevelH
         nn = std::sqrt(nn);
         std::vector<double> e(nc);
         for (int i = 0; i < nc; ++i) e[i] = cand[i] / nn;
-        dense_inverse(last.A, e, last.Ainv);
-        for (int i = 0; i < nc; ++i)
-            for (int j = 0; j < nc; ++j) last.Ainv[(size_t)i * nc + j] -= e[i] * e[j];
+        if (p.device_inverse) {
+            last.coarse_inverse = AMG_COARSE_PINV_CONSTANT + 1;
+            last.coarse_shift = e;
+        } else {
+            dense_inverse(last.A, e, last.Ainv);
+            for (int i = 0; i < nc; ++i)
+                for (int j = 0; j < nc; ++j) last.Ainv[(size_t)i * nc + j] -= e[i] * e[j];
+        }
     }
     timer.lap("coarse solve", (int)levels.size() - 1);
 }

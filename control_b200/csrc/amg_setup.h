@@ -22,6 +22,9 @@ struct AmgParams {
     int cycles = 3;      // see oracle/amg.py::solve for why not the reference's 2
     double acc_lo = 0.0, acc_hi = 1.0;   // > 0: Chebyshev-accelerated cycles (oracle/amg.py::solve)
     int coarse = 0;                      // AMG_COARSE_*: what happens on the coarsest level
+    int device_inverse = 1;              // 1: the dense inverse of the coarsest level is left to the device
+                                         // (dense_inverse.cu: 2205 rows at C2 = 5 s on one host core, 50 ms on the GPU);
+                                         // 0: computed here (host-only checks)
 };
 
 struct AmgLevelHost {
@@ -30,7 +33,10 @@ struct AmgLevelHost {
     double rho = 0.0;          // Gershgorin bound of D^-1 A
     std::vector<int> agg;      // aggregate id per row (-1 = not aggregated); empty on the last level
     HostCSR P, R;              // prolongation (n x n_coarse) and R = P^T; empty on the last level
-    std::vector<double> Ainv;  // dense inverse, row-major (last level, n <= 4096)
+    std::vector<double> Ainv;  // dense inverse, row-major (last level, n <= 4096); empty when left to the device:
+    int coarse_inverse = 0;    // ... then AMG_COARSE_INVERSE + 1 / AMG_COARSE_PINV_CONSTANT + 1 says what to compute,
+    std::vector<double> coarse_shift;   // and this is the normalised kernel vector of the pseudo-inverse
+    bool has_inverse() const { return !Ainv.empty() || coarse_inverse != 0; }
 };
 
 // A must have sorted column indices.  Returns the levels, finest first.

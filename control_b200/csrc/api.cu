@@ -5,7 +5,6 @@
 #include <cstring>
 
 #include "common.cuh"
-#include "kkt_plan.h"
 
 static thread_local std::string g_create_error;
 
@@ -123,14 +122,6 @@ int ctl_destroy(ctl_handle h)
     cudaFree(h->d_K);
     cudaFree(h->d_bcmask);
     cudaFree(h->d_bc_rows_all);
-    cudaFree(h->d_rec);
-    cudaFree(h->d_rec_off);
-    cudaFree(h->d_gptr);
-    cudaFree(h->d_gcols);
-    cudaFree(h->d_gvals);
-    cudaFree(h->d_tile_uptr);
-    cudaFree(h->d_tile_ucols);
-    cudaFree(h->d_tile_slot);
     cudaFree(h->d_halo);
     cudaFree(h->d_red);
     if (h->h_red) cudaFreeHost(h->h_red);
@@ -248,10 +239,6 @@ static int build_local_pattern(ctl_handle_s *h)
         h->max_row_len = std::max(h->max_row_len, ip[g + 1] - ip[g]);
     }
     if (const char *e = getenv("CTL_KKT_UNSTAGED")) h->force_unstaged = (e[0] == '1');
-    if (const char *e = getenv("CTL_KKT_GROUP")) {
-        const int R = atoi(e);
-        h->group_R = (R == 2 || R == 4) ? R : 0;
-    }
     {   // gather chunk with the fewest padding slots over all rows (ties: the larger chunk)
         const int cand[4] = {4, 5, 7, 8};
         long best = -1;
@@ -266,64 +253,9 @@ static int build_local_pattern(ctl_handle_s *h)
                 h->gather_chunk = c;
             }
         }
-        if (const char *e = getenv("CTL_KKT_CHUNK")) h->gather_chunk = atoi(e);
-    }
-    h->no_tma = true;      // the TMA-staged apply is opt-in (CTL_KKT_TMA=1): measured slower than the LDG-gather kernel
-    if (const char *e = getenv("CTL_KKT_TMA")) {
-        h->no_tma = !(e[0] >= '1' && e[0] <= '4');
-        h->tma_pipe = (e[0] == '2' || e[0] == '3' || e[0] == '4');
-        h->tma_rec = (e[0] == '3' || e[0] == '4');
-        h->tma_ws = (e[0] == '4');
-    }
-    // tile plan for the TMA-staged apply: unique gathered columns per block of 32 rows
-    {
-        int TR = 32;
-        if (const char *e = getenv("CTL_TILE_ROWS")) TR = atoi(e) == 16 ? 16 : 32;
-        const int nblk = (nl + TR - 1) / TR;
-        // per block: the sorted unique columns, stored as maximal runs of consecutive columns
-        // (col_start, length, slot_start) so that one bulk copy moves a whole run
-        std::vector<int> uptr(nblk + 1, 0), ucols, tmp;
-        std::vector<int> utot(nblk, 0);
-        std::vector<uint8_t> slot(L.indices.size(), 0);
-        int umax = 0;
-        bool ok = true;
-        for (int b = 0; b < nblk && ok; ++b) {
-            const int r0 = b * TR, r1 = std::min(nl, r0 + TR);
-            tmp.assign(L.indices.begin() + L.indptr[r0], L.indices.begin() + L.indptr[r1]);
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-            if (tmp.size() > 255) ok = false;
-            umax = std::max(umax, (int)tmp.size());
-            for (int k = L.indptr[r0]; k < L.indptr[r1] && ok; ++k)
-                slot[k] = (uint8_t)(std::lower_bound(tmp.begin(), tmp.end(), L.indices[k]) - tmp.begin());
-            for (size_t i = 0; i < tmp.size();) {
-                size_t j = i + 1;
-                while (j < tmp.size() && tmp[j] == tmp[j - 1] + 1 && (tmp[j] < nl) == (tmp[i] < nl)) ++j;
-                ucols.push_back(tmp[i]);
-                ucols.push_back((int)(j - i));
-                ucols.push_back((int)i);
-                i = j;
-            }
-            utot[b] = (int)tmp.size();
-            uptr[b + 1] = (int)ucols.size() / 3;
-        }
-        // the per-block unique counts ride behind the run table
-        const size_t n_runs = ucols.size() / 3;
-        ucols.insert(ucols.end(), utot.begin(), utot.end());
-        h->tile_count_off = (int)(3 * n_runs);
-        cudaFree(h->d_tile_uptr);
-        cudaFree(h->d_tile_ucols);
-        cudaFree(h->d_tile_slot);
-        h->d_tile_uptr = h->d_tile_ucols = nullptr;
-        h->d_tile_slot = nullptr;
-        h->tile_rows = 0;
-        if (ok && nblk > 0) {
-            CTL_TRY(ctl_upload(h, &h->d_tile_uptr, uptr.data(), uptr.size()));
-            CTL_TRY(ctl_upload(h, &h->d_tile_ucols, ucols.data(), ucols.size()));
-            CTL_TRY(ctl_upload(h, &h->d_tile_slot, slot.data(), slot.size()));
-            h->tile_rows = TR;
-            h->tile_umax = umax;
-            if (h->tma_rec) h->h_tile_slot = slot;
+        if (const char *e = getenv("CTL_KKT_CHUNK")) {      // experiment: only the instantiated chunk sizes
+            const int c = atoi(e);
+            if (c == 4 || c == 5 || c == 7 || c == 8) h->gather_chunk = c;
         }
     }
     // note: local column order within a row is no longer sorted when ghosts precede owned
@@ -389,61 +321,7 @@ int ctl_assemble(ctl_handle h)
         h->k_symmetric = sym;
         if (sym) h->d_KT = h->d_K;
         else CTL_TRY(ctl_upload(h, &h->d_KT, bt.data(), bt.size()));
-        // row-group plan (opt-in): union of the columns of R consecutive rows, R value pairs per union entry
-        h->group_ready = false;
-        if (h->group_R > 0 && sym && h->n_halo == 0 && h->ld == 64) {
-            const int R = h->group_R;
-            const int ng = (nl + R - 1) / R;
-            std::vector<int> gptr(ng + 1, 0), gcols, tmp;
-            std::vector<double> gvals;
-            gcols.reserve((size_t)nnz);
-            gvals.reserve((size_t)nnz * 2 * R);
-            int umax = 0;
-            for (int g = 0; g < ng; ++g) {
-                const int ra = g * R, rb_ = std::min(nl, ra + R);
-                tmp.assign(h->loc.indices.begin() + h->loc.indptr[ra], h->loc.indices.begin() + h->loc.indptr[rb_]);
-                std::sort(tmp.begin(), tmp.end());
-                tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-                const size_t base = gcols.size();
-                gcols.insert(gcols.end(), tmp.begin(), tmp.end());
-                gvals.resize((base + tmp.size()) * 2 * R, 0.0);
-                for (int r = ra; r < rb_; ++r)
-                    for (int p = h->loc.indptr[r]; p < h->loc.indptr[r + 1]; ++p) {
-                        const size_t u = base + (std::lower_bound(tmp.begin(), tmp.end(), h->loc.indices[p]) - tmp.begin());
-                        const double mval = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
-                        gvals[(u * R + (r - ra)) * 2 + 0] += mval;      // += : duplicate entries of a row accumulate
-                        gvals[(u * R + (r - ra)) * 2 + 1] += buf[p];
-                    }
-                gptr[g + 1] = (int)gcols.size();
-                umax = std::max(umax, (int)tmp.size());
-            }
-            cudaFree(h->d_gptr);
-            cudaFree(h->d_gcols);
-            cudaFree(h->d_gvals);
-            h->d_gptr = h->d_gcols = nullptr;
-            h->d_gvals = nullptr;
-            CTL_TRY(ctl_upload(h, &h->d_gptr, gptr.data(), gptr.size()));
-            CTL_TRY(ctl_upload(h, &h->d_gcols, gcols.data(), gcols.size()));
-            CTL_TRY(ctl_upload(h, &h->d_gvals, gvals.data(), gvals.size()));
-            h->group_umax = umax;
-            h->group_ready = true;
-        }
-        // record stream of the CTL_KKT_TMA=3 kernel: the CSR slice of every row block in the layout the kernel
-        // reads from shared memory, so that it arrives with one bulk copy (16-byte aligned offsets and sizes)
-        h->rec_max = 0;
-        if (h->tma_rec && h->tile_rows > 0 && !h->h_tile_slot.empty() && h->ld == 64) {
-            std::vector<double> mz(nnz);
-            for (int64_t p = 0; p < nnz; ++p) mz[p] = colmask(p) ? 0.0 : h->h_M[h->loc_entry[p]];
-            std::vector<uint8_t> rec;
-            std::vector<int> roff;
-            h->rec_max = kkt_build_block_records(h->tile_rows, nl, h->loc.indptr.data(), h->h_tile_slot.data(), mz.data(),
-                                                 buf.data(), sym ? nullptr : bt.data(), (size_t)h->ld * 8, rec, roff);
-            CTL_TRY(ctl_upload(h, &h->d_rec, rec.data(), rec.size()));
-            CTL_TRY(ctl_upload(h, &h->d_rec_off, roff.data(), roff.size()));
-        }
     } else {
-        h->group_ready = false;
-        h->rec_max = 0;
         // panels [nnz][ld]: column j of the K panel multiplies column j of X_v, i.e. level
         // j+1 for CN (block j holds v_{j+1}) and level j for BE; the K^T panel holds level j
         const int ld = h->ld, N = h->N;

@@ -86,33 +86,8 @@ struct ctl_handle_s {
     bool per_level = false;
     int max_row_len = 0;        // longest local row (sizes the shared-memory staging)
     int gather_chunk = 4;       // entries per gather pass of the staged KKT apply (4, 5, 7 or 8: least padding)
-    bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged reference kernel
-    bool no_tma = true;            // CTL_KKT_TMA=1 selects the TMA-staged kernel (opt-in: slower in round 1)
-    bool tma_pipe = false;         // CTL_KKT_TMA=2|3: persistent two-stage variant (next tile copied while this one is consumed)
-    bool tma_rec = false;          // CTL_KKT_TMA=3|4: ... and the CSR slice of a row block arrives as ONE bulk copy too
-    bool tma_ws = false;           // CTL_KKT_TMA=4: warp-specialised producer / consumers, no block barrier in the loop
-    // record stream of CTL_KKT_TMA=3 (built at ctl_assemble): per row block a 16-byte aligned record
-    // [int ptr[TR+1] | double2 (m,k)[cnt+1] | double kt[cnt+1] (non-symmetric K) | unsigned off[cnt+1]], entry cnt = zero sentinel
-    std::vector<uint8_t> h_tile_slot;      // host copy of d_tile_slot
-    uint8_t *d_rec = nullptr;
-    int *d_rec_off = nullptr;              // n_blocks + 1 offsets in units of 16 bytes
-    int rec_max = 0;                       // longest record in bytes
-    // TMA tile plan of the fused KKT apply (kkt_apply.cu): row blocks of TILE_ROWS rows, the
-    // unique columns each block gathers, and for every CSR entry its slot in that list
-    int tile_rows = 0, tile_umax = 0;      // 0 = no plan (fallback to the LDG-gather kernel)
-    int tile_count_off = 0;                // offset of the per-block unique-row counts inside d_tile_ucols
-    int *d_tile_uptr = nullptr;            // n_blocks + 1: run ranges of each block
-    int *d_tile_ucols = nullptr;           // runs (first column, length, first slot) x 3, then per-block unique counts
-    uint8_t *d_tile_slot = nullptr;        // per local CSR entry
+    bool force_unstaged = false;   // CTL_KKT_UNSTAGED=1: launch the unstaged kernel (the fallback for very long rows)
     bool k_symmetric = false;
-    // row-group plan of the grouped KKT apply (kkt_apply.cu, opt-in CTL_KKT_GROUP=2|4): R consecutive rows
-    // share one gather of the UNION of their columns; per union entry R (m, k) value pairs (zero where a
-    // row does not have the column).  Built at ctl_assemble for a time-independent symmetric K, one rank.
-    int group_R = 0;               // requested rows per group (0 = off)
-    bool group_ready = false;
-    int group_umax = 0;            // longest union list
-    int *d_gptr = nullptr, *d_gcols = nullptr;
-    double *d_gvals = nullptr;     // [entries][R] double2 (m, k)
     uint8_t *d_bcmask = nullptr;   // local rows (owned + ghost)
     int *d_bc_rows_all = nullptr;  // list of constrained owned rows
     int n_bc_all = 0;
@@ -128,7 +103,6 @@ struct ctl_handle_s {
     std::shared_ptr<struct PcState> pc;
     std::shared_ptr<struct KrylovState> ks;
     std::shared_ptr<struct CommState> comm;
-    struct FusedProgram *recorder = nullptr;   // sell.cu: record operations instead of launching them
     ctl_pc_callback pc_cb = nullptr;
     void *pc_cb_user = nullptr;
 
@@ -143,6 +117,8 @@ int ctl_to_bm(ctl_handle_s *h, const double *src_tf, double *dst_bm);
 int ctl_kkt_apply_tf(ctl_handle_s *h, const double *x_tf, double *y_tf);
 // pc.cu: Preconditioner.apply on time-fastest vectors
 int ctl_pc_apply_tf(ctl_handle_s *h, const double *b_tf, double *u_tf);
+// stokes.cu: in place on one time-fastest panel, X[r, :] <- T_1^-1 (which = 1) / T_2^-1 (which = 2) X[r, :]
+int ctl_panel_tinv(ctl_handle_s *h, double *X, int which, int n_rows);
 // krylov.cu: MultiBlockSystem.solve on time-fastest vectors (u: initial guess in, solution out)
 int ctl_solve_tf(ctl_handle_s *h, const double *b_tf, double *u_tf, const ctl_krylov_options *opts,
                  ctl_solve_result *result);
@@ -168,21 +144,9 @@ int ctl_upload(ctl_handle_s *h, T **dst, const T *src, size_t count);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-// Programmatic dependent launch (sm_90+): the time sweeps are chains of ~10^4 small dependent
-// kernels per preconditioner application, so the gap between two launches matters as much as
-// the kernels.  A kernel launched through pdl_launch may be scheduled while its predecessor
-// drains; it calls pdl_sync() before its first global memory access, which (a) lets ITS
-// successor be scheduled early and (b) waits until the predecessor grid has completed and its
-// writes are visible.
-#ifdef __CUDACC__
-__device__ __forceinline__ void pdl_sync()
-{
-#if __CUDA_ARCH__ >= 900
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
-}
+#include "pdl.cuh"
 
+#ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline void pdl_launch(ctl_handle_s *h, int grid, int block, void (*kernel)(KArgs...), Args &&...args)
 {

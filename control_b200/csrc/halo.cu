@@ -189,6 +189,11 @@ HaloCtx halo_ctx(const ctl_handle_s *h)
         c.epoch = h->comm->d_epoch;
         c.err = h->comm->d_err;
         c.max_spins = h->comm->max_spins;
+        static const int early = [] {
+            const char *e = getenv("CTL_MP_EARLY_WAIT");
+            return (e && e[0] == '1') ? 1 : 0;
+        }();
+        c.early_wait = early;
     }
     return c;
 }
@@ -214,6 +219,11 @@ unsigned halo_idx1(const HaloPlan *p) { return p->idx; }      // the last exchan
 namespace {
 
 __global__ void epoch_bump_kernel(unsigned long long *epoch) { *epoch += 1ull; }
+// A complete kernel boundary behind the bump.  The sweep kernels read the epoch word BEFORE they wait for their
+// predecessor (sell.cu, kernel_prologue); a kernel launched with the programmatic attribute right behind the bump could
+// do so before the bump's store is visible.  This one is launched without the attribute: it starts after the bump has
+// completed and its store has been flushed, and everything launched later starts later still.
+__global__ void epoch_fence_kernel() {}
 
 // boundary rows of an existing vector: push warps only
 __global__ void __launch_bounds__(128) halo_push_kernel(const double *__restrict__ x, const HaloCtx ctx, const HaloPush push)
@@ -267,7 +277,8 @@ int halo_epoch_begin(ctl_handle_s *h)
     CommState &c = *h->comm;
     CTL_NCCL(ncclAllReduce(c.d_barrier, c.d_barrier, 1, ncclInt, ncclMax, c.comm, h->stream));
     epoch_bump_kernel<<<1, 1, 0, h->stream>>>(c.d_epoch);
-    h->launches++;
+    epoch_fence_kernel<<<1, 1, 0, h->stream>>>();
+    h->launches += 2;
     CTL_CUDA(cudaGetLastError());
     for (HaloPlan *p : c.plans) p->idx = 0;
     return CTL_OK;
@@ -348,7 +359,10 @@ int amg_build_distributed(ctl_handle_s *h, const AmgParams &p, const std::shared
             CTL_TRY(sell_from_csr(h, Dl.R, Ld.R));
             finish_matrix(Dl.R, Dl.R_own, Ld.R);
         } else if (!Dl.Ainv.empty()) {
-            CTL_TRY(ctl_upload(h, &Ld.Ainv, Dl.Ainv.data(), Dl.Ainv.size()));
+            CTL_TRY(dense_inverse_upload(h, Dl.Ainv, Dl.n, &Ld.Ainv, &Ld.Ainv_ld));
+        } else if (Dl.coarse_inverse) {
+            CTL_CHECK(Dl.A.n_rows == Dl.n && Dl.A.n_cols == Dl.n, CTL_ERR_STATE, "amg_build: the level with the dense inverse must be replicated");
+            CTL_TRY(dense_inverse_device(h, Dl.A, Dl.coarse_shift, &Ld.Ainv, &Ld.Ainv_ld));
         }
     }
     return CTL_OK;

@@ -24,6 +24,8 @@ struct HaloCtx {                                 // per-handle constants of the 
     const unsigned long long *epoch = nullptr;   // null: one GPU
     int *err = nullptr;                          // set when a bounded spin gives up
     long long max_spins = 0;
+    int early_wait = 0;                          // CTL_MP_EARLY_WAIT=1: kernels wait for their predecessor before
+                                                 // anything else (no loads of constant data ahead of the wait)
 };
 
 struct PushDst {

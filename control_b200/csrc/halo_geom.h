@@ -209,7 +209,9 @@ struct DistLevel {
     HostCSR A, P, R;                 // local blocks (P, R empty where the hierarchy has none)
     int A_own = 0, P_own = 0, R_own = 0;      // owned columns of each block's column space (0: all columns are local)
     std::vector<double> dinv;        // own rows, then the ghosts
-    std::vector<double> Ainv;        // dense inverse in local numbering (last level)
+    std::vector<double> Ainv;        // dense inverse in local numbering (last level), or, when it is left to the device:
+    int coarse_inverse = 0;          // what to compute from A (AmgLevelHost::coarse_inverse)
+    std::vector<double> coarse_shift;   // kernel vector of the pseudo-inverse in local numbering
     std::shared_ptr<HaloGeom> space; // vectors of this level (levels < L_rep: halo; level L_rep: replicating)
 };
 
@@ -227,7 +229,7 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
     const int nl = (int)host_in.size();
     int L_rep = nl;
     for (int l = 1; l < nl; ++l)
-        if (host_in[l].A.nnz() < rep_nnz * world || !host_in[l].Ainv.empty()) {
+        if (host_in[l].A.nnz() < rep_nnz * world || host_in[l].has_inverse()) {
             L_rep = l;
             break;
         }
@@ -300,6 +302,8 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
             Lo.R = Li.R;
             Lo.dinv = Li.dinv;
             Lo.Ainv = Li.Ainv;
+            Lo.coarse_inverse = Li.coarse_inverse;
+            Lo.coarse_shift = Li.coarse_shift;
             continue;
         }
         if (l == 0) {      // level 0 keeps its numbering and is read through the handle's mesh pattern: sizes only
@@ -314,6 +318,9 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
         }
         Lo.dinv.resize(Li.dinv.size());
         for (size_t i = 0; i < Li.dinv.size(); ++i) Lo.dinv[pl.empty() ? i : pl[i]] = Li.dinv[i];
+        Lo.coarse_inverse = Li.coarse_inverse;
+        Lo.coarse_shift.resize(Li.coarse_shift.size());
+        for (size_t i = 0; i < Li.coarse_shift.size(); ++i) Lo.coarse_shift[pl.empty() ? i : pl[i]] = Li.coarse_shift[i];
         if (!Li.Ainv.empty()) {
             const int n = Li.A.n_rows;
             Lo.Ainv.resize(Li.Ainv.size());
@@ -404,6 +411,12 @@ inline void amg_distribute_host(int world, int me, const std::vector<AmgLevelHos
             const auto rf = row_of(l);
             for (int i = 0; i < n; ++i)
                 for (int j = 0; j < n; ++j) Ld.Ainv[(size_t)i * n + j] = Lh.Ainv[(size_t)rf(i) * n + rf(j)];
+        } else if (Lh.coarse_inverse) {
+            // left to the device: the inverse of the LOCAL block Ld.A is the inverse in local numbering
+            Ld.coarse_inverse = Lh.coarse_inverse;
+            const auto rf = row_of(l);
+            Ld.coarse_shift.resize(Lh.coarse_shift.size());
+            for (size_t i = 0; i < Lh.coarse_shift.size(); ++i) Ld.coarse_shift[i] = Lh.coarse_shift[rf((int)i)];
         }
     }
 }

@@ -164,6 +164,49 @@ int ctl_kkt_residual_norm(ctl_handle h, const double *b, const double *x, int la
     return rc;
 }
 
+// Residual of the outer Picard / Gauss-Newton loop on device vectors.  non_linear_res_eval (control/control.py:
+// 2442-2818) assembles it row by row from 2 n_t FE mat-vecs; after the T_1 / T_2 transforms that linear_solve
+// applies to ready right-hand sides it EQUALS b - A x with b the right-hand side of linear_solve for the data and
+// A the operator with D_v at the iterate (tests/test_oracle.py::test_non_linear_residual_is_rhs_minus_operator), so
+// it is one fused operator apply and one vector update here, and doubles as the right-hand side of the increment
+// solve.  The norm the loop tests is that of the UNtransformed residual: ||T^-1 r||.
+int ctl_nonlinear_residual(ctl_handle h, const double *b, const double *x, double *r_out, int layout, double *norm_host)
+{
+    CTL_CHECK(h && b && x && r_out && norm_host, CTL_ERR_ARG, "ctl_nonlinear_residual: null argument");
+    CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_nonlinear_residual: ctl_assemble has not been called");
+    CTL_CUDA(cudaSetDevice(h->cfg.device));
+    double *bt = nullptr, *xt = nullptr, *r = nullptr;
+    CTL_TRY(ctl_scratch_get(h, &bt));
+    CTL_TRY(ctl_scratch_get(h, &xt));
+    CTL_TRY(ctl_scratch_get(h, &r));
+    const int64_t len = h->vec_len();
+    const size_t panel = (size_t)h->n_loc * h->ld;
+    int rc;
+    if (layout == CTL_LAYOUT_TIME_FASTEST) {
+        rc = vec_copy(h, bt, b, len);
+        if (rc == CTL_OK) rc = vec_copy(h, xt, x, len);
+    } else {
+        rc = ctl_to_tf(h, b, bt);
+        if (rc == CTL_OK) rc = ctl_to_tf(h, x, xt);
+    }
+    if (rc == CTL_OK) rc = ctl_kkt_apply_tf(h, xt, r);
+    if (rc == CTL_OK) rc = vec_lincomb(h, r, 1.0, bt, -1.0, r, 0.0, nullptr, nullptr, len);
+    if (rc == CTL_OK && h->d_bc_rows_all) {      // rows of constrained dofs carry no residual (2816-2817)
+        rc = pcb_bc_fixup(h, h->d_bc_rows_all, h->n_bc_all, nullptr, r);
+        if (rc == CTL_OK) rc = pcb_bc_fixup(h, h->d_bc_rows_all, h->n_bc_all, nullptr, r + panel);
+    }
+    if (rc == CTL_OK) rc = (layout == CTL_LAYOUT_TIME_FASTEST) ? vec_copy(h, r_out, r, len) : ctl_to_bm(h, r, r_out);
+    if (rc == CTL_OK && h->cfg.CN) {
+        rc = ctl_panel_tinv(h, r, 1, h->n_loc);
+        if (rc == CTL_OK) rc = ctl_panel_tinv(h, r + panel, 2, h->n_loc);
+    }
+    if (rc == CTL_OK) rc = vec_norm_host(h, r, len, norm_host);
+    ctl_scratch_put(h, bt);
+    ctl_scratch_put(h, xt);
+    ctl_scratch_put(h, r);
+    return rc;
+}
+
 // J_h, evaluated on the host from the mass matrix the caller handed over
 int ctl_objective_host(ctl_handle h, const double *v, const double *zeta, const double *v_hat, double *out)
 {

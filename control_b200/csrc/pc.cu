@@ -642,26 +642,37 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
     AmgHierarchyDev &H = h->pc->hier[hi];
     AmgLevelDev &L0 = H.dev[0];
     const int n = L0.n;
-    double *x = nullptr, *b = nullptr, *flush = nullptr;
-    const size_t flush_bytes = 256u << 20;
     const size_t nv = (size_t)n + L0.n_ghost;      // ghost entries behind the owned ones (multi-GPU; left at zero)
-    CTL_CUDA(cudaMalloc((void **)&x, nv * sizeof(double)));
-    CTL_CUDA(cudaMalloc((void **)&b, nv * sizeof(double)));
-    CTL_CUDA(cudaMemset(b, 0, nv * sizeof(double)));
+    // Cold-cache timing of the two fine-level kernels: INPUTS LARGER THAN L2.  Each launch works on its own set of
+    // vectors (dinv, b, p_prev, p_cur, out), and the sets rotate through more than twice the 126 MB of L2, so no
+    // launch finds its operands there.  (Round 1 overwrote a 256 MB buffer between launches instead: that leaves
+    // L2 full of DIRTY lines whose write-back then competes with the kernel's own traffic -- 18.4 us for the
+    // stencil-format smoother against 12 us back to back -- and is no state the solve ever runs in.)
+    constexpr int kSetVecs = 5;
+    const size_t set_bytes = (size_t)kSetVecs * nv * sizeof(double);
+    const int n_sets = flush_l2 ? (int)std::max<size_t>(2, ((size_t)300 << 20) / set_bytes + 1) : 1;
+    double *sets = nullptr, *flush = nullptr;
+    const size_t flush_bytes = 256u << 20;
+    CTL_CUDA(cudaMalloc((void **)&sets, (size_t)n_sets * set_bytes));
+    CTL_CUDA(cudaMemset(sets, 0, (size_t)n_sets * set_bytes));
     if (flush_l2) CTL_CUDA(cudaMalloc((void **)&flush, flush_bytes));
+    auto vec = [&](int set, int k) { return sets + ((size_t)set * kSetVecs + k) * nv; };      // k: 0 dinv 1 b 2 x 3 p 4 out
     {
         std::vector<double> hb(n);
         for (int i = 0; i < n; ++i) hb[i] = std::sin(0.37 * i) + 0.1;
-        CTL_CUDA(cudaMemcpy(b, hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
-        CTL_CUDA(cudaMemset(x, 0, nv * sizeof(double)));
+        for (int s = 0; s < n_sets; ++s) {
+            CTL_CUDA(cudaMemcpy(vec(s, 0), L0.dinv, nv * sizeof(double), cudaMemcpyDeviceToDevice));
+            CTL_CUDA(cudaMemcpy(vec(s, 1), hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+            CTL_CUDA(cudaMemcpy(vec(s, 3), hb.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+        }
     }
-    const GVec gb = L0.px ? GVec(b, b + n) : GVec(b);
+    double *b = vec(0, 1), *x = vec(0, 2);
     cudaEvent_t e0, e1;
     CTL_CUDA(cudaEventCreate(&e0));
     CTL_CUDA(cudaEventCreate(&e1));
-    // Each kernel is timed as (reps x [flush, kernel]) minus (reps x [flush]) between ONE pair of
-    // events: an event pair around a single 25 us launch would add several microseconds of
-    // record / launch latency to it.
+    // Each kernel is timed over `reps` launches between ONE pair of events: an event pair around a single 10 us
+    // launch would add several microseconds of record / launch latency to it.  The whole inner solve (which = 2)
+    // streams 2 GB per call; it is timed as (reps x [256 MB overwrite, solve]) minus (reps x [overwrite]).
     double acc[3] = {0, 0, 0};
     int64_t launches_solve = 0;
     int rc = CTL_OK;
@@ -669,11 +680,13 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
         int r2 = which == 2 ? halo_epoch_begin(h) : CTL_OK;      // every rank times the same sequence
         cudaEventRecord(e0, h->stream);
         for (int r = 0; r < reps && r2 == CTL_OK; ++r) {
-            if (flush) cudaMemsetAsync(flush, r & 0xff, flush_bytes, h->stream);
+            if (which == 2 && flush) cudaMemsetAsync(flush, r & 0xff, flush_bytes, h->stream);
             if (!with_kernel) continue;
             const int64_t l0 = h->launches;
-            if (which == 0) r2 = sell_cheb_step(h, L0.A, L0.dinv, b, x, gb, L0.t0, 0.3, 0.7, 0.1);
-            else if (which == 1) r2 = sell_spmv(h, L0.A, gb, L0.r, x, SELL_RESIDUAL);
+            const int s = r % n_sets;
+            const GVec gp = L0.px ? GVec(vec(s, 3), vec(s, 3) + n) : GVec(vec(s, 3));
+            if (which == 0) r2 = sell_cheb_step(h, L0.A, vec(s, 0), vec(s, 1), vec(s, 2), gp, vec(s, 4), 0.3, 0.7, 0.1);
+            else if (which == 1) r2 = sell_spmv(h, L0.A, gp, vec(s, 4), vec(s, 1), SELL_RESIDUAL);
             else r2 = amg_solve(h, H, b, x);
             launches_solve = h->launches - l0;
         }
@@ -686,8 +699,8 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
         float warm = 0.f, with_k = 0.f, without_k = 0.f;
         rc = timed(which, true, &warm);
         if (rc == CTL_OK) rc = timed(which, true, &with_k);
-        if (rc == CTL_OK) rc = timed(which, false, &without_k);
-        acc[which] = with_k - (flush ? without_k : 0.f);
+        if (rc == CTL_OK && which == 2) rc = timed(which, false, &without_k);
+        acc[which] = with_k - ((flush && which == 2) ? without_k : 0.f);
     }
     const double mat = (double)L0.A.bytes_per_pass;      // matrix stream of the format in use (sell_format.h)
     out[0] = acc[0] / reps;
@@ -699,8 +712,7 @@ int ctl_time_amg(ctl_handle h, int32_t hi, int reps, int flush_l2, double *out)
     out[6] = (double)launches_solve;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(x);
-    cudaFree(b);
+    cudaFree(sets);
     cudaFree(flush);
     return rc;
 }

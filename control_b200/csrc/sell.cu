@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "sell.cuh"
 
@@ -60,10 +61,12 @@ MatView SellMat::view() const
     v.ps_off = ps_off;
     v.ps_w = ps_w;
     v.ps_dmax = 0;
+    v.ps_dmin = 0;
     for (int k = 0; k < ps_w && k < SF_PS; ++k) {
         v.ps_delta[k] = ps[k].delta;
         v.ps_v[k] = ps[k].v;
         v.ps_dmax = std::max(v.ps_dmax, ps[k].delta);
+        v.ps_dmin = std::min(v.ps_dmin, ps[k].delta);
     }
     return v;
 }
@@ -273,35 +276,65 @@ struct DVec {
 // seq_hi: the epoch bits of the running sequence numbers (halo_epoch_bits), read once per thread
 __device__ __forceinline__ double dvec_get(const DVec &v, int c, unsigned seq_hi, const HaloCtx &ctx)
 {
-    if (c < v.n_own) return __ldg(v.x + c);
+    if (c < v.n_own) return v.x[c];      // (a plain load: see the note on read-only loads below)
     if (v.ll) return halo_ll_read(v.ll + (c - v.n_own), seq_hi | v.idx1, ctx);
     return __ldcg(v.ghost + (c - v.n_own));
 }
 
+// READ-ONLY LOADS.  Vectors that a kernel of the chain writes (iterates, right-hand sides, residuals) are read with
+// PLAIN loads in this file, never with __ldg / through a const __restrict__ parameter: ptxas orders a plain ld.global
+// against griddepcontrol.wait but moves a non-coherent one (LDG.CONSTANT) freely -- with the wait no longer the first
+// instruction of the kernel it hoisted the gathers of the iterate above it (as soon as their column indices had
+// arrived), i.e. read the predecessor's output before the predecessor had finished: wrong sweeps on the GPU, caught
+// by the parity tests.  Constant data (matrices, dinv) keeps __ldg: hoisting those is the point.
+//
+// Every row-dot helper below follows one schedule (pdl.cuh, pdl_trigger / pdl_wait): the loads of the MATRIX
+// stream of the first chunk are issued first (constant data), then pdl_wait(), then `pre()` -- the caller's loads of
+// the vector entries of its own row -- and only then the dependent gathers.  What a thread of the chain waits for
+// after its predecessor has finished is ONE round trip (gathers and own-row loads together), not three.
+//
 // FMT_STENCIL: a slice whose 32 rows share one stencil reads (delta_k, value_k) through warp-uniform loads and
 // gathers x[row + delta_k] (coalesced); the other slices take the per-entry DICT16 path.
 // g: gather of a column that may be a ghost; g_own: gather of a column known to be owned (no ghost test)
-template <typename G, typename G0>
-__device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row, G g, G0 g_own)
+template <typename G, typename G0, typename PRE>
+__device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row, G g, G0 g_own, PRE pre)
 {
     const int s = row >> 5, lane = row & 31;
-    const int4 s0 = __ldg(A.sp4 + s);
+    const int4 s0 = pre_ld(A.sp4 + s);
+    // the most frequent stencil travels with the kernel parameters.  Whether its gathers would all stay inside the
+    // owned columns is known from the row number alone, so they are issued SPECULATIVELY, together with the slice
+    // descriptor: the common slice (99.6 % at C2) costs no dependent round trip for its descriptor, the others
+    // throw eight loads away.
+    const int first = s << 5;
+    const bool spec = A.ps_w > 0 && first + A.ps_dmin >= 0 && first + 31 + A.ps_dmax < A.n_own;
+    pdl_wait();
+    pre();
     double acc = 0.0;
-    if (s0.z == A.ps_off) {
-        // the most frequent stencil: offsets and values are kernel parameters, the only loads are the gathers
-        // (in two halves of 8: a P1 triangle stencil has 7 entries, a P1 tetrahedron stencil 15)
-        const bool own = (s << 5) + 31 + A.ps_dmax < A.n_own;      // the whole slice stays inside the owned columns
+    if (spec) {
+        double xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = (j < A.ps_w) ? g_own(row + A.ps_delta[j]) : 0.0;
+        if (s0.z == A.ps_off) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < A.ps_w) acc = fma(A.ps_v[j], xv[j], acc);
+            if (A.ps_w > 8) {      // second half (a P1 tetrahedron stencil has 15 entries)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) xv[j] = (8 + j < A.ps_w) ? g_own(row + A.ps_delta[8 + j]) : 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (8 + j < A.ps_w) acc = fma(A.ps_v[8 + j], xv[j], acc);
+            }
+            return acc;
+        }
+    } else if (s0.z == A.ps_off) {
+        // the same stencil next to a partition boundary: ghost-aware gathers, in two halves of 8
 #pragma unroll
         for (int h0 = 0; h0 < SF_PS; h0 += 8) {
             if (h0 < A.ps_w) {
                 double xv[8];
-                if (own) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) xv[j] = (h0 + j < A.ps_w) ? g_own(row + A.ps_delta[h0 + j]) : 0.0;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) xv[j] = (h0 + j < A.ps_w) ? g(row + A.ps_delta[h0 + j]) : 0.0;
-                }
+                for (int j = 0; j < 8; ++j) xv[j] = (h0 + j < A.ps_w) ? g(row + A.ps_delta[h0 + j]) : 0.0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     if (h0 + j < A.ps_w) acc = fma(A.ps_v[h0 + j], xv[j], acc);
@@ -341,20 +374,26 @@ __device__ __forceinline__ double sell_row_dot_stencil(const MatView &A, int row
 // One row of a SELL-32 slice.  The slice width is uniform across the warp, so the loop is divergence free;
 // entries are fetched in chunks of SC with all stream loads issued before the dependent gathers
 // (memory-level parallelism instead of a serial load -> gather -> fma chain per entry).
-template <int FMT, bool STREAM, typename G, typename G0>
-__device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g, G0 g_own)
+template <int FMT, bool STREAM, typename G, typename G0, typename PRE>
+__device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g, G0 g_own, PRE pre)
 {
-    if (FMT == FMT_STENCIL) return sell_row_dot_stencil(A, row, g, g_own);
+    if (FMT == FMT_STENCIL) return sell_row_dot_stencil(A, row, g, g_own, pre);
     const int s = row >> 5, lane = row & 31;
-    const int2 s0 = __ldg(A.sp + s);
-    const int end = __ldg(reinterpret_cast<const int *>(A.sp + s + 1));
+    const int2 s0 = pre_ld(A.sp + s);
+    const int end = pre_ld(reinterpret_cast<const int *>(A.sp + s + 1));
     double acc = 0.0;
-    for (int p0 = s0.x + lane; p0 < end; p0 += 32 * SC) {
+    // chunk 0: its stream loads are issued before the wait for the predecessor grid
+    auto chunk = [&](int p0, auto first) {
+        constexpr bool PRE = decltype(first)::value;
         SfRaw raw[SC];
 #pragma unroll
         for (int j = 0; j < SC; ++j) {
             const int p = p0 + 32 * j;
-            if (p < end) raw[j] = sf_load<FMT, STREAM>(A, p);
+            if (p < end) raw[j] = sf_load<FMT, STREAM, PRE>(A, p);
+        }
+        if (PRE) {
+            pdl_wait();
+            pre();
         }
         int c[SC];
         double v[SC];
@@ -373,7 +412,10 @@ __device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g, G
         for (int j = 0; j < SC; ++j) xv[j] = g(c[j]);
 #pragma unroll
         for (int j = 0; j < SC; ++j) acc = fma(v[j], xv[j], acc);
-    }
+    };
+    int p0 = s0.x + lane;
+    chunk(p0, std::true_type());      // (a slice without entries loads nothing and only waits)
+    for (p0 += 32 * SC; p0 < end; p0 += 32 * SC) chunk(p0, std::false_type());
     return acc;
 }
 
@@ -381,13 +423,14 @@ __device__ __forceinline__ double sell_row_dot(const MatView &A, int row, G g, G
 template <typename G>
 __device__ __forceinline__ double sell_row_dot_rt(const MatView &A, int row, G g)
 {
+    auto none = [] {};
     switch (A.fmt) {
-    case FMT_F64: return sell_row_dot<FMT_F64, false>(A, row, g, g);
-    case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g, g);
-    case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g, g);
-    case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g, g);
-    case FMT_STENCIL: return sell_row_dot_stencil(A, row, g, g);
-    default: return sell_row_dot<FMT_DICT8, false>(A, row, g, g);
+    case FMT_F64: return sell_row_dot<FMT_F64, false>(A, row, g, g, none);
+    case FMT_D16: return sell_row_dot<FMT_D16, false>(A, row, g, g, none);
+    case FMT_PK: return sell_row_dot<FMT_PK, false>(A, row, g, g, none);
+    case FMT_DICT16: return sell_row_dot<FMT_DICT16, false>(A, row, g, g, none);
+    case FMT_STENCIL: return sell_row_dot_stencil(A, row, g, g, none);
+    default: return sell_row_dot<FMT_DICT8, false>(A, row, g, g, none);
     }
 }
 
@@ -395,17 +438,22 @@ __device__ __forceinline__ double sell_row_dot_rt(const MatView &A, int row, G g
 // entries in chunks of CU with the stream loads issued before the dependent gathers (the rows of the restrictions
 // and of R A are long: a serial load -> gather chain per entry is what these latency-bound kernels cannot afford).
 constexpr int CU = 4;
-template <int T, int FMT, bool STREAM, typename G>
-__device__ __forceinline__ double csrv_row_dot_f(const MatView &A, int row, int sub, G g)
+template <int T, int FMT, bool STREAM, typename G, typename PRE>
+__device__ __forceinline__ double csrv_row_dot_f(const MatView &A, int row, int sub, G g, PRE pre)
 {
-    const int beg = __ldg(A.ptr + row), end = __ldg(A.ptr + row + 1);
-    const int base = (FMT == FMT_F64) ? 0 : __ldg(A.rbase + row);
+    const int beg = pre_ld(A.ptr + row), end = pre_ld(A.ptr + row + 1);
+    const int base = (FMT == FMT_F64) ? 0 : pre_ld(A.rbase + row);
     double acc = 0.0;
-    for (int p0 = beg + sub; p0 < end; p0 += CU * T) {
+    auto chunk = [&](int p0, auto first) {
+        constexpr bool PRE = decltype(first)::value;
         SfRaw raw[CU];
 #pragma unroll
         for (int j = 0; j < CU; ++j)
-            if (p0 + j * T < end) raw[j] = sf_load<FMT, STREAM>(A, p0 + j * T);
+            if (p0 + j * T < end) raw[j] = sf_load<FMT, STREAM, PRE>(A, p0 + j * T);
+        if (PRE) {
+            pdl_wait();
+            pre();
+        }
         int c[CU];
         double v[CU];
 #pragma unroll
@@ -422,18 +470,21 @@ __device__ __forceinline__ double csrv_row_dot_f(const MatView &A, int row, int 
         for (int j = 0; j < CU; ++j) xv[j] = g(c[j]);
 #pragma unroll
         for (int j = 0; j < CU; ++j) acc = fma(v[j], xv[j], acc);
-    }
+    };
+    int p0 = beg + sub;
+    chunk(p0, std::true_type());      // (a lane without entries of its own loads nothing and only waits)
+    for (p0 += CU * T; p0 < end; p0 += CU * T) chunk(p0, std::false_type());
 #pragma unroll
     for (int o = T / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, T);
     return acc;
 }
 
-template <int T, bool STREAM, typename G>
-__device__ __forceinline__ double csrv_row_dot(const MatView &A, int row, int sub, G g)
+template <int T, bool STREAM, typename G, typename PRE>
+__device__ __forceinline__ double csrv_row_dot(const MatView &A, int row, int sub, G g, PRE pre)
 {
-    if (A.fmt == FMT_F64) return csrv_row_dot_f<T, FMT_F64, STREAM>(A, row, sub, g);
-    if (A.fmt == FMT_D16) return csrv_row_dot_f<T, FMT_D16, STREAM>(A, row, sub, g);
-    return csrv_row_dot_f<T, FMT_PK, STREAM>(A, row, sub, g);
+    if (A.fmt == FMT_F64) return csrv_row_dot_f<T, FMT_F64, STREAM>(A, row, sub, g, pre);
+    if (A.fmt == FMT_D16) return csrv_row_dot_f<T, FMT_D16, STREAM>(A, row, sub, g, pre);
+    return csrv_row_dot_f<T, FMT_PK, STREAM>(A, row, sub, g, pre);
 }
 
 // Row assignment shared by every kernel: the push CTAs (halo.cuh) come first and compute the listed boundary
@@ -448,7 +499,10 @@ __device__ __forceinline__ void run_rows(int n_rows, const HaloPush &push, unsig
     const int n_pc = (push.n_chunks + ST / 32 - 1) / (ST / 32);
     if ((int)blockIdx.x < n_pc) {
         const int ci = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
-        if (ci >= push.n_chunks) return;
+        if (ci >= push.n_chunks) {
+            pdl_wait();      // no thread leaves before the predecessor is complete: grids finish in launch order
+            return;
+        }
         const PushChunk ch = push.chunks[ci];
         const unsigned seq = seq_hi | push.idx1;
 #pragma unroll 1
@@ -467,11 +521,15 @@ __device__ __forceinline__ void run_rows(int n_rows, const HaloPush &push, unsig
         }
         return;
     }
-    if (push.all_rows) return;
+    if (push.all_rows) {
+        pdl_wait();
+        return;
+    }
     const int r0 = ((int)blockIdx.x - n_pc) * RPC;
     const int row = r0 + (int)threadIdx.x / T;
     if (T == 1) {
         if (row < n_rows) out[row] = f(row);
+        else pdl_wait();      // no thread leaves before the predecessor is complete: grids finish in launch order
     } else {
         const bool live = row < n_rows;
         const double v = f(live ? row : n_rows - 1);
@@ -479,12 +537,24 @@ __device__ __forceinline__ void run_rows(int n_rows, const HaloPush &push, unsig
     }
 }
 
-// kernel-side modes: y = A x | b - A x | b + sign A x (ADD / SUB arrive as b = y)
-__device__ __forceinline__ double apply_mode(int mode, double ax, const double *b, int row)
+// kernel-side modes: y = A x | b - A x | b + sign A x (ADD / SUB arrive as b = y); bi = b[row], loaded by the caller
+__device__ __forceinline__ double apply_mode(int mode, double ax, double bi)
 {
     if (mode == SELL_ASSIGN) return ax;
-    if (mode == SELL_RESIDUAL) return b[row] - ax;
-    return b[row] + ax;      // SELL_BPLUS
+    if (mode == SELL_RESIDUAL) return bi - ax;
+    return bi + ax;      // SELL_BPLUS
+}
+
+// Start of every kernel of this file: let the successor be scheduled and read the epoch bits of the exchange's
+// sequence numbers.  The wait for the predecessor happens inside the row-dot helpers, after the loads of the matrix
+// stream.  (The epoch word is bumped once per replay behind a complete kernel boundary, halo.cu::halo_epoch_begin,
+// so it may be read before the wait.)
+__device__ __forceinline__ unsigned kernel_prologue(const HaloCtx &ctx)
+{
+    pdl_trigger();
+    if (!ctx.epoch) return 0u;
+    if (ctx.early_wait) pdl_wait();
+    return halo_epoch_bits(ctx);
 }
 
 // ---------------------------------------------------------------- SELL kernels
@@ -493,33 +563,43 @@ template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    const unsigned hi = kernel_prologue(ctx);
     run_rows<1>(A.n_rows, push, hi, y, [&](int row) {
+        double bi = 0.0;
         const double ax = sign * sell_row_dot<FMT, STREAM>(
-                                     A, row, [&](int c) { return GH ? dvec_get(x, c, hi, ctx) : __ldg(x.x + c); },
-                                     [&](int c) { return __ldg(x.x + c); });
-        return apply_mode(mode, ax, b, row);
+                                     A, row, [&](int c) { return GH ? dvec_get(x, c, hi, ctx) : x.x[c]; },
+                                     [&](int c) { return x.x[c]; },
+                                     [&] { if (mode != SELL_ASSIGN) bi = b[row]; });
+        return apply_mode(mode, ax, bi);
     });
 }
 
+// one Chebyshev step; the loads of the row's own entries (b, p_cur, p_prev) travel with the gathers
+#define CHEB_ROW_UPDATE(DOT)                                                                              \
+    const double di = pre_ld(dinv + row);      /* constant: before the wait */                             \
+    double bi = 0.0, pc = 0.0, pp = 0.0;                                                                  \
+    auto pre = [&] {                                                                                      \
+        bi = b[row];                                                                                      \
+        pc = p_cur.x[row];                                                                                \
+        if (prev_scale == 0.0 && a != 0.0) pp = p_prev[row];                                              \
+    };                                                                                                    \
+    const double ax = DOT;                                                                                \
+    double r = bq * pc + c * di * (bi - ax);                                                              \
+    if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);                                           \
+    else if (a != 0.0) r = fma(a, pp, r);                                                                 \
+    return r
+
 template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
-                                                      const double *__restrict__ b, const double *p_prev, const DVec p_cur,
+                                                      const double *b, const double *p_prev, const DVec p_cur,
                                                       const HaloCtx ctx, double *out, double a, double bq, double c,
                                                       double prev_scale, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    const unsigned hi = kernel_prologue(ctx);
     run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
-        const double ax = sell_row_dot<FMT, STREAM>(
-            A, row, [&](int cc) { return GH ? dvec_get(p_cur, cc, hi, ctx) : __ldg(p_cur.x + cc); },
-            [&](int cc) { return __ldg(p_cur.x + cc); });
-        const double di = dinv[row], bi = b[row];
-        double r = bq * p_cur.x[row] + c * di * (bi - ax);
-        if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
-        else if (a != 0.0) r = fma(a, p_prev[row], r);
-        return r;
+        CHEB_ROW_UPDATE((sell_row_dot<FMT, STREAM>(
+            A, row, [&](int cc) { return GH ? dvec_get(p_cur, cc, hi, ctx) : p_cur.x[cc]; },
+            [&](int cc) { return p_cur.x[cc]; }, pre)));
     });
 }
 
@@ -527,14 +607,14 @@ template <int FMT, bool STREAM, bool GH>
 __global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = (GH || push.n_chunks) ? halo_epoch_bits(ctx) : 0u;
+    const unsigned hi = kernel_prologue(ctx);
     run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
+        const double di = pre_ld(dinv.x + row);
+        double bi = 0.0;
         const double ax = sell_row_dot<FMT, STREAM>(
             A, row,
-            [&](int c) { return GH ? s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx) : s * __ldg(dinv.x + c) * __ldg(b.x + c); },
-            [&](int c) { return s * __ldg(dinv.x + c) * __ldg(b.x + c); });
-        const double di = dinv.x[row], bi = b.x[row];
+            [&](int c) { return GH ? s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx) : s * __ldg(dinv.x + c) * b.x[c]; },
+            [&](int c) { return s * __ldg(dinv.x + c) * b.x[c]; }, [&] { bi = b.x[row]; });
         const double p1 = s * di * bi;
         return wgt * p1 + (wgt * s) * di * (bi - ax);
     });
@@ -544,8 +624,7 @@ __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const MatView A1, const 
                                                        const DVec x3, double *y, double alpha, double beta,
                                                        const HaloCtx ctx, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = halo_epoch_bits(ctx);
+    const unsigned hi = kernel_prologue(ctx);
     run_rows<1>(A1.n_rows, push, hi, y, [&](int row) {
         double acc1;
         if (x2.x) acc1 = sell_row_dot_rt(A1, row, [&](int c) { return dvec_get(x1, c, hi, ctx) + dvec_get(x2, c, hi, ctx); });
@@ -556,46 +635,70 @@ __global__ void __launch_bounds__(ST) sell_spmv2_kernel(const MatView A1, const 
     });
 }
 
-__global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *__restrict__ b,
-                                                       double *__restrict__ out, double c, int n, const HaloCtx ctx,
+__global__ void __launch_bounds__(ST) dinv_scale_kernel(const double *__restrict__ dinv, const double *b,
+                                                       double *out, double c, int n, const HaloCtx ctx,
                                                        const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = push.n_chunks ? halo_epoch_bits(ctx) : 0u;
-    run_rows<1>(n, push, hi, out, [&](int row) { return c * dinv[row] * b[row]; });
+    const unsigned hi = kernel_prologue(ctx);
+    run_rows<1>(n, push, hi, out, [&](int row) {
+        const double di = pre_ld(dinv + row);
+        pdl_wait();
+        return c * di * b[row];
+    });
 }
 
-// Small dense matrix (the coarsest level: 2205 rows at C2, 39 MB, L2-resident): one CTA per GR rows, so that b is
-// read once per GR rows and every thread keeps GR independent 16-byte loads in flight
+// Small dense matrix (the coarsest level: 2205 rows at C2, 39 MB, L2-resident), rows padded to `lda` (even: every
+// row starts 16-byte aligned).  One CTA per GR rows, so that b is read once per GR rows; a thread keeps GU x GR
+// independent 16-byte loads of the matrix in flight, and the first batch of them is issued BEFORE the wait for the
+// predecessor (the matrix is constant).  Round 2: 15 us -> see profiles/r02_*: the first version walked odd-sized
+// rows with 8-byte loads, four per thread and iteration.
 constexpr int GR = 4;
-__global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ b,
-                                                       double *__restrict__ y, int n)
+constexpr int GU = 2;
+__global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict__ A, const double *b,
+                                                       double *y, int n, int lda)
 {
-    pdl_sync();
+    pdl_trigger();
     __shared__ double part[GR][ST / 32];
     const int r0 = blockIdx.x * GR;
     double acc[GR];
 #pragma unroll
     for (int q = 0; q < GR; ++q) acc[q] = 0.0;
-    if ((n & 1) == 0) {      // rows start 16-byte aligned
-        const double2 *b2 = reinterpret_cast<const double2 *>(b);
-        const int n2 = n >> 1;
-        for (int j = threadIdx.x; j < n2; j += ST) {
-            const double2 bv = b2[j];
-            double2 av[GR];
+    const int n2 = n >> 1;      // complete pairs; an odd last column is handled below (the padding column is zero)
+    const bool b_aligned = (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+    const double2 *rowp[GR];
 #pragma unroll
-            for (int q = 0; q < GR; ++q)
-                av[q] = (r0 + q < n) ? __ldg(reinterpret_cast<const double2 *>(A + (size_t)(r0 + q) * n) + j) : make_double2(0.0, 0.0);
+    for (int q = 0; q < GR; ++q) rowp[q] = reinterpret_cast<const double2 *>(A + (size_t)min(r0 + q, n - 1) * lda);
+    bool waited = false;
+    for (int j0 = threadIdx.x; j0 < n2; j0 += GU * ST) {
+        double2 av[GU][GR];
 #pragma unroll
-            for (int q = 0; q < GR; ++q) acc[q] = fma(av[q].y, bv.y, fma(av[q].x, bv.x, acc[q]));
+        for (int u = 0; u < GU; ++u) {
+            const int j = j0 + u * ST;
+#pragma unroll
+            for (int q = 0; q < GR; ++q) av[u][q] = (j < n2) ? pre_ld(rowp[q] + j) : make_double2(0.0, 0.0);
         }
-    } else {
-        for (int j = threadIdx.x; j < n; j += ST) {
-            const double bv = b[j];
-#pragma unroll
-            for (int q = 0; q < GR; ++q)
-                if (r0 + q < n) acc[q] = fma(__ldg(A + (size_t)(r0 + q) * n + j), bv, acc[q]);
+        if (!waited) {
+            pdl_wait();
+            waited = true;
         }
+        double2 bv[GU];
+#pragma unroll
+        for (int u = 0; u < GU; ++u) {
+            const int j = j0 + u * ST;
+            if (j >= n2) bv[u] = make_double2(0.0, 0.0);
+            else if (b_aligned) bv[u] = reinterpret_cast<const double2 *>(b)[j];
+            else bv[u] = make_double2(b[2 * j], b[2 * j + 1]);
+        }
+#pragma unroll
+        for (int u = 0; u < GU; ++u)
+#pragma unroll
+            for (int q = 0; q < GR; ++q) acc[q] = fma(av[u][q].y, bv[u].y, fma(av[u][q].x, bv[u].x, acc[q]));
+    }
+    if (!waited) pdl_wait();
+    if ((n & 1) && threadIdx.x == 0) {
+        const double bl = b[n - 1];
+#pragma unroll
+        for (int q = 0; q < GR; ++q) acc[q] = fma(__ldg(A + (size_t)min(r0 + q, n - 1) * lda + n - 1), bl, acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < GR; ++q) {
@@ -614,31 +717,26 @@ template <int T, bool STREAM>
 __global__ void __launch_bounds__(ST) csrv_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = halo_epoch_bits(ctx);
+    const unsigned hi = kernel_prologue(ctx);
     const int sub = threadIdx.x % T;
     run_rows<T>(A.n_rows, push, hi, y, [&](int row) {
-        const double ax = sign * csrv_row_dot<T, STREAM>(A, row, sub, [&](int c) { return dvec_get(x, c, hi, ctx); });
-        return apply_mode(mode, ax, b, row);
+        double bi = 0.0;
+        const double ax = sign * csrv_row_dot<T, STREAM>(A, row, sub, [&](int c) { return dvec_get(x, c, hi, ctx); },
+                                                         [&] { if (mode != SELL_ASSIGN) bi = b[row]; });
+        return apply_mode(mode, ax, bi);
     });
 }
 
 template <int T>
 __global__ void __launch_bounds__(ST) csrv_cheb_kernel(const MatView A, const double *__restrict__ dinv,
-                                                      const double *__restrict__ b, const double *p_prev, const DVec p_cur,
+                                                      const double *b, const double *p_prev, const DVec p_cur,
                                                       const HaloCtx ctx, double *out, double a, double bq, double c,
                                                       double prev_scale, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = halo_epoch_bits(ctx);
+    const unsigned hi = kernel_prologue(ctx);
     const int sub = threadIdx.x % T;
     run_rows<T>(A.n_rows, push, hi, out, [&](int row) {
-        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int cc) { return dvec_get(p_cur, cc, hi, ctx); });
-        const double di = dinv[row], bi = b[row];
-        double r = bq * p_cur.x[row] + c * di * (bi - ax);
-        if (prev_scale != 0.0) r = fma(a, prev_scale * di * bi, r);
-        else if (a != 0.0) r = fma(a, p_prev[row], r);
-        return r;
+        CHEB_ROW_UPDATE((csrv_row_dot<T, false>(A, row, sub, [&](int cc) { return dvec_get(p_cur, cc, hi, ctx); }, pre)));
     });
 }
 
@@ -646,12 +744,13 @@ template <int T>
 __global__ void __launch_bounds__(ST) csrv_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
-    pdl_sync();
-    const unsigned hi = halo_epoch_bits(ctx);
+    const unsigned hi = kernel_prologue(ctx);
     const int sub = threadIdx.x % T;
     run_rows<T>(A.n_rows, push, hi, out, [&](int row) {
-        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int c) { return s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx); });
-        const double di = dinv.x[row], bi = b.x[row];
+        const double di = pre_ld(dinv.x + row);
+        double bi = 0.0;
+        const double ax = csrv_row_dot<T, false>(A, row, sub, [&](int c) { return s * dvec_get(dinv, c, hi, ctx) * dvec_get(b, c, hi, ctx); },
+                                                 [&] { bi = b.x[row]; });
         const double p1 = s * di * bi;
         return wgt * p1 + (wgt * s) * di * (bi - ax);
     });
@@ -790,10 +889,11 @@ int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double 
     return CTL_OK;
 }
 
-int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n)
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, int lda)
 {
+    CTL_CHECK(lda >= n && (lda & 1) == 0, CTL_ERR_ARG, "dense_gemv: the row stride must be even and >= n");
     if (n == 0) return CTL_OK;
-    pdl_launch(h, ceil_div(n, GR), ST, dense_gemv_kernel, Ainv, b, y, n);
+    pdl_launch(h, ceil_div(n, GR), ST, dense_gemv_kernel, Ainv, b, y, n, lda);
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;

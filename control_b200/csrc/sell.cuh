@@ -101,8 +101,8 @@ int sell_cheb_first2(ctl_handle_s *h, const SellMat &A, const GVec &dinv, const 
 // out = c * dinv .* b   (first step from a zero guess)
 int vec_dinv_scale(ctl_handle_s *h, const double *dinv, const double *b, double *out, double c, int n,
                    const HaloPush &push = HaloPush());
-// y = Ainv b, dense row-major n x n
-int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n);
+// y = Ainv b, dense row-major n x n with row stride lda (even)
+int dense_gemv(ctl_handle_s *h, const double *Ainv, const double *b, double *y, int n, int lda);
 // two-matrix product on one shared row set (backward-sweep right-hand side, pc.cu):
 //   y = alpha * A1 (x1 + x2) + beta * A2 x3      (x2, x3 may be null)
 int sell_spmv2(ctl_handle_s *h, const SellMat &A1, const SellMat &A2, const GVec &x1, const GVec &x2, const GVec &x3,

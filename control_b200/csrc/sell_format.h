@@ -31,6 +31,8 @@
 #include <cstring>
 #include <vector>
 
+#include "pdl.cuh"
+
 #ifdef __CUDACC__
 #define SF_HD __host__ __device__ __forceinline__
 #else
@@ -72,14 +74,18 @@ struct MatView {
     // cost no load instructions); ps_off = its offset in stab (-2: none), at most SF_PS entries (15 = P1 tetrahedra)
     int ps_off = -2, ps_w = 0;
     int ps_dmax = 0;                  // largest offset of that stencil: rows below n_own - ps_dmax gather no ghost
+    int ps_dmin = 0;                  // smallest offset (<= 0 on a square matrix)
     int ps_delta[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     double ps_v[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
-template <bool STREAM, typename T>
+// PRE: a load of the first chunk of a row, issued before the wait for the predecessor grid (pdl.cuh); it must keep
+// its place in the instruction stream
+template <bool STREAM, bool PRE = false, typename T>
 SF_HD T sf_ld(const T *p)
 {
 #ifdef __CUDA_ARCH__
+    if (PRE) return (T)pre_ld<STREAM>(p);
     return STREAM ? __ldcs(p) : __ldg(p);      // STREAM: read once per pass, evict first
 #else
     return *p;
@@ -109,7 +115,7 @@ struct SfRaw {
     double v;
 };
 
-template <int FMT, bool STREAM>
+template <int FMT, bool STREAM, bool PRE = false>
 SF_HD SfRaw sf_load(const MatView &A, int p)
 {
     SfRaw r;
@@ -117,18 +123,18 @@ SF_HD SfRaw sf_load(const MatView &A, int p)
     r.k = 0;
     r.v = 0.0;
     if (FMT == FMT_F64) {
-        r.c = sf_ld<STREAM>(A.cols + p);
-        r.v = sf_ld<STREAM>(A.vals + p);
+        r.c = sf_ld<STREAM, PRE>(A.cols + p);
+        r.v = sf_ld<STREAM, PRE>(A.vals + p);
     } else if (FMT == FMT_D16) {
-        r.c = (int)sf_ld<STREAM>(A.dcol + p);
-        r.v = sf_ld<STREAM>(A.vals + p);
+        r.c = (int)sf_ld<STREAM, PRE>(A.dcol + p);
+        r.v = sf_ld<STREAM, PRE>(A.vals + p);
     } else if (FMT == FMT_PK) {
-        r.c = (int)sf_ld<STREAM>(A.dcol + p);
-        r.k = sf_ld<STREAM>(A.vcode + p);
+        r.c = (int)sf_ld<STREAM, PRE>(A.dcol + p);
+        r.k = sf_ld<STREAM, PRE>(A.vcode + p);
     } else if (FMT == FMT_DICT16) {
-        r.k = sf_ld<STREAM>(reinterpret_cast<const uint16_t *>(A.code) + p);
+        r.k = sf_ld<STREAM, PRE>(reinterpret_cast<const uint16_t *>(A.code) + p);
     } else {
-        r.k = sf_ld<STREAM>(reinterpret_cast<const uint8_t *>(A.code) + p);
+        r.k = sf_ld<STREAM, PRE>(reinterpret_cast<const uint8_t *>(A.code) + p);
     }
     return r;
 }

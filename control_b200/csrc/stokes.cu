@@ -221,15 +221,17 @@ int panel_spmm(ctl_stokes_s *S, const DevCSR &A, const double *X, const double *
     return CTL_OK;
 }
 
-int panel_tinv(ctl_stokes_s *S, double *X, int t_inv, int n_rows)
+// in place on one time-fastest panel of handle h: X[r, :] <- T_1^-1 (which = 1) / T_2^-1 (which = 2) X[r, :]
+int panel_tinv_h(ctl_handle_s *h, double *X, int which, int n_rows)
 {
-    ctl_handle_s *h = S->hv;
     const int ld = h->ld, nb = blocks_for(n_rows, ld);
-    DISPATCH_G(ld, (panel_tinv_kernel<GG, CC><<<nb, 256, 0, h->stream>>>(X, t_inv, n_rows, h->N, ld)));
+    DISPATCH_G(ld, (panel_tinv_kernel<GG, CC><<<nb, 256, 0, h->stream>>>(X, which == 1 ? T_ONE : T_TWO, n_rows, h->N, ld)));
     h->launches++;
     CTL_CUDA(cudaGetLastError());
     return CTL_OK;
 }
+
+int panel_tinv(ctl_stokes_s *S, double *X, int t_inv, int n_rows) { return panel_tinv_h(S->hv, X, t_inv, n_rows); }
 
 // ConstantNullspace on a pressure vector (both panels): out = v - mean(v) [+ mean(w)]
 //   project / pre_mult_corrected_lhs / pc_pre_mult_corrected: w = null
@@ -455,6 +457,8 @@ int with_tf(ctl_stokes_s *S, const double *b, double *u, bool u_in, F fn)
 }
 
 }  // namespace
+
+int ctl_panel_tinv(ctl_handle_s *h, double *X, int which, int n_rows) { return panel_tinv_h(h, X, which, n_rows); }
 
 extern "C" {
 

@@ -318,6 +318,21 @@ class MultiBlockSystem:
         o.max_it = int(sp.get("maximum_iterations", 1000))
         if "gmres_restart" in sp:                                 # "fgmres_restart" is never read: 747-748
             o.restart = int(sp["gmres_restart"])
+        # "pc_side" (735-736) and "norm_type" (744-746) are forwarded to PETSc by the reference.  krylov.cuh
+        # implements PETSc's defaults for each solver -- left + preconditioned norm for gmres / minres, right +
+        # unpreconditioned norm for fgmres -- so any other request is refused instead of silently ignored (a
+        # different side or norm changes the convergence test and the iteration count)
+        right = ksp_type == "fgmres"
+        side = sp.get("pc_side")
+        if side is not None and str(side).lower() not in (("right", "2", "pc_right") if right else ("left", "1", "pc_left")):
+            raise ValueError(f"pc_side={side!r} is not implemented for {ksp_type}: only PETSc's default side "
+                             f"({'right' if right else 'left'})")
+        norm = sp.get("norm_type")
+        if norm is not None and str(norm).lower() not in (
+                ("default", "-1", "unpreconditioned", "2", "norm_unpreconditioned") if right
+                else ("default", "-1", "preconditioned", "1", "norm_preconditioned")):
+            raise ValueError(f"norm_type={norm!r} is not implemented for {ksp_type}: only PETSc's default "
+                             f"({'unpreconditioned' if right else 'preconditioned'})")
         o.pc = pc_kind
         return o
 
@@ -380,7 +395,7 @@ class MultiBlockSystem:
         r0, r1 = self.to_host_blocks(u)
         np.copyto(_as_host_f64(u_0).reshape(r0.shape), r0)
         np.copyto(_as_host_f64(u_1).reshape(r1.shape), r1)
-        if solver_parameters.get("monitor_convergence", False):   # 749-754
+        if solver_parameters.get("monitor_convergence", True):    # 749-754 (the reference's default is True)
             for it, r_norm in enumerate(info.history):
                 print(f"KSP: iteration {it:d}, residual norm {r_norm:.16e}")
         if not solver_parameters.get("preconditioner", False):    # 756, 768-770
@@ -408,6 +423,16 @@ class MultiBlockSystem:
     def residual_norm(self, b_dev, x_dev, layout=L.CTL_LAYOUT_BLOCK_MAJOR):
         out = C.c_double()
         self._call(self._lib.ctl_kkt_residual_norm, b_dev.data_ptr(), x_dev.data_ptr(), layout, C.byref(out))
+        return float(out.value)
+
+    def nonlinear_residual(self, b_dev, x_dev, r_dev, layout=L.CTL_LAYOUT_BLOCK_MAJOR):
+        """Residual of the outer Picard / Gauss-Newton loop on device vectors (``ctl_nonlinear_residual``; replaces
+        ``non_linear_res_eval``, control/control.py:2442-2818): fills ``r_dev = b - A x`` (constrained rows zero) --
+        the right-hand side of the increment solve -- and returns the norm of the untransformed residual, the
+        quantity the reference's loop tests.  ``A`` carries ``D_v`` at the iterate: call ``set_K`` first."""
+        out = C.c_double()
+        self._call(self._lib.ctl_nonlinear_residual, b_dev.data_ptr(), x_dev.data_ptr(), r_dev.data_ptr(), layout,
+                   C.byref(out))
         return float(out.value)
 
     def objective_device(self, v_dev, zeta_dev, v_hat_dev):

@@ -187,6 +187,13 @@ int ctl_solve_host(ctl_handle h, const double *b_host, double *u_host,
 /* ||b - A x||_2 with the projected operator */
 int ctl_kkt_residual_norm(ctl_handle h, const double *b, const double *x, int layout,
                           double *out);
+/* residual of the outer Picard / Gauss-Newton loop (replaces non_linear_res_eval, control/control.py:2442-2818)
+ * on DEVICE vectors: r = b - A x with the rows of constrained dofs zeroed, where b is the right-hand side of
+ * linear_solve for the problem data and A carries D_v at the iterate x (ctl_set_values per level first).  r is
+ * the residual AFTER the T_1 / T_2 transforms, i.e. the right-hand side of the increment solve; *norm_host is
+ * || T^-1 r ||_2, the norm of the reference's (untransformed) residual, reduced over all ranks. */
+int ctl_nonlinear_residual(ctl_handle h, const double *b, const double *x, double *r, int layout,
+                           double *norm_host);
 /* discrete objective J_h; v, zeta, v_hat: n_t levels x n, host */
 int ctl_objective_host(ctl_handle h, const double *v_host, const double *zeta_host,
                        const double *v_hat_host, double *out);
@@ -286,8 +293,10 @@ int64_t ctl_kernel_launches(ctl_handle h);     /* kernels launched by this handl
 int ctl_time_kkt_apply(ctl_handle h, const double *x_tf, double *y_tf, int reps, float *ms);
 
 /* time the kernels of the time sweeps in isolation on AMG hierarchy `hierarchy` (CUDA
- * events around each launch on the handle's stream; flush_l2 != 0 overwrites a 256 MB
- * buffer between launches).  out[0] = level-0 smoother step, ms; out[1] = its algorithmic
+ * events on the handle's stream around `reps` launches).  flush_l2 != 0: cold operands --
+ * every launch of the two fine-level kernels works on its own set of vectors and the sets
+ * rotate through more than twice the L2 capacity (inputs larger than L2); the inner solve
+ * is preceded by the overwrite of a 256 MB buffer, whose time is subtracted.  out[0] = level-0 smoother step, ms; out[1] = its algorithmic
  * bytes; out[2] = level-0 residual SpMV, ms; out[3] = its bytes; out[4] = one inner solve
  * (all cycles, all levels), ms; out[5] = its algorithmic bytes; out[6] = kernels per solve */
 int ctl_time_amg(ctl_handle h, int32_t hierarchy, int reps, int flush_l2, double *out7);

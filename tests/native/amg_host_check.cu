@@ -20,7 +20,7 @@ int main() {
     // full setup on a 1-D Laplacian-like matrix: levels and Galerkin sizes
     int n = 5000; HostCSR A; A.n_rows = A.n_cols = n; A.indptr.assign(n + 1, 0);
     for (int i = 0; i < n; ++i) { if (i) { A.indices.push_back(i - 1); A.values.push_back(-1); } A.indices.push_back(i); A.values.push_back(2.001); if (i + 1 < n) { A.indices.push_back(i + 1); A.values.push_back(-1); } A.indptr[i + 1] = (int)A.indices.size(); }
-    AmgParams p; p.coarse_max = 600; std::vector<AmgLevelHost> L; amg_setup_host(A, p, L, 2);
+    AmgParams p; p.coarse_max = 600; p.device_inverse = 0; std::vector<AmgLevelHost> L; amg_setup_host(A, p, L, 2);
     for (auto &l : L) printf("level n=%d nnz=%zu rho=%.6f P=%dx%d Ainv=%zu\n", l.A.n_rows, l.A.values.size(), l.rho, l.P.n_rows, l.P.n_cols, l.Ainv.size());
     // coarse inverse check on the last level
     auto &last = L.back(); int nc = last.A.n_rows; double err = 0;

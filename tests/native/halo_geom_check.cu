@@ -264,6 +264,7 @@ int main()
     for (int fuse = 0; fuse < 1; ++fuse) {
         AmgParams p;
         p.coarse_max = 40;
+        p.device_inverse = 0;
         std::vector<AmgLevelHost> H;
         amg_setup_host(A, p, H, 1);
         const int nl = (int)H.size();

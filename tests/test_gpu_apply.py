@@ -123,22 +123,6 @@ def test_errors_are_reported_not_swallowed():
             _system(M, K2, n_t=4, beta=1e-2, CN=True, bc_dofs=bd)   # different pattern
 
 
-@pytest.mark.parametrize("tile_rows", ["16", "32"])
-def test_tma_staged_apply_matches_literal_operator(tile_rows, monkeypatch):
-    """The opt-in TMA-staged kernel (cp.async.bulk tiles + mbarrier, CTL_KKT_TMA=1)."""
-    monkeypatch.setenv("CTL_KKT_TMA", "1")
-    monkeypatch.setenv("CTL_TILE_ROWS", tile_rows)
-    M, K, _, bd = fem.assemble_p1_2d(23, 17, 2.0, 1.0)
-    for CN in (True, False):
-        for n_t in (5, 33, 64):
-            _check_apply(M, K, n_t, CN, bd, tau_interval=(0.0, 2.0), seed=n_t)
-    K2 = K.copy()
-    K2.data = K2.data * (1.0 + 0.2 * np.random.default_rng(1).standard_normal(K2.nnz))
-    _check_apply(M, K2, 20, True, bd)                      # non-symmetric K
-    M3, K3, _, bd3 = fem.assemble_p1_3d(6, 5, 4)
-    _check_apply(M3, K3, 9, True, bd3)
-
-
 @pytest.mark.parametrize("CN", [True, False])
 @pytest.mark.parametrize("n_t", [66, 100, 129, 200, 256])
 def test_apply_more_than_64_time_blocks(CN, n_t):

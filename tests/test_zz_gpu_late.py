@@ -189,25 +189,6 @@ def test_reference_stationary_stokes_known_answer_on_gpu():
     c.close()
 
 
-@pytest.mark.parametrize("R", ["2", "4"])
-def test_grouped_rows_apply_matches_literal_operator(R, monkeypatch):
-    """The opt-in grouped-rows KKT-apply kernel (CTL_KKT_GROUP=2|4: R consecutive rows share one gather of the
-    union of their columns; ld = 64 only) against the literal block-by-block operator: CN and BE, row counts that
-    are not multiples of R, Dirichlet rows, a 3-D tetrahedral stencil, no constrained dofs."""
-    from test_gpu_apply import _check_apply
-    from synthetic import fem
-    monkeypatch.setenv("CTL_KKT_GROUP", R)
-    M, K, _, bd = fem.assemble_p1_2d(23, 17, 2.0, 1.0)              # n = 432
-    M2, K2, _, bd2 = fem.assemble_p1_2d(6, 8, 1.0, 1.0)             # n = 63: last group incomplete
-    M3, K3, _, bd3 = fem.assemble_p1_3d(6, 5, 4)
-    for CN in (True, False):
-        for n_t in (40, 64):
-            _check_apply(M, K, n_t, CN, bd, tau_interval=(0.0, 2.0), seed=n_t)
-        _check_apply(M2, K2, 50, CN, bd2)
-        _check_apply(M2, K2, 50, CN, np.zeros(0, dtype=np.int32))
-        _check_apply(M3, K3, 64 if CN else 63, CN, bd3)
-
-
 def test_stokes_control_with_multigrid_mass_solver():
     """``incompressible_linear_solve(Multigrid=True)``: the (1,1) block of the inner heat-type preconditioner is
     solved with AMG cycles on ``M_v`` instead of Chebyshev (control/control.py:1954-1965 inside 4346-4353)."""
@@ -235,28 +216,3 @@ def test_stokes_control_with_multigrid_mass_solver():
     assert abs(info.its - res.its) <= max(1, int(0.03 * res.its))
     assert np.abs(c._v - v).max() < 1e-5 * np.abs(v).max() and np.abs(c._zeta - zeta).max() < 1e-5 * np.abs(zeta).max()
     c.close()
-
-
-@pytest.mark.skipif(__import__("os").environ.get("CTL_RUN_UNVERIFIED") != "1",
-                    reason="persistent two-stage TMA kernels (experiments): mode 2 ran bit-identical to the default kernel on "
-                           "a B200 at 512^2 CN (profiles/r01_kkt_apply_tma_pipe.txt); modes 3, 4 and these further shapes have "
-                           "not run on hardware yet (set CTL_RUN_UNVERIFIED=1 to run them)")
-@pytest.mark.parametrize("tile_rows", ["32", "16"])
-@pytest.mark.parametrize("mode", ["2", "3", "4"])
-def test_pipelined_tma_apply_matches_literal_operator(mode, tile_rows, monkeypatch):
-    """The opt-in persistent two-stage TMA kernels (CTL_KKT_TMA=2; =3: the CSR slice of a row block arrives as one
-    more bulk copy; =4: warp-specialised producer / consumers): more row blocks than CTAs (several pipeline iterations per CTA, both barrier phases), CN and
-    BE, non-symmetric K, a 3-D stencil."""
-    from test_gpu_apply import _check_apply
-    from synthetic import fem
-    monkeypatch.setenv("CTL_KKT_TMA", mode)
-    monkeypatch.setenv("CTL_TILE_ROWS", tile_rows)
-    M, K, _, bd = fem.assemble_p1_2d(160, 150, 2.0, 1.0)            # 24,311 rows: > 148 x 2 blocks of 32 rows
-    for CN in (True, False):
-        _check_apply(M, K, 64, CN, bd, tau_interval=(0.0, 2.0), seed=1)
-        _check_apply(M, K, 40, CN, bd, tau_interval=(0.0, 2.0), seed=2)
-    K2 = K.copy()
-    K2.data = K2.data * (1.0 + 0.2 * np.random.default_rng(1).standard_normal(K2.nnz))
-    _check_apply(M, K2, 50, True, bd)
-    M3, K3, _, bd3 = fem.assemble_p1_3d(12, 11, 10)
-    _check_apply(M3, K3, 64, True, bd3)
