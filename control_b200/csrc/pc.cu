@@ -15,6 +15,9 @@
 #include "pc.cuh"
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <map>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -347,8 +350,24 @@ int ctl_amg_setup_probe(const int32_t *indptr, const int32_t *indices, const dou
     return CTL_OK;
 }
 
+namespace {
+// CTL_SETUP_TIMING=1: where the time of ctl_pc_setup goes (stderr), next to the phases of the host AMG set-up
+struct SetupLap {
+    bool on = getenv("CTL_SETUP_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void operator()(const char *what)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ctl pc_setup] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
+}  // namespace
+
 int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
 {
+    SetupLap lap;
     CTL_CHECK(h && opts, CTL_ERR_ARG, "ctl_pc_setup: null argument");
     CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_pc_setup: ctl_assemble has not been called");
     CTL_CHECK(opts->mode == CTL_PCMODE_TRIANGULAR || opts->mode == CTL_PCMODE_DIAGONAL, CTL_ERR_ARG,
@@ -416,7 +435,9 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         CTL_TRY(ctl_upload(h, &st.d_mass_dinv, dinv.data(), dinv.size()));
     }
 
+    lap("transposition map, mass dinv");
     CTL_TRY(sell_build_pattern(h, h->loc, st.fine));
+    lap("fine SELL pattern");
     // multi-GPU: exchange geometry of everything that gathers through the mesh pattern, and the two level-0
     // exchange streams (iterates, right-hand sides) every hierarchy shares
     if (h->cfg.world > 1) {
@@ -447,6 +468,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         mesh_matrix(st.Msell);
     }
 
+    lap("mass matrix values");
     // distinct diagonal blocks -> AMG hierarchies; distinct off-diagonal blocks -> SELL
     const bool per_level = h->h_K.size() > 1;
     const bool sym = h->k_symmetric;
@@ -544,10 +566,12 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
             for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
             for (auto &t : pool) t.join();
         }
+        lap("host AMG set-up (all)");
         for (int i = 0; i < nh; ++i) {
             CTL_CHECK(errors[i].empty(), CTL_ERR_STATE, errors[i]);
             CTL_TRY(amg_build(h, st.hier[i].host[0].A, st.amg, st.fine, st.hier[i]));
         }
+        lap("formats, uploads, inverse");
         st.off.assign(n_off, SellMat());
         for (int i = 0; i < n_off; ++i) {
             CTL_TRY(sell_set_values(h, st.fine, off_values[i].data(), st.off[i]));
@@ -555,6 +579,7 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
             off_values[i] = std::vector<double>();
         }
         if (h->cfg.world > 1) CTL_TRY(halo_arena_finalize(h, st.arena));
+        lap("off-diagonal blocks, arena");
     }
 
     st.ts_stride = (size_t)nl + h->n_halo;
