@@ -1,5 +1,6 @@
-"""BASELINE config C2 at FULL size (2-D heat control, P1 on 1024x1024, n_t = 64, CN) through the
-C ABI: direct comparison of the fused KKT apply with the oracle (one application is seconds on the
+"""BASELINE configs C2 (2-D heat control, P1 on 1024x1024, n_t = 64, CN) and C3 (3-D, P1 tetrahedra on 128^3,
+n_t = 32, backward Euler) at FULL size through the C ABI, plus iteration-count parity with the CPU port at a size
+between the KATs and the BASELINE configs.  For C2: direct comparison of the fused KKT apply with the oracle (one application is seconds on the
 host), and the size-independent properties of the path -- linearity and symmetry of the operator,
 symmetry and positivity of the block-diagonal preconditioner, a converged solve whose true
 residual meets the tolerance, and J_h consistent with the objective evaluated by the oracle."""
@@ -90,3 +91,144 @@ def test_c2_solve_meets_tolerance_and_objective(c2):
     # the optimal state tracks the desired state: J is far below J(v = 0, zeta = 0)
     J0 = ocontrol.objective(q["M"], 0 * v, 0 * zeta, q["v_hat"], q["tau"], q["beta"], True)
     assert J_gpu < 0.5 * J0
+
+
+def test_c2_iteration_counts_of_record(c2):
+    """The counts every bench line and the CPU arm refer to (profiles/iteration_counts.json): MINRES + block-diagonal
+    preconditioner 15 iterations with the library's three V(3,3) cycles AND with the two V(4,4) cycles of the bench
+    configuration, FGMRES + block-triangular 11.  (Parity of the counts with the oracle: the mid-size test below and
+    tests/test_gpu_pc.py -- a full-size oracle solve takes minutes.)"""
+    from control_b200.control import build_rhs
+    q, s = c2
+    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], True, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
+    b = s.to_device(b0, b1)
+
+    def solve(ksp, mode, **amg):
+        s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode, **amg)
+        u = s.new_vector()
+        info = s.solve_device(b, u, pc="builtin", solver_parameters={
+            "linear_solver": ksp, "gmres_restart": 30, "maximum_iterations": 60, "relative_tolerance": 1e-6,
+            "absolute_tolerance": 0.0})
+        assert info.reason > 0
+        return info.its
+    assert abs(solve("minres", "diagonal") - 15) <= 1
+    assert abs(solve("minres", "diagonal", cycles=2, nu=4) - 15) <= 1
+    assert abs(solve("fgmres", "triangular") - 11) <= 1
+
+
+@pytest.mark.parametrize("ksp,mode,CN,amg", [("minres", "diagonal", True, dict(cycles=2, nu=4)),
+                                             ("fgmres", "triangular", True, {}),
+                                             ("gmres", "triangular", False, {})])
+def test_mid_size_iteration_counts_match_cpu_port(ksp, mode, CN, amg):
+    """Iteration-count parity ABOVE the KAT sizes: 256 x 256, n_t = 64 (n = 66,049, three-level hierarchy with the
+    library's default coarse_max; CPU counts 22 / 10 / 19), the library's solve against the oracle's Krylov method driving the C / OpenMP port of
+    operator and preconditioner (oracle/fastpc.py, itself checked against the numpy oracle in tests/test_oracle_fast.py):
+    identical counts, solutions equal to solver accuracy."""
+    from control_b200 import MultiBlockSystem
+    from control_b200.control import build_rhs
+    from oracle import krylov
+    fastpc = pytest.importorskip("oracle.fastpc")
+    try:
+        fastpc.lib()
+    except ImportError:
+        pytest.skip("oracle/_build/liboracle.so not built")
+    fastpc.set_threads()
+    q = kat.heat_problem(256, 64, CN)
+    M, K, bd, n_t = q["M"], q["K"], q["bdofs"], q["n_t"]
+    rtol = 1e-8
+    s = MultiBlockSystem(M, K, n_t=n_t, beta=q["beta"], CN=CN, time_interval=q["time_interval"], bc_dofs=bd)
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode=mode, **amg)
+    b0, b1 = build_rhs(M, K, q["tau"], n_t, CN, bd, q["v_d"], q["f"], np.zeros(s.n))
+    b = s.to_device(b0, b1)
+    u = s.new_vector()
+    restart = 30 if ksp != "gmres" else 10
+    info = s.solve_device(b, u, pc="builtin", solver_parameters={
+        "linear_solver": ksp, "gmres_restart": restart, "maximum_iterations": 100, "relative_tolerance": rtol,
+        "absolute_tolerance": 0.0})
+    assert info.reason > 0
+    f = fastpc.FastPc(M, K, q["tau"], q["beta"], n_t, CN, bd, lambda_v_bounds=q["lambda_v_bounds"], mode=mode,
+                      amg_params=amg or None)
+    N, n = f.N, f.n
+
+    def split(x):
+        return x[:N * n].reshape(N, n), x[N * n:].reshape(N, n)
+
+    def A(x):
+        return np.concatenate([a.ravel() for a in f.kkt_apply(*split(x))])
+
+    def wrap(x):                 # Preconditioner.apply: constrained entries of u take the values of b
+        x0, x1 = split(x)
+        p0, p1 = x0.copy(), x1.copy()
+        p0[:, bd] = 0.0
+        p1[:, bd] = 0.0
+        u0, u1 = f.pc_apply(p0, p1)
+        u0[:, bd] = x0[:, bd]
+        u1[:, bd] = x1[:, bd]
+        return np.concatenate([u0.ravel(), u1.ravel()])
+    bh = np.concatenate([b0.ravel(), b1.ravel()])
+    if ksp == "minres":
+        x, res = krylov.minres(A, bh, np.zeros_like(bh), pc=wrap, rtol=rtol, atol=0.0, max_it=100)
+    else:
+        x, res = krylov.gmres(A, bh, np.zeros_like(bh), pc=wrap, flexible=(ksp == "fgmres"), restart=restart, rtol=rtol,
+                              atol=0.0, max_it=100)
+    assert res.reason > 0
+    assert abs(info.its - res.its) <= 1, (info.its, res.its)      # north_star: counts within +-1 (measured: equal)
+    g = np.concatenate([a.ravel() for a in s.to_host_blocks(u)])
+    assert np.abs(g - x).max() <= 1e-6 * np.abs(x).max()
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def c3():
+    """BASELINE config C3 at full size: 3-D heat control, P1 tetrahedra on the 128^3 unit-cube mesh (n = 2,146,689,
+    32 M matrix entries), n_t = 32, backward Euler (control/control.py:2191-2438)."""
+    from control_b200 import MultiBlockSystem
+    q = kat.heat_problem_3d(128, 32, False)
+    s = MultiBlockSystem(q["M"], q["K"], n_t=q["n_t"], beta=q["beta"], CN=False, time_interval=q["time_interval"],
+                         bc_dofs=q["bdofs"])
+    yield q, s
+    s.close()
+
+
+def test_c3_apply_matches_oracle(c3):
+    q, s = c3
+    g = torch.Generator(device=s.device).manual_seed(3)
+    x = torch.randn(s.vec_len(), dtype=torch.float64, device=s.device, generator=g)
+    Ax = s.apply(x)
+    x0, x1 = s.to_host_blocks(x)
+    r0, r1 = kkt.kkt_apply_fused(q["M"], q["K"], q["tau"], q["beta"], q["n_t"], False, q["bdofs"], x0, x1)
+    g0, g1 = s.to_host_blocks(Ax)
+    scale = max(np.abs(r0).max(), np.abs(r1).max())
+    assert np.abs(g0 - r0).max() <= 1e-13 * scale and np.abs(g1 - r1).max() <= 1e-13 * scale
+    # constrained rows return x bit for bit (DirichletBCNullspace, preconditioner/preconditioner.py:158-197)
+    assert np.array_equal(g0[:, q["bdofs"]], x0[:, q["bdofs"]]) and np.array_equal(g1[:, q["bdofs"]], x1[:, q["bdofs"]])
+
+
+def test_c3_solve_with_the_reference_defaults(c3):
+    """GMRES(10) + in-built block-triangular preconditioner, rtol 1e-6: the reference's default Krylov parameters
+    (control/control.py:3260-3266).  The count is the one of record (18), the TRUE residual meets the tolerance the
+    preconditioned recurrence was stopped at up to the conditioning of the preconditioner, and J_h on the device
+    equals the oracle's."""
+    from control_b200.control import build_rhs
+    q, s = c3
+    s.setup_preconditioner(lambda_v_bounds=q["lambda_v_bounds"], mode="triangular")
+    b0, b1 = build_rhs(q["M"], q["K"], q["tau"], q["n_t"], False, q["bdofs"], q["v_d"], q["f"], np.zeros(s.n))
+    b = s.to_device(b0, b1)
+    u = s.new_vector()
+    info = s.solve_device(b, u, pc="builtin", solver_parameters={
+        "linear_solver": "gmres", "gmres_restart": 10, "maximum_iterations": 50, "relative_tolerance": 1e-6,
+        "absolute_tolerance": 0.0})
+    assert info.reason > 0 and abs(info.its - 18) <= 1
+    assert s.residual_norm(b, u) <= 1e-3 * float(b.norm())
+    # preconditioner: linear (fixed cycles, fixed polynomial smoothers)
+    g = torch.Generator(device=s.device).manual_seed(4)
+    x = torch.randn(s.vec_len(), dtype=torch.float64, device=s.device, generator=g)
+    y = torch.randn(s.vec_len(), dtype=torch.float64, device=s.device, generator=g)
+    z = s.pc_apply(2.0 * x - 3.0 * y)
+    assert float((z - (2.0 * s.pc_apply(x) - 3.0 * s.pc_apply(y))).abs().max()) <= 1e-10 * float(z.abs().max())
+    v, zeta = s.to_host_blocks(u)
+    J_ref = ocontrol.objective(q["M"], v, zeta, q["v_hat"], q["tau"], q["beta"], False)
+    J_dev = s.objective_device(torch.from_numpy(np.ascontiguousarray(v)).to(s.device),
+                               torch.from_numpy(np.ascontiguousarray(zeta)).to(s.device),
+                               torch.from_numpy(np.ascontiguousarray(q["v_hat"])).to(s.device))
+    assert abs(J_dev - J_ref) <= 1e-12 * abs(J_ref)
