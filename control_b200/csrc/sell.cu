@@ -261,7 +261,10 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
 
 namespace {
 
-constexpr int ST = 128;      // threads per CTA of every kernel in this file
+#ifndef CTL_ST
+#define CTL_ST 128
+#endif
+constexpr int ST = CTL_ST;      // threads per CTA of every kernel in this file (128; -DCTL_ST=256 is an experiment build)
 constexpr int SC = 8;        // SELL entries fetched per thread before the first dependent gather
 
 // ---- a gathered vector on the device: owned entries, and the ghosts either plainly stored (completed earlier) or
@@ -709,7 +712,13 @@ __global__ void __launch_bounds__(ST) dense_gemv_kernel(const double *__restrict
     }
     __syncthreads();
     if (threadIdx.x < GR && r0 + threadIdx.x < n)
-        y[r0 + threadIdx.x] = (part[threadIdx.x][0] + part[threadIdx.x][1]) + (part[threadIdx.x][2] + part[threadIdx.x][3]);
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < ST / 32; w += 4)      // fixed order: pairs first
+            s += (part[threadIdx.x][w] + part[threadIdx.x][w + 1]) + (part[threadIdx.x][w + 2] + part[threadIdx.x][w + 3]);
+        y[r0 + threadIdx.x] = s;
+    }
 }
 
 // ---------------------------------------------------------------- CSR-vector kernels
