@@ -8,8 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CTL_LIB_VARIANT=<dir>: an experiment build of the same sources (e.g. lib/st256: -DCTL_ST=256), never the default
-LIB_PATH = os.path.join(_HERE, "lib", os.environ.get("CTL_LIB_VARIANT", ""), "libctl_b200.so")
+LIB_PATH = os.path.join(_HERE, "lib", "libctl_b200.so")
 
 CTL_LAYOUT_BLOCK_MAJOR, CTL_LAYOUT_TIME_FASTEST = 0, 1
 CTL_MAT_M, CTL_MAT_K, CTL_MAT_KT = 0, 1, 2

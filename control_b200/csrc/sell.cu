@@ -261,10 +261,8 @@ int sell_from_csr(ctl_handle_s *h, const HostCSR &A, SellMat &out, int force_lan
 
 namespace {
 
-#ifndef CTL_ST
-#define CTL_ST 128
-#endif
-constexpr int ST = CTL_ST;      // threads per CTA of every kernel in this file (128; -DCTL_ST=256 is an experiment build)
+constexpr int ST = 128;      // threads per CTA of the kernels in this file (the one-row-per-thread kernels of a large
+                             // level run 256: big_block_rows)
 constexpr int SC = 8;        // SELL entries fetched per thread before the first dependent gather
 
 // ---- a gathered vector on the device: owned entries, and the ghosts either plainly stored (completed earlier) or
@@ -494,14 +492,14 @@ __device__ __forceinline__ double csrv_row_dot(const MatView &A, int row, int su
 // rows, one chunk of <= 32 rows per warp, storing them locally and into the ghost slots of the ranks that gather
 // them; the regular CTAs compute ST / T consecutive rows each.  f(row) is evaluated by all T lanes of a row's
 // group and returns the value to store in out[row].
-template <int T, typename F>
+template <int T, int BS = ST, typename F>
 __device__ __forceinline__ void run_rows(int n_rows, const HaloPush &push, unsigned seq_hi, double *out, F f)
 {
-    constexpr int RPC = ST / T;
+    constexpr int RPC = BS / T;
     const int lane = threadIdx.x & 31;
-    const int n_pc = (push.n_chunks + ST / 32 - 1) / (ST / 32);
+    const int n_pc = (push.n_chunks + BS / 32 - 1) / (BS / 32);
     if ((int)blockIdx.x < n_pc) {
-        const int ci = blockIdx.x * (ST / 32) + (threadIdx.x >> 5);
+        const int ci = blockIdx.x * (BS / 32) + (threadIdx.x >> 5);
         if (ci >= push.n_chunks) {
             pdl_wait();      // no thread leaves before the predecessor is complete: grids finish in launch order
             return;
@@ -562,12 +560,12 @@ __device__ __forceinline__ unsigned kernel_prologue(const HaloCtx &ctx)
 
 // ---------------------------------------------------------------- SELL kernels
 // GH: the gathered vector has ghost entries (several GPUs); without them the gather is a plain read-only load
-template <int FMT, bool STREAM, bool GH>
-__global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
+template <int FMT, bool STREAM, bool GH, int BS>
+__global__ void __launch_bounds__(BS) sell_spmv_kernel(const MatView A, const DVec x, const HaloCtx ctx, const double *b,
                                                       double *y, int mode, double sign, const HaloPush push)
 {
     const unsigned hi = kernel_prologue(ctx);
-    run_rows<1>(A.n_rows, push, hi, y, [&](int row) {
+    run_rows<1, BS>(A.n_rows, push, hi, y, [&](int row) {
         double bi = 0.0;
         const double ax = sign * sell_row_dot<FMT, STREAM>(
                                      A, row, [&](int c) { return GH ? dvec_get(x, c, hi, ctx) : x.x[c]; },
@@ -592,26 +590,26 @@ __global__ void __launch_bounds__(ST) sell_spmv_kernel(const MatView A, const DV
     else if (a != 0.0) r = fma(a, pp, r);                                                                 \
     return r
 
-template <int FMT, bool STREAM, bool GH>
-__global__ void __launch_bounds__(ST) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
+template <int FMT, bool STREAM, bool GH, int BS>
+__global__ void __launch_bounds__(BS) sell_cheb_kernel(const MatView A, const double *__restrict__ dinv,
                                                       const double *b, const double *p_prev, const DVec p_cur,
                                                       const HaloCtx ctx, double *out, double a, double bq, double c,
                                                       double prev_scale, const HaloPush push)
 {
     const unsigned hi = kernel_prologue(ctx);
-    run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
+    run_rows<1, BS>(A.n_rows, push, hi, out, [&](int row) {
         CHEB_ROW_UPDATE((sell_row_dot<FMT, STREAM>(
             A, row, [&](int cc) { return GH ? dvec_get(p_cur, cc, hi, ctx) : p_cur.x[cc]; },
             [&](int cc) { return p_cur.x[cc]; }, pre)));
     });
 }
 
-template <int FMT, bool STREAM, bool GH>
-__global__ void __launch_bounds__(ST) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
+template <int FMT, bool STREAM, bool GH, int BS>
+__global__ void __launch_bounds__(BS) sell_first2_kernel(const MatView A, const DVec dinv, const DVec b, const HaloCtx ctx,
                                                         double *out, double s, double wgt, const HaloPush push)
 {
     const unsigned hi = kernel_prologue(ctx);
-    run_rows<1>(A.n_rows, push, hi, out, [&](int row) {
+    run_rows<1, BS>(A.n_rows, push, hi, out, [&](int row) {
         const double di = pre_ld(dinv.x + row);
         double bi = 0.0;
         const double ax = sell_row_dot<FMT, STREAM>(
@@ -779,16 +777,32 @@ DVec dvec(const GVec &g, const MatView &A)
 bool has_ghosts(const GVec &g) { return g.ghost != nullptr || g.ll != nullptr; }
 
 // push CTAs first; a replicating exchange pushes every row, so the regular CTAs are not launched at all
-int grid_for(int n_rows, int T, const HaloPush &push)
+int grid_for(int n_rows, int T, const HaloPush &push, int bs = ST)
 {
-    if (push.all_rows) return halo_push_ctas(push, ST);
-    return ceil_div((int64_t)n_rows * T, ST) + halo_push_ctas(push, ST);
+    if (push.all_rows) return halo_push_ctas(push, bs);
+    return ceil_div((int64_t)n_rows * T, bs) + halo_push_ctas(push, bs);
+}
+
+// CTAs of 256 threads for the one-row-per-thread kernels of a LARGE level on one GPU: the 1 M-row kernels of C2 are
+// bound by launch ramp and tail of their 8209 small CTAs (43 % of the warp slots active, ncu), and half as many CTAs
+// of twice the size take 11-15 % off them (smoother step 11.95 -> 10.63 us, residual 11.76 -> 10.02 us, measured with
+// an all-256 build: profiles/r02_inner_solve_variants.txt); the small levels lose with fewer, larger CTAs and keep 128.
+int big_block_rows()
+{
+    static int v = -1;
+    if (v < 0) {
+        v = 400000;
+        if (const char *e = getenv("CTL_BIG_BLOCK_ROWS")) v = atoi(e);      // experiment; 0 = never
+        if (v <= 0) v = 2147483647;
+    }
+    return v;
 }
 
 #define SELL_LAUNCH_GH(KERNEL, FMT, STREAM, ...)                                                            \
     do {                                                                                                    \
-        if (gh__) pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, true>, __VA_ARGS__);                        \
-        else pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, false>, __VA_ARGS__);                            \
+        if (gh__) pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, true, ST>, __VA_ARGS__);                    \
+        else if (big__) pdl_launch(h, grid__, 256, KERNEL<FMT, STREAM, false, 256>, __VA_ARGS__);           \
+        else pdl_launch(h, grid__, ST, KERNEL<FMT, STREAM, false, ST>, __VA_ARGS__);                        \
     } while (0)
 
 #define SELL_LAUNCH_ST(KERNEL, FMT, ...)                                                                    \
@@ -800,9 +814,10 @@ int grid_for(int n_rows, int T, const HaloPush &push)
 // gh__: a gathered vector comes with ghost entries
 #define SELL_DISPATCH(KERNEL, A, GHOSTS, ...)                                                               \
     do {                                                                                                    \
-        const int grid__ = grid_for((A).pat->n_rows, 1, push);                                              \
-        if (grid__ == 0) return CTL_OK;                                                                     \
         const bool st__ = (A).stream, gh__ = (GHOSTS);                                                      \
+        const bool big__ = !gh__ && push.n_chunks == 0 && (A).pat->n_rows >= big_block_rows();              \
+        const int grid__ = grid_for((A).pat->n_rows, 1, push, big__ ? 256 : ST);                            \
+        if (grid__ == 0) return CTL_OK;                                                                     \
         switch ((A).fmt) {                                                                                  \
         case FMT_F64: SELL_LAUNCH_ST(KERNEL, FMT_F64, __VA_ARGS__); break;                                  \
         case FMT_D16: SELL_LAUNCH_ST(KERNEL, FMT_D16, __VA_ARGS__); break;                                  \
