@@ -4,6 +4,12 @@
 // block_11, control/control.py:2915-2923, 2940-2953; the reference itself never evaluates J).
 // One kernel over (rows x levels) with the FULL mass matrix (no Dirichlet elimination: vhat need not
 // vanish on the boundary), fixed-order two-stage reduction, 2 n_t doubles read back.
+//
+// Several ranks (round 2): every rank hands over ITS rows of the level-major arrays (n_t x n_local).  The products
+// with M gather ghost columns, so the arrays are first extended to n_t x (n_local + n_halo) -- owned entries copied,
+// ghost entries fetched from their owners with the row exchange of the batched kernels (levels travel as the
+// columns of a time-fastest panel, comm.cu) -- and the same kernels run on the local pattern, whose column
+// numbering is exactly that (owned columns first, ghosts behind).  Scalars are all-reduced.
 #include "common.cuh"
 
 namespace {
@@ -14,10 +20,10 @@ __global__ void __launch_bounds__(QT) quadform_partial_kernel(const int *__restr
                                                              const double *__restrict__ Mv, const double *__restrict__ v,
                                                              const double *__restrict__ zeta,
                                                              const double *__restrict__ vhat, double *__restrict__ partial,
-                                                             int n)
+                                                             int n, int stride)
 {
     __shared__ double sh[2][QT / 32];
-    const size_t base = (size_t)blockIdx.y * n;
+    const size_t base = (size_t)blockIdx.y * stride;      // n rows of this rank; stride = n + ghost entries
     const int row = blockIdx.x * QT + threadIdx.x;
     double qd = 0.0, qz = 0.0;
     if (row < n) {
@@ -63,37 +69,102 @@ __global__ void quadform_finish_kernel(const double *__restrict__ partial, doubl
     out[2 * blockIdx.x + threadIdx.x] = s;
 }
 
+// panel[r][j] = x[(l0 + j) * n + r] for j < cnt, 0 otherwise (levels of a level-major array as panel columns)
+__global__ void levels_to_panel_kernel(const double *__restrict__ x, int l0, int cnt, int n, int ld, double *__restrict__ panel)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * ld) return;
+    const int r = (int)(idx / ld), j = (int)(idx % ld);
+    panel[idx] = j < cnt ? x[(size_t)(l0 + j) * n + r] : 0.0;
+}
+
+// ext[(l0 + j) * stride + n + g] = halo[g][j]: ghost entries behind the owned ones
+__global__ void halo_to_levels_kernel(const double *__restrict__ halo, int l0, int cnt, int n_halo, int ld, int n, int stride,
+                                      double *__restrict__ ext)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n_halo * cnt) return;
+    const int g = (int)(idx / cnt), j = (int)(idx % cnt);
+    ext[(size_t)(l0 + j) * stride + n + g] = halo[(size_t)g * ld + j];
+}
+
 }  // namespace
+
+// L levels of this rank's rows -> L levels of (n_loc + n_halo) entries in local column numbering (ext: device,
+// allocated by the caller).  One rank: ext is not needed (callers pass the array itself with stride n).
+static int extend_levels(ctl_handle_s *h, const double *x_loc, int L, double *ext)
+{
+    const int nl = h->n_loc, nh = h->n_halo, ld = h->ld, stride = nl + nh;
+    CTL_CUDA(cudaMemcpy2DAsync(ext, (size_t)stride * sizeof(double), x_loc, (size_t)nl * sizeof(double),
+                               (size_t)nl * sizeof(double), (size_t)L, cudaMemcpyDeviceToDevice, h->stream));
+    if (nh == 0) return CTL_OK;
+    double *panel = nullptr;
+    CTL_TRY(ctl_scratch_get(h, &panel));
+    int rc = CTL_OK;
+    for (int l0 = 0; l0 < L && rc == CTL_OK; l0 += ld) {
+        const int cnt = std::min(ld, L - l0);
+        levels_to_panel_kernel<<<ceil_div((int64_t)nl * ld, 256), 256, 0, h->stream>>>(x_loc, l0, cnt, nl, ld, panel);
+        h->launches++;
+        rc = ctl_halo_exchange_panel(h, panel);
+        if (rc != CTL_OK) break;
+        halo_to_levels_kernel<<<ceil_div((int64_t)nh * cnt, 256), 256, 0, h->stream>>>(h->d_halo, l0, cnt, nh, ld, nl, stride, ext);
+        h->launches++;
+        if (cudaGetLastError() != cudaSuccess) {
+            ctl_set_error(h, "extend_levels: CUDA failure");
+            rc = CTL_ERR_CUDA;
+        }
+    }
+    ctl_scratch_put(h, panel);
+    return rc;
+}
 
 extern "C" int ctl_objective(ctl_handle h, const double *v, const double *zeta, const double *v_hat, double *out)
 {
     CTL_CHECK(h && v && zeta && v_hat && out, CTL_ERR_ARG, "ctl_objective: null argument");
     CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_objective: ctl_assemble has not been called");
-    CTL_CHECK(h->cfg.world == 1, CTL_ERR_ARG, "ctl_objective: single-rank only (use ctl_objective_host)");
+    CTL_CHECK(h->cfg.world == 1 || h->comm, CTL_ERR_STATE, "ctl_objective: call ctl_comm_init first (world > 1)");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
-    const int n = h->n, n_t = h->cfg.n_t;
+    const int n = h->n_loc, n_t = h->cfg.n_t, stride = h->n_loc + h->n_halo;
     if (!h->d_M_full) {
         std::vector<double> buf(h->loc_entry.size());
         for (size_t p = 0; p < buf.size(); ++p) buf[p] = h->h_M[h->loc_entry[p]];
         CTL_TRY(ctl_upload(h, &h->d_M_full, buf.data(), buf.size()));
     }
     const int blocks = ceil_div(n, QT);
-    double *partial = nullptr, *sums = nullptr;
-    CTL_CUDA(cudaMalloc((void **)&partial, sizeof(double) * 2 * (size_t)blocks * n_t));
-    CTL_CUDA(cudaMalloc((void **)&sums, sizeof(double) * 2 * n_t));
-    quadform_partial_kernel<<<dim3(blocks, n_t), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, v, zeta, v_hat,
-                                                                    partial, n);
-    quadform_finish_kernel<<<n_t, 32, 0, h->stream>>>(partial, sums, blocks);
-    h->launches += 2;
+    double *partial = nullptr, *sums = nullptr, *ext = nullptr;
+    int rc = CTL_OK;
+    cudaError_t e = cudaSuccess;
     std::vector<double> hs(2 * (size_t)n_t);
-    cudaError_t e = cudaMemcpyAsync(hs.data(), sums, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    do {
+        const double *pv = v, *pz = zeta, *ph = v_hat;
+        if (h->n_halo > 0) {      // several ranks: ghost entries of the three arrays behind the owned ones
+            const size_t one = (size_t)n_t * stride;
+            if ((e = cudaMalloc((void **)&ext, 3 * one * sizeof(double))) != cudaSuccess) break;
+            if ((rc = extend_levels(h, v, n_t, ext)) != CTL_OK) break;
+            if ((rc = extend_levels(h, zeta, n_t, ext + one)) != CTL_OK) break;
+            if ((rc = extend_levels(h, v_hat, n_t, ext + 2 * one)) != CTL_OK) break;
+            pv = ext;
+            pz = ext + one;
+            ph = ext + 2 * one;
+        }
+        if ((e = cudaMalloc((void **)&partial, sizeof(double) * 2 * (size_t)blocks * n_t)) != cudaSuccess) break;
+        if ((e = cudaMalloc((void **)&sums, sizeof(double) * 2 * n_t)) != cudaSuccess) break;
+        quadform_partial_kernel<<<dim3(blocks, n_t), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, pv, pz, ph,
+                                                                        partial, n, h->n_halo > 0 ? stride : n);
+        quadform_finish_kernel<<<n_t, 32, 0, h->stream>>>(partial, sums, blocks);
+        h->launches += 2;
+        if ((rc = ctl_allreduce_sum(h, sums, 2 * n_t)) != CTL_OK) break;      // (no-op on one rank)
+        e = cudaMemcpyAsync(hs.data(), sums, sizeof(double) * hs.size(), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    } while (0);
     cudaFree(partial);
     cudaFree(sums);
+    cudaFree(ext);
     if (e != cudaSuccess) {
         ctl_set_error(h, std::string("ctl_objective: ") + cudaGetErrorString(e));
         return CTL_ERR_CUDA;
     }
+    if (rc != CTL_OK) return rc;
     const double tau = h->cfg.tau, beta = h->cfg.beta;
     double J = 0.0;
     for (int i = 0; i < n_t; ++i) {
@@ -118,14 +189,14 @@ namespace {
 __global__ void __launch_bounds__(QT) rhs_rows_kernel(const int *__restrict__ ptr, const int *__restrict__ cols,
                                                      const double *__restrict__ Mv, const uint8_t *__restrict__ bc,
                                                      const double *__restrict__ x, double *__restrict__ out, int n,
-                                                     double alpha, int pair, int off)
+                                                     int stride, double alpha, int pair, int off)
 {
     const int row = blockIdx.x * QT + threadIdx.x;
     if (row >= n) return;
     const int i = blockIdx.y;
     double acc = 0.0;
     if (!bc[row]) {
-        const double *x0 = x + (size_t)(i + off) * n, *x1 = x0 + n;
+        const double *x0 = x + (size_t)(i + off) * stride, *x1 = x0 + stride;      // stride = n + ghost entries
         for (int k = ptr[row]; k < ptr[row + 1]; ++k) {
             const int c = cols[k];
             acc = fma(Mv[k], pair ? x0[c] + x1[c] : x0[c], acc);
@@ -160,9 +231,10 @@ extern "C" int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_
 {
     CTL_CHECK(h && v_hat && f_nodal && b, CTL_ERR_ARG, "ctl_build_rhs: null argument");
     CTL_CHECK(h->assembled, CTL_ERR_STATE, "ctl_build_rhs: ctl_assemble has not been called");
-    CTL_CHECK(h->cfg.world == 1, CTL_ERR_ARG, "ctl_build_rhs: single-rank only");
+    CTL_CHECK(h->cfg.world == 1 || h->comm, CTL_ERR_STATE, "ctl_build_rhs: call ctl_comm_init first (world > 1)");
     CTL_CUDA(cudaSetDevice(h->cfg.device));
-    const int n = h->n, n_t = h->cfg.n_t, N = h->N;
+    const int n = h->n_loc, n_t = h->cfg.n_t, N = h->N, rb = h->row_begin;
+    const int stride = h->n_halo > 0 ? h->n_loc + h->n_halo : n;
     const bool cn = h->cfg.CN != 0;
     const double tau = h->cfg.tau;
     if (!h->d_M_full) {
@@ -170,17 +242,34 @@ extern "C" int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_
         for (size_t p = 0; p < buf.size(); ++p) buf[p] = h->h_M[h->loc_entry[p]];
         CTL_TRY(ctl_upload(h, &h->d_M_full, buf.data(), buf.size()));
     }
+    double *ext = nullptr;
+    const double *pv = v_hat, *pf = f_nodal;
+    if (h->n_halo > 0) {      // several ranks: this rank's rows of the nodal data + the ghost entries the products gather
+        const size_t one = (size_t)n_t * stride;
+        CTL_CUDA(cudaMalloc((void **)&ext, 2 * one * sizeof(double)));
+        int rc0 = extend_levels(h, v_hat, n_t, ext);
+        if (rc0 == CTL_OK) rc0 = extend_levels(h, f_nodal, n_t, ext + one);
+        if (rc0 != CTL_OK) {
+            cudaFree(ext);
+            return rc0;
+        }
+        pv = ext;
+        pf = ext + one;
+    }
     const int blocks = ceil_div(n, QT);
     const size_t half = (size_t)N * n;
     double *work = nullptr;                       // untransformed rows (CN) before T_1 / T_2
-    CTL_TRY(ctl_scratch_get(h, &work));           // a scratch vector holds at least 2 N n doubles
+    if (ctl_scratch_get(h, &work) != CTL_OK) {    // a scratch vector holds at least 2 N n doubles
+        cudaFree(ext);
+        return CTL_ERR_CUDA;
+    }
     double *r0 = cn ? work : b, *r1 = cn ? work + half : b + half;
     // M-weighted rows: CN h M (x_i + x_{i+1}), i < N;  BE tau M x_i, with b_0 row n_t - 1 = 0 and b_1 row 0 from v_0
     const double alpha = cn ? 0.5 * tau : tau;
-    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, v_hat, r0, n,
-                                                          alpha, cn ? 1 : 0, 0);
-    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, f_nodal, r1, n,
-                                                          alpha, cn ? 1 : 0, 0);
+    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, pv, r0, n,
+                                                          stride, alpha, cn ? 1 : 0, 0);
+    rhs_rows_kernel<<<dim3(blocks, N), QT, 0, h->stream>>>(h->d_indptr, h->d_indices, h->d_M_full, h->d_bcmask, pf, r1, n,
+                                                          stride, alpha, cn ? 1 : 0, 0);
     h->launches += 2;
     int rc = CTL_OK;
     if (!cn) {
@@ -189,13 +278,14 @@ extern "C" int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_
             rc = CTL_ERR_CUDA;
     }
     // terms of the initial condition (control/control.py:3000-3004 BE, 3217-3240 CN), on the host:
-    // two products with one n-vector
+    // two products with one n-vector (v_0: all n entries on every rank; the rows of this rank are computed)
     if (rc == CTL_OK && v_0_host) {
         const std::vector<double> &K0 = h->h_K[0];
         std::vector<double> c0(n, 0.0), c1(n, 0.0);
         for (int r = 0; r < n; ++r) {
+            const int g = rb + r;
             double mv = 0.0, kv = 0.0;
-            for (int k = h->h_indptr[r]; k < h->h_indptr[r + 1]; ++k) {
+            for (int k = h->h_indptr[g]; k < h->h_indptr[g + 1]; ++k) {
                 const double x = v_0_host[h->h_indices[k]];
                 mv += h->h_M[k] * x;
                 kv += K0[k] * x;
@@ -226,7 +316,9 @@ extern "C" int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_
         h->launches += 2;
     }
     if (rc == CTL_OK && cudaGetLastError() != cudaSuccess) rc = CTL_ERR_CUDA;
+    if (rc == CTL_OK && ext && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = CTL_ERR_CUDA;      // ext is freed below
     if (rc != CTL_OK) ctl_set_error(h, "ctl_build_rhs: CUDA failure");
     ctl_scratch_put(h, work);
+    cudaFree(ext);
     return rc;
 }

@@ -786,7 +786,8 @@ int grid_for(int n_rows, int T, const HaloPush &push, int bs = ST)
 // CTAs of 256 threads for the one-row-per-thread kernels of a LARGE level on one GPU: the 1 M-row kernels of C2 are
 // bound by launch ramp and tail of their 8209 small CTAs (43 % of the warp slots active, ncu), and half as many CTAs
 // of twice the size take 11-15 % off them (smoother step 11.95 -> 10.63 us, residual 11.76 -> 10.02 us, measured with
-// an all-256 build: profiles/r02_inner_solve_variants.txt); the small levels lose with fewer, larger CTAs and keep 128.
+// an all-256 build: profiles/r02_inner_solve_variants.txt); the small levels lose with fewer, larger CTAs and keep 128,
+// and so do long rows (the 15-point stencil of C3: its level-0 smoother went from 53 to 58 us with 256-thread CTAs).
 int big_block_rows()
 {
     static int v = -1;
@@ -815,7 +816,8 @@ int big_block_rows()
 #define SELL_DISPATCH(KERNEL, A, GHOSTS, ...)                                                               \
     do {                                                                                                    \
         const bool st__ = (A).stream, gh__ = (GHOSTS);                                                      \
-        const bool big__ = !gh__ && push.n_chunks == 0 && (A).pat->n_rows >= big_block_rows();              \
+        const bool big__ = !gh__ && push.n_chunks == 0 && (A).pat->n_rows >= big_block_rows() &&            \
+                           (A).pat->nnz <= 10ll * (A).pat->n_rows;                                          \
         const int grid__ = grid_for((A).pat->n_rows, 1, push, big__ ? 256 : ST);                            \
         if (grid__ == 0) return CTL_OK;                                                                     \
         switch ((A).fmt) {                                                                                  \

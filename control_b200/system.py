@@ -436,22 +436,26 @@ class MultiBlockSystem:
         return float(out.value)
 
     def objective_device(self, v_dev, zeta_dev, v_hat_dev):
-        """J_h from device arrays of n_t levels x n (level-major), evaluated on the GPU."""
-        need = self.n_t * self.n
+        """J_h from device arrays of n_t levels x n_local (level-major; this rank's rows), evaluated on the GPU;
+        on several ranks every rank receives the global value."""
+        need = self.n_t * self.n_local
         for t in (v_dev, zeta_dev, v_hat_dev):
             if t.numel() != need or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
-                raise ValueError("objective_device needs contiguous float64 CUDA tensors of n_t * n entries")
+                raise ValueError("objective_device needs contiguous float64 CUDA tensors of n_t * n_local entries")
         out = C.c_double()
         self._call(self._lib.ctl_objective, v_dev.data_ptr(), zeta_dev.data_ptr(), v_hat_dev.data_ptr(), C.byref(out))
         return float(out.value)
 
     def build_rhs_device(self, v_hat_dev, f_nodal_dev, v_0=None):
         """Block-major device right-hand side of ``linear_solve`` from nodal data on the device
-        (n_t levels x n each); ``v_0``: host initial condition or None (``ctl_build_rhs``)."""
-        need = self.n_t * self.n
+        (n_t levels x n_local each: this rank's rows); ``v_0``: host initial condition (all n entries) or None
+        (``ctl_build_rhs``)."""
+        need = self.n_t * self.n_local
         for t in (v_hat_dev, f_nodal_dev):
             if t.numel() != need or t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
-                raise ValueError("build_rhs_device needs contiguous float64 CUDA tensors of n_t * n entries")
+                raise ValueError("build_rhs_device needs contiguous float64 CUDA tensors of n_t * n_local entries")
+        if v_0 is not None and np.size(v_0) != self.n:
+            raise ValueError("build_rhs_device: v_0 must hold all n entries")
         b = self.new_vector()
         v0 = None if v_0 is None else np.ascontiguousarray(v_0, dtype=np.float64)
         self._call(self._lib.ctl_build_rhs, v_hat_dev.data_ptr(), f_nodal_dev.data_ptr(),

@@ -197,14 +197,17 @@ int ctl_nonlinear_residual(ctl_handle h, const double *b, const double *x, doubl
 /* discrete objective J_h; v, zeta, v_hat: n_t levels x n, host */
 int ctl_objective_host(ctl_handle h, const double *v_host, const double *zeta_host,
                        const double *v_hat_host, double *out);
-/* the same on DEVICE arrays (n_t levels x n, level-major); the scalar is returned to the host.
- * Single rank. */
+/* the same on DEVICE arrays (n_t levels x n_local, level-major: this rank's rows); the scalar is returned to the
+ * host.  Several ranks: ghost entries are fetched from their owners, the sums are all-reduced, every rank
+ * receives J_h. */
 int ctl_objective(ctl_handle h, const double *v, const double *zeta, const double *v_hat,
                   double *out_host);
 /* ---- right-hand sides of linear_solve from NODAL data (control/control.py:2980-3243, homogeneous
  *      Dirichlet data): v_hat, f_nodal are DEVICE arrays of n_t levels x n (the reference's
  *      cofunctions are M v_hat_i, M f_i for interpolated data); v_0_host: the initial condition
- *      (n doubles, host) or NULL = 0; b: DEVICE block-major output, T_1 / T_2 applied.  Single rank. */
+ *      (n doubles, host: ALL n entries on every rank) or NULL = 0; b: DEVICE block-major output (this rank's
+ *      rows), T_1 / T_2 applied.  Several ranks: v_hat, f_nodal hold this rank's rows (n_t x n_local); the ghost
+ *      entries the products gather are fetched from their owners. */
 int ctl_build_rhs(ctl_handle h, const double *v_hat, const double *f_nodal, const double *v_0_host,
                   double *b);
 

@@ -68,6 +68,25 @@ def main():
         e_sol = max(rel(u0, loc(ref["v_blocks"])), rel(u1, loc(ref["zeta_blocks"])))
         assert info.reason > 0 and abs(info.its - ref["ksp"].its) <= 1, (info.its, ref["ksp"].its)
         assert e_sol < (1e-6 if CN else 1e-4), e_sol
+        # right-hand sides from nodal data and the objective on this rank's rows (ctl_build_rhs, ctl_objective)
+        n_t = q["n_t"]
+        f_nodal = rng.standard_normal((n_t, n))
+        v_hat = q["v_hat"] + 0.1 * rng.standard_normal(q["v_hat"].shape)
+        v_0 = rng.standard_normal(n)
+        v_0[q["bdofs"]] = 0.0
+        rows = slice(s.row_begin, s.row_begin + s.n_local)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a[:, rows])).to(s.device)
+        bd_ = s.build_rhs_device(dev(v_hat), dev(f_nodal), v_0)
+        d0, d1 = s.to_host_blocks(bd_)
+        r0, r1 = kkt.build_rhs(q["M"], q["K"], q["tau"], n_t, CN, q["bdofs"], (q["M"] @ v_hat.T).T, (q["M"] @ f_nodal.T).T, v_0)
+        e_rhs = max(np.abs(d0 - loc(r0)).max(), np.abs(d1 - loc(r1)).max()) / max(np.abs(r0).max(), np.abs(r1).max())
+        assert e_rhs < 1e-13, e_rhs
+        vv, zz = rng.standard_normal((n_t, n)), rng.standard_normal((n_t, n))
+        J_dev = s.objective_device(dev(vv), dev(zz), dev(v_hat))
+        J_ref = ocontrol.objective(q["M"], vv, zz, v_hat, q["tau"], q["beta"], CN)
+        assert abs(J_dev - J_ref) <= 1e-12 * abs(J_ref), (J_dev, J_ref)
+        if rank == 0:
+            print(f"CN={CN} world={world} nx={nx} rhs {e_rhs:.1e} J {abs(J_dev - J_ref) / abs(J_ref):.1e}", flush=True)
         if rank == 0:
             print(f"CN={CN} world={world} nx={nx} levels {s._lib.ctl_amg_num_levels(s._h, 0)}: apply {e_apply:.1e} pc {e_pc:.1e} solve its {info.its}/{ref['ksp'].its} "
                   f"diff {e_sol:.1e}", flush=True)
