@@ -112,6 +112,7 @@ SIGNATURES = {
     "ctl_stokes_pc_setup": (C.c_int, [_H, C.POINTER(ctl_stokes_pc_options)]),
     "ctl_stokes_pc_apply": (C.c_int, [_H, _F64P, _F64P]),
     "ctl_stokes_pc_fn": (C.c_int, [_H, _F64P, _F64P]),
+    "ctl_stokes_set_pc_callback": (C.c_int, [_H, PC_CALLBACK, C.c_void_p]),
     "ctl_stokes_solve": (C.c_int, [_H, _F64P, _F64P, C.POINTER(ctl_krylov_options),
                                    C.POINTER(ctl_solve_result)]),
     "ctl_stokes_time": (C.c_int, [_H, C.c_int, C.POINTER(C.c_double)]),

@@ -284,8 +284,6 @@ class Control:
                 self.set_space_p(space_p)
             if nullspace_p not in (None, "constant"):
                 raise ValueError("only the constant pressure nullspace is supported")
-            if P is not None:
-                raise NotImplementedError("user preconditioners are not wired for the Stokes system")
             n_t, n, tau, CN = self._n_t, self._n, self.tau, self._CN
             N = n_t - 1 if CN else n_t
             n_p = space_p["M_p"].shape[0]
@@ -330,11 +328,13 @@ class Control:
             elif not self._is_linear():
                 self._stokes.set_forward(K, D_p)
             system = self._stokes
-            system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
-                                        amg_p=amg_p, Multigrid=Multigrid)
+            if P is None:                                           # control.py:4686-4689: pc_fn = P or the in-built one
+                system.setup_preconditioner(lambda_v_bounds=lambda_v_bounds, lambda_p_bounds=lambda_p_bounds, amg=amg,
+                                            amg_p=amg_p, Multigrid=Multigrid)
             u_0 = np.zeros((2 * N, n))
             u_1 = np.zeros((2 * N, n_p))
-            self.last_ksp = system.solve(u_0, u_1, b_0, b_1, solver_parameters=solver_parameters, pc_fn="builtin")
+            self.last_ksp = system.solve(u_0, u_1, b_0, b_1, solver_parameters=solver_parameters,
+                                         pc_fn="builtin" if P is None else P)
             if solver_parameters.get("monitor_convergence", True):
                 for it, r_norm in enumerate(self.last_ksp.history):
                     print(f"KSP: iteration {it:d}, residual norm {r_norm:.16e}")

@@ -47,6 +47,8 @@ struct ctl_stokes_s {
     int colsum_blocks = 0;
     std::vector<double *> pool;   // outer-length scratch vectors
     KrylovState ks;
+    ctl_pc_callback pc_cb = nullptr;   // user preconditioner P= of incompressible_linear_solve (control/control.py:4686-4689)
+    void *pc_cb_user = nullptr;
     int64_t len() const { return hv->vec_len() + hp->vec_len(); }
 };
 
@@ -424,10 +426,32 @@ struct StokesSolver : Solver {
     void put_vec(double *p) override { S->pool.push_back(p); }
     int apply_operator(const double *x, double *y) override { return stokes_apply_tf(S, x, y); }
     int apply_builtin_pc(const double *x, double *y) override { return stokes_pc_tf(S, x, y, true); }
-    int apply_callback_pc(const double *, double *) override
+    // Preconditioner.apply around a user pc_fn (preconditioner/preconditioner.py:562-656): project the right-hand
+    // side, hand block-major device vectors of the outer system to the callback, restore the constrained entries
+    int apply_callback_pc(const double *x, double *y) override
     {
-        ctl_set_error(h, "ctl_stokes_solve: callback preconditioners are not supported");
-        return CTL_ERR_ARG;
+        CTL_CHECK(S->pc_cb, CTL_ERR_STATE, "ctl_stokes_solve: no preconditioner callback installed");
+        double *bm_b = nullptr, *bm_u = nullptr, *xc = nullptr;
+        CTL_TRY(outer_get(S, &bm_b));
+        CTL_TRY(outer_get(S, &bm_u));
+        CTL_TRY(outer_get(S, &xc));
+        int rc = vec_copy(h, xc, x, len);
+        if (rc == CTL_OK) rc = project(xc, nullptr);                  // pc_pre_mult_corrected
+        if (rc == CTL_OK) rc = outer_to_bm(S, xc, bm_b);
+        if (rc == CTL_OK) rc = vec_zero(h, bm_u, len);
+        if (rc == CTL_OK) {
+            cudaStreamSynchronize(h->stream);
+            if (S->pc_cb(S->pc_cb_user, bm_b, bm_u) != 0) {
+                ctl_set_error(h, "preconditioner callback failed");
+                rc = CTL_ERR_CALLBACK;
+            }
+        }
+        if (rc == CTL_OK) rc = outer_to_tf(S, bm_u, y);
+        if (rc == CTL_OK) rc = project(y, x);                         // pc_post_mult_correct
+        S->pool.push_back(bm_b);
+        S->pool.push_back(bm_u);
+        S->pool.push_back(xc);
+        return rc;
     }
     // velocity blocks: Dirichlet rows; pressure blocks: constants (full_nullspace_0 / _1, 3628-3652)
     int project(double *v, const double *wrap) override
@@ -664,6 +688,14 @@ int ctl_stokes_pc_fn(ctl_stokes S, const double *b, double *u)
     return with_tf(S, b, u, false, [&](const double *bt, double *ut) { return stokes_pc_tf(S, bt, ut, false); });
 }
 
+int ctl_stokes_set_pc_callback(ctl_stokes S, ctl_pc_callback fn, void *user)
+{
+    if (!S) return CTL_ERR_ARG;
+    S->pc_cb = fn;
+    S->pc_cb_user = user;
+    return CTL_OK;
+}
+
 int ctl_stokes_solve(ctl_stokes S, const double *b, double *u, const ctl_krylov_options *opts, ctl_solve_result *result)
 {
     if (!S) return CTL_ERR_ARG;
@@ -671,8 +703,8 @@ int ctl_stokes_solve(ctl_stokes S, const double *b, double *u, const ctl_krylov_
     CTL_CHECK(b && u && opts && result, CTL_ERR_ARG, "ctl_stokes_solve: null argument");
     CTL_CHECK(opts->ksp_type >= CTL_KSP_GMRES && opts->ksp_type <= CTL_KSP_MINRES, CTL_ERR_ARG,
               "ctl_stokes_solve: unknown ksp_type");
-    CTL_CHECK(opts->pc == CTL_PC_NONE || opts->pc == CTL_PC_BUILTIN, CTL_ERR_ARG,
-              "ctl_stokes_solve: pc must be CTL_PC_NONE or CTL_PC_BUILTIN");
+    CTL_CHECK(opts->pc >= CTL_PC_NONE && opts->pc <= CTL_PC_CALLBACK, CTL_ERR_ARG, "ctl_stokes_solve: unknown pc kind");
+    if (opts->pc == CTL_PC_CALLBACK) CTL_CHECK(S->pc_cb, CTL_ERR_STATE, "ctl_stokes_solve: call ctl_stokes_set_pc_callback first");
     if (opts->pc == CTL_PC_BUILTIN) CTL_CHECK(S->pc_ready, CTL_ERR_STATE, "ctl_stokes_solve: call ctl_stokes_pc_setup first");
     memset(result, 0, sizeof(*result));
     S->ks.next_event = 0;

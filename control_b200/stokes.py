@@ -161,7 +161,7 @@ class StokesSystem:
         if solver_parameters is None:                             # control/control.py:4291-4297
             solver_parameters = {"linear_solver": "fgmres", "maximum_iterations": 100,
                                  "relative_tolerance": 1.0e-6, "absolute_tolerance": 0.0}
-        kind = {"none": L.CTL_PC_NONE, "builtin": L.CTL_PC_BUILTIN}[pc]
+        kind = {"none": L.CTL_PC_NONE, "builtin": L.CTL_PC_BUILTIN, "callback": L.CTL_PC_CALLBACK}[pc]
         if kind == L.CTL_PC_BUILTIN and not self._pc_ready:
             raise L.CtlError("call setup_preconditioner() first")
         o = self.velocity._krylov_options(solver_parameters, kind)
@@ -169,12 +169,51 @@ class StokesSystem:
         self._call(self._lib.ctl_stokes_solve, b_dev.data_ptr(), u_dev.data_ptr(), C.byref(o), C.byref(res))
         return KSPInfo(res)
 
+    def _install_callback(self, pc_fn):
+        """``P=`` of ``incompressible_linear_solve``: ``pc_fn(u_0, u_1, b_0, b_1)`` on host block arrays of shape
+        (2N, n_v) and (2N, n_p); ``b_*`` projected and read-only, ``u_*`` zero, filled in place
+        (preconditioner/preconditioner.py:620-627)."""
+        from .system import _error_flag, _wrap_device_ptr
+        sys_ = self
+
+        def trampoline(_user, b_ptr, u_ptr):
+            try:
+                b = _wrap_device_ptr(b_ptr, sys_.vec_len(), sys_.device)
+                u = _wrap_device_ptr(u_ptr, sys_.vec_len(), sys_.device)
+                b0, b1 = sys_.to_host_blocks(b)
+                u0, u1 = np.zeros_like(b0), np.zeros_like(b1)
+                pc_fn(u0, u1, b0, b1)
+                u.copy_(sys_.to_device(u0, u1))
+                torch.cuda.current_stream(sys_.device).synchronize()
+                return 0
+            except Exception:                                     # flag_errors, preconditioner.py:64-72
+                _error_flag[0] = True
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = L.PC_CALLBACK(trampoline)
+        self._cb_keepalive = cb
+        self.velocity._check(self._lib.ctl_stokes_set_pc_callback(self._s, cb, None))
+
+    def builtin_pc_fn(self):
+        """The in-built pressure-Schur preconditioner as a ``P``-compatible callable on host block arrays."""
+        def pc_fn(u_0, u_1, b_0, b_1):
+            u = torch.empty(self.vec_len(), dtype=torch.float64, device=self.device)
+            self._call(self._lib.ctl_stokes_pc_fn, self.to_device(b_0, b_1).data_ptr(), u.data_ptr())
+            r0, r1 = self.to_host_blocks(u)
+            np.copyto(_as_host_f64(u_0).reshape(r0.shape), r0)
+            np.copyto(_as_host_f64(u_1).reshape(r1.shape), r1)
+        return pc_fn
+
     def solve(self, u_0, u_1, b_0, b_1, *, solver_parameters=None, pc_fn="builtin"):
         """``MultiBlockSystem.solve`` of the outer system on host block arrays: ``u_0`` (2N, n_v)
         and ``u_1`` (2N, n_p) carry the initial guess in and the solution out."""
         pc = "none" if pc_fn is None else pc_fn
-        if pc not in ("none", "builtin"):
-            raise ValueError("the Stokes system takes pc_fn=None or 'builtin'")
+        if callable(pc_fn):                     # a user P(u_0, u_1, b_0, b_1): control/control.py:4686-4689
+            self._install_callback(pc_fn)
+            pc = "callback"
+        elif pc not in ("none", "builtin"):
+            raise ValueError("the Stokes system takes pc_fn=None, 'builtin' or a callable P(u_0, u_1, b_0, b_1)")
         b = self.to_device(b_0, b_1)
         u = self.to_device(u_0, u_1)
         info = self.solve_device(b, u, solver_parameters=solver_parameters, pc=pc)

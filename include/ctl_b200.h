@@ -266,6 +266,12 @@ int ctl_stokes_pc_setup(ctl_stokes s, const ctl_stokes_pc_options *opts);
 /* Preconditioner.apply around pc_fn (with the nullspace wrapping) / the raw pc_fn */
 int ctl_stokes_pc_apply(ctl_stokes s, const double *b, double *u);
 int ctl_stokes_pc_fn(ctl_stokes s, const double *b, double *u);
+/* user preconditioner of the outer Stokes system: the `P=` argument of incompressible_linear_solve
+ * (control/control.py:3592-3594, 4686-4689).  fn(user, b, u) receives DEVICE vectors of ctl_stokes_vec_len doubles
+ * in the outer block-major layout, b projected (Dirichlet rows of the velocity blocks zero, pressure blocks mean
+ * free), u zero, and fills u; a non-zero return aborts the solve (flag_errors, preconditioner.py:64-72).  Selected
+ * with opts->pc = CTL_PC_CALLBACK. */
+int ctl_stokes_set_pc_callback(ctl_stokes s, ctl_pc_callback fn, void *user);
 /* MultiBlockSystem.solve of the outer system (control/control.py:4273-4297, 4688-4693);
  * opts->pc: CTL_PC_NONE or CTL_PC_BUILTIN */
 int ctl_stokes_solve(ctl_stokes s, const double *b, double *u, const ctl_krylov_options *opts,

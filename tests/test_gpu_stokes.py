@@ -131,6 +131,50 @@ def test_stokes_solve_matches_oracle(CN):
     s.close()
 
 
+def test_stokes_user_preconditioner_hook():
+    """``P=`` of ``incompressible_linear_solve`` (control/control.py:3592-3594, 4686-4689): a user callable
+    ``pc_fn(u_0, u_1, b_0, b_1)`` on the blocks of the outer system, called through ctl_stokes_set_pc_callback.  Handing
+    the in-built preconditioner back in as the user's P must reproduce the in-built solve (same count, same solution);
+    the callable sees projected right-hand sides (Dirichlet rows zero, pressure blocks mean free) and zero u's; an
+    exception inside it surfaces as the reference's RuntimeError."""
+    q = _problem(6, 5, True)
+    th, N = q["th"], q["N"]
+    s = _system(q)
+    s.setup_preconditioner(lambda_v_bounds=LAMBDA_V, lambda_p_bounds=LAMBDA_P, amg=AMG, amg_p=AMG_P)
+    rng = np.random.default_rng(7)
+    xr0 = rng.standard_normal((2 * N, s.n_v))
+    xr0[:, th["bdofs_v"]] = 0.0
+    xr1 = rng.standard_normal((2 * N, s.n_p))
+    xr1 -= xr1.mean(axis=1, keepdims=True)
+    b0, b1 = stokes.stokes_apply_fused(th["M_v"], th["K_v"], th["B"], q["tau"], q["beta"], q["n_t"], True, th["bdofs_v"],
+                                       xr0, xr1)
+    sp_ = {"linear_solver": "fgmres", "maximum_iterations": 300, "relative_tolerance": 1e-8, "absolute_tolerance": 0.0,
+           "gmres_restart": 100}
+    u0, u1 = np.zeros_like(xr0), np.zeros_like(xr1)
+    ref = s.solve(u0, u1, b0, b1, solver_parameters=sp_)
+    inner = s.builtin_pc_fn()
+    seen = []
+
+    def P(w_0, w_1, c_0, c_1):
+        assert not w_0.any() and not w_1.any()
+        assert not c_0[:, th["bdofs_v"]].any() and np.abs(c_1.mean(axis=1)).max() <= 1e-12 * max(np.abs(c_1).max(), 1e-300)
+        seen.append(1)
+        inner(w_0, w_1, c_0, c_1)
+    w0, w1 = np.zeros_like(xr0), np.zeros_like(xr1)
+    info = s.solve(w0, w1, b0, b1, solver_parameters=sp_, pc_fn=P)
+    assert info.reason > 0 and len(seen) == info.n_pc >= info.its
+    assert abs(info.its - ref.its) <= 1
+    assert _rel(w0, u0) < 1e-6 and _rel(w1, u1) < 1e-4
+
+    def broken(w_0, w_1, c_0, c_1):
+        raise ValueError("user preconditioner failed")
+    with pytest.raises(Exception):
+        s.solve(np.zeros_like(xr0), np.zeros_like(xr1), b0, b1, solver_parameters=sp_, pc_fn=broken)
+    from control_b200 import system as sysm
+    sysm._error_flag[0] = False
+    s.close()
+
+
 def test_stokes_rejects_mismatched_handles():
     from control_b200 import CtlError, MultiBlockSystem
     from control_b200 import _lib as L
