@@ -22,15 +22,16 @@ def rel(a, b):
     return np.abs(a - b).max() / np.abs(b).max()
 
 
-@pytest.mark.parametrize("CN,mode", [(True, "triangular"), (True, "diagonal"), (False, "triangular")])
-def test_c_port_matches_numpy_oracle(CN, mode):
+@pytest.mark.parametrize("CN,mode,cycles", [(True, "triangular", {}), (True, "diagonal", {}), (False, "triangular", {}),
+                                            (True, "diagonal", dict(cycles=2, nu=4))])      # last: bench.py's C2 arm
+def test_c_port_matches_numpy_oracle(CN, mode, cycles):
     try:
         fastpc.lib()
     except ImportError:
         pytest.skip("oracle/_build/liboracle.so not built")
     fastpc.set_threads(4)
     q = kat.heat_problem(30, 7, CN, beta=1e-3)
-    amg = dict(coarse_max=40)
+    amg = dict(coarse_max=40, **cycles)
     M, K, bd = q["M"], q["K"], q["bdofs"]
     f = fastpc.FastPc(M, K, q["tau"], q["beta"], q["n_t"], CN, bd, lambda_v_bounds=q["lambda_v_bounds"], mode=mode,
                       amg_params=amg)
