@@ -131,7 +131,6 @@ int ctl_pc_invalidate(ctl_handle_s *h);   // pc.cu: matrices changed, rebuild on
 // comm.cu
 int ctl_halo_exchange(ctl_handle_s *h, const double *x_tf);            // both panels -> d_halo
 int ctl_halo_exchange_panel(ctl_handle_s *h, const double *panel_tf);  // one panel -> d_halo[0]
-int ctl_halo_exchange_vec(ctl_handle_s *h, double *x);                 // n_loc owned + n_halo ghost entries, in place
 int ctl_allreduce_sum(ctl_handle_s *h, double *dev, int count);
 int ctl_comm_check(ctl_handle_s *h);                                   // peer-to-peer exchange timed out?
 
