@@ -300,6 +300,35 @@ int main()
                     }
                     printf("\n");
                 }
+                {
+                    // the coarsest-level inverse left to the device (AmgParams::device_inverse): the level must still
+                    // be replicated, carry the request instead of values, and the inverse of its LOCAL block -- what
+                    // dense_inverse.cu computes on every rank -- must be the host inverse in local numbering
+                    AmgParams pd = p;
+                    pd.device_inverse = 1;
+                    std::vector<AmgLevelHost> Hd;
+                    amg_setup_host(A, pd, Hd, 1);
+                    CHECK(Hd.back().Ainv.empty() && Hd.back().coarse_inverse == AMG_COARSE_INVERSE + 1 && Hd.back().has_inverse(),
+                          "deferred inverse not requested");
+                    for (int me = 0; me < world; ++me) {
+                        auto mesh = std::make_shared<HaloGeom>();
+                        halo_geometry(world, me, part0, {halo_consumer(A, part0)}, false, *mesh);
+                        DistHierarchy Dd;
+                        amg_distribute_host(world, me, Hd, rep_min, mesh, Dd);
+                        const DistLevel &Ll = Dd.levels[nl - 1], &Lr = D[me].levels[nl - 1];
+                        CHECK(Dd.L_rep == D[me].L_rep && !Ll.distributed && Ll.Ainv.empty() && Ll.coarse_inverse == AMG_COARSE_INVERSE + 1,
+                              "deferred inverse lost on the way (world %d rank %d)", world, me);
+                        CHECK(Ll.A.n_rows == Ll.n && Ll.A.n_cols == Ll.n, "level with the dense inverse is not square / replicated");
+                        std::vector<double> inv;
+                        dense_inverse(Ll.A, {}, inv);
+                        double d = 0.0, m = 0.0;
+                        for (size_t q = 0; q < inv.size(); ++q) {
+                            d = std::max(d, std::fabs(inv[q] - Lr.Ainv[q]));
+                            m = std::max(m, std::fabs(Lr.Ainv[q]));
+                        }
+                        CHECK(inv.size() == Lr.Ainv.size() && d <= 1e-11 * m, "inverse of the local block differs from the permuted inverse (%.2e)", d / m);
+                    }
+                }
                 Emu E{world, H, p, D};
                 for (int me = 0; me < world; ++me) {
                     const std::shared_ptr<HaloGeom> mesh = D[me].levels[0].space;
