@@ -535,7 +535,9 @@ int ctl_pc_setup(ctl_handle h, const ctl_pc_options *opts)
         st.hier.assign(nh, AmgHierarchyDev());
         std::vector<std::string> errors(nh);
         std::vector<std::vector<double>> off_values(n_off);
-        int n_threads = (int)std::thread::hardware_concurrency();
+        // one process per GPU on one host: every rank sets the same hierarchies up, so each takes its share of the
+        // cores (8 ranks x all 16 cores oversubscribed the box: 10-13 s of set-up at 8 GPUs against 2 s at one)
+        int n_threads = std::max(1, (int)std::thread::hardware_concurrency() / std::max(1, h->cfg.world));
         if (const char *e = getenv("CTL_SETUP_THREADS")) n_threads = atoi(e);
         const int hw_threads = std::max(1, std::min(n_threads, 32));
         n_threads = std::max(1, std::min(std::min(n_threads, nh + n_off), 32));
